@@ -1,0 +1,193 @@
+"""ctypes front-end of the CPU oracle (oracle/svox_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs. The product package (svox_t_b200) must never import this module.
+
+All entry points take/return numpy arrays. ``dtype`` selects the arithmetic: ``np.float32`` restates the
+reference's fp32 CUDA instantiation, ``np.float64`` is the all-double mathematical truth.
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+_SO = os.path.join(_BUILD, "libsvox_oracle.so")
+_SRC = [os.path.join(_HERE, "svox_oracle.c"), os.path.join(_HERE, "svox_oracle_impl.inc")]
+_lock = threading.Lock()
+_lib = None
+
+SENTINEL = 1410065408  # int(1e10) wrapped to int32 (svox_t/svox.py:124)
+
+
+def _cpu_has_fma():
+    try:
+        with open("/proc/cpuinfo") as f:
+            return " fma " in f.read().replace("\n", " ")
+    except OSError:
+        return False
+
+
+def build(force=False):
+    """Compile the C restatement with gcc (about one second). Idempotent."""
+    os.makedirs(_BUILD, exist_ok=True)
+    flag_file = os.path.join(_BUILD, "flags.txt")
+    flags = ["-O2", "-fopenmp", "-ffp-contract=off"] + (["-mfma"] if _cpu_has_fma() else [])
+    want = " ".join(flags)
+    stale = force or not os.path.exists(_SO) or not os.path.exists(flag_file)
+    if not stale:
+        stale = open(flag_file).read().strip() != want or any(
+            os.path.getmtime(s) > os.path.getmtime(_SO) for s in _SRC)
+    if stale:
+        tmp = _SO + ".tmp.%d" % os.getpid()
+        subprocess.check_call(["gcc", *flags, "-shared", "-fPIC", _SRC[0], "-o", tmp, "-lm"])
+        os.replace(tmp, _SO)
+        with open(flag_file, "w") as f:
+            f.write(want)
+    return _SO
+
+
+def lib():
+    global _lib
+    with _lock:
+        if _lib is None:
+            _lib = ctypes.CDLL(build())
+            _lib.orc_leafset.restype = ctypes.c_int64
+    return _lib
+
+
+def _sfx(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return "_f32", ctypes.c_float
+    if dtype == np.float64:
+        return "_f64", ctypes.c_double
+    raise TypeError(dtype)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Tree:
+    """Plain container of the reference tensor format (svox_t/svox.py:121-139) as numpy arrays."""
+
+    def __init__(self, child, data, offset=(0.0, 0.0, 0.0), scaling=(1.0, 1.0, 1.0)):
+        self.child = _c(child, np.int32)
+        self.data = _c(data, np.int32).reshape(self.child.shape)
+        self.N = int(self.child.shape[1])
+        self.offset = np.asarray(offset, dtype=np.float64)
+        self.scaling = np.asarray(scaling, dtype=np.float64)
+
+    def args(self, features, dtype):
+        f = _c(features, dtype)
+        M, D = f.shape
+        off, sc = _c(self.offset, dtype), _c(self.scaling, dtype)
+        keep = (f, off, sc)
+        return keep, (_p(self.child), _p(self.data), ctypes.c_int(self.N), _p(f), ctypes.c_int64(M),
+                      ctypes.c_int(D), _p(off), _p(sc))
+
+
+def query(tree, features, pts, dtype=np.float32):
+    """-> values[Q,D], node_ids[Q] i64, data_ids[Q] i64, valid[Q] bool (rows of empty leaves are zero)."""
+    sfx, _ = _sfx(dtype)
+    keep, targs = tree.args(features, dtype)
+    pts = _c(pts, dtype)
+    Q, D = pts.shape[0], keep[0].shape[1]
+    values = np.zeros((Q, D), dtype=dtype)
+    node_ids = np.zeros(Q, dtype=np.int64)
+    data_ids = np.zeros(Q, dtype=np.int64)
+    valid = np.zeros(Q, dtype=np.uint8)
+    getattr(lib(), "orc_query" + sfx)(*targs, _p(pts), ctypes.c_int64(Q), _p(values), _p(node_ids),
+                                       _p(data_ids), _p(valid))
+    return values, node_ids, data_ids, valid.astype(bool)
+
+
+def leafset(node_ids, N):
+    node_ids = _c(node_ids, np.int64)
+    out = np.zeros((max(len(node_ids), 1), 4), dtype=np.int64)
+    n = lib().orc_leafset(_p(node_ids), ctypes.c_int64(len(node_ids)), ctypes.c_int(N), _p(out))
+    return out[:n].copy()
+
+
+def construct_tree(tree, pts, dtype=np.float32):
+    """In place: tree.data[leaf(p_i)] = i (highest i wins on a shared leaf)."""
+    sfx, _ = _sfx(dtype)
+    pts = _c(pts, dtype)
+    off, sc = _c(tree.offset, dtype), _c(tree.scaling, dtype)
+    getattr(lib(), "orc_construct_tree" + sfx)(_p(tree.child), _p(tree.data), ctypes.c_int(tree.N),
+                                                _p(off), _p(sc), _p(pts), ctypes.c_int64(len(pts)))
+
+
+def render_rays(tree, features, origins, dirs, step_size=1e-3, background_brightness=1.0,
+                sigma_thresh=0.0, stop_thresh=0.0, dtype=np.float32, want_depth=True, want_counters=False):
+    """-> out[Q,D] (D-1 composited sigmoid features + opacity), depth[Q], [counters dict S, LV, V, H]."""
+    sfx, cr = _sfx(dtype)
+    keep, targs = tree.args(features, dtype)
+    o, d = _c(origins, dtype), _c(dirs, dtype)
+    Q, D = o.shape[0], keep[0].shape[1]
+    out = np.zeros((Q, D), dtype=dtype)
+    depth = np.zeros(Q, dtype=dtype) if want_depth else None
+    cnt = np.zeros(4, dtype=np.int64)
+    getattr(lib(), "orc_render_rays" + sfx)(*targs, _p(o), _p(d), ctypes.c_int64(Q), cr(step_size),
+                                             cr(background_brightness), cr(sigma_thresh), cr(stop_thresh),
+                                             _p(out), _p(depth), _p(cnt))
+    ret = [out, depth]
+    if want_counters:
+        ret.append(dict(S=int(cnt[0]), LV=int(cnt[1]), V=int(cnt[2]), H=int(cnt[3]), Q=int(Q)))
+    return tuple(ret)
+
+
+def render_rays_backward(tree, features, origins, dirs, grad_out, step_size=1e-3,
+                         background_brightness=1.0, dtype=np.float32):
+    """-> grad[M,D] following the reference's two-pass backward (hit predicate sigma > 0, no early stop)."""
+    sfx, cr = _sfx(dtype)
+    keep, targs = tree.args(features, dtype)
+    o, d, g = _c(origins, dtype), _c(dirs, dtype), _c(grad_out, dtype)
+    grad = np.zeros_like(keep[0])
+    getattr(lib(), "orc_render_rays_backward" + sfx)(*targs, _p(o), _p(d), ctypes.c_int64(o.shape[0]),
+                                                      cr(step_size), cr(background_brightness), _p(g), _p(grad))
+    return grad
+
+
+def camera_rays(c2w, fx, fy, width, height, dtype=np.float32):
+    """-> origins[H*W,3], dirs[H*W,3] in row-major pixel order (iy*W + ix), world space."""
+    sfx, cr = _sfx(dtype)
+    c = np.zeros((3, 4), dtype=dtype)
+    c[:] = np.asarray(c2w, dtype=dtype)[:3, :4]
+    n = width * height
+    o = np.zeros((n, 3), dtype=dtype)
+    d = np.zeros((n, 3), dtype=dtype)
+    getattr(lib(), "orc_camera_rays" + sfx)(_p(c), cr(fx), cr(fy), ctypes.c_int(width), ctypes.c_int(height),
+                                             _p(o), _p(d))
+    return o, d
+
+
+def warp_vertices(T, coords, weights, joint_index, dtype=np.float32):
+    sfx, _ = _sfx(dtype)
+    T, coords, weights = _c(T, dtype), _c(coords, dtype), _c(weights, dtype)
+    ji = _c(joint_index, np.int32)
+    P, B = weights.shape
+    co = np.zeros((P, 3), dtype=dtype)
+    mo = np.zeros((P, 4, 4), dtype=dtype)
+    getattr(lib(), "orc_warp_vertices" + sfx)(_p(T), _p(coords), _p(weights), _p(ji), ctypes.c_int64(P),
+                                               ctypes.c_int(B), _p(co), _p(mo))
+    return co, mo
+
+
+def p2v(points, feat, corner, size, n_voxels, kernel_radius, conv_radius, dtype=np.float32):
+    sfx, cr = _sfx(dtype)
+    points, feat = _c(points, dtype), _c(feat, dtype)
+    corner, size = _c(corner, dtype), _c(size, dtype)
+    vox = np.zeros((n_voxels, n_voxels, n_voxels, 1), dtype=dtype)
+    getattr(lib(), "orc_p2v" + sfx)(_p(points), _p(feat), ctypes.c_int64(points.shape[0]),
+                                     ctypes.c_int(feat.shape[1]), _p(corner), _p(size), ctypes.c_int(n_voxels),
+                                     cr(kernel_radius), cr(conv_radius), _p(vox))
+    return vox
