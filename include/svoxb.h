@@ -1,0 +1,180 @@
+/*
+ * svoxb.h -- C ABI of libsvoxb: the B200-native (sm_100a) replacement for the octree volume-rendering
+ * hot path of HaiminLuo/svox_t.
+ *
+ * This header is the drop-in boundary. Every entry point below replaces one function that the reference
+ * exposes through its pybind11 module `svox_t.csrc` (reference: svox_t/csrc/svox.cpp:119-144); the
+ * reference file:line is cited per function. Conventions:
+ *   - plain C: raw DEVICE pointers + sizes, no C++/torch types; all tensors contiguous, row-major;
+ *   - outputs are caller-allocated (the reference allocates them inside C++ with torch::zeros/empty);
+ *   - every call takes the CUDA stream to launch on (the reference always uses the legacy default stream);
+ *   - every call returns 0 on success or a negative SVOXB_E* code; svoxb_last_error() gives the message
+ *     (the reference raises TORCH_CHECK exceptions and only printf()s CUDA launch errors,
+ *     include/common.cuh:108-111);
+ *   - no host<->device synchronisation inside any call unless stated.
+ * The library never falls back to a CPU path: without a CUDA device every compute call fails with
+ * SVOXB_ECUDA.
+ */
+#ifndef SVOXB_H_
+#define SVOXB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVOXB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SVOXB_API __attribute__((visibility("default")))
+#else
+#define SVOXB_API
+#endif
+
+enum {
+    SVOXB_OK = 0,
+    SVOXB_EINVAL = -1,      /* bad argument (null pointer, unsupported N / D / format ...) */
+    SVOXB_ECUDA = -2,       /* CUDA runtime / launch error */
+    SVOXB_EUNSUPPORTED = -3 /* feature of the reference deliberately not implemented (SH/SG/ASG, NDC) */
+};
+
+/* DataFormat enum of the reference (include/data_spec.hpp:45-50). Only RGBA (feature-level) is implemented. */
+enum { SVOXB_FORMAT_RGBA = 0, SVOXB_FORMAT_SH = 1, SVOXB_FORMAT_SG = 2, SVOXB_FORMAT_ASG = 3 };
+
+/* Opaque acceleration structure built from (child, data) by svoxb_accel_create(): a dense top grid plus
+ * dense bricks holding one tagged 32-bit word per cell (leaf depth | feature-row index). */
+typedef struct svoxb_accel svoxb_accel;
+
+/* Replaces TreeSpec / PackedTreeSpec (include/data_spec.hpp:67-111, include/data_spec_packed.cuh:57-100).
+ * Fields the feature-level path never reads (extra_data, _weight_accum, joint_*, transformation_matrices --
+ * a no-op for FORMAT_RGBA, rt_kernel.cu:181-183,283-291) are omitted. */
+typedef struct svoxb_tree {
+    const float* features;      /* [M, D] float32; last channel = sigma                               */
+    int64_t M;                  /* features.size(0); a data index >= M marks an empty leaf            */
+    int32_t D;                  /* features.size(1)                                                   */
+    int32_t N;                  /* branching factor per axis (child.size(1)); N == 2 is the fast path */
+    const int32_t* child;       /* [n_nodes, N, N, N]  relative child offset, 0 = leaf                */
+    const int32_t* data;        /* [n_nodes, N, N, N, 1] feature-row index per leaf slot              */
+    const int32_t* parent_depth;/* [n_nodes, 2] (packed parent slot, depth); may be NULL              */
+    int64_t n_nodes;            /* rows allocated in child/data (capacity)                            */
+    int64_t n_internal;         /* rows in use (TreeSpec.n_internal = tree.filled)                    */
+    const float* offset;        /* [3] device; world -> tree: q = offset + scaling * q                */
+    const float* scaling;       /* [3] device (the reference's invradius)                             */
+    const svoxb_accel* accel;   /* optional; NULL = walk child/data exactly like the reference        */
+} svoxb_tree;
+
+/* Field-for-field the reference's RenderOptions (include/data_spec.hpp:129-145). */
+typedef struct svoxb_render_options {
+    float step_size;
+    float background_brightness;
+    int32_t format;
+    int32_t basis_dim;
+    int32_t ndc_width;          /* < 0 disables NDC (renderer.py:426); >= 0 is SVOXB_EUNSUPPORTED     */
+    int32_t ndc_height;
+    float ndc_focal;
+    int32_t min_comp;
+    int32_t max_comp;
+    float sigma_thresh;
+    float stop_thresh;
+} svoxb_render_options;
+
+/* Replaces CameraSpec (include/data_spec.hpp:113-126). */
+typedef struct svoxb_camera {
+    const float* c2w;           /* device, row-major [3 or 4, 4] camera-to-world, OpenGL convention   */
+    float fx, fy;
+    int32_t width, height;
+} svoxb_camera;
+
+/* ---- housekeeping ------------------------------------------------------------------------------ */
+SVOXB_API int svoxb_abi_version(void);
+SVOXB_API const char* svoxb_last_error(void);          /* thread-local message of the last failing call         */
+SVOXB_API int64_t svoxb_launch_count(void);            /* number of kernels this library has launched so far    */
+SVOXB_API int svoxb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- acceleration structure (no reference counterpart; derived data, rebuilt when child/data change) */
+/* max_depth <= 0: derive it from parent_depth (must then be non-NULL). Synchronises the stream. */
+SVOXB_API int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* stream, svoxb_accel** out);
+SVOXB_API void svoxb_accel_destroy(svoxb_accel* accel);
+SVOXB_API int64_t svoxb_accel_bytes(const svoxb_accel* accel);
+SVOXB_API int svoxb_accel_describe(const svoxb_accel* accel, int* n_stages, int* bits /*[4]*/, int64_t* bricks /*[4]*/);
+
+/* ---- octree descent ---------------------------------------------------------------------------- */
+/* query_vertical, first kernel (svox_kernel.cu:66-81, 274-302): per point p (world coords) the leaf's packed
+ * slot id node*N^3 + u*N^2 + v*N + w -> node_ids[q]; if the leaf holds a row (data idx < M): data_ids[q] = idx
+ * and values[q,:] = features[idx,:]; rows of empty leaves are left untouched, as in the reference.
+ * values / data_ids / slot_mask may be NULL. slot_mask[n_internal*N^3] (uint8, zeroed by the caller) gets 1 at
+ * every visited leaf slot (empty leaves included, svox_kernel.cu:57-58). */
+SVOXB_API int svoxb_query(const svoxb_tree* tree, const float* pts, int64_t Q,
+                float* values, int64_t* node_ids, int64_t* data_ids, uint8_t* slot_mask, void* stream);
+
+/* query_vertical, kernels 2+3 (svox_kernel.cu:239-269, 304-320) as a deterministic two-step compaction:
+ * _scan counts the set slots (exclusive block offsets into scratch, total into *n_hit_dev); the caller reads
+ * n_hit (the one device->host sync the reference also has, svox_kernel.cu:312), allocates leaf_node[n_hit,4]
+ * and calls _emit, which writes [node, i, j, k] rows in increasing slot order. */
+SVOXB_API size_t svoxb_leafset_scratch_bytes(int64_t n_slots);
+SVOXB_API int svoxb_leafset_scan(const uint8_t* slot_mask, int64_t n_slots, void* scratch, int64_t* n_hit_dev, void* stream);
+SVOXB_API int svoxb_leafset_emit(const uint8_t* slot_mask, int64_t n_slots, int32_t N, const void* scratch,
+                       int64_t* leaf_node, void* stream);
+
+/* construct_tree (svox_kernel.cu:110-121, 341-352): data[leaf(p_i)] = i. data_mut aliases tree->data. */
+SVOXB_API int svoxb_construct_tree(const svoxb_tree* tree, int32_t* data_mut, const float* pts, int64_t P, void* stream);
+
+/* ---- ray march --------------------------------------------------------------------------------- */
+/* volume_render (rt_kernel.cu:654-671, 1362-1379) fused with render_depth (rt_kernel.cu:865-882, 1506-1523):
+ * out[Q, D] = D-1 composited sigmoid features + opacity (1 - T); depth[Q] (nullable) = first-hit depth.
+ * vdirs is accepted for signature parity and ignored (no effect for FORMAT_RGBA). */
+SVOXB_API int svoxb_render_rays_fwd(const svoxb_tree* tree, const float* origins, const float* dirs, const float* vdirs,
+                          int64_t Q, const svoxb_render_options* opt, float* out, float* depth, void* stream);
+
+/* volume_render_backward (rt_kernel.cu:674-694, 1402-1426): grad_features[M, D] += dL/dfeatures.
+ * One re-march instead of the reference's two: saved_out[Q, D] is the forward output computed with
+ * sigma_thresh = 0 and stop_thresh < 0 (the backward's own hit predicate, rt_kernel.cu:382,456); with the
+ * default options that is exactly what svoxb_render_rays_fwd returned. The caller zero-fills
+ * grad_features (the reference allocates zeros_like(features), rt_kernel.cu:1415). */
+SVOXB_API int svoxb_render_rays_bwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                          const svoxb_render_options* opt, const float* grad_out, const float* saved_out,
+                          float* grad_features, void* stream);
+
+/* volume_render_image / _backward (rt_kernel.cu:1152-1166, 1193-1238, 1381-1452): pinhole camera rays generated
+ * in-kernel; out[H, W, D], depth[H, W] (nullable). */
+SVOXB_API int svoxb_render_image_fwd(const svoxb_tree* tree, const svoxb_camera* cam, const svoxb_render_options* opt,
+                           float* out, float* depth, void* stream);
+SVOXB_API int svoxb_render_image_bwd(const svoxb_tree* tree, const svoxb_camera* cam, const svoxb_render_options* opt,
+                           const float* grad_out, const float* saved_out, float* grad_features, void* stream);
+
+/* render_depth alone (rt_kernel.cu:781-834, 865-882, 1506-1523): depth[Q] = delta_scale * t of the first
+ * sample with sigma > sigma_thresh, 0 on miss. */
+SVOXB_API int svoxb_render_depth(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                       const svoxb_render_options* opt, float* depth, void* stream);
+
+/* ---- animated-frame rebuild -------------------------------------------------------------------- */
+/* warp_vertices (svox_kernel.cu:123-154, 354-378): linear blend skinning. T[J,4,4], coords[P,3], w[P,B],
+ * joint_index[P,B] -> coords_out[P,3], mats_out[P,4,4] (fully written, no zero-fill needed). */
+SVOXB_API int svoxb_warp_vertices(const float* T, const float* coords, const float* w, const int32_t* joint_index,
+                        int64_t P, int32_t B, float* coords_out, float* mats_out, void* stream);
+
+/* p2v (p2v_kernel.cu:103-151, 240-261): Gaussian splat of point_features[:, F-1] into voxels[n,n,n,1]
+ * (zero-filled by this call). corner[3], size[3] are device pointers like in the reference. */
+SVOXB_API int svoxb_p2v(const float* points, const float* point_features, int64_t P, int32_t F,
+              const float* corner, const float* size, int32_t n_voxels, float kernel_radius, float conv_radius,
+              float* voxels, void* stream);
+
+/* One-shot octree build from points (replaces the reference's depth-1 rounds of
+ * query_vertical + N3Tree.refine, svox_t/svox.py:488-560 + helpers.py:38-109, and the final construct_tree):
+ * emits child/data/parent_depth in the reference tensor format for the octree whose depth-L leaves are the
+ * occupied finest cells; nodes are numbered breadth-first, by Morton key within a level (deterministic).
+ * data[leaf(p_i)] = the largest i among the points in that leaf. Two calls:
+ *   _count: sorts the point keys and returns the node count in *n_nodes_host (synchronises the stream);
+ *   _emit : fills the caller-allocated tensors (n_nodes rows). `work` comes from svoxb_build_work_bytes(P, L). */
+SVOXB_API size_t svoxb_build_work_bytes(int64_t P, int32_t L);
+SVOXB_API int svoxb_build_octree_count(const float* pts, int64_t P, int32_t L, const float* offset, const float* scaling,
+                             void* work, int64_t* n_nodes_host, void* stream);
+SVOXB_API int svoxb_build_octree_emit(int64_t P, int32_t L, const void* work, int64_t n_nodes,
+                            int32_t* child, int32_t* data, int32_t* parent_depth, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVOXB_H_ */

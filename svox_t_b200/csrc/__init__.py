@@ -1,0 +1,474 @@
+"""``svox_t_b200.csrc`` -- host-side mirror of the reference's pybind11 module ``svox_t.csrc``
+(reference: svox_t/csrc/svox.cpp:73-145) on top of the C-ABI library ``libsvoxb.so`` (include/svoxb.h).
+
+Same names, argument meaning and error behaviour as the reference: ``TreeSpec`` / ``RaysSpec`` / ``CameraSpec`` /
+``RenderOptions`` are mutable records with the reference's field names; every function takes CUDA, contiguous
+torch tensors, allocates its outputs on the inputs' device (as the reference does with ``torch::zeros/empty``)
+and raises ``RuntimeError`` on a failed check. Differences, all deliberate:
+
+* kernels launch on torch's *current* stream (the reference uses the legacy default stream);
+* only float32 and the feature-level ``FORMAT_RGBA`` are implemented; anything else raises;
+* there is NO CPU fallback: a missing ``libsvoxb.so`` or a non-CUDA tensor is an error, never a slow path.
+
+PyTorch is plumbing here (device memory, streams); all compute happens in hand-written sm_100a kernels.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO_PATH = os.path.join(_HERE, "libsvoxb.so")
+
+FORMAT_RGBA, FORMAT_SH, FORMAT_SG, FORMAT_ASG = 0, 1, 2, 3
+
+
+class _CTree(ctypes.Structure):
+    _fields_ = [
+        ("features", ctypes.c_void_p), ("M", ctypes.c_int64), ("D", ctypes.c_int32), ("N", ctypes.c_int32),
+        ("child", ctypes.c_void_p), ("data", ctypes.c_void_p), ("parent_depth", ctypes.c_void_p),
+        ("n_nodes", ctypes.c_int64), ("n_internal", ctypes.c_int64),
+        ("offset", ctypes.c_void_p), ("scaling", ctypes.c_void_p), ("accel", ctypes.c_void_p),
+    ]
+
+
+class _COptions(ctypes.Structure):
+    _fields_ = [
+        ("step_size", ctypes.c_float), ("background_brightness", ctypes.c_float),
+        ("format", ctypes.c_int32), ("basis_dim", ctypes.c_int32),
+        ("ndc_width", ctypes.c_int32), ("ndc_height", ctypes.c_int32), ("ndc_focal", ctypes.c_float),
+        ("min_comp", ctypes.c_int32), ("max_comp", ctypes.c_int32),
+        ("sigma_thresh", ctypes.c_float), ("stop_thresh", ctypes.c_float),
+    ]
+
+
+class _CCamera(ctypes.Structure):
+    _fields_ = [("c2w", ctypes.c_void_p), ("fx", ctypes.c_float), ("fy", ctypes.c_float),
+                ("width", ctypes.c_int32), ("height", ctypes.c_int32)]
+
+
+# Every symbol include/svoxb.h declares: (restype, argtypes). tests/test_cabi.py checks the list against the header.
+_VP, _I64, _I32, _F = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float
+_PT, _PO, _PC = ctypes.POINTER(_CTree), ctypes.POINTER(_COptions), ctypes.POINTER(_CCamera)
+SYMBOLS = {
+    "svoxb_abi_version": (ctypes.c_int, []),
+    "svoxb_last_error": (ctypes.c_char_p, []),
+    "svoxb_launch_count": (_I64, []),
+    "svoxb_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3),
+    "svoxb_accel_create": (ctypes.c_int, [_PT, ctypes.c_int, _VP, ctypes.POINTER(_VP)]),
+    "svoxb_accel_destroy": (None, [_VP]),
+    "svoxb_accel_bytes": (_I64, [_VP]),
+    "svoxb_accel_describe": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                            ctypes.POINTER(_I64)]),
+    "svoxb_query": (ctypes.c_int, [_PT, _VP, _I64, _VP, _VP, _VP, _VP, _VP]),
+    "svoxb_leafset_scratch_bytes": (ctypes.c_size_t, [_I64]),
+    "svoxb_leafset_scan": (ctypes.c_int, [_VP, _I64, _VP, _VP, _VP]),
+    "svoxb_leafset_emit": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP, _VP]),
+    "svoxb_construct_tree": (ctypes.c_int, [_PT, _VP, _VP, _I64, _VP]),
+    "svoxb_render_rays_fwd": (ctypes.c_int, [_PT, _VP, _VP, _VP, _I64, _PO, _VP, _VP, _VP]),
+    "svoxb_render_rays_bwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _VP]),
+    "svoxb_render_image_fwd": (ctypes.c_int, [_PT, _PC, _PO, _VP, _VP, _VP]),
+    "svoxb_render_image_bwd": (ctypes.c_int, [_PT, _PC, _PO, _VP, _VP, _VP, _VP]),
+    "svoxb_render_depth": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP]),
+    "svoxb_warp_vertices": (ctypes.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _VP, _VP, _VP]),
+    "svoxb_p2v": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP, _VP, _I32, _F, _F, _VP, _VP]),
+    "svoxb_build_work_bytes": (ctypes.c_size_t, [_I64, _I32]),
+    "svoxb_build_octree_count": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP, _VP, ctypes.POINTER(_I64), _VP]),
+    "svoxb_build_octree_emit": (ctypes.c_int, [_I64, _I32, _VP, _I64, _VP, _VP, _VP, _VP]),
+}
+
+_lib = None
+
+
+def load_library():
+    """Load libsvoxb.so (built by ``__graft_entry__.build()`` / ``make -C svox_t_b200/csrc``). Fails loudly."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO_PATH):
+            raise ImportError(
+                f"svox_t_b200: the CUDA library {_SO_PATH} is missing and there is no CPU fallback. "
+                "Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C svox_t_b200/csrc`.")
+        lib = ctypes.CDLL(_SO_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.svoxb_abi_version() != 1:
+            raise ImportError("svox_t_b200: libsvoxb.so ABI version mismatch; rebuild it")
+        _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError("svox_t_b200.csrc: " + load_library().svoxb_last_error().decode("utf-8", "replace"))
+
+
+def launch_count():
+    return int(load_library().svoxb_launch_count())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else ctypes.c_void_p(0)
+
+
+def _check_input(t, name, dtype=None):
+    # CHECK_INPUT of the reference (include/data_spec.hpp:38-43)
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype} (got {t.dtype}); only float32 features/rays are implemented")
+
+
+# ---- spec records (field names of svox.cpp:74-117) --------------------------------------------------------------
+class RaysSpec:
+    def __init__(self):
+        self.origins = None
+        self.dirs = None
+        self.vdirs = None
+
+    def check(self):
+        for n in ("origins", "dirs", "vdirs"):
+            _check_input(getattr(self, n), n, torch.float32)
+
+
+class TreeSpec:
+    def __init__(self):
+        self.features = None
+        self.data = None
+        self.child = None
+        self.parent_depth = None
+        self.extra_data = None
+        self.offset = None
+        self.scaling = None
+        self._weight_accum = None
+        self.joint_features = None
+        self.skinning_weights = None
+        self.joint_index = None
+        self.transformation_matrices = None
+        self.n_internal = 0
+        self._accel = None          # svox_t_b200 extension: Accel handle cached by N3Tree (None = reference walk)
+
+    def check(self):
+        _check_input(self.features, "features", torch.float32)
+        _check_input(self.data, "data", torch.int32)
+        _check_input(self.child, "child", torch.int32)
+        _check_input(self.parent_depth, "parent_depth", torch.int32)
+        _check_input(self.offset, "offset", torch.float32)
+        _check_input(self.scaling, "scaling", torch.float32)
+        if self.features.dim() != 2 or self.child.dim() != 4:
+            raise RuntimeError("features must be [M, D] and child [n, N, N, N]")
+        if self._weight_accum is not None and self._weight_accum.numel():
+            raise RuntimeError("_weight_accum (accumulate_weights) is not implemented in svox_t_b200")
+
+    def _c(self):
+        self.check()
+        acc = self._accel
+        if acc is not None and not acc.matches(self):
+            acc = None
+        c = _CTree(
+            features=_ptr(self.features), M=self.features.shape[0], D=self.features.shape[1],
+            N=self.child.shape[1], child=_ptr(self.child), data=_ptr(self.data),
+            parent_depth=_ptr(self.parent_depth), n_nodes=self.child.shape[0], n_internal=int(self.n_internal),
+            offset=_ptr(self.offset), scaling=_ptr(self.scaling),
+            accel=acc.handle if acc is not None else ctypes.c_void_p(0))
+        return c
+
+
+class CameraSpec:
+    def __init__(self):
+        self.c2w = None
+        self.fx = 0.0
+        self.fy = 0.0
+        self.width = 0
+        self.height = 0
+
+    def check(self):
+        _check_input(self.c2w, "c2w", torch.float32)
+        if self.c2w.dim() != 2 or self.c2w.shape[1] != 4 or self.c2w.shape[0] < 3:
+            raise RuntimeError("c2w must be [3 or 4, 4]")
+
+    def _c(self):
+        self.check()
+        return _CCamera(c2w=_ptr(self.c2w), fx=float(self.fx), fy=float(self.fy), width=int(self.width),
+                        height=int(self.height))
+
+
+class RenderOptions:
+    def __init__(self):
+        self.step_size = 1e-3
+        self.background_brightness = 1.0
+        self.format = FORMAT_RGBA
+        self.basis_dim = -1
+        self.ndc_width = -1
+        self.ndc_height = -1
+        self.ndc_focal = 0.0
+        self.min_comp = 0
+        self.max_comp = -1
+        self.sigma_thresh = 0.0
+        self.stop_thresh = 0.0
+
+    def _c(self, **override):
+        v = dict(step_size=self.step_size, background_brightness=self.background_brightness,
+                 format=int(self.format), basis_dim=int(self.basis_dim), ndc_width=int(self.ndc_width),
+                 ndc_height=int(self.ndc_height), ndc_focal=float(self.ndc_focal), min_comp=int(self.min_comp),
+                 max_comp=int(self.max_comp), sigma_thresh=self.sigma_thresh, stop_thresh=self.stop_thresh)
+        v.update(override)
+        return _COptions(**v)
+
+
+class Accel:
+    """Owner of a packed grid+brick accelerator (svoxb_accel_create). Valid while child/data are unchanged."""
+
+    def __init__(self, tree_spec, max_depth=0):
+        lib = load_library()
+        tree_spec._accel = None
+        self._key = self._make_key(tree_spec)
+        h = ctypes.c_void_p(0)
+        with torch.cuda.device(tree_spec.child.device):
+            _check(lib.svoxb_accel_create(ctypes.byref(tree_spec._c()), int(max_depth), _stream(), ctypes.byref(h)))
+        self.handle = h
+        self._lib = lib
+
+    @staticmethod
+    def _make_key(ts):
+        return (ts.child.data_ptr(), ts.data.data_ptr(), ts.child._version, ts.data._version,
+                tuple(ts.child.shape), int(ts.features.shape[0]), int(ts.n_internal))
+
+    def matches(self, ts):
+        return self.handle and self._key == self._make_key(ts)
+
+    @property
+    def nbytes(self):
+        return int(self._lib.svoxb_accel_bytes(self.handle))
+
+    def describe(self):
+        n = ctypes.c_int(0)
+        bits = (ctypes.c_int * 4)()
+        bricks = (ctypes.c_int64 * 4)()
+        _check(self._lib.svoxb_accel_describe(self.handle, ctypes.byref(n), bits, bricks))
+        return dict(stages=n.value, bits=list(bits)[:n.value], bricks=list(bricks)[:n.value], bytes=self.nbytes)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._lib.svoxb_accel_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+# ---- functions (svox.cpp:119-144) -----------------------------------------------------------------------------------
+def query_vertical(tree, indices):
+    """(values[Q,D], node_ids[Q] i64, data_ids[Q] i64, leaf_node[n_hit,4] i64) -- svox_kernel.cu:274-324.
+    Rows of ``values`` / ``data_ids`` whose leaf is empty are zero / -1 here (uninitialised in the reference)."""
+    lib = load_library()
+    _check_input(indices, "indices", torch.float32)
+    if indices.dim() != 2 or indices.shape[1] != 3:
+        raise RuntimeError("indices must be [Q, 3]")
+    ct = tree._c()
+    dev = indices.device
+    Q, D = indices.shape[0], tree.features.shape[1]
+    N = tree.child.shape[1]
+    with torch.cuda.device(dev):
+        values = torch.zeros((Q, D), dtype=torch.float32, device=dev)
+        node_ids = torch.empty((Q,), dtype=torch.int64, device=dev)
+        data_ids = torch.full((Q,), -1, dtype=torch.int64, device=dev)
+        n_slots = int(tree.n_internal) * N ** 3
+        mask = torch.zeros((n_slots,), dtype=torch.uint8, device=dev)
+        _check(lib.svoxb_query(ctypes.byref(ct), _ptr(indices), Q, _ptr(values), _ptr(node_ids), _ptr(data_ids),
+                               _ptr(mask), _stream()))
+        scratch = torch.empty((lib.svoxb_leafset_scratch_bytes(n_slots),), dtype=torch.uint8, device=dev)
+        n_hit = torch.zeros((1,), dtype=torch.int64, device=dev)
+        _check(lib.svoxb_leafset_scan(_ptr(mask), n_slots, _ptr(scratch), _ptr(n_hit), _stream()))
+        n = int(n_hit.item())                         # the one sync the reference also has (svox_kernel.cu:312)
+        leaf_node = torch.empty((n, 4), dtype=torch.int64, device=dev)
+        if n:
+            _check(lib.svoxb_leafset_emit(_ptr(mask), n_slots, N, _ptr(scratch), _ptr(leaf_node), _stream()))
+    return values, node_ids, data_ids, leaf_node
+
+
+def construct_tree(tree, indices):
+    """data[leaf(p_i)] = i, in place (svox_kernel.cu:341-352). Deterministic: the largest i wins a shared leaf."""
+    lib = load_library()
+    _check_input(indices, "indices", torch.float32)
+    ct = tree._c()
+    with torch.cuda.device(indices.device):
+        _check(lib.svoxb_construct_tree(ctypes.byref(ct), _ptr(tree.data), _ptr(indices), indices.shape[0], _stream()))
+    tree.data.add_(0)   # bump the tensor version: cached accelerators built from the old data are now stale
+
+
+def _render_fwd(tree, rays, opt, want_depth):
+    lib = load_library()
+    rays.check()
+    ct = tree._c()
+    Q, D = rays.origins.shape[0], tree.features.shape[1]
+    dev = rays.origins.device
+    with torch.cuda.device(dev):
+        out = torch.empty((Q, D), dtype=torch.float32, device=dev)
+        depth = torch.empty((Q, 1), dtype=torch.float32, device=dev) if want_depth else None
+        _check(lib.svoxb_render_rays_fwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), _ptr(rays.vdirs), Q,
+                                         ctypes.byref(opt._c()), _ptr(out), _ptr(depth), _stream()))
+    return out, depth
+
+
+def volume_render(tree, rays, opt):
+    """[Q, D] composited features + opacity (rt_kernel.cu:1362-1379)."""
+    return _render_fwd(tree, rays, opt, False)[0]
+
+
+def volume_render_with_depth(tree, rays, opt):
+    """svox_t_b200 extension: (out[Q,D], depth[Q,1]) from ONE march (the reference needs a second kernel)."""
+    return _render_fwd(tree, rays, opt, True)
+
+
+def _saved_out_for_backward(tree, opt, fwd_out, render_again):
+    # The backward's hit predicate is sigma > 0 with no early stop (rt_kernel.cu:382,456). With the default
+    # options the forward output IS the backward's saved state; otherwise re-render with those semantics.
+    if fwd_out is not None and opt.sigma_thresh == 0.0 and opt.stop_thresh <= 0.0:
+        return fwd_out
+    return render_again()
+
+
+def volume_render_backward(tree, rays, opt, grad_output, saved_out=None):
+    """[M, D] dL/dfeatures (rt_kernel.cu:1402-1426). ``saved_out`` = the forward output, if the caller kept it."""
+    lib = load_library()
+    rays.check()
+    _check_input(grad_output, "grad_output", torch.float32)
+    ct = tree._c()
+    Q = rays.origins.shape[0]
+    dev = rays.origins.device
+    bopt = opt._c(sigma_thresh=0.0, stop_thresh=-1.0)
+
+    def again():
+        o = torch.empty_like(grad_output)
+        _check(lib.svoxb_render_rays_fwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), _ptr(rays.vdirs), Q,
+                                         ctypes.byref(bopt), _ptr(o), ctypes.c_void_p(0), _stream()))
+        return o
+
+    with torch.cuda.device(dev):
+        so = _saved_out_for_backward(tree, opt, saved_out, again)
+        grad = torch.zeros_like(tree.features)
+        _check(lib.svoxb_render_rays_bwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q,
+                                         ctypes.byref(bopt), _ptr(grad_output), _ptr(so), _ptr(grad), _stream()))
+    return grad
+
+
+def _render_image_fwd(tree, cam, opt, want_depth):
+    lib = load_library()
+    ct, cc = tree._c(), cam._c()
+    dev = tree.features.device
+    D = tree.features.shape[1]
+    with torch.cuda.device(dev):
+        out = torch.empty((cam.height, cam.width, D), dtype=torch.float32, device=dev)
+        depth = torch.empty((cam.height, cam.width, 1), dtype=torch.float32, device=dev) if want_depth else None
+        _check(lib.svoxb_render_image_fwd(ctypes.byref(ct), ctypes.byref(cc), ctypes.byref(opt._c()), _ptr(out),
+                                          _ptr(depth), _stream()))
+    return out, depth
+
+
+def volume_render_image(tree, cam, opt):
+    """[H, W, D] (rt_kernel.cu:1381-1400; broken in the reference by its int32 dtype dispatch)."""
+    return _render_image_fwd(tree, cam, opt, False)[0]
+
+
+def volume_render_image_with_depth(tree, cam, opt):
+    return _render_image_fwd(tree, cam, opt, True)
+
+
+def volume_render_image_backward(tree, cam, opt, grad_output, saved_out=None):
+    lib = load_library()
+    _check_input(grad_output, "grad_output", torch.float32)
+    ct, cc = tree._c(), cam._c()
+    dev = tree.features.device
+    bopt = opt._c(sigma_thresh=0.0, stop_thresh=-1.0)
+
+    def again():
+        o = torch.empty_like(grad_output)
+        _check(lib.svoxb_render_image_fwd(ctypes.byref(ct), ctypes.byref(cc), ctypes.byref(bopt), _ptr(o),
+                                          ctypes.c_void_p(0), _stream()))
+        return o
+
+    with torch.cuda.device(dev):
+        so = _saved_out_for_backward(tree, opt, saved_out, again)
+        grad = torch.zeros_like(tree.features)
+        _check(lib.svoxb_render_image_bwd(ctypes.byref(ct), ctypes.byref(cc), ctypes.byref(bopt), _ptr(grad_output),
+                                          _ptr(so), _ptr(grad), _stream()))
+    return grad
+
+
+def render_depth(tree, rays, opt):
+    """[Q, 1] first-hit depth (rt_kernel.cu:1506-1523)."""
+    lib = load_library()
+    rays.check()
+    ct = tree._c()
+    Q = rays.origins.shape[0]
+    dev = rays.origins.device
+    with torch.cuda.device(dev):
+        depth = torch.empty((Q, 1), dtype=torch.float32, device=dev)
+        _check(lib.svoxb_render_depth(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q,
+                                      ctypes.byref(opt._c()), _ptr(depth), _stream()))
+    return depth
+
+
+def warp_vertices(matrices, indices, skinning_weights, joint_index):
+    """[coords'[P,3], mats[P,4,4]] (svox_kernel.cu:354-378)."""
+    lib = load_library()
+    _check_input(indices, "indices", torch.float32)
+    _check_input(matrices, "matrices", torch.float32)
+    _check_input(skinning_weights, "skinning_weights", torch.float32)
+    _check_input(joint_index, "joint_index", torch.int32)
+    P, B = skinning_weights.shape
+    dev = indices.device
+    with torch.cuda.device(dev):
+        vout = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        mout = torch.empty((P, 4, 4), dtype=torch.float32, device=dev)
+        _check(lib.svoxb_warp_vertices(_ptr(matrices), _ptr(indices), _ptr(skinning_weights), _ptr(joint_index), P, B,
+                                       _ptr(vout), _ptr(mout), _stream()))
+    return [vout, mout]
+
+
+def p2v(points, point_features, volume_corner, volume_size, n_voxels, kernel_radius, conv_radius):
+    """[n, n, n, 1] Gaussian splat (p2v_kernel.cu:240-261)."""
+    lib = load_library()
+    for t, n in ((points, "points"), (point_features, "point_features"), (volume_corner, "volume_corner"),
+                 (volume_size, "volume_size")):
+        _check_input(t, n, torch.float32)
+    dev = points.device
+    with torch.cuda.device(dev):
+        vox = torch.empty((n_voxels, n_voxels, n_voxels, 1), dtype=torch.float32, device=dev)
+        _check(lib.svoxb_p2v(_ptr(points), _ptr(point_features), points.shape[0], point_features.shape[1],
+                             _ptr(volume_corner), _ptr(volume_size), int(n_voxels), float(kernel_radius),
+                             float(conv_radius), _ptr(vox), _stream()))
+    return vox
+
+
+def _unsupported(name, why):
+    def f(*a, **k):
+        raise RuntimeError(f"svox_t_b200.csrc.{name} is not implemented: {why}")
+    f.__name__ = name
+    return f
+
+
+# Reference entry points outside the hot path: present so that
+# `hasattr(_C, name)` behaves, but they raise instead of silently doing something else.
+query_vertical_backward = _unsupported("query_vertical_backward", "faults in the reference (Appendix B1); out of scope")
+assign_vertical = _unsupported("assign_vertical", "faults in the reference (Appendix B1); out of scope")
+warp_vertices_backward = _unsupported("warp_vertices_backward", "next-rank component (SURVEY 8f rank 2)")
+p2v_backward = _unsupported("p2v_backward", "next-rank component (SURVEY 8f rank 2)")
+motion_render = _unsupported("motion_render", "next-rank component (SURVEY 8f rank 1)")
+motion_feature_render = _unsupported("motion_feature_render", "next-rank component (SURVEY 8f rank 3)")
+motion_feature_render_backward = _unsupported("motion_feature_render_backward", "buggy in the reference (Appendix B3)")
+opacity_render = _unsupported("opacity_render", "next-rank component (SURVEY 8f rank 1)")
+opacity_render_backward = _unsupported("opacity_render_backward", "wired to the wrong kernel in the reference (B2)")
+calc_corners = _unsupported("calc_corners", "dtype bug in the reference (Appendix B4); out of scope")
+grid_weight_render = _unsupported("grid_weight_render", "no caller in the reference; out of scope")
+quantize_median_cut = _unsupported("quantize_median_cut", "CPU-only PlenOctree leftover; out of scope")

@@ -1,0 +1,510 @@
+// svoxb_tree.cu -- octree descent outside the march: batched point query + unique-leaf set, construct_tree, and the
+// packed grid+brick accelerator the march kernels walk. Also the library's housekeeping (errors, launch counter).
+//
+// Replaces (reference paths relative to /root/reference/svox_t/csrc):
+//   query_single_from_root                                   include/common.cuh:62-100
+//   query_single_kernel / query_vertical                     svox_kernel.cu:44-81, 274-324
+//   generate_index_kernel / unpack_mask_kernel               svox_kernel.cu:239-269
+//   construct_tree_kernel / construct_tree                   svox_kernel.cu:110-121, 341-352
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <mutex>
+#include "svoxb_common.cuh"
+
+namespace svoxb {
+
+// ---- housekeeping -------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+    return SVOXB_ECUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+// Ring of 64-bit work counters per device; each launch gets the next slot, zeroed in stream order.
+static constexpr int N_COUNTERS = 256;
+static unsigned long long* g_counters[64] = {nullptr};
+static std::atomic<unsigned> g_counter_next{0};
+static std::mutex g_counter_mu;
+
+unsigned long long* work_counter(cudaStream_t stream) {
+    int dev = 0;
+    if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return nullptr;
+    if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return nullptr; }
+    if (!g_counters[dev]) {
+        std::lock_guard<std::mutex> lk(g_counter_mu);
+        if (!g_counters[dev]) {
+            unsigned long long* p = nullptr;
+            if (check_cuda(cudaMalloc(&p, sizeof(unsigned long long) * N_COUNTERS), "cudaMalloc(work counters)"))
+                return nullptr;
+            g_counters[dev] = p;
+        }
+    }
+    unsigned long long* c = g_counters[dev] + (g_counter_next.fetch_add(1) % N_COUNTERS);
+    if (check_cuda(cudaMemsetAsync(c, 0, sizeof(unsigned long long), stream), "cudaMemsetAsync(work counter)"))
+        return nullptr;
+    return c;
+}
+
+}  // namespace svoxb
+
+// The accelerator object behind the opaque handle.
+struct svoxb_accel {
+    svoxb::AccelView view;
+    uint32_t* cells[svoxb::MAX_STAGES];
+    int64_t n_bricks[svoxb::MAX_STAGES];
+    int64_t bytes;
+    int64_t M;
+    const int32_t* child;   // identity of the tensors it was built from (sanity check only)
+    const int32_t* data;
+};
+
+namespace svoxb {
+
+int make_tree_args(const svoxb_tree* t, TreeArgs& a) {
+    SVOXB_REQUIRE(t != nullptr, "tree is NULL");
+    SVOXB_REQUIRE(t->features && t->child && t->data && t->offset && t->scaling, "tree has NULL tensors");
+    SVOXB_REQUIRE(t->N >= 2 && t->N <= 16, "branching factor N=%d out of range [2,16]", t->N);
+    SVOXB_REQUIRE(t->D >= 2, "feature width D=%d must be >= 2 (payload + sigma)", t->D);
+    SVOXB_REQUIRE(t->M >= 0 && t->M < (1ll << 31), "M=%lld out of range", (long long)t->M);
+    SVOXB_REQUIRE(t->n_internal >= 1 && t->n_internal <= t->n_nodes, "n_internal=%lld out of range",
+                  (long long)t->n_internal);
+    a.features = t->features; a.M = t->M; a.D = t->D; a.N = t->N;
+    a.child = t->child; a.data = t->data; a.offset = t->offset; a.scaling = t->scaling;
+    a.use_accel = 0;
+    memset(&a.acc, 0, sizeof(a.acc));
+    if (t->accel) {
+        SVOXB_REQUIRE(t->N == 2, "accelerator requires N == 2");
+        SVOXB_REQUIRE(t->accel->child == t->child && t->accel->data == t->data,
+                      "accelerator was built from different child/data tensors");
+        SVOXB_REQUIRE(t->accel->M == t->M, "accelerator was built for M=%lld, tree has M=%lld",
+                      (long long)t->accel->M, (long long)t->M);
+        a.acc = t->accel->view;
+        a.use_accel = 1;
+    }
+    return 0;
+}
+
+// ---- accelerator build ----------------------------------------------------------------------------------------------
+__global__ void max_depth_kernel(const int32_t* __restrict__ parent_depth, int64_t n, int* __restrict__ out) {
+    int m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, __ldg(parent_depth + 2 * i + 1));
+    for (int s = 16; s > 0; s >>= 1) m = max(m, __shfl_xor_sync(FULL, m, s));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// One thread per cell of one stage. roots == nullptr: stage 0 (single grid rooted at node 0).
+__global__ void accel_stage_kernel(const int32_t* __restrict__ child, const int32_t* __restrict__ data, int64_t M,
+                                   const int32_t* __restrict__ roots, int64_t n_bricks, int bits, int base_depth,
+                                   uint32_t* __restrict__ cells, int32_t* __restrict__ next_roots,
+                                   int* __restrict__ next_count, int is_last, int* __restrict__ overflow) {
+    const int64_t per = 1ll << (3 * bits);
+    const int64_t total = n_bricks * per;
+    for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t brick = gid >> (3 * bits);
+        const int lin = (int)(gid & (per - 1));
+        const int m = (1 << bits) - 1;
+        const int x = (lin >> (2 * bits)) & m, y = (lin >> bits) & m, z = lin & m;
+        int64_t node = roots ? (int64_t)__ldg(roots + brick) : 0;
+        uint32_t cell = 0;
+        bool done = false;
+        for (int l = 0; l < bits; ++l) {
+            const int sh = bits - 1 - l;
+            const int64_t slot = node * 8 + (((x >> sh) & 1) << 2) + (((y >> sh) & 1) << 1) + ((z >> sh) & 1);
+            const int skip = __ldg(child + slot);
+            if (skip == 0) {
+                const int idx = __ldg(data + slot);
+                const uint32_t enc = (idx < 0 || (int64_t)idx >= M) ? ACC_EMPTY : (uint32_t)idx;
+                cell = ((uint32_t)(base_depth + l + 1) << ACC_DEPTH_SHIFT) | enc;
+                done = true;
+                break;
+            }
+            node += skip;
+        }
+        if (!done) {
+            if (is_last) {
+                *overflow = 1;
+                cell = ((uint32_t)(base_depth + bits) << ACC_DEPTH_SHIFT) | ACC_EMPTY;
+            } else {
+                const int id = atomicAdd(next_count, 1);
+                next_roots[id] = (int32_t)node;
+                cell = ACC_PTR | (uint32_t)id;
+            }
+        }
+        cells[gid] = cell;
+    }
+}
+
+// ---- point query ------------------------------------------------------------------------------------------------------
+// One lane per point for the descent; the row copy is served by the whole warp (coalesced 4*D-byte rows).
+__global__ void __launch_bounds__(256)
+query_kernel(TreeArgs tr, const float* __restrict__ pts, int64_t Q, float* __restrict__ values,
+             int64_t* __restrict__ node_ids, int64_t* __restrict__ data_ids, uint8_t* __restrict__ slot_mask) {
+    const int lane = threadIdx.x & 31;
+    const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
+    const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (int64_t base = warp_id * 32; base < Q; base += warps_total * 32) {
+        const int64_t q = base + lane;
+        int idx = -1;
+        if (q < Q) {
+            // common.cuh:44-51: one FFMA per axis
+            const float px = fmaf(scl[0], __ldg(pts + 3 * q), off[0]);
+            const float py = fmaf(scl[1], __ldg(pts + 3 * q + 1), off[1]);
+            const float pz = fmaf(scl[2], __ldg(pts + 3 * q + 2), off[2]);
+            float rx, ry, rz, cube;
+            const int64_t slot = descend_ref(tr.child, tr.N, px, py, pz, rx, ry, rz, cube);
+            node_ids[q] = slot;
+            if (slot_mask) slot_mask[slot] = 1;                       // svox_kernel.cu:57-58 (empty leaves too)
+            const int di = __ldg(tr.data + slot);
+            if (di >= 0 && (int64_t)di < tr.M) {                       // svox_kernel.cu:61
+                idx = di;
+                if (data_ids) data_ids[q] = di;
+            }
+        }
+        if (values) {
+            unsigned vm = __ballot_sync(FULL, idx >= 0);
+            while (vm) {
+                const int r = __ffs(vm) - 1;
+                vm &= vm - 1;
+                const int idx_r = __shfl_sync(FULL, idx, r);
+                const float* src = tr.features + (int64_t)idx_r * tr.D;
+                float* dst = values + (base + r) * tr.D;
+                for (int c = lane; c < tr.D; c += 32) dst[c] = __ldg(src + c);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+construct_mark_kernel(TreeArgs tr, int32_t* __restrict__ data_mut, const float* __restrict__ pts, int64_t P,
+                      int phase) {
+    const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
+    const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < P; q += (int64_t)gridDim.x * blockDim.x) {
+        const float px = fmaf(scl[0], __ldg(pts + 3 * q), off[0]);
+        const float py = fmaf(scl[1], __ldg(pts + 3 * q + 1), off[1]);
+        const float pz = fmaf(scl[2], __ldg(pts + 3 * q + 2), off[2]);
+        float rx, ry, rz, cube;
+        const int64_t slot = descend_ref(tr.child, tr.N, px, py, pz, rx, ry, rz, cube);
+        if (phase == 0) data_mut[slot] = -1;                 // every leaf that receives a point
+        else atomicMax(data_mut + slot, (int)q);             // deterministic winner: the largest point index
+    }
+}
+
+// ---- unique-leaf compaction -------------------------------------------------------------------------------------------------
+constexpr int LS_THREADS = 256;
+constexpr int LS_PER_THREAD = 16;
+constexpr int LS_PER_BLOCK = LS_THREADS * LS_PER_THREAD;
+
+__device__ __forceinline__ unsigned load_mask16(const uint8_t* __restrict__ mask, int64_t n, int64_t start) {
+    unsigned bits = 0;
+#pragma unroll
+    for (int i = 0; i < LS_PER_THREAD; ++i) {
+        const int64_t s = start + i;
+        if (s < n && mask[s]) bits |= 1u << i;
+    }
+    return bits;
+}
+
+__global__ void __launch_bounds__(LS_THREADS)
+leafset_count_kernel(const uint8_t* __restrict__ mask, int64_t n, int64_t* __restrict__ block_counts) {
+    __shared__ int wsum[LS_THREADS / 32];
+    const int64_t start = ((int64_t)blockIdx.x * LS_THREADS + threadIdx.x) * LS_PER_THREAD;
+    int c = __popc(load_mask16(mask, n, start));
+    for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(FULL, c, s);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < LS_THREADS / 32; ++i) t += wsum[i];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+// Single block: exclusive scan of the block counts in place; total -> *n_hit. Thread t owns a contiguous chunk.
+__global__ void __launch_bounds__(1024)
+leafset_scan_kernel(int64_t* __restrict__ block_counts, int64_t n_blocks, int64_t* __restrict__ n_hit) {
+    __shared__ int64_t wtot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t per = (n_blocks + 1023) / 1024;
+    const int64_t lo = min(n_blocks, (int64_t)threadIdx.x * per), hi = min(n_blocks, lo + per);
+    int64_t sum = 0;
+    for (int64_t i = lo; i < hi; ++i) sum += block_counts[i];
+    int64_t inc = sum;
+    for (int s = 1; s < 32; s <<= 1) {
+        const int64_t o = __shfl_up_sync(FULL, inc, s);
+        if (lane >= s) inc += o;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int64_t w = wtot[lane];
+        int64_t winc = w;
+        for (int s = 1; s < 32; s <<= 1) {
+            const int64_t o = __shfl_up_sync(FULL, winc, s);
+            if (lane >= s) winc += o;
+        }
+        wtot[lane] = winc - w;            // exclusive offset of each warp
+        if (lane == 31) *n_hit = winc;
+    }
+    __syncthreads();
+    int64_t run = wtot[warp] + inc - sum; // exclusive offset of this thread's chunk
+    for (int64_t i = lo; i < hi; ++i) {
+        const int64_t c = block_counts[i];
+        block_counts[i] = run;
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(LS_THREADS)
+leafset_emit_kernel(const uint8_t* __restrict__ mask, int64_t n, int N, const int64_t* __restrict__ block_offsets,
+                    int64_t* __restrict__ leaf_node) {
+    __shared__ int woff[LS_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t start = ((int64_t)blockIdx.x * LS_THREADS + threadIdx.x) * LS_PER_THREAD;
+    const unsigned bits = load_mask16(mask, n, start);
+    const int c = __popc(bits);
+    int inc = c;
+    for (int s = 1; s < 32; s <<= 1) {
+        const int o = __shfl_up_sync(FULL, inc, s);
+        if (lane >= s) inc += o;
+    }
+    if (lane == 31) woff[warp] = inc;
+    __syncthreads();
+    int wbase = 0;
+    for (int i = 0; i < warp; ++i) wbase += woff[i];
+    int64_t pos = block_offsets[blockIdx.x] + wbase + inc - c;
+    unsigned b = bits;
+    while (b) {
+        const int i = __ffs(b) - 1;
+        b &= b - 1;
+        int64_t v = start + i;                       // packed slot id node*N^3 + u*N^2 + v*N + w
+        int64_t* o = leaf_node + pos * 4;
+        o[3] = v % N; v /= N;
+        o[2] = v % N; v /= N;
+        o[1] = v % N; v /= N;
+        o[0] = v;
+        ++pos;
+    }
+}
+
+}  // namespace svoxb
+
+using namespace svoxb;
+
+// ---- C ABI --------------------------------------------------------------------------------------------------------
+extern "C" int svoxb_abi_version(void) { return SVOXB_ABI_VERSION; }
+extern "C" const char* svoxb_last_error(void) { return g_err; }
+extern "C" int64_t svoxb_launch_count(void) { return g_launches.load(); }
+
+extern "C" int svoxb_device_info(int* sm, int* major, int* minor) {
+    int dev = 0;
+    SVOXB_CUDA(cudaGetDevice(&dev));
+    int a = 0, b = 0, c = 0;
+    SVOXB_CUDA(cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev));
+    SVOXB_CUDA(cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMajor, dev));
+    SVOXB_CUDA(cudaDeviceGetAttribute(&c, cudaDevAttrComputeCapabilityMinor, dev));
+    if (sm) *sm = a;
+    if (major) *major = b;
+    if (minor) *minor = c;
+    return 0;
+}
+
+extern "C" void svoxb_accel_destroy(svoxb_accel* a) {
+    if (!a) return;
+    for (int s = 0; s < MAX_STAGES; ++s)
+        if (a->cells[s]) cudaFree(a->cells[s]);
+    delete a;
+}
+
+extern "C" int64_t svoxb_accel_bytes(const svoxb_accel* a) { return a ? a->bytes : 0; }
+
+extern "C" int svoxb_accel_describe(const svoxb_accel* a, int* n_stages, int* bits, int64_t* bricks) {
+    SVOXB_REQUIRE(a != nullptr, "accel is NULL");
+    if (n_stages) *n_stages = a->view.n_stages;
+    for (int s = 0; s < MAX_STAGES; ++s) {
+        if (bits) bits[s] = s < a->view.n_stages ? a->view.bits[s] : 0;
+        if (bricks) bricks[s] = s < a->view.n_stages ? a->n_bricks[s] : 0;
+    }
+    return 0;
+}
+
+extern "C" int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* stream, svoxb_accel** out) {
+    SVOXB_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    SVOXB_REQUIRE(tree != nullptr && tree->child && tree->data, "tree has NULL tensors");
+    if (tree->N != 2) { set_error("accelerator requires N == 2 (got %d)", tree->N); return SVOXB_EUNSUPPORTED; }
+    if (tree->M >= (int64_t)ACC_EMPTY) {
+        set_error("accelerator supports M < %u feature rows (got %lld)", ACC_EMPTY, (long long)tree->M);
+        return SVOXB_EUNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int* d_scalars = nullptr;     // [0] max depth, [1] overflow, [2..] brick counts per stage
+    SVOXB_CUDA(cudaMalloc(&d_scalars, sizeof(int) * 8));
+    SVOXB_CUDA(cudaMemsetAsync(d_scalars, 0, sizeof(int) * 8, st));
+    int h_scalars[8] = {0};
+    int lmax = max_depth;
+    if (lmax <= 0) {
+        if (!tree->parent_depth) {
+            cudaFree(d_scalars);
+            set_error("max_depth <= 0 needs tree->parent_depth");
+            return SVOXB_EINVAL;
+        }
+        const int grid = (int)min((tree->n_internal + 255) / 256, (int64_t)1024);
+        max_depth_kernel<<<grid, 256, 0, st>>>(tree->parent_depth, tree->n_internal, d_scalars);
+        count_launch();
+        SVOXB_CUDA(cudaMemcpyAsync(h_scalars, d_scalars, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SVOXB_CUDA(cudaStreamSynchronize(st));
+        lmax = h_scalars[0] + 1;
+    }
+    if (lmax > ACC_MAX_DEPTH) {
+        cudaFree(d_scalars);
+        set_error("accelerator supports depth <= %d (tree depth %d)", ACC_MAX_DEPTH, lmax);
+        return SVOXB_EUNSUPPORTED;
+    }
+    svoxb_accel* a = new svoxb_accel();
+    memset(a, 0, sizeof(*a));
+    a->M = tree->M; a->child = tree->child; a->data = tree->data;
+    // stage split: top grid of <= 4 levels (16 KB of shared memory), the rest in bricks of <= 4 levels
+    AccelView& v = a->view;
+    v.lmax = lmax;
+    const int b0 = lmax < 4 ? lmax : 4;
+    const int rem = lmax - b0;
+    const int more = (rem + 3) / 4;
+    v.n_stages = 1 + more;
+    v.bits[0] = b0;
+    for (int s = 0; s < more; ++s) v.bits[1 + s] = rem / more + (s < rem % more ? 1 : 0);
+    int resolved = 0;
+    for (int s = 0; s < v.n_stages; ++s) { resolved += v.bits[s]; v.shift[s] = lmax - resolved; }
+
+    int32_t* roots[2] = {nullptr, nullptr};
+    int rc = 0;
+    auto fail = [&](int code) {
+        if (roots[0]) cudaFree(roots[0]);
+        if (roots[1]) cudaFree(roots[1]);
+        cudaFree(d_scalars);
+        svoxb_accel_destroy(a);
+        return code;
+    };
+    if (v.n_stages > 1) {
+        for (int i = 0; i < 2; ++i)
+            if ((rc = check_cuda(cudaMalloc(&roots[i], sizeof(int32_t) * (size_t)tree->n_internal), "cudaMalloc(roots)")))
+                return fail(rc);
+    }
+    int64_t n_bricks = 1;
+    int base_depth = 0;
+    for (int s = 0; s < v.n_stages; ++s) {
+        const int64_t words = n_bricks << (3 * v.bits[s]);
+        a->n_bricks[s] = n_bricks;
+        if ((rc = check_cuda(cudaMalloc(&a->cells[s], sizeof(uint32_t) * (size_t)max(words, (int64_t)1)), "cudaMalloc(cells)")))
+            return fail(rc);
+        a->bytes += (int64_t)sizeof(uint32_t) * words;
+        v.cells[s] = a->cells[s];
+        const int is_last = (s == v.n_stages - 1);
+        if (words > 0) {
+            const int grid = (int)min((words + 255) / 256, (int64_t)sm_count() * 16);
+            accel_stage_kernel<<<grid, 256, 0, st>>>(tree->child, tree->data, tree->M, s == 0 ? nullptr : roots[(s - 1) & 1],
+                                                     n_bricks, v.bits[s], base_depth, a->cells[s],
+                                                     is_last ? nullptr : roots[s & 1], d_scalars + 2 + s, is_last,
+                                                     d_scalars + 1);
+            count_launch();
+            if ((rc = check_cuda(cudaGetLastError(), "accel_stage_kernel launch"))) return fail(rc);
+        }
+        if ((rc = check_cuda(cudaMemcpyAsync(h_scalars, d_scalars, sizeof(int) * 8, cudaMemcpyDeviceToHost, st), "memcpy")))
+            return fail(rc);
+        if ((rc = check_cuda(cudaStreamSynchronize(st), "accel build sync"))) return fail(rc);
+        n_bricks = is_last ? 0 : h_scalars[2 + s];
+        base_depth += v.bits[s];
+    }
+    if (h_scalars[1]) {
+        set_error("tree is deeper than max_depth=%d", lmax);
+        return fail(SVOXB_EINVAL);
+    }
+    if (roots[0]) cudaFree(roots[0]);
+    if (roots[1]) cudaFree(roots[1]);
+    cudaFree(d_scalars);
+    *out = a;
+    return 0;
+}
+
+extern "C" int svoxb_query(const svoxb_tree* tree, const float* pts, int64_t Q, float* values, int64_t* node_ids,
+                           int64_t* data_ids, uint8_t* slot_mask, void* stream) {
+    TreeArgs tr;
+    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (pts && node_ids)), "pts/node_ids NULL");
+    if (Q == 0) return 0;
+    const int grid = (int)min((Q + 255) / 256, (int64_t)sm_count() * 8);
+    query_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tr, pts, Q, values, node_ids, data_ids, slot_mask);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "query_kernel launch");
+}
+
+extern "C" size_t svoxb_leafset_scratch_bytes(int64_t n_slots) {
+    const int64_t n_blocks = (n_slots + LS_PER_BLOCK - 1) / LS_PER_BLOCK;
+    return sizeof(int64_t) * (size_t)(n_blocks + 1);
+}
+
+extern "C" int svoxb_leafset_scan(const uint8_t* slot_mask, int64_t n_slots, void* scratch, int64_t* n_hit_dev,
+                                  void* stream) {
+    SVOXB_REQUIRE(slot_mask && scratch && n_hit_dev && n_slots > 0, "leafset_scan: bad arguments");
+    const int64_t n_blocks = (n_slots + LS_PER_BLOCK - 1) / LS_PER_BLOCK;
+    cudaStream_t st = (cudaStream_t)stream;
+    leafset_count_kernel<<<(int)n_blocks, LS_THREADS, 0, st>>>(slot_mask, n_slots, (int64_t*)scratch);
+    leafset_scan_kernel<<<1, 1024, 0, st>>>((int64_t*)scratch, n_blocks, n_hit_dev);
+    count_launch(2);
+    return check_cuda(cudaGetLastError(), "leafset_scan launch");
+}
+
+extern "C" int svoxb_leafset_emit(const uint8_t* slot_mask, int64_t n_slots, int32_t N, const void* scratch,
+                                  int64_t* leaf_node, void* stream) {
+    SVOXB_REQUIRE(slot_mask && scratch && leaf_node && n_slots > 0 && N >= 2, "leafset_emit: bad arguments");
+    const int64_t n_blocks = (n_slots + LS_PER_BLOCK - 1) / LS_PER_BLOCK;
+    leafset_emit_kernel<<<(int)n_blocks, LS_THREADS, 0, (cudaStream_t)stream>>>(slot_mask, n_slots, N,
+                                                                                 (const int64_t*)scratch, leaf_node);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "leafset_emit launch");
+}
+
+extern "C" int svoxb_construct_tree(const svoxb_tree* tree, int32_t* data_mut, const float* pts, int64_t P,
+                                    void* stream) {
+    TreeArgs tr;
+    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    SVOXB_REQUIRE(data_mut != nullptr && (P == 0 || pts != nullptr), "data/pts NULL");
+    SVOXB_REQUIRE(P >= 0 && P < (1ll << 31), "point count out of range");
+    if (P == 0) return 0;
+    const int grid = (int)min((P + 255) / 256, (int64_t)sm_count() * 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    construct_mark_kernel<<<grid, 256, 0, st>>>(tr, data_mut, pts, P, 0);
+    construct_mark_kernel<<<grid, 256, 0, st>>>(tr, data_mut, pts, P, 1);
+    count_launch(2);
+    return check_cuda(cudaGetLastError(), "construct_tree launch");
+}

@@ -1,0 +1,103 @@
+"""Small host-side helpers of the N3Tree API: ``N3TreeView`` (the ``tree[points]`` selector used by the per-frame
+rebuild), ``LocalIndex`` and ``DataFormat``. Behaviour follows the reference (svox_t/helpers.py:38-109, 378-420);
+the legacy value accessors that index ``tree.data`` as floats (helpers.py:111-338) are out of scope.
+"""
+import torch
+
+
+class LocalIndex:
+    """Query with points already in tree space [0,1]^3: ``tree[LocalIndex(pts)]`` (helpers.py:378-384)."""
+
+    def __init__(self, val):
+        self.val = val
+
+
+class DataFormat:
+    """Parsed ``data_format`` string: "RGBA", "SH9", "SG25", "ASG4" ... (helpers.py:386-420)."""
+    RGBA, SH, SG, ASG = 0, 1, 2, 3
+    _NAMES = {0: "RGBA", 1: "SH", 2: "SG", 3: "ASG"}
+
+    def __init__(self, txt):
+        head = txt.rstrip("0123456789")
+        tail = txt[len(head):]
+        self.format = {"SH": self.SH, "SG": self.SG, "ASG": self.ASG}.get(head, self.RGBA) if tail else self.RGBA
+        self.basis_dim = int(tail) if tail else -1
+
+    def __repr__(self):
+        return self._NAMES[self.format] + (str(self.basis_dim) if self.basis_dim >= 0 else "")
+
+
+class N3TreeView:
+    """Selection of leaves: by world points (``tree[pts]``), tree-space points (``tree[LocalIndex(pts)]``) or a
+    slice over all leaves (``tree[:]``). ``.refine()`` splits the selected unique leaves (helpers.py:101-109)."""
+
+    def __init__(self, tree, key):
+        self.tree = tree
+        local = False
+        if isinstance(key, LocalIndex):
+            key, local = key.val, True
+        if isinstance(key, tuple) and len(key) >= 3 and not torch.is_tensor(key[0]):
+            key = torch.tensor(key[:3], dtype=torch.float32, device=tree.data.device).reshape(1, 3)
+        if torch.is_tensor(key) and key.ndim == 2 and key.shape[1] == 3:
+            pts = key if key.dtype == torch.float32 else key.float()
+            _, node_ids, leaf_node = tree.forward(tree.features, pts.contiguous(), want_node_ids=True,
+                                                  world=not local, want_leaf_node=True)
+            self._packed_ids = node_ids          # packed slot id of every query point
+            self.leaf_node_id = node_ids
+            self.unique_leaf_node = leaf_node    # [n_hit, 4] unique leaves, increasing slot order
+        else:
+            self._packed_ids = None
+            self.leaf_node_id = None
+            leaves = tree._all_leaves()
+            if isinstance(key, int):
+                key = slice(key, key + 1)
+            self.unique_leaf_node = leaves[key]
+        self.key = (*self.unique_leaf_node.T,)
+        self._tree_ver = tree._ver
+
+    def _check_ver(self):
+        if self.tree._ver > self._tree_ver:
+            raise RuntimeError("N3TreeView has been invalidated because tree data layout has changed")
+
+    def refine(self, repeats=1):
+        self._check_ver()
+        return self.tree.refine(repeats, sel=self.key, leaf_node=self.unique_leaf_node)
+
+    @property
+    def depths(self):
+        """Depth of each selected leaf's node (root = 0)."""
+        self._check_ver()
+        return self.tree.parent_depth[self.key[0], 1]
+
+    @property
+    def lengths_local(self):
+        """Side length of each selected leaf in tree space."""
+        return float(self.tree.N) ** (-self.depths.float() - 1.0)
+
+    @property
+    def lengths(self):
+        return self.lengths_local[:, None] / self.tree.invradius
+
+    @property
+    def corners_local(self):
+        """Lower corner of each selected leaf in tree space, walking parent_depth upward (svox.py:808-826)."""
+        self._check_ver()
+        tree = self.tree
+        curr = self.unique_leaf_node.clone()
+        out = torch.zeros(curr.shape[0], 3, device=curr.device, dtype=torch.float32)
+        alive = torch.ones(curr.shape[0], dtype=torch.bool, device=curr.device)
+        while True:
+            out[alive] = (out[alive] + curr[alive, 1:].float()) / tree.N
+            alive = alive & (curr[:, 0] != 0)
+            if not bool(alive.any()):
+                break
+            packed = tree.parent_depth[curr[alive, 0], 0].long()
+            curr[alive] = tree._unpack_index(packed)
+        return out
+
+    @property
+    def corners(self):
+        return self.tree.tree2world(self.corners_local)
+
+    def __len__(self):
+        return self.unique_leaf_node.shape[0]

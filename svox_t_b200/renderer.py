@@ -1,0 +1,175 @@
+"""VolumeRenderer -- differentiable feature-level volume rendering of an N3Tree.
+
+API of the reference's ``svox_t.renderer`` (svox_t/renderer.py:162-439): ``forward(features, rays, ...)``,
+``render_persp(features, c2w, width, height, fx, fy)``, ``render_depth(features, rays)``; output rows are
+``D-1`` composited sigmoid features followed by opacity. Gradients flow into ``features`` through a custom
+autograd Function backed by the single-re-march backward kernel.
+
+Extensions: ``forward_with_depth`` / ``render_persp_with_depth`` return the first-hit depth from the same march
+(the reference launches a second kernel, renderer.py:377-382).
+"""
+from collections import namedtuple
+from warnings import warn
+
+import torch
+from torch import autograd, nn
+
+from . import csrc as _C
+from .helpers import DataFormat
+
+NDCConfig = namedtuple("NDCConfig", ["width", "height", "focal"])
+Rays = namedtuple("Rays", ["origins", "dirs", "viewdirs"])
+
+
+def _rays_spec_from_rays(rays):
+    spec = _C.RaysSpec()
+    spec.origins = rays.origins
+    spec.dirs = rays.dirs
+    spec.vdirs = rays.viewdirs
+    return spec
+
+
+def _make_camera_spec(c2w, width, height, fx, fy):
+    spec = _C.CameraSpec()
+    spec.c2w = c2w
+    spec.width = width
+    spec.height = height
+    spec.fx = fx
+    spec.fy = fy
+    return spec
+
+
+class _VolumeRenderFunction(autograd.Function):
+    """renderer.py:60-77; additionally keeps the forward output, which the one-pass backward consumes."""
+
+    @staticmethod
+    def forward(ctx, data, tree, rays, opt, want_depth):
+        out, depth = _C._render_fwd(tree, rays, opt, want_depth)
+        ctx.tree, ctx.rays, ctx.opt = tree, rays, opt
+        ctx.saved_out = out
+        if want_depth:
+            ctx.mark_non_differentiable(depth)
+            return out, depth
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out, *_unused):
+        if ctx.needs_input_grad[0]:
+            return (_C.volume_render_backward(ctx.tree, ctx.rays, ctx.opt, grad_out.contiguous(),
+                                              saved_out=ctx.saved_out), None, None, None, None)
+        return None, None, None, None, None
+
+
+class _VolumeRenderImageFunction(autograd.Function):
+    """renderer.py:79-94."""
+
+    @staticmethod
+    def forward(ctx, data, tree, cam, opt, want_depth):
+        out, depth = _C._render_image_fwd(tree, cam, opt, want_depth)
+        ctx.tree, ctx.cam, ctx.opt = tree, cam, opt
+        ctx.saved_out = out
+        if want_depth:
+            ctx.mark_non_differentiable(depth)
+            return out, depth
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out, *_unused):
+        if ctx.needs_input_grad[0]:
+            return (_C.volume_render_image_backward(ctx.tree, ctx.cam, ctx.opt, grad_out.contiguous(),
+                                                    saved_out=ctx.saved_out), None, None, None, None)
+        return None, None, None, None, None
+
+
+class VolumeRenderer(nn.Module):
+    """Volume renderer bound to an N3Tree (renderer.py:162-205)."""
+
+    def __init__(self, tree, step_size: float = 1e-3, background_brightness: float = 1.0, ndc: NDCConfig = None,
+                 min_comp=0, max_comp=-1):
+        super().__init__()
+        self.tree = tree
+        self.step_size = step_size
+        self.background_brightness = background_brightness
+        self.ndc_config = ndc
+        self.min_comp = min_comp
+        self.max_comp = max_comp
+        if isinstance(tree.data_format, DataFormat):
+            self.data_format = tree.data_format
+        else:
+            warn("N3Tree without data_format, assuming the feature-level RGBA format")
+            self.data_format = DataFormat("RGBA")
+        if self.max_comp < 0:
+            self.max_comp += self.data_format.basis_dim
+        self.tree._weight_accum = None
+
+    def _require_cuda(self, cuda):
+        if not cuda or not self.tree.data.is_cuda:
+            # the reference asserts False here (renderer.py:225,335): its PyTorch path is dead code
+            raise RuntimeError("svox_t_b200 renders on CUDA only: there is no CPU / PyTorch fallback path")
+
+    def forward(self, features, rays: Rays, transformation_matrices=None, cuda=True, fast=False):
+        """Render a ray batch -> (B, D): D-1 features + opacity. Differentiable w.r.t. ``features``.
+        ``transformation_matrices`` is accepted and, as in the reference's RGBA path, has no effect."""
+        self._require_cuda(cuda)
+        return _VolumeRenderFunction.apply(
+            features, self.tree._spec(features, transformation_matrices=transformation_matrices),
+            _rays_spec_from_rays(rays), self._get_options(fast), False)
+
+    def forward_with_depth(self, features, rays: Rays, fast=False):
+        """(out (B, D), depth (B, 1)) from one march."""
+        self._require_cuda(True)
+        return _VolumeRenderFunction.apply(features, self.tree._spec(features), _rays_spec_from_rays(rays),
+                                           self._get_options(fast), True)
+
+    def render_persp(self, features, c2w, width=800, height=800, fx=1111.111, fy=None, cuda=True, fast=False):
+        """Perspective image -> (height, width, D). Differentiable (renderer.py:310-366)."""
+        self._require_cuda(cuda)
+        fy = fx if fy is None else fy
+        return _VolumeRenderImageFunction.apply(features, self.tree._spec(features),
+                                                _make_camera_spec(c2w, width, height, fx, fy),
+                                                self._get_options(fast), False)
+
+    def render_persp_with_depth(self, features, c2w, width=800, height=800, fx=1111.111, fy=None, fast=False):
+        """(image (H, W, D), depth (H, W, 1)) from one march."""
+        self._require_cuda(True)
+        fy = fx if fy is None else fy
+        return _VolumeRenderImageFunction.apply(features, self.tree._spec(features),
+                                                _make_camera_spec(c2w, width, height, fx, fy),
+                                                self._get_options(fast), True)
+
+    def render_depth(self, features, rays: Rays, cuda=True, fast=False):
+        """First-hit depth (B, 1), not differentiable (renderer.py:377-382)."""
+        self._require_cuda(cuda)
+        return _C.render_depth(self.tree._spec(features), _rays_spec_from_rays(rays), self._get_options(fast))
+
+    def motion_render(self, *a, **k):
+        return _C.motion_render()
+
+    def motion_feature_render(self, *a, **k):
+        return _C.motion_feature_render()
+
+    def opacity_render(self, *a, **k):
+        return _C.opacity_render()
+
+    def _get_options(self, fast=False):
+        """RenderOptions for the kernels (renderer.py:408-439)."""
+        opts = _C.RenderOptions()
+        opts.step_size = self.step_size
+        opts.background_brightness = self.background_brightness
+        opts.format = self.data_format.format
+        opts.basis_dim = self.data_format.basis_dim
+        opts.min_comp = self.min_comp
+        opts.max_comp = self.max_comp
+        if self.ndc_config is not None:
+            opts.ndc_width = self.ndc_config.width
+            opts.ndc_height = self.ndc_config.height
+            opts.ndc_focal = self.ndc_config.focal
+        else:
+            opts.ndc_width = -1
+        opts.sigma_thresh = 1e-2 if fast else 0.0
+        opts.stop_thresh = 1e-2 if fast else 0.0
+        if hasattr(self, "sigma_thresh"):
+            opts.sigma_thresh = self.sigma_thresh
+        if hasattr(self, "stop_thresh"):
+            opts.stop_thresh = self.stop_thresh
+        return opts
