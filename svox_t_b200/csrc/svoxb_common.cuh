@@ -96,13 +96,22 @@ __device__ __forceinline__ void dda_unit(float cx, float cy, float cz, float ix,
     t1 = -cz * iz; t2 = t1 + iz; tmin = fmaxf(tmin, fminf(t1, t2)); tmax = fminf(tmax, fmaxf(t1, t2));
 }
 
-// sigmoid(x) = 1 / (1 + e^-x) with MUFU.EX2 + MUFU.RCP (abs error ~2e-7; the reference evaluates the same
-// expression with expf and a double divide, rt_kernel.cu:304).
+// sigmoid(x) = 1 / (1 + e^-x) = rcp(1 + ex2(-x * log2 e)): one FMUL, MUFU.EX2, FADD, MUFU.RCP (abs error ~2e-7;
+// the reference evaluates the same expression with expf and a double divide, rt_kernel.cu:304). The .ftz forms
+// skip the denormal range fix-up __expf would add (3 extra instructions per call).
 __device__ __forceinline__ float fast_sigmoid(float x) {
-    float e = __expf(-x);
-    float r;
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return r;
+}
+
+// Address of channel `lane` (+32k) of feature row idx: lane_base + idx * row_bytes, one IMAD.WIDE.U32.
+__device__ __forceinline__ const float* row_ptr(const char* lane_base, int idx, unsigned row_bytes) {
+    return reinterpret_cast<const float*>(lane_base + (size_t)(unsigned)idx * (size_t)row_bytes);
+}
+__device__ __forceinline__ float* row_ptr(char* lane_base, int idx, unsigned row_bytes) {
+    return reinterpret_cast<float*>(lane_base + (size_t)(unsigned)idx * (size_t)row_bytes);
 }
 
 struct Leaf {

@@ -176,6 +176,12 @@ march_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ 
     const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
     const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
 
+    const char* fbase = reinterpret_cast<const char*>(tr.features + lane);
+    const unsigned row_bytes = (unsigned)D * 4u;
+    bool chan_ok[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) chan_ok[k] = lane + 32 * k < D - 1;
+
     float acc[32][K];
 #pragma unroll
     for (int r = 0; r < 32; ++r)
@@ -232,21 +238,20 @@ march_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ 
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int r = 8 * g + i;
-                        const int idx_r = __shfl_sync(FULL, hidx, r);
+                        const int idx_r = __shfl_sync(FULL, hidx, r);      // 0 for lanes without a hit: a valid row
                         wr[i] = __shfl_sync(FULL, w, r);
-                        const float* rowp = tr.features + (int64_t)idx_r * D;
-                        const bool on = (gm >> i) & 1u;
+                        const float* rowp = row_ptr(fbase, idx_r, row_bytes);
 #pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            const int c = lane + 32 * k;
-                            x[i][k] = (on && c < D - 1) ? __ldg(rowp + c) : 0.0f;
-                        }
+                        for (int k = 0; k < K; ++k) x[i][k] = chan_ok[k] ? __ldg(rowp + 32 * k) : 0.0f;
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
+                    for (int i = 0; i < 8; ++i) {
+                        if ((gm >> i) & 1u) {
 #pragma unroll
-                        for (int k = 0; k < K; ++k)
-                            acc[8 * g + i][k] = fmaf(wr[i], fast_sigmoid(x[i][k]), acc[8 * g + i][k]);
+                            for (int k = 0; k < K; ++k)
+                                acc[8 * g + i][k] = fmaf(wr[i], fast_sigmoid(x[i][k]), acc[8 * g + i][k]);
+                        }
+                    }
                 }
             }
         }
@@ -299,6 +304,13 @@ march_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restr
     const int D = tr.D;
     const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
     const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
+
+    const char* fbase = reinterpret_cast<const char*>(tr.features + lane);
+    char* gbase = reinterpret_cast<char*>(grad + lane);
+    const unsigned row_bytes = (unsigned)D * 4u;
+    bool chan_ok[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) chan_ok[k] = lane + 32 * k < D - 1;
 
     Ray ray;
     float T = 1.0f, accum = 0.0f, T_end = 0.0f, gop = 0.0f;
@@ -375,15 +387,10 @@ march_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restr
                     int idxr[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int r = 8 * g + i;
-                        idxr[i] = __shfl_sync(FULL, hidx, r);
-                        const float* rowp = tr.features + (int64_t)idxr[i] * D;
-                        const bool on = (gm >> i) & 1u;
+                        idxr[i] = __shfl_sync(FULL, hidx, 8 * g + i);     // 0 for lanes without a hit: a valid row
+                        const float* rowp = row_ptr(fbase, idxr[i], row_bytes);
 #pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            const int c = lane + 32 * k;
-                            x[i][k] = (on && c < D - 1) ? __ldg(rowp + c) : 0.0f;
-                        }
+                        for (int k = 0; k < K; ++k) x[i][k] = chan_ok[k] ? __ldg(rowp + 32 * k) : 0.0f;
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -392,10 +399,9 @@ march_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restr
                         cp[i] = 0.0f;
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
-                            const int c = lane + 32 * k;
                             const float s = fast_sigmoid(x[i][k]);
-                            const float gv = gs[r * (32 * K) + c];
-                            const float sg = (on && c < D - 1) ? s * gv : 0.0f;
+                            const float gv = gs[r * (32 * K) + lane + 32 * k];
+                            const float sg = (on && chan_ok[k]) ? s * gv : 0.0f;
                             cp[i] += sg;
                             sv[i][k] = sg * (1.0f - s);
                         }
@@ -440,12 +446,11 @@ march_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restr
                         const float w_i = __shfl_sync(FULL, w, r);
                         const float sg_i = __shfl_sync(FULL, sgrad, r);
                         if ((gm >> i) & 1u) {
-                            float* grow = grad + (int64_t)idxr[i] * D;
+                            float* grow = row_ptr(gbase, idxr[i], row_bytes);
 #pragma unroll
                             for (int k = 0; k < K; ++k) {
-                                const int c = lane + 32 * k;
-                                if (c < D - 1) atomicAdd(grow + c, w_i * sv[i][k]);
-                                else if (c == D - 1) atomicAdd(grow + c, sg_i);
+                                if (chan_ok[k]) atomicAdd(grow + 32 * k, w_i * sv[i][k]);
+                                else if (lane + 32 * k == D - 1) atomicAdd(grow + 32 * k, sg_i);
                             }
                         }
                     }
