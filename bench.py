@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the octree volume-rendering hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+Workload (config C3 of BASELINE.json, the configuration the metric is quoted on): depth-8 ball octree
+(1 897 408 leaf rows x 32 channels), 2^20 random rays PER GPU, one step = forward feature render + backward into
+the leaf feature table (+ NCCL all-reduce of the leaf gradients when N > 1). Weak scaling: rays shard across
+ranks with a fixed per-GPU batch, tree and features replicated, the only exchange is the gradient sum.
+
+One JSON line on stdout (rank 0). `value` = whole-job Mrays/s with inputs resident in HBM; `e2e` = the same step
+through the public API (VolumeRenderer + autograd) with rays and targets coming from pinned host memory and the
+loss read back every step; `roofline` = the dominant kernel (backward march) against the measured HBM peak;
+`cpu_baseline` = the CPU oracle (a port of the reference's CUDA algorithm; the reference has no working CPU path)
+timed on this box's cores on a bounded ray sample. `--impl reference` times that CPU port as its own arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+L_TREE, SHAPE, D_FEAT = 8, "ball", 32
+Q_PER_GPU = 1 << 20
+CPU_SAMPLE = 32768          # rays per CPU-baseline measurement / per reference-arm step
+WORKLOAD = ("C3 training step: depth-8 ball octree (1897408 leaf rows x 32 ch, 281697 nodes), 2^20 random rays per "
+            "GPU, fwd feature render + bwd into leaf features")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(cnt, D, M, explicit_rays=True, depth=False):
+    """bytes per launch from the oracle's counters (S samples, LV child lookups, V valid rows, H hits)."""
+    Q, S, LV, V, H = cnt["Q"], cnt["S"], cnt["LV"], cnt["V"], cnt["H"]
+    r_in = 36 if explicit_rays else 0
+    d_out = 4 * D + (4 if depth else 0)
+    b_fwd = Q * (r_in + d_out) + 4 * LV + 4 * S + 4 * V + 4 * (D - 1) * H
+    b_bwd = Q * (r_in + 8 * D) + 4 * LV + 4 * S + 4 * V + 4 * (D - 1) * H + 4 * D * H + 4 * M * D
+    return b_fwd, b_bwd
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples taken DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100", "-i", uuid],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.05:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def scene_numpy(seed_rays):
+    from svox_t_b200 import synth
+    tr = synth.synth_tree(L_TREE, SHAPE)
+    f = synth.synth_features(tr["M"], D_FEAT, seed=0)
+    o, d = synth.synth_rays(Q_PER_GPU, seed=seed_rays)
+    return tr, f, o, d
+
+
+def cpu_port_step(T, f, o, d, g, orc):
+    """One fwd+bwd of the CPU oracle on a ray sample; returns (seconds, counters)."""
+    t0 = time.perf_counter()
+    _, _, cnt = orc.render_rays(T, f, o, d, want_counters=True)
+    orc.render_rays_backward(T, f, o, d, g)
+    return time.perf_counter() - t0, cnt
+
+
+def run_reference_arm(args):
+    """The reference's algorithm on the host cores (CPU port = the oracle; the reference itself has no runnable CPU
+    path and its CUDA extension is not a CPU baseline). Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import oracle as orc
+    tr, f, o, d = scene_numpy(1)
+    T = orc.Tree(tr["child"], tr["data"])
+    rng = np.random.default_rng(5)
+    n = CPU_SAMPLE
+    times = []
+    for s in range(args.warmup + args.steps):
+        lo = (s * n) % (Q_PER_GPU - n)
+        g = rng.standard_normal((n, D_FEAT)).astype(np.float32)
+        dt, _ = cpu_port_step(T, f, o[lo:lo + n], d[lo:lo + n], g, orc)
+        if s >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = n / (ms * 1e-3) / 1e6
+    cores = os.cpu_count()
+    sample = f"each step = fwd+bwd of a {n}-ray slice of the 2^20-ray batch (C oracle, OpenMP over rays)"
+    print(json.dumps({
+        "impl": "reference", "metric": "Mrays/s fwd+bwd feature render", "value": val, "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step": n},
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--skip-extras", action="store_true", help="skip the C2 image / reference-CUDA side measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import svox_t_b200 as sv
+    from svox_t_b200 import csrc as C, dist as svd, synth
+
+    rank, world, local_rank = svd.init_from_env()
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    C.load_library()
+
+    tr, f, o, d = scene_numpy(1 + rank)
+    Q, D, M = Q_PER_GPU, D_FEAT, tr["M"]
+    tree = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=D, map_location=dev)
+    feats = torch.from_numpy(f).to(dev)
+    o_t, d_t = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
+    g_t = torch.randn(Q, D, device=dev, generator=torch.Generator(device=dev).manual_seed(5 + rank))
+    renderer = sv.VolumeRenderer(tree)
+    opt = renderer._get_options()
+    ts = tree._spec(feats)
+    rs = sv.renderer._rays_spec_from_rays(sv.Rays(o_t, d_t, d_t))
+    accel = tree.accel(feats)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(rec=None):
+        e = [ev() for _ in range(4)] if rec is not None else None
+        if e: e[0].record()
+        out = C.volume_render(ts, rs, opt)
+        if e: e[1].record()
+        grad = torch.zeros_like(feats)
+        if e: e[2].record()
+        C._check(C.load_library().svoxb_render_rays_bwd(
+            C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), Q, C.ctypes.byref(opt._c(sigma_thresh=0.0, stop_thresh=-1.0)),
+            C._ptr(g_t), C._ptr(out), C._ptr(grad), C._stream()))
+        if e: e[3].record()
+        svd.all_reduce_leaf_grads(grad)
+        if rec is not None:
+            rec.append(e)
+        return out, grad
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+    sampler = ClockSampler(uuid) if rank == 0 else None
+    time.sleep(0.25)
+    svd.barrier(); torch.cuda.synchronize()
+    launches0 = C.launch_count()
+    t_wall0 = time.time()
+    rec = []
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(args.steps):
+        step(rec)
+    e1.record()
+    torch.cuda.synchronize(); svd.barrier()
+    t_wall1 = time.time()
+    launches = C.launch_count() - launches0
+    total_ms = svd.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms_per_step = total_ms / args.steps
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in rec]))
+    bwd_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in rec]))
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    value = world * Q / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the public API: pinned host rays + targets in, loss out, every step ----------------------
+    h_o, h_d = torch.from_numpy(o).pin_memory(), torch.from_numpy(d).pin_memory()
+    h_tgt = torch.rand(Q, D, generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
+    fparam = feats.clone().requires_grad_(True)
+
+    def e2e_step():
+        ro, rd, tgt = (h.to(dev, non_blocking=True) for h in (h_o, h_d, h_tgt))
+        fparam.grad = None
+        out = renderer(fparam, sv.Rays(ro, rd, rd))
+        loss = 0.5 * ((out - tgt) ** 2).mean()
+        loss.backward()
+        svd.all_reduce_leaf_grads(fparam.grad)
+        return float(loss.item())                      # device -> host read of the step's result
+
+    for _ in range(3):
+        e2e_step()
+    svd.barrier(); torch.cuda.synchronize()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize(); svd.barrier()
+    e2e_ms = svd.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    e2e = {"value": world * Q / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(h_o.numel() + h_d.numel() + h_tgt.numel()) * 4, "d2h_bytes_per_step": 4,
+           "api": "VolumeRenderer.forward + autograd backward, loss = 0.5*mean((out-target)^2)"}
+
+    if rank != 0:
+        return
+    # ---- CPU baseline + counters (rank 0, bounded sample) ---------------------------------------------------------------
+    from oracle import oracle as orc
+    T = orc.Tree(tr["child"], tr["data"])
+    n = CPU_SAMPLE
+    g_np = np.random.default_rng(5).standard_normal((n, D)).astype(np.float32)
+    cpu_s, cnt = cpu_port_step(T, f, o[:n], d[:n], g_np, orc)
+    cpu_baseline = {"value": n / cpu_s / 1e6, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port",
+                    "sample": f"first {n} of the 2^20 rays, fwd+bwd once, C oracle with OpenMP over rays ({cpu_s:.2f} s)"}
+    scale = Q / cnt["Q"]
+    cnt_full = {k: (v * scale if k != "Q" else Q) for k, v in cnt.items()}
+    b_fwd, b_bwd = algorithmic_bytes(cnt_full, D, M)
+    peak, peak_src = measured_peaks()
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
+    roof = lambda b, ms, key: {"bound": "hbm", "achieved": b / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                               "frac": b / (ms * 1e-3) / 1e9 / peak, "traffic": traffic.get(key),
+                               "kernel": key, "ms_per_launch": ms, "algorithmic_bytes_per_launch": b,
+                               "peak_source": peak_src}
+    out = {
+        "metric": "Mrays/s fwd+bwd feature render", "value": value, "unit": "Mrays/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_gpu": Q, "global_rays": world * Q, "D": D, "leaf_rows": M,
+                   "nodes": tr["n_nodes"], "options": "step_size=1e-3, background=1, sigma_thresh=stop_thresh=0",
+                   "parallelism": f"ray-sharded x{world}, tree+features replicated, NCCL all-reduce of grad[M,D]",
+                   "l2": "inputs larger than L2: features 243 MB + grad 243 MB + out 134 MB + rays 25 MB vs 126 MB",
+                   "accelerator": accel.describe() if accel is not None else None},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": roof(b_bwd, bwd_ms, "march_bwd_kernel"),
+        "roofline_fwd": roof(b_fwd, fwd_ms, "march_fwd_kernel"),
+        "roofline_step": {"achieved": (b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": (b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9 / peak,
+                          "bytes_per_ray": (b_fwd + b_bwd) / Q},
+        "kernel_ms": {"fwd": fwd_ms, "bwd": bwd_ms},
+        "counters_per_ray": {k: cnt[k] / cnt["Q"] for k in ("S", "LV", "V", "H")},
+        "cpu_baseline": cpu_baseline,
+    }
+    if not args.skip_extras and world == 1:
+        out["extras"] = extras(sv, C, synth, tree, feats, renderer, opt, ts, rs, o_t, d_t, g_t, dev, peak)
+    print(json.dumps(out), flush=True)
+
+
+def extras(sv, C, synth, tree, feats, renderer, opt, ts, rs, o_t, d_t, g_t, dev, peak):
+    """Side measurements (N = 1): config C2 image render, and the reference's own CUDA kernels on the same inputs."""
+    import torch
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def best(fn, warm=2, it=5):
+        for _ in range(warm):
+            fn()
+        ts_ = []
+        for _ in range(it):
+            a, b = ev(), ev()
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts_.append(a.elapsed_time(b))
+        return float(np.median(ts_))
+
+    ex = {}
+    cam = torch.from_numpy(synth.synth_cameras(1)[0]).to(dev)
+    cs = sv.renderer._make_camera_spec(cam, 800, 800, 1111.111, 1111.111)
+    ms = best(lambda: C.volume_render_image_with_depth(ts, cs, opt))
+    ex["c2_image_800x800_fwd_with_depth"] = {"ms": ms, "Mrays/s": 0.64 / (ms * 1e-3)}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import refdrv
+        if refdrv.available():
+            m = refdrv.module()
+            rts = refdrv.tree_spec(feats, tree.child, tree.data, tree.parent_depth, tree.offset, tree.invradius, tree.filled)
+            rrs, ro = refdrv.rays_spec(o_t, d_t), refdrv.options()
+            f_ms = best(lambda: m.volume_render(rts, rrs, ro), 1, 3)
+            b_ms = best(lambda: m.volume_render_backward(rts, rrs, ro, g_t), 1, 3)
+            ex["reference_cuda_same_inputs"] = {"fwd_ms": f_ms, "bwd_ms": b_ms,
+                                                "Mrays/s_fwd_bwd": Q_PER_GPU / ((f_ms + b_ms) * 1e-3) / 1e6,
+                                                "note": "unmodified svox_t csrc compiled for sm_100a (oracle/_ref)"}
+    except Exception as e:  # the checker is optional here
+        ex["reference_cuda_same_inputs"] = {"unavailable": str(e)[:200]}
+    return ex
+
+
+if __name__ == "__main__":
+    main()

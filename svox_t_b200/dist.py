@@ -1,0 +1,81 @@
+"""Multi-GPU data path: rays shard across ranks, the tree and feature table are replicated, and the only exchange
+step is the sum of the leaf-feature gradients. One process per GPU, torch.distributed
+for the plumbing (NCCL over NVLink/NVSwitch on the B200 box, gloo on CPU for the host-logic tests).
+
+The reference has no multi-GPU support at all; this module is new.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from RANK / WORLD_SIZE / MASTER_* (torchrun). Returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local_rank
+
+
+def shard_range(n, rank, world):
+    """Contiguous, balanced slice [lo, hi) of n units (rays, image rows, views) owned by ``rank``."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_rays(rays, rank, world):
+    """Slice every field of a Rays namedtuple to this rank's contiguous share."""
+    lo, hi = shard_range(rays.origins.shape[0], rank, world)
+    return type(rays)(*(t[lo:hi].contiguous() for t in rays))
+
+
+def shard_image_rows(height, rank, world, tile=8):
+    """Row band [y0, y1) of an image for this rank, aligned to the kernels' 8-pixel tiles."""
+    lo, hi = shard_range((height + tile - 1) // tile, rank, world)
+    return min(lo * tile, height), min(hi * tile, height)
+
+
+def all_reduce_leaf_grads(grad, group=None, async_op=False):
+    """Sum dL/dfeatures[M, D] over the ranks, in place (fp32; NCCL all-reduce on NVLink). No-op for one rank."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def barrier():
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
+def max_over_ranks(value_ms, device):
+    """Max of a per-rank scalar (device time in ms) over all ranks."""
+    t = torch.tensor([float(value_ms)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def render_step_sharded(renderer, features, rays, loss_fn, rank, world):
+    """One ray-sharded training step: this rank renders its slice, back-propagates, and the leaf gradients are
+    summed over ranks. ``loss_fn(out, lo, hi)`` must return this shard's contribution to the global loss.
+    Returns (local_loss, features.grad summed over ranks)."""
+    local = shard_rays(rays, rank, world)
+    lo, hi = shard_range(rays.origins.shape[0], rank, world)
+    out = renderer(features, local)
+    loss = loss_fn(out, lo, hi)
+    loss.backward()
+    all_reduce_leaf_grads(features.grad)
+    return loss.detach(), features.grad

@@ -1,0 +1,311 @@
+"""GPU parity tests (B200, `pytest -m gpu`): the CUDA path, called through the C-ABI mirror, against
+  (1) the reference's own CUDA outputs in tests/golden/*.npz,
+  (2) the CPU oracle on the same seeded inputs,
+  (3) the compiled reference extension itself when oracle/_ref is present on the box,
+and, at BASELINE.json's full sizes, size-independent properties.
+
+Tolerances: leaf indices bit-exact; fwd |a-ref| <= 1e-4 + 1e-3|ref| on >= 99.9 % of
+entries and mean abs err <= 1e-5; depth <= 1e-5 on >= 99.9 % of rays; grads relative L2 <= 1e-4.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import refdrv
+import svox_t_b200 as sv
+from conftest import GOLDEN_DIR, golden_files
+from oracle import oracle as orc
+from svox_t_b200 import csrc as C
+from svox_t_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def frac_within(a, ref, atol=1e-4, rtol=1e-3):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    return float((np.abs(a - ref) <= atol + rtol * np.abs(ref)).mean())
+
+
+def rel_l2(a, ref):
+    return float(np.linalg.norm(np.asarray(a, np.float64) - ref) / max(np.linalg.norm(ref), 1e-30))
+
+
+def make_tree(z_or_tr, D, dev, offset=None, scaling=None):
+    t = sv.N3Tree.from_tensors(z_or_tr["child"], z_or_tr["data"], z_or_tr["parent_depth"], data_dim=D,
+                               map_location=dev)
+    if offset is not None:
+        t.offset = torch.from_numpy(np.asarray(offset, np.float32)).to(dev)
+        t.invradius = torch.from_numpy(np.asarray(scaling, np.float32)).to(dev)
+    return t
+
+
+def cu(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def assert_render_parity(out, depth, grad, ref_out, ref_depth, ref_grad):
+    assert frac_within(out, ref_out) >= 0.999
+    assert float(np.abs(out - ref_out).mean()) <= 1e-5
+    assert float((np.abs(depth - ref_depth) <= 1e-5).mean()) >= 0.999
+    assert rel_l2(grad, ref_grad) <= 1e-4
+
+
+# ---- (1) golden vectors produced by the reference's CUDA kernels ----------------------------------------------------
+@pytest.mark.parametrize("accel", [True, False], ids=["accel", "refwalk"])
+@pytest.mark.parametrize("name", golden_files())
+def test_against_reference_golden(dev, name, accel):
+    z = np.load(os.path.join(GOLDEN_DIR, name))
+    D = z["features"].shape[1]
+    tree = make_tree(z, D, dev, z["offset"], z["scaling"])
+    feats = cu(z["features"], dev).requires_grad_(True)
+    r = sv.VolumeRenderer(tree)
+    r.sigma_thresh, r.stop_thresh = float(z["sigma_thresh"]), float(z["stop_thresh"])
+    rays = sv.Rays(cu(z["origins"], dev), cu(z["dirs"], dev), cu(z["dirs"], dev))
+    ts = tree._spec(feats, _with_accel=accel)
+    assert (ts._accel is not None) == accel
+    rs, opt = sv.renderer._rays_spec_from_rays(rays), r._get_options()
+    out, depth = C.volume_render_with_depth(ts, rs, opt)
+    grad = C.volume_render_backward(ts, rs, opt, cu(z["grad_out"], dev), saved_out=out)
+    assert_render_parity(out.detach().cpu().numpy(), depth.cpu().numpy()[:, 0], grad.cpu().numpy(),
+                         z["ref_out"], z["ref_depth"], z["ref_grad"])
+    # standalone depth kernel and the backward without a saved forward agree with the fused path
+    assert torch.equal(C.render_depth(ts, rs, opt), depth)
+    grad2 = C.volume_render_backward(ts, rs, opt, cu(z["grad_out"], dev))
+    assert rel_l2(grad2.cpu().numpy(), z["ref_grad"]) <= 1e-4
+    # descent: bit-exact leaf indices, rows and unique-leaf set
+    vals, node_ids, data_ids, leaf = C.query_vertical(ts, cu(z["pts"], dev))
+    valid = z["ref_valid"]
+    assert (node_ids.cpu().numpy() == z["ref_node_ids"]).all()
+    assert ((data_ids.cpu().numpy() >= 0) == valid).all()
+    assert (data_ids.cpu().numpy()[valid] == z["ref_data_ids"][valid]).all()
+    assert (vals.cpu().numpy()[valid] == z["ref_values"][valid]).all()
+    assert (leaf.cpu().numpy() == z["ref_leaf_node"]).all()
+
+
+def test_image_kernel_matches_golden_camera_rays(dev):
+    z = np.load(os.path.join(GOLDEN_DIR, "ball_L5_D40_cam.npz"))
+    cam = z["camera"]
+    c2w, fx, W, H = cam[:16].reshape(4, 4), float(cam[16]), int(cam[18]), int(cam[19])
+    D = z["features"].shape[1]
+    tree = make_tree(z, D, dev)
+    feats = cu(z["features"], dev).requires_grad_(True)
+    r = sv.VolumeRenderer(tree)
+    img, depth = r.render_persp_with_depth(feats, cu(c2w, dev), width=W, height=H, fx=fx)
+    assert img.shape == (H, W, D) and depth.shape == (H, W, 1)
+    (img * cu(z["grad_out"], dev).view(H, W, D)).sum().backward()
+    assert_render_parity(img.detach().cpu().numpy().reshape(-1, D), depth.cpu().numpy().reshape(-1),
+                         feats.grad.cpu().numpy(), z["ref_out"], z["ref_depth"], z["ref_grad"])
+    # 3x4 pose and the plain render_persp entry point
+    img2 = r.render_persp(feats.detach(), cu(c2w[:3], dev), width=W, height=H, fx=fx)
+    assert torch.equal(img2, img.detach())
+
+
+# ---- (2) CPU oracle on seeded inputs, autograd plumbing, edge cases -------------------------------------------------
+@pytest.mark.parametrize("L,shape,D,Q", [(4, "all", 16, 2048), (6, "ball", 33, 2048), (5, "ball", 64, 1024),
+                                         (3, "ball", 2, 512), (5, "shell", 100, 512)])
+def test_autograd_path_vs_oracle(dev, L, shape, D, Q):
+    tr = synth.synth_tree(L, shape, r_out=0.45 if L <= 3 else 0.30, r_in=0.2)
+    f = synth.synth_features(tr["M"], D)
+    o, d = synth.synth_rays(Q)
+    g = np.random.default_rng(5).standard_normal((Q, D)).astype(np.float32)
+    tree = make_tree(tr, D, dev)
+    feats = cu(f, dev).requires_grad_(True)
+    rays = sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev))
+    out, depth = sv.VolumeRenderer(tree).forward_with_depth(feats, rays)
+    (out * cu(g, dev)).sum().backward()
+    T = orc.Tree(tr["child"], tr["data"])
+    o_ref, d_ref = orc.render_rays(T, f, o, d)
+    g_ref = orc.render_rays_backward(T, f, o, d, g)
+    assert_render_parity(out.detach().cpu().numpy(), depth.cpu().numpy()[:, 0], feats.grad.cpu().numpy(),
+                         o_ref, d_ref, g_ref)
+
+
+def test_non_octree_branching_factor(dev):
+    t = sv.N3Tree(N=3, data_dim=5, map_location=dev)
+    t.refine(repeats=2)                                   # 27^3 leaves of side 1/27
+    n_leaf = t.n_leaves
+    leaves = t._all_leaves()
+    t.data[(*leaves.T,)] = torch.arange(n_leaf, dtype=torch.int32, device=dev)[:, None]
+    t._invalidate()
+    f = synth.synth_features(n_leaf, 5)
+    o, d = synth.synth_rays(777)
+    feats = cu(f, dev).requires_grad_(True)
+    assert t.accel(feats) is None                          # packed accelerator is octree-only
+    out, depth = sv.VolumeRenderer(t).forward_with_depth(feats, sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev)))
+    g = np.random.default_rng(5).standard_normal((777, 5)).astype(np.float32)
+    (out * cu(g, dev)).sum().backward()
+    T = orc.Tree(t.child.cpu().numpy(), t.data.cpu().numpy())
+    o_ref, d_ref = orc.render_rays(T, f, o, d)
+    assert_render_parity(out.detach().cpu().numpy(), depth.cpu().numpy()[:, 0], feats.grad.cpu().numpy(),
+                         o_ref, d_ref, orc.render_rays_backward(T, f, o, d, g))
+
+
+def test_edge_cases(dev):
+    tr = synth.synth_tree(4, "ball")
+    D = 8
+    tree = make_tree(tr, D, dev)
+    f = synth.synth_features(tr["M"], D)
+    feats = cu(f, dev)
+    r = sv.VolumeRenderer(tree, background_brightness=0.25)
+    # empty batch
+    e = torch.zeros(0, 3, device=dev)
+    assert r(feats, sv.Rays(e, e, e)).shape == (0, D)
+    # rays that miss the cube, axis-aligned rays (dir components exactly 0), origin inside the cube, ragged batch size
+    o = np.array([[3, 3, 3], [0.5, 0.5, -1], [0.5, 0.5, 0.5], [-1, 0.25, 0.75], [0.5, 2.0, 0.5]], np.float32)
+    d = np.array([[0, 1, 0], [0, 0, 1], [1, 0, 0], [1, 0, 0], [0, -1, 0]], np.float32)
+    o = np.concatenate([o, synth.synth_rays(32)[0]]); d = np.concatenate([d, synth.synth_rays(32)[1]])
+    out, depth = r.forward_with_depth(feats, sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev)))
+    T = orc.Tree(tr["child"], tr["data"])
+    o_ref, d_ref = orc.render_rays(T, f, o, d, background_brightness=0.25)
+    assert np.allclose(out.cpu().numpy(), o_ref, atol=2e-5) and np.allclose(depth.cpu().numpy()[:, 0], d_ref, atol=1e-5)
+    assert np.allclose(out[0].cpu().numpy(), [0.25] * (D - 1) + [0.0])       # miss: background, opacity 0
+    # all-empty tree (no row anywhere): pure background
+    empty = sv.N3Tree(N=2, data_dim=D, init_refine=2, map_location=dev)
+    out = sv.VolumeRenderer(empty)(torch.zeros(1, D, device=dev), sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev)))
+    assert torch.allclose(out[:, :-1], torch.ones_like(out[:, :-1])) and not out[:, -1].any()
+    # unsupported formats fail loudly instead of rendering something else
+    bad = sv.VolumeRenderer(tree)
+    bad.data_format = sv.DataFormat("SH9")
+    with pytest.raises(RuntimeError):
+        bad(feats, sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev)))
+    with pytest.raises(RuntimeError):
+        r(feats.double(), sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev)))
+
+
+def test_refine_by_points_then_construct_tree(dev):
+    """The per-frame rebuild through the reference API: tree[pts].refine() x (L-1), then construct_tree."""
+    L = 5
+    tr = synth.synth_tree(L, "ball")
+    keys = np.nonzero(tr["data"].reshape(-1) != synth.SENTINEL)[0]
+    rng = np.random.default_rng(2)
+    vox = synth._occupied_keys(L, "ball")
+    pts = synth.voxel_centers(vox, L)
+    pts = pts[rng.permutation(len(pts))]
+    tree = sv.N3Tree(N=2, data_dim=4, init_reserve=64, map_location=dev)
+    p = cu(pts, dev)
+    for _ in range(L - 1):
+        tree[p].refine()
+    tree.construct_tree(p)
+    assert tree.filled == tr["n_nodes"] and tree.n_leaves == tr["n_leaves"]   # isomorphic to the sorted build
+    _, node_ids, data_ids = tree(torch.zeros(len(pts), 4, device=dev), p, want_node_ids=True, want_data_ids=True)
+    assert (data_ids.cpu().numpy() == np.arange(len(pts))).all()               # one point per leaf: point i -> row i
+    assert len(keys) == len(pts)
+    # same geometry => same render as the canonical tree, once rows are permuted accordingly
+    f = synth.synth_features(len(pts), 4)
+    o, d = synth.synth_rays(512)
+    rays = sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev))
+    out = sv.VolumeRenderer(tree)(cu(f, dev), rays)
+    T = orc.Tree(tree.child.cpu().numpy(), tree.data.cpu().numpy())
+    assert frac_within(out.cpu().numpy(), orc.render_rays(T, f, o, d)[0]) >= 0.999
+
+
+def test_warp_vertices_and_p2v_vs_oracle(dev):
+    P = 5000
+    rng = np.random.default_rng(2)
+    pts = (0.5 + 0.3 * (rng.random((P, 3)) - 0.5)).astype(np.float32)
+    Tm, w, ji = synth.synth_skeleton(P)
+    w[:, 3] = 0.0                                            # exercise the w > 0 guard
+    co, mats = sv.warp_vertices(cu(Tm, dev), cu(pts, dev), cu(w, dev), cu(ji, dev))
+    co_ref, m_ref = orc.warp_vertices(Tm, pts, w, ji)
+    assert np.allclose(co.cpu().numpy(), co_ref, atol=1e-6) and np.allclose(mats.cpu().numpy(), m_ref, atol=1e-6)
+    assert torch.equal(sv.blend_transformation_matrix(cu(Tm, dev), cu(w, dev), cu(ji, dev)), mats)
+    feat = rng.random((P, 3)).astype(np.float32)
+    corner, size = np.zeros(3, np.float32), np.ones(3, np.float32)
+    vox = sv.voxelize(cu(pts, dev), cu(feat, dev), cu(corner, dev), cu(size, dev), 64, 1.5 / 64, 2.0 / 64)
+    v_ref = orc.p2v(pts, feat, corner, size, 64, 1.5 / 64, 2.0 / 64)
+    assert vox.shape == (64, 64, 64, 1)
+    assert np.allclose(vox.cpu().numpy(), v_ref, rtol=1e-4, atol=1e-5)
+
+
+# ---- (3) the compiled reference itself, when it travelled to this box -----------------------------------------------
+@pytest.mark.skipif(not os.path.exists(refdrv.REF_SO), reason="oracle/_ref not built")
+def test_against_live_reference_extension(dev):
+    m = refdrv.module()
+    tr = synth.synth_tree(7, "ball")
+    D, Q = 32, 20000
+    f = synth.synth_features(tr["M"], D)
+    o, d = synth.synth_rays(Q, seed=11)
+    tree = make_tree(tr, D, dev)
+    feats = cu(f, dev).requires_grad_(True)
+    o_t, d_t = cu(o, dev), cu(d, dev)
+    g_t = torch.randn(Q, D, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    out, depth = sv.VolumeRenderer(tree).forward_with_depth(feats, sv.Rays(o_t, d_t, d_t))
+    (out * g_t).sum().backward()
+    rts = refdrv.tree_spec(feats.detach(), tree.child, tree.data, tree.parent_depth, tree.offset, tree.invradius,
+                           tree.filled)
+    rrs, ro = refdrv.rays_spec(o_t, d_t), refdrv.options()
+    assert_render_parity(out.detach().cpu().numpy(), depth.cpu().numpy()[:, 0], feats.grad.cpu().numpy(),
+                         m.volume_render(rts, rrs, ro).cpu().numpy(), m.render_depth(rts, rrs, ro).cpu().numpy()[:, 0],
+                         m.volume_render_backward(rts, rrs, ro, g_t).cpu().numpy())
+    pts = torch.rand(100000, 3, device=dev) * 1.2 - 0.1
+    v, nid, did, leaf = tree(feats.detach(), pts, want_node_ids=True, want_data_ids=True, want_leaf_node=True)
+    rv, rnid, rdid, rleaf = m.query_vertical(rts, pts)
+    ok = did >= 0
+    assert torch.equal(nid, rnid) and torch.equal(did[ok], rdid[ok]) and torch.equal(v[ok], rv[ok])
+    assert torch.equal(leaf, rleaf[torch.argsort(tree._pack_index(rleaf))])
+
+
+# ---- full-size properties (BASELINE configs C2 / C3) -----------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c3_scene(dev):
+    tr = synth.synth_tree(8, "ball")
+    D = 32
+    tree = make_tree(tr, D, dev)
+    feats = cu(synth.synth_features(tr["M"], D), dev)
+    return tr, tree, feats
+
+
+def test_full_size_c3_properties(dev, c3_scene):
+    tr, tree, feats = c3_scene
+    assert tr["M"] == 1897408 and tr["n_nodes"] == 281697
+    Q = 1 << 20
+    o, d = synth.synth_rays(Q)
+    o_t, d_t = cu(o, dev), cu(d, dev)
+    r = sv.VolumeRenderer(tree)
+    fw = feats.clone().requires_grad_(True)
+    out, depth = r.forward_with_depth(fw, sv.Rays(o_t, d_t, d_t))
+    assert torch.isfinite(out).all()
+    op = out[:, -1]
+    assert float(op.min()) >= 0 and float(op.max()) <= 1 and float((op > 0).float().mean()) > 0.95
+    assert float(out[:, :-1].min()) >= 0 and float(out[:, :-1].max()) <= 1 + 1e-5   # convex mix of sigmoids and bg
+    # invariance to ray order (ray compaction must not mix rays up)
+    perm = torch.randperm(Q, device=dev)
+    out_p = r(feats, sv.Rays(o_t[perm].contiguous(), d_t[perm].contiguous(), d_t[perm].contiguous()))
+    assert torch.equal(out_p, out.detach()[perm])
+    # linearity of the backward in grad_output and additivity over ray subsets
+    g1, g2 = torch.randn(Q, 32, device=dev), torch.randn(Q, 32, device=dev)
+    ts = tree._spec(feats)
+    rs, opt = sv.renderer._rays_spec_from_rays(sv.Rays(o_t, d_t, d_t)), r._get_options()
+    G1 = C.volume_render_backward(ts, rs, opt, g1, saved_out=out.detach())
+    G2 = C.volume_render_backward(ts, rs, opt, g2, saved_out=out.detach())
+    G12 = C.volume_render_backward(ts, rs, opt, (g1 + 2 * g2).contiguous(), saved_out=out.detach())
+    assert float((G12 - (G1 + 2 * G2)).norm() / G12.norm()) < 1e-4
+    h = Q // 2
+    rsa = sv.renderer._rays_spec_from_rays(sv.Rays(o_t[:h], d_t[:h], d_t[:h]))
+    rsb = sv.renderer._rays_spec_from_rays(sv.Rays(o_t[h:], d_t[h:], d_t[h:]))
+    Ga = C.volume_render_backward(ts, rsa, opt, g1[:h].contiguous(), saved_out=out.detach()[:h].contiguous())
+    Gb = C.volume_render_backward(ts, rsb, opt, g1[h:].contiguous(), saved_out=out.detach()[h:].contiguous())
+    assert float((Ga + Gb - G1).norm() / G1.norm()) < 1e-5
+    # a sample of the full batch against the oracle
+    T = orc.Tree(tr["child"], tr["data"])
+    sel = np.arange(0, Q, Q // 2048)[:2048]
+    o_ref, d_ref = orc.render_rays(T, feats.cpu().numpy(), o[sel], d[sel])
+    assert frac_within(out.detach().cpu().numpy()[sel], o_ref) >= 0.999
+    assert float((np.abs(depth.cpu().numpy()[sel, 0] - d_ref) <= 1e-5).mean()) >= 0.999
+
+
+def test_full_size_c2_image(dev, c3_scene):
+    tr, tree, feats = c3_scene
+    r = sv.VolumeRenderer(tree)
+    cam = cu(synth.synth_cameras(1)[0], dev)
+    img, depth = r.render_persp_with_depth(feats, cam)                      # 800 x 800, fx = 1111.111 (API defaults)
+    assert img.shape == (800, 800, 32)
+    hit = img[..., -1] > 0
+    assert 0.55 < float(hit.float().mean()) < 0.66                          # ~61 % of pixels hit
+    assert bool(((depth[..., 0] > 0) == (img[..., -1] > 0)).float().mean() > 0.99)
+    # the same pixels rendered as explicit rays (restated cam2world_ray) agree statistically
+    oc, dc = orc.camera_rays(cam.cpu().numpy(), 1111.111, 1111.111, 800, 800)
+    out = r(feats, sv.Rays(cu(oc, dev), cu(dc, dev), cu(dc, dev)))
+    assert frac_within(out.cpu().numpy(), img.cpu().numpy().reshape(-1, 32)) >= 0.999

@@ -1,0 +1,117 @@
+"""CPU tests of the host logic: N3Tree structure ops, spec packing, options, persistence, and that the product
+path FAILS LOUDLY (no CPU fallback, no oracle behind the API) when there is no CUDA device."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import svox_t_b200 as sv
+from svox_t_b200 import synth
+
+
+def test_refine_builds_full_tree_like_reference():
+    t = sv.N3Tree(N=2, data_dim=16)
+    for _ in range(3):
+        t.refine()
+    assert (t.filled, t.n_leaves, t.max_depth, t.capacity) == (585, 4096, 3, 585)
+    ch, pd = t.child.reshape(-1, 8).numpy(), t.parent_depth.numpy()
+    node, slot = np.nonzero(ch)
+    kid = node + ch[node, slot]
+    assert (pd[kid, 0] == node * 8 + slot).all() and (pd[kid, 1] == pd[node, 1] + 1).all()
+    assert (t.data == sv.svox.EMPTY).all()
+
+
+def test_init_refine_and_repeats_work():
+    t = sv.N3Tree(N=2, data_dim=4, init_refine=2)           # the reference crashes here (Appendix B5)
+    assert t.n_leaves == 512 and t.filled == 73
+    t3 = sv.N3Tree(N=3, data_dim=4)
+    t3.refine(repeats=2)
+    assert t3.n_leaves == 27 ** 3 and t3.child.shape[1:] == (3, 3, 3)
+
+
+def test_depth_limit_and_selected_refine():
+    t = sv.N3Tree(N=2, data_dim=4, depth_limit=1)
+    t.refine(); t.refine(); t.refine()
+    assert t.max_depth == 1                                   # never deeper than depth_limit
+    t = sv.N3Tree(N=2, data_dim=4)
+    t.data[0, 1, 0, 1, 0] = 7
+    leaf = torch.tensor([[0, 1, 0, 1]])
+    t.refine(sel=(*leaf.T,), leaf_node=leaf)
+    assert t.filled == 2 and int(t.child[0, 1, 0, 1]) == 1
+    assert (t.data[1] == 7).all()                             # children inherit the parent's row (svox.py:539-540)
+    assert t.parent_depth[1].tolist() == [5, 1]
+
+
+def test_resize_keeps_sentinel_and_state_dict_names():
+    t = sv.N3Tree(N=2, data_dim=4, init_reserve=1, geom_resize_fact=1.5)
+    assert t.refine() is True
+    assert (t.data[t.filled:] == sv.svox.EMPTY).all() and (t.child[t.filled:] == 0).all()
+    names = set(t.state_dict().keys())
+    assert {"features", "data", "child", "parent_depth", "_n_internal", "_n_free", "invradius", "offset"} <= names
+    assert sv.svox.EMPTY == 1410065408
+
+
+def test_world_transform_and_pack_index():
+    t = sv.N3Tree(radius=[1.0, 2.0, 4.0], center=[0.0, 1.0, -1.0])
+    p = torch.tensor([[0.0, 1.0, -1.0], [1.0, 3.0, 3.0]])
+    assert torch.allclose(t.world2tree(p), torch.tensor([[0.5, 0.5, 0.5], [1.0, 1.0, 1.0]]))
+    assert torch.allclose(t.tree2world(t.world2tree(p)), p)
+    x = torch.tensor([[5, 1, 0, 1], [0, 0, 0, 0]])
+    assert t._pack_index(x).tolist() == [45, 0]
+    assert t._unpack_index(t._pack_index(x)).tolist() == x.tolist()
+
+
+def test_from_tensors_and_save_load_roundtrip(tmp_path):
+    tr = synth.synth_tree(3, "ball", r_out=0.4)
+    t = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=8)
+    assert t.filled == tr["n_nodes"] and t.n_leaves == tr["n_leaves"] and t.max_depth == 2
+    path = str(tmp_path / "tree.npz")
+    t.save(path)
+    u = sv.N3Tree.load(path)
+    for k in ("child", "data", "parent_depth", "invradius", "offset"):
+        assert torch.equal(getattr(t, k), getattr(u, k))
+    assert u.filled == t.filled and u.data_dim == 8 and repr(u.data_format) == "RGBA"
+
+
+def test_data_format_parsing():
+    assert (sv.DataFormat("RGBA").format, sv.DataFormat("RGBA").basis_dim) == (0, -1)
+    assert (sv.DataFormat("SH9").format, sv.DataFormat("SH9").basis_dim) == (1, 9)
+    assert repr(sv.DataFormat("SG25")) == "SG25" and repr(sv.DataFormat("ASG4")) == "ASG4"
+
+
+def test_render_options_follow_reference_defaults():
+    r = sv.VolumeRenderer(sv.N3Tree(data_dim=8))
+    o = r._get_options()
+    assert (o.step_size, o.background_brightness, o.sigma_thresh, o.stop_thresh, o.ndc_width) == (1e-3, 1.0, 0.0, 0.0, -1)
+    o = r._get_options(fast=True)
+    assert (o.sigma_thresh, o.stop_thresh) == (1e-2, 1e-2)
+    r.sigma_thresh = 0.5
+    assert r._get_options().sigma_thresh == 0.5               # instance override (renderer.py:435-438)
+
+
+def test_no_cpu_fallback_anywhere():
+    t = sv.N3Tree(data_dim=8, init_refine=1)
+    r = sv.VolumeRenderer(t)
+    rays = sv.Rays(torch.zeros(4, 3), torch.ones(4, 3), torch.ones(4, 3))
+    with pytest.raises(RuntimeError):
+        r(t.features, rays)
+    with pytest.raises(RuntimeError):
+        r(t.features, rays, cuda=False)
+    with pytest.raises(RuntimeError):
+        r.render_persp(t.features, torch.eye(4))
+    with pytest.raises(RuntimeError):
+        t(t.features, torch.rand(3, 3))
+    with pytest.raises(RuntimeError):
+        sv.csrc.volume_render(t._spec(t.features), sv.renderer._rays_spec_from_rays(rays), r._get_options())
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.join(os.path.dirname(__file__), "..", "svox_t_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle\.oracle|svox_oracle|_ref/", re.M)
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not pat.search(src), f"{f} references the oracle"

@@ -1,0 +1,197 @@
+"""CPU tests of the oracle (oracle/svox_oracle.c): hand-computed cases, internal consistency, and -- the pin --
+agreement with the reference's own CUDA outputs stored in tests/golden/*.npz (see tests/golden/make_golden.py).
+
+Tolerances are the ones of SURVEY.md section 8(c):
+  fwd features/opacity : |a - ref| <= 1e-4 + 1e-3*|ref| on >= 99.9 % of entries, mean abs err <= 1e-5
+  depth                : <= 1e-5 on >= 99.9 % of rays
+  grads                : relative L2 over grad[M, D] <= 1e-4
+  leaf indices         : bit-exact
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR, golden_files
+from oracle import oracle as orc
+from svox_t_b200 import synth
+
+FWD_ATOL, FWD_RTOL = 1e-4, 1e-3
+
+
+def frac_within(a, ref, atol=FWD_ATOL, rtol=FWD_RTOL):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    return float((np.abs(a - ref) <= atol + rtol * np.abs(ref)).mean())
+
+
+def single_leaf_tree():
+    """Root only: 8 leaf slots, slot (0,0,0) holds row 0, the rest are empty."""
+    child = np.zeros((1, 2, 2, 2), np.int32)
+    data = np.full((1, 2, 2, 2, 1), orc.SENTINEL, np.int32)
+    data[0, 0, 0, 0, 0] = 0
+    return orc.Tree(child, data)
+
+
+def test_sentinel_value():
+    assert orc.SENTINEL == int(np.array(int(1e10)).astype(np.int32)) == 1410065408
+
+
+def test_single_leaf_axis_ray_closed_form():
+    T = single_leaf_tree()
+    f = np.array([[0.3, -1.2, 2.0]], np.float32)          # two payload channels + sigma = 2
+    o = np.array([[0.25, 0.25, -1.0]], np.float32)
+    d = np.array([[0.0, 0.0, 1.0]], np.float32)
+    out, depth = orc.render_rays(T, f, o, d, step_size=1e-3)
+    # leaf (0,0,0) spans z in [0, .5]; delta_t = 0.5 + step; the second half of the ray is an empty leaf
+    att = math.exp(-(0.5 + 1e-3) * 2.0)
+    sig = 1.0 / (1.0 + np.exp(-f[0, :2].astype(np.float64)))
+    expect = (1 - att) * sig + att * 1.0
+    assert np.allclose(out[0, :2], expect, atol=2e-6)
+    assert abs(out[0, 2] - (1 - att)) < 2e-6
+    assert abs(depth[0] - 1.0) < 1e-6                     # enters the cube after travelling 1.0
+
+
+def test_ray_missing_the_cube_returns_background():
+    T = single_leaf_tree()
+    f = np.array([[0.3, -1.2, 2.0]], np.float32)
+    o = np.array([[2.0, 2.0, 2.0]], np.float32)
+    d = np.array([[0.0, 1.0, 0.0]], np.float32)
+    out, depth = orc.render_rays(T, f, o, d, background_brightness=0.7)
+    assert np.allclose(out[0], [0.7, 0.7, 0.0]) and depth[0] == 0.0
+    g = np.ones((1, 3), np.float32)
+    assert not orc.render_rays_backward(T, f, o, d, g).any()
+
+
+def test_clamp_and_slot_packing():
+    tr = synth.synth_tree(3, "all")
+    T = orc.Tree(tr["child"], tr["data"])
+    f = np.zeros((tr["M"], 2), np.float32)
+    pts = np.array([[1.0, 1.0, 1.0], [0.0, 0.0, 0.0], [-3.0, 0.5, 2.0], [0.999, 0.001, 0.5]], np.float32)
+    _, node_ids, data_ids, valid = orc.query(T, f, pts)
+    assert valid.all()
+    # full tree: voxel rank = linear key of the finest cell; (1,1,1) clamps into the last cell
+    R = 8
+    cell = np.clip(np.floor(np.clip(pts, 0, 1 - 1e-6) * R), 0, R - 1).astype(np.int64)
+    assert (data_ids == (cell[:, 0] * R + cell[:, 1]) * R + cell[:, 2]).all()
+    # packed slot id decodes to a leaf slot of an existing node
+    assert (node_ids // 8 < tr["n_nodes"]).all() and (tr["child"].reshape(-1)[node_ids] == 0).all()
+
+
+def test_tree_generator_invariants():
+    tr = synth.synth_tree(4, "all")
+    assert (tr["n_nodes"], tr["n_leaves"], tr["M"]) == (585, 4096, 4096)       # C1
+    tr = synth.synth_tree(5, "ball")
+    n = tr["n_nodes"]
+    assert tr["n_leaves"] == 7 * n + 1                                          # every split adds 7 leaves
+    ch, pd = tr["child"].reshape(n, 8), tr["parent_depth"]
+    node, slot = np.nonzero(ch)
+    kid = node + ch[node, slot]
+    assert (pd[kid, 0] == node * 8 + slot).all() and (pd[kid, 1] == pd[node, 1] + 1).all()
+    assert sorted(kid.tolist()) == list(range(1, n))
+    d = tr["data"].reshape(-1)
+    assert sorted(d[d != synth.SENTINEL].tolist()) == list(range(tr["M"]))
+    assert (d[ch.reshape(-1) != 0] == synth.SENTINEL).all()                    # interior slots carry no row
+
+
+def test_backward_matches_finite_differences_fp64():
+    tr = synth.synth_tree(3, "ball", r_out=0.45)
+    T = orc.Tree(tr["child"], tr["data"])
+    rng = np.random.default_rng(0)
+    f = synth.synth_features(tr["M"], 4).astype(np.float64)
+    f[:, 3] = np.abs(f[:, 3]) + 0.5                      # keep sigma away from the sigma > 0 kink
+    o, d = synth.synth_rays(64)
+    g = rng.standard_normal((64, 4))
+    grad = orc.render_rays_backward(T, f, o, d, g, dtype=np.float64)
+    loss = lambda ff: float((orc.render_rays(T, ff, o, d, dtype=np.float64)[0] * g).sum())
+    rows = np.argsort(-np.abs(grad).sum(1))[:6]
+    for r in rows:
+        for c in range(4):
+            fp, fm = f.copy(), f.copy()
+            fp[r, c] += 1e-6
+            fm[r, c] -= 1e-6
+            fd = (loss(fp) - loss(fm)) / 2e-6
+            assert abs(fd - grad[r, c]) <= 1e-6 + 1e-5 * abs(fd), (r, c, fd, grad[r, c])
+
+
+def test_f32_restatement_tracks_f64_truth():
+    tr = synth.synth_tree(5, "ball")
+    T = orc.Tree(tr["child"], tr["data"])
+    f = synth.synth_features(tr["M"], 8)
+    o, d = synth.synth_rays(2048)
+    o32, dep32 = orc.render_rays(T, f, o, d)
+    o64, dep64 = orc.render_rays(T, f, o, d, dtype=np.float64)
+    assert frac_within(o32, o64) >= 0.999
+    assert float(np.abs(o32 - o64).mean()) < 1e-5
+    assert float((np.abs(dep32 - dep64) <= 1e-5).mean()) >= 0.999
+
+
+def test_counters_define_algorithmic_bytes():
+    tr = synth.synth_tree(4, "all")
+    T = orc.Tree(tr["child"], tr["data"])
+    f = synth.synth_features(tr["M"], 16)
+    o, d = synth.synth_rays(512)
+    _, _, c = orc.render_rays(T, f, o, d, want_counters=True)
+    assert c["V"] == c["S"] and c["H"] <= c["V"] and c["LV"] == 4 * c["S"]     # full depth-4 tree: 4 lookups/sample
+    assert 20 < c["S"] / c["Q"] < 40                                            # ~27.6 samples/ray
+
+
+def test_camera_rays_convention():
+    c2w = synth.look_at([0.5, 0.5, 2.5])
+    o, d = orc.camera_rays(c2w, 100.0, 100.0, 8, 6)
+    assert np.allclose(o, [0.5, 0.5, 2.5])
+    centre = d[3 * 8 + 4]                                # pixel (ix=4, iy=3) = principal point: straight down -z
+    assert np.allclose(centre, [0, 0, -1], atol=1e-6)
+    assert d[0, 0] < 0 and d[0, 1] > 0                   # top-left pixel looks left and up
+    assert np.allclose(np.linalg.norm(d, axis=1), 1, atol=1e-6)
+
+
+def test_lbs_and_splat_small():
+    rng = np.random.default_rng(1)
+    T = np.tile(np.eye(4, dtype=np.float32), (3, 1, 1))
+    T[1, :3, 3] = [0.1, 0.0, 0.0]
+    T[2, :3, 3] = [0.0, 0.2, 0.0]
+    pts = rng.random((5, 3)).astype(np.float32)
+    w = np.array([[0.5, 0.5, 0.0]] * 5, np.float32)
+    ji = np.array([[1, 2, 0]] * 5, np.int32)
+    co, mats = orc.warp_vertices(T, pts, w, ji)
+    assert np.allclose(co, pts + [0.05, 0.1, 0.0], atol=1e-6)
+    assert np.allclose(mats[:, 3], [0, 0, 0, 1])
+    vox = orc.p2v(np.array([[0.5, 0.5, 0.5]], np.float32), np.array([[9.0, 2.0]], np.float32),
+                  np.zeros(3, np.float32), np.ones(3, np.float32), 3, 0.5, 0.1)
+    assert vox[1, 1, 1, 0] == pytest.approx(2.0) and vox.sum() == pytest.approx(2.0)   # only the centre voxel in range
+
+
+def test_construct_tree_highest_index_wins():
+    tr = synth.synth_tree(2, "all")
+    T = orc.Tree(tr["child"], tr["data"].copy())
+    pts = np.array([[0.1, 0.1, 0.1], [0.9, 0.9, 0.9], [0.12, 0.11, 0.1]], np.float32)
+    orc.construct_tree(T, pts)
+    _, _, ids, _ = orc.query(T, np.zeros((64, 1), np.float32), pts)
+    assert ids.tolist() == [2, 1, 2]
+
+
+# ---- the pin: oracle vs the reference's own CUDA outputs -----------------------------------------------------------
+@pytest.mark.parametrize("name", golden_files())
+def test_oracle_matches_reference_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name))
+    T = orc.Tree(z["child"], z["data"], z["offset"], z["scaling"])
+    f = z["features"]
+    st, sp = float(z["sigma_thresh"]), float(z["stop_thresh"])
+    out, depth = orc.render_rays(T, f, z["origins"], z["dirs"], sigma_thresh=st, stop_thresh=sp)
+    assert frac_within(out, z["ref_out"]) >= 0.999
+    assert float(np.abs(out - z["ref_out"]).mean()) <= 1e-5
+    assert float((np.abs(depth - z["ref_depth"]) <= 1e-5).mean()) >= 0.999
+    grad = orc.render_rays_backward(T, f, z["origins"], z["dirs"], z["grad_out"])
+    rel = np.linalg.norm(grad - z["ref_grad"]) / np.linalg.norm(z["ref_grad"])
+    assert rel <= 1e-4, rel
+    vals, node_ids, data_ids, valid = orc.query(T, f, z["pts"])
+    assert (node_ids == z["ref_node_ids"]).all()                               # bit-exact leaf indices
+    assert (valid == z["ref_valid"]).all()
+    assert (data_ids[valid] == z["ref_data_ids"][valid]).all()
+    assert (vals[valid] == z["ref_values"][valid]).all()
+    assert (orc.leafset(node_ids, T.N) == z["ref_leaf_node"]).all()
+
+
+def test_golden_fixtures_present():
+    assert len(golden_files()) >= 3, "tests/golden/*.npz missing: run tests/golden/make_golden.py on a GPU box"
