@@ -21,146 +21,9 @@
 //     (9 shuffles per 8 hits) and the row gradient leaves as one coalesced red.global.add per hit;
 //   * N == 2 trees are walked through the packed grid+brick accelerator (top grid staged in shared memory),
 //     any other N through the reference tensors.
-#include <math.h>
-#include "svoxb_common.cuh"
+#include "svoxb_march.cuh"
 
 namespace svoxb {
-
-constexpr int BLOCK = 256;
-constexpr int WARPS = BLOCK / 32;
-constexpr int CHUNK = 64;          // rays fetched from the global queue per atomic; one 8x8 pixel tile for images
-
-struct RaySource {
-    const float* origins;          // explicit rays: [Q,3] world space
-    const float* dirs;
-    const float* c2w;              // camera rays: row-major [>=3,4]
-    float fx, fy;
-    int width, height;
-    int tiles_x;
-    int64_t total;                 // queue length: Q, or n_tiles * 64
-};
-
-struct MarchOpts {
-    float step, bg, sigma_thresh, stop_thresh;
-};
-
-struct Ray {
-    float ox, oy, oz, dx, dy, dz, ix, iy, iz, t, tmax, ds;
-};
-
-// rt_kernel.cu:663-665 (transform_coord, one FFMA per axis) + 227-247 (delta scale, invdir in double, slab test).
-__device__ __forceinline__ void ray_setup(const float* __restrict__ off, const float* __restrict__ scl,
-                                          float owx, float owy, float owz, float dwx, float dwy, float dwz, Ray& r) {
-    r.ox = fmaf(scl[0], owx, off[0]);
-    r.oy = fmaf(scl[1], owy, off[1]);
-    r.oz = fmaf(scl[2], owz, off[2]);
-    float dx = dwx * scl[0], dy = dwy * scl[1], dz = dwz * scl[2];
-    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
-    r.ds = 1.0f / nrm;
-    dx *= r.ds; dy *= r.ds; dz *= r.ds;
-    r.dx = dx; r.dy = dy; r.dz = dz;
-    r.ix = (float)(1.0 / ((double)dx + 1e-9));
-    r.iy = (float)(1.0 / ((double)dy + 1e-9));
-    r.iz = (float)(1.0 / ((double)dz + 1e-9));
-    float tmin, tmax;
-    dda_unit(r.ox, r.oy, r.oz, r.ix, r.iy, r.iz, tmin, tmax);
-    if (tmax < 0.0f || tmin > tmax) { tmin = 0.0f; tmax = 0.0f; }   // misses the cube: zero samples, T stays 1
-    r.t = tmin; r.tmax = tmax;
-}
-
-// rt_kernel.cu:1152-1166 -- pinhole ray of pixel (px, py); double sub-expressions as in the reference.
-__device__ __forceinline__ void camera_ray(const RaySource& s, int px, int py,
-                                           float& ox, float& oy, float& oz, float& dx, float& dy, float& dz) {
-    float x = (float)(((double)px - 0.5 * (double)s.width) / (double)s.fx);
-    float y = (float)(-((double)py - 0.5 * (double)s.height) / (double)s.fy);
-    float z = sqrtf((float)((double)(x * x + y * y) + 1.0));
-    x /= z; y /= z; z = -1.0f / z;
-    const float* c = s.c2w;
-    dx = __ldg(c + 0) * x + __ldg(c + 1) * y + __ldg(c + 2) * z;
-    dy = __ldg(c + 4) * x + __ldg(c + 5) * y + __ldg(c + 6) * z;
-    dz = __ldg(c + 8) * x + __ldg(c + 9) * y + __ldg(c + 10) * z;
-    ox = __ldg(c + 3); oy = __ldg(c + 7); oz = __ldg(c + 11);
-}
-
-// Per-warp view of the global ray queue.
-struct Queue {
-    int64_t next, end;
-    bool exhausted;
-};
-
-// Hands queue entries to the lanes in `need`; returns the mask of lanes that now own a fresh ray.
-// row = output row of the ray (ray index, or iy*W+ix).
-template <bool IMAGE>
-__device__ __forceinline__ unsigned refill(const RaySource& src, const float* off, const float* scl,
-                                           unsigned long long* counter, Queue& q, unsigned need, int lane,
-                                           Ray& ray, int& row) {
-    unsigned got = 0;
-    while (need) {
-        if (q.next >= q.end) {
-            if (q.exhausted) break;
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(counter, (unsigned long long)CHUNK);
-            base = __shfl_sync(FULL, base, 0);
-            if ((int64_t)base >= src.total) { q.exhausted = true; break; }
-            q.next = (int64_t)base;
-            q.end = min((int64_t)base + CHUNK, src.total);
-        }
-        const int avail = (int)(q.end - q.next);
-        const int rank = __popc(need & ((1u << lane) - 1u));
-        const bool take = ((need >> lane) & 1u) && rank < avail;
-        bool valid = false;
-        if (take) {
-            const int64_t id = q.next + rank;
-            float ox, oy, oz, dx, dy, dz;
-            if (IMAGE) {
-                const int tile = (int)(id >> 6), in = (int)(id & 63);
-                const int px = (tile % src.tiles_x) * 8 + (in & 7);
-                const int py = (tile / src.tiles_x) * 8 + (in >> 3);
-                valid = px < src.width && py < src.height;
-                if (valid) {
-                    camera_ray(src, px, py, ox, oy, oz, dx, dy, dz);
-                    row = py * src.width + px;
-                }
-            } else {
-                valid = true;
-                const float* o = src.origins + id * 3;
-                const float* d = src.dirs + id * 3;
-                ox = __ldg(o); oy = __ldg(o + 1); oz = __ldg(o + 2);
-                dx = __ldg(d); dy = __ldg(d + 1); dz = __ldg(d + 2);
-                row = (int)id;
-            }
-            if (valid) ray_setup(off, scl, ox, oy, oz, dx, dy, dz, ray);
-        }
-        const unsigned tm = __ballot_sync(FULL, take);
-        const unsigned vm = __ballot_sync(FULL, valid);
-        q.next += __popc(tm);
-        need &= ~vm;
-        got |= vm;
-        // lanes that drew an out-of-image pixel stay in `need` and draw again
-    }
-    return got;
-}
-
-__device__ __forceinline__ void load_top(const TreeArgs& tr, uint32_t* top) {
-    const int n = 1 << (3 * tr.acc.bits[0]);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) top[i] = __ldg(tr.acc.cells[0] + i);
-    __syncthreads();
-}
-
-// One march sample of the lane's ray (rt_kernel.cu:261-277): returns the leaf row (or -1), delta_t and sigma.
-template <bool ACCEL>
-__device__ __forceinline__ void sample(const TreeArgs& tr, const uint32_t* top, const Ray& r, float step,
-                                       int64_t& idx, float& delta_t, float& sigma) {
-    const float px = fmaf(r.t, r.dx, r.ox), py = fmaf(r.t, r.dy, r.oy), pz = fmaf(r.t, r.dz, r.oz);
-    const Leaf lf = locate<ACCEL>(tr, top, px, py, pz);
-    float smin, smax;
-    dda_unit(lf.rx, lf.ry, lf.rz, r.ix, r.iy, r.iz, smin, smax);
-    const float tsub = ACCEL ? (smax - smin) * lf.inv_cube : (smax - smin) / lf.cube;
-    delta_t = tsub + step;
-    idx = lf.idx;
-    sigma = 0.0f;
-    if (idx >= 0) sigma = __ldg(tr.features + idx * tr.D + (tr.D - 1));
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // Forward: out[row, 0..D-2] = sum_i w_i * sigmoid(f_i) + T * bg ; out[row, D-1] = 1 - T ; depth[row] = first hit.
@@ -526,27 +389,14 @@ static int make_source(const float* origins, const float* dirs, int64_t Q, const
     return 0;
 }
 
-template <typename Kern>
-static int persistent_grid(Kern kern, size_t smem, int& grid) {
-    if (smem > 48 * 1024)
-        SVOXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    SVOXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
-    SVOXB_REQUIRE(per_sm > 0, "kernel does not fit on an SM (smem %zu)", smem);
-    grid = per_sm * sm_count();
-    return 0;
-}
-
 template <int K, bool ACCEL, bool IMAGE>
 static int launch_fwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
                       cudaStream_t st) {
     const size_t smem = ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0;
     auto kern = march_fwd_kernel<K, ACCEL, IMAGE>;
     int grid = 0;
-    int rc = persistent_grid(kern, smem, grid);
+    int rc = persistent_grid(kern, smem, src.total, grid);
     if (rc) return rc;
-    const int64_t warps_needed = (src.total + CHUNK - 1) / CHUNK;
-    grid = (int)max((int64_t)1, min((int64_t)grid, (warps_needed + WARPS - 1) / WARPS));
     unsigned long long* counter = work_counter(st);
     if (!counter) return SVOXB_ECUDA;
     kern<<<grid, BLOCK, smem, st>>>(tr, src, m, out, depth, counter);
@@ -560,10 +410,8 @@ static int launch_bwd(const TreeArgs& tr, const RaySource& src, const MarchOpts&
     const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * WARPS * 32 * 32 * K;
     auto kern = march_bwd_kernel<K, ACCEL, IMAGE>;
     int grid = 0;
-    int rc = persistent_grid(kern, smem, grid);
+    int rc = persistent_grid(kern, smem, src.total, grid);
     if (rc) return rc;
-    const int64_t warps_needed = (src.total + CHUNK - 1) / CHUNK;
-    grid = (int)max((int64_t)1, min((int64_t)grid, (warps_needed + WARPS - 1) / WARPS));
     unsigned long long* counter = work_counter(st);
     if (!counter) return SVOXB_ECUDA;
     kern<<<grid, BLOCK, smem, st>>>(tr, src, m, grad_out, saved_out, grad, counter);
@@ -574,6 +422,7 @@ static int launch_bwd(const TreeArgs& tr, const RaySource& src, const MarchOpts&
 template <bool IMAGE>
 static int dispatch_fwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
+    if (quad_supported(tr.D)) return launch_fwd_quad(tr, src, m, IMAGE, out, depth, st);
     const int K = (tr.D + 31) / 32;
 #define SVOXB_FWD(KK)                                                                        \
     case KK:                                                                                 \
@@ -591,6 +440,7 @@ static int dispatch_fwd(const TreeArgs& tr, const RaySource& src, const MarchOpt
 template <bool IMAGE>
 static int dispatch_bwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const float* go,
                         const float* so, float* grad, cudaStream_t st) {
+    if (quad_supported(tr.D)) return launch_bwd_quad(tr, src, m, IMAGE, go, so, grad, st);
     const int K = (tr.D + 31) / 32;
 #define SVOXB_BWD(KK)                                                                        \
     case KK:                                                                                 \

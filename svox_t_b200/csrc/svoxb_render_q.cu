@@ -1,0 +1,432 @@
+// svoxb_render_q.cu -- "quad-lane" march kernels: the fast path for feature widths D % 4 == 0, 8 < D <= 128.
+//
+// Same semantics as the scalar-lane kernels in svoxb_render.cu (reference: rt_kernel.cu:221-328 forward,
+// 330-496 backward, 781-834 depth); what changes is how a warp touches the feature table:
+//   * a feature row is covered by LPR = pow2ceil(D/4) lanes holding one float4 each, so ONE 128-bit load
+//     instruction fetches RPI = 32/LPR whole rows (4 rows = 512 B at D = 32), one 128-bit store writes RPI output
+//     rows and one red.global.add.v4.f32 scatters RPI gradient rows;
+//   * the lanes' traversal (phase A) never reads the feature table: every leaf that holds a row becomes a
+//     candidate, the rows of all candidates of the round are in flight together, and each owner lane picks its
+//     sample's sigma out of the loaded row with one shuffle (the reference's separate 4-byte sigma gather and the
+//     second dependent round trip are gone);
+//   * the per-hit channel dot product of the backward is reduced with a transposing butterfly over the LPR lanes
+//     of a row (LPR-1 shuffles for LPR hits instead of log2(LPR) per hit).
+// Lane layout: lane = q * LPR + c4; q = which of the RPI rows of a load, c4 = channel quad (channels 4*c4..4*c4+3).
+// Ray r of the warp (owner lane r) is served as row q = r % RPI of group j = r / RPI; acc[j] is this lane's float4
+// of ray RPI*j + q.
+#include "svoxb_march.cuh"
+
+namespace svoxb {
+
+__device__ __forceinline__ float4 sigmoid4(const float4 x) {
+    return make_float4(fast_sigmoid(x.x), fast_sigmoid(x.y), fast_sigmoid(x.z), fast_sigmoid(x.w));
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// NB per-lane partials -> totals over the LPR consecutive lanes of a row group. On return the lane holds the
+// total of value index (lane % NB). Transposing steps (each halves the live values), then plain butterfly steps.
+template <int NB, int LPR>
+__device__ __forceinline__ float quad_reduce(float (&v)[NB], int lane) {
+    static_assert(NB == 4 || NB == 8, "NB");
+    if constexpr (NB == 8) {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float send = up ? v[j] : v[j + 4];
+            const float keep = up ? v[j + 4] : v[j];
+            v[j] = keep + __shfl_xor_sync(FULL, send, 4);
+        }
+    }
+    {
+        const bool up = lane & 2;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float send = up ? v[j] : v[j + 2];
+            const float keep = up ? v[j + 2] : v[j];
+            v[j] = keep + __shfl_xor_sync(FULL, send, 2);
+        }
+    }
+    {
+        const bool up = lane & 1;
+        const float send = up ? v[0] : v[1];
+        const float keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(FULL, send, 1);
+    }
+    float r = v[0];
+#pragma unroll
+    for (int w = NB; w < LPR; w <<= 1) r += __shfl_xor_sync(FULL, r, w);
+    return r;
+}
+
+template <int LPR>
+struct Quad {
+    static constexpr int RPI = 32 / LPR;                 // rows per load instruction
+    static constexpr int NB = LPR < 8 ? LPR : 8;         // row groups in flight per batch (4*NB registers)
+    static constexpr int NBATCH = LPR / NB;
+    static constexpr int RAYS_PER_BATCH = RPI * NB;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+template <int LPR, bool ACCEL, bool IMAGE>
+__global__ void __launch_bounds__(BLOCK, (LPR <= 8 ? 2 : 1))
+march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
+                      unsigned long long* counter) {
+    using G = Quad<LPR>;
+    constexpr int RPI = G::RPI, NB = G::NB, NBATCH = G::NBATCH;
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t* top = smem_u32;
+    if (ACCEL) load_top(tr, top);
+    const int lane = threadIdx.x & 31;
+    const int q = lane / LPR, c4 = lane % LPR;
+    const int D = tr.D, D4 = D >> 2;
+    const bool lane_ok = c4 < D4, is_sig = c4 == D4 - 1;
+    const int sig_src = (lane % RPI) * LPR + (D4 - 1);   // lane that holds sigma of this owner lane's row
+    const char* fbase = reinterpret_cast<const char*>(tr.features) + 16 * c4;
+    const unsigned row_bytes = (unsigned)D * 4u;
+    const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
+    const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
+
+    float4 acc[LPR];
+#pragma unroll
+    for (int j = 0; j < LPR; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    Ray ray;
+    float T = 1.0f, depth_v = 0.0f;
+    int row = 0;
+    bool active = false, got_depth = false;
+    Queue qu{0, 0, false};
+    unsigned need = FULL;
+
+    while (true) {
+        if (need) {
+            const unsigned got = refill<IMAGE>(src, off, scl, counter, qu, need, lane, ray, row);
+            if ((got >> lane) & 1u) { active = true; T = 1.0f; got_depth = false; depth_v = 0.0f; }
+            need = 0;
+        }
+        if (__ballot_sync(FULL, active) == 0u) break;
+
+        // ---- phase A: traversal only; a leaf holding a row becomes this lane's candidate ---------------------------
+        int cidx = -1, fin = 0;
+        float cdt = 0.0f, ct = 0.0f;
+        if (active) {
+            if (!(ray.t < ray.tmax)) {
+                fin = 1;
+            } else {
+                traverse<ACCEL>(tr, top, ray, opt.step, cidx, cdt);
+                ct = ray.t;
+                ray.t += cdt;
+                if (!(ray.t < ray.tmax)) fin = 1;
+            }
+        }
+
+        // ---- phase B: rows of all candidates in flight, sigma -> owner, composite -----------------------------------
+        const unsigned vm = __ballot_sync(FULL, cidx >= 0);
+        if (vm) {
+#pragma unroll
+            for (int b = 0; b < NBATCH; ++b) {
+                const unsigned bm = NBATCH == 1 ? vm : (vm >> (G::RAYS_PER_BATCH * b)) & ((1u << G::RAYS_PER_BATCH) - 1u);
+                if (bm) {
+                    float4 x[NB];
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {
+                        const int idx = __shfl_sync(FULL, cidx, RPI * (b * NB + jj) + q);
+                        x[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (idx >= 0 && lane_ok)
+                            x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
+                    }
+                    float sig = 0.0f;
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {
+                        const float v = __shfl_sync(FULL, x[jj].w, sig_src);
+                        if (lane / RPI == b * NB + jj) sig = v;
+                    }
+                    float w = 0.0f;
+                    if ((NBATCH == 1 || lane / G::RAYS_PER_BATCH == b) && cidx >= 0 && sig > opt.sigma_thresh) {
+                        const float att = expf(-cdt * ray.ds * sig);                  // rt_kernel.cu:280
+                        w = T * (1.0f - att);
+                        if (!got_depth) { depth_v = ray.ds * ct; got_depth = true; }  // rt_kernel.cu:826-830
+                        T *= att;
+                        if (T <= opt.stop_thresh) fin = 2;                            // rt_kernel.cu:313
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {
+                        const int j = b * NB + jj;
+                        const float w_j = __shfl_sync(FULL, w, RPI * j + q);
+                        if (w_j != 0.0f) {
+                            const float4 s = sigmoid4(x[jj]);
+                            acc[j].x = fmaf(w_j, s.x, acc[j].x);
+                            acc[j].y = fmaf(w_j, s.y, acc[j].y);
+                            acc[j].z = fmaf(w_j, s.z, acc[j].z);
+                            acc[j].w = fmaf(w_j, s.w, acc[j].w);
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- finished rays: RPI output rows per 128-bit store -----------------------------------------------------
+        const unsigned fm = __ballot_sync(FULL, fin != 0);
+        if (fm) {
+#pragma unroll
+            for (int j = 0; j < LPR; ++j) {
+                const unsigned gm = RPI == 32 ? fm : (fm >> (RPI * j)) & ((1u << RPI) - 1u);
+                if (gm) {
+                    const int r = RPI * j + q;
+                    const float T_r = __shfl_sync(FULL, T, r);
+                    const int fin_r = __shfl_sync(FULL, fin, r);
+                    const int row_r = __shfl_sync(FULL, row, r);
+                    if (fin_r != 0) {
+                        float4 v = acc[j];
+                        if (fin_r == 2) {
+                            const float scale = (float)(1.0 / (1.0 - (double)T_r));   // rt_kernel.cu:315
+                            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+                        } else {
+                            const float add = T_r * opt.bg;                           // rt_kernel.cu:323-325
+                            v.x += add; v.y += add; v.z += add; v.w += add;
+                        }
+                        if (is_sig) v.w = 1.0f - T_r;                                 // rt_kernel.cu:317,326
+                        if (lane_ok) *reinterpret_cast<float4*>(out + (int64_t)row_r * D + 4 * c4) = v;
+                        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+            if (fin != 0) {
+                if (depth) depth[row] = depth_v;
+                active = false;
+            }
+            need = fm;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template <int LPR, bool ACCEL, bool IMAGE>
+__global__ void __launch_bounds__(BLOCK, (LPR <= 8 ? 2 : 1))
+march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restrict__ grad_out,
+                      const float* __restrict__ saved_out, float* __restrict__ grad, unsigned long long* counter) {
+    using G = Quad<LPR>;
+    constexpr int RPI = G::RPI, NB = G::NB, NBATCH = G::NBATCH, DP = 4 * LPR;
+    extern __shared__ uint32_t smem_u32[];
+    const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
+    uint32_t* top = smem_u32;
+    if (ACCEL) load_top(tr, top);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* gs = reinterpret_cast<float*>(smem_u32 + top_words) + (size_t)warp * 32 * DP;   // [32 rays][DP]
+    const int q = lane / LPR, c4 = lane % LPR;
+    const int D = tr.D, D4 = D >> 2;
+    const bool lane_ok = c4 < D4, is_sig = c4 == D4 - 1;
+    const int sig_src = (lane % RPI) * LPR + (D4 - 1);
+    const int red_src = (lane % RPI) * LPR + ((lane / RPI) % NB);     // lane holding this owner's reduced dot product
+    const char* fbase = reinterpret_cast<const char*>(tr.features) + 16 * c4;
+    char* gbase = reinterpret_cast<char*>(grad) + 16 * c4;
+    const unsigned row_bytes = (unsigned)D * 4u;
+    const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
+    const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
+
+    Ray ray;
+    float T = 1.0f, accum = 0.0f, T_end = 0.0f, gop = 0.0f;
+    int row = 0;
+    bool active = false;
+    Queue qu{0, 0, false};
+    unsigned need = FULL;
+
+    while (true) {
+        if (need) {
+            unsigned got = refill<IMAGE>(src, off, scl, counter, qu, need, lane, ray, row);
+            if ((got >> lane) & 1u) { active = true; T = 1.0f; }
+            need = 0;
+            // per new ray: stage its grad_out row, accum = <g, out> over the payload channels, T_end, g_opacity
+            while (got) {
+                const int r = __ffs(got) - 1;
+                got &= got - 1;
+                const int row_r = __shfl_sync(FULL, row, r);
+                const float* g = grad_out + (int64_t)row_r * D;
+                const float* so = saved_out + (int64_t)row_r * D;
+                float part = 0.0f, g_last = 0.0f, o_last = 0.0f;
+                for (int c = lane; c < DP; c += 32) {
+                    const float gv = (c < D) ? __ldg(g + c) : 0.0f;
+                    const float ov = (c < D) ? __ldg(so + c) : 0.0f;
+                    gs[r * DP + c] = gv;
+                    if (c < D - 1) part = fmaf(gv, ov, part);
+                    if (c == D - 1) { g_last = gv; o_last = ov; }
+                }
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(FULL, part, s);
+                g_last = __shfl_sync(FULL, g_last, (D - 1) & 31);
+                o_last = __shfl_sync(FULL, o_last, (D - 1) & 31);
+                if (lane == r) { accum = part; T_end = 1.0f - o_last; gop = g_last; }
+            }
+            __syncwarp();
+        }
+        if (__ballot_sync(FULL, active) == 0u) break;
+
+        // ---- phase A --------------------------------------------------------------------------------------------
+        int cidx = -1;
+        bool fin = false;
+        float cdt = 0.0f;
+        if (active) {
+            if (!(ray.t < ray.tmax)) {
+                fin = true;
+            } else {
+                traverse<ACCEL>(tr, top, ray, opt.step, cidx, cdt);
+                ray.t += cdt;
+                if (!(ray.t < ray.tmax)) fin = true;
+            }
+        }
+
+        // ---- phase B --------------------------------------------------------------------------------------------
+        const unsigned vm = __ballot_sync(FULL, cidx >= 0);
+        if (vm) {
+#pragma unroll
+            for (int b = 0; b < NBATCH; ++b) {
+                const unsigned bm = NBATCH == 1 ? vm : (vm >> (G::RAYS_PER_BATCH * b)) & ((1u << G::RAYS_PER_BATCH) - 1u);
+                if (bm) {
+                    float4 x[NB];
+                    int idxs[NB];
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {
+                        idxs[jj] = __shfl_sync(FULL, cidx, RPI * (b * NB + jj) + q);
+                        x[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (idxs[jj] >= 0 && lane_ok)
+                            x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idxs[jj] * row_bytes));
+                    }
+                    float sig = 0.0f;
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {
+                        const float v = __shfl_sync(FULL, x[jj].w, sig_src);
+                        if (lane / RPI == b * NB + jj) sig = v;
+                    }
+                    float w = 0.0f, dd = 0.0f;
+                    const bool hit = (NBATCH == 1 || lane / G::RAYS_PER_BATCH == b) && cidx >= 0 && sig > 0.0f;
+                    if (hit) {                                                      // rt_kernel.cu:382,456
+                        const float att = expf(-cdt * sig * ray.ds);
+                        w = T * (1.0f - att);
+                        dd = cdt * ray.ds;
+                        T *= att;
+                    }
+                    const unsigned hb = __ballot_sync(FULL, hit);
+                    // pass 1: per-lane partial of c = sum_j s_j g_j; keep s(1-s)g for the scatter
+                    float cp[NB];
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {
+                        const int r = RPI * (b * NB + jj) + q;
+                        const bool on = ((hb >> r) & 1u) && lane_ok;
+                        const float4 g4 = *reinterpret_cast<const float4*>(gs + r * DP + 4 * c4);
+                        const float4 s = sigmoid4(x[jj]);
+                        const float sx = s.x * g4.x, sy = s.y * g4.y, sz = s.z * g4.z, sw = s.w * g4.w;
+                        cp[jj] = on ? (sx + sy) + (sz + (is_sig ? 0.0f : sw)) : 0.0f;
+                        x[jj] = make_float4(sx * (1.0f - s.x), sy * (1.0f - s.y), sz * (1.0f - s.z), sw * (1.0f - s.w));
+                    }
+                    const float c_tot = quad_reduce<NB, LPR>(cp, lane);
+                    const float c_own = __shfl_sync(FULL, c_tot, red_src);
+                    float sgrad = 0.0f;
+                    if (hit) {
+                        accum -= w * c_own;                                          // rt_kernel.cu:479-480
+                        sgrad = dd * (c_own * T - accum) + dd * gop * T_end;         // rt_kernel.cu:486-490
+                    }
+                    // pass 2: one vector reduction per RPI gradient rows
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {
+                        const int r = RPI * (b * NB + jj) + q;
+                        const float w_j = __shfl_sync(FULL, w, r);
+                        const float sg_j = __shfl_sync(FULL, sgrad, r);
+                        if (((hb >> r) & 1u) && lane_ok) {
+                            float* grow = reinterpret_cast<float*>(gbase + (size_t)(unsigned)idxs[jj] * row_bytes);
+                            red_add_v4(grow, w_j * x[jj].x, w_j * x[jj].y, w_j * x[jj].z, is_sig ? sg_j : w_j * x[jj].w);
+                        }
+                    }
+                }
+            }
+        }
+
+        const unsigned fm = __ballot_sync(FULL, fin);
+        if (fm) {
+            if (fin) active = false;
+            need = fm;
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+bool quad_supported(int D) { return D % 4 == 0 && D > 8 && D <= 128; }
+
+static int lpr_for(int D) {
+    int l = 4;
+    while (l * 4 < D) l <<= 1;
+    return l;
+}
+
+template <int LPR, bool ACCEL, bool IMAGE>
+static int launch_fwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
+                        cudaStream_t st) {
+    const size_t smem = ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0;
+    auto kern = march_fwd_quad_kernel<LPR, ACCEL, IMAGE>;
+    int grid = 0;
+    int rc = persistent_grid(kern, smem, src.total, grid);
+    if (rc) return rc;
+    unsigned long long* counter = work_counter(st);
+    if (!counter) return SVOXB_ECUDA;
+    kern<<<grid, BLOCK, smem, st>>>(tr, src, m, out, depth, counter);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "march_fwd_quad_kernel launch");
+}
+
+template <int LPR, bool ACCEL, bool IMAGE>
+static int launch_bwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const float* go, const float* so,
+                        float* grad, cudaStream_t st) {
+    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * WARPS * 32 * 4 * LPR;
+    auto kern = march_bwd_quad_kernel<LPR, ACCEL, IMAGE>;
+    int grid = 0;
+    int rc = persistent_grid(kern, smem, src.total, grid);
+    if (rc) return rc;
+    unsigned long long* counter = work_counter(st);
+    if (!counter) return SVOXB_ECUDA;
+    kern<<<grid, BLOCK, smem, st>>>(tr, src, m, go, so, grad, counter);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "march_bwd_quad_kernel launch");
+}
+
+#define SVOXB_Q_DISPATCH(FN, ...)                                                                      \
+    do {                                                                                               \
+        const int lpr = lpr_for(tr.D);                                                                 \
+        const int sel = (tr.use_accel ? 2 : 0) | (image ? 1 : 0);                                      \
+        switch (lpr * 4 + sel) {                                                                       \
+            case 4 * 4 + 0: return FN<4, false, false>(__VA_ARGS__);                                   \
+            case 4 * 4 + 1: return FN<4, false, true>(__VA_ARGS__);                                    \
+            case 4 * 4 + 2: return FN<4, true, false>(__VA_ARGS__);                                    \
+            case 4 * 4 + 3: return FN<4, true, true>(__VA_ARGS__);                                     \
+            case 8 * 4 + 0: return FN<8, false, false>(__VA_ARGS__);                                   \
+            case 8 * 4 + 1: return FN<8, false, true>(__VA_ARGS__);                                    \
+            case 8 * 4 + 2: return FN<8, true, false>(__VA_ARGS__);                                    \
+            case 8 * 4 + 3: return FN<8, true, true>(__VA_ARGS__);                                     \
+            case 16 * 4 + 0: return FN<16, false, false>(__VA_ARGS__);                                 \
+            case 16 * 4 + 1: return FN<16, false, true>(__VA_ARGS__);                                  \
+            case 16 * 4 + 2: return FN<16, true, false>(__VA_ARGS__);                                  \
+            case 16 * 4 + 3: return FN<16, true, true>(__VA_ARGS__);                                   \
+            case 32 * 4 + 0: return FN<32, false, false>(__VA_ARGS__);                                 \
+            case 32 * 4 + 1: return FN<32, false, true>(__VA_ARGS__);                                  \
+            case 32 * 4 + 2: return FN<32, true, false>(__VA_ARGS__);                                  \
+            case 32 * 4 + 3: return FN<32, true, true>(__VA_ARGS__);                                   \
+            default: break;                                                                            \
+        }                                                                                              \
+        set_error("quad kernels: unsupported feature width D=%d", tr.D);                              \
+        return SVOXB_EINVAL;                                                                           \
+    } while (0)
+
+int launch_fwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, float* out,
+                    float* depth, cudaStream_t st) {
+    SVOXB_REQUIRE(((uintptr_t)tr.features & 15) == 0 && ((uintptr_t)out & 15) == 0, "features/out must be 16-byte aligned");
+    SVOXB_Q_DISPATCH(launch_fwd_q, tr, src, m, out, depth, st);
+}
+
+int launch_bwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, const float* grad_out,
+                    const float* saved_out, float* grad, cudaStream_t st) {
+    SVOXB_REQUIRE(((uintptr_t)tr.features & 15) == 0 && ((uintptr_t)grad & 15) == 0,
+                  "features/grad_features must be 16-byte aligned");
+    SVOXB_Q_DISPATCH(launch_bwd_q, tr, src, m, grad_out, saved_out, grad, st);
+}
+
+}  // namespace svoxb
