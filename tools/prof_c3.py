@@ -13,6 +13,26 @@ dev = torch.device("cuda:0"); torch.cuda.set_device(0)
 tr = synth.synth_tree(L, "ball")
 f = synth.synth_features(tr["M"], D)
 o, d = synth.synth_rays(Q)
+SORT = os.environ.get("SORT", "")
+if SORT:
+    # host-side experiment: order rays by (direction bin, Morton of the cube entry point)
+    nb = int(SORT)
+    ax = np.abs(d).argmax(1); sg = (d[np.arange(Q), ax] > 0).astype(np.int64)
+    uv = np.stack([d[np.arange(Q), (ax + 1) % 3], d[np.arange(Q), (ax + 2) % 3]], 1) / np.abs(d[np.arange(Q), ax])[:, None]
+    cell = np.clip(((uv + 1) * 0.5 * nb).astype(np.int64), 0, nb - 1)
+    dbin = ((ax * 2 + sg) * nb + cell[:, 0]) * nb + cell[:, 1]
+    inv = 1.0 / (d.astype(np.float64) + 1e-9)
+    t1 = -o * inv; t2 = t1 + inv
+    tmin = np.maximum(0, np.minimum(t1, t2).max(1))
+    pin = np.clip(o + tmin[:, None] * d, 0, 1 - 1e-6)
+    I = (pin * 1024).astype(np.int64)
+    def part(x):
+        x = x & 0x3ff; x = (x | (x << 16)) & 0x30000ff; x = (x | (x << 8)) & 0x300f00f
+        x = (x | (x << 4)) & 0x30c30c3; x = (x | (x << 2)) & 0x9249249; return x
+    mort = (part(I[:, 0]) << 2) | (part(I[:, 1]) << 1) | part(I[:, 2])
+    order = np.argsort((dbin << 30) | mort, kind="stable")
+    o, d = o[order].copy(), d[order].copy()
+    print("sorted into", 6 * nb * nb, "direction bins")
 tree = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=D, map_location=dev)
 feats = torch.from_numpy(f).to(dev)
 o_t, d_t = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
