@@ -157,6 +157,73 @@ __device__ __forceinline__ void traverse(const TreeArgs& tr, const uint32_t* top
     idx = (int)lf.idx;
 }
 
+
+// Split traversal step for software pipelining: probe_begin computes the sample position and ISSUES the first
+// brick lookup (accelerator path); probe_end consumes it -- deeper stages if any, leaf decode, slab test, delta_t.
+// Whatever the caller runs in between hides the lookup latency.
+struct Probe {
+    float px, py, pz;
+    uint32_t cell;
+};
+
+template <bool ACCEL>
+__device__ __forceinline__ void probe_begin(const TreeArgs& tr, const uint32_t* __restrict__ top, const Ray& r,
+                                            Probe& pb) {
+    pb.px = fmaf(r.t, r.dx, r.ox); pb.py = fmaf(r.t, r.dy, r.oy); pb.pz = fmaf(r.t, r.dz, r.oz);
+    pb.cell = 0;
+    if (ACCEL) {
+        const AccelView& a = tr.acc;
+        pb.px = clamp01(pb.px); pb.py = clamp01(pb.py); pb.pz = clamp01(pb.pz);
+        const float s = __int_as_float((127 + a.lmax) << 23);
+        const int Ix = (int)(pb.px * s), Iy = (int)(pb.py * s), Iz = (int)(pb.pz * s);
+        const int b0 = a.bits[0], s0 = a.shift[0];
+        uint32_t cell = top[(((Ix >> s0) << b0 | (Iy >> s0)) << b0) | (Iz >> s0)];
+        if (cell & ACC_PTR) {
+            const int b = a.bits[1], sh = a.shift[1], m = (1 << b) - 1;
+            const uint32_t lin = (((((Ix >> sh) & m) << b) | ((Iy >> sh) & m)) << b) | ((Iz >> sh) & m);
+            cell = __ldg(a.cells[1] + (((size_t)(cell & 0x7fffffffu)) << (3 * b)) + lin);
+        }
+        pb.cell = cell;
+    }
+}
+
+template <bool ACCEL>
+__device__ __forceinline__ void probe_end(const TreeArgs& tr, const Probe& pb, const Ray& r, float step,
+                                          int& idx, float& delta_t) {
+    float rx, ry, rz, smin, smax;
+    if (ACCEL) {
+        const AccelView& a = tr.acc;
+        uint32_t cell = pb.cell;
+        if (cell & ACC_PTR) {                                   // trees deeper than two stages (depth > 8)
+            const float s = __int_as_float((127 + a.lmax) << 23);
+            const int Ix = (int)(pb.px * s), Iy = (int)(pb.py * s), Iz = (int)(pb.pz * s);
+#pragma unroll
+            for (int st = 2; st < MAX_STAGES; ++st) {
+                if (cell & ACC_PTR) {
+                    const int b = a.bits[st], sh = a.shift[st], m = (1 << b) - 1;
+                    const uint32_t lin = (((((Ix >> sh) & m) << b) | ((Iy >> sh) & m)) << b) | ((Iz >> sh) & m);
+                    cell = __ldg(a.cells[st] + (((size_t)(cell & 0x7fffffffu)) << (3 * b)) + lin);
+                }
+            }
+        }
+        const int d = (int)(cell >> ACC_DEPTH_SHIFT) & 0xf;
+        const uint32_t ci = cell & ACC_IDX_MASK;
+        idx = (ci == ACC_EMPTY) ? -1 : (int)ci;
+        const float sc = __int_as_float((127 + d) << 23);
+        const float qx = pb.px * sc, qy = pb.py * sc, qz = pb.pz * sc;
+        rx = qx - floorf(qx); ry = qy - floorf(qy); rz = qz - floorf(qz);
+        dda_unit(rx, ry, rz, r.ix, r.iy, r.iz, smin, smax);
+        delta_t = (smax - smin) * __int_as_float((127 - d) << 23) + step;
+    } else {
+        float cube;
+        const int64_t slot = descend_ref(tr.child, tr.N, pb.px, pb.py, pb.pz, rx, ry, rz, cube);
+        const int di = __ldg(tr.data + slot);
+        idx = ((int64_t)di >= tr.M || di < 0) ? -1 : di;
+        dda_unit(rx, ry, rz, r.ix, r.iy, r.iz, smin, smax);
+        delta_t = (smax - smin) / cube + step;
+    }
+}
+
 // Host-side launch helpers shared by the scalar-lane and quad-lane kernels.
 template <typename Kern>
 static int persistent_grid(Kern kern, size_t smem, int64_t queue_len, int& grid) {

@@ -350,6 +350,286 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Software-pipelined variants for LPR <= 8 (D <= 32: all rows of a round fit one batch). Per loop iteration:
+//   S1  probe_begin : next sample position, top-grid lookup in shared memory, brick lookup ISSUED
+//   S2  composite   : the candidate found in the PREVIOUS iteration, whose rows were requested at the end of it
+//   S3  probe_end   : brick word consumed -> new candidate, t advanced
+//   S4  request rows of the new candidate (consumed in the next iteration's S2), flush finished rays, refill
+// so the brick lookup latency hides behind the compositing math and the row latency behind the next probe.
+template <int LPR, bool ACCEL, bool IMAGE>
+__global__ void __launch_bounds__(BLOCK, 2)
+march_fwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
+                      unsigned long long* counter) {
+    constexpr int RPI = 32 / LPR, NB = LPR;
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t* top = smem_u32;
+    if (ACCEL) load_top(tr, top);
+    const int lane = threadIdx.x & 31;
+    const int q = lane / LPR, c4 = lane % LPR;
+    const int D = tr.D, D4 = D >> 2;
+    const bool lane_ok = c4 < D4, is_sig = c4 == D4 - 1;
+    const int sig_src = (lane % RPI) * LPR + (D4 - 1);
+    const char* fbase = reinterpret_cast<const char*>(tr.features) + 16 * min(c4, D4 - 1);
+    const unsigned row_bytes = (unsigned)D * 4u;
+    const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
+    const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
+
+    float4 acc[LPR], x[NB];
+#pragma unroll
+    for (int j = 0; j < LPR; ++j) { acc[j] = make_float4(0.f, 0.f, 0.f, 0.f); x[j] = acc[j]; }
+
+    Ray ray;
+    float T = 1.0f, depth_v = 0.0f, p_dt = 0.0f, p_t = 0.0f;
+    int row = 0, p_idx = -1;
+    bool active = false, got_depth = false, trav_done = true;
+    Queue qu{0, 0, false};
+    unsigned need = FULL;
+
+    while (true) {
+        if (need) {
+            const unsigned got = refill<IMAGE>(src, off, scl, counter, qu, need, lane, ray, row);
+            if ((got >> lane) & 1u) { active = true; trav_done = false; T = 1.0f; got_depth = false; depth_v = 0.0f; }
+            need = 0;
+        }
+        if (__ballot_sync(FULL, active) == 0u) break;
+
+        // ---- S1 -------------------------------------------------------------------------------------------------
+        bool trav = active && !trav_done;
+        Probe pb;
+        if (trav) {
+            if (!(ray.t < ray.tmax)) { trav_done = true; trav = false; }
+            else probe_begin<ACCEL>(tr, top, ray, pb);
+        }
+
+        // ---- S2: composite the pending candidates -------------------------------------------------------------------
+        bool stopped = false;
+        if (__ballot_sync(FULL, p_idx >= 0)) {
+            float sig = 0.0f;
+#pragma unroll
+            for (int jj = 0; jj < NB; ++jj) {
+                const float v = __shfl_sync(FULL, x[jj].w, sig_src);
+                if (lane / RPI == jj) sig = v;
+            }
+            float w = 0.0f;
+            if (p_idx >= 0 && sig > opt.sigma_thresh) {
+                const float att = expf(-p_dt * ray.ds * sig);                         // rt_kernel.cu:280
+                w = T * (1.0f - att);
+                if (!got_depth) { depth_v = ray.ds * p_t; got_depth = true; }         // rt_kernel.cu:826-830
+                T *= att;
+                if (T <= opt.stop_thresh) stopped = true;                             // rt_kernel.cu:313
+            }
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const float w_j = __shfl_sync(FULL, w, RPI * j + q);
+                if (w_j != 0.0f) {
+                    const float4 s = sigmoid4(x[j]);
+                    acc[j].x = fmaf(w_j, s.x, acc[j].x);
+                    acc[j].y = fmaf(w_j, s.y, acc[j].y);
+                    acc[j].z = fmaf(w_j, s.z, acc[j].z);
+                    acc[j].w = fmaf(w_j, s.w, acc[j].w);
+                }
+            }
+        }
+
+        // ---- S3 -------------------------------------------------------------------------------------------------
+        p_idx = -1;
+        if (trav) {
+            p_t = ray.t;
+            probe_end<ACCEL>(tr, pb, ray, opt.step, p_idx, p_dt);
+            ray.t += p_dt;
+            if (!(ray.t < ray.tmax)) trav_done = true;
+        }
+        if (stopped) { p_idx = -1; trav_done = true; }
+        const int fin = (active && trav_done && p_idx < 0) ? (stopped ? 2 : 1) : 0;
+
+        // ---- S4: request the rows of the new candidates ---------------------------------------------------------------
+        if (__ballot_sync(FULL, p_idx >= 0)) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const int idx = max(__shfl_sync(FULL, p_idx, RPI * j + q), 0);        // row 0 stands in for "none"
+                x[j] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
+            }
+        }
+
+        const unsigned fm = __ballot_sync(FULL, fin != 0);
+        if (fm) {
+#pragma unroll
+            for (int j = 0; j < LPR; ++j) {
+                const unsigned gm = (fm >> (RPI * j)) & ((1u << RPI) - 1u);
+                if (gm) {
+                    const int r = RPI * j + q;
+                    const float T_r = __shfl_sync(FULL, T, r);
+                    const int fin_r = __shfl_sync(FULL, fin, r);
+                    const int row_r = __shfl_sync(FULL, row, r);
+                    if (fin_r != 0) {
+                        float4 v = acc[j];
+                        if (fin_r == 2) {
+                            const float scale = (float)(1.0 / (1.0 - (double)T_r));   // rt_kernel.cu:315
+                            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+                        } else {
+                            const float add = T_r * opt.bg;                           // rt_kernel.cu:323-325
+                            v.x += add; v.y += add; v.z += add; v.w += add;
+                        }
+                        if (is_sig) v.w = 1.0f - T_r;                                 // rt_kernel.cu:317,326
+                        if (lane_ok) *reinterpret_cast<float4*>(out + (int64_t)row_r * D + 4 * c4) = v;
+                        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+            if (fin != 0) {
+                if (depth) depth[row] = depth_v;
+                active = false;
+            }
+            need = fm;
+        }
+    }
+}
+
+template <int LPR, bool ACCEL, bool IMAGE>
+__global__ void __launch_bounds__(BLOCK, 2)
+march_bwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restrict__ grad_out,
+                      const float* __restrict__ saved_out, float* __restrict__ grad, unsigned long long* counter) {
+    constexpr int RPI = 32 / LPR, NB = LPR, DP = 4 * LPR;
+    extern __shared__ uint32_t smem_u32[];
+    const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
+    uint32_t* top = smem_u32;
+    if (ACCEL) load_top(tr, top);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* gs = reinterpret_cast<float*>(smem_u32 + top_words) + (size_t)warp * 32 * DP;   // [32 rays][DP]
+    const int q = lane / LPR, c4 = lane % LPR;
+    const int D = tr.D, D4 = D >> 2;
+    const bool lane_ok = c4 < D4, is_sig = c4 == D4 - 1;
+    const int sig_src = (lane % RPI) * LPR + (D4 - 1);
+    const int red_src = (lane % RPI) * LPR + (lane / RPI);
+    const char* fbase = reinterpret_cast<const char*>(tr.features) + 16 * min(c4, D4 - 1);
+    char* gbase = reinterpret_cast<char*>(grad) + 16 * c4;
+    const unsigned row_bytes = (unsigned)D * 4u;
+    const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
+    const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
+
+    float4 x[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    Ray ray;
+    float T = 1.0f, accum = 0.0f, T_end = 0.0f, gop = 0.0f, p_dt = 0.0f;
+    int row = 0, p_idx = -1;
+    bool active = false, trav_done = true;
+    Queue qu{0, 0, false};
+    unsigned need = FULL;
+
+    while (true) {
+        if (need) {
+            unsigned got = refill<IMAGE>(src, off, scl, counter, qu, need, lane, ray, row);
+            if ((got >> lane) & 1u) { active = true; trav_done = false; T = 1.0f; }
+            need = 0;
+            while (got) {       // per new ray: stage grad_out row, accum = <g, out>, T_end, g_opacity
+                const int r = __ffs(got) - 1;
+                got &= got - 1;
+                const int row_r = __shfl_sync(FULL, row, r);
+                const float* g = grad_out + (int64_t)row_r * D;
+                const float* so = saved_out + (int64_t)row_r * D;
+                float part = 0.0f, g_last = 0.0f, o_last = 0.0f;
+                for (int c = lane; c < DP; c += 32) {
+                    const float gv = (c < D) ? __ldg(g + c) : 0.0f;
+                    const float ov = (c < D) ? __ldg(so + c) : 0.0f;
+                    gs[r * DP + c] = gv;
+                    if (c < D - 1) part = fmaf(gv, ov, part);
+                    if (c == D - 1) { g_last = gv; o_last = ov; }
+                }
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(FULL, part, s);
+                g_last = __shfl_sync(FULL, g_last, (D - 1) & 31);
+                o_last = __shfl_sync(FULL, o_last, (D - 1) & 31);
+                if (lane == r) { accum = part; T_end = 1.0f - o_last; gop = g_last; }
+            }
+            __syncwarp();
+        }
+        if (__ballot_sync(FULL, active) == 0u) break;
+
+        // ---- S1 -------------------------------------------------------------------------------------------------
+        bool trav = active && !trav_done;
+        Probe pb;
+        if (trav) {
+            if (!(ray.t < ray.tmax)) { trav_done = true; trav = false; }
+            else probe_begin<ACCEL>(tr, top, ray, pb);
+        }
+
+        // ---- S2: gradient of the pending candidates ------------------------------------------------------------------
+        if (__ballot_sync(FULL, p_idx >= 0)) {
+            float sig = 0.0f;
+#pragma unroll
+            for (int jj = 0; jj < NB; ++jj) {
+                const float v = __shfl_sync(FULL, x[jj].w, sig_src);
+                if (lane / RPI == jj) sig = v;
+            }
+            float w = 0.0f, dd = 0.0f;
+            const bool hit = p_idx >= 0 && sig > 0.0f;                              // rt_kernel.cu:382,456
+            if (hit) {
+                const float att = expf(-p_dt * sig * ray.ds);
+                w = T * (1.0f - att);
+                dd = p_dt * ray.ds;
+                T *= att;
+            }
+            const unsigned hb = __ballot_sync(FULL, hit);
+            if (hb) {
+                float cp[NB];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    const int r = RPI * j + q;
+                    const bool on = ((hb >> r) & 1u) && lane_ok;
+                    const float4 g4 = *reinterpret_cast<const float4*>(gs + r * DP + 4 * c4);
+                    const float4 s = sigmoid4(x[j]);
+                    const float sx = s.x * g4.x, sy = s.y * g4.y, sz = s.z * g4.z, sw = s.w * g4.w;
+                    cp[j] = on ? (sx + sy) + (sz + (is_sig ? 0.0f : sw)) : 0.0f;
+                    x[j] = make_float4(sx * (1.0f - s.x), sy * (1.0f - s.y), sz * (1.0f - s.z), sw * (1.0f - s.w));
+                }
+                const float c_tot = quad_reduce<NB, LPR>(cp, lane);
+                const float c_own = __shfl_sync(FULL, c_tot, red_src);
+                float sgrad = 0.0f;
+                if (hit) {
+                    accum -= w * c_own;                                              // rt_kernel.cu:479-480
+                    sgrad = dd * (c_own * T - accum) + dd * gop * T_end;             // rt_kernel.cu:486-490
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    const int r = RPI * j + q;
+                    const float w_j = __shfl_sync(FULL, w, r);
+                    const float sg_j = __shfl_sync(FULL, sgrad, r);
+                    const int idx_j = __shfl_sync(FULL, p_idx, r);
+                    if (((hb >> r) & 1u) && lane_ok) {
+                        float* grow = reinterpret_cast<float*>(gbase + (size_t)(unsigned)idx_j * row_bytes);
+                        red_add_v4(grow, w_j * x[j].x, w_j * x[j].y, w_j * x[j].z, is_sig ? sg_j : w_j * x[j].w);
+                    }
+                }
+            }
+        }
+
+        // ---- S3 -------------------------------------------------------------------------------------------------
+        p_idx = -1;
+        if (trav) {
+            probe_end<ACCEL>(tr, pb, ray, opt.step, p_idx, p_dt);
+            ray.t += p_dt;
+            if (!(ray.t < ray.tmax)) trav_done = true;
+        }
+        const bool fin = active && trav_done && p_idx < 0;
+
+        // ---- S4 -------------------------------------------------------------------------------------------------
+        if (__ballot_sync(FULL, p_idx >= 0)) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const int idx = max(__shfl_sync(FULL, p_idx, RPI * j + q), 0);
+                x[j] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
+            }
+        }
+        const unsigned fm = __ballot_sync(FULL, fin);
+        if (fm) {
+            if (fin) active = false;
+            need = fm;
+        }
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 bool quad_supported(int D) { return D % 4 == 0 && D > 8 && D <= 128; }
 
@@ -363,7 +643,9 @@ template <int LPR, bool ACCEL, bool IMAGE>
 static int launch_fwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
     const size_t smem = ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0;
-    auto kern = march_fwd_quad_kernel<LPR, ACCEL, IMAGE>;
+    void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
+    if constexpr (LPR <= 8) kern = march_fwd_pipe_kernel<LPR, ACCEL, IMAGE>;
+    else kern = march_fwd_quad_kernel<LPR, ACCEL, IMAGE>;
     int grid = 0;
     int rc = persistent_grid(kern, smem, src.total, grid);
     if (rc) return rc;
@@ -378,7 +660,9 @@ template <int LPR, bool ACCEL, bool IMAGE>
 static int launch_bwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const float* go, const float* so,
                         float* grad, cudaStream_t st) {
     const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * WARPS * 32 * 4 * LPR;
-    auto kern = march_bwd_quad_kernel<LPR, ACCEL, IMAGE>;
+    void (*kern)(TreeArgs, RaySource, MarchOpts, const float*, const float*, float*, unsigned long long*);
+    if constexpr (LPR <= 8) kern = march_bwd_pipe_kernel<LPR, ACCEL, IMAGE>;
+    else kern = march_bwd_quad_kernel<LPR, ACCEL, IMAGE>;
     int grid = 0;
     int rc = persistent_grid(kern, smem, src.total, grid);
     if (rc) return rc;
