@@ -358,14 +358,23 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
 //   S4  request rows of the new candidate (consumed in the next iteration's S2), flush finished rays, refill
 // so the brick lookup latency hides behind the compositing math and the row latency behind the next probe.
 template <int LPR, bool ACCEL, bool IMAGE>
-__global__ void __launch_bounds__(BLOCK, 2)
+#ifndef SVOXB_FWD_MINB
+#define SVOXB_FWD_MINB 2
+#endif
+#ifndef SVOXB_BWD_MINB
+#define SVOXB_BWD_MINB 2
+#endif
+__global__ void __launch_bounds__(BLOCK, SVOXB_FWD_MINB)
 march_fwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
                       unsigned long long* counter) {
     constexpr int RPI = 32 / LPR, NB = LPR;
     extern __shared__ uint32_t smem_u32[];
     uint32_t* top = smem_u32;
+    const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31;
+    // this warp's 32 x D partial outputs live in shared memory: accs[j * 32 + lane] = float4 of ray RPI*j + q
+    float4* accs = reinterpret_cast<float4*>(smem_u32 + top_words) + (size_t)(threadIdx.x >> 5) * 32 * LPR + lane;
     const int q = lane / LPR, c4 = lane % LPR;
     const int D = tr.D, D4 = D >> 2;
     const bool lane_ok = c4 < D4, is_sig = c4 == D4 - 1;
@@ -375,9 +384,9 @@ march_fwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
     const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
 
-    float4 acc[LPR], x[NB];
+    float4 x[NB];
 #pragma unroll
-    for (int j = 0; j < LPR; ++j) { acc[j] = make_float4(0.f, 0.f, 0.f, 0.f); x[j] = acc[j]; }
+    for (int j = 0; j < LPR; ++j) { x[j] = make_float4(0.f, 0.f, 0.f, 0.f); accs[j * 32] = x[j]; }
 
     Ray ray;
     float T = 1.0f, depth_v = 0.0f, p_dt = 0.0f, p_t = 0.0f;
@@ -424,10 +433,12 @@ march_fwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                 const float w_j = __shfl_sync(FULL, w, RPI * j + q);
                 if (w_j != 0.0f) {
                     const float4 s = sigmoid4(x[j]);
-                    acc[j].x = fmaf(w_j, s.x, acc[j].x);
-                    acc[j].y = fmaf(w_j, s.y, acc[j].y);
-                    acc[j].z = fmaf(w_j, s.z, acc[j].z);
-                    acc[j].w = fmaf(w_j, s.w, acc[j].w);
+                    float4 a = accs[j * 32];
+                    a.x = fmaf(w_j, s.x, a.x);
+                    a.y = fmaf(w_j, s.y, a.y);
+                    a.z = fmaf(w_j, s.z, a.z);
+                    a.w = fmaf(w_j, s.w, a.w);
+                    accs[j * 32] = a;
                 }
             }
         }
@@ -444,12 +455,11 @@ march_fwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
         const int fin = (active && trav_done && p_idx < 0) ? (stopped ? 2 : 1) : 0;
 
         // ---- S4: request the rows of the new candidates ---------------------------------------------------------------
-        if (__ballot_sync(FULL, p_idx >= 0)) {
+        // unconditional on purpose: a guarded load turns x into a phi and the register copies stall on the data
 #pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                const int idx = max(__shfl_sync(FULL, p_idx, RPI * j + q), 0);        // row 0 stands in for "none"
-                x[j] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
-            }
+        for (int j = 0; j < NB; ++j) {
+            const int idx = max(__shfl_sync(FULL, p_idx, RPI * j + q), 0);            // row 0 stands in for "none"
+            x[j] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
         }
 
         const unsigned fm = __ballot_sync(FULL, fin != 0);
@@ -463,7 +473,7 @@ march_fwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                     const int fin_r = __shfl_sync(FULL, fin, r);
                     const int row_r = __shfl_sync(FULL, row, r);
                     if (fin_r != 0) {
-                        float4 v = acc[j];
+                        float4 v = accs[j * 32];
                         if (fin_r == 2) {
                             const float scale = (float)(1.0 / (1.0 - (double)T_r));   // rt_kernel.cu:315
                             v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
@@ -473,7 +483,7 @@ march_fwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                         }
                         if (is_sig) v.w = 1.0f - T_r;                                 // rt_kernel.cu:317,326
                         if (lane_ok) *reinterpret_cast<float4*>(out + (int64_t)row_r * D + 4 * c4) = v;
-                        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        accs[j * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
             }
@@ -487,7 +497,7 @@ march_fwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
 }
 
 template <int LPR, bool ACCEL, bool IMAGE>
-__global__ void __launch_bounds__(BLOCK, 2)
+__global__ void __launch_bounds__(BLOCK, SVOXB_BWD_MINB)
 march_bwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restrict__ grad_out,
                       const float* __restrict__ saved_out, float* __restrict__ grad, unsigned long long* counter) {
     constexpr int RPI = 32 / LPR, NB = LPR, DP = 4 * LPR;
@@ -615,12 +625,11 @@ march_bwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
         const bool fin = active && trav_done && p_idx < 0;
 
         // ---- S4 -------------------------------------------------------------------------------------------------
-        if (__ballot_sync(FULL, p_idx >= 0)) {
+        // unconditional on purpose: a guarded load turns x into a phi and the register copies stall on the data
 #pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                const int idx = max(__shfl_sync(FULL, p_idx, RPI * j + q), 0);
-                x[j] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
-            }
+        for (int j = 0; j < NB; ++j) {
+            const int idx = max(__shfl_sync(FULL, p_idx, RPI * j + q), 0);            // row 0 stands in for "none"
+            x[j] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
         }
         const unsigned fm = __ballot_sync(FULL, fin);
         if (fm) {
@@ -642,7 +651,8 @@ static int lpr_for(int D) {
 template <int LPR, bool ACCEL, bool IMAGE>
 static int launch_fwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
-    const size_t smem = ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0;
+    size_t smem = ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0;
+    if (LPR <= 8) smem += sizeof(float4) * WARPS * 32 * LPR;          // pipelined kernel: accumulators in smem
     void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
     if constexpr (LPR <= 8) kern = march_fwd_pipe_kernel<LPR, ACCEL, IMAGE>;
     else kern = march_fwd_quad_kernel<LPR, ACCEL, IMAGE>;

@@ -88,13 +88,23 @@ namespace svoxb {
 
 int make_tree_args(const svoxb_tree* t, TreeArgs& a) {
     SVOXB_REQUIRE(t != nullptr, "tree is NULL");
-    SVOXB_REQUIRE(t->features && t->child && t->data && t->offset && t->scaling, "tree has NULL tensors");
+    SVOXB_REQUIRE((t->features || t->M == 0) && t->child && t->data && t->offset && t->scaling, "tree has NULL tensors");
     SVOXB_REQUIRE(t->N >= 2 && t->N <= 16, "branching factor N=%d out of range [2,16]", t->N);
     SVOXB_REQUIRE(t->D >= 2, "feature width D=%d must be >= 2 (payload + sigma)", t->D);
     SVOXB_REQUIRE(t->M >= 0 && t->M < (1ll << 31), "M=%lld out of range", (long long)t->M);
     SVOXB_REQUIRE(t->n_internal >= 1 && t->n_internal <= t->n_nodes, "n_internal=%lld out of range",
                   (long long)t->n_internal);
-    a.features = t->features; a.M = t->M; a.D = t->D; a.N = t->N;
+    a.features = t->features; a.M = t->M;
+    if (t->M == 0) {                       // no rows at all: the kernels still prefetch "row 0" -> point at zeros
+        static float* dummy[64] = {nullptr};
+        int dev = 0;
+        SVOXB_CUDA(cudaGetDevice(&dev));
+        if (!dummy[dev & 63]) {
+            SVOXB_CUDA(cudaMalloc(&dummy[dev & 63], 2048));
+            SVOXB_CUDA(cudaMemset(dummy[dev & 63], 0, 2048));
+        }
+        a.features = dummy[dev & 63];
+    } a.D = t->D; a.N = t->N;
     a.child = t->child; a.data = t->data; a.offset = t->offset; a.scaling = t->scaling;
     a.use_accel = 0;
     memset(&a.acc, 0, sizeof(a.acc));
