@@ -32,10 +32,12 @@ struct Ray {
 // rt_kernel.cu:663-665 (transform_coord, one FFMA per axis) + 227-247 (delta scale, invdir in double, slab test).
 __device__ __forceinline__ void ray_setup(const float* __restrict__ off, const float* __restrict__ scl,
                                           float owx, float owy, float owz, float dwx, float dwy, float dwz, Ray& r) {
-    r.ox = fmaf(scl[0], owx, off[0]);
-    r.oy = fmaf(scl[1], owy, off[1]);
-    r.oz = fmaf(scl[2], owz, off[2]);
-    float dx = dwx * scl[0], dy = dwy * scl[1], dz = dwz * scl[2];
+    // offset / scaling are read here (L1-resident, once per ray) rather than held in registers by every lane
+    const float s0 = __ldg(scl), s1 = __ldg(scl + 1), s2 = __ldg(scl + 2);
+    r.ox = fmaf(s0, owx, __ldg(off));
+    r.oy = fmaf(s1, owy, __ldg(off + 1));
+    r.oz = fmaf(s2, owz, __ldg(off + 2));
+    float dx = dwx * s0, dy = dwy * s1, dz = dwz * s2;
     const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
     r.ds = 1.0f / nrm;
     dx *= r.ds; dy *= r.ds; dz *= r.ds;
@@ -65,7 +67,7 @@ __device__ __forceinline__ void camera_ray(const RaySource& s, int px, int py,
 
 // Per-warp view of the global ray queue.
 struct Queue {
-    int64_t next, end;
+    int next, end;          // queue positions fit 31 bits (checked on the host)
     bool exhausted;
 };
 
@@ -83,15 +85,15 @@ __device__ __forceinline__ unsigned refill(const RaySource& src, const float* of
             if (lane == 0) base = atomicAdd(counter, (unsigned long long)CHUNK);
             base = __shfl_sync(FULL, base, 0);
             if ((int64_t)base >= src.total) { q.exhausted = true; break; }
-            q.next = (int64_t)base;
-            q.end = min((int64_t)base + CHUNK, src.total);
+            q.next = (int)base;
+            q.end = (int)min((int64_t)base + CHUNK, src.total);
         }
-        const int avail = (int)(q.end - q.next);
+        const int avail = q.end - q.next;
         const int rank = __popc(need & ((1u << lane) - 1u));
         const bool take = ((need >> lane) & 1u) && rank < avail;
         bool valid = false;
         if (take) {
-            const int64_t id = q.next + rank;
+            const int id = q.next + rank;
             float ox, oy, oz, dx, dy, dz;
             if (IMAGE) {
                 const int tile = (int)(id >> 6), in = (int)(id & 63);
@@ -104,11 +106,11 @@ __device__ __forceinline__ unsigned refill(const RaySource& src, const float* of
                 }
             } else {
                 valid = true;
-                const float* o = src.origins + id * 3;
-                const float* d = src.dirs + id * 3;
+                const float* o = src.origins + (int64_t)id * 3;
+                const float* d = src.dirs + (int64_t)id * 3;
                 ox = __ldg(o); oy = __ldg(o + 1); oz = __ldg(o + 2);
                 dx = __ldg(d); dy = __ldg(d + 1); dz = __ldg(d + 2);
-                row = (int)id;
+                row = id;
             }
             if (valid) ray_setup(off, scl, ox, oy, oz, dx, dy, dz, ray);
         }

@@ -36,8 +36,8 @@ march_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ 
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31;
     const int D = tr.D;
-    const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
-    const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
+    const float* off = tr.offset;
+    const float* scl = tr.scaling;
 
     const char* fbase = reinterpret_cast<const char*>(tr.features + lane);
     const unsigned row_bytes = (unsigned)D * 4u;
@@ -165,8 +165,8 @@ march_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restr
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* gs = gs_all + (size_t)warp * 32 * (32 * K);
     const int D = tr.D;
-    const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
-    const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
+    const float* off = tr.offset;
+    const float* scl = tr.scaling;
 
     const char* fbase = reinterpret_cast<const char*>(tr.features + lane);
     char* gbase = reinterpret_cast<char*>(grad + lane);
@@ -338,8 +338,8 @@ depth_kernel(TreeArgs tr, const float* __restrict__ origins, const float* __rest
     extern __shared__ uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     if (ACCEL) load_top(tr, top);
-    const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
-    const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
+    const float* off = tr.offset;
+    const float* scl = tr.scaling;
     for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < Q; id += (int64_t)gridDim.x * blockDim.x) {
         Ray ray;
         ray_setup(off, scl, __ldg(origins + 3 * id), __ldg(origins + 3 * id + 1), __ldg(origins + 3 * id + 2),

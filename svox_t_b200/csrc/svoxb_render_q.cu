@@ -86,8 +86,8 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     const int sig_src = (lane % RPI) * LPR + (D4 - 1);   // lane that holds sigma of this owner lane's row
     const char* fbase = reinterpret_cast<const char*>(tr.features) + 16 * c4;
     const unsigned row_bytes = (unsigned)D * 4u;
-    const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
-    const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
+    const float* off = tr.offset;
+    const float* scl = tr.scaling;
 
     float4 acc[LPR];
 #pragma unroll
@@ -223,8 +223,8 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
     const char* fbase = reinterpret_cast<const char*>(tr.features) + 16 * c4;
     char* gbase = reinterpret_cast<char*>(grad) + 16 * c4;
     const unsigned row_bytes = (unsigned)D * 4u;
-    const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
-    const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
+    const float* off = tr.offset;
+    const float* scl = tr.scaling;
 
     Ray ray;
     float T = 1.0f, accum = 0.0f, T_end = 0.0f, gop = 0.0f;
@@ -381,8 +381,8 @@ march_fwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     const int sig_src = (lane % RPI) * LPR + (D4 - 1);
     const char* fbase = reinterpret_cast<const char*>(tr.features) + 16 * min(c4, D4 - 1);
     const unsigned row_bytes = (unsigned)D * 4u;
-    const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
-    const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
+    const float* off = tr.offset;
+    const float* scl = tr.scaling;
 
     float4 x[NB];
 #pragma unroll
@@ -515,8 +515,8 @@ march_bwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
     const char* fbase = reinterpret_cast<const char*>(tr.features) + 16 * min(c4, D4 - 1);
     char* gbase = reinterpret_cast<char*>(grad) + 16 * c4;
     const unsigned row_bytes = (unsigned)D * 4u;
-    const float off[3] = {__ldg(tr.offset), __ldg(tr.offset + 1), __ldg(tr.offset + 2)};
-    const float scl[3] = {__ldg(tr.scaling), __ldg(tr.scaling + 1), __ldg(tr.scaling + 2)};
+    const float* off = tr.offset;
+    const float* scl = tr.scaling;
 
     float4 x[NB];
 #pragma unroll
