@@ -26,6 +26,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's banner / debug output on stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 
@@ -111,6 +113,13 @@ def scene_numpy(seed_rays):
     return tr, f, o, d
 
 
+def host_threads():
+    """The CPU legs use every host core; torchrun injects OMP_NUM_THREADS=1, which would silently serialise them."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
+
+
 def cpu_port_step(T, f, o, d, g, orc):
     """One fwd+bwd of the CPU oracle on a ray sample; returns (seconds, counters)."""
     t0 = time.perf_counter()
@@ -124,6 +133,7 @@ def run_reference_arm(args):
     path and its CUDA extension is not a CPU baseline). Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    cores = host_threads()
     from oracle import oracle as orc
     tr, f, o, d = scene_numpy(1)
     T = orc.Tree(tr["child"], tr["data"])
@@ -138,7 +148,6 @@ def run_reference_arm(args):
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     val = n / (ms * 1e-3) / 1e6
-    cores = os.cpu_count()
     sample = f"each step = fwd+bwd of a {n}-ray slice of the 2^20-ray batch (C oracle, OpenMP over rays)"
     print(json.dumps({
         "impl": "reference", "metric": "Mrays/s fwd+bwd feature render", "value": val, "unit": "Mrays/s",
@@ -260,12 +269,13 @@ def main():
     if rank != 0:
         return
     # ---- CPU baseline + counters (rank 0, bounded sample) ---------------------------------------------------------------
+    cores = host_threads()
     from oracle import oracle as orc
     T = orc.Tree(tr["child"], tr["data"])
     n = CPU_SAMPLE
     g_np = np.random.default_rng(5).standard_normal((n, D)).astype(np.float32)
     cpu_s, cnt = cpu_port_step(T, f, o[:n], d[:n], g_np, orc)
-    cpu_baseline = {"value": n / cpu_s / 1e6, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port",
+    cpu_baseline = {"value": n / cpu_s / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                     "sample": f"first {n} of the 2^20 rays, fwd+bwd once, C oracle with OpenMP over rays ({cpu_s:.2f} s)"}
     scale = Q / cnt["Q"]
     cnt_full = {k: (v * scale if k != "Q" else Q) for k, v in cnt.items()}
