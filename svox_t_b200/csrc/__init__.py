@@ -451,6 +451,32 @@ def p2v(points, point_features, volume_corner, volume_size, n_voxels, kernel_rad
     return vox
 
 
+def build_octree(points, depth, offset, scaling):
+    """One-shot octree of finest level ``depth`` whose leaves at that level are the cells occupied by ``points``
+    (svox_t_b200 extension; replaces depth-1 rounds of tree[pts].refine() + construct_tree, svox.py:488-560).
+    Returns (child[n,2,2,2], data[n,2,2,2,1], parent_depth[n,2]) int32, reference format; data = point index."""
+    lib = load_library()
+    _check_input(points, "points", torch.float32)
+    _check_input(offset, "offset", torch.float32)
+    _check_input(scaling, "scaling", torch.float32)
+    P, dev = points.shape[0], points.device
+    with torch.cuda.device(dev):
+        nbytes = lib.svoxb_build_work_bytes(P, int(depth))
+        if nbytes == 0:
+            raise RuntimeError("svox_t_b200.csrc.build_octree: depth/point count out of range")
+        work = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        n = ctypes.c_int64(0)
+        _check(lib.svoxb_build_octree_count(_ptr(points), P, int(depth), _ptr(offset), _ptr(scaling), _ptr(work),
+                                            ctypes.byref(n), _stream()))
+        n = int(n.value)
+        child = torch.empty((n, 2, 2, 2), dtype=torch.int32, device=dev)
+        data = torch.empty((n, 2, 2, 2, 1), dtype=torch.int32, device=dev)
+        parent_depth = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        _check(lib.svoxb_build_octree_emit(P, int(depth), _ptr(work), n, _ptr(child), _ptr(data), _ptr(parent_depth),
+                                           _stream()))
+    return child, data, parent_depth
+
+
 def _unsupported(name, why):
     def f(*a, **k):
         raise RuntimeError(f"svox_t_b200.csrc.{name} is not implemented: {why}")

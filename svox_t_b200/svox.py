@@ -122,6 +122,22 @@ class N3Tree(nn.Module):
         tree._invalidate()
         return tree
 
+    def build_from_points(self, points, depth):
+        """Rebuild the whole tree in one shot: finest level ``depth``, one depth-``depth`` leaf per occupied cell,
+        leaf row = index of the (last) point inside it. Equivalent to (depth-1) x ``tree[points].refine()`` followed by
+        ``construct_tree(points)`` (the per-frame rebuild of svox.py:160-161,488-560), isomorphic result."""
+        assert self.N == 2, "the one-shot builder is octree-only"
+        if self._lock_tree_structure:
+            raise RuntimeError("Tree locked")
+        if depth - 1 > self.depth_limit:
+            raise RuntimeError("depth exceeds depth_limit")
+        child, data, parent_depth = _C.build_octree(points, depth, self.offset, self.invradius)
+        self.child, self.data, self.parent_depth = child, data, parent_depth
+        self.filled = int(child.shape[0])
+        self._n_internal.fill_(self.filled)
+        self._invalidate()
+        return self
+
     def construct_tree(self, indices):
         """data[leaf(p_i)] = i: point i becomes the feature row of its leaf (svox.py:160-161)."""
         _C.construct_tree(self._spec(self.features), indices)

@@ -201,6 +201,40 @@ def test_refine_by_points_then_construct_tree(dev):
     assert frac_within(out.cpu().numpy(), orc.render_rays(T, f, o, d)[0]) >= 0.999
 
 
+@pytest.mark.parametrize("L", [1, 3, 6])
+def test_one_shot_builder_is_isomorphic_to_refine_loop(dev, L):
+    rng = np.random.default_rng(2)
+    vox = synth._occupied_keys(L, "ball", r_out=0.45 if L < 4 else 0.30)
+    centers = synth.voxel_centers(vox, L)
+    # several points per voxel, jittered inside it, shuffled
+    pts = np.repeat(centers, 3, axis=0) + (rng.random((3 * len(centers), 3)).astype(np.float32) - 0.5) * (0.6 / (1 << L))
+    pts = pts[rng.permutation(len(pts))].astype(np.float32)
+    p = cu(pts, dev)
+    a = sv.N3Tree(N=2, data_dim=4, map_location=dev).build_from_points(p, L)
+    b = sv.N3Tree(N=2, data_dim=4, init_reserve=64, map_location=dev)
+    for _ in range(L - 1):
+        b[p].refine()
+    b.construct_tree(p)
+    assert a.filled == b.filled and a.n_leaves == b.n_leaves and a.max_depth == b.max_depth == L - 1
+    # structural invariants of the emitted tensors
+    ch, pd = a.child.reshape(-1, 8).cpu().numpy(), a.parent_depth.cpu().numpy()
+    node, slot = np.nonzero(ch)
+    kid = node + ch[node, slot]
+    assert sorted(kid.tolist()) == list(range(1, a.filled))
+    assert (pd[kid, 0] == node * 8 + slot).all() and (pd[kid, 1] == pd[node, 1] + 1).all()
+    # same point -> leaf-row map (largest point index of the voxel) and same geometry at arbitrary query points
+    f = torch.zeros(len(pts), 4, device=dev)
+    _, _, ida = a(f, p, want_node_ids=True, want_data_ids=True)
+    _, _, idb = b(f, p, want_node_ids=True, want_data_ids=True)
+    assert torch.equal(ida, idb)
+    qp = torch.rand(20000, 3, device=dev)
+    _, _, qa = a(f, qp, want_node_ids=True, want_data_ids=True)
+    _, _, qb = b(f, qp, want_node_ids=True, want_data_ids=True)
+    assert torch.equal(qa, qb)
+    T = orc.Tree(a.child.cpu().numpy(), a.data.cpu().numpy())
+    assert (orc.query(T, np.zeros((len(pts), 4), np.float32), pts)[2] == ida.cpu().numpy()).all()
+
+
 def test_warp_vertices_and_p2v_vs_oracle(dev):
     P = 5000
     rng = np.random.default_rng(2)
