@@ -94,7 +94,9 @@ SVOXB_API int64_t svoxb_launch_count(void);            /* number of kernels this
 SVOXB_API int svoxb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* ---- acceleration structure (no reference counterpart; derived data, rebuilt when child/data change) */
-/* max_depth <= 0: derive it from parent_depth (must then be non-NULL). Synchronises the stream. */
+/* max_depth <= 0: derive it from parent_depth (must then be non-NULL). Synchronises the stream (one small read-back
+ * per stage). Memory comes from the device's default stream-ordered pool on `stream`; svoxb_accel_destroy releases it
+ * in stream order on that same stream, so work reading the accelerator on OTHER streams must have completed. */
 SVOXB_API int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* stream, svoxb_accel** out);
 SVOXB_API void svoxb_accel_destroy(svoxb_accel* accel);
 SVOXB_API int64_t svoxb_accel_bytes(const svoxb_accel* accel);

@@ -37,48 +37,44 @@ warp_vertices_kernel(const float* __restrict__ T, const float* __restrict__ coor
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// One warp serves 32 points; for each point the lanes sweep the footprint voxels (z fastest, so the atomics of a
-// warp fall on consecutive addresses). The reference walks the footprint serially in one thread per point.
+// Eight threads per point, one per x-slice of the footprint (the footprint of the reference's configurations is
+// at most 6 cells per axis; wider ones loop). The Gaussian is separable, exp(-r^2/2k^2) = ex*ey*ez, so a thread
+// evaluates ~13 exponentials instead of one per cell; the cutoff r <= conv_radius is the reference's own test.
+// The reference walks the whole footprint serially in one thread per point with an expf per cell.
 __global__ void __launch_bounds__(256)
 p2v_kernel(const float* __restrict__ points, const float* __restrict__ feat, int64_t P, int F,
            const float* __restrict__ corner, const float* __restrict__ size, int n, float kr, float cr,
            float* __restrict__ voxels) {
-    const int lane = threadIdx.x & 31;
     const float c0 = __ldg(corner), c1 = __ldg(corner + 1), c2 = __ldg(corner + 2);
     const float vs0 = __ldg(size) / (float)(n - 1), vs1 = __ldg(size + 1) / (float)(n - 1),
                 vs2 = __ldg(size + 2) / (float)(n - 1);
-    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    for (int64_t base = warp_id * 32; base < P; base += warps_total * 32) {
-        const int64_t p = base + lane;
-        float x = 0.f, y = 0.f, z = 0.f, sg = 0.f;
-        int lx = 0, hx = -1, ly = 0, hy = -1, lz = 0, hz = -1;
-        if (p < P) {
-            x = __ldg(points + 3 * p); y = __ldg(points + 3 * p + 1); z = __ldg(points + 3 * p + 2);
-            sg = __ldg(feat + p * F + (F - 1));
-            lx = clampi((int)floorf((x - cr - c0) / vs0), 0, n - 1); hx = clampi((int)ceilf((x + cr - c0) / vs0), 0, n - 1);
-            ly = clampi((int)floorf((y - cr - c1) / vs1), 0, n - 1); hy = clampi((int)ceilf((y + cr - c1) / vs1), 0, n - 1);
-            lz = clampi((int)floorf((z - cr - c2) / vs2), 0, n - 1); hz = clampi((int)ceilf((z + cr - c2) / vs2), 0, n - 1);
-        }
-        const int np = (int)min((int64_t)32, P - base);
-        for (int r = 0; r < np; ++r) {
-            const float px = __shfl_sync(FULL, x, r), py = __shfl_sync(FULL, y, r), pz = __shfl_sync(FULL, z, r);
-            const float ps = __shfl_sync(FULL, sg, r);
-            const int ax = __shfl_sync(FULL, lx, r), bx = __shfl_sync(FULL, hx, r);
-            const int ay = __shfl_sync(FULL, ly, r), by = __shfl_sync(FULL, hy, r);
-            const int az = __shfl_sync(FULL, lz, r), bz = __shfl_sync(FULL, hz, r);
-            const int nx = bx - ax + 1, ny = by - ay + 1, nz = bz - az + 1;
-            const int total = nx * ny * nz;
-            for (int i = lane; i < total; i += 32) {
-                const int kz = i % nz, ky = (i / nz) % ny, kx = i / (nz * ny);
-                const int vx = ax + kx, vy = ay + ky, vz = az + kz;
-                const float dx = px - ((float)vx * vs0 + c0);
-                const float dy = py - ((float)vy * vs1 + c1);
-                const float dz = pz - ((float)vz * vs2 + c2);
-                const float rr = sqrtf(dx * dx + dy * dy + dz * dz);
-                if (rr <= cr) {
-                    const float wgt = expf(-rr * rr / (2 * kr * kr));
-                    atomicAdd(voxels + ((int64_t)vx * n + vy) * n + vz, wgt * ps);
+    const float inv2k = 1.0f / (2 * kr * kr);
+    const float cr2 = cr * cr * 1.0001f;          // slack: the early-outs must never drop a cell the exact test keeps
+    for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < P * 8;
+         gid += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = gid >> 3;
+        const int xi = (int)(gid & 7);
+        const float x = __ldg(points + 3 * p), y = __ldg(points + 3 * p + 1), z = __ldg(points + 3 * p + 2);
+        const float sg = __ldg(feat + p * F + (F - 1));
+        const int lx = clampi((int)floorf((x - cr - c0) / vs0), 0, n - 1), hx = clampi((int)ceilf((x + cr - c0) / vs0), 0, n - 1);
+        const int ly = clampi((int)floorf((y - cr - c1) / vs1), 0, n - 1), hy = clampi((int)ceilf((y + cr - c1) / vs1), 0, n - 1);
+        const int lz = clampi((int)floorf((z - cr - c2) / vs2), 0, n - 1), hz = clampi((int)ceilf((z + cr - c2) / vs2), 0, n - 1);
+        for (int vx = lx + xi; vx <= hx; vx += 8) {
+            const float dx = x - ((float)vx * vs0 + c0);
+            const float dx2 = dx * dx;
+            if (dx2 > cr2) continue;
+            const float ex = expf(-dx2 * inv2k) * sg;
+            for (int vy = ly; vy <= hy; ++vy) {
+                const float dy = y - ((float)vy * vs1 + c1);
+                const float dxy2 = dx2 + dy * dy;
+                if (dxy2 > cr2) continue;
+                const float exy = ex * expf(-(dy * dy) * inv2k);
+                float* rowp = voxels + ((int64_t)vx * n + vy) * n;
+                for (int vz = lz; vz <= hz; ++vz) {
+                    const float dz = z - ((float)vz * vs2 + c2);
+                    // the cutoff exactly as the reference states it (p2v_kernel.cu:137-139): r = sqrt(...) <= conv_radius
+                    const float r = sqrtf(dx * dx + dy * dy + dz * dz);
+                    if (r <= cr) atomicAdd(rowp + vz, exy * expf(-(dz * dz) * inv2k));
                 }
             }
         }
@@ -110,7 +106,7 @@ extern "C" int svoxb_p2v(const float* points, const float* point_features, int64
     cudaStream_t st = (cudaStream_t)stream;
     SVOXB_CUDA(cudaMemsetAsync(voxels, 0, sizeof(float) * (size_t)n_voxels * n_voxels * n_voxels, st));
     if (P == 0) return 0;
-    const int grid = (int)min((P + 255) / 256, (int64_t)sm_count() * 8);
+    const int grid = (int)min((P * 8 + 255) / 256, (int64_t)sm_count() * 32);
     p2v_kernel<<<grid, 256, 0, st>>>(points, point_features, P, F, corner, size, n_voxels, kernel_radius,
                                      conv_radius, voxels);
     count_launch();

@@ -82,6 +82,7 @@ struct svoxb_accel {
     int64_t M;
     const int32_t* child;   // identity of the tensors it was built from (sanity check only)
     const int32_t* data;
+    cudaStream_t stream;    // creation stream: the stream-ordered allocations are released on it
 };
 
 namespace svoxb {
@@ -349,10 +350,34 @@ extern "C" int svoxb_device_info(int* sm, int* major, int* minor) {
     return 0;
 }
 
+// Stream-ordered allocation from the device's default pool, which is told to keep its memory: per-frame rebuilds
+// then recycle the same blocks instead of paying cudaMalloc/cudaFree (and their device-wide syncs) every frame.
+static int pool_alloc(void** p, size_t bytes, cudaStream_t st) {
+    static bool tuned[64] = {false};
+    int dev = 0;
+    SVOXB_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !tuned[dev]) {
+        cudaMemPool_t pool;
+        SVOXB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = ~0ull;
+        SVOXB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        tuned[dev] = true;
+    }
+    return check_cuda(cudaMallocAsync(p, bytes ? bytes : 4, st), "cudaMallocAsync");
+}
+
+static int* pinned_scalars() {
+    static thread_local int* h = nullptr;
+    if (!h && cudaHostAlloc(&h, sizeof(int) * 8, cudaHostAllocDefault) != cudaSuccess) h = nullptr;
+    return h;
+}
+
 extern "C" void svoxb_accel_destroy(svoxb_accel* a) {
     if (!a) return;
+    // released in stream order on the creation stream: work that still reads the accelerator on that stream
+    // finishes first. Callers using it on other streams must have synchronised them (documented in svoxb.h).
     for (int s = 0; s < MAX_STAGES; ++s)
-        if (a->cells[s]) cudaFree(a->cells[s]);
+        if (a->cells[s]) cudaFreeAsync(a->cells[s], a->stream);
     delete a;
 }
 
@@ -378,14 +403,16 @@ extern "C" int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* s
         return SVOXB_EUNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    int* h_scalars = pinned_scalars();
+    SVOXB_REQUIRE(h_scalars != nullptr, "cudaHostAlloc failed");
     int* d_scalars = nullptr;     // [0] max depth, [1] overflow, [2..] brick counts per stage
-    SVOXB_CUDA(cudaMalloc(&d_scalars, sizeof(int) * 8));
+    int rc = pool_alloc((void**)&d_scalars, sizeof(int) * 8, st);
+    if (rc) return rc;
     SVOXB_CUDA(cudaMemsetAsync(d_scalars, 0, sizeof(int) * 8, st));
-    int h_scalars[8] = {0};
     int lmax = max_depth;
     if (lmax <= 0) {
         if (!tree->parent_depth) {
-            cudaFree(d_scalars);
+            cudaFreeAsync(d_scalars, st);
             set_error("max_depth <= 0 needs tree->parent_depth");
             return SVOXB_EINVAL;
         }
@@ -397,13 +424,13 @@ extern "C" int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* s
         lmax = h_scalars[0] + 1;
     }
     if (lmax > ACC_MAX_DEPTH) {
-        cudaFree(d_scalars);
+        cudaFreeAsync(d_scalars, st);
         set_error("accelerator supports depth <= %d (tree depth %d)", ACC_MAX_DEPTH, lmax);
         return SVOXB_EUNSUPPORTED;
     }
     svoxb_accel* a = new svoxb_accel();
     memset(a, 0, sizeof(*a));
-    a->M = tree->M; a->child = tree->child; a->data = tree->data;
+    a->M = tree->M; a->child = tree->child; a->data = tree->data; a->stream = st;
     // stage split: top grid of <= 4 levels (16 KB of shared memory), the rest in bricks of <= 4 levels
     AccelView& v = a->view;
     v.lmax = lmax;
@@ -417,26 +444,23 @@ extern "C" int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* s
     for (int s = 0; s < v.n_stages; ++s) { resolved += v.bits[s]; v.shift[s] = lmax - resolved; }
 
     int32_t* roots[2] = {nullptr, nullptr};
-    int rc = 0;
     auto fail = [&](int code) {
-        if (roots[0]) cudaFree(roots[0]);
-        if (roots[1]) cudaFree(roots[1]);
-        cudaFree(d_scalars);
+        if (roots[0]) cudaFreeAsync(roots[0], st);
+        if (roots[1]) cudaFreeAsync(roots[1], st);
+        cudaFreeAsync(d_scalars, st);
         svoxb_accel_destroy(a);
         return code;
     };
     if (v.n_stages > 1) {
         for (int i = 0; i < 2; ++i)
-            if ((rc = check_cuda(cudaMalloc(&roots[i], sizeof(int32_t) * (size_t)tree->n_internal), "cudaMalloc(roots)")))
-                return fail(rc);
+            if ((rc = pool_alloc((void**)&roots[i], sizeof(int32_t) * (size_t)tree->n_internal, st))) return fail(rc);
     }
     int64_t n_bricks = 1;
     int base_depth = 0;
     for (int s = 0; s < v.n_stages; ++s) {
         const int64_t words = n_bricks << (3 * v.bits[s]);
         a->n_bricks[s] = n_bricks;
-        if ((rc = check_cuda(cudaMalloc(&a->cells[s], sizeof(uint32_t) * (size_t)max(words, (int64_t)1)), "cudaMalloc(cells)")))
-            return fail(rc);
+        if ((rc = pool_alloc((void**)&a->cells[s], sizeof(uint32_t) * (size_t)max(words, (int64_t)1), st))) return fail(rc);
         a->bytes += (int64_t)sizeof(uint32_t) * words;
         v.cells[s] = a->cells[s];
         const int is_last = (s == v.n_stages - 1);
@@ -449,6 +473,7 @@ extern "C" int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* s
             count_launch();
             if ((rc = check_cuda(cudaGetLastError(), "accel_stage_kernel launch"))) return fail(rc);
         }
+        // the brick count of the next stage sizes its allocation: one small pinned read-back per stage
         if ((rc = check_cuda(cudaMemcpyAsync(h_scalars, d_scalars, sizeof(int) * 8, cudaMemcpyDeviceToHost, st), "memcpy")))
             return fail(rc);
         if ((rc = check_cuda(cudaStreamSynchronize(st), "accel build sync"))) return fail(rc);
@@ -459,9 +484,9 @@ extern "C" int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* s
         set_error("tree is deeper than max_depth=%d", lmax);
         return fail(SVOXB_EINVAL);
     }
-    if (roots[0]) cudaFree(roots[0]);
-    if (roots[1]) cudaFree(roots[1]);
-    cudaFree(d_scalars);
+    if (roots[0]) cudaFreeAsync(roots[0], st);
+    if (roots[1]) cudaFreeAsync(roots[1], st);
+    cudaFreeAsync(d_scalars, st);
     *out = a;
     return 0;
 }

@@ -136,6 +136,7 @@ class N3Tree(nn.Module):
         self.filled = int(child.shape[0])
         self._n_internal.fill_(self.filled)
         self._invalidate()
+        self._known_depth = int(depth)     # spares the accelerator build its max-depth reduction + read-back
         return self
 
     def construct_tree(self, indices):
@@ -259,12 +260,13 @@ class N3Tree(nn.Module):
         return (indices - self.offset) / self.invradius
 
     def _invalidate(self):
+        self._known_depth = 0
         self._ver += 1
         self._last_all_leaves = None
         self._accel_cache = None
 
     # ---- the bridge to the kernels ---------------------------------------------------------------------------
-    def accel(self, features=None):
+    def accel(self, features=None, max_depth=0):
         """Packed grid+brick accelerator for the current child/data (N == 2 only; None otherwise). Cached."""
         if self.N != 2 or not self.data.is_cuda:
             return None
@@ -273,7 +275,7 @@ class N3Tree(nn.Module):
         acc = self._accel_cache
         if acc is None or not acc.matches(spec):
             try:
-                acc = _C.Accel(spec)
+                acc = _C.Accel(spec, max_depth=max_depth or getattr(self, "_known_depth", 0))
             except RuntimeError as e:      # e.g. more rows than the packed index field can hold
                 warn(f"svox_t_b200: accelerator not built ({e}); walking the reference tensors instead")
                 acc = None
