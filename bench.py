@@ -266,6 +266,10 @@ def main():
            "h2d_bytes_per_step": int(h_o.numel() + h_d.numel() + h_tgt.numel()) * 4, "d2h_bytes_per_step": 4,
            "api": "VolumeRenderer.forward + autograd backward, loss = 0.5*mean((out-target)^2)"}
 
+    if world > 1:
+        import torch.distributed as tdist
+        svd.barrier()
+        tdist.destroy_process_group()
     if rank != 0:
         return
     # ---- CPU baseline + counters (rank 0, bounded sample) ---------------------------------------------------------------
