@@ -151,6 +151,23 @@ SVOXB_API int svoxb_render_image_bwd(const svoxb_tree* tree, const svoxb_camera*
 SVOXB_API int svoxb_render_depth(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
                        const svoxb_render_options* opt, float* depth, void* stream);
 
+/* opacity_render (rt_kernel.cu:499-560, 1574-1591): out[Q] = 1 - T, same thresholds / early stop as the forward. */
+SVOXB_API int svoxb_opacity_render_fwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                             const svoxb_render_options* opt, float* out, void* stream);
+
+/* Backward of opacity_render as the reference WROTE it (opacity_trace_ray_backward, rt_kernel.cu:562-651):
+ * grad_features[idx, D-1] += delta_t * delta_scale * grad_out[q] * T_end for every sample with sigma > 0.
+ * (The reference's own entry point launches the wrong kernel, rt_kernel.cu:1607; this is the intended semantics.) */
+SVOXB_API int svoxb_opacity_render_bwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                             const svoxb_render_options* opt, const float* grad_out, float* grad_features, void* stream);
+
+/* motion_render (rt_kernel.cu:698-778, 1480-1504): at the first sample with sigma > sigma_thresh:
+ * out[Q, J] = distance of the hit point to each row of extra_data[J, 3], depth[Q], hit_point[Q, 3], data_idx[Q]
+ * (all zero when nothing is hit). The hit point reproduces the reference's arithmetic (see svoxb_render_x.cu). */
+SVOXB_API int svoxb_motion_render(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                        const svoxb_render_options* opt, const float* extra_data, int32_t J, float* out, float* depth,
+                        float* hit_point, int64_t* data_idx, void* stream);
+
 /* ---- animated-frame rebuild -------------------------------------------------------------------- */
 /* warp_vertices (svox_kernel.cu:123-154, 354-378): linear blend skinning. T[J,4,4], coords[P,3], w[P,B],
  * joint_index[P,B] -> coords_out[P,3], mats_out[P,4,4] (fully written, no zero-fill needed). */

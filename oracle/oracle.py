@@ -157,6 +157,43 @@ def render_rays_backward(tree, features, origins, dirs, grad_out, step_size=1e-3
     return grad
 
 
+def opacity_render(tree, features, origins, dirs, step_size=1e-3, sigma_thresh=0.0, stop_thresh=0.0,
+                   dtype=np.float32):
+    sfx, cr = _sfx(dtype)
+    keep, targs = tree.args(features, dtype)
+    o, d = _c(origins, dtype), _c(dirs, dtype)
+    out = np.zeros(o.shape[0], dtype=dtype)
+    getattr(lib(), "orc_opacity_render" + sfx)(*targs, _p(o), _p(d), ctypes.c_int64(o.shape[0]), cr(step_size),
+                                                cr(sigma_thresh), cr(stop_thresh), _p(out))
+    return out
+
+
+def opacity_render_backward(tree, features, origins, dirs, grad_out, step_size=1e-3, dtype=np.float32):
+    sfx, cr = _sfx(dtype)
+    keep, targs = tree.args(features, dtype)
+    o, d, g = _c(origins, dtype), _c(dirs, dtype), _c(grad_out, dtype).reshape(-1)
+    grad = np.zeros_like(keep[0])
+    getattr(lib(), "orc_opacity_render_backward" + sfx)(*targs, _p(o), _p(d), ctypes.c_int64(o.shape[0]),
+                                                         cr(step_size), _p(g), _p(grad))
+    return grad
+
+
+def motion_render(tree, features, origins, dirs, extra, step_size=1e-3, sigma_thresh=0.0, dtype=np.float32):
+    """-> out[Q,J], depth[Q], hit_point[Q,3], data_idx[Q] i64 (zeros where nothing is hit)."""
+    sfx, cr = _sfx(dtype)
+    keep, targs = tree.args(features, dtype)
+    o, d, e = _c(origins, dtype), _c(dirs, dtype), _c(extra, dtype)
+    Q, J = o.shape[0], e.shape[0]
+    out = np.zeros((Q, J), dtype=dtype)
+    depth = np.zeros(Q, dtype=dtype)
+    hit = np.zeros((Q, 3), dtype=dtype)
+    didx = np.zeros(Q, dtype=np.int64)
+    getattr(lib(), "orc_motion_render" + sfx)(*targs, _p(o), _p(d), ctypes.c_int64(Q), cr(step_size),
+                                               cr(sigma_thresh), _p(e), ctypes.c_int(J), _p(out), _p(depth), _p(hit),
+                                               _p(didx))
+    return out, depth, hit, didx
+
+
 def camera_rays(c2w, fx, fy, width, height, dtype=np.float32):
     """-> origins[H*W,3], dirs[H*W,3] in row-major pixel order (iy*W + ix), world space."""
     sfx, cr = _sfx(dtype)

@@ -70,6 +70,9 @@ SYMBOLS = {
     "svoxb_render_image_fwd": (ctypes.c_int, [_PT, _PC, _PO, _VP, _VP, _VP]),
     "svoxb_render_image_bwd": (ctypes.c_int, [_PT, _PC, _PO, _VP, _VP, _VP, _VP]),
     "svoxb_render_depth": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP]),
+    "svoxb_opacity_render_fwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP]),
+    "svoxb_opacity_render_bwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP, _VP]),
+    "svoxb_motion_render": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _I32, _VP, _VP, _VP, _VP, _VP]),
     "svoxb_warp_vertices": (ctypes.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _VP, _VP, _VP]),
     "svoxb_p2v": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP, _VP, _I32, _F, _F, _VP, _VP]),
     "svoxb_build_work_bytes": (ctypes.c_size_t, [_I64, _I32]),
@@ -419,6 +422,54 @@ def render_depth(tree, rays, opt):
     return depth
 
 
+def opacity_render(tree, rays, opt):
+    """[Q, 1] opacity 1 - T (rt_kernel.cu:1574-1591)."""
+    lib = load_library()
+    rays.check()
+    ct = tree._c()
+    Q, dev = rays.origins.shape[0], rays.origins.device
+    with torch.cuda.device(dev):
+        out = torch.empty((Q, 1), dtype=torch.float32, device=dev)
+        _check(lib.svoxb_opacity_render_fwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q,
+                                            ctypes.byref(opt._c()), _ptr(out), _stream()))
+    return out
+
+
+def opacity_render_backward(tree, rays, opt, grad_output):
+    """[M, D] gradient of opacity_render w.r.t. the sigma channel -- the semantics of the reference's
+    opacity_trace_ray_backward (rt_kernel.cu:562-651), which its own wrapper never launches (Appendix B2)."""
+    lib = load_library()
+    rays.check()
+    _check_input(grad_output, "grad_output", torch.float32)
+    ct = tree._c()
+    Q, dev = rays.origins.shape[0], rays.origins.device
+    with torch.cuda.device(dev):
+        grad = torch.zeros_like(tree.features)
+        _check(lib.svoxb_opacity_render_bwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q,
+                                            ctypes.byref(opt._c()), _ptr(grad_output), _ptr(grad), _stream()))
+    return grad
+
+
+def motion_render(tree, rays, opt):
+    """[out[Q,J], depth[Q,1], hit_point[Q,3], data_idx[Q,1] i64] at the first hit (rt_kernel.cu:1480-1504)."""
+    lib = load_library()
+    rays.check()
+    if tree.extra_data is None or tree.extra_data.numel() == 0:
+        raise RuntimeError("motion_render needs tree.extra_data [J, 3]")
+    _check_input(tree.extra_data, "extra_data", torch.float32)
+    ct = tree._c()
+    Q, dev, J = rays.origins.shape[0], rays.origins.device, tree.extra_data.shape[0]
+    with torch.cuda.device(dev):
+        out = torch.empty((Q, J), dtype=torch.float32, device=dev)
+        depth = torch.empty((Q, 1), dtype=torch.float32, device=dev)
+        hit = torch.empty((Q, 3), dtype=torch.float32, device=dev)
+        didx = torch.empty((Q, 1), dtype=torch.int64, device=dev)
+        _check(lib.svoxb_motion_render(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q, ctypes.byref(opt._c()),
+                                       _ptr(tree.extra_data), J, _ptr(out), _ptr(depth), _ptr(hit), _ptr(didx),
+                                       _stream()))
+    return [out, depth, hit, didx]
+
+
 def warp_vertices(matrices, indices, skinning_weights, joint_index):
     """[coords'[P,3], mats[P,4,4]] (svox_kernel.cu:354-378)."""
     lib = load_library()
@@ -490,11 +541,8 @@ query_vertical_backward = _unsupported("query_vertical_backward", "faults in the
 assign_vertical = _unsupported("assign_vertical", "faults in the reference (Appendix B1); out of scope")
 warp_vertices_backward = _unsupported("warp_vertices_backward", "next-rank component (SURVEY 8f rank 2)")
 p2v_backward = _unsupported("p2v_backward", "next-rank component (SURVEY 8f rank 2)")
-motion_render = _unsupported("motion_render", "next-rank component (SURVEY 8f rank 1)")
 motion_feature_render = _unsupported("motion_feature_render", "next-rank component (SURVEY 8f rank 3)")
 motion_feature_render_backward = _unsupported("motion_feature_render_backward", "buggy in the reference (Appendix B3)")
-opacity_render = _unsupported("opacity_render", "next-rank component (SURVEY 8f rank 1)")
-opacity_render_backward = _unsupported("opacity_render_backward", "wired to the wrong kernel in the reference (B2)")
 calc_corners = _unsupported("calc_corners", "dtype bug in the reference (Appendix B4); out of scope")
 grid_weight_render = _unsupported("grid_weight_render", "no caller in the reference; out of scope")
 quantize_median_cut = _unsupported("quantize_median_cut", "CPU-only PlenOctree leftover; out of scope")

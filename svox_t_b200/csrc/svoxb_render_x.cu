@@ -1,0 +1,192 @@
+// svoxb_render_x.cu -- march variants next to the feature render: opacity-only render with a
+// CORRECT backward, and the first-hit "motion" outputs. One thread per ray: these touch one float per sample
+// (sigma), so there is no row work to share across a warp.
+//
+// Replaces (reference paths relative to /root/reference/svox_t/csrc):
+//   opacity_trace_ray / opacity_render                 rt_kernel.cu:499-560, 1109-1126, 1574-1591
+//   opacity_trace_ray_backward                         rt_kernel.cu:562-651  (never instantiated in the reference:
+//                                                      its host wrapper launches render_ray_backward_kernel, :1607)
+//   motion_trace_ray / motion_render                   rt_kernel.cu:698-778, 836-862, 1480-1504
+#include "svoxb_march.cuh"
+
+namespace svoxb {
+
+template <bool ACCEL>
+__device__ __forceinline__ void sample_sigma(const TreeArgs& tr, const uint32_t* top, const Ray& r, float step,
+                                             Leaf& lf, float& delta_t, float& sigma) {
+    const float px = fmaf(r.t, r.dx, r.ox), py = fmaf(r.t, r.dy, r.oy), pz = fmaf(r.t, r.dz, r.oz);
+    lf = locate<ACCEL>(tr, top, px, py, pz);
+    float smin, smax;
+    dda_unit(lf.rx, lf.ry, lf.rz, r.ix, r.iy, r.iz, smin, smax);
+    const float tsub = ACCEL ? (smax - smin) * lf.inv_cube : (smax - smin) / lf.cube;
+    delta_t = tsub + step;
+    sigma = 0.0f;
+    if (lf.idx >= 0) sigma = __ldg(tr.features + lf.idx * tr.D + (tr.D - 1));
+}
+
+__device__ __forceinline__ void load_ray(const TreeArgs& tr, const float* origins, const float* dirs, int64_t id, Ray& ray) {
+    ray_setup(tr.offset, tr.scaling, __ldg(origins + 3 * id), __ldg(origins + 3 * id + 1), __ldg(origins + 3 * id + 2),
+              __ldg(dirs + 3 * id), __ldg(dirs + 3 * id + 1), __ldg(dirs + 3 * id + 2), ray);
+}
+
+template <bool ACCEL>
+__global__ void __launch_bounds__(BLOCK)
+opacity_fwd_kernel(TreeArgs tr, const float* __restrict__ origins, const float* __restrict__ dirs, int64_t Q,
+                   MarchOpts opt, float* __restrict__ out) {
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t* top = smem_u32;
+    if (ACCEL) load_top(tr, top);
+    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < Q; id += (int64_t)gridDim.x * blockDim.x) {
+        Ray ray;
+        load_ray(tr, origins, dirs, id, ray);
+        float T = 1.0f;
+        while (ray.t < ray.tmax) {
+            Leaf lf; float delta_t, sigma;
+            sample_sigma<ACCEL>(tr, top, ray, opt.step, lf, delta_t, sigma);
+            if (sigma > opt.sigma_thresh) {                                  // rt_kernel.cu:547-555
+                T *= expf(-delta_t * ray.ds * sigma);
+                if (T <= opt.stop_thresh) break;
+            }
+            ray.t += delta_t;
+        }
+        out[id] = 1.0f - T;
+    }
+}
+
+// d(1 - T_end)/d sigma_i = delta_i * delta_scale * T_end for every sample with sigma_i > 0 (rt_kernel.cu:610-646).
+template <bool ACCEL>
+__global__ void __launch_bounds__(BLOCK)
+opacity_bwd_kernel(TreeArgs tr, const float* __restrict__ origins, const float* __restrict__ dirs, int64_t Q,
+                   MarchOpts opt, const float* __restrict__ grad_out, float* __restrict__ grad) {
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t* top = smem_u32;
+    if (ACCEL) load_top(tr, top);
+    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < Q; id += (int64_t)gridDim.x * blockDim.x) {
+        Ray ray;
+        load_ray(tr, origins, dirs, id, ray);
+        const float t0 = ray.t;
+        float T = 1.0f;
+        while (ray.t < ray.tmax) {                                           // pass 1: T_end
+            Leaf lf; float delta_t, sigma;
+            sample_sigma<ACCEL>(tr, top, ray, opt.step, lf, delta_t, sigma);
+            if (sigma > 0.0f) T *= expf(-delta_t * sigma * ray.ds);
+            ray.t += delta_t;
+        }
+        const float gT = __ldg(grad_out + id) * T;
+        ray.t = t0;
+        while (ray.t < ray.tmax) {                                           // pass 2: scatter
+            Leaf lf; float delta_t, sigma;
+            sample_sigma<ACCEL>(tr, top, ray, opt.step, lf, delta_t, sigma);
+            if (sigma > 0.0f) atomicAdd(grad + lf.idx * tr.D + (tr.D - 1), delta_t * ray.ds * gT);
+            ray.t += delta_t;
+        }
+    }
+}
+
+// First hit: distances from the hit point to the J rows of extra_data, depth, hit point, data index.
+// NOTE the hit point is what the reference computes (rt_kernel.cu:757-761): transform_coord_world applied to the
+// IN-LEAF RELATIVE coordinates the descent leaves in `pos`, not to the sample position. Kept for parity.
+template <bool ACCEL>
+__global__ void __launch_bounds__(BLOCK)
+motion_kernel(TreeArgs tr, const float* __restrict__ origins, const float* __restrict__ dirs, int64_t Q, MarchOpts opt,
+              const float* __restrict__ extra, int J, float* __restrict__ out, float* __restrict__ depth,
+              float* __restrict__ hit_point, int64_t* __restrict__ data_idx) {
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t* top = smem_u32;
+    if (ACCEL) load_top(tr, top);
+    const float o0 = __ldg(tr.offset), o1 = __ldg(tr.offset + 1), o2 = __ldg(tr.offset + 2);
+    const float s0 = __ldg(tr.scaling), s1 = __ldg(tr.scaling + 1), s2 = __ldg(tr.scaling + 2);
+    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < Q; id += (int64_t)gridDim.x * blockDim.x) {
+        Ray ray;
+        load_ray(tr, origins, dirs, id, ray);
+        float d = 0.0f, hx = 0.0f, hy = 0.0f, hz = 0.0f;
+        int64_t di = 0;
+        bool hit = false;
+        while (ray.t < ray.tmax) {
+            Leaf lf; float delta_t, sigma;
+            sample_sigma<ACCEL>(tr, top, ray, opt.step, lf, delta_t, sigma);
+            if (sigma > opt.sigma_thresh) {
+                hx = (lf.rx - o0) / s0; hy = (lf.ry - o1) / s1; hz = (lf.rz - o2) / s2;   // common.cuh:53-60
+                d = ray.t * ray.ds;
+                di = lf.idx;
+                hit = true;
+                break;
+            }
+            ray.t += delta_t;
+        }
+        for (int j = 0; j < J; ++j) {
+            float v = 0.0f;
+            if (hit) {
+                const float a = hx - __ldg(extra + 3 * j), b = hy - __ldg(extra + 3 * j + 1), c = hz - __ldg(extra + 3 * j + 2);
+                v = sqrtf(a * a + b * b + c * c);
+            }
+            out[id * J + j] = v;
+        }
+        depth[id] = d;
+        hit_point[3 * id] = hx; hit_point[3 * id + 1] = hy; hit_point[3 * id + 2] = hz;
+        data_idx[id] = di;
+    }
+}
+
+int make_tree_args(const svoxb_tree* t, TreeArgs& a);
+
+static int simple_opts(const svoxb_render_options* opt, MarchOpts& m) {
+    SVOXB_REQUIRE(opt != nullptr, "render options are NULL");
+    if (opt->ndc_width >= 0) { set_error("NDC ray conversion is not implemented"); return SVOXB_EUNSUPPORTED; }
+    m.step = opt->step_size; m.bg = opt->background_brightness;
+    m.sigma_thresh = opt->sigma_thresh; m.stop_thresh = opt->stop_thresh;
+    return 0;
+}
+
+template <typename KA, typename KR, typename... Args>
+static int launch_simple(const TreeArgs& tr, int64_t Q, cudaStream_t st, KA kacc, KR kref, Args... args) {
+    const int grid = (int)min((Q + BLOCK - 1) / BLOCK, (int64_t)sm_count() * 8);
+    if (tr.use_accel) {
+        const size_t smem = sizeof(uint32_t) << (3 * tr.acc.bits[0]);
+        kacc<<<grid, BLOCK, smem, st>>>(tr, args...);
+    } else {
+        kref<<<grid, BLOCK, 0, st>>>(tr, args...);
+    }
+    count_launch();
+    return check_cuda(cudaGetLastError(), "ray kernel launch");
+}
+
+}  // namespace svoxb
+
+using namespace svoxb;
+
+extern "C" int svoxb_opacity_render_fwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                                        const svoxb_render_options* opt, float* out, void* stream) {
+    TreeArgs tr; MarchOpts m;
+    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    rc = simple_opts(opt, m); if (rc) return rc;
+    SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (origins && dirs && out)), "bad ray batch");
+    if (Q == 0) return 0;
+    return launch_simple(tr, Q, (cudaStream_t)stream, opacity_fwd_kernel<true>, opacity_fwd_kernel<false>, origins, dirs,
+                         Q, m, out);
+}
+
+extern "C" int svoxb_opacity_render_bwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                                        const svoxb_render_options* opt, const float* grad_out, float* grad_features,
+                                        void* stream) {
+    TreeArgs tr; MarchOpts m;
+    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    rc = simple_opts(opt, m); if (rc) return rc;
+    SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (origins && dirs && grad_out && grad_features)), "bad arguments");
+    if (Q == 0) return 0;
+    return launch_simple(tr, Q, (cudaStream_t)stream, opacity_bwd_kernel<true>, opacity_bwd_kernel<false>, origins, dirs,
+                         Q, m, grad_out, grad_features);
+}
+
+extern "C" int svoxb_motion_render(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                                   const svoxb_render_options* opt, const float* extra_data, int32_t J, float* out,
+                                   float* depth, float* hit_point, int64_t* data_idx, void* stream) {
+    TreeArgs tr; MarchOpts m;
+    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    rc = simple_opts(opt, m); if (rc) return rc;
+    SVOXB_REQUIRE(J >= 0 && (J == 0 || extra_data), "extra_data is NULL");
+    SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (origins && dirs && depth && hit_point && data_idx && (J == 0 || out))), "bad arguments");
+    if (Q == 0) return 0;
+    return launch_simple(tr, Q, (cudaStream_t)stream, motion_kernel<true>, motion_kernel<false>, origins, dirs, Q, m,
+                         extra_data, (int)J, out, depth, hit_point, data_idx);
+}

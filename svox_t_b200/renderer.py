@@ -81,6 +81,21 @@ class _VolumeRenderImageFunction(autograd.Function):
         return None, None, None, None, None
 
 
+class _OpacityRenderFunction(autograd.Function):
+    """renderer.py:118-138, with the backward the reference meant to run (Appendix B2)."""
+
+    @staticmethod
+    def forward(ctx, data, tree, rays, opt):
+        ctx.tree, ctx.rays, ctx.opt = tree, rays, opt
+        return _C.opacity_render(tree, rays, opt)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if ctx.needs_input_grad[0]:
+            return _C.opacity_render_backward(ctx.tree, ctx.rays, ctx.opt, grad_out.contiguous()), None, None, None
+        return None, None, None, None
+
+
 class VolumeRenderer(nn.Module):
     """Volume renderer bound to an N3Tree (renderer.py:162-205)."""
 
@@ -142,14 +157,20 @@ class VolumeRenderer(nn.Module):
         self._require_cuda(cuda)
         return _C.render_depth(self.tree._spec(features), _rays_spec_from_rays(rays), self._get_options(fast))
 
-    def motion_render(self, *a, **k):
-        return _C.motion_render()
+    def motion_render(self, features, rays: Rays, cuda=True, fast=False):
+        """First-hit joint distances, depth, hit point and data index (renderer.py:367-375)."""
+        assert self.tree.extra_data is not None, "Need extra data to store skeleton postion."
+        self._require_cuda(cuda)
+        return tuple(_C.motion_render(self.tree._spec(features), _rays_spec_from_rays(rays), self._get_options(fast)))
 
     def motion_feature_render(self, *a, **k):
         return _C.motion_feature_render()
 
-    def opacity_render(self, *a, **k):
-        return _C.opacity_render()
+    def opacity_render(self, features, rays: Rays, cuda=True, fast=False):
+        """Opacity only (B, 1); differentiable w.r.t. the sigma channel of ``features`` (renderer.py:397-406)."""
+        self._require_cuda(cuda)
+        return _OpacityRenderFunction.apply(features, self.tree._spec(features), _rays_spec_from_rays(rays),
+                                            self._get_options(fast))
 
     def _get_options(self, fast=False):
         """RenderOptions for the kernels (renderer.py:408-439)."""

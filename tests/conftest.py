@@ -16,7 +16,13 @@ def pytest_configure(config):
 
 
 def golden_files():
-    return sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    """Fixtures of the main render path (volume_render / backward / depth / query)."""
+    return sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("x_"))
+
+
+def golden_variant_files():
+    """Fixtures of the march variants (opacity_render, motion_render)."""
+    return sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("x_"))
 
 
 @pytest.fixture(scope="session")

@@ -15,7 +15,7 @@ import torch
 
 import refdrv
 import svox_t_b200 as sv
-from conftest import GOLDEN_DIR, golden_files
+from conftest import GOLDEN_DIR, golden_files, golden_variant_files
 from oracle import oracle as orc
 from svox_t_b200 import csrc as C
 from svox_t_b200 import synth
@@ -251,6 +251,40 @@ def test_warp_vertices_and_p2v_vs_oracle(dev):
     v_ref = orc.p2v(pts, feat, corner, size, 64, 1.5 / 64, 2.0 / 64)
     assert vox.shape == (64, 64, 64, 1)
     assert np.allclose(vox.cpu().numpy(), v_ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("accel", [True, False], ids=["accel", "refwalk"])
+@pytest.mark.parametrize("name", golden_variant_files())
+def test_march_variants_against_reference_golden(dev, name, accel):
+    z = np.load(os.path.join(GOLDEN_DIR, name))
+    D = z["features"].shape[1]
+    tree = make_tree(z, D, dev, z["offset"], z["scaling"])
+    tree.extra_data = cu(z["extra"], dev)
+    feats = cu(z["features"], dev)
+    rays = sv.Rays(cu(z["origins"], dev), cu(z["dirs"], dev), cu(z["dirs"], dev))
+    rs = sv.renderer._rays_spec_from_rays(rays)
+    ts = tree._spec(feats, _with_accel=accel)
+    r = sv.VolumeRenderer(tree)
+    for tag, fast in (("default", False), ("fast", True)):
+        opt = r._get_options(fast)
+        op = C.opacity_render(ts, rs, opt).cpu().numpy()[:, 0]
+        assert frac_within(op, z["opacity_" + tag]) >= 0.999
+        out, dep, hit, idx = (t.cpu().numpy() for t in C.motion_render(ts, rs, opt))
+        same = idx[:, 0] == z["motion_idx_" + tag]
+        assert same.mean() >= 0.999
+        assert np.allclose(dep[same, 0], z["motion_depth_" + tag][same], atol=1e-5)
+        assert np.allclose(hit[same], z["motion_hit_" + tag][same], atol=1e-5)
+        assert np.allclose(out[same], z["motion_out_" + tag][same], atol=1e-5)
+    # opacity backward: the reference never runs its own kernel for it (Appendix B2) -> oracle + autograd plumbing
+    fw = feats.clone().requires_grad_(True)
+    g = np.random.default_rng(4).standard_normal((len(z["origins"]), 1)).astype(np.float32)
+    (r.opacity_render(fw, rays) * cu(g, dev)).sum().backward()
+    T = orc.Tree(z["child"], z["data"], z["offset"], z["scaling"])
+    g_ref = orc.opacity_render_backward(T, z["features"], z["origins"], z["dirs"], g)
+    assert rel_l2(fw.grad.cpu().numpy(), g_ref) <= 1e-4
+    # the opacity channel of the full render and the opacity-only render agree
+    full = r(feats, rays)
+    assert torch.allclose(full[:, -1:], C.opacity_render(ts, rs, r._get_options()), atol=1e-6)
 
 
 # ---- (3) the compiled reference itself, when it travelled to this box -----------------------------------------------

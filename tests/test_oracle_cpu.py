@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_DIR, golden_files
+from conftest import GOLDEN_DIR, golden_files, golden_variant_files
 from oracle import oracle as orc
 from svox_t_b200 import synth
 
@@ -191,6 +191,42 @@ def test_oracle_matches_reference_golden(name):
     assert (data_ids[valid] == z["ref_data_ids"][valid]).all()
     assert (vals[valid] == z["ref_values"][valid]).all()
     assert (orc.leafset(node_ids, T.N) == z["ref_leaf_node"]).all()
+
+
+def test_opacity_oracle_consistency_and_gradient():
+    tr = synth.synth_tree(4, "ball")
+    T = orc.Tree(tr["child"], tr["data"])
+    f = synth.synth_features(tr["M"], 6)
+    o, d = synth.synth_rays(300)
+    for st, sp in ((0.0, 0.0), (1e-2, 1e-2)):
+        assert np.array_equal(orc.opacity_render(T, f, o, d, sigma_thresh=st, stop_thresh=sp),
+                              orc.render_rays(T, f, o, d, sigma_thresh=st, stop_thresh=sp)[0][:, -1])
+    g = np.random.default_rng(0).standard_normal(300)
+    f64 = f.astype(np.float64)
+    f64[:, -1] = np.abs(f64[:, -1]) + 0.3
+    grad = orc.opacity_render_backward(T, f64, o, d, g, dtype=np.float64)
+    assert not grad[:, :-1].any()
+    for r in np.argsort(-np.abs(grad[:, -1]))[:5]:
+        fp, fm = f64.copy(), f64.copy()
+        fp[r, -1] += 1e-6
+        fm[r, -1] -= 1e-6
+        fd = ((orc.opacity_render(T, fp, o, d, dtype=np.float64) - orc.opacity_render(T, fm, o, d, dtype=np.float64)) * g).sum() / 2e-6
+        assert abs(fd - grad[r, -1]) <= 1e-6 + 1e-5 * abs(fd)
+
+
+@pytest.mark.parametrize("name", golden_variant_files())
+def test_variant_oracle_matches_reference_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name))
+    T = orc.Tree(z["child"], z["data"], z["offset"], z["scaling"])
+    for tag, (st, sp) in {"default": (0.0, 0.0), "fast": (1e-2, 1e-2)}.items():
+        op = orc.opacity_render(T, z["features"], z["origins"], z["dirs"], sigma_thresh=st, stop_thresh=sp)
+        assert frac_within(op, z["opacity_" + tag]) >= 0.999
+        out, dep, hit, idx = orc.motion_render(T, z["features"], z["origins"], z["dirs"], z["extra"], sigma_thresh=st)
+        same = idx == z["motion_idx_" + tag]
+        assert same.mean() >= 0.999                                              # first-hit leaf: exact but for ties
+        assert np.allclose(dep[same], z["motion_depth_" + tag][same], atol=1e-5)
+        assert np.allclose(hit[same], z["motion_hit_" + tag][same], atol=1e-5)
+        assert np.allclose(out[same], z["motion_out_" + tag][same], atol=1e-5)
 
 
 def test_golden_fixtures_present():
