@@ -5,10 +5,13 @@
 //   * a feature row is covered by LPR = pow2ceil(D/4) lanes holding one float4 each, so ONE 128-bit load
 //     instruction fetches RPI = 32/LPR whole rows (4 rows = 512 B at D = 32), one 128-bit store writes RPI output
 //     rows and one red.global.add.v4.f32 scatters RPI gradient rows;
-//   * the lanes' traversal (phase A) never reads the feature table: every leaf that holds a row becomes a
-//     candidate, the rows of all candidates of the round are in flight together, and each owner lane picks its
-//     sample's sigma out of the loaded row with one shuffle (the reference's separate 4-byte sigma gather and the
-//     second dependent round trip are gone);
+//   * the lanes' traversal never reads the feature table: every leaf that holds a row becomes a candidate, the rows
+//     of the candidates are requested as a batch and each owner lane picks its sample's sigma out of the loaded row
+//     with one shuffle (the reference's separate 4-byte sigma gather and second dependent round trip are gone);
+//   * software pipelining: the brick lookup of sample i+1 is issued before, and consumed after, the compositing of
+//     sample i, whose rows were requested one step earlier -- both latencies hide behind arithmetic;
+//   * the 32 x D partial outputs of a warp's rays (forward) / the staged grad_out rows (backward) live in shared
+//     memory, which keeps the kernels at 80 registers (3 CTAs per SM at D <= 32);
 //   * the per-hit channel dot product of the backward is reduced with a transposing butterfly over the LPR lanes
 //     of a row (LPR-1 shuffles for LPR hits instead of log2(LPR) per hit).
 // Lane layout: lane = q * LPR + c4; q = which of the RPI rows of a load, c4 = channel quad (channels 4*c4..4*c4+3).
@@ -70,315 +73,29 @@ struct Quad {
 };
 
 // ------------------------------------------------------------------------------------------------------------
+// Loop structure (NBATCH = 1 for D <= 32, 2 for D <= 64, 4 for D <= 128; x holds the rows of ONE batch):
+//   S1   probe_begin : next sample position, top-grid lookup in shared memory, brick lookup ISSUED
+//   S2.0 composite batch 0 of the candidates found in the PREVIOUS iteration (their rows were requested at its end)
+//   S3   probe_end   : brick word consumed -> new candidates, t advanced
+//   S2.b request rows of batch b, composite it            (b = 1 .. NBATCH-1; latency hides behind S3 / S2.b-1)
+//   S4   request rows of batch 0 of the new candidates, flush finished rays, refill
 template <int LPR, bool ACCEL, bool IMAGE>
-__global__ void __launch_bounds__(BLOCK, (LPR <= 8 ? 2 : 1))
+__global__ void __launch_bounds__(BLOCK, (LPR <= 8 ? 3 : (LPR == 16 ? 2 : 1)))
 march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
                       unsigned long long* counter) {
     using G = Quad<LPR>;
-    constexpr int RPI = G::RPI, NB = G::NB, NBATCH = G::NBATCH;
-    extern __shared__ uint32_t smem_u32[];
-    uint32_t* top = smem_u32;
-    if (ACCEL) load_top(tr, top);
-    const int lane = threadIdx.x & 31;
-    const int q = lane / LPR, c4 = lane % LPR;
-    const int D = tr.D, D4 = D >> 2;
-    const bool lane_ok = c4 < D4, is_sig = c4 == D4 - 1;
-    const int sig_src = (lane % RPI) * LPR + (D4 - 1);   // lane that holds sigma of this owner lane's row
-    const char* fbase = reinterpret_cast<const char*>(tr.features) + 16 * c4;
-    const unsigned row_bytes = (unsigned)D * 4u;
-    const float* off = tr.offset;
-    const float* scl = tr.scaling;
-
-    float4 acc[LPR];
-#pragma unroll
-    for (int j = 0; j < LPR; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    Ray ray;
-    float T = 1.0f, depth_v = 0.0f;
-    int row = 0;
-    bool active = false, got_depth = false;
-    Queue qu{0, 0, false};
-    unsigned need = FULL;
-
-    while (true) {
-        if (need) {
-            const unsigned got = refill<IMAGE>(src, off, scl, counter, qu, need, lane, ray, row);
-            if ((got >> lane) & 1u) { active = true; T = 1.0f; got_depth = false; depth_v = 0.0f; }
-            need = 0;
-        }
-        if (__ballot_sync(FULL, active) == 0u) break;
-
-        // ---- phase A: traversal only; a leaf holding a row becomes this lane's candidate ---------------------------
-        int cidx = -1, fin = 0;
-        float cdt = 0.0f, ct = 0.0f;
-        if (active) {
-            if (!(ray.t < ray.tmax)) {
-                fin = 1;
-            } else {
-                traverse<ACCEL>(tr, top, ray, opt.step, cidx, cdt);
-                ct = ray.t;
-                ray.t += cdt;
-                if (!(ray.t < ray.tmax)) fin = 1;
-            }
-        }
-
-        // ---- phase B: rows of all candidates in flight, sigma -> owner, composite -----------------------------------
-        const unsigned vm = __ballot_sync(FULL, cidx >= 0);
-        if (vm) {
-#pragma unroll
-            for (int b = 0; b < NBATCH; ++b) {
-                const unsigned bm = NBATCH == 1 ? vm : (vm >> (G::RAYS_PER_BATCH * b)) & ((1u << G::RAYS_PER_BATCH) - 1u);
-                if (bm) {
-                    float4 x[NB];
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        const int idx = __shfl_sync(FULL, cidx, RPI * (b * NB + jj) + q);
-                        x[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (idx >= 0 && lane_ok)
-                            x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
-                    }
-                    float sig = 0.0f;
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        const float v = __shfl_sync(FULL, x[jj].w, sig_src);
-                        if (lane / RPI == b * NB + jj) sig = v;
-                    }
-                    float w = 0.0f;
-                    if ((NBATCH == 1 || lane / G::RAYS_PER_BATCH == b) && cidx >= 0 && sig > opt.sigma_thresh) {
-                        const float att = expf(-cdt * ray.ds * sig);                  // rt_kernel.cu:280
-                        w = T * (1.0f - att);
-                        if (!got_depth) { depth_v = ray.ds * ct; got_depth = true; }  // rt_kernel.cu:826-830
-                        T *= att;
-                        if (T <= opt.stop_thresh) fin = 2;                            // rt_kernel.cu:313
-                    }
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        const int j = b * NB + jj;
-                        const float w_j = __shfl_sync(FULL, w, RPI * j + q);
-                        if (w_j != 0.0f) {
-                            const float4 s = sigmoid4(x[jj]);
-                            acc[j].x = fmaf(w_j, s.x, acc[j].x);
-                            acc[j].y = fmaf(w_j, s.y, acc[j].y);
-                            acc[j].z = fmaf(w_j, s.z, acc[j].z);
-                            acc[j].w = fmaf(w_j, s.w, acc[j].w);
-                        }
-                    }
-                }
-            }
-        }
-
-        // ---- finished rays: RPI output rows per 128-bit store -----------------------------------------------------
-        const unsigned fm = __ballot_sync(FULL, fin != 0);
-        if (fm) {
-#pragma unroll
-            for (int j = 0; j < LPR; ++j) {
-                const unsigned gm = RPI == 32 ? fm : (fm >> (RPI * j)) & ((1u << RPI) - 1u);
-                if (gm) {
-                    const int r = RPI * j + q;
-                    const float T_r = __shfl_sync(FULL, T, r);
-                    const int fin_r = __shfl_sync(FULL, fin, r);
-                    const int row_r = __shfl_sync(FULL, row, r);
-                    if (fin_r != 0) {
-                        float4 v = acc[j];
-                        if (fin_r == 2) {
-                            const float scale = (float)(1.0 / (1.0 - (double)T_r));   // rt_kernel.cu:315
-                            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
-                        } else {
-                            const float add = T_r * opt.bg;                           // rt_kernel.cu:323-325
-                            v.x += add; v.y += add; v.z += add; v.w += add;
-                        }
-                        if (is_sig) v.w = 1.0f - T_r;                                 // rt_kernel.cu:317,326
-                        if (lane_ok) *reinterpret_cast<float4*>(out + (int64_t)row_r * D + 4 * c4) = v;
-                        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-            }
-            if (fin != 0) {
-                if (depth) depth[row] = depth_v;
-                active = false;
-            }
-            need = fm;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-template <int LPR, bool ACCEL, bool IMAGE>
-__global__ void __launch_bounds__(BLOCK, (LPR <= 8 ? 2 : 1))
-march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restrict__ grad_out,
-                      const float* __restrict__ saved_out, float* __restrict__ grad, unsigned long long* counter) {
-    using G = Quad<LPR>;
-    constexpr int RPI = G::RPI, NB = G::NB, NBATCH = G::NBATCH, DP = 4 * LPR;
-    extern __shared__ uint32_t smem_u32[];
-    const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
-    uint32_t* top = smem_u32;
-    if (ACCEL) load_top(tr, top);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* gs = reinterpret_cast<float*>(smem_u32 + top_words) + (size_t)warp * 32 * DP;   // [32 rays][DP]
-    const int q = lane / LPR, c4 = lane % LPR;
-    const int D = tr.D, D4 = D >> 2;
-    const bool lane_ok = c4 < D4, is_sig = c4 == D4 - 1;
-    const int sig_src = (lane % RPI) * LPR + (D4 - 1);
-    const int red_src = (lane % RPI) * LPR + ((lane / RPI) % NB);     // lane holding this owner's reduced dot product
-    const char* fbase = reinterpret_cast<const char*>(tr.features) + 16 * c4;
-    char* gbase = reinterpret_cast<char*>(grad) + 16 * c4;
-    const unsigned row_bytes = (unsigned)D * 4u;
-    const float* off = tr.offset;
-    const float* scl = tr.scaling;
-
-    Ray ray;
-    float T = 1.0f, accum = 0.0f, T_end = 0.0f, gop = 0.0f;
-    int row = 0;
-    bool active = false;
-    Queue qu{0, 0, false};
-    unsigned need = FULL;
-
-    while (true) {
-        if (need) {
-            unsigned got = refill<IMAGE>(src, off, scl, counter, qu, need, lane, ray, row);
-            if ((got >> lane) & 1u) { active = true; T = 1.0f; }
-            need = 0;
-            // per new ray: stage its grad_out row, accum = <g, out> over the payload channels, T_end, g_opacity
-            while (got) {
-                const int r = __ffs(got) - 1;
-                got &= got - 1;
-                const int row_r = __shfl_sync(FULL, row, r);
-                const float* g = grad_out + (int64_t)row_r * D;
-                const float* so = saved_out + (int64_t)row_r * D;
-                float part = 0.0f, g_last = 0.0f, o_last = 0.0f;
-                for (int c = lane; c < DP; c += 32) {
-                    const float gv = (c < D) ? __ldg(g + c) : 0.0f;
-                    const float ov = (c < D) ? __ldg(so + c) : 0.0f;
-                    gs[r * DP + c] = gv;
-                    if (c < D - 1) part = fmaf(gv, ov, part);
-                    if (c == D - 1) { g_last = gv; o_last = ov; }
-                }
-#pragma unroll
-                for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(FULL, part, s);
-                g_last = __shfl_sync(FULL, g_last, (D - 1) & 31);
-                o_last = __shfl_sync(FULL, o_last, (D - 1) & 31);
-                if (lane == r) { accum = part; T_end = 1.0f - o_last; gop = g_last; }
-            }
-            __syncwarp();
-        }
-        if (__ballot_sync(FULL, active) == 0u) break;
-
-        // ---- phase A --------------------------------------------------------------------------------------------
-        int cidx = -1;
-        bool fin = false;
-        float cdt = 0.0f;
-        if (active) {
-            if (!(ray.t < ray.tmax)) {
-                fin = true;
-            } else {
-                traverse<ACCEL>(tr, top, ray, opt.step, cidx, cdt);
-                ray.t += cdt;
-                if (!(ray.t < ray.tmax)) fin = true;
-            }
-        }
-
-        // ---- phase B --------------------------------------------------------------------------------------------
-        const unsigned vm = __ballot_sync(FULL, cidx >= 0);
-        if (vm) {
-#pragma unroll
-            for (int b = 0; b < NBATCH; ++b) {
-                const unsigned bm = NBATCH == 1 ? vm : (vm >> (G::RAYS_PER_BATCH * b)) & ((1u << G::RAYS_PER_BATCH) - 1u);
-                if (bm) {
-                    float4 x[NB];
-                    int idxs[NB];
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        idxs[jj] = __shfl_sync(FULL, cidx, RPI * (b * NB + jj) + q);
-                        x[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (idxs[jj] >= 0 && lane_ok)
-                            x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idxs[jj] * row_bytes));
-                    }
-                    float sig = 0.0f;
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        const float v = __shfl_sync(FULL, x[jj].w, sig_src);
-                        if (lane / RPI == b * NB + jj) sig = v;
-                    }
-                    float w = 0.0f, dd = 0.0f;
-                    const bool hit = (NBATCH == 1 || lane / G::RAYS_PER_BATCH == b) && cidx >= 0 && sig > 0.0f;
-                    if (hit) {                                                      // rt_kernel.cu:382,456
-                        const float att = expf(-cdt * sig * ray.ds);
-                        w = T * (1.0f - att);
-                        dd = cdt * ray.ds;
-                        T *= att;
-                    }
-                    const unsigned hb = __ballot_sync(FULL, hit);
-                    // pass 1: per-lane partial of c = sum_j s_j g_j; keep s(1-s)g for the scatter
-                    float cp[NB];
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        const int r = RPI * (b * NB + jj) + q;
-                        const bool on = ((hb >> r) & 1u) && lane_ok;
-                        const float4 g4 = *reinterpret_cast<const float4*>(gs + r * DP + 4 * c4);
-                        const float4 s = sigmoid4(x[jj]);
-                        const float sx = s.x * g4.x, sy = s.y * g4.y, sz = s.z * g4.z, sw = s.w * g4.w;
-                        cp[jj] = on ? (sx + sy) + (sz + (is_sig ? 0.0f : sw)) : 0.0f;
-                        x[jj] = make_float4(sx * (1.0f - s.x), sy * (1.0f - s.y), sz * (1.0f - s.z), sw * (1.0f - s.w));
-                    }
-                    const float c_tot = quad_reduce<NB, LPR>(cp, lane);
-                    const float c_own = __shfl_sync(FULL, c_tot, red_src);
-                    float sgrad = 0.0f;
-                    if (hit) {
-                        accum -= w * c_own;                                          // rt_kernel.cu:479-480
-                        sgrad = dd * (c_own * T - accum) + dd * gop * T_end;         // rt_kernel.cu:486-490
-                    }
-                    // pass 2: one vector reduction per RPI gradient rows
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        const int r = RPI * (b * NB + jj) + q;
-                        const float w_j = __shfl_sync(FULL, w, r);
-                        const float sg_j = __shfl_sync(FULL, sgrad, r);
-                        if (((hb >> r) & 1u) && lane_ok) {
-                            float* grow = reinterpret_cast<float*>(gbase + (size_t)(unsigned)idxs[jj] * row_bytes);
-                            red_add_v4(grow, w_j * x[jj].x, w_j * x[jj].y, w_j * x[jj].z, is_sig ? sg_j : w_j * x[jj].w);
-                        }
-                    }
-                }
-            }
-        }
-
-        const unsigned fm = __ballot_sync(FULL, fin);
-        if (fm) {
-            if (fin) active = false;
-            need = fm;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// Software-pipelined variants for LPR <= 8 (D <= 32: all rows of a round fit one batch). Per loop iteration:
-//   S1  probe_begin : next sample position, top-grid lookup in shared memory, brick lookup ISSUED
-//   S2  composite   : the candidate found in the PREVIOUS iteration, whose rows were requested at the end of it
-//   S3  probe_end   : brick word consumed -> new candidate, t advanced
-//   S4  request rows of the new candidate (consumed in the next iteration's S2), flush finished rays, refill
-// so the brick lookup latency hides behind the compositing math and the row latency behind the next probe.
-template <int LPR, bool ACCEL, bool IMAGE>
-#ifndef SVOXB_FWD_MINB
-#define SVOXB_FWD_MINB 2
-#endif
-#ifndef SVOXB_BWD_MINB
-#define SVOXB_BWD_MINB 2
-#endif
-__global__ void __launch_bounds__(BLOCK, SVOXB_FWD_MINB)
-march_fwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
-                      unsigned long long* counter) {
-    constexpr int RPI = 32 / LPR, NB = LPR;
+    constexpr int RPI = G::RPI, NB = G::NB, NBATCH = G::NBATCH, RPB = G::RAYS_PER_BATCH;
     extern __shared__ uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31;
-    // this warp's 32 x D partial outputs live in shared memory: accs[j * 32 + lane] = float4 of ray RPI*j + q
+    // this warp's 32 x D partial outputs: accs[j * 32] = this lane's float4 of ray RPI*j + q
     float4* accs = reinterpret_cast<float4*>(smem_u32 + top_words) + (size_t)(threadIdx.x >> 5) * 32 * LPR + lane;
     const int q = lane / LPR, c4 = lane % LPR;
     const int D = tr.D, D4 = D >> 2;
     const bool lane_ok = c4 < D4, is_sig = c4 == D4 - 1;
-    const int sig_src = (lane % RPI) * LPR + (D4 - 1);
+    const int sig_src = (lane % RPI) * LPR + (D4 - 1);   // lane that holds sigma of this owner lane's row
     const char* fbase = reinterpret_cast<const char*>(tr.features) + 16 * min(c4, D4 - 1);
     const unsigned row_bytes = (unsigned)D * 4u;
     const float* off = tr.offset;
@@ -386,7 +103,9 @@ march_fwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
 
     float4 x[NB];
 #pragma unroll
-    for (int j = 0; j < LPR; ++j) { x[j] = make_float4(0.f, 0.f, 0.f, 0.f); accs[j * 32] = x[j]; }
+    for (int j = 0; j < NB; ++j) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < LPR; ++j) accs[j * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     Ray ray;
     float T = 1.0f, depth_v = 0.0f, p_dt = 0.0f, p_t = 0.0f;
@@ -411,55 +130,69 @@ march_fwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             else probe_begin<ACCEL>(tr, top, ray, pb);
         }
 
-        // ---- S2: composite the pending candidates -------------------------------------------------------------------
+        const unsigned pm = __ballot_sync(FULL, p_idx >= 0);
         bool stopped = false;
-        if (__ballot_sync(FULL, p_idx >= 0)) {
-            float sig = 0.0f;
+        int n_idx = -1;
+        float n_dt = 0.0f, n_t = 0.0f;
 #pragma unroll
-            for (int jj = 0; jj < NB; ++jj) {
-                const float v = __shfl_sync(FULL, x[jj].w, sig_src);
-                if (lane / RPI == jj) sig = v;
-            }
-            float w = 0.0f;
-            if (p_idx >= 0 && sig > opt.sigma_thresh) {
-                const float att = expf(-p_dt * ray.ds * sig);                         // rt_kernel.cu:280
-                w = T * (1.0f - att);
-                if (!got_depth) { depth_v = ray.ds * p_t; got_depth = true; }         // rt_kernel.cu:826-830
-                T *= att;
-                if (T <= opt.stop_thresh) stopped = true;                             // rt_kernel.cu:313
-            }
+        for (int b = 0; b < NBATCH; ++b) {
+            if (b > 0) {        // rows of batch b of the pending candidates (batch 0 was requested last iteration)
 #pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                const float w_j = __shfl_sync(FULL, w, RPI * j + q);
-                if (w_j != 0.0f) {
-                    const float4 s = sigmoid4(x[j]);
-                    float4 a = accs[j * 32];
-                    a.x = fmaf(w_j, s.x, a.x);
-                    a.y = fmaf(w_j, s.y, a.y);
-                    a.z = fmaf(w_j, s.z, a.z);
-                    a.w = fmaf(w_j, s.w, a.w);
-                    accs[j * 32] = a;
+                for (int jj = 0; jj < NB; ++jj) {
+                    const int idx = max(__shfl_sync(FULL, p_idx, RPI * (b * NB + jj) + q), 0);
+                    x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
                 }
             }
+            // ---- S2.b: composite ---------------------------------------------------------------------------------
+            const unsigned bm = NBATCH == 1 ? pm : (pm >> (RPB * b)) & ((1u << RPB) - 1u);
+            if (bm) {
+                float sig = 0.0f;
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) {
+                    const float v = __shfl_sync(FULL, x[jj].w, sig_src);
+                    if (lane / RPI == b * NB + jj) sig = v;
+                }
+                float w = 0.0f;
+                if ((NBATCH == 1 || lane / RPB == b) && p_idx >= 0 && sig > opt.sigma_thresh) {
+                    const float att = expf(-p_dt * ray.ds * sig);                     // rt_kernel.cu:280
+                    w = T * (1.0f - att);
+                    if (!got_depth) { depth_v = ray.ds * p_t; got_depth = true; }     // rt_kernel.cu:826-830
+                    T *= att;
+                    if (T <= opt.stop_thresh) stopped = true;                         // rt_kernel.cu:313
+                }
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) {
+                    const int j = b * NB + jj;
+                    const float w_j = __shfl_sync(FULL, w, RPI * j + q);
+                    if (w_j != 0.0f) {
+                        const float4 s = sigmoid4(x[jj]);
+                        float4 a = accs[j * 32];
+                        a.x = fmaf(w_j, s.x, a.x);
+                        a.y = fmaf(w_j, s.y, a.y);
+                        a.z = fmaf(w_j, s.z, a.z);
+                        a.w = fmaf(w_j, s.w, a.w);
+                        accs[j * 32] = a;
+                    }
+                }
+            }
+            // ---- S3 (once, after the first batch) ------------------------------------------------------------------
+            if (b == 0 && trav) {
+                n_t = ray.t;
+                probe_end<ACCEL>(tr, pb, ray, opt.step, n_idx, n_dt);
+                ray.t += n_dt;
+                if (!(ray.t < ray.tmax)) trav_done = true;
+            }
         }
-
-        // ---- S3 -------------------------------------------------------------------------------------------------
-        p_idx = -1;
-        if (trav) {
-            p_t = ray.t;
-            probe_end<ACCEL>(tr, pb, ray, opt.step, p_idx, p_dt);
-            ray.t += p_dt;
-            if (!(ray.t < ray.tmax)) trav_done = true;
-        }
-        if (stopped) { p_idx = -1; trav_done = true; }
+        if (stopped) { n_idx = -1; trav_done = true; }
+        p_idx = n_idx; p_dt = n_dt; p_t = n_t;
         const int fin = (active && trav_done && p_idx < 0) ? (stopped ? 2 : 1) : 0;
 
-        // ---- S4: request the rows of the new candidates ---------------------------------------------------------------
-        // unconditional on purpose: a guarded load turns x into a phi and the register copies stall on the data
+        // ---- S4: request batch 0 of the new candidates. Unconditional on purpose: a guarded load turns x into a
+        // phi and the register copies stall on the data; row 0 stands in for "no candidate".
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            const int idx = max(__shfl_sync(FULL, p_idx, RPI * j + q), 0);            // row 0 stands in for "none"
-            x[j] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
+        for (int jj = 0; jj < NB; ++jj) {
+            const int idx = max(__shfl_sync(FULL, p_idx, RPI * jj + q), 0);
+            x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
         }
 
         const unsigned fm = __ballot_sync(FULL, fin != 0);
@@ -497,10 +230,11 @@ march_fwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
 }
 
 template <int LPR, bool ACCEL, bool IMAGE>
-__global__ void __launch_bounds__(BLOCK, SVOXB_BWD_MINB)
-march_bwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restrict__ grad_out,
+__global__ void __launch_bounds__(BLOCK, (LPR <= 8 ? 3 : (LPR == 16 ? 2 : 1)))
+march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restrict__ grad_out,
                       const float* __restrict__ saved_out, float* __restrict__ grad, unsigned long long* counter) {
-    constexpr int RPI = 32 / LPR, NB = LPR, DP = 4 * LPR;
+    using G = Quad<LPR>;
+    constexpr int RPI = G::RPI, NB = G::NB, NBATCH = G::NBATCH, RPB = G::RAYS_PER_BATCH, DP = 4 * LPR;
     extern __shared__ uint32_t smem_u32[];
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     uint32_t* top = smem_u32;
@@ -511,7 +245,7 @@ march_bwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
     const int D = tr.D, D4 = D >> 2;
     const bool lane_ok = c4 < D4, is_sig = c4 == D4 - 1;
     const int sig_src = (lane % RPI) * LPR + (D4 - 1);
-    const int red_src = (lane % RPI) * LPR + (lane / RPI);
+    const int red_src = (lane % RPI) * LPR + ((lane / RPI) % NB);     // lane holding this owner's reduced dot product
     const char* fbase = reinterpret_cast<const char*>(tr.features) + 16 * min(c4, D4 - 1);
     char* gbase = reinterpret_cast<char*>(grad) + 16 * c4;
     const unsigned row_bytes = (unsigned)D * 4u;
@@ -565,71 +299,85 @@ march_bwd_pipe_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
             else probe_begin<ACCEL>(tr, top, ray, pb);
         }
 
-        // ---- S2: gradient of the pending candidates ------------------------------------------------------------------
-        if (__ballot_sync(FULL, p_idx >= 0)) {
-            float sig = 0.0f;
+        const unsigned pm = __ballot_sync(FULL, p_idx >= 0);
+        int n_idx = -1;
+        float n_dt = 0.0f;
 #pragma unroll
-            for (int jj = 0; jj < NB; ++jj) {
-                const float v = __shfl_sync(FULL, x[jj].w, sig_src);
-                if (lane / RPI == jj) sig = v;
-            }
-            float w = 0.0f, dd = 0.0f;
-            const bool hit = p_idx >= 0 && sig > 0.0f;                              // rt_kernel.cu:382,456
-            if (hit) {
-                const float att = expf(-p_dt * sig * ray.ds);
-                w = T * (1.0f - att);
-                dd = p_dt * ray.ds;
-                T *= att;
-            }
-            const unsigned hb = __ballot_sync(FULL, hit);
-            if (hb) {
-                float cp[NB];
+        for (int b = 0; b < NBATCH; ++b) {
+            if (b > 0) {
 #pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    const int r = RPI * j + q;
-                    const bool on = ((hb >> r) & 1u) && lane_ok;
-                    const float4 g4 = *reinterpret_cast<const float4*>(gs + r * DP + 4 * c4);
-                    const float4 s = sigmoid4(x[j]);
-                    const float sx = s.x * g4.x, sy = s.y * g4.y, sz = s.z * g4.z, sw = s.w * g4.w;
-                    cp[j] = on ? (sx + sy) + (sz + (is_sig ? 0.0f : sw)) : 0.0f;
-                    x[j] = make_float4(sx * (1.0f - s.x), sy * (1.0f - s.y), sz * (1.0f - s.z), sw * (1.0f - s.w));
+                for (int jj = 0; jj < NB; ++jj) {
+                    const int idx = max(__shfl_sync(FULL, p_idx, RPI * (b * NB + jj) + q), 0);
+                    x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
                 }
-                const float c_tot = quad_reduce<NB, LPR>(cp, lane);
-                const float c_own = __shfl_sync(FULL, c_tot, red_src);
-                float sgrad = 0.0f;
+            }
+            // ---- S2.b: gradient of batch b of the pending candidates ------------------------------------------------
+            const unsigned bm = NBATCH == 1 ? pm : (pm >> (RPB * b)) & ((1u << RPB) - 1u);
+            if (bm) {
+                float sig = 0.0f;
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) {
+                    const float v = __shfl_sync(FULL, x[jj].w, sig_src);
+                    if (lane / RPI == b * NB + jj) sig = v;
+                }
+                float w = 0.0f, dd = 0.0f;
+                const bool hit = (NBATCH == 1 || lane / RPB == b) && p_idx >= 0 && sig > 0.0f;   // rt_kernel.cu:382,456
                 if (hit) {
-                    accum -= w * c_own;                                              // rt_kernel.cu:479-480
-                    sgrad = dd * (c_own * T - accum) + dd * gop * T_end;             // rt_kernel.cu:486-490
+                    const float att = expf(-p_dt * sig * ray.ds);
+                    w = T * (1.0f - att);
+                    dd = p_dt * ray.ds;
+                    T *= att;
                 }
+                const unsigned hb = __ballot_sync(FULL, hit);
+                if (hb) {
+                    float cp[NB];
+                    float4 sv[NB];
 #pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    const int r = RPI * j + q;
-                    const float w_j = __shfl_sync(FULL, w, r);
-                    const float sg_j = __shfl_sync(FULL, sgrad, r);
-                    const int idx_j = __shfl_sync(FULL, p_idx, r);
-                    if (((hb >> r) & 1u) && lane_ok) {
-                        float* grow = reinterpret_cast<float*>(gbase + (size_t)(unsigned)idx_j * row_bytes);
-                        red_add_v4(grow, w_j * x[j].x, w_j * x[j].y, w_j * x[j].z, is_sig ? sg_j : w_j * x[j].w);
+                    for (int jj = 0; jj < NB; ++jj) {
+                        const int r = RPI * (b * NB + jj) + q;
+                        const bool on = ((hb >> r) & 1u) && lane_ok;
+                        const float4 g4 = *reinterpret_cast<const float4*>(gs + r * DP + 4 * c4);
+                        const float4 s = sigmoid4(x[jj]);
+                        const float sx = s.x * g4.x, sy = s.y * g4.y, sz = s.z * g4.z, sw = s.w * g4.w;
+                        cp[jj] = on ? (sx + sy) + (sz + (is_sig ? 0.0f : sw)) : 0.0f;
+                        sv[jj] = make_float4(sx * (1.0f - s.x), sy * (1.0f - s.y), sz * (1.0f - s.z), sw * (1.0f - s.w));
+                    }
+                    const float c_tot = quad_reduce<NB, LPR>(cp, lane);
+                    const float c_own = __shfl_sync(FULL, c_tot, red_src);
+                    float sgrad = 0.0f;
+                    if (hit) {
+                        accum -= w * c_own;                                              // rt_kernel.cu:479-480
+                        sgrad = dd * (c_own * T - accum) + dd * gop * T_end;             // rt_kernel.cu:486-490
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {
+                        const int r = RPI * (b * NB + jj) + q;
+                        const float w_j = __shfl_sync(FULL, w, r);
+                        const float sg_j = __shfl_sync(FULL, sgrad, r);
+                        const int idx_j = __shfl_sync(FULL, p_idx, r);
+                        if (((hb >> r) & 1u) && lane_ok) {
+                            float* grow = reinterpret_cast<float*>(gbase + (size_t)(unsigned)idx_j * row_bytes);
+                            red_add_v4(grow, w_j * sv[jj].x, w_j * sv[jj].y, w_j * sv[jj].z,
+                                       is_sig ? sg_j : w_j * sv[jj].w);
+                        }
                     }
                 }
             }
+            // ---- S3 (once, after the first batch) ------------------------------------------------------------------
+            if (b == 0 && trav) {
+                probe_end<ACCEL>(tr, pb, ray, opt.step, n_idx, n_dt);
+                ray.t += n_dt;
+                if (!(ray.t < ray.tmax)) trav_done = true;
+            }
         }
-
-        // ---- S3 -------------------------------------------------------------------------------------------------
-        p_idx = -1;
-        if (trav) {
-            probe_end<ACCEL>(tr, pb, ray, opt.step, p_idx, p_dt);
-            ray.t += p_dt;
-            if (!(ray.t < ray.tmax)) trav_done = true;
-        }
+        p_idx = n_idx; p_dt = n_dt;
         const bool fin = active && trav_done && p_idx < 0;
 
         // ---- S4 -------------------------------------------------------------------------------------------------
-        // unconditional on purpose: a guarded load turns x into a phi and the register copies stall on the data
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            const int idx = max(__shfl_sync(FULL, p_idx, RPI * j + q), 0);            // row 0 stands in for "none"
-            x[j] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
+        for (int jj = 0; jj < NB; ++jj) {
+            const int idx = max(__shfl_sync(FULL, p_idx, RPI * jj + q), 0);
+            x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
         }
         const unsigned fm = __ballot_sync(FULL, fin);
         if (fm) {
@@ -651,11 +399,8 @@ static int lpr_for(int D) {
 template <int LPR, bool ACCEL, bool IMAGE>
 static int launch_fwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
-    size_t smem = ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0;
-    if (LPR <= 8) smem += sizeof(float4) * WARPS * 32 * LPR;          // pipelined kernel: accumulators in smem
-    void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
-    if constexpr (LPR <= 8) kern = march_fwd_pipe_kernel<LPR, ACCEL, IMAGE>;
-    else kern = march_fwd_quad_kernel<LPR, ACCEL, IMAGE>;
+    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * WARPS * 32 * LPR;
+    auto kern = march_fwd_quad_kernel<LPR, ACCEL, IMAGE>;
     int grid = 0;
     int rc = persistent_grid(kern, smem, src.total, grid);
     if (rc) return rc;
@@ -670,9 +415,7 @@ template <int LPR, bool ACCEL, bool IMAGE>
 static int launch_bwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const float* go, const float* so,
                         float* grad, cudaStream_t st) {
     const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * WARPS * 32 * 4 * LPR;
-    void (*kern)(TreeArgs, RaySource, MarchOpts, const float*, const float*, float*, unsigned long long*);
-    if constexpr (LPR <= 8) kern = march_bwd_pipe_kernel<LPR, ACCEL, IMAGE>;
-    else kern = march_bwd_quad_kernel<LPR, ACCEL, IMAGE>;
+    auto kern = march_bwd_quad_kernel<LPR, ACCEL, IMAGE>;
     int grid = 0;
     int rc = persistent_grid(kern, smem, src.total, grid);
     if (rc) return rc;
