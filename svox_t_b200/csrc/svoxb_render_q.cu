@@ -79,8 +79,14 @@ struct Quad {
 //   S3   probe_end   : brick word consumed -> new candidates, t advanced
 //   S2.b request rows of batch b, composite it            (b = 1 .. NBATCH-1; latency hides behind S3 / S2.b-1)
 //   S4   request rows of batch 0 of the new candidates, flush finished rays, refill
-template <int LPR, bool ACCEL, bool IMAGE>
-__global__ void __launch_bounds__(BLOCK, (LPR <= 8 ? 3 : (LPR == 16 ? 2 : 1)))
+#ifndef SVOXB_FWD_MINB
+#define SVOXB_FWD_MINB 3
+#endif
+#ifndef SVOXB_BWD_MINB
+#define SVOXB_BWD_MINB 3
+#endif
+template <int LPR, bool ACCEL, bool IMAGE, bool DEPTH>
+__global__ void __launch_bounds__(BLOCK, (LPR <= 8 ? SVOXB_FWD_MINB : (LPR == 16 ? 2 : 1)))
 march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
                       unsigned long long* counter) {
     using G = Quad<LPR>;
@@ -108,7 +114,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     for (int j = 0; j < LPR; ++j) accs[j * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     Ray ray;
-    float T = 1.0f, depth_v = 0.0f, p_dt = 0.0f, p_t = 0.0f;
+    float T = 1.0f, p_dt = 0.0f, p_t = 0.0f;
     int row = 0, p_idx = -1;
     bool active = false, got_depth = false, trav_done = true;
     Queue qu{0, 0, false};
@@ -117,7 +123,10 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     while (true) {
         if (need) {
             const unsigned got = refill<IMAGE>(src, off, scl, counter, qu, need, lane, ray, row);
-            if ((got >> lane) & 1u) { active = true; trav_done = false; T = 1.0f; got_depth = false; depth_v = 0.0f; }
+            if ((got >> lane) & 1u) {
+                active = true; trav_done = false; T = 1.0f; got_depth = false;
+                if (DEPTH) depth[row] = 0.0f;           // overwritten at the first hit, if any
+            }
             need = 0;
         }
         if (__ballot_sync(FULL, active) == 0u) break;
@@ -156,7 +165,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                 if ((NBATCH == 1 || lane / RPB == b) && p_idx >= 0 && sig > opt.sigma_thresh) {
                     const float att = expf(-p_dt * ray.ds * sig);                     // rt_kernel.cu:280
                     w = T * (1.0f - att);
-                    if (!got_depth) { depth_v = ray.ds * p_t; got_depth = true; }     // rt_kernel.cu:826-830
+                    if (DEPTH && !got_depth) { depth[row] = ray.ds * p_t; got_depth = true; }   // rt_kernel.cu:826-830
                     T *= att;
                     if (T <= opt.stop_thresh) stopped = true;                         // rt_kernel.cu:313
                 }
@@ -177,7 +186,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             }
             // ---- S3 (once, after the first batch) ------------------------------------------------------------------
             if (b == 0 && trav) {
-                n_t = ray.t;
+                if (DEPTH) n_t = ray.t;
                 probe_end<ACCEL>(tr, pb, ray, opt.step, n_idx, n_dt);
                 ray.t += n_dt;
                 if (!(ray.t < ray.tmax)) trav_done = true;
@@ -220,17 +229,14 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                     }
                 }
             }
-            if (fin != 0) {
-                if (depth) depth[row] = depth_v;
-                active = false;
-            }
+            if (fin != 0) active = false;
             need = fm;
         }
     }
 }
 
 template <int LPR, bool ACCEL, bool IMAGE>
-__global__ void __launch_bounds__(BLOCK, (LPR <= 8 ? 3 : (LPR == 16 ? 2 : 1)))
+__global__ void __launch_bounds__(BLOCK, (LPR <= 8 ? SVOXB_BWD_MINB : (LPR == 16 ? 2 : 1)))
 march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restrict__ grad_out,
                       const float* __restrict__ saved_out, float* __restrict__ grad, unsigned long long* counter) {
     using G = Quad<LPR>;
@@ -400,7 +406,9 @@ template <int LPR, bool ACCEL, bool IMAGE>
 static int launch_fwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
     const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * WARPS * 32 * LPR;
-    auto kern = march_fwd_quad_kernel<LPR, ACCEL, IMAGE>;
+    void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
+    if (depth) kern = march_fwd_quad_kernel<LPR, ACCEL, IMAGE, true>;
+    else kern = march_fwd_quad_kernel<LPR, ACCEL, IMAGE, false>;
     int grid = 0;
     int rc = persistent_grid(kern, smem, src.total, grid);
     if (rc) return rc;
