@@ -1,0 +1,35 @@
+"""Small end-to-end run for compute-sanitizer: every kernel family once on tiny inputs."""
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import numpy as np, torch
+import svox_t_b200 as sv
+from svox_t_b200 import synth, csrc as C
+dev = torch.device("cuda:0"); torch.cuda.set_device(0)
+for (L, shape, D, accel) in [(4, "ball", 32, True), (3, "ball", 16, False), (4, "ball", 64, True), (3, "ball", 9, True), (5, "shell", 100, True)]:
+    tr = synth.synth_tree(L, shape, r_out=0.45, r_in=0.2)
+    f = synth.synth_features(tr["M"], D)
+    o, d = synth.synth_rays(700)
+    tree = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=D, map_location=dev)
+    tree.extra_data = torch.rand(4, 3, device=dev)
+    feats = torch.from_numpy(f).to(dev).requires_grad_(True)
+    rays = sv.Rays(*(torch.from_numpy(a).to(dev) for a in (o, d, d)))
+    r = sv.VolumeRenderer(tree)
+    if not accel:
+        tree.accel = lambda *a, **k: None
+    out, depth = r.forward_with_depth(feats, rays)
+    out.sum().backward()
+    img, dep = r.render_persp_with_depth(feats.detach(), torch.from_numpy(synth.synth_cameras(1)[0]).to(dev), width=37, height=21, fx=30.0)
+    img2 = r.render_persp(feats, torch.from_numpy(synth.synth_cameras(1)[0]).to(dev), width=37, height=21, fx=30.0)
+    img2.sum().backward()
+    r.render_depth(feats.detach(), rays); r.opacity_render(feats, rays).sum().backward(); r.motion_render(feats.detach(), rays)
+    tree(feats.detach(), torch.rand(500, 3, device=dev), want_node_ids=True, want_leaf_node=True)
+pts = torch.rand(3000, 3, device=dev) * 0.5 + 0.25
+t2 = sv.N3Tree(N=2, data_dim=8, map_location=dev).build_from_points(pts, 5)
+t3 = sv.N3Tree(N=2, data_dim=8, init_reserve=8, map_location=dev)
+for _ in range(3): t3[pts].refine()
+t3.construct_tree(pts)
+Tm, w, ji = synth.synth_skeleton(3000)
+wv, mats = sv.warp_vertices(torch.from_numpy(Tm).to(dev), pts, torch.from_numpy(w).to(dev), torch.from_numpy(ji).to(dev))
+sv.voxelize(wv, torch.rand(3000, 4, device=dev), torch.zeros(3, device=dev), torch.ones(3, device=dev), 32, 0.05, 0.07)
+torch.cuda.synchronize()
+print("sanitize_small done, launches", C.launch_count())
