@@ -180,6 +180,18 @@ SVOXB_API int svoxb_p2v(const float* points, const float* point_features, int64_
               const float* corner, const float* size, int32_t n_voxels, float kernel_radius, float conv_radius,
               float* voxels, void* stream);
 
+/* warp_vertices_backward (svox_kernel.cu:156-211, 404-436): grad_T[J,4,4] (zero-filled here; rows 0..2 receive),
+ * grad_coords[P,3], grad_w[P,B] from the upstream gradients of coords_out[P,3] and mats_out[P,4,4]. */
+SVOXB_API int svoxb_warp_vertices_bwd(const float* T, const float* coords, const float* w, const int32_t* joint_index,
+                            const float* grad_coords_out, const float* grad_mats_out, int64_t P, int32_t B, int32_t J,
+                            float* grad_T, float* grad_coords, float* grad_w, void* stream);
+
+/* p2v_backward (p2v_kernel.cu:153-234, 263-285): grad_points[P,3], grad_features[P,F] (zero-filled here; the value
+ * lands in channel 0 exactly as in the reference) from grad_voxels[n,n,n,1]. */
+SVOXB_API int svoxb_p2v_bwd(const float* grad_voxels, const float* points, const float* point_features, int64_t P,
+                  int32_t F, const float* corner, const float* size, int32_t n_voxels, float kernel_radius,
+                  float conv_radius, float* grad_points, float* grad_features, void* stream);
+
 /* One-shot octree build from points (replaces the reference's depth-1 rounds of
  * query_vertical + N3Tree.refine, svox_t/svox.py:488-560 + helpers.py:38-109, and the final construct_tree):
  * emits child/data/parent_depth in the reference tensor format for the octree whose depth-L leaves are the

@@ -228,3 +228,28 @@ def p2v(points, feat, corner, size, n_voxels, kernel_radius, conv_radius, dtype=
                                      ctypes.c_int(feat.shape[1]), _p(corner), _p(size), ctypes.c_int(n_voxels),
                                      cr(kernel_radius), cr(conv_radius), _p(vox))
     return vox
+
+
+def warp_vertices_backward(T, coords, weights, joint_index, g_coords, g_mats, dtype=np.float32):
+    """-> grad_coords[P,3], grad_T[J,4,4], grad_w[P,B]."""
+    sfx, _ = _sfx(dtype)
+    T, coords, weights = _c(T, dtype), _c(coords, dtype), _c(weights, dtype)
+    g_coords, g_mats = _c(g_coords, dtype), _c(g_mats, dtype)
+    ji = _c(joint_index, np.int32)
+    P, B = weights.shape
+    gT, gx, gw = np.zeros_like(T), np.zeros((P, 3), dtype=dtype), np.zeros((P, B), dtype=dtype)
+    getattr(lib(), "orc_warp_vertices_backward" + sfx)(_p(T), _p(coords), _p(weights), _p(ji), _p(g_coords), _p(g_mats),
+                                                        ctypes.c_int64(P), ctypes.c_int(B), _p(gT), _p(gx), _p(gw))
+    return gx, gT, gw
+
+
+def p2v_backward(g_vox, points, feat, corner, size, n_voxels, kernel_radius, conv_radius, dtype=np.float32):
+    """-> grad_points[P,3], grad_feat[P,F] (value in channel 0, as the reference writes it)."""
+    sfx, cr = _sfx(dtype)
+    g_vox, points, feat = _c(g_vox, dtype), _c(points, dtype), _c(feat, dtype)
+    corner, size = _c(corner, dtype), _c(size, dtype)
+    gp, gf = np.zeros_like(points), np.zeros_like(feat)
+    getattr(lib(), "orc_p2v_backward" + sfx)(_p(g_vox), _p(points), _p(feat), ctypes.c_int64(points.shape[0]),
+                                              ctypes.c_int(feat.shape[1]), _p(corner), _p(size), ctypes.c_int(n_voxels),
+                                              cr(kernel_radius), cr(conv_radius), _p(gp), _p(gf))
+    return gp, gf

@@ -74,6 +74,8 @@ SYMBOLS = {
     "svoxb_opacity_render_bwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP, _VP]),
     "svoxb_motion_render": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _I32, _VP, _VP, _VP, _VP, _VP]),
     "svoxb_warp_vertices": (ctypes.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _VP, _VP, _VP]),
+    "svoxb_warp_vertices_bwd": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _I32, _I32, _VP, _VP, _VP, _VP]),
+    "svoxb_p2v_bwd": (ctypes.c_int, [_VP, _VP, _VP, _I64, _I32, _VP, _VP, _I32, _F, _F, _VP, _VP, _VP]),
     "svoxb_p2v": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP, _VP, _I32, _F, _F, _VP, _VP]),
     "svoxb_build_work_bytes": (ctypes.c_size_t, [_I64, _I32]),
     "svoxb_build_octree_count": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP, _VP, ctypes.POINTER(_I64), _VP]),
@@ -487,6 +489,41 @@ def warp_vertices(matrices, indices, skinning_weights, joint_index):
     return [vout, mout]
 
 
+def warp_vertices_backward(matrices, indices, skinning_weights, joint_index, indices_grad_out, matrices_grad_out):
+    """[grad_indices[P,3], grad_matrices[J,4,4], grad_skinning_weights[P,B]] (svox_kernel.cu:404-436)."""
+    lib = load_library()
+    for t, n in ((matrices, "matrices"), (indices, "indices"), (skinning_weights, "skinning_weights"),
+                 (indices_grad_out, "indices_grad_out"), (matrices_grad_out, "matrices_grad_out")):
+        _check_input(t, n, torch.float32)
+    _check_input(joint_index, "joint_index", torch.int32)
+    P, B = skinning_weights.shape
+    J, dev = matrices.shape[0], indices.device
+    with torch.cuda.device(dev):
+        g_T = torch.empty((J, 4, 4), dtype=torch.float32, device=dev)
+        g_x = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        g_w = torch.empty((P, B), dtype=torch.float32, device=dev)
+        _check(lib.svoxb_warp_vertices_bwd(_ptr(matrices), _ptr(indices), _ptr(skinning_weights), _ptr(joint_index),
+                                           _ptr(indices_grad_out), _ptr(matrices_grad_out), P, B, J, _ptr(g_T), _ptr(g_x),
+                                           _ptr(g_w), _stream()))
+    return [g_x, g_T, g_w]
+
+
+def p2v_backward(grad_output, points, point_features, volume_corner, volume_size, n_voxels, kernel_radius, conv_radius):
+    """[points_grad[P,3], point_features_grad[P,F]] (p2v_kernel.cu:263-285)."""
+    lib = load_library()
+    for t, n in ((grad_output, "grad_output"), (points, "points"), (point_features, "point_features"),
+                 (volume_corner, "volume_corner"), (volume_size, "volume_size")):
+        _check_input(t, n, torch.float32)
+    P, F, dev = points.shape[0], point_features.shape[1], points.device
+    with torch.cuda.device(dev):
+        g_p = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        g_f = torch.empty((P, F), dtype=torch.float32, device=dev)
+        _check(lib.svoxb_p2v_bwd(_ptr(grad_output), _ptr(points), _ptr(point_features), P, F, _ptr(volume_corner),
+                                 _ptr(volume_size), int(n_voxels), float(kernel_radius), float(conv_radius), _ptr(g_p),
+                                 _ptr(g_f), _stream()))
+    return [g_p, g_f]
+
+
 def p2v(points, point_features, volume_corner, volume_size, n_voxels, kernel_radius, conv_radius):
     """[n, n, n, 1] Gaussian splat (p2v_kernel.cu:240-261)."""
     lib = load_library()
@@ -539,8 +576,6 @@ def _unsupported(name, why):
 # `hasattr(_C, name)` behaves, but they raise instead of silently doing something else.
 query_vertical_backward = _unsupported("query_vertical_backward", "faults in the reference (Appendix B1); out of scope")
 assign_vertical = _unsupported("assign_vertical", "faults in the reference (Appendix B1); out of scope")
-warp_vertices_backward = _unsupported("warp_vertices_backward", "next-rank component (SURVEY 8f rank 2)")
-p2v_backward = _unsupported("p2v_backward", "next-rank component (SURVEY 8f rank 2)")
 motion_feature_render = _unsupported("motion_feature_render", "next-rank component (SURVEY 8f rank 3)")
 motion_feature_render_backward = _unsupported("motion_feature_render_backward", "buggy in the reference (Appendix B3)")
 calc_corners = _unsupported("calc_corners", "dtype bug in the reference (Appendix B4); out of scope")

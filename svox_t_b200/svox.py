@@ -48,17 +48,24 @@ class _QueryVerticalFunction(autograd.Function):
 
 
 class _WarpVerticalFunction(autograd.Function):
-    """svox.py:58-75 (forward only; warp_vertices_backward is a next-rank component)."""
+    """svox.py:58-75."""
 
     @staticmethod
     def forward(ctx, transformation_matrix, coordinates, skinning_weights, joint_index):
         vertices, matrices = _C.warp_vertices(transformation_matrix, coordinates, skinning_weights, joint_index)
-        ctx.mark_non_differentiable(vertices, matrices)
+        ctx.save_for_backward(transformation_matrix, coordinates, skinning_weights, joint_index)
         return vertices, matrices
 
     @staticmethod
-    def backward(ctx, *grads):
-        raise RuntimeError("warp_vertices backward is not implemented in svox_t_b200 (SURVEY 8f rank 2)")
+    def backward(ctx, vertices_grad_out, matrices_grad_out):
+        T, x, w, ji = ctx.saved_tensors
+        if vertices_grad_out is None:
+            vertices_grad_out = torch.zeros_like(x)
+        if matrices_grad_out is None:
+            matrices_grad_out = torch.zeros(x.shape[0], 4, 4, dtype=x.dtype, device=x.device)
+        g_x, g_T, g_w = _C.warp_vertices_backward(T, x, w, ji, vertices_grad_out.contiguous(),
+                                                  matrices_grad_out.contiguous())
+        return g_T, g_x, g_w, None
 
 
 class N3Tree(nn.Module):

@@ -22,7 +22,7 @@ def golden_files():
 
 def golden_variant_files():
     """Fixtures of the march variants (opacity_render, motion_render)."""
-    return sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("x_"))
+    return sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("x_ball"))
 
 
 @pytest.fixture(scope="session")

@@ -47,3 +47,26 @@ if __name__ == "__main__":
                         parent_depth=tr["parent_depth"], features=f, offset=off, scaling=inv, origins=o, dirs=d,
                         extra=extra, **res)
     print("ok", {k: v.shape for k, v in res.items()})
+
+    # ---- point kernels: LBS warp + p2v splat, forward and backward, from the reference extension ----------------------
+    rng = np.random.default_rng(12)
+    P, Jn, B, nv, kr, cr = 3000, 6, 4, 24, 1.5 / 24, 2.0 / 24
+    Tm, w, ji = synth.synth_skeleton(P, J=Jn, B=B, seed=5)
+    w[::5, 2] = 0.0
+    pts = (0.5 + 0.5 * (rng.random((P, 3)) - 0.5)).astype(np.float32)
+    feat = rng.random((P, 3)).astype(np.float32) * 4 - 1
+    corner, size = np.zeros(3, np.float32), np.ones(3, np.float32)
+    g_c = rng.standard_normal((P, 3)).astype(np.float32)
+    g_m = rng.standard_normal((P, 4, 4)).astype(np.float32)
+    g_v = rng.standard_normal((nv, nv, nv, 1)).astype(np.float32)
+    co, mats = m.warp_vertices(t(Tm), t(pts), t(w), t(ji))
+    gx, gT, gw = m.warp_vertices_backward(t(Tm), t(pts), t(w), t(ji), t(g_c), t(g_m))
+    vox = m.p2v(co, t(feat), t(corner), t(size), nv, kr, cr)
+    gp, gf = m.p2v_backward(t(g_v), co, t(feat), t(corner), t(size), nv, kr, cr)
+    np.savez_compressed(os.path.join(out_dir, "x_points_lbs_p2v.npz"), T=Tm, pts=pts, w=w, ji=ji, feat=feat,
+                        corner=corner, size=size, n_voxels=nv, kernel_radius=np.float32(kr), conv_radius=np.float32(cr),
+                        g_coords=g_c, g_mats=g_m, g_vox=g_v,
+                        ref_coords=co.cpu().numpy(), ref_mats=mats.cpu().numpy(), ref_gx=gx.cpu().numpy(),
+                        ref_gT=gT.cpu().numpy(), ref_gw=gw.cpu().numpy(), ref_vox=vox.cpu().numpy(),
+                        ref_gp=gp.cpu().numpy(), ref_gf=gf.cpu().numpy())
+    print("points fixture ok")

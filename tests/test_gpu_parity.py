@@ -287,6 +287,40 @@ def test_march_variants_against_reference_golden(dev, name, accel):
     assert torch.allclose(full[:, -1:], C.opacity_render(ts, rs, r._get_options()), atol=1e-6)
 
 
+def test_point_kernels_forward_backward_against_reference_golden(dev):
+    z = np.load(os.path.join(GOLDEN_DIR, "x_points_lbs_p2v.npz"))
+    T = cu(z["T"], dev).requires_grad_(True)
+    x = cu(z["pts"], dev).requires_grad_(True)
+    w = cu(z["w"], dev).requires_grad_(True)
+    co, mats = sv.warp_vertices(T, x, w, cu(z["ji"], dev))
+    assert np.allclose(co.detach().cpu().numpy(), z["ref_coords"], atol=1e-6)
+    assert np.allclose(mats.detach().cpu().numpy(), z["ref_mats"], atol=1e-6)
+    ((co * cu(z["g_coords"], dev)).sum() + (mats * cu(z["g_mats"], dev)).sum()).backward()
+    assert np.allclose(x.grad.cpu().numpy(), z["ref_gx"], atol=1e-5)
+    assert np.allclose(w.grad.cpu().numpy(), z["ref_gw"], atol=1e-5)
+    assert rel_l2(T.grad.cpu().numpy(), z["ref_gT"]) <= 1e-4
+    n, kr, cr = int(z["n_voxels"]), float(z["kernel_radius"]), float(z["conv_radius"])
+    p = cu(z["ref_coords"], dev).requires_grad_(True)
+    f = cu(z["feat"], dev).requires_grad_(True)
+    vox = sv.voxelize(p, f, cu(z["corner"], dev), cu(z["size"], dev), n, kr, cr)
+    assert np.allclose(vox.detach().cpu().numpy(), z["ref_vox"], rtol=1e-4, atol=1e-4)
+    (vox * cu(z["g_vox"], dev)).sum().backward()
+    assert np.allclose(f.grad.cpu().numpy(), z["ref_gf"], rtol=1e-4, atol=1e-4)
+    assert np.allclose(p.grad.cpu().numpy(), z["ref_gp"], rtol=1e-3, atol=1e-2)
+    # many joints: the bone-gradient table no longer fits shared memory -> global-atomic path
+    P, J = 4000, 5000
+    rng = np.random.default_rng(1)
+    Tb = rng.standard_normal((J, 4, 4)).astype(np.float32)
+    wb = rng.dirichlet(np.ones(3), P).astype(np.float32)
+    jb = rng.integers(0, J, (P, 3)).astype(np.int32)
+    xb = rng.random((P, 3)).astype(np.float32)
+    gc, gm = rng.standard_normal((P, 3)).astype(np.float32), rng.standard_normal((P, 4, 4)).astype(np.float32)
+    gx, gT, gw = C.warp_vertices_backward(cu(Tb, dev), cu(xb, dev), cu(wb, dev), cu(jb, dev), cu(gc, dev), cu(gm, dev))
+    ox, oT, ow = orc.warp_vertices_backward(Tb, xb, wb, jb, gc, gm)
+    assert np.allclose(gx.cpu().numpy(), ox, atol=1e-4) and np.allclose(gw.cpu().numpy(), ow, atol=1e-4)
+    assert rel_l2(gT.cpu().numpy(), oT) <= 1e-5
+
+
 # ---- (3) the compiled reference itself, when it travelled to this box -----------------------------------------------
 @pytest.mark.skipif(not os.path.exists(refdrv.REF_SO), reason="oracle/_ref not built")
 def test_against_live_reference_extension(dev):

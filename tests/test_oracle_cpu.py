@@ -162,6 +162,38 @@ def test_lbs_and_splat_small():
     assert vox[1, 1, 1, 0] == pytest.approx(2.0) and vox.sum() == pytest.approx(2.0)   # only the centre voxel in range
 
 
+def test_point_kernel_backwards_match_finite_differences_fp64():
+    rng = np.random.default_rng(3)
+    P, J, B = 40, 5, 3
+    T = rng.standard_normal((J, 4, 4)); T[:, 3] = [0, 0, 0, 1]
+    x = rng.random((P, 3)); w = rng.dirichlet(np.ones(B), P); w[::4, 1] = 0.0
+    ji = rng.integers(0, J, (P, B)).astype(np.int32)
+    gc, gm = rng.standard_normal((P, 3)), rng.standard_normal((P, 4, 4))
+    gx, gT, gw = orc.warp_vertices_backward(T, x, w, ji, gc, gm, dtype=np.float64)
+
+    def loss(T_, x_, w_):
+        co, mats = orc.warp_vertices(T_, x_, w_, ji, dtype=np.float64)
+        return float((co * gc).sum() + (mats[:, :3] * gm[:, :3]).sum())
+    for arr, grad, idx in ((T, gT, (2, 1, 3)), (x, gx, (7, 2)), (w, gw, (9, 2)), (T, gT, (0, 0, 0))):
+        ap, am = arr.copy(), arr.copy()
+        ap[idx] += 1e-6; am[idx] -= 1e-6
+        args = lambda a: (a if arr is T else T, a if arr is x else x, a if arr is w else w)
+        fd = (loss(*args(ap)) - loss(*args(am))) / 2e-6
+        assert abs(fd - grad[idx]) <= 1e-6 + 1e-5 * abs(fd), (idx, fd, grad[idx])
+    pts = 0.3 + 0.4 * rng.random((30, 3)); feat = rng.random((30, 2)) + 0.5
+    corner, size, n = np.zeros(3), np.ones(3), 12
+    gv = rng.standard_normal((n, n, n, 1))
+    gp, gf = orc.p2v_backward(gv, pts, feat, corner, size, n, 0.12, 0.2, dtype=np.float64)
+    lossv = lambda p_, f_: float((orc.p2v(p_, f_, corner, size, n, 0.12, 0.2, dtype=np.float64) * gv).sum())
+    fp, fm = feat.copy(), feat.copy(); fp[4, 1] += 1e-6; fm[4, 1] -= 1e-6
+    assert abs((lossv(pts, fp) - lossv(pts, fm)) / 2e-6 - gf[4, 0]) < 1e-5          # value sits in channel 0 (App. B12)
+    assert not gf[:, 1:].any()
+    # position gradient: the splat's footprint is discontinuous at the cutoff, so check a point away from it loosely
+    pp, pm = pts.copy(), pts.copy(); pp[3, 0] += 1e-7; pm[3, 0] -= 1e-7
+    fd = (lossv(pp, feat) - lossv(pm, feat)) / 2e-7
+    assert abs(fd - gp[3, 0]) <= 1e-3 * max(1.0, abs(fd))
+
+
 def test_construct_tree_highest_index_wins():
     tr = synth.synth_tree(2, "all")
     T = orc.Tree(tr["child"], tr["data"].copy())
@@ -227,6 +259,23 @@ def test_variant_oracle_matches_reference_golden(name):
         assert np.allclose(dep[same], z["motion_depth_" + tag][same], atol=1e-5)
         assert np.allclose(hit[same], z["motion_hit_" + tag][same], atol=1e-5)
         assert np.allclose(out[same], z["motion_out_" + tag][same], atol=1e-5)
+
+
+def test_point_kernel_oracle_matches_reference_golden():
+    path = os.path.join(GOLDEN_DIR, "x_points_lbs_p2v.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated yet")
+    z = np.load(path)
+    co, mats = orc.warp_vertices(z["T"], z["pts"], z["w"], z["ji"])
+    assert np.allclose(co, z["ref_coords"], atol=1e-6) and np.allclose(mats, z["ref_mats"], atol=1e-6)
+    gx, gT, gw = orc.warp_vertices_backward(z["T"], z["pts"], z["w"], z["ji"], z["g_coords"], z["g_mats"])
+    assert np.allclose(gx, z["ref_gx"], atol=1e-5) and np.allclose(gw, z["ref_gw"], atol=1e-5)
+    assert np.linalg.norm(gT - z["ref_gT"]) <= 1e-4 * np.linalg.norm(z["ref_gT"])
+    n, kr, cr = int(z["n_voxels"]), float(z["kernel_radius"]), float(z["conv_radius"])
+    vox = orc.p2v(z["ref_coords"], z["feat"], z["corner"], z["size"], n, kr, cr)
+    assert np.allclose(vox, z["ref_vox"], rtol=1e-4, atol=1e-4)
+    gp, gf = orc.p2v_backward(z["g_vox"], z["ref_coords"], z["feat"], z["corner"], z["size"], n, kr, cr)
+    assert np.allclose(gf, z["ref_gf"], rtol=1e-4, atol=1e-4) and np.allclose(gp, z["ref_gp"], rtol=1e-3, atol=1e-2)
 
 
 def test_golden_fixtures_present():
