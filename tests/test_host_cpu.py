@@ -107,6 +107,14 @@ def test_no_cpu_fallback_anywhere():
         sv.csrc.volume_render(t._spec(t.features), sv.renderer._rays_spec_from_rays(rays), r._get_options())
 
 
+def test_drop_in_alias_package():
+    import svox_t
+    import svox_t.csrc as _C
+    assert svox_t.N3Tree is sv.N3Tree and svox_t.VolumeRenderer is sv.VolumeRenderer and svox_t.Rays is sv.Rays
+    # the reference probes its extension exactly like this (svox_t/helpers.py:363-376)
+    assert hasattr(_C, "query_vertical") and hasattr(_C, "volume_render") and hasattr(_C, "TreeSpec")
+
+
 def test_product_never_imports_the_oracle():
     root = os.path.join(os.path.dirname(__file__), "..", "svox_t_b200")
     pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle\.oracle|svox_oracle|_ref/", re.M)
