@@ -74,11 +74,13 @@ struct Quad {
 
 // ------------------------------------------------------------------------------------------------------------
 // Loop structure (NBATCH = 1 for D <= 32, 2 for D <= 64, 4 for D <= 128; x holds the rows of ONE batch):
+//   S0   request the rows of batch 0 of the pending candidates (found in the PREVIOUS iteration)
 //   S1   probe_begin : next sample position, top-grid lookup in shared memory, brick lookup ISSUED
-//   S2.0 composite batch 0 of the candidates found in the PREVIOUS iteration (their rows were requested at its end)
+//   S2.0 composite batch 0 (its rows have been in flight since S0)
 //   S3   probe_end   : brick word consumed -> new candidates, t advanced
 //   S2.b request rows of batch b, composite it            (b = 1 .. NBATCH-1; latency hides behind S3 / S2.b-1)
-//   S4   request rows of batch 0 of the new candidates, flush finished rays, refill
+//   S4   flush finished rays, refill; the rows of batch 0 of the new candidates are requested first thing in the
+//        next iteration (S0), ahead of S1
 #ifndef SVOXB_FWD_MINB
 #define SVOXB_FWD_MINB 3
 #endif
@@ -130,6 +132,15 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             need = 0;
         }
         if (__ballot_sync(FULL, active) == 0u) break;
+
+        // ---- S0: request the rows of batch 0 of the pending candidates. First thing in the iteration (a load left
+        // in flight across the loop back-edge is waited for at the loop header); unconditional on purpose (a guarded
+        // load turns x into a phi whose register copies stall on the data); row 0 stands in for "no candidate".
+#pragma unroll
+        for (int jj = 0; jj < NB; ++jj) {
+            const int idx = max(__shfl_sync(FULL, p_idx, RPI * jj + q), 0);
+            x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
+        }
 
         // ---- S1 -------------------------------------------------------------------------------------------------
         bool trav = active && !trav_done;
@@ -195,14 +206,6 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
         if (stopped) { n_idx = -1; trav_done = true; }
         p_idx = n_idx; p_dt = n_dt; p_t = n_t;
         const int fin = (active && trav_done && p_idx < 0) ? (stopped ? 2 : 1) : 0;
-
-        // ---- S4: request batch 0 of the new candidates. Unconditional on purpose: a guarded load turns x into a
-        // phi and the register copies stall on the data; row 0 stands in for "no candidate".
-#pragma unroll
-        for (int jj = 0; jj < NB; ++jj) {
-            const int idx = max(__shfl_sync(FULL, p_idx, RPI * jj + q), 0);
-            x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
-        }
 
         const unsigned fm = __ballot_sync(FULL, fin != 0);
         if (fm) {
@@ -297,6 +300,13 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
         }
         if (__ballot_sync(FULL, active) == 0u) break;
 
+        // ---- S0: rows of batch 0 of the pending candidates (see the forward kernel) ---------------------------------
+#pragma unroll
+        for (int jj = 0; jj < NB; ++jj) {
+            const int idx = max(__shfl_sync(FULL, p_idx, RPI * jj + q), 0);
+            x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
+        }
+
         // ---- S1 -------------------------------------------------------------------------------------------------
         bool trav = active && !trav_done;
         Probe pb;
@@ -379,12 +389,6 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
         p_idx = n_idx; p_dt = n_dt;
         const bool fin = active && trav_done && p_idx < 0;
 
-        // ---- S4 -------------------------------------------------------------------------------------------------
-#pragma unroll
-        for (int jj = 0; jj < NB; ++jj) {
-            const int idx = max(__shfl_sync(FULL, p_idx, RPI * jj + q), 0);
-            x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
-        }
         const unsigned fm = __ballot_sync(FULL, fin);
         if (fm) {
             if (fin) active = false;
