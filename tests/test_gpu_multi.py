@@ -1,0 +1,63 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): rays sharded over the ranks, tree + features
+replicated, NCCL all-reduce of the leaf gradients == the single-GPU gradient."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import svox_t_b200 as sv
+    from svox_t_b200 import dist as svd, synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    svd.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    tr = synth.synth_tree(6, "ball")
+    D, Q = 32, 40000
+    f = synth.synth_features(tr["M"], D)
+    o, d = synth.synth_rays(Q)
+    g = np.random.default_rng(5).standard_normal((Q, D)).astype(np.float32)
+    tree = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=D, map_location=dev)
+    feats = torch.from_numpy(f).to(dev).requires_grad_(True)
+    rays = sv.Rays(*(torch.from_numpy(a).to(dev) for a in (o, d, d)))
+    g_t = torch.from_numpy(g).to(dev)
+    r = sv.VolumeRenderer(tree)
+    loss, grad = svd.render_step_sharded(r, feats, rays, lambda out, lo, hi: (out * g_t[lo:hi]).sum(), rank, world)
+    torch.cuda.synchronize()
+    if rank == 0:
+        full = feats.detach().clone().requires_grad_(True)
+        (r(full, rays) * g_t).sum().backward()
+        rel = float((grad - full.grad).norm() / full.grad.norm())
+        q.put(rel)
+    svd.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_gradients_match_single_gpu():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    rel = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert rel < 1e-5, rel
