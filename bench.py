@@ -199,6 +199,7 @@ def main():
     def step(rec=None):
         e = [ev() for _ in range(4)] if rec is not None else None
         if e: e[0].record()
+        ts._act = C.Activated(feats)          # features change every training step: the activation pass is part of it
         out = C.volume_render(ts, rs, opt)
         if e: e[1].record()
         grad = torch.zeros_like(feats)
@@ -233,67 +234,64 @@ def main():
     launches = C.launch_count() - launches0
     total_ms = svd.max_over_ranks(e0.elapsed_time(e1), dev)
     ms_per_step = total_ms / args.steps
-    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in rec]))
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in rec]))       # includes the activation pass
     bwd_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in rec]))
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     value = world * Q / (ms_per_step * 1e-3) / 1e6
 
     # ---- end to end through the public API: pinned host rays + targets in, loss out, every step ----------------------
-    # The step streams its inputs: the batch is cut into E2E_CHUNKS ray chunks; a copy stream uploads chunk c+1 into
-    # the second of two device buffer sets while the default stream renders chunk c (forward, loss, backward through
-    # VolumeRenderer + autograd; features.grad accumulates over the chunks). One loss read-back closes the step.
-    E2E_CHUNKS = int(os.environ.get("SVOXB_E2E_CHUNKS", "2"))
+    # Data-loader style pipeline: two device buffer sets; while step k renders out of one, a copy stream uploads the
+    # inputs of step k+1 into the other. Every step's host->device copy and loss read-back happen inside the timed
+    # region (K uploads + K renders + K read-backs for K steps; the first upload is exposed, the rest overlap).
     h_o, h_d = torch.from_numpy(o).pin_memory(), torch.from_numpy(d).pin_memory()
     h_tgt = torch.rand(Q, D, generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
     fparam = feats.clone().requires_grad_(True)
-    cq = Q // E2E_CHUNKS
-    bufs = [(torch.empty(cq, 3, device=dev), torch.empty(cq, 3, device=dev), torch.empty(cq, D, device=dev))
+    bufs = [(torch.empty(Q, 3, device=dev), torch.empty(Q, 3, device=dev), torch.empty(Q, D, device=dev))
             for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
     free_ev = [None, None]
 
-    def upload(c):
-        bo, bd, bt = bufs[c & 1]
-        sl = slice(c * cq, (c + 1) * cq)
+    def upload(k):
+        bo, bd, bt = bufs[k & 1]
         with torch.cuda.stream(copy_stream):
-            if free_ev[c & 1] is not None:
-                copy_stream.wait_event(free_ev[c & 1])          # the chunk that last used this buffer set is done
-            bo.copy_(h_o[sl], non_blocking=True); bd.copy_(h_d[sl], non_blocking=True); bt.copy_(h_tgt[sl], non_blocking=True)
+            if free_ev[k & 1] is not None:
+                copy_stream.wait_event(free_ev[k & 1])          # the step that last used this buffer set is done
+            bo.copy_(h_o, non_blocking=True); bd.copy_(h_d, non_blocking=True); bt.copy_(h_tgt, non_blocking=True)
             e = torch.cuda.Event(); e.record(copy_stream)
         return e
 
-    def e2e_step():
-        fparam.grad = None
-        total = torch.zeros((), device=dev)
+    def e2e_run(n_steps):
+        losses = []
         ready = upload(0)
-        for c in range(E2E_CHUNKS):
-            nxt = upload(c + 1) if c + 1 < E2E_CHUNKS else None
+        for k in range(n_steps):
+            nxt = upload(k + 1) if k + 1 < n_steps else None
             main_stream.wait_event(ready)
-            bo, bd, bt = bufs[c & 1]
+            bo, bd, bt = bufs[k & 1]
+            fparam.grad = None
+            with torch.no_grad():
+                fparam.add_(0.0)                       # stands in for the optimiser update: features change every step
             out = renderer(fparam, sv.Rays(bo, bd, bd))
-            loss = 0.5 * ((out - bt) ** 2).sum() / (Q * D)
+            loss = 0.5 * ((out - bt) ** 2).mean()
             loss.backward()
-            total += loss.detach()
-            free_ev[c & 1] = torch.cuda.Event(); free_ev[c & 1].record(main_stream)
+            svd.all_reduce_leaf_grads(fparam.grad)
+            free_ev[k & 1] = torch.cuda.Event(); free_ev[k & 1].record(main_stream)
+            losses.append(float(loss.item()))          # device -> host read of the step's result
             ready = nxt
-        svd.all_reduce_leaf_grads(fparam.grad)
-        return float(total.item())                     # device -> host read of the step's result
+        return losses
 
-    for _ in range(3):
-        e2e_step()
+    e2e_run(3)
     svd.barrier(); torch.cuda.synchronize()
     e0, e1 = ev(), ev()
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     e1.record()
     torch.cuda.synchronize(); svd.barrier()
     e2e_ms = svd.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
     e2e = {"value": world * Q / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(h_o.numel() + h_d.numel() + h_tgt.numel()) * 4, "d2h_bytes_per_step": 4,
-           "api": f"VolumeRenderer.forward + autograd backward, loss = 0.5*mean((out-target)^2), inputs streamed from "
-                  f"pinned host memory in {E2E_CHUNKS} chunks (upload of chunk c+1 overlaps the render of chunk c)"}
+           "api": "VolumeRenderer.forward + autograd backward, loss = 0.5*mean((out-target)^2); inputs come from pinned "
+                  "host memory every step, the upload of step k+1 overlaps the render of step k (double buffering)"}
 
     if world > 1:
         import torch.distributed as tdist

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SVOXB_ABI_VERSION 1
+#define SVOXB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SVOXB_API __attribute__((visibility("default")))
@@ -63,6 +63,8 @@ typedef struct svoxb_tree {
     const float* offset;        /* [3] device; world -> tree: q = offset + scaling * q                */
     const float* scaling;       /* [3] device (the reference's invradius)                             */
     const svoxb_accel* accel;   /* optional; NULL = walk child/data exactly like the reference        */
+    const float* features_act;  /* optional [M, D]: features with the sigmoid already applied to channels  */
+                                /* 0..D-2 (svoxb_activate_features); the march kernels then skip it       */
 } svoxb_tree;
 
 /* Field-for-field the reference's RenderOptions (include/data_spec.hpp:129-145). */
@@ -101,6 +103,12 @@ SVOXB_API int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* st
 SVOXB_API void svoxb_accel_destroy(svoxb_accel* accel);
 SVOXB_API int64_t svoxb_accel_bytes(const svoxb_accel* accel);
 SVOXB_API int svoxb_accel_describe(const svoxb_accel* accel, int* n_stages, int* bits /*[4]*/, int64_t* bricks /*[4]*/);
+
+/* ---- per-row activation (no reference counterpart; derived data, rebuilt whenever features change) ------------ */
+/* out[i, c] = sigmoid(features[i, c]) for c < D-1, out[i, D-1] = features[i, D-1] (sigma stays raw). A leaf row is
+ * visited by ~77 rays in the reference's headline configuration, so applying the sigmoid once per row instead of once
+ * per visit removes almost all transcendental work from the march. One streaming pass over the table. */
+SVOXB_API int svoxb_activate_features(const float* features, int64_t M, int32_t D, float* out, void* stream);
 
 /* ---- octree descent ---------------------------------------------------------------------------- */
 /* query_vertical, first kernel (svox_kernel.cu:66-81, 274-302): per point p (world coords) the leaf's packed

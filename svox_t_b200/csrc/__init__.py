@@ -29,6 +29,7 @@ class _CTree(ctypes.Structure):
         ("child", ctypes.c_void_p), ("data", ctypes.c_void_p), ("parent_depth", ctypes.c_void_p),
         ("n_nodes", ctypes.c_int64), ("n_internal", ctypes.c_int64),
         ("offset", ctypes.c_void_p), ("scaling", ctypes.c_void_p), ("accel", ctypes.c_void_p),
+        ("features_act", ctypes.c_void_p),
     ]
 
 
@@ -60,6 +61,7 @@ SYMBOLS = {
     "svoxb_accel_bytes": (_I64, [_VP]),
     "svoxb_accel_describe": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                             ctypes.POINTER(_I64)]),
+    "svoxb_activate_features": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP]),
     "svoxb_query": (ctypes.c_int, [_PT, _VP, _I64, _VP, _VP, _VP, _VP, _VP]),
     "svoxb_leafset_scratch_bytes": (ctypes.c_size_t, [_I64]),
     "svoxb_leafset_scan": (ctypes.c_int, [_VP, _I64, _VP, _VP, _VP]),
@@ -98,7 +100,7 @@ def load_library():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.svoxb_abi_version() != 1:
+        if lib.svoxb_abi_version() != 2:
             raise ImportError("svox_t_b200: libsvoxb.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib
@@ -161,6 +163,7 @@ class TreeSpec:
         self.transformation_matrices = None
         self.n_internal = 0
         self._accel = None          # svox_t_b200 extension: Accel handle cached by N3Tree (None = reference walk)
+        self._act = None            # svox_t_b200 extension: Activated table for `features` (None = sigmoid in-kernel)
 
     def check(self):
         _check_input(self.features, "features", torch.float32)
@@ -179,12 +182,16 @@ class TreeSpec:
         acc = self._accel
         if acc is not None and not acc.matches(self):
             acc = None
+        act = self._act
+        if act is not None and not act.matches(self.features):
+            act = None
         c = _CTree(
             features=_ptr(self.features), M=self.features.shape[0], D=self.features.shape[1],
             N=self.child.shape[1], child=_ptr(self.child), data=_ptr(self.data),
             parent_depth=_ptr(self.parent_depth), n_nodes=self.child.shape[0], n_internal=int(self.n_internal),
             offset=_ptr(self.offset), scaling=_ptr(self.scaling),
-            accel=acc.handle if acc is not None else ctypes.c_void_p(0))
+            accel=acc.handle if acc is not None else ctypes.c_void_p(0),
+            features_act=_ptr(act.table) if act is not None else ctypes.c_void_p(0))
         return c
 
 
@@ -269,6 +276,27 @@ class Accel:
                 self.handle = None
         except Exception:
             pass
+
+
+class Activated:
+    """features with the sigmoid applied once per row to the payload channels (svoxb_activate_features). Valid for
+    exactly one (storage, version, shape) of ``features``; the renderer rebuilds it whenever features change."""
+
+    def __init__(self, features):
+        lib = load_library()
+        _check_input(features, "features", torch.float32)
+        self._key = self._make_key(features)
+        with torch.cuda.device(features.device):
+            self.table = torch.empty_like(features)
+            _check(lib.svoxb_activate_features(_ptr(features), features.shape[0], features.shape[1], _ptr(self.table),
+                                               _stream()))
+
+    @staticmethod
+    def _make_key(f):
+        return (f.data_ptr(), f._version, tuple(f.shape))
+
+    def matches(self, features):
+        return self._key == self._make_key(features)
 
 
 # ---- functions (svox.cpp:119-144) -----------------------------------------------------------------------------------

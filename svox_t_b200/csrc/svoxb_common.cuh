@@ -74,6 +74,7 @@ struct TreeArgs {
     const float* scaling;
     AccelView acc;
     int use_accel;
+    const float* feat_act;   // optional pre-activated table (sigmoid applied to channels 0..D-2), or nullptr
 };
 
 // ---- device math ----------------------------------------------------------------------------------------------

@@ -24,6 +24,8 @@ namespace svoxb {
 __device__ __forceinline__ float4 sigmoid4(const float4 x) {
     return make_float4(fast_sigmoid(x.x), fast_sigmoid(x.y), fast_sigmoid(x.z), fast_sigmoid(x.w));
 }
+// `act` (warp-uniform): the rows come from the pre-activated table, the sigmoid has been applied already.
+__device__ __forceinline__ float4 activated(const float4 x, bool act) { return act ? x : sigmoid4(x); }
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -104,7 +106,8 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     const int D = tr.D, D4 = D >> 2;
     const bool lane_ok = c4 < D4, is_sig = c4 == D4 - 1;
     const int sig_src = (lane % RPI) * LPR + (D4 - 1);   // lane that holds sigma of this owner lane's row
-    const char* fbase = reinterpret_cast<const char*>(tr.features) + 16 * min(c4, D4 - 1);
+    const bool act = tr.feat_act != nullptr;
+    const char* fbase = reinterpret_cast<const char*>(act ? tr.feat_act : tr.features) + 16 * min(c4, D4 - 1);
     const unsigned row_bytes = (unsigned)D * 4u;
     const float* off = tr.offset;
     const float* scl = tr.scaling;
@@ -185,7 +188,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                     const int j = b * NB + jj;
                     const float w_j = __shfl_sync(FULL, w, RPI * j + q);
                     if (w_j != 0.0f) {
-                        const float4 s = sigmoid4(x[jj]);
+                        const float4 s = activated(x[jj], act);
                         float4 a = accs[j * 32];
                         a.x = fmaf(w_j, s.x, a.x);
                         a.y = fmaf(w_j, s.y, a.y);
@@ -255,7 +258,8 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
     const bool lane_ok = c4 < D4, is_sig = c4 == D4 - 1;
     const int sig_src = (lane % RPI) * LPR + (D4 - 1);
     const int red_src = (lane % RPI) * LPR + ((lane / RPI) % NB);     // lane holding this owner's reduced dot product
-    const char* fbase = reinterpret_cast<const char*>(tr.features) + 16 * min(c4, D4 - 1);
+    const bool act = tr.feat_act != nullptr;
+    const char* fbase = reinterpret_cast<const char*>(act ? tr.feat_act : tr.features) + 16 * min(c4, D4 - 1);
     char* gbase = reinterpret_cast<char*>(grad) + 16 * c4;
     const unsigned row_bytes = (unsigned)D * 4u;
     const float* off = tr.offset;
@@ -353,7 +357,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                         const int r = RPI * (b * NB + jj) + q;
                         const bool on = ((hb >> r) & 1u) && lane_ok;
                         const float4 g4 = *reinterpret_cast<const float4*>(gs + r * DP + 4 * c4);
-                        const float4 s = sigmoid4(x[jj]);
+                        const float4 s = activated(x[jj], act);
                         const float sx = s.x * g4.x, sy = s.y * g4.y, sz = s.z * g4.z, sw = s.w * g4.w;
                         cp[jj] = on ? (sx + sy) + (sz + (is_sig ? 0.0f : sw)) : 0.0f;
                         sv[jj] = make_float4(sx * (1.0f - s.x), sy * (1.0f - s.y), sz * (1.0f - s.z), sw * (1.0f - s.w));
@@ -467,13 +471,14 @@ static int launch_bwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpt
 
 int launch_fwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, float* out,
                     float* depth, cudaStream_t st) {
-    SVOXB_REQUIRE(((uintptr_t)tr.features & 15) == 0 && ((uintptr_t)out & 15) == 0, "features/out must be 16-byte aligned");
+    SVOXB_REQUIRE(((uintptr_t)tr.features & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)tr.feat_act & 15) == 0,
+                  "features/out must be 16-byte aligned");
     SVOXB_Q_DISPATCH(launch_fwd_q, tr, src, m, out, depth, st);
 }
 
 int launch_bwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, const float* grad_out,
                     const float* saved_out, float* grad, cudaStream_t st) {
-    SVOXB_REQUIRE(((uintptr_t)tr.features & 15) == 0 && ((uintptr_t)grad & 15) == 0,
+    SVOXB_REQUIRE(((uintptr_t)tr.features & 15) == 0 && ((uintptr_t)grad & 15) == 0 && ((uintptr_t)tr.feat_act & 15) == 0,
                   "features/grad_features must be 16-byte aligned");
     SVOXB_Q_DISPATCH(launch_bwd_q, tr, src, m, grad_out, saved_out, grad, st);
 }

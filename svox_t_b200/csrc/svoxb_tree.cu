@@ -108,6 +108,7 @@ int make_tree_args(const svoxb_tree* t, TreeArgs& a) {
     } a.D = t->D; a.N = t->N;
     a.child = t->child; a.data = t->data; a.offset = t->offset; a.scaling = t->scaling;
     a.use_accel = 0;
+    a.feat_act = t->M > 0 ? t->features_act : nullptr;
     memset(&a.acc, 0, sizeof(a.acc));
     if (t->accel) {
         SVOXB_REQUIRE(t->N == 2, "accelerator requires N == 2");
@@ -170,6 +171,25 @@ __global__ void accel_stage_kernel(const int32_t* __restrict__ child, const int3
             }
         }
         cells[gid] = cell;
+    }
+}
+
+// ---- per-row activation -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+activate_kernel(const float* __restrict__ f, int64_t n, int D, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = __ldg(f + i);
+        out[i] = ((int)(i % D) == D - 1) ? v : fast_sigmoid(v);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+activate4_kernel(const float4* __restrict__ f, int64_t n4, int D4, float4* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(f + i);
+        float4 r = make_float4(fast_sigmoid(v.x), fast_sigmoid(v.y), fast_sigmoid(v.z), fast_sigmoid(v.w));
+        if ((int)(i % D4) == D4 - 1) r.w = v.w;           // the sigma channel stays raw
+        out[i] = r;
     }
 }
 
@@ -489,6 +509,24 @@ extern "C" int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* s
     cudaFreeAsync(d_scalars, st);
     *out = a;
     return 0;
+}
+
+extern "C" int svoxb_activate_features(const float* features, int64_t M, int32_t D, float* out, void* stream) {
+    SVOXB_REQUIRE(M >= 0 && D >= 2, "bad sizes");
+    if (M == 0) return 0;
+    SVOXB_REQUIRE(features && out, "NULL tensor");
+    const int64_t n = M * D;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (D % 4 == 0 && (((uintptr_t)features | (uintptr_t)out) & 15) == 0) {
+        const int grid = (int)min((n / 4 + 255) / 256, (int64_t)sm_count() * 16);
+        activate4_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(features), n / 4, D / 4,
+                                              reinterpret_cast<float4*>(out));
+    } else {
+        const int grid = (int)min((n + 255) / 256, (int64_t)sm_count() * 16);
+        activate_kernel<<<grid, 256, 0, st>>>(features, n, D, out);
+    }
+    count_launch();
+    return check_cuda(cudaGetLastError(), "activate_kernel launch");
 }
 
 extern "C" int svoxb_query(const svoxb_tree* tree, const float* pts, int64_t Q, float* values, int64_t* node_ids,

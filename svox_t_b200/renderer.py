@@ -117,6 +117,16 @@ class VolumeRenderer(nn.Module):
             self.max_comp += self.data_format.basis_dim
         self.tree._weight_accum = None
 
+    def _render_spec(self, features, n_rays, **kw):
+        """TreeSpec for a march over ``n_rays`` rays. When the batch is large enough for every leaf row to be visited
+        many times, attach the pre-activated table (sigmoid once per row instead of once per visit); small batches
+        keep the in-kernel sigmoid, for which one pass over the whole table would cost more than it saves."""
+        ts = self.tree._spec(features, **kw)
+        M, D = features.shape
+        if D % 4 == 0 and 8 < D <= 128 and n_rays * 32 >= M and features.is_cuda:
+            ts._act = self.tree.activated(features.detach())
+        return ts
+
     def _require_cuda(self, cuda):
         if not cuda or not self.tree.data.is_cuda:
             # the reference asserts False here (renderer.py:225,335): its PyTorch path is dead code
@@ -127,20 +137,20 @@ class VolumeRenderer(nn.Module):
         ``transformation_matrices`` is accepted and, as in the reference's RGBA path, has no effect."""
         self._require_cuda(cuda)
         return _VolumeRenderFunction.apply(
-            features, self.tree._spec(features, transformation_matrices=transformation_matrices),
+            features, self._render_spec(features, rays.origins.shape[0], transformation_matrices=transformation_matrices),
             _rays_spec_from_rays(rays), self._get_options(fast), False)
 
     def forward_with_depth(self, features, rays: Rays, fast=False):
         """(out (B, D), depth (B, 1)) from one march."""
         self._require_cuda(True)
-        return _VolumeRenderFunction.apply(features, self.tree._spec(features), _rays_spec_from_rays(rays),
-                                           self._get_options(fast), True)
+        return _VolumeRenderFunction.apply(features, self._render_spec(features, rays.origins.shape[0]),
+                                           _rays_spec_from_rays(rays), self._get_options(fast), True)
 
     def render_persp(self, features, c2w, width=800, height=800, fx=1111.111, fy=None, cuda=True, fast=False):
         """Perspective image -> (height, width, D). Differentiable (renderer.py:310-366)."""
         self._require_cuda(cuda)
         fy = fx if fy is None else fy
-        return _VolumeRenderImageFunction.apply(features, self.tree._spec(features),
+        return _VolumeRenderImageFunction.apply(features, self._render_spec(features, width * height),
                                                 _make_camera_spec(c2w, width, height, fx, fy),
                                                 self._get_options(fast), False)
 
@@ -148,7 +158,7 @@ class VolumeRenderer(nn.Module):
         """(image (H, W, D), depth (H, W, 1)) from one march."""
         self._require_cuda(True)
         fy = fx if fy is None else fy
-        return _VolumeRenderImageFunction.apply(features, self.tree._spec(features),
+        return _VolumeRenderImageFunction.apply(features, self._render_spec(features, width * height),
                                                 _make_camera_spec(c2w, width, height, fx, fy),
                                                 self._get_options(fast), True)
 

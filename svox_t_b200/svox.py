@@ -289,6 +289,14 @@ class N3Tree(nn.Module):
             self._accel_cache = acc
         return acc
 
+    def activated(self, features):
+        """Table of ``features`` with the sigmoid applied once per row (cached until ``features`` changes)."""
+        act = getattr(self, "_act_cache", None)
+        if act is None or not act.matches(features):
+            act = _C.Activated(features)
+            self._act_cache = act
+        return act
+
     def _spec(self, features, joint_features=None, skinning_weights=None, joint_index=None,
               transformation_matrices=None, world=True, _with_accel=True):
         """Pack the tree into a TreeSpec (svox.py:899-925). transformation_matrices / joint_* are carried for

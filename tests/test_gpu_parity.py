@@ -70,6 +70,14 @@ def test_against_reference_golden(dev, name, accel):
     grad = C.volume_render_backward(ts, rs, opt, cu(z["grad_out"], dev), saved_out=out)
     assert_render_parity(out.detach().cpu().numpy(), depth.cpu().numpy()[:, 0], grad.cpu().numpy(),
                          z["ref_out"], z["ref_depth"], z["ref_grad"])
+    # the pre-activated table (sigmoid once per row) must give the same answers as the in-kernel sigmoid
+    ts._act = C.Activated(feats.detach())
+    out_a, depth_a = C.volume_render_with_depth(ts, rs, opt)
+    grad_a = C.volume_render_backward(ts, rs, opt, cu(z["grad_out"], dev), saved_out=out_a)
+    assert_render_parity(out_a.cpu().numpy(), depth_a.cpu().numpy()[:, 0], grad_a.cpu().numpy(),
+                         z["ref_out"], z["ref_depth"], z["ref_grad"])
+    assert torch.equal(depth_a, depth) and float((out_a - out.detach()).abs().max()) < 1e-6
+    ts._act = None
     # standalone depth kernel and the backward without a saved forward agree with the fused path
     assert torch.equal(C.render_depth(ts, rs, opt), depth)
     grad2 = C.volume_render_backward(ts, rs, opt, cu(z["grad_out"], dev))
