@@ -240,7 +240,7 @@ static int persistent_grid(Kern kern, size_t smem, int64_t queue_len, int& grid)
     return 0;
 }
 
-// Quad-lane kernels (svoxb_render_q.cu): feature width D % 4 == 0, 8 < D <= 128.
+// Quad-lane kernels (svoxb_render_q.cu): feature width D % 4 == 0, 4 <= D <= 128.
 bool quad_supported(int D);
 int launch_fwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, float* out,
                     float* depth, cudaStream_t st);

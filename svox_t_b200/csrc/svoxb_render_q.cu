@@ -1,4 +1,4 @@
-// svoxb_render_q.cu -- "quad-lane" march kernels: the fast path for feature widths D % 4 == 0, 8 < D <= 128.
+// svoxb_render_q.cu -- "quad-lane" march kernels: the fast path for feature widths D % 4 == 0, 4 <= D <= 128.
 //
 // Same semantics as the scalar-lane kernels in svoxb_render.cu (reference: rt_kernel.cu:221-328 forward,
 // 330-496 backward, 781-834 depth); what changes is how a warp touches the feature table:
@@ -35,7 +35,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // total of value index (lane % NB). Transposing steps (each halves the live values), then plain butterfly steps.
 template <int NB, int LPR>
 __device__ __forceinline__ float quad_reduce(float (&v)[NB], int lane) {
-    static_assert(NB == 4 || NB == 8, "NB");
+    static_assert(NB == 1 || NB == 2 || NB == 4 || NB == 8, "NB");
     if constexpr (NB == 8) {
         const bool up = lane & 4;
 #pragma unroll
@@ -45,7 +45,7 @@ __device__ __forceinline__ float quad_reduce(float (&v)[NB], int lane) {
             v[j] = keep + __shfl_xor_sync(FULL, send, 4);
         }
     }
-    {
+    if constexpr (NB >= 4) {
         const bool up = lane & 2;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -54,7 +54,7 @@ __device__ __forceinline__ float quad_reduce(float (&v)[NB], int lane) {
             v[j] = keep + __shfl_xor_sync(FULL, send, 2);
         }
     }
-    {
+    if constexpr (NB >= 2) {
         const bool up = lane & 1;
         const float send = up ? v[0] : v[1];
         const float keep = up ? v[1] : v[0];
@@ -65,6 +65,9 @@ __device__ __forceinline__ float quad_reduce(float (&v)[NB], int lane) {
     for (int w = NB; w < LPR; w <<= 1) r += __shfl_xor_sync(FULL, r, w);
     return r;
 }
+
+template <int BITS>
+__device__ __forceinline__ constexpr unsigned low_mask() { return BITS >= 32 ? 0xffffffffu : ((1u << (BITS & 31)) - 1u); }
 
 template <int LPR>
 struct Quad {
@@ -167,7 +170,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                 }
             }
             // ---- S2.b: composite ---------------------------------------------------------------------------------
-            const unsigned bm = NBATCH == 1 ? pm : (pm >> (RPB * b)) & ((1u << RPB) - 1u);
+            const unsigned bm = NBATCH == 1 ? pm : (pm >> ((RPB * b) & 31)) & low_mask<RPB>();
             if (bm) {
                 float sig = 0.0f;
 #pragma unroll
@@ -214,7 +217,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
         if (fm) {
 #pragma unroll
             for (int j = 0; j < LPR; ++j) {
-                const unsigned gm = (fm >> (RPI * j)) & ((1u << RPI) - 1u);
+                const unsigned gm = (fm >> ((RPI * j) & 31)) & low_mask<RPI>();
                 if (gm) {
                     const int r = RPI * j + q;
                     const float T_r = __shfl_sync(FULL, T, r);
@@ -332,7 +335,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                 }
             }
             // ---- S2.b: gradient of batch b of the pending candidates ------------------------------------------------
-            const unsigned bm = NBATCH == 1 ? pm : (pm >> (RPB * b)) & ((1u << RPB) - 1u);
+            const unsigned bm = NBATCH == 1 ? pm : (pm >> ((RPB * b) & 31)) & low_mask<RPB>();
             if (bm) {
                 float sig = 0.0f;
 #pragma unroll
@@ -402,10 +405,10 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
-bool quad_supported(int D) { return D % 4 == 0 && D > 8 && D <= 128; }
+bool quad_supported(int D) { return D % 4 == 0 && D >= 4 && D <= 128; }
 
 static int lpr_for(int D) {
-    int l = 4;
+    int l = 1;
     while (l * 4 < D) l <<= 1;
     return l;
 }
@@ -447,6 +450,14 @@ static int launch_bwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpt
         const int lpr = lpr_for(tr.D);                                                                 \
         const int sel = (tr.use_accel ? 2 : 0) | (image ? 1 : 0);                                      \
         switch (lpr * 4 + sel) {                                                                       \
+            case 1 * 4 + 0: return FN<1, false, false>(__VA_ARGS__);                                   \
+            case 1 * 4 + 1: return FN<1, false, true>(__VA_ARGS__);                                    \
+            case 1 * 4 + 2: return FN<1, true, false>(__VA_ARGS__);                                    \
+            case 1 * 4 + 3: return FN<1, true, true>(__VA_ARGS__);                                     \
+            case 2 * 4 + 0: return FN<2, false, false>(__VA_ARGS__);                                   \
+            case 2 * 4 + 1: return FN<2, false, true>(__VA_ARGS__);                                    \
+            case 2 * 4 + 2: return FN<2, true, false>(__VA_ARGS__);                                    \
+            case 2 * 4 + 3: return FN<2, true, true>(__VA_ARGS__);                                     \
             case 4 * 4 + 0: return FN<4, false, false>(__VA_ARGS__);                                   \
             case 4 * 4 + 1: return FN<4, false, true>(__VA_ARGS__);                                    \
             case 4 * 4 + 2: return FN<4, true, false>(__VA_ARGS__);                                    \

@@ -123,7 +123,7 @@ class VolumeRenderer(nn.Module):
         keep the in-kernel sigmoid, for which one pass over the whole table would cost more than it saves."""
         ts = self.tree._spec(features, **kw)
         M, D = features.shape
-        if D % 4 == 0 and 8 < D <= 128 and n_rays * 32 >= M and features.is_cuda:
+        if D % 4 == 0 and 4 <= D <= 128 and n_rays * 32 >= M and features.is_cuda:
             ts._act = self.tree.activated(features.detach())
         return ts
 

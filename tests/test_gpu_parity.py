@@ -112,7 +112,9 @@ def test_image_kernel_matches_golden_camera_rays(dev):
 
 # ---- (2) CPU oracle on seeded inputs, autograd plumbing, edge cases -------------------------------------------------
 @pytest.mark.parametrize("L,shape,D,Q", [(4, "all", 16, 2048), (6, "ball", 33, 2048), (5, "ball", 64, 1024),
-                                         (3, "ball", 2, 512), (5, "shell", 100, 512)])
+                                         (3, "ball", 2, 512), (5, "shell", 100, 512),
+                                         (5, "ball", 4, 1024), (5, "ball", 8, 1024), (5, "ball", 12, 1024),
+                                         (4, "ball", 128, 512)])
 def test_autograd_path_vs_oracle(dev, L, shape, D, Q):
     tr = synth.synth_tree(L, shape, r_out=0.45 if L <= 3 else 0.30, r_in=0.2)
     f = synth.synth_features(tr["M"], D)
