@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SVOXB_ABI_VERSION 2
+#define SVOXB_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SVOXB_API __attribute__((visibility("default")))
@@ -37,10 +37,12 @@ enum {
     SVOXB_OK = 0,
     SVOXB_EINVAL = -1,      /* bad argument (null pointer, unsupported N / D / format ...) */
     SVOXB_ECUDA = -2,       /* CUDA runtime / launch error */
-    SVOXB_EUNSUPPORTED = -3 /* feature of the reference deliberately not implemented (SH/SG/ASG, NDC) */
+    SVOXB_EUNSUPPORTED = -3 /* feature of the reference deliberately not implemented */
 };
 
-/* DataFormat enum of the reference (include/data_spec.hpp:45-50). Only RGBA (feature-level) is implemented. */
+/* DataFormat enum of the reference (include/data_spec.hpp:45-50). RGBA is the feature-level format of the hot path
+ * (output = D-1 sigmoid features + opacity); SH/SG/ASG rows hold basis_dim coefficients per output channel
+ * (output = (D-1)/basis_dim channels + opacity, rt_kernel.cu:1352-1358). */
 enum { SVOXB_FORMAT_RGBA = 0, SVOXB_FORMAT_SH = 1, SVOXB_FORMAT_SG = 2, SVOXB_FORMAT_ASG = 3 };
 
 /* Opaque acceleration structure built from (child, data) by svoxb_accel_create(): a dense top grid plus
@@ -48,8 +50,8 @@ enum { SVOXB_FORMAT_RGBA = 0, SVOXB_FORMAT_SH = 1, SVOXB_FORMAT_SG = 2, SVOXB_FO
 typedef struct svoxb_accel svoxb_accel;
 
 /* Replaces TreeSpec / PackedTreeSpec (include/data_spec.hpp:67-111, include/data_spec_packed.cuh:57-100).
- * Fields the feature-level path never reads (extra_data, _weight_accum, joint_*, transformation_matrices --
- * a no-op for FORMAT_RGBA, rt_kernel.cu:181-183,283-291) are omitted. */
+ * _weight_accum is omitted (not implemented); joint_features / skinning_weights / joint_index are arguments of the
+ * motion-feature entry points instead of fields. */
 typedef struct svoxb_tree {
     const float* features;      /* [M, D] float32; last channel = sigma                               */
     int64_t M;                  /* features.size(0); a data index >= M marks an empty leaf            */
@@ -65,6 +67,11 @@ typedef struct svoxb_tree {
     const svoxb_accel* accel;   /* optional; NULL = walk child/data exactly like the reference        */
     const float* features_act;  /* optional [M, D]: features with the sigmoid already applied to channels  */
                                 /* 0..D-2 (svoxb_activate_features); the march kernels then skip it       */
+    const float* extra_data;    /* optional [extra_rows, extra_cols]: SG rows (lambda, mu[3]); ASG rows (a, b, x[3],  */
+    int32_t extra_rows;         /* y[3], z[3]) -- the basis parameters of rt_kernel.cu:116-140. Unused for RGBA / SH.  */
+    int32_t extra_cols;
+    const float* transformation_matrices; /* optional [M,4,4]: per-row rotation of the view direction before the     */
+                                /* basis is evaluated (rt_kernel.cu:283-291). No effect for RGBA.                    */
 } svoxb_tree;
 
 /* Field-for-field the reference's RenderOptions (include/data_spec.hpp:129-145). */
@@ -73,7 +80,8 @@ typedef struct svoxb_render_options {
     float background_brightness;
     int32_t format;
     int32_t basis_dim;
-    int32_t ndc_width;          /* < 0 disables NDC (renderer.py:426); >= 0 is SVOXB_EUNSUPPORTED     */
+    int32_t ndc_width;          /* < 0 disables NDC (renderer.py:426). Like the reference, only the IMAGE entry   */
+                                /* points convert their camera rays to NDC (rt_kernel.cu:1168-1191, 1204)          */
     int32_t ndc_height;
     float ndc_focal;
     int32_t min_comp;
@@ -133,8 +141,10 @@ SVOXB_API int svoxb_construct_tree(const svoxb_tree* tree, int32_t* data_mut, co
 
 /* ---- ray march --------------------------------------------------------------------------------- */
 /* volume_render (rt_kernel.cu:654-671, 1362-1379) fused with render_depth (rt_kernel.cu:865-882, 1506-1523):
- * out[Q, D] = D-1 composited sigmoid features + opacity (1 - T); depth[Q] (nullable) = first-hit depth.
- * vdirs is accepted for signature parity and ignored (no effect for FORMAT_RGBA). */
+ * out[Q, Do] with Do = svoxb_out_data_dim(): RGBA: D-1 composited sigmoid features + opacity (1 - T);
+ * SH/SG/ASG: (D-1)/basis_dim view-dependent channels + opacity. depth[Q] (nullable, RGBA only) = first-hit depth.
+ * vdirs[Q,3] is read by the view-dependent formats only (may be NULL for RGBA). */
+SVOXB_API int svoxb_out_data_dim(int32_t format, int32_t basis_dim, int32_t D);
 SVOXB_API int svoxb_render_rays_fwd(const svoxb_tree* tree, const float* origins, const float* dirs, const float* vdirs,
                           int64_t Q, const svoxb_render_options* opt, float* out, float* depth, void* stream);
 
@@ -143,8 +153,8 @@ SVOXB_API int svoxb_render_rays_fwd(const svoxb_tree* tree, const float* origins
  * sigma_thresh = 0 and stop_thresh < 0 (the backward's own hit predicate, rt_kernel.cu:382,456); with the
  * default options that is exactly what svoxb_render_rays_fwd returned. The caller zero-fills
  * grad_features (the reference allocates zeros_like(features), rt_kernel.cu:1415). */
-SVOXB_API int svoxb_render_rays_bwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
-                          const svoxb_render_options* opt, const float* grad_out, const float* saved_out,
+SVOXB_API int svoxb_render_rays_bwd(const svoxb_tree* tree, const float* origins, const float* dirs, const float* vdirs,
+                          int64_t Q, const svoxb_render_options* opt, const float* grad_out, const float* saved_out,
                           float* grad_features, void* stream);
 
 /* volume_render_image / _backward (rt_kernel.cu:1152-1166, 1193-1238, 1381-1452): pinhole camera rays generated
@@ -175,6 +185,22 @@ SVOXB_API int svoxb_opacity_render_bwd(const svoxb_tree* tree, const float* orig
 SVOXB_API int svoxb_motion_render(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
                         const svoxb_render_options* opt, const float* extra_data, int32_t J, float* out, float* depth,
                         float* hit_point, int64_t* data_idx, void* stream);
+
+/* motion_feature_render (rt_kernel.cu:885-979, 1525-1543): out[Q, F] += weight * sigmoid(sum_j w_j * JF[joint_j][k]) at
+ * every hit, where (w_j, joint_j) are the B skinning weights / joint indices of the hit ROW (skinning_weights[M,B],
+ * joint_index[M,B]) and JF = joint_features[J,F], F <= 32. No opacity channel; rays that miss the cube return 0. */
+SVOXB_API int svoxb_motion_feature_render_fwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                                    const svoxb_render_options* opt, const float* joint_features,
+                                    const float* skinning_weights, const int32_t* joint_index, int32_t J, int32_t F,
+                                    int32_t B, float* out, void* stream);
+
+/* motion_feature_render_backward (rt_kernel.cu:981-1064, 1546-1572) with the arithmetic it was meant to have:
+ * grad_joint_features[J,F] (zero-filled here) += w_j * weight * s (1 - s) * grad_out[q,k] over every sample with
+ * sigma > 0. (The reference adds into an uninitialised array and indexes it by bone slot) */
+SVOXB_API int svoxb_motion_feature_render_bwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                                    const svoxb_render_options* opt, const float* joint_features,
+                                    const float* skinning_weights, const int32_t* joint_index, int32_t J, int32_t F,
+                                    int32_t B, const float* grad_out, float* grad_joint_features, void* stream);
 
 /* ---- animated-frame rebuild -------------------------------------------------------------------- */
 /* warp_vertices (svox_kernel.cu:123-154, 354-378): linear blend skinning. T[J,4,4], coords[P,3], w[P,B],

@@ -253,3 +253,94 @@ def p2v_backward(g_vox, points, feat, corner, size, n_voxels, kernel_radius, con
                                               ctypes.c_int(feat.shape[1]), _p(corner), _p(size), ctypes.c_int(n_voxels),
                                               cr(kernel_radius), cr(conv_radius), _p(gp), _p(gf))
     return gp, gf
+
+
+# ---- view-dependent formats, NDC cameras, motion-feature render ---------------------------------
+FORMAT_RGBA, FORMAT_SH, FORMAT_SG, FORMAT_ASG = 0, 1, 2, 3
+
+
+def _fmt_args(fmt, basis_dim, min_comp, max_comp, extra, tm, dtype):
+    max_comp = max_comp if max_comp >= 0 else max_comp + basis_dim
+    e = None if extra is None else _c(extra, dtype)
+    t = None if tm is None else _c(tm, dtype)
+    cols = 0 if e is None else int(e.shape[1])
+    keep = (e, t)
+    return keep, (ctypes.c_int(fmt), ctypes.c_int(basis_dim), ctypes.c_int(min_comp), ctypes.c_int(max_comp),
+                  _p(e), ctypes.c_int(cols), _p(t))
+
+
+def render_rays_fmt(tree, features, origins, dirs, vdirs, fmt, basis_dim, extra=None, tm=None, min_comp=0,
+                    max_comp=-1, step_size=1e-3, background_brightness=1.0, sigma_thresh=0.0, stop_thresh=0.0,
+                    dtype=np.float32):
+    """SH / SG / ASG render -> out[Q, C+1], C = (D-1)//basis_dim (rt_kernel.cu:293-301). ``tm`` [M,4,4] rotates the
+    view direction per hit row (rt_kernel.cu:283-291)."""
+    sfx, cr = _sfx(dtype)
+    keep, targs = tree.args(features, dtype)
+    keep2, fargs = _fmt_args(fmt, basis_dim, min_comp, max_comp, extra, tm, dtype)
+    o, d, v = _c(origins, dtype), _c(dirs, dtype), _c(vdirs, dtype)
+    Q, D = o.shape[0], keep[0].shape[1]
+    out = np.zeros((Q, (D - 1) // basis_dim + 1), dtype=dtype)
+    getattr(lib(), "orc_render_rays_fmt" + sfx)(*targs, _p(o), _p(d), _p(v), ctypes.c_int64(Q), cr(step_size),
+                                                 cr(background_brightness), cr(sigma_thresh), cr(stop_thresh),
+                                                 *fargs, _p(out))
+    return out
+
+
+def render_rays_fmt_backward(tree, features, origins, dirs, vdirs, grad_out, fmt, basis_dim, extra=None, tm=None,
+                             min_comp=0, max_comp=-1, step_size=1e-3, background_brightness=1.0, stale_basis=False,
+                             dtype=np.float32):
+    """-> grad[M,D]. stale_basis=True reproduces the reference's second pass with per-row rotations (see the C file)."""
+    sfx, cr = _sfx(dtype)
+    keep, targs = tree.args(features, dtype)
+    keep2, fargs = _fmt_args(fmt, basis_dim, min_comp, max_comp, extra, tm, dtype)
+    o, d, v, g = _c(origins, dtype), _c(dirs, dtype), _c(vdirs, dtype), _c(grad_out, dtype)
+    grad = np.zeros_like(keep[0])
+    getattr(lib(), "orc_render_rays_fmt_backward" + sfx)(*targs, _p(o), _p(d), _p(v), ctypes.c_int64(o.shape[0]),
+                                                          cr(step_size), cr(background_brightness), *fargs, _p(g),
+                                                          ctypes.c_int(1 if stale_basis else 0), _p(grad))
+    return grad
+
+
+def camera_rays_ndc(c2w, fx, fy, width, height, ndc_width=-1, ndc_height=-1, ndc_focal=0.0, dtype=np.float32):
+    """-> origins, dirs (NDC when ndc_width >= 0), vdirs (world) of the image kernels (rt_kernel.cu:1193-1206)."""
+    sfx, cr = _sfx(dtype)
+    c = np.zeros((3, 4), dtype=dtype)
+    c[:] = np.asarray(c2w, dtype=dtype)[:3, :4]
+    n = width * height
+    o, d, v = (np.zeros((n, 3), dtype=dtype) for _ in range(3))
+    getattr(lib(), "orc_camera_rays_ndc" + sfx)(_p(c), cr(fx), cr(fy), ctypes.c_int(width), ctypes.c_int(height),
+                                                 ctypes.c_int(ndc_width), ctypes.c_int(ndc_height), cr(ndc_focal),
+                                                 _p(o), _p(d), _p(v))
+    return o, d, v
+
+
+def motion_feature_render(tree, features, origins, dirs, joint_features, skinning_weights, joint_index,
+                          step_size=1e-3, background_brightness=1.0, sigma_thresh=0.0, stop_thresh=0.0,
+                          dtype=np.float32):
+    """-> out[Q,F] (rt_kernel.cu:885-979)."""
+    sfx, cr = _sfx(dtype)
+    keep, targs = tree.args(features, dtype)
+    o, d = _c(origins, dtype), _c(dirs, dtype)
+    jf, sw, ji = _c(joint_features, dtype), _c(skinning_weights, dtype), _c(joint_index, np.int32)
+    F, B = jf.shape[1], sw.shape[1]
+    assert F <= 64
+    out = np.zeros((o.shape[0], F), dtype=dtype)
+    getattr(lib(), "orc_motion_feature_render" + sfx)(*targs, _p(o), _p(d), ctypes.c_int64(o.shape[0]), cr(step_size),
+                                                       cr(background_brightness), cr(sigma_thresh), cr(stop_thresh),
+                                                       _p(jf), _p(sw), _p(ji), ctypes.c_int(F), ctypes.c_int(B), _p(out))
+    return out
+
+
+def motion_feature_render_backward(tree, features, origins, dirs, joint_features, skinning_weights, joint_index,
+                                   grad_out, step_size=1e-3, dtype=np.float32):
+    """-> grad_joint_features[J,F]: the gradient the reference meant to compute (Appendix B3)."""
+    sfx, cr = _sfx(dtype)
+    keep, targs = tree.args(features, dtype)
+    o, d, g = _c(origins, dtype), _c(dirs, dtype), _c(grad_out, dtype)
+    jf, sw, ji = _c(joint_features, dtype), _c(skinning_weights, dtype), _c(joint_index, np.int32)
+    F, B = jf.shape[1], sw.shape[1]
+    grad = np.zeros_like(jf)
+    getattr(lib(), "orc_motion_feature_render_backward" + sfx)(*targs, _p(o), _p(d), ctypes.c_int64(o.shape[0]),
+                                                                cr(step_size), _p(jf), _p(sw), _p(ji), ctypes.c_int(F),
+                                                                ctypes.c_int(B), _p(g), _p(grad))
+    return grad

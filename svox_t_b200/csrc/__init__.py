@@ -7,7 +7,7 @@ torch tensors, allocates its outputs on the inputs' device (as the reference doe
 and raises ``RuntimeError`` on a failed check. Differences, all deliberate:
 
 * kernels launch on torch's *current* stream (the reference uses the legacy default stream);
-* only float32 and the feature-level ``FORMAT_RGBA`` are implemented; anything else raises;
+* only float32 is implemented (the reference also instantiates float64);
 * there is NO CPU fallback: a missing ``libsvoxb.so`` or a non-CUDA tensor is an error, never a slow path.
 
 PyTorch is plumbing here (device memory, streams); all compute happens in hand-written sm_100a kernels.
@@ -30,6 +30,8 @@ class _CTree(ctypes.Structure):
         ("n_nodes", ctypes.c_int64), ("n_internal", ctypes.c_int64),
         ("offset", ctypes.c_void_p), ("scaling", ctypes.c_void_p), ("accel", ctypes.c_void_p),
         ("features_act", ctypes.c_void_p),
+        ("extra_data", ctypes.c_void_p), ("extra_rows", ctypes.c_int32), ("extra_cols", ctypes.c_int32),
+        ("transformation_matrices", ctypes.c_void_p),
     ]
 
 
@@ -68,13 +70,17 @@ SYMBOLS = {
     "svoxb_leafset_emit": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP, _VP]),
     "svoxb_construct_tree": (ctypes.c_int, [_PT, _VP, _VP, _I64, _VP]),
     "svoxb_render_rays_fwd": (ctypes.c_int, [_PT, _VP, _VP, _VP, _I64, _PO, _VP, _VP, _VP]),
-    "svoxb_render_rays_bwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _VP]),
+    "svoxb_out_data_dim": (ctypes.c_int, [_I32, _I32, _I32]),
+    "svoxb_render_rays_bwd": (ctypes.c_int, [_PT, _VP, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _VP]),
     "svoxb_render_image_fwd": (ctypes.c_int, [_PT, _PC, _PO, _VP, _VP, _VP]),
     "svoxb_render_image_bwd": (ctypes.c_int, [_PT, _PC, _PO, _VP, _VP, _VP, _VP]),
     "svoxb_render_depth": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP]),
     "svoxb_opacity_render_fwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP]),
     "svoxb_opacity_render_bwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP, _VP]),
     "svoxb_motion_render": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _I32, _VP, _VP, _VP, _VP, _VP]),
+    "svoxb_motion_feature_render_fwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
+    "svoxb_motion_feature_render_bwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP,
+                                                       _VP]),
     "svoxb_warp_vertices": (ctypes.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _VP, _VP, _VP]),
     "svoxb_warp_vertices_bwd": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _I32, _I32, _VP, _VP, _VP, _VP]),
     "svoxb_p2v_bwd": (ctypes.c_int, [_VP, _VP, _VP, _I64, _I32, _VP, _VP, _I32, _F, _F, _VP, _VP, _VP]),
@@ -100,7 +106,7 @@ def load_library():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.svoxb_abi_version() != 2:
+        if lib.svoxb_abi_version() != 3:
             raise ImportError("svox_t_b200: libsvoxb.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib
@@ -176,6 +182,16 @@ class TreeSpec:
             raise RuntimeError("features must be [M, D] and child [n, N, N, N]")
         if self._weight_accum is not None and self._weight_accum.numel():
             raise RuntimeError("_weight_accum (accumulate_weights) is not implemented in svox_t_b200")
+        M = self.features.shape[0]
+        ex, tm = self.extra_data, self.transformation_matrices
+        if ex is not None and ex.numel():
+            _check_input(ex, "extra_data", torch.float32)
+            if ex.dim() != 2:
+                raise RuntimeError("extra_data must be 2-D")
+        if tm is not None and tm.numel():
+            _check_input(tm, "transformation_matrices", torch.float32)
+            if tuple(tm.shape) != (M, 4, 4):
+                raise RuntimeError(f"transformation_matrices must be [M={M}, 4, 4]")
 
     def _c(self):
         self.check()
@@ -191,7 +207,11 @@ class TreeSpec:
             parent_depth=_ptr(self.parent_depth), n_nodes=self.child.shape[0], n_internal=int(self.n_internal),
             offset=_ptr(self.offset), scaling=_ptr(self.scaling),
             accel=acc.handle if acc is not None else ctypes.c_void_p(0),
-            features_act=_ptr(act.table) if act is not None else ctypes.c_void_p(0))
+            features_act=_ptr(act.table) if act is not None else ctypes.c_void_p(0),
+            extra_data=_ptr(self.extra_data),
+            extra_rows=self.extra_data.shape[0] if self.extra_data is not None and self.extra_data.numel() else 0,
+            extra_cols=self.extra_data.shape[1] if self.extra_data is not None and self.extra_data.numel() else 0,
+            transformation_matrices=_ptr(self.transformation_matrices))
         return c
 
 
@@ -339,17 +359,32 @@ def construct_tree(tree, indices):
     tree.data.add_(0)   # bump the tensor version: cached accelerators built from the old data are now stale
 
 
+def _out_dim(tree, opt):
+    """Output row width (get_out_data_dim, rt_kernel.cu:1352-1358)."""
+    n = load_library().svoxb_out_data_dim(int(opt.format), int(opt.basis_dim), tree.features.shape[1])
+    if n <= 0:
+        raise RuntimeError(f"svox_t_b200.csrc: bad format/basis_dim ({opt.format}, {opt.basis_dim})")
+    return n
+
+
 def _render_fwd(tree, rays, opt, want_depth):
     lib = load_library()
     rays.check()
     ct = tree._c()
-    Q, D = rays.origins.shape[0], tree.features.shape[1]
+    Q, D = rays.origins.shape[0], _out_dim(tree, opt)
     dev = rays.origins.device
     with torch.cuda.device(dev):
         out = torch.empty((Q, D), dtype=torch.float32, device=dev)
-        depth = torch.empty((Q, 1), dtype=torch.float32, device=dev) if want_depth else None
+        depth = None
+        if want_depth and opt.format != FORMAT_RGBA:       # the view-dependent kernels have no fused depth output
+            depth = torch.empty((Q, 1), dtype=torch.float32, device=dev)
+            _check(lib.svoxb_render_depth(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q,
+                                          ctypes.byref(opt._c()), _ptr(depth), _stream()))
+            want_depth = False
+        fused = torch.empty((Q, 1), dtype=torch.float32, device=dev) if want_depth else None
+        depth = fused if want_depth else depth
         _check(lib.svoxb_render_rays_fwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), _ptr(rays.vdirs), Q,
-                                         ctypes.byref(opt._c()), _ptr(out), _ptr(depth), _stream()))
+                                         ctypes.byref(opt._c()), _ptr(out), _ptr(fused), _stream()))
     return out, depth
 
 
@@ -390,7 +425,7 @@ def volume_render_backward(tree, rays, opt, grad_output, saved_out=None):
     with torch.cuda.device(dev):
         so = _saved_out_for_backward(tree, opt, saved_out, again)
         grad = torch.zeros_like(tree.features)
-        _check(lib.svoxb_render_rays_bwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q,
+        _check(lib.svoxb_render_rays_bwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), _ptr(rays.vdirs), Q,
                                          ctypes.byref(bopt), _ptr(grad_output), _ptr(so), _ptr(grad), _stream()))
     return grad
 
@@ -399,7 +434,9 @@ def _render_image_fwd(tree, cam, opt, want_depth):
     lib = load_library()
     ct, cc = tree._c(), cam._c()
     dev = tree.features.device
-    D = tree.features.shape[1]
+    D = _out_dim(tree, opt)
+    if want_depth and opt.format != FORMAT_RGBA:
+        raise RuntimeError("svox_t_b200.csrc: fused image depth is only available for the RGBA format")
     with torch.cuda.device(dev):
         out = torch.empty((cam.height, cam.width, D), dtype=torch.float32, device=dev)
         depth = torch.empty((cam.height, cam.width, 1), dtype=torch.float32, device=dev) if want_depth else None
@@ -498,6 +535,51 @@ def motion_render(tree, rays, opt):
                                        _ptr(tree.extra_data), J, _ptr(out), _ptr(depth), _ptr(hit), _ptr(didx),
                                        _stream()))
     return [out, depth, hit, didx]
+
+
+def _joint_args(tree):
+    jf, sw, ji = tree.joint_features, tree.skinning_weights, tree.joint_index
+    if jf is None or sw is None or ji is None or not jf.numel():
+        raise RuntimeError("motion_feature_render needs tree.joint_features [J,F], skinning_weights [M,B], joint_index [M,B]")
+    _check_input(jf, "joint_features", torch.float32)
+    _check_input(sw, "skinning_weights", torch.float32)
+    _check_input(ji, "joint_index", torch.int32)
+    M = tree.features.shape[0]
+    if jf.dim() != 2 or sw.dim() != 2 or tuple(ji.shape) != tuple(sw.shape) or sw.shape[0] != M:
+        raise RuntimeError(f"joint_features must be [J,F], skinning_weights / joint_index [M={M},B]")
+    return jf, sw, ji
+
+
+def motion_feature_render(tree, rays, opt):
+    """[Q, F] composited per-joint features (rt_kernel.cu:1525-1543)."""
+    lib = load_library()
+    rays.check()
+    jf, sw, ji = _joint_args(tree)
+    ct = tree._c()
+    Q, dev = rays.origins.shape[0], rays.origins.device
+    with torch.cuda.device(dev):
+        out = torch.empty((Q, jf.shape[1]), dtype=torch.float32, device=dev)
+        _check(lib.svoxb_motion_feature_render_fwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q,
+                                                   ctypes.byref(opt._c()), _ptr(jf), _ptr(sw), _ptr(ji), jf.shape[0],
+                                                   jf.shape[1], sw.shape[1], _ptr(out), _stream()))
+    return out
+
+
+def motion_feature_render_backward(tree, rays, opt, grad_output):
+    """[J, F] dL/d joint_features: the gradient the reference's kernel set out to compute (rt_kernel.cu:981-1064 adds
+    into an uninitialised array and indexes it by bone slot)."""
+    lib = load_library()
+    rays.check()
+    _check_input(grad_output, "grad_output", torch.float32)
+    jf, sw, ji = _joint_args(tree)
+    ct = tree._c()
+    Q, dev = rays.origins.shape[0], rays.origins.device
+    with torch.cuda.device(dev):
+        grad = torch.empty_like(jf)
+        _check(lib.svoxb_motion_feature_render_bwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q,
+                                                   ctypes.byref(opt._c()), _ptr(jf), _ptr(sw), _ptr(ji), jf.shape[0],
+                                                   jf.shape[1], sw.shape[1], _ptr(grad_output), _ptr(grad), _stream()))
+    return grad
 
 
 def warp_vertices(matrices, indices, skinning_weights, joint_index):
@@ -604,8 +686,6 @@ def _unsupported(name, why):
 # `hasattr(_C, name)` behaves, but they raise instead of silently doing something else.
 query_vertical_backward = _unsupported("query_vertical_backward", "faults in the reference (Appendix B1); out of scope")
 assign_vertical = _unsupported("assign_vertical", "faults in the reference (Appendix B1); out of scope")
-motion_feature_render = _unsupported("motion_feature_render", "next-rank component (SURVEY 8f rank 3)")
-motion_feature_render_backward = _unsupported("motion_feature_render_backward", "buggy in the reference (Appendix B3)")
 calc_corners = _unsupported("calc_corners", "dtype bug in the reference (Appendix B4); out of scope")
 grid_weight_render = _unsupported("grid_weight_render", "no caller in the reference; out of scope")
 quantize_median_cut = _unsupported("quantize_median_cut", "CPU-only PlenOctree leftover; out of scope")

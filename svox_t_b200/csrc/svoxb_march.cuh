@@ -19,6 +19,13 @@ struct RaySource {
     int width, height;
     int tiles_x;
     int64_t total;                 // queue length: Q, or n_tiles * 64
+    const float* vdirs;            // explicit rays: [Q,3] view directions (view-dependent formats only)
+    int ndc_w, ndc_h;              // camera rays: NDC conversion when ndc_w >= 0 (rt_kernel.cu:1168-1191)
+    float ndc_focal;
+};
+
+struct ViewDir {
+    float x, y, z;
 };
 
 struct MarchOpts {
@@ -65,6 +72,22 @@ __device__ __forceinline__ void camera_ray(const RaySource& s, int px, int py,
     ox = __ldg(c + 3); oy = __ldg(c + 7); oz = __ldg(c + 11);
 }
 
+// rt_kernel.cu:1168-1191 (maybe_world2ndc, near = 1): world-space pinhole ray -> NDC ray, direction re-normalised.
+__device__ __forceinline__ void world2ndc(const RaySource& s, float& ox, float& oy, float& oz,
+                                          float& dx, float& dy, float& dz) {
+    const float t = -(1.0f + oz) / dz;
+    ox = ox + t * dx; oy = oy + t * dy; oz = oz + t * dz;
+    const float kx = (2.0f * s.ndc_focal) / (float)s.ndc_w, ky = (2.0f * s.ndc_focal) / (float)s.ndc_h;
+    dx = -kx * (dx / dz - ox / oz);
+    dy = -ky * (dy / dz - oy / oz);
+    dz = -2.0f / oz;
+    ox = -kx * (ox / oz);
+    oy = -ky * (oy / oz);
+    oz = 1.0f + 2.0f / oz;
+    const float n = sqrtf(dx * dx + dy * dy + dz * dz);
+    dx /= n; dy /= n; dz /= n;
+}
+
 // Per-warp view of the global ray queue.
 struct Queue {
     int next, end;          // queue positions fit 31 bits (checked on the host)
@@ -72,11 +95,12 @@ struct Queue {
 };
 
 // Hands queue entries to the lanes in `need`; returns the mask of lanes that now own a fresh ray.
-// row = output row of the ray (ray index, or iy*W+ix).
-template <bool IMAGE>
+// row = output row of the ray (ray index, or iy*W+ix). VDIR: also hand back the ray's view direction (explicit rays:
+// vdirs[id]; camera rays: the world-space direction before any NDC conversion, rt_kernel.cu:1203).
+template <bool IMAGE, bool VDIR = false>
 __device__ __forceinline__ unsigned refill(const RaySource& src, const float* off, const float* scl,
                                            unsigned long long* counter, Queue& q, unsigned need, int lane,
-                                           Ray& ray, int& row) {
+                                           Ray& ray, int& row, ViewDir* vd = nullptr) {
     unsigned got = 0;
     while (need) {
         if (q.next >= q.end) {
@@ -103,6 +127,8 @@ __device__ __forceinline__ unsigned refill(const RaySource& src, const float* of
                 if (valid) {
                     camera_ray(src, px, py, ox, oy, oz, dx, dy, dz);
                     row = py * src.width + px;
+                    if (VDIR) { vd->x = dx; vd->y = dy; vd->z = dz; }
+                    if (src.ndc_w >= 0) world2ndc(src, ox, oy, oz, dx, dy, dz);
                 }
             } else {
                 valid = true;
@@ -111,6 +137,10 @@ __device__ __forceinline__ unsigned refill(const RaySource& src, const float* of
                 ox = __ldg(o); oy = __ldg(o + 1); oz = __ldg(o + 2);
                 dx = __ldg(d); dy = __ldg(d + 1); dz = __ldg(d + 2);
                 row = id;
+                if (VDIR) {
+                    const float* v = src.vdirs + (int64_t)id * 3;
+                    vd->x = __ldg(v); vd->y = __ldg(v + 1); vd->z = __ldg(v + 2);
+                }
             }
             if (valid) ray_setup(off, scl, ox, oy, oz, dx, dy, dz, ray);
         }

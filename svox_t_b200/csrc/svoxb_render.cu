@@ -358,24 +358,33 @@ depth_kernel(TreeArgs tr, const float* __restrict__ origins, const float* __rest
 // ---- host side ---------------------------------------------------------------------------------------------------
 int make_tree_args(const svoxb_tree* t, TreeArgs& a);   // svoxb_tree.cu
 
+// svoxb_render_sh.cu: the view-dependent formats (SH / SG / ASG)
+int fmt_render_fwd(const svoxb_tree* tree, const TreeArgs& tr, const RaySource& src, const MarchOpts& m,
+                   const svoxb_render_options* opt, bool image, float* out, cudaStream_t st);
+int fmt_render_bwd(const svoxb_tree* tree, const TreeArgs& tr, const RaySource& src, const MarchOpts& m,
+                   const svoxb_render_options* opt, bool image, const float* go, const float* so, float* grad,
+                   cudaStream_t st);
+
 static int check_opts(const svoxb_render_options* opt, MarchOpts& m) {
     SVOXB_REQUIRE(opt != nullptr, "render options are NULL");
-    if (opt->format != SVOXB_FORMAT_RGBA) {
-        set_error("data format %d (SH/SG/ASG) is not implemented: only the feature-level RGBA format is", opt->format);
-        return SVOXB_EUNSUPPORTED;
-    }
-    if (opt->ndc_width >= 0) {
-        set_error("NDC ray conversion (ndc_width >= 0) is not implemented");
-        return SVOXB_EUNSUPPORTED;
-    }
+    SVOXB_REQUIRE(opt->format >= SVOXB_FORMAT_RGBA && opt->format <= SVOXB_FORMAT_ASG, "unknown data format %d",
+                  opt->format);
     m.step = opt->step_size; m.bg = opt->background_brightness;
     m.sigma_thresh = opt->sigma_thresh; m.stop_thresh = opt->stop_thresh;
     return 0;
 }
 
-static int make_source(const float* origins, const float* dirs, int64_t Q, const svoxb_camera* cam, RaySource& s) {
+// NDC (rt_kernel.cu:1168-1191) applies to camera rays only: the reference's ray-batch kernels never call it.
+static int make_source(const float* origins, const float* dirs, const float* vdirs, int64_t Q, const svoxb_camera* cam,
+                       const svoxb_render_options* opt, RaySource& s) {
     s = RaySource{};
+    s.ndc_w = -1;
+    s.vdirs = vdirs;
     if (cam) {
+        if (opt->ndc_width >= 0) {
+            SVOXB_REQUIRE(opt->ndc_width > 0 && opt->ndc_height > 0, "bad NDC size %d x %d", opt->ndc_width, opt->ndc_height);
+            s.ndc_w = opt->ndc_width; s.ndc_h = opt->ndc_height; s.ndc_focal = opt->ndc_focal;
+        }
         SVOXB_REQUIRE(cam->c2w != nullptr && cam->width > 0 && cam->height > 0, "bad camera spec");
         SVOXB_REQUIRE((int64_t)cam->width * cam->height < (1ll << 31), "image too large");
         s.c2w = cam->c2w; s.fx = cam->fx; s.fy = cam->fy; s.width = cam->width; s.height = cam->height;
@@ -462,25 +471,33 @@ using namespace svoxb;
 extern "C" int svoxb_render_rays_fwd(const svoxb_tree* tree, const float* origins, const float* dirs,
                                      const float* vdirs, int64_t Q, const svoxb_render_options* opt, float* out,
                                      float* depth, void* stream) {
-    (void)vdirs;
     TreeArgs tr; MarchOpts m; RaySource src;
     int rc = make_tree_args(tree, tr); if (rc) return rc;
     rc = check_opts(opt, m); if (rc) return rc;
-    rc = make_source(origins, dirs, Q, nullptr, src); if (rc) return rc;
+    rc = make_source(origins, dirs, vdirs, Q, nullptr, opt, src); if (rc) return rc;
     SVOXB_REQUIRE(Q == 0 || out != nullptr, "out is NULL");
     if (Q == 0) return 0;
+    if (opt->format != SVOXB_FORMAT_RGBA) {
+        SVOXB_REQUIRE(vdirs != nullptr, "view-dependent formats need vdirs");
+        SVOXB_REQUIRE(depth == nullptr, "fused depth is only available for the RGBA format; call svoxb_render_depth");
+        return fmt_render_fwd(tree, tr, src, m, opt, false, out, (cudaStream_t)stream);
+    }
     return dispatch_fwd<false>(tr, src, m, out, depth, (cudaStream_t)stream);
 }
 
-extern "C" int svoxb_render_rays_bwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
-                                     const svoxb_render_options* opt, const float* grad_out, const float* saved_out,
-                                     float* grad_features, void* stream) {
+extern "C" int svoxb_render_rays_bwd(const svoxb_tree* tree, const float* origins, const float* dirs,
+                                     const float* vdirs, int64_t Q, const svoxb_render_options* opt,
+                                     const float* grad_out, const float* saved_out, float* grad_features, void* stream) {
     TreeArgs tr; MarchOpts m; RaySource src;
     int rc = make_tree_args(tree, tr); if (rc) return rc;
     rc = check_opts(opt, m); if (rc) return rc;
-    rc = make_source(origins, dirs, Q, nullptr, src); if (rc) return rc;
+    rc = make_source(origins, dirs, vdirs, Q, nullptr, opt, src); if (rc) return rc;
     SVOXB_REQUIRE(Q == 0 || (grad_out && saved_out && grad_features), "grad_out/saved_out/grad_features NULL");
     if (Q == 0) return 0;
+    if (opt->format != SVOXB_FORMAT_RGBA) {
+        SVOXB_REQUIRE(vdirs != nullptr, "view-dependent formats need vdirs");
+        return fmt_render_bwd(tree, tr, src, m, opt, false, grad_out, saved_out, grad_features, (cudaStream_t)stream);
+    }
     return dispatch_bwd<false>(tr, src, m, grad_out, saved_out, grad_features, (cudaStream_t)stream);
 }
 
@@ -490,7 +507,11 @@ extern "C" int svoxb_render_image_fwd(const svoxb_tree* tree, const svoxb_camera
     int rc = make_tree_args(tree, tr); if (rc) return rc;
     rc = check_opts(opt, m); if (rc) return rc;
     SVOXB_REQUIRE(cam != nullptr && out != nullptr, "camera/out NULL");
-    rc = make_source(nullptr, nullptr, 0, cam, src); if (rc) return rc;
+    rc = make_source(nullptr, nullptr, nullptr, 0, cam, opt, src); if (rc) return rc;
+    if (opt->format != SVOXB_FORMAT_RGBA) {
+        SVOXB_REQUIRE(depth == nullptr, "fused depth is only available for the RGBA format");
+        return fmt_render_fwd(tree, tr, src, m, opt, true, out, (cudaStream_t)stream);
+    }
     return dispatch_fwd<true>(tr, src, m, out, depth, (cudaStream_t)stream);
 }
 
@@ -501,7 +522,9 @@ extern "C" int svoxb_render_image_bwd(const svoxb_tree* tree, const svoxb_camera
     int rc = make_tree_args(tree, tr); if (rc) return rc;
     rc = check_opts(opt, m); if (rc) return rc;
     SVOXB_REQUIRE(cam && grad_out && saved_out && grad_features, "camera/grad_out/saved_out/grad_features NULL");
-    rc = make_source(nullptr, nullptr, 0, cam, src); if (rc) return rc;
+    rc = make_source(nullptr, nullptr, nullptr, 0, cam, opt, src); if (rc) return rc;
+    if (opt->format != SVOXB_FORMAT_RGBA)
+        return fmt_render_bwd(tree, tr, src, m, opt, true, grad_out, saved_out, grad_features, (cudaStream_t)stream);
     return dispatch_bwd<true>(tr, src, m, grad_out, saved_out, grad_features, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,733 @@
+// svoxb_render_sh.cu -- the march for the reference's remaining render variants:
+//   * view-dependent leaf formats: every output channel is sigmoid(<basis(view dir), B coefficients of the row>)
+//     with a spherical-harmonics (1/4/9/16/25), spherical-Gaussian or anisotropic-SG basis, optionally re-evaluated
+//     per hit after rotating the view direction by the hit row's 3x3 matrix;
+//   * motion-feature render: every hit blends a small per-joint feature table with the hit row's skinning weights.
+//
+// Replaces (reference paths relative to /root/reference/svox_t/csrc):
+//   maybe_precalc_basis                                         rt_kernel.cu:109-185
+//   trace_ray / trace_ray_backward, non-RGBA branches           rt_kernel.cu:283-301, 388-417, 463-473
+//   motion_feature_trace_ray (+ the backward it meant to be)    rt_kernel.cu:885-1064, 1525-1572
+//
+// Same skeleton as the scalar-lane RGBA kernels (svoxb_render.cu): persistent warps, lane = ray for the traversal,
+// finished lanes refilled from the global queue, and the per-hit ROW work done by the whole warp with coalesced row
+// reads (lane <-> coefficient c, c+32, ...). What differs is the per-hit arithmetic:
+//   view-dependent : lanes multiply their coefficients by the owner ray's basis values (kept in shared memory, one
+//                    25-float slot per ray), the products go through a shared scratch row and lane t < C sums the
+//                    B products of output channel t in the reference's order;
+//   motion feature : lane k < F accumulates sum_j w_j * JF[joint_j][k] (the joint table is a few KB, L1-resident);
+//                    the backward reduces dL/dJF in a per-CTA shared-memory table (J x F addresses receive every
+//                    contribution of every ray -- global atomics would serialise on them) and flushes it once.
+#include "svoxb_march.cuh"
+
+namespace svoxb {
+
+constexpr int MAXB = 25;      // basis functions per channel (SH degree 4)
+constexpr int MAXC = 32;      // output channels of the view-dependent / motion-feature renders
+
+struct FmtArgs {
+    int format, B, C, min_comp, max_comp, extra_cols;
+    const float* extra;       // SG [B,>=4]: (lambda, mu) ; ASG [B,>=11]: (a, b, x, y, z)
+    const float* tm;          // [M,4,4] per-row view rotation or nullptr
+};
+
+__constant__ float kSH[22] = {
+    1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f, 0.5462742152960396f,
+    -0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f, -0.4570457994644658f,
+    1.445305721320277f, -0.5900435899266435f,
+    2.5033429417967046f, -1.7701307697799304f, 0.9461746957575601f, -0.6690465435572892f, 0.10578554691520431f,
+    -0.6690465435572892f, 0.47308734787878004f, -1.7701307697799304f, 0.6258357354491761f, 0.0f};
+
+// rt_kernel.cu:109-185. `out` is this ray's slot in shared memory.
+__device__ __forceinline__ void eval_basis(const FmtArgs& f, float x, float y, float z, float* out) {
+    if (f.format == SVOXB_FORMAT_SH) {
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        out[0] = 0.28209479177387814f;
+        if (f.B >= 4) {
+            out[1] = -0.4886025119029199f * y;
+            out[2] = 0.4886025119029199f * z;
+            out[3] = -0.4886025119029199f * x;
+        }
+        if (f.B >= 9) {
+            out[4] = kSH[0] * xy;
+            out[5] = kSH[1] * yz;
+            out[6] = kSH[2] * (2.0f * zz - xx - yy);
+            out[7] = kSH[3] * xz;
+            out[8] = kSH[4] * (xx - yy);
+        }
+        if (f.B >= 16) {
+            out[9] = kSH[5] * y * (3.0f * xx - yy);
+            out[10] = kSH[6] * xy * z;
+            out[11] = kSH[7] * y * (4.0f * zz - xx - yy);
+            out[12] = kSH[8] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+            out[13] = kSH[9] * x * (4.0f * zz - xx - yy);
+            out[14] = kSH[10] * z * (xx - yy);
+            out[15] = kSH[11] * x * (xx - 3.0f * yy);
+        }
+        if (f.B >= 25) {
+            out[16] = kSH[12] * xy * (xx - yy);
+            out[17] = kSH[13] * yz * (3.0f * xx - yy);
+            out[18] = kSH[14] * xy * (7.0f * zz - 1.0f);
+            out[19] = kSH[15] * yz * (7.0f * zz - 3.0f);
+            out[20] = kSH[16] * (zz * (35.0f * zz - 30.0f) + 3.0f);
+            out[21] = kSH[17] * xz * (7.0f * zz - 3.0f);
+            out[22] = kSH[18] * (xx - yy) * (7.0f * zz - 1.0f);
+            out[23] = kSH[19] * xz * (xx - 3.0f * yy);
+            out[24] = kSH[20] * (xx * (xx - 3.0f * yy) - yy * (3.0f * xx - yy));
+        }
+    } else if (f.format == SVOXB_FORMAT_SG) {
+        for (int i = 0; i < f.B; ++i) {
+            const float* p = f.extra + (size_t)i * f.extra_cols;
+            const float dt = x * __ldg(p + 1) + y * __ldg(p + 2) + z * __ldg(p + 3);
+            out[i] = expf(__ldg(p) * (dt - 1.0f)) / (float)f.B;
+        }
+    } else {    // ASG
+        for (int i = 0; i < f.B; ++i) {
+            const float* p = f.extra + (size_t)i * f.extra_cols;
+            const float S = x * __ldg(p + 8) + y * __ldg(p + 9) + z * __ldg(p + 10);
+            const float dx = x * __ldg(p + 2) + y * __ldg(p + 3) + z * __ldg(p + 4);
+            const float dy = x * __ldg(p + 5) + y * __ldg(p + 6) + z * __ldg(p + 7);
+            out[i] = S * expf(-__ldg(p) * dx * dx - __ldg(p + 1) * dy * dy) / (float)f.B;
+        }
+    }
+}
+
+// rt_kernel.cu:283-291: rotate the view direction by the upper 3x3 of the hit row's matrix, then re-evaluate.
+__device__ __forceinline__ void eval_basis_rotated(const FmtArgs& f, int idx, const ViewDir& v, float* out) {
+    const float* m = f.tm + (size_t)(unsigned)idx * 16;
+    const float x = __ldg(m + 0) * v.x + __ldg(m + 1) * v.y + __ldg(m + 2) * v.z;
+    const float y = __ldg(m + 4) * v.x + __ldg(m + 5) * v.y + __ldg(m + 6) * v.z;
+    const float z = __ldg(m + 8) * v.x + __ldg(m + 9) * v.y + __ldg(m + 10) * v.z;
+    eval_basis(f, x, y, z, out);
+}
+
+// Shared memory per warp of the view-dependent kernels.
+struct FmtSmem {
+    float basis[32][MAXB];     // basis of each lane's ray (odd stride: conflict-free lane-per-ray writes)
+    float acc[32][MAXC + 1];   // forward: partial outputs; backward: staged grad_out row (C+1 values)
+    float prod[128];           // per-hit products, coefficient order
+    float gch[MAXC];           // backward: per-channel w * s(1-s) * g
+};
+
+// ------------------------------------------------------------------------------------------------------------
+template <int K, bool ACCEL, bool IMAGE>
+__global__ void __launch_bounds__(BLOCK)
+march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, float* __restrict__ out,
+                     unsigned long long* counter) {
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t* top = smem_u32;
+    const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
+    if (ACCEL) load_top(tr, top);
+    const int lane = threadIdx.x & 31;
+    FmtSmem& sm = reinterpret_cast<FmtSmem*>(smem_u32 + top_words)[threadIdx.x >> 5];
+    const int D = tr.D, B = fa.B, C = fa.C, Co = C + 1;
+    const float* off = tr.offset;
+    const float* scl = tr.scaling;
+    const char* fbase = reinterpret_cast<const char*>(tr.features + lane);
+    const unsigned row_bytes = (unsigned)D * 4u;
+    int comp[K];            // basis index of coefficient lane + 32k, or -1 when it takes no part
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int c = lane + 32 * k, i = c % B;
+        comp[k] = (c < C * B && i >= fa.min_comp && i <= fa.max_comp) ? i : -1;
+    }
+    for (int r = 0; r < 32; ++r) sm.acc[r][lane] = 0.0f;
+    if (lane == 0) for (int r = 0; r < 32; ++r) sm.acc[r][MAXC] = 0.0f;
+
+    Ray ray;
+    ViewDir vd{0.f, 0.f, 0.f};
+    float T = 1.0f;
+    int row = 0;
+    bool active = false;
+    Queue q{0, 0, false};
+    unsigned need = FULL;
+
+    while (true) {
+        if (need) {
+            const unsigned got = refill<IMAGE, true>(src, off, scl, counter, q, need, lane, ray, row, &vd);
+            if ((got >> lane) & 1u) {
+                active = true; T = 1.0f;
+                eval_basis(fa, vd.x, vd.y, vd.z, sm.basis[lane]);
+            }
+            need = 0;
+        }
+        if (__ballot_sync(FULL, active) == 0u) break;
+
+        // ---- phase A: one sample per lane (rt_kernel.cu:261-292) ------------------------------------------------
+        bool hit = false;
+        float w = 0.0f;
+        int hidx = 0, fin = 0;
+        if (active) {
+            if (!(ray.t < ray.tmax)) {
+                fin = 1;
+            } else {
+                int64_t idx; float delta_t, sigma;
+                sample<ACCEL>(tr, top, ray, opt.step, idx, delta_t, sigma);
+                if (sigma > opt.sigma_thresh) {
+                    const float att = expf(-delta_t * ray.ds * sigma);
+                    w = T * (1.0f - att);
+                    hit = true; hidx = (int)idx;
+                    if (fa.tm) eval_basis_rotated(fa, hidx, vd, sm.basis[lane]);
+                    T *= att;
+                    if (T <= opt.stop_thresh) fin = 2;
+                }
+                ray.t += delta_t;
+                if (fin == 0 && !(ray.t < ray.tmax)) fin = 1;
+            }
+        }
+        __syncwarp();
+
+        // ---- phase B: the warp serves the hits one after another (rt_kernel.cu:293-301) ---------------------------
+        unsigned hm = __ballot_sync(FULL, hit);
+        while (hm) {
+            const int r = __ffs(hm) - 1;
+            hm &= hm - 1;
+            const int idx_r = __shfl_sync(FULL, hidx, r);
+            const float w_r = __shfl_sync(FULL, w, r);
+            const float* rowp = row_ptr(fbase, idx_r, row_bytes);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float p = 0.0f;
+                if (comp[k] >= 0) p = sm.basis[r][comp[k]] * __ldg(rowp + 32 * k);
+                sm.prod[lane + 32 * k] = p;
+            }
+            __syncwarp();
+            if (lane < C) {
+                float tmp = 0.0f;
+                for (int i = fa.min_comp; i <= fa.max_comp; ++i) tmp += sm.prod[lane * B + i];
+                sm.acc[r][lane] = fmaf(w_r, fast_sigmoid(tmp), sm.acc[r][lane]);
+            }
+            __syncwarp();
+        }
+
+        // ---- finished rays (rt_kernel.cu:313-326) -----------------------------------------------------------------
+        unsigned fm = __ballot_sync(FULL, fin != 0);
+        if (fm) {
+            need = fm;
+            if (fin != 0) active = false;
+            while (fm) {
+                const int r = __ffs(fm) - 1;
+                fm &= fm - 1;
+                const float T_r = __shfl_sync(FULL, T, r);
+                const int fin_r = __shfl_sync(FULL, fin, r);
+                const int row_r = __shfl_sync(FULL, row, r);
+                if (lane < Co) {
+                    float v;
+                    if (lane == C) v = 1.0f - T_r;
+                    else if (fin_r == 2) v = sm.acc[r][lane] * (float)(1.0 / (1.0 - (double)T_r));
+                    else v = sm.acc[r][lane] + T_r * opt.bg;
+                    out[(int64_t)row_r * Co + lane] = v;
+                    sm.acc[r][lane] = 0.0f;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Backward of the above: ONE re-march with accum = <g, out> from the saved forward output (see svoxb_render.cu).
+// With per-row rotations the basis is re-evaluated at every hit -- the reference's second pass keeps the basis of
+// the last hit of its first pass (rt_kernel.cu:446-494 never call maybe_precalc_basis), which is not the gradient.
+template <int K, bool ACCEL, bool IMAGE>
+__global__ void __launch_bounds__(BLOCK)
+march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, const float* __restrict__ grad_out,
+                     const float* __restrict__ saved_out, float* __restrict__ grad, unsigned long long* counter) {
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t* top = smem_u32;
+    const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
+    if (ACCEL) load_top(tr, top);
+    const int lane = threadIdx.x & 31;
+    FmtSmem& sm = reinterpret_cast<FmtSmem*>(smem_u32 + top_words)[threadIdx.x >> 5];
+    const int D = tr.D, B = fa.B, C = fa.C, Co = C + 1;
+    const float* off = tr.offset;
+    const float* scl = tr.scaling;
+    const char* fbase = reinterpret_cast<const char*>(tr.features + lane);
+    char* gbase = reinterpret_cast<char*>(grad + lane);
+    const unsigned row_bytes = (unsigned)D * 4u;
+    int comp[K], chan[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int c = lane + 32 * k, i = c % B;
+        comp[k] = (c < C * B && i >= fa.min_comp && i <= fa.max_comp) ? i : -1;
+        chan[k] = min(c / B, MAXC - 1);
+    }
+
+    Ray ray;
+    ViewDir vd{0.f, 0.f, 0.f};
+    float T = 1.0f, accum = 0.0f, T_end = 0.0f, gop = 0.0f;
+    int row = 0;
+    bool active = false;
+    Queue q{0, 0, false};
+    unsigned need = FULL;
+
+    while (true) {
+        if (need) {
+            unsigned got = refill<IMAGE, true>(src, off, scl, counter, q, need, lane, ray, row, &vd);
+            if ((got >> lane) & 1u) {
+                active = true; T = 1.0f;
+                eval_basis(fa, vd.x, vd.y, vd.z, sm.basis[lane]);
+            }
+            need = 0;
+            while (got) {       // per new ray: stage grad_out, accum = sum_{t<C} g_t out_t, T_end, g_opacity
+                const int r = __ffs(got) - 1;
+                got &= got - 1;
+                const int row_r = __shfl_sync(FULL, row, r);
+                float gv = 0.0f, ov = 0.0f;
+                if (lane < Co) {
+                    gv = __ldg(grad_out + (int64_t)row_r * Co + lane);
+                    ov = __ldg(saved_out + (int64_t)row_r * Co + lane);
+                    sm.acc[r][lane] = gv;
+                }
+                float part = lane < C ? gv * ov : 0.0f;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(FULL, part, s);
+                const float g_last = __shfl_sync(FULL, gv, C), o_last = __shfl_sync(FULL, ov, C);
+                if (lane == r) { accum = part; T_end = 1.0f - o_last; gop = g_last; }
+            }
+            __syncwarp();
+        }
+        if (__ballot_sync(FULL, active) == 0u) break;
+
+        bool hit = false, fin = false;
+        float w = 0.0f, dd = 0.0f;
+        int hidx = 0;
+        if (active) {
+            if (!(ray.t < ray.tmax)) {
+                fin = true;
+            } else {
+                int64_t idx; float delta_t, sigma;
+                sample<ACCEL>(tr, top, ray, opt.step, idx, delta_t, sigma);
+                if (sigma > 0.0f) {                                              // rt_kernel.cu:382,456
+                    const float att = expf(-delta_t * sigma * ray.ds);
+                    w = T * (1.0f - att);
+                    dd = delta_t * ray.ds;
+                    hit = true; hidx = (int)idx;
+                    if (fa.tm) eval_basis_rotated(fa, hidx, vd, sm.basis[lane]);
+                    T *= att;
+                }
+                ray.t += delta_t;
+                if (!(ray.t < ray.tmax)) fin = true;
+            }
+        }
+        __syncwarp();
+
+        unsigned hm = __ballot_sync(FULL, hit);
+        while (hm) {
+            const int r = __ffs(hm) - 1;
+            hm &= hm - 1;
+            const int idx_r = __shfl_sync(FULL, hidx, r);
+            const float w_r = __shfl_sync(FULL, w, r);
+            const float* rowp = row_ptr(fbase, idx_r, row_bytes);
+            float bas[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float p = 0.0f;
+                bas[k] = 0.0f;
+                if (comp[k] >= 0) { bas[k] = sm.basis[r][comp[k]]; p = bas[k] * __ldg(rowp + 32 * k); }
+                sm.prod[lane + 32 * k] = p;
+            }
+            __syncwarp();
+            float cpart = 0.0f;
+            if (lane < C) {
+                float tmp = 0.0f;
+                for (int i = fa.min_comp; i <= fa.max_comp; ++i) tmp += sm.prod[lane * B + i];
+                const float s = fast_sigmoid(tmp), gv = sm.acc[r][lane];
+                cpart = s * gv;                                                  // rt_kernel.cu:416
+                sm.gch[lane] = w_r * s * (1.0f - s) * gv;                        // rt_kernel.cu:409-413
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) cpart += __shfl_xor_sync(FULL, cpart, s);
+            float sgrad = 0.0f;
+            if (lane == r) {
+                accum -= w * cpart;                                              // rt_kernel.cu:479-480
+                sgrad = dd * (cpart * T - accum) + dd * gop * T_end;             // rt_kernel.cu:486-490
+            }
+            sgrad = __shfl_sync(FULL, sgrad, r);
+            __syncwarp();
+            float* grow = row_ptr(gbase, idx_r, row_bytes);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (comp[k] >= 0) atomicAdd(grow + 32 * k, sm.gch[chan[k]] * bas[k]);
+                else if (lane + 32 * k == D - 1) atomicAdd(grow + 32 * k, sgrad);
+            }
+            __syncwarp();
+        }
+
+        const unsigned fm = __ballot_sync(FULL, fin);
+        if (fm) {
+            if (fin) active = false;
+            need = fm;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Motion-feature render. jf[J,F] joint features, sw[M,NB] skinning weights and ji[M,NB] joint indices per leaf row.
+struct JointArgs {
+    const float* jf;
+    const float* sw;
+    const int32_t* ji;
+    int J, F, NB;
+};
+
+// pos_joint_feature[k] of row idx (rt_kernel.cu:953-958); lane k < F.
+__device__ __forceinline__ float blend_joint_feature(const JointArgs& ja, int idx, int lane) {
+    float pj = 0.0f;
+    const float* swr = ja.sw + (size_t)(unsigned)idx * ja.NB;
+    const int32_t* jir = ja.ji + (size_t)(unsigned)idx * ja.NB;
+    for (int j = 0; j < ja.NB; ++j) {
+        const float wj = __ldg(swr + j);
+        if (wj > 0.0f) pj += wj * __ldg(ja.jf + (size_t)__ldg(jir + j) * ja.F + lane);
+    }
+    return pj;
+}
+
+template <bool ACCEL>
+__global__ void __launch_bounds__(BLOCK)
+motion_feature_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, float* __restrict__ out,
+                          unsigned long long* counter) {
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t* top = smem_u32;
+    const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
+    if (ACCEL) load_top(tr, top);
+    const int lane = threadIdx.x & 31;
+    float (*acc)[32] = reinterpret_cast<float (*)[32]>(smem_u32 + top_words) + (threadIdx.x >> 5) * 32;
+    const int F = ja.F;
+    const float* off = tr.offset;
+    const float* scl = tr.scaling;
+    for (int r = 0; r < 32; ++r) acc[r][lane] = 0.0f;
+
+    Ray ray;
+    float T = 1.0f;
+    int row = 0;
+    bool active = false, missed = false;
+    Queue q{0, 0, false};
+    unsigned need = FULL;
+
+    while (true) {
+        if (need) {
+            const unsigned got = refill<false>(src, off, scl, counter, q, need, lane, ray, row);
+            if ((got >> lane) & 1u) {
+                active = true; T = 1.0f;
+                float a, b;                                      // a ray that misses the cube returns zeros, not the
+                dda_unit(ray.ox, ray.oy, ray.oz, ray.ix, ray.iy, ray.iz, a, b);   // background (rt_kernel.cu:911-916)
+                missed = b < 0.0f || a > b;
+            }
+            need = 0;
+        }
+        if (__ballot_sync(FULL, active) == 0u) break;
+
+        bool hit = false;
+        float w = 0.0f;
+        int hidx = 0, fin = 0;
+        if (active) {
+            if (!(ray.t < ray.tmax)) {
+                fin = missed ? 3 : 1;
+            } else {
+                int64_t idx; float delta_t, sigma;
+                sample<ACCEL>(tr, top, ray, opt.step, idx, delta_t, sigma);
+                if (sigma > opt.sigma_thresh) {
+                    const float att = expf(-delta_t * ray.ds * sigma);
+                    w = T * (1.0f - att);
+                    hit = true; hidx = (int)idx;
+                    T *= att;
+                    if (T <= opt.stop_thresh) fin = 2;
+                }
+                ray.t += delta_t;
+                if (fin == 0 && !(ray.t < ray.tmax)) fin = 1;
+            }
+        }
+
+        unsigned hm = __ballot_sync(FULL, hit);
+        while (hm) {
+            const int r = __ffs(hm) - 1;
+            hm &= hm - 1;
+            const int idx_r = __shfl_sync(FULL, hidx, r);
+            const float w_r = __shfl_sync(FULL, w, r);
+            if (lane < F) acc[r][lane] = fmaf(w_r, fast_sigmoid(blend_joint_feature(ja, idx_r, lane)), acc[r][lane]);
+        }
+
+        unsigned fm = __ballot_sync(FULL, fin != 0);
+        if (fm) {
+            need = fm;
+            if (fin != 0) active = false;
+            while (fm) {
+                const int r = __ffs(fm) - 1;
+                fm &= fm - 1;
+                const float T_r = __shfl_sync(FULL, T, r);
+                const int fin_r = __shfl_sync(FULL, fin, r);
+                const int row_r = __shfl_sync(FULL, row, r);
+                if (lane < F) {
+                    float v = acc[r][lane];
+                    if (fin_r == 2) v *= (float)(1.0 / (1.0 - (double)T_r));     // rt_kernel.cu:966-970
+                    else if (fin_r == 1) v += T_r * opt.bg;                      // rt_kernel.cu:975-977
+                    else v = 0.0f;
+                    out[(int64_t)row_r * F + lane] = v;
+                    acc[r][lane] = 0.0f;
+                }
+            }
+        }
+    }
+}
+
+// dL/dJF[joint_j][k] += w_j * weight * s_k (1 - s_k) * g[k] at every sample with sigma > 0: what
+// rt_kernel.cu:981-1064 set out to compute (Appendix B3 lists what its code does instead).
+template <bool ACCEL>
+__global__ void __launch_bounds__(BLOCK)
+motion_feature_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, const float* __restrict__ grad_out,
+                          float* __restrict__ grad_jf, int use_table, unsigned long long* counter) {
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t* top = smem_u32;
+    const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
+    if (ACCEL) load_top(tr, top);
+    const int lane = threadIdx.x & 31;
+    float (*gs)[32] = reinterpret_cast<float (*)[32]>(smem_u32 + top_words) + (threadIdx.x >> 5) * 32;
+    float* table = reinterpret_cast<float*>(smem_u32 + top_words) + WARPS * 32 * 32;     // [J][F], this CTA's partial sums
+    const int F = ja.F, JF = ja.J * ja.F;
+    const float* off = tr.offset;
+    const float* scl = tr.scaling;
+    if (use_table) {
+        for (int i = threadIdx.x; i < JF; i += blockDim.x) table[i] = 0.0f;
+        __syncthreads();
+    }
+    float* dst = use_table ? table : grad_jf;
+
+    Ray ray;
+    float T = 1.0f;
+    int row = 0;
+    bool active = false;
+    Queue q{0, 0, false};
+    unsigned need = FULL;
+
+    while (true) {
+        if (need) {
+            unsigned got = refill<false>(src, off, scl, counter, q, need, lane, ray, row);
+            if ((got >> lane) & 1u) { active = true; T = 1.0f; }
+            need = 0;
+            while (got) {
+                const int r = __ffs(got) - 1;
+                got &= got - 1;
+                const int row_r = __shfl_sync(FULL, row, r);
+                gs[r][lane] = lane < F ? __ldg(grad_out + (int64_t)row_r * F + lane) : 0.0f;
+            }
+            __syncwarp();
+        }
+        if (__ballot_sync(FULL, active) == 0u) break;
+
+        bool hit = false, fin = false;
+        float w = 0.0f;
+        int hidx = 0;
+        if (active) {
+            if (!(ray.t < ray.tmax)) {
+                fin = true;
+            } else {
+                int64_t idx; float delta_t, sigma;
+                sample<ACCEL>(tr, top, ray, opt.step, idx, delta_t, sigma);
+                if (sigma > 0.0f) {                                              // rt_kernel.cu:1029
+                    const float att = expf(-delta_t * sigma * ray.ds);
+                    w = T * (1.0f - att);
+                    hit = true; hidx = (int)idx;
+                    T *= att;
+                }
+                ray.t += delta_t;
+                if (!(ray.t < ray.tmax)) fin = true;
+            }
+        }
+
+        unsigned hm = __ballot_sync(FULL, hit);
+        while (hm) {
+            const int r = __ffs(hm) - 1;
+            hm &= hm - 1;
+            const int idx_r = __shfl_sync(FULL, hidx, r);
+            const float w_r = __shfl_sync(FULL, w, r);
+            if (lane < F) {
+                const float s = fast_sigmoid(blend_joint_feature(ja, idx_r, lane));
+                const float gt = w_r * s * (1.0f - s) * gs[r][lane];
+                const float* swr = ja.sw + (size_t)(unsigned)idx_r * ja.NB;
+                const int32_t* jir = ja.ji + (size_t)(unsigned)idx_r * ja.NB;
+                for (int j = 0; j < ja.NB; ++j) {
+                    const float wj = __ldg(swr + j);
+                    if (wj > 0.0f) atomicAdd(dst + (size_t)__ldg(jir + j) * F + lane, wj * gt);
+                }
+            }
+        }
+
+        const unsigned fm = __ballot_sync(FULL, fin);
+        if (fm) {
+            if (fin) active = false;
+            need = fm;
+        }
+    }
+    if (use_table) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < JF; i += blockDim.x) {
+            const float v = table[i];
+            if (v != 0.0f) atomicAdd(grad_jf + i, v);
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+int make_tree_args(const svoxb_tree* t, TreeArgs& a);   // svoxb_tree.cu
+
+static int make_fmt(const svoxb_tree* tree, const svoxb_render_options* opt, FmtArgs& f) {
+    const int D = tree->D, B = opt->basis_dim;
+    SVOXB_REQUIRE(opt->format == SVOXB_FORMAT_SH || opt->format == SVOXB_FORMAT_SG || opt->format == SVOXB_FORMAT_ASG,
+                  "unknown data format %d", opt->format);
+    SVOXB_REQUIRE(B >= 1 && B <= MAXB, "basis_dim=%d out of range [1,%d]", B, MAXB);
+    if (opt->format == SVOXB_FORMAT_SH)
+        SVOXB_REQUIRE(B == 1 || B == 4 || B == 9 || B == 16 || B == 25, "SH basis_dim=%d must be 1, 4, 9, 16 or 25", B);
+    SVOXB_REQUIRE(D <= 128, "feature width D=%d not supported (max 128)", D);
+    f.format = opt->format; f.B = B; f.C = (D - 1) / B;                    // rt_kernel.cu:1352-1358
+    SVOXB_REQUIRE(f.C >= 1 && f.C <= MAXC, "%d output channels out of range [1,%d]", f.C, MAXC);
+    f.min_comp = opt->min_comp; f.max_comp = opt->max_comp;
+    SVOXB_REQUIRE(f.min_comp >= 0 && f.max_comp < B && f.min_comp <= f.max_comp,
+                  "min_comp=%d / max_comp=%d out of range for basis_dim=%d", f.min_comp, f.max_comp, B);
+    f.extra = tree->extra_data; f.extra_cols = tree->extra_cols;
+    if (opt->format != SVOXB_FORMAT_SH) {
+        const int need = opt->format == SVOXB_FORMAT_SG ? 4 : 11;
+        SVOXB_REQUIRE(f.extra != nullptr && tree->extra_rows >= B && tree->extra_cols >= need,
+                      "SG/ASG formats need extra_data [>=%d, >=%d]", B, need);
+    }
+    f.tm = tree->transformation_matrices;
+    return 0;
+}
+
+template <int K, bool ACCEL, bool IMAGE>
+static int launch_fmt_fwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const FmtArgs& f, float* out,
+                          cudaStream_t st) {
+    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(FmtSmem) * WARPS;
+    auto kern = march_fmt_fwd_kernel<K, ACCEL, IMAGE>;
+    int grid = 0;
+    int rc = persistent_grid(kern, smem, src.total, grid);
+    if (rc) return rc;
+    unsigned long long* counter = work_counter(st);
+    if (!counter) return SVOXB_ECUDA;
+    kern<<<grid, BLOCK, smem, st>>>(tr, src, m, f, out, counter);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "march_fmt_fwd_kernel launch");
+}
+
+template <int K, bool ACCEL, bool IMAGE>
+static int launch_fmt_bwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const FmtArgs& f,
+                          const float* go, const float* so, float* grad, cudaStream_t st) {
+    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(FmtSmem) * WARPS;
+    auto kern = march_fmt_bwd_kernel<K, ACCEL, IMAGE>;
+    int grid = 0;
+    int rc = persistent_grid(kern, smem, src.total, grid);
+    if (rc) return rc;
+    unsigned long long* counter = work_counter(st);
+    if (!counter) return SVOXB_ECUDA;
+    kern<<<grid, BLOCK, smem, st>>>(tr, src, m, f, go, so, grad, counter);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "march_fmt_bwd_kernel launch");
+}
+
+#define SVOXB_FMT_DISPATCH(FN, ...)                                                                       \
+    do {                                                                                                  \
+        const int K = (tr.D + 31) / 32;                                                                   \
+        const int sel = K * 4 + (tr.use_accel ? 2 : 0) + (image ? 1 : 0);                                 \
+        switch (sel) {                                                                                    \
+            case 4: return FN<1, false, false>(__VA_ARGS__);  case 5: return FN<1, false, true>(__VA_ARGS__);   \
+            case 6: return FN<1, true, false>(__VA_ARGS__);   case 7: return FN<1, true, true>(__VA_ARGS__);    \
+            case 8: return FN<2, false, false>(__VA_ARGS__);  case 9: return FN<2, false, true>(__VA_ARGS__);   \
+            case 10: return FN<2, true, false>(__VA_ARGS__);  case 11: return FN<2, true, true>(__VA_ARGS__);   \
+            case 12: return FN<3, false, false>(__VA_ARGS__); case 13: return FN<3, false, true>(__VA_ARGS__);  \
+            case 14: return FN<3, true, false>(__VA_ARGS__);  case 15: return FN<3, true, true>(__VA_ARGS__);   \
+            case 16: return FN<4, false, false>(__VA_ARGS__); case 17: return FN<4, false, true>(__VA_ARGS__);  \
+            case 18: return FN<4, true, false>(__VA_ARGS__);  case 19: return FN<4, true, true>(__VA_ARGS__);   \
+            default: break;                                                                               \
+        }                                                                                                 \
+        set_error("feature width D=%d not supported (max 128)", tr.D);                                   \
+        return SVOXB_EINVAL;                                                                              \
+    } while (0)
+
+// Entry points used by svoxb_render.cu when opt->format != RGBA.
+int fmt_render_fwd(const svoxb_tree* tree, const TreeArgs& tr, const RaySource& src, const MarchOpts& m,
+                   const svoxb_render_options* opt, bool image, float* out, cudaStream_t st) {
+    FmtArgs f;
+    int rc = make_fmt(tree, opt, f); if (rc) return rc;
+    SVOXB_FMT_DISPATCH(launch_fmt_fwd, tr, src, m, f, out, st);
+}
+
+int fmt_render_bwd(const svoxb_tree* tree, const TreeArgs& tr, const RaySource& src, const MarchOpts& m,
+                   const svoxb_render_options* opt, bool image, const float* go, const float* so, float* grad,
+                   cudaStream_t st) {
+    FmtArgs f;
+    int rc = make_fmt(tree, opt, f); if (rc) return rc;
+    SVOXB_FMT_DISPATCH(launch_fmt_bwd, tr, src, m, f, go, so, grad, st);
+}
+
+static int make_joint_args(const svoxb_tree* tree, const float* jf, const float* sw, const int32_t* ji, int J, int F,
+                           int NB, JointArgs& ja) {
+    SVOXB_REQUIRE(jf && sw && ji, "joint_features / skinning_weights / joint_index are NULL");
+    SVOXB_REQUIRE(J >= 1 && F >= 1 && F <= 32 && NB >= 1, "motion feature render: J=%d, F=%d (max 32), B=%d", J, F, NB);
+    (void)tree;
+    ja.jf = jf; ja.sw = sw; ja.ji = ji; ja.J = J; ja.F = F; ja.NB = NB;
+    return 0;
+}
+
+}  // namespace svoxb
+
+using namespace svoxb;
+
+extern "C" int svoxb_out_data_dim(int32_t format, int32_t basis_dim, int32_t D) {
+    if (format == SVOXB_FORMAT_RGBA) return D;
+    return basis_dim > 0 ? (D - 1) / basis_dim + 1 : -1;
+}
+
+extern "C" int svoxb_motion_feature_render_fwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                                               const svoxb_render_options* opt, const float* joint_features,
+                                               const float* skinning_weights, const int32_t* joint_index, int32_t J,
+                                               int32_t F, int32_t B, float* out, void* stream) {
+    TreeArgs tr; JointArgs ja;
+    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    SVOXB_REQUIRE(opt != nullptr, "render options are NULL");
+    rc = make_joint_args(tree, joint_features, skinning_weights, joint_index, J, F, B, ja); if (rc) return rc;
+    SVOXB_REQUIRE(Q >= 0 && Q < (1ll << 31) && (Q == 0 || (origins && dirs && out)), "bad ray batch");
+    if (Q == 0) return 0;
+    MarchOpts m{opt->step_size, opt->background_brightness, opt->sigma_thresh, opt->stop_thresh};
+    RaySource src{}; src.origins = origins; src.dirs = dirs; src.total = Q; src.ndc_w = -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (tr.use_accel ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * WARPS * 32 * 32;
+    void (*kern)(TreeArgs, RaySource, MarchOpts, JointArgs, float*, unsigned long long*) =
+        tr.use_accel ? motion_feature_fwd_kernel<true> : motion_feature_fwd_kernel<false>;
+    int grid = 0;
+    rc = persistent_grid(kern, smem, Q, grid); if (rc) return rc;
+    unsigned long long* counter = work_counter(st);
+    if (!counter) return SVOXB_ECUDA;
+    kern<<<grid, BLOCK, smem, st>>>(tr, src, m, ja, out, counter);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "motion_feature_fwd_kernel launch");
+}
+
+extern "C" int svoxb_motion_feature_render_bwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                                               const svoxb_render_options* opt, const float* joint_features,
+                                               const float* skinning_weights, const int32_t* joint_index, int32_t J,
+                                               int32_t F, int32_t B, const float* grad_out, float* grad_joint_features,
+                                               void* stream) {
+    TreeArgs tr; JointArgs ja;
+    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    SVOXB_REQUIRE(opt != nullptr, "render options are NULL");
+    rc = make_joint_args(tree, joint_features, skinning_weights, joint_index, J, F, B, ja); if (rc) return rc;
+    SVOXB_REQUIRE(grad_joint_features != nullptr, "grad_joint_features is NULL");
+    SVOXB_REQUIRE(Q >= 0 && Q < (1ll << 31) && (Q == 0 || (origins && dirs && grad_out)), "bad ray batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    SVOXB_CUDA(cudaMemsetAsync(grad_joint_features, 0, sizeof(float) * (size_t)J * F, st));
+    if (Q == 0) return 0;
+    MarchOpts m{opt->step_size, opt->background_brightness, opt->sigma_thresh, opt->stop_thresh};
+    RaySource src{}; src.origins = origins; src.dirs = dirs; src.total = Q; src.ndc_w = -1;
+    const size_t table = sizeof(float) * (size_t)J * F;
+    const int use_table = table <= 96 * 1024;
+    const size_t smem = (tr.use_accel ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * WARPS * 32 * 32 +
+                        (use_table ? table : 0);
+    void (*kern)(TreeArgs, RaySource, MarchOpts, JointArgs, const float*, float*, int, unsigned long long*) =
+        tr.use_accel ? motion_feature_bwd_kernel<true> : motion_feature_bwd_kernel<false>;
+    int grid = 0;
+    rc = persistent_grid(kern, smem, Q, grid); if (rc) return rc;
+    unsigned long long* counter = work_counter(st);
+    if (!counter) return SVOXB_ECUDA;
+    kern<<<grid, BLOCK, smem, st>>>(tr, src, m, ja, grad_out, grad_joint_features, use_table, counter);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "motion_feature_bwd_kernel launch");
+}

@@ -132,7 +132,7 @@ int make_tree_args(const svoxb_tree* t, TreeArgs& a);
 
 static int simple_opts(const svoxb_render_options* opt, MarchOpts& m) {
     SVOXB_REQUIRE(opt != nullptr, "render options are NULL");
-    if (opt->ndc_width >= 0) { set_error("NDC ray conversion is not implemented"); return SVOXB_EUNSUPPORTED; }
+    // ndc_* are ignored here exactly as in the reference: only its image kernels convert rays (rt_kernel.cu:1204)
     m.step = opt->step_size; m.bg = opt->background_brightness;
     m.sigma_thresh = opt->sigma_thresh; m.stop_thresh = opt->stop_thresh;
     return 0;

@@ -2,8 +2,9 @@
 
 API of the reference's ``svox_t.renderer`` (svox_t/renderer.py:162-439): ``forward(features, rays, ...)``,
 ``render_persp(features, c2w, width, height, fx, fy)``, ``render_depth(features, rays)``; output rows are
-``D-1`` composited sigmoid features followed by opacity. Gradients flow into ``features`` through a custom
-autograd Function backed by the single-re-march backward kernel.
+``D-1`` composited sigmoid features followed by opacity (``data_format`` RGBA, the hot path) or
+``(D-1)/basis_dim`` view-dependent channels followed by opacity (SH / SG / ASG trees). Gradients flow into
+``features`` through a custom autograd Function backed by the single-re-march backward kernel.
 
 Extensions: ``forward_with_depth`` / ``render_persp_with_depth`` return the first-hit depth from the same march
 (the reference launches a second kernel, renderer.py:377-382).
@@ -81,6 +82,23 @@ class _VolumeRenderImageFunction(autograd.Function):
         return None, None, None, None, None
 
 
+class _MotionFeatureRenderFunction(autograd.Function):
+    """renderer.py:96-116; differentiable w.r.t. ``joint_features`` with the gradient the reference meant to compute
+    (its kernel is broken)."""
+
+    @staticmethod
+    def forward(ctx, data, tree, rays, opt):
+        ctx.tree, ctx.rays, ctx.opt = tree, rays, opt
+        return _C.motion_feature_render(tree, rays, opt)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if ctx.needs_input_grad[0]:
+            return (_C.motion_feature_render_backward(ctx.tree, ctx.rays, ctx.opt, grad_out.contiguous()),
+                    None, None, None)
+        return None, None, None, None
+
+
 class _OpacityRenderFunction(autograd.Function):
     """renderer.py:118-138, with the backward the reference meant to run (Appendix B2)."""
 
@@ -123,7 +141,8 @@ class VolumeRenderer(nn.Module):
         keep the in-kernel sigmoid, for which one pass over the whole table would cost more than it saves."""
         ts = self.tree._spec(features, **kw)
         M, D = features.shape
-        if D % 4 == 0 and 4 <= D <= 128 and n_rays * 32 >= M and features.is_cuda:
+        if (self.data_format.format == DataFormat.RGBA and D % 4 == 0 and 4 <= D <= 128 and n_rays * 32 >= M
+                and features.is_cuda):
             ts._act = self.tree.activated(features.detach())
         return ts
 
@@ -133,8 +152,9 @@ class VolumeRenderer(nn.Module):
             raise RuntimeError("svox_t_b200 renders on CUDA only: there is no CPU / PyTorch fallback path")
 
     def forward(self, features, rays: Rays, transformation_matrices=None, cuda=True, fast=False):
-        """Render a ray batch -> (B, D): D-1 features + opacity. Differentiable w.r.t. ``features``.
-        ``transformation_matrices`` is accepted and, as in the reference's RGBA path, has no effect."""
+        """Render a ray batch -> (B, D): D-1 features + opacity (RGBA), or (B, (D-1)/basis_dim + 1) for SH / SG / ASG
+        trees. Differentiable w.r.t. ``features``. ``transformation_matrices`` [M,4,4] rotates the view direction per
+        hit row before the basis is evaluated; as in the reference it has no effect on the RGBA format."""
         self._require_cuda(cuda)
         return _VolumeRenderFunction.apply(
             features, self._render_spec(features, rays.origins.shape[0], transformation_matrices=transformation_matrices),
@@ -173,8 +193,14 @@ class VolumeRenderer(nn.Module):
         self._require_cuda(cuda)
         return tuple(_C.motion_render(self.tree._spec(features), _rays_spec_from_rays(rays), self._get_options(fast)))
 
-    def motion_feature_render(self, *a, **k):
-        return _C.motion_feature_render()
+    def motion_feature_render(self, features, joint_features, skinning_weights, joint_index, rays: Rays, cuda=True,
+                              fast=False):
+        """Composited per-joint features (B, F): every hit blends ``joint_features`` [J,F] with the hit row's
+        ``skinning_weights`` / ``joint_index`` [M,B]. Differentiable w.r.t. ``joint_features`` (renderer.py:384-396)."""
+        self._require_cuda(cuda)
+        return _MotionFeatureRenderFunction.apply(
+            joint_features, self.tree._spec(features, joint_features, skinning_weights, joint_index),
+            _rays_spec_from_rays(rays), self._get_options(fast))
 
     def opacity_render(self, features, rays: Rays, cuda=True, fast=False):
         """Opacity only (B, 1); differentiable w.r.t. the sigma channel of ``features`` (renderer.py:397-406)."""

@@ -17,12 +17,21 @@ def pytest_configure(config):
 
 def golden_files():
     """Fixtures of the main render path (volume_render / backward / depth / query)."""
-    return sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("x_"))
+    return sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("x_", "y_")))
 
 
 def golden_variant_files():
     """Fixtures of the march variants (opacity_render, motion_render)."""
     return sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("x_ball"))
+
+
+def golden_fmt_file():
+    """Fixture of the view-dependent formats + motion-feature render (tests/golden/make_golden_fmt.py)."""
+    return os.path.join(GOLDEN_DIR, "y_fmt_ball_L4.npz")
+
+
+def fmt_case_names(z):
+    return sorted(k[:-5] for k in z.files if k.endswith("_meta"))
 
 
 @pytest.fixture(scope="session")

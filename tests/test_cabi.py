@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), f"{name} declared in include/svoxb.h but not exported by libsvoxb.so"
     assert sorted(C.SYMBOLS) == declared_symbols(), "python prototypes out of sync with include/svoxb.h"
-    assert lib.svoxb_abi_version() == 2
+    assert lib.svoxb_abi_version() == 3
 
 
 def test_struct_layouts_match_header():
@@ -35,7 +35,28 @@ def test_struct_layouts_match_header():
     assert [f[0] for f in C._COptions._fields_] == ["step_size", "background_brightness", "format", "basis_dim",
                                                     "ndc_width", "ndc_height", "ndc_focal", "min_comp", "max_comp",
                                                     "sigma_thresh", "stop_thresh"]
-    assert ctypes.sizeof(C._CTree) == 96 and ctypes.sizeof(C._CCamera) == 24
+    assert ctypes.sizeof(C._CTree) == 120 and ctypes.sizeof(C._CCamera) == 24
+
+
+def test_ctypes_structs_match_the_header_as_gcc_lays_it_out(tmp_path):
+    """Compile include/svoxb.h with gcc and compare sizeof / offsetof of every struct field with the ctypes mirrors."""
+    import subprocess
+    structs = {"svoxb_tree": C._CTree, "svoxb_render_options": C._COptions, "svoxb_camera": C._CCamera}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.abspath(HEADER)}"', "int main(void) {"]
+    for cname, ct in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, ct in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
 
 
 def test_bad_arguments_return_error_codes_not_crashes():

@@ -15,7 +15,7 @@ import torch
 
 import refdrv
 import svox_t_b200 as sv
-from conftest import GOLDEN_DIR, golden_files, golden_variant_files
+from conftest import GOLDEN_DIR, fmt_case_names, golden_files, golden_fmt_file, golden_variant_files
 from oracle import oracle as orc
 from svox_t_b200 import csrc as C
 from svox_t_b200 import synth
@@ -421,3 +421,120 @@ def test_full_size_c2_image(dev, c3_scene):
     oc, dc = orc.camera_rays(cam.cpu().numpy(), 1111.111, 1111.111, 800, 800)
     out = r(feats, sv.Rays(cu(oc, dev), cu(dc, dev), cu(dc, dev)))
     assert frac_within(out.cpu().numpy(), img.cpu().numpy().reshape(-1, 32)) >= 0.999
+
+
+# ---- view-dependent formats, NDC cameras, motion-feature render -------------------------------------
+_FMT_NAMES = {1: "SH", 2: "SG", 3: "ASG"}
+
+
+def _fmt_tree(z, D, fmt, B, extra, dev, accel=True):
+    tree = sv.N3Tree.from_tensors(z["child"], z["data"], z["parent_depth"], data_dim=D,
+                                  data_format=f"{_FMT_NAMES[fmt]}{B}", map_location=dev)
+    if extra is not None:
+        tree.extra_data = cu(extra, dev)
+    if not accel:
+        tree.accel = lambda *a, **k: None          # walk the reference tensors instead of the packed accelerator
+    return tree
+
+
+@pytest.mark.parametrize("accel", [True, False], ids=["accel", "refwalk"])
+def test_view_dependent_formats_against_reference_golden(dev, accel):
+    z = np.load(golden_fmt_file())
+    T = orc.Tree(z["child"], z["data"])
+    rays = sv.Rays(cu(z["origins"], dev), cu(z["dirs"], dev), cu(z["vdirs"], dev))
+    for name in fmt_case_names(z):
+        fmt, B, Cc, cmin, cmax, with_tm = (int(v) for v in z[name + "_meta"])
+        f, g, thr = z[name + "_features"], z[name + "_grad_out"], float(z[name + "_thresh"])
+        extra = z[name + "_extra"] if name + "_extra" in z.files else None
+        tree = _fmt_tree(z, f.shape[1], fmt, B, extra, dev, accel)
+        r = sv.VolumeRenderer(tree, min_comp=cmin, max_comp=cmax)
+        r.sigma_thresh, r.stop_thresh = thr, thr
+        feats = cu(f, dev).requires_grad_(True)
+        out = r(feats, rays, transformation_matrices=cu(z["tm"], dev) if with_tm else None)
+        assert tuple(out.shape) == (len(z["origins"]), Cc + 1)
+        (out * cu(g, dev)).sum().backward()
+        out_n = out.detach().cpu().numpy()
+        assert frac_within(out_n, z[name + "_ref_out"]) >= 0.999, name
+        assert float(np.abs(out_n - z[name + "_ref_out"]).mean()) <= 1e-5, name
+        if with_tm:     # the reference's gradient uses a stale basis here: compare with the oracle's correct one
+            ref_grad = orc.render_rays_fmt_backward(T, f, z["origins"], z["dirs"], z["vdirs"], g, fmt, B, extra=extra,
+                                                    tm=z["tm"], min_comp=cmin, max_comp=cmax)
+        else:
+            ref_grad = z[name + "_ref_grad"]
+        assert rel_l2(feats.grad.cpu().numpy(), ref_grad) <= 1e-4, name
+
+
+def test_motion_feature_render_forward_reference_backward_oracle(dev):
+    z = np.load(golden_fmt_file())
+    f4, jf, sw, ji = z["mf_features"], z["mf_jf"], z["mf_sw"], z["mf_ji"]
+    T = orc.Tree(z["child"], z["data"])
+    tree = make_tree(z, 4, dev)
+    rays = sv.Rays(cu(z["origins"], dev), cu(z["dirs"], dev), cu(z["dirs"], dev))
+    for tag, thr in (("default", 0.0), ("fast", 1e-2)):
+        r = sv.VolumeRenderer(tree, background_brightness=0.5)
+        r.sigma_thresh, r.stop_thresh = thr, thr
+        jft = cu(jf, dev).requires_grad_(True)
+        out = r.motion_feature_render(cu(f4, dev), jft, cu(sw, dev), cu(ji, dev), rays)
+        assert frac_within(out.detach().cpu().numpy(), z["mf_ref_out_" + tag]) >= 0.999
+        g = np.random.default_rng(1).standard_normal(tuple(out.shape)).astype(np.float32)
+        (out * cu(g, dev)).sum().backward()
+        g_ref = orc.motion_feature_render_backward(T, f4, z["origins"], z["dirs"], jf, sw, ji, g)
+        assert rel_l2(jft.grad.cpu().numpy(), g_ref) <= 1e-4
+    # rays that miss the cube return zeros, not the background (rt_kernel.cu:911-916)
+    o = np.array([[3, 3, 3], [0.5, 0.5, -1.0]], np.float32)
+    d = np.array([[0, 1, 0], [0, 0, 1]], np.float32)
+    out = sv.VolumeRenderer(tree, background_brightness=0.5).motion_feature_render(
+        cu(f4, dev), cu(jf, dev), cu(sw, dev), cu(ji, dev), sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev)))
+    assert not out[0].any() and out[1].any()
+    # many joints: the per-CTA gradient table no longer fits shared memory -> global atomics
+    J2 = 2000
+    rng = np.random.default_rng(3)
+    jf2 = rng.standard_normal((J2, 16)).astype(np.float32)
+    ji2 = rng.integers(0, J2, ji.shape).astype(np.int32)
+    jft = cu(jf2, dev).requires_grad_(True)
+    out = sv.VolumeRenderer(tree).motion_feature_render(cu(f4, dev), jft, cu(sw, dev), cu(ji2, dev), rays)
+    g = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+    (out * cu(g, dev)).sum().backward()
+    assert frac_within(out.detach().cpu().numpy(), orc.motion_feature_render(T, f4, z["origins"], z["dirs"], jf2, sw, ji2)) >= 0.999
+    assert rel_l2(jft.grad.cpu().numpy(),
+                  orc.motion_feature_render_backward(T, f4, z["origins"], z["dirs"], jf2, sw, ji2, g)) <= 1e-4
+
+
+@pytest.mark.parametrize("ndc", [False, True], ids=["world", "ndc"])
+def test_image_render_sh_and_ndc_vs_oracle(dev, ndc):
+    """Camera rays generated in-kernel (+ NDC conversion, rt_kernel.cu:1168-1206) for an SH tree and for the RGBA
+    format, against the oracle marching the oracle's own camera rays. The reference cannot run this path (fact #4)."""
+    tr = synth.synth_tree(5, "ball")
+    T = orc.Tree(tr["child"], tr["data"])
+    W, H, fx = 52, 37, 60.0
+    if ndc:    # forward-facing set-up: camera in front of the NDC cube looking down -z
+        c2w = synth.look_at((0.1, -0.05, 3.0), target=(0.0, 0.0, 0.0))
+        nd = sv.NDCConfig(W, H, fx)
+        kw = dict(ndc_width=W, ndc_height=H, ndc_focal=fx)
+        radius, center = 1.0, 0.0
+    else:
+        c2w = synth.synth_cameras(1)[0]
+        nd, kw, radius, center = None, {}, 0.5, 0.5
+    inv, off = np.full(3, 0.5 / radius), np.full(3, 0.5 * (1.0 - center / radius))
+    T = orc.Tree(tr["child"], tr["data"], off, inv)
+    o, d, vd = orc.camera_rays_ndc(c2w, fx, fx, W, H, **kw)
+    g_rng = np.random.default_rng(8)
+    for fmtname, D in (("SH4", 13), ("RGBA", 8)):
+        f = synth.synth_features(tr["M"], D)
+        tree = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=D, radius=radius,
+                                      center=[center] * 3, data_format=fmtname, map_location=dev)
+        r = sv.VolumeRenderer(tree, ndc=nd)
+        feats = cu(f, dev).requires_grad_(True)
+        img = r.render_persp(feats, cu(c2w, dev), width=W, height=H, fx=fx)
+        Do = img.shape[-1]
+        g = g_rng.standard_normal((H * W, Do)).astype(np.float32)
+        (img * cu(g, dev).view(H, W, Do)).sum().backward()
+        if fmtname == "RGBA":
+            o_ref = orc.render_rays(T, f, o, d)[0]
+            g_ref = orc.render_rays_backward(T, f, o, d, g)
+        else:
+            o_ref = orc.render_rays_fmt(T, f, o, d, vd, orc.FORMAT_SH, 4)
+            g_ref = orc.render_rays_fmt_backward(T, f, o, d, vd, g, orc.FORMAT_SH, 4)
+        assert o_ref[:, -1].max() > 0.5                                   # the object is in view
+        assert frac_within(img.detach().cpu().numpy().reshape(-1, Do), o_ref) >= 0.999
+        assert rel_l2(feats.grad.cpu().numpy(), g_ref) <= 1e-4

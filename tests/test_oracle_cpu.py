@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_DIR, golden_files, golden_variant_files
+from conftest import GOLDEN_DIR, fmt_case_names, golden_files, golden_fmt_file, golden_variant_files
 from oracle import oracle as orc
 from svox_t_b200 import synth
 
@@ -276,6 +276,98 @@ def test_point_kernel_oracle_matches_reference_golden():
     assert np.allclose(vox, z["ref_vox"], rtol=1e-4, atol=1e-4)
     gp, gf = orc.p2v_backward(z["g_vox"], z["ref_coords"], z["feat"], z["corner"], z["size"], n, kr, cr)
     assert np.allclose(gf, z["ref_gf"], rtol=1e-4, atol=1e-4) and np.allclose(gp, z["ref_gp"], rtol=1e-3, atol=1e-2)
+
+
+def test_format_oracle_matches_reference_golden():
+    """SH / SG / ASG (+ per-row rotation, component window, thresholds) and motion-feature forward against the
+    reference's CUDA outputs. Backward with rotations: the reference's second pass keeps a stale basis; the oracle
+    reproduces that with stale_basis=True (and is checked against finite differences without it, below)."""
+    z = np.load(golden_fmt_file())
+    T = orc.Tree(z["child"], z["data"])
+    o, d, vd = z["origins"], z["dirs"], z["vdirs"]
+    names = fmt_case_names(z)
+    assert len(names) >= 8
+    for name in names:
+        fmt, B, C, cmin, cmax, with_tm = (int(v) for v in z[name + "_meta"])
+        f, thr = z[name + "_features"], float(z[name + "_thresh"])
+        extra = z[name + "_extra"] if name + "_extra" in z.files else None
+        tm = z["tm"] if with_tm else None
+        out = orc.render_rays_fmt(T, f, o, d, vd, fmt, B, extra=extra, tm=tm, min_comp=cmin, max_comp=cmax,
+                                  sigma_thresh=thr, stop_thresh=thr)
+        assert out.shape == (len(o), C + 1)
+        assert frac_within(out, z[name + "_ref_out"]) >= 0.999, name
+        assert float(np.abs(out - z[name + "_ref_out"]).mean()) <= 1e-5, name
+        grad = orc.render_rays_fmt_backward(T, f, o, d, vd, z[name + "_grad_out"], fmt, B, extra=extra, tm=tm,
+                                            min_comp=cmin, max_comp=cmax, stale_basis=True)
+        ref = z[name + "_ref_grad"]
+        assert np.linalg.norm(grad - ref) <= 1e-4 * np.linalg.norm(ref), name
+    for tag, thr in (("default", 0.0), ("fast", 1e-2)):
+        mf = orc.motion_feature_render(T, z["mf_features"], o, d, z["mf_jf"], z["mf_sw"], z["mf_ji"],
+                                       background_brightness=0.5, sigma_thresh=thr, stop_thresh=thr)
+        assert frac_within(mf, z["mf_ref_out_" + tag]) >= 0.999
+
+
+def test_format_and_motion_feature_backwards_match_finite_differences_fp64():
+    tr = synth.synth_tree(4, "ball")
+    M = tr["M"]
+    T = orc.Tree(tr["child"], tr["data"])
+    rng = np.random.default_rng(0)
+    o, d = synth.synth_rays(48)
+    vd = synth._unit(rng, 48)
+    tm = np.zeros((M, 4, 4))
+    for i in range(M):
+        tm[i, :3, :3] = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+    B, C = 4, 2
+    D = B * C + 1
+    f = synth.synth_features(M, D).astype(np.float64)
+    f[:, -1] = np.abs(f[:, -1]) + 0.2
+    sg = np.concatenate([rng.uniform(1, 4, (B, 1)), synth._unit(rng, B)], 1)
+    asg = rng.standard_normal((B, 11))
+    for fmt, extra in ((orc.FORMAT_SH, None), (orc.FORMAT_SG, sg), (orc.FORMAT_ASG, asg)):
+        kw = dict(extra=extra, tm=tm, min_comp=1, max_comp=3, background_brightness=0.3, dtype=np.float64)
+        g = rng.standard_normal((48, C + 1))
+        grad = orc.render_rays_fmt_backward(T, f, o, d, vd, g, fmt, B, **kw)
+        assert not grad.reshape(M, -1)[:, [0, B]].any()                       # component 0 is outside the window
+        for k in np.argsort(-np.abs(grad).ravel())[:5]:
+            i, j = divmod(int(k), D)
+            fp, fm = f.copy(), f.copy()
+            fp[i, j] += 1e-6
+            fm[i, j] -= 1e-6
+            fd = ((orc.render_rays_fmt(T, fp, o, d, vd, fmt, B, **kw) - orc.render_rays_fmt(T, fm, o, d, vd, fmt, B, **kw)) * g).sum() / 2e-6
+            assert abs(fd - grad[i, j]) <= 1e-6 + 1e-5 * abs(fd), (fmt, i, j)
+    J, F, Bn = 5, 7, 3
+    jf = rng.standard_normal((J, F))
+    sw = rng.dirichlet(np.ones(Bn), M)
+    sw[sw < 0.15] = 0.0
+    ji = rng.integers(0, J, (M, Bn))
+    f4 = synth.synth_features(M, 4).astype(np.float64)
+    f4[:, -1] = np.abs(f4[:, -1]) + 0.2
+    g = rng.standard_normal((48, F))
+    gj = orc.motion_feature_render_backward(T, f4, o, d, jf, sw, ji, g, dtype=np.float64)
+    for a, b in ((0, 0), (2, 3), (4, 6)):
+        jp, jm = jf.copy(), jf.copy()
+        jp[a, b] += 1e-6
+        jm[a, b] -= 1e-6
+        fd = ((orc.motion_feature_render(T, f4, o, d, jp, sw, ji, dtype=np.float64)
+               - orc.motion_feature_render(T, f4, o, d, jm, sw, ji, dtype=np.float64)) * g).sum() / 2e-6
+        assert abs(fd - gj[a, b]) <= 1e-6 + 1e-5 * abs(fd)
+
+
+def test_ndc_camera_rays():
+    """NDC conversion of pinhole rays (rt_kernel.cu:1168-1191): forward-facing camera at the origin looking down -z.
+    Every NDC origin lies on the near plane z_ndc = -1 and directions are unit length; ndc_width < 0 is a no-op."""
+    c2w = np.eye(4, dtype=np.float32)
+    W, H, fx = 16, 12, 20.0
+    o0, d0 = orc.camera_rays(c2w, fx, fx, W, H)
+    o1, d1, v1 = orc.camera_rays_ndc(c2w, fx, fx, W, H)
+    assert np.array_equal(o0, o1) and np.array_equal(d0, d1) and np.array_equal(d0, v1)
+    o2, d2, v2 = orc.camera_rays_ndc(c2w, fx, fx, W, H, ndc_width=W, ndc_height=H, ndc_focal=fx)
+    assert np.array_equal(v2, d0)
+    assert np.allclose(o2[:, 2], -1.0, atol=1e-6) and np.allclose(np.linalg.norm(d2, axis=1), 1.0, atol=1e-6)
+    # pixel (ix, iy) maps to NDC x = (ix - W/2) / (W/2), y = -(iy - H/2) / (H/2)
+    ix, iy = np.meshgrid(np.arange(W), np.arange(H))
+    assert np.allclose(o2[:, 0], ((ix - W / 2) / (W / 2)).ravel(), atol=1e-5)
+    assert np.allclose(o2[:, 1], (-(iy - H / 2) / (H / 2)).ravel(), atol=1e-5)
 
 
 def test_golden_fixtures_present():
