@@ -357,13 +357,14 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                     float4 sv[NB];
 #pragma unroll
                     for (int jj = 0; jj < NB; ++jj) {
+                        // Rows of rays without a hit (stand-in row 0) are reduced too: their totals are never read.
                         const int r = RPI * (b * NB + jj) + q;
-                        const bool on = ((hb >> r) & 1u) && lane_ok;
                         const float4 g4 = *reinterpret_cast<const float4*>(gs + r * DP + 4 * c4);
                         const float4 s = activated(x[jj], act);
                         const float sx = s.x * g4.x, sy = s.y * g4.y, sz = s.z * g4.z, sw = s.w * g4.w;
-                        cp[jj] = on ? (sx + sy) + (sz + (is_sig ? 0.0f : sw)) : 0.0f;
-                        sv[jj] = make_float4(sx * (1.0f - s.x), sy * (1.0f - s.y), sz * (1.0f - s.z), sw * (1.0f - s.w));
+                        cp[jj] = lane_ok ? (sx + sy) + (sz + (is_sig ? 0.0f : sw)) : 0.0f;
+                        sv[jj] = make_float4(fmaf(-sx, s.x, sx), fmaf(-sy, s.y, sy), fmaf(-sz, s.z, sz),
+                                             fmaf(-sw, s.w, sw));                        // s (1 - s) g
                     }
                     const float c_tot = quad_reduce<NB, LPR>(cp, lane);
                     const float c_own = __shfl_sync(FULL, c_tot, red_src);

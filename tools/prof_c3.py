@@ -39,6 +39,8 @@ o_t, d_t = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
 rs = sv.renderer._rays_spec_from_rays(sv.Rays(o_t, d_t, d_t))
 opt = sv.VolumeRenderer(tree)._get_options()
 ts = tree._spec(feats)
+if os.environ.get("ACT", "1") == "1":
+    ts._act = tree.activated(feats)          # what VolumeRenderer attaches for large batches
 g = torch.randn(Q, D, device=dev)
 for _ in range(iters):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
