@@ -18,7 +18,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO_PATH = os.path.join(_HERE, "libsvoxb.so")
+# SVOXB_LIBRARY: load another build of the same library (kernel experiments); the default is the in-tree one.
+_SO_PATH = os.environ.get("SVOXB_LIBRARY") or os.path.join(_HERE, "libsvoxb.so")
 
 FORMAT_RGBA, FORMAT_SH, FORMAT_SG, FORMAT_ASG = 0, 1, 2, 3
 
