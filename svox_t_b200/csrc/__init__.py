@@ -32,7 +32,7 @@ class _CTree(ctypes.Structure):
         ("offset", ctypes.c_void_p), ("scaling", ctypes.c_void_p), ("accel", ctypes.c_void_p),
         ("features_act", ctypes.c_void_p),
         ("extra_data", ctypes.c_void_p), ("extra_rows", ctypes.c_int32), ("extra_cols", ctypes.c_int32),
-        ("transformation_matrices", ctypes.c_void_p),
+        ("transformation_matrices", ctypes.c_void_p), ("accel_marks_current", ctypes.c_int32),
     ]
 
 
@@ -64,6 +64,7 @@ SYMBOLS = {
     "svoxb_accel_bytes": (_I64, [_VP]),
     "svoxb_accel_describe": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                             ctypes.POINTER(_I64)]),
+    "svoxb_accel_mark_hits": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP]),
     "svoxb_activate_features": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP]),
     "svoxb_query": (ctypes.c_int, [_PT, _VP, _I64, _VP, _VP, _VP, _VP, _VP]),
     "svoxb_leafset_scratch_bytes": (ctypes.c_size_t, [_I64]),
@@ -212,7 +213,8 @@ class TreeSpec:
             extra_data=_ptr(self.extra_data),
             extra_rows=self.extra_data.shape[0] if self.extra_data is not None and self.extra_data.numel() else 0,
             extra_cols=self.extra_data.shape[1] if self.extra_data is not None and self.extra_data.numel() else 0,
-            transformation_matrices=_ptr(self.transformation_matrices))
+            transformation_matrices=_ptr(self.transformation_matrices),
+            accel_marks_current=1 if acc is not None and acc.marks_match(self.features) else 0)
         return c
 
 
@@ -278,6 +280,20 @@ class Accel:
 
     def matches(self, ts):
         return self.handle and self._key == self._make_key(ts)
+
+    def mark_hits(self, features):
+        """Refresh the per-leaf "sigma <= 0" marks for this exact (storage, version) of ``features``; the march then
+        never fetches those rows. No-op when the marks are current."""
+        if self.marks_match(features):
+            return
+        _check_input(features, "features", torch.float32)
+        with torch.cuda.device(features.device):
+            _check(self._lib.svoxb_accel_mark_hits(self.handle, _ptr(features), features.shape[0], features.shape[1],
+                                                   _stream()))
+        self._marks_key = Activated._make_key(features)
+
+    def marks_match(self, features):
+        return getattr(self, "_marks_key", None) == Activated._make_key(features)
 
     @property
     def nbytes(self):

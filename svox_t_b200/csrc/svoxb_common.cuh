@@ -35,11 +35,14 @@ int sm_count();
 // ---- packed accelerator ------------------------------------------------------------------------------------------
 // One 32-bit word per cell:
 //   bit 31 set  : pointer -- low 31 bits = brick index in the next stage
-//   bit 31 clear: leaf    -- bits 27..30 = leaf depth d (cube_sz = 2^d), bits 0..26 = feature-row index,
-//                            ACC_EMPTY in the index field = empty leaf (reference: data idx >= M)
+//   bit 31 clear: leaf    -- bits 27..30 = leaf depth d (cube_sz = 2^d), bits 0..25 = feature-row index,
+//                            ACC_EMPTY in the index field = empty leaf (reference: data idx >= M);
+//                            bit 26 (ACC_MISS) = "this row's sigma was <= 0 when svoxb_accel_mark_hits last ran":
+//                            kernels told that the marks are current skip such rows without fetching them
 constexpr uint32_t ACC_PTR = 0x80000000u;
-constexpr uint32_t ACC_IDX_MASK = 0x07ffffffu;
-constexpr uint32_t ACC_EMPTY = 0x07ffffffu;
+constexpr uint32_t ACC_IDX_MASK = 0x03ffffffu;
+constexpr uint32_t ACC_EMPTY = 0x03ffffffu;
+constexpr uint32_t ACC_MISS = 0x04000000u;
 constexpr int ACC_DEPTH_SHIFT = 27;
 constexpr int ACC_MAX_DEPTH = 15;
 
@@ -75,6 +78,7 @@ struct TreeArgs {
     AccelView acc;
     int use_accel;
     const float* feat_act;   // optional pre-activated table (sigmoid applied to channels 0..D-2), or nullptr
+    uint32_t acc_miss_mask;  // ACC_MISS when the accelerator's hit marks are current for `features`, else 0
 };
 
 // ---- device math ----------------------------------------------------------------------------------------------

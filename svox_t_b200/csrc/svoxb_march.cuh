@@ -240,7 +240,8 @@ __device__ __forceinline__ void probe_end(const TreeArgs& tr, const Probe& pb, c
         }
         const int d = (int)(cell >> ACC_DEPTH_SHIFT) & 0xf;
         const uint32_t ci = cell & ACC_IDX_MASK;
-        idx = (ci == ACC_EMPTY) ? -1 : (int)ci;
+        // rows marked "sigma <= 0" are not candidates: no row fetch, exactly what the hit predicate would decide
+        idx = (ci == ACC_EMPTY || (cell & tr.acc_miss_mask)) ? -1 : (int)ci;
         const float sc = __int_as_float((127 + d) << 23);
         const float qx = pb.px * sc, qy = pb.py * sc, qz = pb.pz * sc;
         rx = qx - floorf(qx); ry = qy - floorf(qy); rz = qz - floorf(qz);

@@ -533,8 +533,10 @@ static int launch_bwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpt
         return SVOXB_EINVAL;                                                                           \
     } while (0)
 
-int launch_fwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, float* out,
+int launch_fwd_quad(const TreeArgs& tr_in, const RaySource& src, const MarchOpts& m, bool image, float* out,
                     float* depth, cudaStream_t st) {
+    TreeArgs tr = tr_in;
+    if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;     // the marks encode sigma > 0: too strict for this predicate
     SVOXB_REQUIRE(((uintptr_t)tr.features & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)tr.feat_act & 15) == 0,
                   "features/out must be 16-byte aligned");
     SVOXB_Q_DISPATCH(launch_fwd_q, tr, src, m, out, depth, st);

@@ -83,6 +83,8 @@ struct svoxb_accel {
     const int32_t* child;   // identity of the tensors it was built from (sanity check only)
     const int32_t* data;
     cudaStream_t stream;    // creation stream: the stream-ordered allocations are released on it
+    const float* marks_features;   // table the ACC_MISS bits were last computed from (svoxb_accel_mark_hits), or NULL
+    int marks_D;
 };
 
 namespace svoxb {
@@ -109,6 +111,7 @@ int make_tree_args(const svoxb_tree* t, TreeArgs& a) {
     a.child = t->child; a.data = t->data; a.offset = t->offset; a.scaling = t->scaling;
     a.use_accel = 0;
     a.feat_act = t->M > 0 ? t->features_act : nullptr;
+    a.acc_miss_mask = 0;
     memset(&a.acc, 0, sizeof(a.acc));
     if (t->accel) {
         SVOXB_REQUIRE(t->N == 2, "accelerator requires N == 2");
@@ -118,6 +121,11 @@ int make_tree_args(const svoxb_tree* t, TreeArgs& a) {
                       (long long)t->accel->M, (long long)t->M);
         a.acc = t->accel->view;
         a.use_accel = 1;
+        if (t->accel_marks_current) {
+            SVOXB_REQUIRE(t->accel->marks_features == t->features && t->accel->marks_D == t->D,
+                          "accel_marks_current is set but svoxb_accel_mark_hits was last run on a different table");
+            a.acc_miss_mask = ACC_MISS;
+        }
     }
     return 0;
 }
@@ -171,6 +179,21 @@ __global__ void accel_stage_kernel(const int32_t* __restrict__ child, const int3
             }
         }
         cells[gid] = cell;
+    }
+}
+
+// Hit marks: one thread per cell; leaf cells that hold a row get ACC_MISS iff !(sigma > 0) -- the negation of the
+// hit predicate of the march (rt_kernel.cu:279 with the default threshold, :382/:456 always), NaN included.
+__global__ void __launch_bounds__(256)
+accel_mark_kernel(uint32_t* __restrict__ cells, int64_t n, const float* __restrict__ features, int D) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t cell = cells[i];
+        if (cell & ACC_PTR) continue;
+        const uint32_t ci = cell & ACC_IDX_MASK;
+        if (ci == ACC_EMPTY) continue;
+        const float sigma = __ldg(features + (size_t)ci * D + (D - 1));
+        const uint32_t marked = (sigma > 0.0f) ? (cell & ~ACC_MISS) : (cell | ACC_MISS);
+        if (marked != cell) cells[i] = marked;
     }
 }
 
@@ -508,6 +531,23 @@ extern "C" int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* s
     if (roots[1]) cudaFreeAsync(roots[1], st);
     cudaFreeAsync(d_scalars, st);
     *out = a;
+    return 0;
+}
+
+extern "C" int svoxb_accel_mark_hits(svoxb_accel* a, const float* features, int64_t M, int32_t D, void* stream) {
+    SVOXB_REQUIRE(a != nullptr, "accel is NULL");
+    SVOXB_REQUIRE(M == a->M, "accelerator was built for M=%lld, got M=%lld", (long long)a->M, (long long)M);
+    SVOXB_REQUIRE(D >= 2 && (features != nullptr || M == 0), "bad feature table");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int s = 0; s < a->view.n_stages && M > 0; ++s) {
+        const int64_t words = a->n_bricks[s] << (3 * a->view.bits[s]);
+        if (words <= 0) continue;
+        const int grid = (int)min((words + 255) / 256, (int64_t)sm_count() * 16);
+        accel_mark_kernel<<<grid, 256, 0, st>>>(a->cells[s], words, features, D);
+        count_launch();
+        SVOXB_CUDA(cudaGetLastError());
+    }
+    a->marks_features = features; a->marks_D = D;
     return 0;
 }
 

@@ -144,6 +144,8 @@ class VolumeRenderer(nn.Module):
         if (self.data_format.format == DataFormat.RGBA and D % 4 == 0 and 4 <= D <= 128 and n_rays * 32 >= M
                 and features.is_cuda):
             ts._act = self.tree.activated(features.detach())
+            if ts._accel is not None:
+                ts._accel.mark_hits(features.detach())
         return ts
 
     def _require_cuda(self, cuda):

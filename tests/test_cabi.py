@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     assert [f[0] for f in C._COptions._fields_] == ["step_size", "background_brightness", "format", "basis_dim",
                                                     "ndc_width", "ndc_height", "ndc_focal", "min_comp", "max_comp",
                                                     "sigma_thresh", "stop_thresh"]
-    assert ctypes.sizeof(C._CTree) == 120 and ctypes.sizeof(C._CCamera) == 24
+    assert ctypes.sizeof(C._CTree) == 128 and ctypes.sizeof(C._CCamera) == 24
 
 
 def test_ctypes_structs_match_the_header_as_gcc_lays_it_out(tmp_path):

@@ -41,6 +41,8 @@ opt = sv.VolumeRenderer(tree)._get_options()
 ts = tree._spec(feats)
 if os.environ.get("ACT", "1") == "1":
     ts._act = tree.activated(feats)          # what VolumeRenderer attaches for large batches
+    if os.environ.get("MARKS", "1") == "1":
+        ts._accel.mark_hits(feats)
 g = torch.randn(Q, D, device=dev)
 for _ in range(iters):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
