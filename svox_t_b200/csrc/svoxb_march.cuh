@@ -7,7 +7,10 @@
 
 namespace svoxb {
 
-constexpr int BLOCK = 256;
+#ifndef SVOXB_BLOCK
+#define SVOXB_BLOCK 256
+#endif
+constexpr int BLOCK = SVOXB_BLOCK;
 constexpr int WARPS = BLOCK / 32;
 constexpr int CHUNK = 64;          // rays fetched from the global queue per atomic; one 8x8 pixel tile for images
 
@@ -257,16 +260,22 @@ __device__ __forceinline__ void probe_end(const TreeArgs& tr, const Probe& pb, c
     }
 }
 
-// Host-side launch helpers shared by the scalar-lane and quad-lane kernels.
+// Host-side launch helpers shared by the scalar-lane and quad-lane kernels. `carveout_kb` > 0: ask for exactly that
+// much shared memory per SM, so that everything else of the 228 KB stays L1 (see svoxb_render_q.cu).
 template <typename Kern>
-static int persistent_grid(Kern kern, size_t smem, int64_t queue_len, int& grid) {
+static int persistent_grid(Kern kern, size_t smem, int64_t queue_len, int& grid, int threads = BLOCK,
+                           int carveout_kb = 0) {
     if (smem > 48 * 1024)
         SVOXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (carveout_kb > 0)
+        SVOXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        min(100, (carveout_kb * 100 + 227) / 228)));
     int per_sm = 0;
-    SVOXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem));
+    SVOXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     SVOXB_REQUIRE(per_sm > 0, "kernel does not fit on an SM (smem %zu)", smem);
+    const int warps = threads / 32;
     const int64_t warps_needed = (queue_len + CHUNK - 1) / CHUNK;
-    const int64_t want = (warps_needed + WARPS - 1) / WARPS;
+    const int64_t want = (warps_needed + warps - 1) / warps;
     grid = (int)max((int64_t)1, min((int64_t)per_sm * sm_count(), want));
     return 0;
 }

@@ -2,9 +2,9 @@
 //
 // Same semantics as the scalar-lane kernels in svoxb_render.cu (reference: rt_kernel.cu:221-328 forward,
 // 330-496 backward, 781-834 depth); what changes is how a warp touches the feature table:
-//   * a feature row is covered by LPR = pow2ceil(D/4) lanes holding one float4 each, so ONE 128-bit load
-//     instruction fetches RPI = 32/LPR whole rows (4 rows = 512 B at D = 32), one 128-bit store writes RPI output
-//     rows and one red.global.add.v4.f32 scatters RPI gradient rows;
+//   * a feature row is covered by LPR lanes holding V4 float4 each (V4 = 2 when D % 8 == 0: Blackwell's 256-bit
+//     LDG, LPR = pow2ceil(D/8); else V4 = 1, LPR = pow2ceil(D/4)), so ONE load instruction fetches RPI = 32/LPR
+//     whole rows (8 rows = 1 KB at D = 32) and V4 red.global.add.v4.f32 per lane scatter RPI gradient rows;
 //   * the lanes' traversal never reads the feature table: every leaf that holds a row becomes a candidate, the rows
 //     of the candidates are requested as a batch and each owner lane picks its sample's sigma out of the loaded row
 //     with one shuffle (the reference's separate 4-byte sigma gather and second dependent round trip are gone);
@@ -14,9 +14,9 @@
 //     memory, which keeps the kernels at 80 registers (3 CTAs per SM at D <= 32);
 //   * the per-hit channel dot product of the backward is reduced with a transposing butterfly over the LPR lanes
 //     of a row (LPR-1 shuffles for LPR hits instead of log2(LPR) per hit).
-// Lane layout: lane = q * LPR + c4; q = which of the RPI rows of a load, c4 = channel quad (channels 4*c4..4*c4+3).
-// Ray r of the warp (owner lane r) is served as row q = r % RPI of group j = r / RPI; acc[j] is this lane's float4
-// of ray RPI*j + q.
+// Lane layout: lane = q * LPR + c; q = which of the RPI rows of a load, c = channel block (channels VEC*c ..
+// VEC*c+VEC-1, VEC = 4*V4). Ray r of the warp (owner lane r) is served as row q = r % RPI of group j = r / RPI.
+#include <stdlib.h>
 #include "svoxb_march.cuh"
 
 namespace svoxb {
@@ -53,10 +53,26 @@ __device__ __forceinline__ void red_add_v4_hint(float* p, float a, float b, floa
     asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(a), "f"(b), "f"(c),
                  "f"(d), "l"(pol) : "memory");
 }
+#ifndef SVOXB_ROWS_NO_L1
+#define SVOXB_ROWS_NO_L1 0
+#endif
+#if SVOXB_ROWS_NO_L1
+#define SVOXB_L1_HINT ".L1::no_allocate"
+#else
+#define SVOXB_L1_HINT ""
+#endif
 __device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t pol) {
     float4 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+    asm volatile("ld.global.nc" SVOXB_L1_HINT ".L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+// Row gather of the forward: the rows stream through (a row is not touched twice by the same SM within its L1
+// lifetime), so they are kept out of L1, which then holds the brick sectors consecutive samples of a ray re-read.
+__device__ __forceinline__ float4 ldg_row(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc" SVOXB_L1_HINT ".v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
 
@@ -98,13 +114,47 @@ __device__ __forceinline__ float quad_reduce(float (&v)[NB], int lane) {
 template <int BITS>
 __device__ __forceinline__ constexpr unsigned low_mask() { return BITS >= 32 ? 0xffffffffu : ((1u << (BITS & 31)) - 1u); }
 
-template <int LPR>
+template <int LPR, int V4>
 struct Quad {
+    static constexpr int VEC = 4 * V4;                   // channels per lane
     static constexpr int RPI = 32 / LPR;                 // rows per load instruction
-    static constexpr int NB = LPR < 8 ? LPR : 8;         // row groups in flight per batch (4*NB registers)
+    static constexpr int NB = (LPR * V4 <= 8) ? LPR : 8 / V4;   // row groups in flight per batch (4*V4*NB registers)
     static constexpr int NBATCH = LPR / NB;
     static constexpr int RAYS_PER_BATCH = RPI * NB;
+    static constexpr int DP = VEC * LPR;                 // padded row width
+    // ONE CTA per SM (a single copy of the top grid in shared memory); its size is what registers (80 per thread)
+    // and the per-warp rows in shared memory allow
+#ifndef SVOXB_THREADS32
+#define SVOXB_THREADS32 768
+#endif
+    static constexpr int THREADS = DP <= 32 ? SVOXB_THREADS32 : (DP <= 64 ? 512 : 256);
+    static constexpr int NWARPS = THREADS / 32;
 };
+
+// V4 float4 of one row block. 256-bit form: LDG.E.256 (sm_100+), which carries its L2 eviction priority inline.
+template <int V4>
+struct RowBlk {
+    float4 v[V4];
+};
+
+template <int V4, bool EVICT_FIRST>
+__device__ __forceinline__ RowBlk<V4> load_row_block(const char* p, uint64_t pol_first) {
+    RowBlk<V4> r;
+    if constexpr (V4 == 2) {
+        if constexpr (EVICT_FIRST)
+            asm volatile("ld.global.nc.L2::evict_first.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=f"(r.v[0].x), "=f"(r.v[0].y), "=f"(r.v[0].z), "=f"(r.v[0].w), "=f"(r.v[1].x), "=f"(r.v[1].y),
+                           "=f"(r.v[1].z), "=f"(r.v[1].w) : "l"(p));
+        else
+            asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=f"(r.v[0].x), "=f"(r.v[0].y), "=f"(r.v[0].z), "=f"(r.v[0].w), "=f"(r.v[1].x), "=f"(r.v[1].y),
+                           "=f"(r.v[1].z), "=f"(r.v[1].w) : "l"(p));
+    } else {
+        if constexpr (EVICT_FIRST) r.v[0] = ldg_hint(reinterpret_cast<const float4*>(p), pol_first);
+        else r.v[0] = ldg_row(reinterpret_cast<const float4*>(p));
+    }
+    return r;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // Loop structure (NBATCH = 1 for D <= 32, 2 for D <= 64, 4 for D <= 128; x holds the rows of ONE batch):
@@ -115,40 +165,36 @@ struct Quad {
 //   S2.b request rows of batch b, composite it            (b = 1 .. NBATCH-1; latency hides behind S3 / S2.b-1)
 //   S4   flush finished rays, refill; the rows of batch 0 of the new candidates are requested first thing in the
 //        next iteration (S0), ahead of S1
-#ifndef SVOXB_FWD_MINB
-#define SVOXB_FWD_MINB 3
-#endif
-#ifndef SVOXB_BWD_MINB
-#define SVOXB_BWD_MINB 3
-#endif
-template <int LPR, bool ACCEL, bool IMAGE, bool DEPTH>
-__global__ void __launch_bounds__(BLOCK, (LPR <= 8 ? SVOXB_FWD_MINB : (LPR == 16 ? 2 : 1)))
+template <int LPR, int V4, bool ACCEL, bool IMAGE, bool DEPTH>
+__global__ void __launch_bounds__((Quad<LPR, V4>::THREADS), 1)
 march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
                       unsigned long long* counter) {
-    using G = Quad<LPR>;
-    constexpr int RPI = G::RPI, NB = G::NB, NBATCH = G::NBATCH, RPB = G::RAYS_PER_BATCH;
+    using G = Quad<LPR, V4>;
+    constexpr int RPI = G::RPI, NB = G::NB, NBATCH = G::NBATCH, RPB = G::RAYS_PER_BATCH, VEC = G::VEC;
     extern __shared__ uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31;
-    // this warp's 32 x D partial outputs: accs[j * 32] = this lane's float4 of ray RPI*j + q
-    float4* accs = reinterpret_cast<float4*>(smem_u32 + top_words) + (size_t)(threadIdx.x >> 5) * 32 * LPR + lane;
-    const int q = lane / LPR, c4 = lane % LPR;
-    const int D = tr.D, D4 = D >> 2;
-    const bool lane_ok = c4 < D4, is_sig = c4 == D4 - 1;
-    const int sig_src = (lane % RPI) * LPR + (D4 - 1);   // lane that holds sigma of this owner lane's row
+    // this warp's 32 x DP partial outputs: accs[(j * V4 + h) * 32] = float4 h of this lane's block of ray RPI*j + q
+    float4* accs = reinterpret_cast<float4*>(smem_u32 + top_words) + (size_t)(threadIdx.x >> 5) * 32 * LPR * V4 + lane;
+    const int q = lane / LPR, c = lane % LPR;
+    const int D = tr.D, DV = D / VEC;
+    const bool lane_ok = c < DV, is_sig = c == DV - 1;
+    const int sig_src = (lane % RPI) * LPR + (DV - 1);   // lane that holds sigma of this owner lane's row
     const bool act = tr.feat_act != nullptr;
-    const char* fbase = reinterpret_cast<const char*>(act ? tr.feat_act : tr.features) + 16 * min(c4, D4 - 1);
+    const char* fbase = reinterpret_cast<const char*>(act ? tr.feat_act : tr.features) + 4 * VEC * min(c, DV - 1);
     const unsigned row_bytes = (unsigned)D * 4u;
     const float* off = tr.offset;
     const float* scl = tr.scaling;
 
-    float4 x[NB];
+    RowBlk<V4> x[NB];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < NB; ++j)
 #pragma unroll
-    for (int j = 0; j < LPR; ++j) accs[j * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int h = 0; h < V4; ++h) x[j].v[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < LPR * V4; ++j) accs[j * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     Ray ray;
     float T = 1.0f, p_dt = 0.0f, p_t = 0.0f;
@@ -174,7 +220,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
 #pragma unroll
         for (int jj = 0; jj < NB; ++jj) {
             const int idx = max(__shfl_sync(FULL, p_idx, RPI * jj + q), 0);
-            x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
+            x[jj] = load_row_block<V4, false>(fbase + (size_t)(unsigned)idx * row_bytes, 0);
         }
 
         // ---- S1 -------------------------------------------------------------------------------------------------
@@ -195,7 +241,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
 #pragma unroll
                 for (int jj = 0; jj < NB; ++jj) {
                     const int idx = max(__shfl_sync(FULL, p_idx, RPI * (b * NB + jj) + q), 0);
-                    x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
+                    x[jj] = load_row_block<V4, false>(fbase + (size_t)(unsigned)idx * row_bytes, 0);
                 }
             }
             // ---- S2.b: composite ---------------------------------------------------------------------------------
@@ -204,7 +250,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                 float sig = 0.0f;
 #pragma unroll
                 for (int jj = 0; jj < NB; ++jj) {
-                    const float v = __shfl_sync(FULL, x[jj].w, sig_src);
+                    const float v = __shfl_sync(FULL, x[jj].v[V4 - 1].w, sig_src);
                     if (lane / RPI == b * NB + jj) sig = v;
                 }
                 float w = 0.0f;
@@ -220,13 +266,16 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                     const int j = b * NB + jj;
                     const float w_j = __shfl_sync(FULL, w, RPI * j + q);
                     if (w_j != 0.0f) {
-                        const float4 s = activated(x[jj], act);
-                        float4 a = accs[j * 32];
-                        a.x = fmaf(w_j, s.x, a.x);
-                        a.y = fmaf(w_j, s.y, a.y);
-                        a.z = fmaf(w_j, s.z, a.z);
-                        a.w = fmaf(w_j, s.w, a.w);
-                        accs[j * 32] = a;
+#pragma unroll
+                        for (int h = 0; h < V4; ++h) {
+                            const float4 s = activated(x[jj].v[h], act);
+                            float4 a = accs[(j * V4 + h) * 32];
+                            a.x = fmaf(w_j, s.x, a.x);
+                            a.y = fmaf(w_j, s.y, a.y);
+                            a.z = fmaf(w_j, s.z, a.z);
+                            a.w = fmaf(w_j, s.w, a.w);
+                            accs[(j * V4 + h) * 32] = a;
+                        }
                     }
                 }
             }
@@ -253,21 +302,21 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                     const int fin_r = __shfl_sync(FULL, fin, r);
                     const int row_r = __shfl_sync(FULL, row, r);
                     if (fin_r != 0) {
-                        float4 v = accs[j * 32];
-                        if (fin_r == 2) {
-                            const float scale = (float)(1.0 / (1.0 - (double)T_r));   // rt_kernel.cu:315
-                            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
-                        } else {
-                            const float add = T_r * opt.bg;                           // rt_kernel.cu:323-325
-                            v.x += add; v.y += add; v.z += add; v.w += add;
+#pragma unroll
+                        for (int h = 0; h < V4; ++h) {
+                            float4 v = accs[(j * V4 + h) * 32];
+                            if (fin_r == 2) {
+                                const float scale = (float)(1.0 / (1.0 - (double)T_r));   // rt_kernel.cu:315
+                                v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+                            } else {
+                                const float add = T_r * opt.bg;                           // rt_kernel.cu:323-325
+                                v.x += add; v.y += add; v.z += add; v.w += add;
+                            }
+                            if (is_sig && h == V4 - 1) v.w = 1.0f - T_r;                  // rt_kernel.cu:317,326
+                            // written once, never re-read by this kernel: streaming store
+                            if (lane_ok) __stcs(reinterpret_cast<float4*>(out + (int64_t)row_r * D + VEC * c + 4 * h), v);
+                            accs[(j * V4 + h) * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
-                        if (is_sig) v.w = 1.0f - T_r;                                 // rt_kernel.cu:317,326
-#ifdef SVOXB_STREAM_IO
-                        if (lane_ok) __stcs(reinterpret_cast<float4*>(out + (int64_t)row_r * D + 4 * c4), v);
-#else
-                        if (lane_ok) *reinterpret_cast<float4*>(out + (int64_t)row_r * D + 4 * c4) = v;
-#endif
-                        accs[j * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
             }
@@ -277,33 +326,38 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     }
 }
 
-template <int LPR, bool ACCEL, bool IMAGE>
-__global__ void __launch_bounds__(BLOCK, (LPR <= 8 ? SVOXB_BWD_MINB : (LPR == 16 ? 2 : 1)))
+template <int LPR, int V4, bool ACCEL, bool IMAGE>
+__global__ void __launch_bounds__((Quad<LPR, V4>::THREADS), 1)
 march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restrict__ grad_out,
                       const float* __restrict__ saved_out, float* __restrict__ grad, unsigned long long* counter) {
-    using G = Quad<LPR>;
-    constexpr int RPI = G::RPI, NB = G::NB, NBATCH = G::NBATCH, RPB = G::RAYS_PER_BATCH, DP = 4 * LPR;
+    using G = Quad<LPR, V4>;
+    constexpr int RPI = G::RPI, NB = G::NB, NBATCH = G::NBATCH, RPB = G::RAYS_PER_BATCH, VEC = G::VEC, DP = G::DP;
     extern __shared__ uint32_t smem_u32[];
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     uint32_t* top = smem_u32;
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* gs = reinterpret_cast<float*>(smem_u32 + top_words) + (size_t)warp * 32 * DP;   // [32 rays][DP]
-    const int q = lane / LPR, c4 = lane % LPR;
-    const int D = tr.D, D4 = D >> 2;
-    const bool lane_ok = c4 < D4, is_sig = c4 == D4 - 1;
-    const int sig_src = (lane % RPI) * LPR + (D4 - 1);
+    // staged grad_out rows [32 rays][DP]; with 256-bit blocks the two float4 of a block swap places in the rows read
+    // by lanes 4..7 of every quarter-warp, which keeps the 128-bit shared loads conflict-free
+    float* gs = reinterpret_cast<float*>(smem_u32 + top_words) + (size_t)warp * 32 * DP;
+    const int q = lane / LPR, c = lane % LPR;
+    const int D = tr.D, DV = D / VEC;
+    const bool lane_ok = c < DV, is_sig = c == DV - 1;
+    const int sig_src = (lane % RPI) * LPR + (DV - 1);
     const int red_src = (lane % RPI) * LPR + ((lane / RPI) % NB);     // lane holding this owner's reduced dot product
+    const int swz = V4 == 2 ? (lane >> 2) & 1 : 0;
     const bool act = tr.feat_act != nullptr;
-    const char* fbase = reinterpret_cast<const char*>(act ? tr.feat_act : tr.features) + 16 * min(c4, D4 - 1);
-    char* gbase = reinterpret_cast<char*>(grad) + 16 * c4;
+    const char* fbase = reinterpret_cast<const char*>(act ? tr.feat_act : tr.features) + 4 * VEC * min(c, DV - 1);
+    char* gbase = reinterpret_cast<char*>(grad) + 4 * VEC * c;
     const unsigned row_bytes = (unsigned)D * 4u;
     const float* off = tr.offset;
     const float* scl = tr.scaling;
 
-    float4 x[NB];
+    RowBlk<V4> x[NB];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < NB; ++j)
+#pragma unroll
+        for (int h = 0; h < V4; ++h) x[j].v[h] = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint64_t pol_last = policy_evict_last(), pol_first = policy_evict_first();
     Ray ray;
     float T = 1.0f, accum = 0.0f, T_end = 0.0f, gop = 0.0f, p_dt = 0.0f;
@@ -324,17 +378,14 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                 const float* g = grad_out + (int64_t)row_r * D;
                 const float* so = saved_out + (int64_t)row_r * D;
                 float part = 0.0f, g_last = 0.0f, o_last = 0.0f;
-                for (int c = lane; c < DP; c += 32) {
-#ifdef SVOXB_STREAM_IO
-                    const float gv = (c < D) ? __ldcs(g + c) : 0.0f;      // read once: do not let them displace the tables
-                    const float ov = (c < D) ? __ldcs(so + c) : 0.0f;
-#else
-                    const float gv = (c < D) ? __ldg(g + c) : 0.0f;
-                    const float ov = (c < D) ? __ldg(so + c) : 0.0f;
-#endif
-                    gs[r * DP + c] = gv;
-                    if (c < D - 1) part = fmaf(gv, ov, part);
-                    if (c == D - 1) { g_last = gv; o_last = ov; }
+                for (int e = lane; e < DP; e += 32) {
+                    const float gv = (e < D) ? __ldcs(g + e) : 0.0f;      // read once: do not let them displace the tables
+                    const float ov = (e < D) ? __ldcs(so + e) : 0.0f;
+                    int slot = e >> 2;                                   // float4 slot inside the row
+                    if (V4 == 2) slot ^= ((((r % RPI) * LPR + (e / VEC)) >> 2) & 1);   // reader lane = q*LPR + c
+                    gs[r * DP + 4 * slot + (e & 3)] = gv;
+                    if (e < D - 1) part = fmaf(gv, ov, part);
+                    if (e == D - 1) { g_last = gv; o_last = ov; }
                 }
 #pragma unroll
                 for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(FULL, part, s);
@@ -350,11 +401,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
 #pragma unroll
         for (int jj = 0; jj < NB; ++jj) {
             const int idx = max(__shfl_sync(FULL, p_idx, RPI * jj + q), 0);
-#if SVOXB_BWD_HINTS
-            x[jj] = ldg_hint(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes), pol_first);
-#else
-            x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
-#endif
+            x[jj] = load_row_block<V4, SVOXB_BWD_HINTS != 0>(fbase + (size_t)(unsigned)idx * row_bytes, pol_first);
         }
 
         // ---- S1 -------------------------------------------------------------------------------------------------
@@ -374,11 +421,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
 #pragma unroll
                 for (int jj = 0; jj < NB; ++jj) {
                     const int idx = max(__shfl_sync(FULL, p_idx, RPI * (b * NB + jj) + q), 0);
-#if SVOXB_BWD_HINTS
-                    x[jj] = ldg_hint(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes), pol_first);
-#else
-                    x[jj] = __ldg(reinterpret_cast<const float4*>(fbase + (size_t)(unsigned)idx * row_bytes));
-#endif
+                    x[jj] = load_row_block<V4, SVOXB_BWD_HINTS != 0>(fbase + (size_t)(unsigned)idx * row_bytes, pol_first);
                 }
             }
             // ---- S2.b: gradient of batch b of the pending candidates ------------------------------------------------
@@ -387,7 +430,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                 float sig = 0.0f;
 #pragma unroll
                 for (int jj = 0; jj < NB; ++jj) {
-                    const float v = __shfl_sync(FULL, x[jj].w, sig_src);
+                    const float v = __shfl_sync(FULL, x[jj].v[V4 - 1].w, sig_src);
                     if (lane / RPI == b * NB + jj) sig = v;
                 }
                 float w = 0.0f, dd = 0.0f;
@@ -401,17 +444,22 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                 const unsigned hb = __ballot_sync(FULL, hit);
                 if (hb) {
                     float cp[NB];
-                    float4 sv[NB];
+                    RowBlk<V4> sv[NB];
 #pragma unroll
                     for (int jj = 0; jj < NB; ++jj) {
                         // Rows of rays without a hit (stand-in row 0) are reduced too: their totals are never read.
                         const int r = RPI * (b * NB + jj) + q;
-                        const float4 g4 = *reinterpret_cast<const float4*>(gs + r * DP + 4 * c4);
-                        const float4 s = activated(x[jj], act);
-                        const float sx = s.x * g4.x, sy = s.y * g4.y, sz = s.z * g4.z, sw = s.w * g4.w;
-                        cp[jj] = lane_ok ? (sx + sy) + (sz + (is_sig ? 0.0f : sw)) : 0.0f;
-                        sv[jj] = make_float4(fmaf(-sx, s.x, sx), fmaf(-sy, s.y, sy), fmaf(-sz, s.z, sz),
-                                             fmaf(-sw, s.w, sw));                        // s (1 - s) g
+                        float tot = 0.0f;
+#pragma unroll
+                        for (int h = 0; h < V4; ++h) {
+                            const float4 g4 = *reinterpret_cast<const float4*>(gs + r * DP + 4 * ((c * V4 + h) ^ swz));
+                            const float4 s = activated(x[jj].v[h], act);
+                            const float sx = s.x * g4.x, sy = s.y * g4.y, sz = s.z * g4.z, sw = s.w * g4.w;
+                            tot += (sx + sy) + (sz + ((is_sig && h == V4 - 1) ? 0.0f : sw));
+                            sv[jj].v[h] = make_float4(fmaf(-sx, s.x, sx), fmaf(-sy, s.y, sy), fmaf(-sz, s.z, sz),
+                                                      fmaf(-sw, s.w, sw));               // s (1 - s) g
+                        }
+                        cp[jj] = lane_ok ? tot : 0.0f;
                     }
                     const float c_tot = quad_reduce<NB, LPR>(cp, lane);
                     const float c_own = __shfl_sync(FULL, c_tot, red_src);
@@ -428,13 +476,16 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                         const int idx_j = __shfl_sync(FULL, p_idx, r);
                         if (((hb >> r) & 1u) && lane_ok) {
                             float* grow = reinterpret_cast<float*>(gbase + (size_t)(unsigned)idx_j * row_bytes);
+#pragma unroll
+                            for (int h = 0; h < V4; ++h) {
+                                const float4 t = sv[jj].v[h];
+                                const float last = (is_sig && h == V4 - 1) ? sg_j : w_j * t.w;
 #if SVOXB_BWD_HINTS
-                            red_add_v4_hint(grow, w_j * sv[jj].x, w_j * sv[jj].y, w_j * sv[jj].z,
-                                            is_sig ? sg_j : w_j * sv[jj].w, pol_last);
+                                red_add_v4_hint(grow + 4 * h, w_j * t.x, w_j * t.y, w_j * t.z, last, pol_last);
 #else
-                            red_add_v4(grow, w_j * sv[jj].x, w_j * sv[jj].y, w_j * sv[jj].z,
-                                       is_sig ? sg_j : w_j * sv[jj].w);
+                                red_add_v4(grow + 4 * h, w_j * t.x, w_j * t.y, w_j * t.z, last);
 #endif
+                            }
                         }
                     }
                 }
@@ -460,78 +511,93 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
 // ---- host side ---------------------------------------------------------------------------------------------------
 bool quad_supported(int D) { return D % 4 == 0 && D >= 4 && D <= 128; }
 
-static int lpr_for(int D) {
+// Shared memory this one-CTA-per-SM kernel needs (+1 KB the runtime reserves per CTA), in KB; the rest of the SM's
+// 228 KB stays L1, which is what bounds the number of row gathers in flight (measured: forcing the carve-out to the
+// maximum slows the forward from 3.0 to 5.2 ms).
+static int carveout_kb(size_t smem) {
+    int kb = (int)((smem + 1024 + 1023) / 1024);
+    if (const char* e = getenv("SVOXB_CARVEOUT_KB")) kb = atoi(e);
+    return kb;
+}
+
+static int pow2ceil(int n) {
     int l = 1;
-    while (l * 4 < D) l <<= 1;
+    while (l < n) l <<= 1;
     return l;
 }
 
-template <int LPR, bool ACCEL, bool IMAGE>
+template <int LPR, int V4, bool ACCEL, bool IMAGE>
 static int launch_fwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
-    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * WARPS * 32 * LPR;
+    using G = Quad<LPR, V4>;
+    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * G::NWARPS * 32 * LPR * V4;
     void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
-    if (depth) kern = march_fwd_quad_kernel<LPR, ACCEL, IMAGE, true>;
-    else kern = march_fwd_quad_kernel<LPR, ACCEL, IMAGE, false>;
+    if (depth) kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, true>;
+    else kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, false>;
     int grid = 0;
-    int rc = persistent_grid(kern, smem, src.total, grid);
+    int rc = persistent_grid(kern, smem, src.total, grid, G::THREADS, carveout_kb(smem));
     if (rc) return rc;
     unsigned long long* counter = work_counter(st);
     if (!counter) return SVOXB_ECUDA;
-    kern<<<grid, BLOCK, smem, st>>>(tr, src, m, out, depth, counter);
+    kern<<<grid, G::THREADS, smem, st>>>(tr, src, m, out, depth, counter);
     count_launch();
     return check_cuda(cudaGetLastError(), "march_fwd_quad_kernel launch");
 }
 
-template <int LPR, bool ACCEL, bool IMAGE>
+template <int LPR, int V4, bool ACCEL, bool IMAGE>
 static int launch_bwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const float* go, const float* so,
                         float* grad, cudaStream_t st) {
-    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * WARPS * 32 * 4 * LPR;
-    auto kern = march_bwd_quad_kernel<LPR, ACCEL, IMAGE>;
+    using G = Quad<LPR, V4>;
+    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * G::NWARPS * 32 * G::DP;
+    auto kern = march_bwd_quad_kernel<LPR, V4, ACCEL, IMAGE>;
     int grid = 0;
-    int rc = persistent_grid(kern, smem, src.total, grid);
+    int rc = persistent_grid(kern, smem, src.total, grid, G::THREADS, carveout_kb(smem));
     if (rc) return rc;
     unsigned long long* counter = work_counter(st);
     if (!counter) return SVOXB_ECUDA;
-    kern<<<grid, BLOCK, smem, st>>>(tr, src, m, go, so, grad, counter);
+    kern<<<grid, G::THREADS, smem, st>>>(tr, src, m, go, so, grad, counter);
     count_launch();
     return check_cuda(cudaGetLastError(), "march_bwd_quad_kernel launch");
 }
 
-#define SVOXB_Q_DISPATCH(FN, ...)                                                                      \
+#define SVOXB_Q_CASES(FN, L, V, ...)                                                                   \
+    case ((L) * 2 + (V)-1) * 4 + 0: return FN<L, V, false, false>(__VA_ARGS__);                        \
+    case ((L) * 2 + (V)-1) * 4 + 1: return FN<L, V, false, true>(__VA_ARGS__);                         \
+    case ((L) * 2 + (V)-1) * 4 + 2: return FN<L, V, true, false>(__VA_ARGS__);                         \
+    case ((L) * 2 + (V)-1) * 4 + 3: return FN<L, V, true, true>(__VA_ARGS__);
+
+// Measured on B200 (C3): 256-bit row blocks execute 9 % (forward) / 18 % (backward) fewer instructions but run SLOWER
+// (fwd 2.98 -> 3.18 ms, bwd 6.14 -> 7.43 ms): the march is latency-bound, and eight small independent row groups per
+// iteration overlap better than four large ones (short- and long-scoreboard stalls per issue roughly double).
+#ifndef SVOXB_WIDE_ROWS
+#define SVOXB_WIDE_ROWS 0
+#endif
+
+#if SVOXB_WIDE_ROWS
+#define SVOXB_Q_WIDE_CASES(FN, ...)                                                                    \
+    SVOXB_Q_CASES(FN, 1, 2, __VA_ARGS__) SVOXB_Q_CASES(FN, 2, 2, __VA_ARGS__)                          \
+    SVOXB_Q_CASES(FN, 4, 2, __VA_ARGS__) SVOXB_Q_CASES(FN, 8, 2, __VA_ARGS__) SVOXB_Q_CASES(FN, 16, 2, __VA_ARGS__)
+#else
+#define SVOXB_Q_WIDE_CASES(FN, ...)
+#endif
+
+// 256-bit row blocks when enabled and the rows allow it (D % 8 == 0, 32-byte aligned tables), else 128-bit blocks.
+#define SVOXB_Q_DISPATCH(FN, wide, ...)                                                                \
     do {                                                                                               \
-        const int lpr = lpr_for(tr.D);                                                                 \
+        const int v4 = (wide) ? 2 : 1;                                                                 \
+        const int lpr = pow2ceil(tr.D / (4 * v4));                                                     \
         const int sel = (tr.use_accel ? 2 : 0) | (image ? 1 : 0);                                      \
-        switch (lpr * 4 + sel) {                                                                       \
-            case 1 * 4 + 0: return FN<1, false, false>(__VA_ARGS__);                                   \
-            case 1 * 4 + 1: return FN<1, false, true>(__VA_ARGS__);                                    \
-            case 1 * 4 + 2: return FN<1, true, false>(__VA_ARGS__);                                    \
-            case 1 * 4 + 3: return FN<1, true, true>(__VA_ARGS__);                                     \
-            case 2 * 4 + 0: return FN<2, false, false>(__VA_ARGS__);                                   \
-            case 2 * 4 + 1: return FN<2, false, true>(__VA_ARGS__);                                    \
-            case 2 * 4 + 2: return FN<2, true, false>(__VA_ARGS__);                                    \
-            case 2 * 4 + 3: return FN<2, true, true>(__VA_ARGS__);                                     \
-            case 4 * 4 + 0: return FN<4, false, false>(__VA_ARGS__);                                   \
-            case 4 * 4 + 1: return FN<4, false, true>(__VA_ARGS__);                                    \
-            case 4 * 4 + 2: return FN<4, true, false>(__VA_ARGS__);                                    \
-            case 4 * 4 + 3: return FN<4, true, true>(__VA_ARGS__);                                     \
-            case 8 * 4 + 0: return FN<8, false, false>(__VA_ARGS__);                                   \
-            case 8 * 4 + 1: return FN<8, false, true>(__VA_ARGS__);                                    \
-            case 8 * 4 + 2: return FN<8, true, false>(__VA_ARGS__);                                    \
-            case 8 * 4 + 3: return FN<8, true, true>(__VA_ARGS__);                                     \
-            case 16 * 4 + 0: return FN<16, false, false>(__VA_ARGS__);                                 \
-            case 16 * 4 + 1: return FN<16, false, true>(__VA_ARGS__);                                  \
-            case 16 * 4 + 2: return FN<16, true, false>(__VA_ARGS__);                                  \
-            case 16 * 4 + 3: return FN<16, true, true>(__VA_ARGS__);                                   \
-            case 32 * 4 + 0: return FN<32, false, false>(__VA_ARGS__);                                 \
-            case 32 * 4 + 1: return FN<32, false, true>(__VA_ARGS__);                                  \
-            case 32 * 4 + 2: return FN<32, true, false>(__VA_ARGS__);                                  \
-            case 32 * 4 + 3: return FN<32, true, true>(__VA_ARGS__);                                   \
+        switch ((lpr * 2 + v4 - 1) * 4 + sel) {                                                        \
+            SVOXB_Q_CASES(FN, 1, 1, __VA_ARGS__) SVOXB_Q_CASES(FN, 2, 1, __VA_ARGS__)                  \
+            SVOXB_Q_CASES(FN, 4, 1, __VA_ARGS__) SVOXB_Q_CASES(FN, 8, 1, __VA_ARGS__)                  \
+            SVOXB_Q_CASES(FN, 16, 1, __VA_ARGS__) SVOXB_Q_CASES(FN, 32, 1, __VA_ARGS__)                \
+            SVOXB_Q_WIDE_CASES(FN, __VA_ARGS__)                                                        \
             default: break;                                                                            \
         }                                                                                              \
         set_error("quad kernels: unsupported feature width D=%d", tr.D);                              \
         return SVOXB_EINVAL;                                                                           \
     } while (0)
+
 
 int launch_fwd_quad(const TreeArgs& tr_in, const RaySource& src, const MarchOpts& m, bool image, float* out,
                     float* depth, cudaStream_t st) {
@@ -539,14 +605,16 @@ int launch_fwd_quad(const TreeArgs& tr_in, const RaySource& src, const MarchOpts
     if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;     // the marks encode sigma > 0: too strict for this predicate
     SVOXB_REQUIRE(((uintptr_t)tr.features & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)tr.feat_act & 15) == 0,
                   "features/out must be 16-byte aligned");
-    SVOXB_Q_DISPATCH(launch_fwd_q, tr, src, m, out, depth, st);
+    const bool wide = SVOXB_WIDE_ROWS && tr.D % 8 == 0 && (((uintptr_t)tr.features | (uintptr_t)tr.feat_act) & 31) == 0;
+    SVOXB_Q_DISPATCH(launch_fwd_q, wide, tr, src, m, out, depth, st);
 }
 
 int launch_bwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, const float* grad_out,
                     const float* saved_out, float* grad, cudaStream_t st) {
     SVOXB_REQUIRE(((uintptr_t)tr.features & 15) == 0 && ((uintptr_t)grad & 15) == 0 && ((uintptr_t)tr.feat_act & 15) == 0,
                   "features/grad_features must be 16-byte aligned");
-    SVOXB_Q_DISPATCH(launch_bwd_q, tr, src, m, grad_out, saved_out, grad, st);
+    const bool wide = SVOXB_WIDE_ROWS && tr.D % 8 == 0 && (((uintptr_t)tr.features | (uintptr_t)tr.feat_act) & 31) == 0;
+    SVOXB_Q_DISPATCH(launch_bwd_q, wide, tr, src, m, grad_out, saved_out, grad, st);
 }
 
 }  // namespace svoxb
