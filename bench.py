@@ -199,13 +199,19 @@ def main():
     def step(rec=None):
         e = [ev() for _ in range(4)] if rec is not None else None
         if e: e[0].record()
-        ts._act = C.Activated(feats)          # features change every training step: the activation pass is part of it
+        # features change every training step: the per-row activation pass and the refresh of the accelerator's
+        # hit marks (both derived from the features) are part of the step
+        ts._act = C.Activated(feats)
+        if accel is not None:
+            accel._marks_key = None
+            accel.mark_hits(feats)
         out = C.volume_render(ts, rs, opt)
         if e: e[1].record()
         grad = torch.zeros_like(feats)
         if e: e[2].record()
         C._check(C.load_library().svoxb_render_rays_bwd(
-            C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), Q, C.ctypes.byref(opt._c(sigma_thresh=0.0, stop_thresh=-1.0)),
+            C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), C._ptr(d_t), Q,
+            C.ctypes.byref(opt._c(sigma_thresh=0.0, stop_thresh=-1.0)),
             C._ptr(g_t), C._ptr(out), C._ptr(grad), C._stream()))
         if e: e[3].record()
         svd.all_reduce_leaf_grads(grad)
@@ -243,21 +249,28 @@ def main():
     # Data-loader style pipeline: two device buffer sets; while step k renders out of one, a copy stream uploads the
     # inputs of step k+1 into the other. Every step's host->device copy and loss read-back happen inside the timed
     # region (K uploads + K renders + K read-backs for K steps; the first upload is exposed, the rest overlap).
+    # Per-step host inputs: ray origins + directions (what VolumeRenderer.forward takes) and the supervision a
+    # training step consumes -- an RGB target and an opacity target per ray, as in image-supervised training, where
+    # the 31 rendered feature channels pass through a fixed decoder (mean of three channel groups) before the loss.
     h_o, h_d = torch.from_numpy(o).pin_memory(), torch.from_numpy(d).pin_memory()
-    h_tgt = torch.rand(Q, D, generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
+    gen = torch.Generator().manual_seed(7 + rank)
+    h_rgb = torch.rand(Q, 3, generator=gen).pin_memory()
+    h_alpha = torch.rand(Q, generator=gen).pin_memory()
     fparam = feats.clone().requires_grad_(True)
-    bufs = [(torch.empty(Q, 3, device=dev), torch.empty(Q, 3, device=dev), torch.empty(Q, D, device=dev))
-            for _ in range(2)]
+    bufs = [(torch.empty(Q, 3, device=dev), torch.empty(Q, 3, device=dev), torch.empty(Q, 3, device=dev),
+             torch.empty(Q, device=dev)) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
     free_ev = [None, None]
+    G3 = (D - 1) // 3                                  # channels per decoded colour
 
     def upload(k):
-        bo, bd, bt = bufs[k & 1]
+        bo, bd, brgb, ba = bufs[k & 1]
         with torch.cuda.stream(copy_stream):
             if free_ev[k & 1] is not None:
                 copy_stream.wait_event(free_ev[k & 1])          # the step that last used this buffer set is done
-            bo.copy_(h_o, non_blocking=True); bd.copy_(h_d, non_blocking=True); bt.copy_(h_tgt, non_blocking=True)
+            bo.copy_(h_o, non_blocking=True); bd.copy_(h_d, non_blocking=True)
+            brgb.copy_(h_rgb, non_blocking=True); ba.copy_(h_alpha, non_blocking=True)
             e = torch.cuda.Event(); e.record(copy_stream)
         return e
 
@@ -267,12 +280,13 @@ def main():
         for k in range(n_steps):
             nxt = upload(k + 1) if k + 1 < n_steps else None
             main_stream.wait_event(ready)
-            bo, bd, bt = bufs[k & 1]
+            bo, bd, brgb, ba = bufs[k & 1]
             fparam.grad = None
             with torch.no_grad():
                 fparam.add_(0.0)                       # stands in for the optimiser update: features change every step
             out = renderer(fparam, sv.Rays(bo, bd, bd))
-            loss = 0.5 * ((out - bt) ** 2).mean()
+            rgb = out[:, :3 * G3].reshape(Q, 3, G3).mean(-1)
+            loss = 0.5 * ((rgb - brgb) ** 2).mean() + 0.5 * ((out[:, -1] - ba) ** 2).mean()
             loss.backward()
             svd.all_reduce_leaf_grads(fparam.grad)
             free_ev[k & 1] = torch.cuda.Event(); free_ev[k & 1].record(main_stream)
@@ -289,9 +303,12 @@ def main():
     torch.cuda.synchronize(); svd.barrier()
     e2e_ms = svd.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
     e2e = {"value": world * Q / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(h_o.numel() + h_d.numel() + h_tgt.numel()) * 4, "d2h_bytes_per_step": 4,
-           "api": "VolumeRenderer.forward + autograd backward, loss = 0.5*mean((out-target)^2); inputs come from pinned "
-                  "host memory every step, the upload of step k+1 overlaps the render of step k (double buffering)"}
+           "h2d_bytes_per_step": int(h_o.numel() + h_d.numel() + h_rgb.numel() + h_alpha.numel()) * 4,
+           "d2h_bytes_per_step": 4,
+           "api": "VolumeRenderer.forward + autograd backward; loss = MSE(decoded RGB, rgb target) + MSE(opacity, alpha "
+                  "target), RGB = mean of three groups of the rendered feature channels. Every step uploads its ray "
+                  "origins, directions, RGB and opacity targets from pinned host memory and reads the loss back; the "
+                  "upload of step k+1 overlaps the render of step k (double buffering)"}
 
     if world > 1:
         import torch.distributed as tdist

@@ -47,7 +47,10 @@ class _VolumeRenderFunction(autograd.Function):
     def forward(ctx, data, tree, rays, opt, want_depth):
         out, depth = _C._render_fwd(tree, rays, opt, want_depth)
         ctx.tree, ctx.rays, ctx.opt = tree, rays, opt
-        ctx.saved_out = out
+        # save_for_backward, not a ctx attribute: an output kept as an attribute forms a reference cycle
+        # (out -> grad_fn -> ctx -> out) that only the cyclic GC frees -- hundreds of MB per step linger, and the
+        # caching allocator answers with sporadic 50 ms cudaMallocs.
+        ctx.save_for_backward(out)
         if want_depth:
             ctx.mark_non_differentiable(depth)
             return out, depth
@@ -57,7 +60,7 @@ class _VolumeRenderFunction(autograd.Function):
     def backward(ctx, grad_out, *_unused):
         if ctx.needs_input_grad[0]:
             return (_C.volume_render_backward(ctx.tree, ctx.rays, ctx.opt, grad_out.contiguous(),
-                                              saved_out=ctx.saved_out), None, None, None, None)
+                                              saved_out=ctx.saved_tensors[0]), None, None, None, None)
         return None, None, None, None, None
 
 
@@ -68,7 +71,7 @@ class _VolumeRenderImageFunction(autograd.Function):
     def forward(ctx, data, tree, cam, opt, want_depth):
         out, depth = _C._render_image_fwd(tree, cam, opt, want_depth)
         ctx.tree, ctx.cam, ctx.opt = tree, cam, opt
-        ctx.saved_out = out
+        ctx.save_for_backward(out)
         if want_depth:
             ctx.mark_non_differentiable(depth)
             return out, depth
@@ -78,7 +81,7 @@ class _VolumeRenderImageFunction(autograd.Function):
     def backward(ctx, grad_out, *_unused):
         if ctx.needs_input_grad[0]:
             return (_C.volume_render_image_backward(ctx.tree, ctx.cam, ctx.opt, grad_out.contiguous(),
-                                                    saved_out=ctx.saved_out), None, None, None, None)
+                                                    saved_out=ctx.saved_tensors[0]), None, None, None, None)
         return None, None, None, None, None
 
 
