@@ -26,8 +26,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's banner / debug output on stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line. Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+# version banner there), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 
 import numpy as np  # noqa: E402
 
@@ -149,7 +156,7 @@ def run_reference_arm(args):
     ms = 1e3 * float(np.mean(times))
     val = n / (ms * 1e-3) / 1e6
     sample = f"each step = fwd+bwd of a {n}-ray slice of the 2^20-ray batch (C oracle, OpenMP over rays)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "Mrays/s fwd+bwd feature render", "value": val, "unit": "Mrays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -157,7 +164,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
 
 
 def main():
@@ -360,7 +367,7 @@ def main():
     }
     if not args.skip_extras and world == 1:
         out["extras"] = extras(sv, C, synth, tree, feats, renderer, opt, ts, rs, o_t, d_t, g_t, dev, peak)
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def extras(sv, C, synth, tree, feats, renderer, opt, ts, rs, o_t, d_t, g_t, dev, peak):
