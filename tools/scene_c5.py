@@ -20,7 +20,7 @@ tree = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_
 r = sv.VolumeRenderer(tree); opt = r._get_options()
 t0 = time.time(); acc = tree.accel(feats); torch.cuda.synchronize()
 print("accel:", acc.describe(), f"{time.time()-t0:.3f} s", flush=True)
-ts = tree._spec(feats)
+ts = r._render_spec(feats, 1 << 21)      # activated table + hit marks, as VolumeRenderer attaches them
 
 def ev(fn, warm=2, it=5):
     for _ in range(warm): fn()
