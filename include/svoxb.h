@@ -50,7 +50,7 @@ enum { SVOXB_FORMAT_RGBA = 0, SVOXB_FORMAT_SH = 1, SVOXB_FORMAT_SG = 2, SVOXB_FO
 typedef struct svoxb_accel svoxb_accel;
 
 /* Replaces TreeSpec / PackedTreeSpec (include/data_spec.hpp:67-111, include/data_spec_packed.cuh:57-100).
- * _weight_accum is omitted (not implemented); joint_features / skinning_weights / joint_index are arguments of the
+ * _weight_accum is an argument of svoxb_accumulate_weights; joint_features / skinning_weights / joint_index are arguments of the
  * motion-feature entry points instead of fields. */
 typedef struct svoxb_tree {
     const float* features;      /* [M, D] float32; last channel = sigma                               */
@@ -194,6 +194,13 @@ SVOXB_API int svoxb_opacity_render_bwd(const svoxb_tree* tree, const float* orig
 SVOXB_API int svoxb_motion_render(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
                         const svoxb_render_options* opt, const float* extra_data, int32_t J, float* out, float* depth,
                         float* hit_point, int64_t* data_idx, void* stream);
+
+/* The accumulate_weights side effect of volume_render / volume_render_image (rt_kernel.cu:266-267, 308-310; TreeSpec.
+ * _weight_accum): weight_accum[n_nodes * N^3] (float, caller-zeroed, same shape as child) += T (1 - att) at every hit
+ * leaf of every ray. cam != NULL: the camera's pixel rays (origins / dirs / Q ignored); else the explicit batch. Uses the
+ * thresholds / early stop of the forward. Separate entry point: the render calls themselves never write it. */
+SVOXB_API int svoxb_accumulate_weights(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                             const svoxb_camera* cam, const svoxb_render_options* opt, float* weight_accum, void* stream);
 
 /* motion_feature_render (rt_kernel.cu:885-979, 1525-1543): out[Q, F] += weight * sigmoid(sum_j w_j * JF[joint_j][k]) at
  * every hit, where (w_j, joint_j) are the B skinning weights / joint indices of the hit ROW (skinning_weights[M,B],

@@ -344,3 +344,15 @@ def motion_feature_render_backward(tree, features, origins, dirs, joint_features
                                                                 cr(step_size), _p(jf), _p(sw), _p(ji), ctypes.c_int(F),
                                                                 ctypes.c_int(B), _p(g), _p(grad))
     return grad
+
+
+def accumulate_weights(tree, features, origins, dirs, step_size=1e-3, sigma_thresh=0.0, stop_thresh=0.0,
+                       dtype=np.float32):
+    """-> weight_accum with the shape of child: per-leaf sum of the compositing weights (rt_kernel.cu:308-310)."""
+    sfx, cr = _sfx(dtype)
+    keep, targs = tree.args(features, dtype)
+    o, d = _c(origins, dtype), _c(dirs, dtype)
+    wa = np.zeros(tree.child.shape, dtype=dtype)
+    getattr(lib(), "orc_accumulate_weights" + sfx)(*targs, _p(o), _p(d), ctypes.c_int64(o.shape[0]), cr(step_size),
+                                                    cr(sigma_thresh), cr(stop_thresh), _p(wa))
+    return wa

@@ -80,6 +80,7 @@ SYMBOLS = {
     "svoxb_opacity_render_fwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP]),
     "svoxb_opacity_render_bwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP, _VP]),
     "svoxb_motion_render": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _I32, _VP, _VP, _VP, _VP, _VP]),
+    "svoxb_accumulate_weights": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PC, _PO, _VP, _VP]),
     "svoxb_motion_feature_render_fwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
     "svoxb_motion_feature_render_bwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP,
                                                        _VP]),
@@ -183,7 +184,9 @@ class TreeSpec:
         if self.features.dim() != 2 or self.child.dim() != 4:
             raise RuntimeError("features must be [M, D] and child [n, N, N, N]")
         if self._weight_accum is not None and self._weight_accum.numel():
-            raise RuntimeError("_weight_accum (accumulate_weights) is not implemented in svox_t_b200")
+            _check_input(self._weight_accum, "_weight_accum", torch.float32)
+            if self._weight_accum.numel() != self.child.numel():
+                raise RuntimeError("_weight_accum must have the shape of child")
         M = self.features.shape[0]
         ex, tm = self.extra_data, self.transformation_matrices
         if ex is not None and ex.numel():
@@ -384,6 +387,17 @@ def _out_dim(tree, opt):
     return n
 
 
+def _accumulate_weights(tree, ct, rays, cam_c, opt):
+    """TreeSpec._weight_accum side effect of the two render entry points (rt_kernel.cu:308-310)."""
+    wa = tree._weight_accum
+    if wa is None or not wa.numel():
+        return
+    lib = load_library()
+    o, d, Q = (_ptr(rays.origins), _ptr(rays.dirs), rays.origins.shape[0]) if rays is not None else (None, None, 0)
+    _check(lib.svoxb_accumulate_weights(ctypes.byref(ct), o, d, Q, ctypes.byref(cam_c) if cam_c is not None else None,
+                                        ctypes.byref(opt._c()), _ptr(wa), _stream()))
+
+
 def _render_fwd(tree, rays, opt, want_depth):
     lib = load_library()
     rays.check()
@@ -402,6 +416,7 @@ def _render_fwd(tree, rays, opt, want_depth):
         depth = fused if want_depth else depth
         _check(lib.svoxb_render_rays_fwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), _ptr(rays.vdirs), Q,
                                          ctypes.byref(opt._c()), _ptr(out), _ptr(fused), _stream()))
+        _accumulate_weights(tree, ct, rays, None, opt)
     return out, depth
 
 
@@ -459,6 +474,7 @@ def _render_image_fwd(tree, cam, opt, want_depth):
         depth = torch.empty((cam.height, cam.width, 1), dtype=torch.float32, device=dev) if want_depth else None
         _check(lib.svoxb_render_image_fwd(ctypes.byref(ct), ctypes.byref(cc), ctypes.byref(opt._c()), _ptr(out),
                                           _ptr(depth), _stream()))
+        _accumulate_weights(tree, ct, None, cc, opt)
     return out, depth
 
 

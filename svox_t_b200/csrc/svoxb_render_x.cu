@@ -128,6 +128,45 @@ motion_kernel(TreeArgs tr, const float* __restrict__ origins, const float* __res
     }
 }
 
+// Per-leaf accumulation of the compositing weights (rt_kernel.cu:266-267, 308-310): weight_accum[slot] += T (1 - att) at
+// every hit, slot = the leaf's packed id node*N^3 + u*N^2 + v*N + w. The packed accelerator does not carry slot ids,
+// so this walks the reference tensors (any N); it runs only inside a `with tree.accumulate_weights()` block, next to
+// the normal render. float atomics (the reference's plain += loses updates when rays collide).
+template <bool IMAGE>
+__global__ void __launch_bounds__(BLOCK)
+weight_accum_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ weight_accum) {
+    const int64_t total = IMAGE ? (int64_t)src.width * src.height : src.total;
+    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
+        float ox, oy, oz, dx, dy, dz;
+        if (IMAGE) {
+            camera_ray(src, (int)(id % src.width), (int)(id / src.width), ox, oy, oz, dx, dy, dz);
+            if (src.ndc_w >= 0) world2ndc(src, ox, oy, oz, dx, dy, dz);
+        } else {
+            ox = __ldg(src.origins + 3 * id); oy = __ldg(src.origins + 3 * id + 1); oz = __ldg(src.origins + 3 * id + 2);
+            dx = __ldg(src.dirs + 3 * id); dy = __ldg(src.dirs + 3 * id + 1); dz = __ldg(src.dirs + 3 * id + 2);
+        }
+        Ray ray;
+        ray_setup(tr.offset, tr.scaling, ox, oy, oz, dx, dy, dz, ray);
+        float T = 1.0f;
+        while (ray.t < ray.tmax) {
+            const float px = fmaf(ray.t, ray.dx, ray.ox), py = fmaf(ray.t, ray.dy, ray.oy), pz = fmaf(ray.t, ray.dz, ray.oz);
+            float rx, ry, rz, cube, smin, smax;
+            const int64_t slot = descend_ref(tr.child, tr.N, px, py, pz, rx, ry, rz, cube);
+            const int di = __ldg(tr.data + slot);
+            dda_unit(rx, ry, rz, ray.ix, ray.iy, ray.iz, smin, smax);
+            const float delta_t = (smax - smin) / cube + opt.step;
+            const float sigma = ((int64_t)di < tr.M && di >= 0) ? __ldg(tr.features + (int64_t)di * tr.D + (tr.D - 1)) : 0.0f;
+            if (sigma > opt.sigma_thresh) {
+                const float att = expf(-delta_t * ray.ds * sigma);
+                atomicAdd(weight_accum + slot, T * (1.0f - att));
+                T *= att;
+                if (T <= opt.stop_thresh) break;
+            }
+            ray.t += delta_t;
+        }
+    }
+}
+
 int make_tree_args(const svoxb_tree* t, TreeArgs& a);
 
 static int simple_opts(const svoxb_render_options* opt, MarchOpts& m) {
@@ -189,4 +228,32 @@ extern "C" int svoxb_motion_render(const svoxb_tree* tree, const float* origins,
     if (Q == 0) return 0;
     return launch_simple(tr, Q, (cudaStream_t)stream, motion_kernel<true>, motion_kernel<false>, origins, dirs, Q, m,
                          extra_data, (int)J, out, depth, hit_point, data_idx);
+}
+
+extern "C" int svoxb_accumulate_weights(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                                        const svoxb_camera* cam, const svoxb_render_options* opt, float* weight_accum,
+                                        void* stream) {
+    TreeArgs tr; MarchOpts m;
+    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    rc = simple_opts(opt, m); if (rc) return rc;
+    SVOXB_REQUIRE(weight_accum != nullptr, "weight_accum is NULL");
+    RaySource src{};
+    src.ndc_w = -1;
+    int64_t total;
+    if (cam) {
+        SVOXB_REQUIRE(cam->c2w != nullptr && cam->width > 0 && cam->height > 0, "bad camera spec");
+        src.c2w = cam->c2w; src.fx = cam->fx; src.fy = cam->fy; src.width = cam->width; src.height = cam->height;
+        if (opt->ndc_width >= 0) { src.ndc_w = opt->ndc_width; src.ndc_h = opt->ndc_height; src.ndc_focal = opt->ndc_focal; }
+        total = (int64_t)cam->width * cam->height;
+    } else {
+        SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (origins && dirs)), "bad ray batch");
+        src.origins = origins; src.dirs = dirs; src.total = Q;
+        total = Q;
+    }
+    if (total == 0) return 0;
+    const int grid = (int)min((total + BLOCK - 1) / BLOCK, (int64_t)sm_count() * 8);
+    if (cam) weight_accum_kernel<true><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(tr, src, m, weight_accum);
+    else weight_accum_kernel<false><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(tr, src, m, weight_accum);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "weight_accum_kernel launch");
 }

@@ -99,5 +99,10 @@ class N3TreeView:
     def corners(self):
         return self.tree.tree2world(self.corners_local)
 
+    def aux(self, arr):
+        """Index an auxiliary per-slot array of shape (capacity, N, N, N, ...) with this view (helpers.py:239-244)."""
+        self._check_ver()
+        return arr[self.key]
+
     def __len__(self):
         return self.unique_leaf_node.shape[0]

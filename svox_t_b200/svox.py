@@ -322,6 +322,14 @@ class N3Tree(nn.Module):
             ts._accel = self.accel(features)
         return ts
 
+    def accumulate_weights(self):
+        """``with tree.accumulate_weights() as accum: render(...)`` then ``accum()`` -> per-leaf sum of the compositing
+        weights of every ray rendered inside the block, in ``tree[:]`` order (svox.py:664-677, 948-970)."""
+        return WeightAccumulator(self)
+
+    def aux(self, arr):
+        return self[:].aux(arr)
+
     # ---- persistence (svox.py:679-752) -----------------------------------------------------------------------
     def save(self, path, shrink=True, compress=True):
         n = self.filled if shrink else self.capacity
@@ -372,6 +380,30 @@ class N3Tree(nn.Module):
 
     def __len__(self):
         return self.n_leaves
+
+
+class WeightAccumulator:
+    """svox.py:948-970. The tree structure is locked while weights accumulate."""
+
+    def __init__(self, tree):
+        self.tree = tree
+
+    def __enter__(self):
+        self.tree._lock_tree_structure = True
+        self.tree._weight_accum = torch.zeros(self.tree.child.shape, dtype=torch.float32, device=self.tree.data.device)
+        self.weight_accum = self.tree._weight_accum
+        return self
+
+    def __exit__(self, type, value, traceback):
+        self.tree._weight_accum = None
+        self.tree._lock_tree_structure = False
+
+    @property
+    def value(self):
+        return self.weight_accum
+
+    def __call__(self):
+        return self.tree.aux(self.weight_accum)
 
 
 def get_transformation_matrix(src_pose, tgt_pose):

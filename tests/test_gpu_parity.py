@@ -538,3 +538,76 @@ def test_image_render_sh_and_ndc_vs_oracle(dev, ndc):
         assert o_ref[:, -1].max() > 0.5                                   # the object is in view
         assert frac_within(img.detach().cpu().numpy().reshape(-1, Do), o_ref) >= 0.999
         assert rel_l2(feats.grad.cpu().numpy(), g_ref) <= 1e-4
+
+
+def test_accumulate_weights_context(dev):
+    """`with tree.accumulate_weights() as accum:` around ray and image renders (svox.py:664-677, rt_kernel.cu:308-310)."""
+    tr = synth.synth_tree(5, "ball")
+    D = 8
+    f = synth.synth_features(tr["M"], D)
+    o, d = synth.synth_rays(3000)
+    tree = make_tree(tr, D, dev)
+    r = sv.VolumeRenderer(tree)
+    feats = cu(f, dev)
+    rays = sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev))
+    with tree.accumulate_weights() as accum:
+        with pytest.raises(RuntimeError):
+            tree.refine()                                        # structure is locked while weights accumulate
+        out = r(feats, rays)
+        per_leaf = accum()
+        raw = accum.value.clone()
+    assert tree._weight_accum is None
+    T = orc.Tree(tr["child"], tr["data"])
+    ref = orc.accumulate_weights(T, f, o, d)
+    assert raw.shape == tree.child.shape and per_leaf.shape[0] == tree.n_leaves
+    assert np.allclose(raw.cpu().numpy(), ref, rtol=1e-4, atol=1e-5)
+    assert abs(float(raw.sum()) - float(out[:, -1].sum())) <= 1e-3 * float(out[:, -1].sum())
+    # image render accumulates too; a second render inside the same block adds on top
+    cam = cu(synth.synth_cameras(1)[0], dev)
+    with tree.accumulate_weights() as accum:
+        img = r.render_persp(feats, cam, width=64, height=48, fx=70.0)
+        once = float(accum.value.sum())
+        r.render_persp(feats, cam, width=64, height=48, fx=70.0)
+        twice = float(accum.value.sum())
+    assert abs(once - float(img[..., -1].sum())) <= 1e-3 * once and abs(twice - 2 * once) <= 1e-3 * once
+
+
+def test_hit_marks_are_an_exact_acceleration(dev):
+    """Rows marked sigma <= 0 are skipped without being fetched: outputs and gradients do not change, stale marks are
+    not trusted after an in-place update of the features, and a negative sigma_thresh ignores them."""
+    tr = synth.synth_tree(6, "ball")
+    D, Q = 16, 4096
+    f = synth.synth_features(tr["M"], D)
+    o, d = synth.synth_rays(Q)
+    g = cu(np.random.default_rng(2).standard_normal((Q, D)).astype(np.float32), dev)
+    tree = make_tree(tr, D, dev)
+    r = sv.VolumeRenderer(tree)
+    rays = sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev))
+    rs, opt = sv.renderer._rays_spec_from_rays(rays), r._get_options()
+    feats = cu(f, dev)
+    ts_plain = tree._spec(feats)                                  # accelerator, no marks
+    ref_out = C.volume_render(ts_plain, rs, opt)
+    ref_grad = C.volume_render_backward(ts_plain, rs, opt, g, saved_out=ref_out)
+    ts = tree._spec(feats)
+    ts._accel.mark_hits(feats)
+    assert ts._c().accel_marks_current == 1
+    out = C.volume_render(ts, rs, opt)
+    assert torch.equal(out, ref_out)
+    grad = C.volume_render_backward(ts, rs, opt, g, saved_out=out)
+    assert float((grad - ref_grad).norm() / ref_grad.norm()) < 1e-6
+    # flip the sign of every sigma in place: the marks are now wrong, and must no longer be used
+    feats[:, -1].neg_()
+    assert ts._c().accel_marks_current == 0
+    flipped = C.volume_render(ts, rs, opt)
+    T = orc.Tree(tr["child"], tr["data"])
+    f2 = f.copy()
+    f2[:, -1] *= -1
+    assert frac_within(flipped.cpu().numpy()[:512], orc.render_rays(T, f2, o[:512], d[:512])[0]) >= 0.999
+    # a threshold below zero admits rows with thresh < sigma <= 0, which the marks (sigma > 0) would drop: the forward
+    # must ignore them then. (Empty leaves count as sigma = 0 in the reference and would dereference a null row for
+    # such a threshold, rt_kernel.cu:278-304, so only rows that exist are compared: here against the unmarked run.)
+    ts._accel.mark_hits(feats)
+    r.sigma_thresh = -1.0
+    lo = C.volume_render(ts, rs, r._get_options())
+    assert torch.equal(lo, C.volume_render(ts_plain, rs, r._get_options()))
+    assert not torch.equal(lo, flipped)

@@ -353,6 +353,22 @@ def test_format_and_motion_feature_backwards_match_finite_differences_fp64():
         assert abs(fd - gj[a, b]) <= 1e-6 + 1e-5 * abs(fd)
 
 
+def test_accumulated_weights_sum_to_the_opacity():
+    """sum_i w_i = 1 - T_end: the per-leaf weights of a batch add up to the batch's total opacity, and only leaves that
+    hold a row with sigma > 0 receive weight."""
+    tr = synth.synth_tree(5, "ball")
+    T = orc.Tree(tr["child"], tr["data"])
+    f = synth.synth_features(tr["M"], 6)
+    o, d = synth.synth_rays(400)
+    wa = orc.accumulate_weights(T, f, o, d, dtype=np.float64)
+    op = orc.render_rays(T, f, o, d, dtype=np.float64)[0][:, -1]
+    assert wa.shape == tr["child"].shape and abs(wa.sum() - op.sum()) < 1e-9 * max(1.0, op.sum())
+    idx = tr["data"].reshape(tr["child"].shape)
+    has_row = idx < tr["M"]
+    sig = np.where(has_row, f[np.minimum(idx, tr["M"] - 1), -1], -1.0)
+    assert not wa[~(has_row & (sig > 0))].any()
+
+
 def test_ndc_camera_rays():
     """NDC conversion of pinhole rays (rt_kernel.cu:1168-1191): forward-facing camera at the origin looking down -z.
     Every NDC origin lies on the near plane z_ndc = -1 and directions are unit length; ndc_width < 0 is a no-op."""
