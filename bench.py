@@ -270,6 +270,10 @@ def main():
     main_stream = torch.cuda.current_stream(dev)
     free_ev = [None, None]
     G3 = (D - 1) // 3                                  # channels per decoded colour
+    w_dec = torch.zeros(D, 4, device=dev)              # fixed linear decoder: RGB = means of three channel groups,
+    for c in range(3):                                 # column 3 passes the opacity through
+        w_dec[c * G3:(c + 1) * G3, c] = 1.0 / G3
+    w_dec[D - 1, 3] = 1.0
 
     def upload(k):
         bo, bd, brgb, ba = bufs[k & 1]
@@ -292,8 +296,8 @@ def main():
             with torch.no_grad():
                 fparam.add_(0.0)                       # stands in for the optimiser update: features change every step
             out = renderer(fparam, sv.Rays(bo, bd, bd))
-            rgb = out[:, :3 * G3].reshape(Q, 3, G3).mean(-1)
-            loss = 0.5 * ((rgb - brgb) ** 2).mean() + 0.5 * ((out[:, -1] - ba) ** 2).mean()
+            dec = out @ w_dec                          # [Q, 4]: decoded RGB + opacity
+            loss = 0.5 * ((dec[:, :3] - brgb) ** 2).mean() + 0.5 * ((dec[:, 3] - ba) ** 2).mean()
             loss.backward()
             svd.all_reduce_leaf_grads(fparam.grad)
             free_ev[k & 1] = torch.cuda.Event(); free_ev[k & 1].record(main_stream)
@@ -313,7 +317,7 @@ def main():
            "h2d_bytes_per_step": int(h_o.numel() + h_d.numel() + h_rgb.numel() + h_alpha.numel()) * 4,
            "d2h_bytes_per_step": 4,
            "api": "VolumeRenderer.forward + autograd backward; loss = MSE(decoded RGB, rgb target) + MSE(opacity, alpha "
-                  "target), RGB = mean of three groups of the rendered feature channels. Every step uploads its ray "
+                  "target), RGB / opacity = a fixed linear decoder (out @ W[32,4]: means of three groups of the rendered feature channels, opacity passed through). Every step uploads its ray "
                   "origins, directions, RGB and opacity targets from pinned host memory and reads the loss back; the "
                   "upload of step k+1 overlaps the render of step k (double buffering)"}
 
