@@ -611,3 +611,40 @@ def test_hit_marks_are_an_exact_acceleration(dev):
     lo = C.volume_render(ts, rs, r._get_options())
     assert torch.equal(lo, C.volume_render(ts_plain, rs, r._get_options()))
     assert not torch.equal(lo, flipped)
+
+
+def test_deep_tree_three_stage_accelerator(dev):
+    """Depth-9 shell: the accelerator needs three stages ([4,3,2]; the third lookup happens after the compositing of the
+    previous sample). Packed walk == reference walk bit for bit; a ray sample against the oracle; gradients too."""
+    tr = synth.synth_tree(9, "shell", r_out=0.30, r_in=0.2985)
+    D, Q = 16, 20000
+    f = synth.synth_features(tr["M"], D)
+    o, d = synth.synth_rays(Q)
+    tree = make_tree(tr, D, dev)
+    feats = cu(f, dev)
+    acc = tree.accel(feats)
+    assert acc.describe()["stages"] == 3 and tree.max_depth == 8
+    r = sv.VolumeRenderer(tree)
+    rays = sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev))
+    rs, opt = sv.renderer._rays_spec_from_rays(rays), r._get_options()
+    out_a, dep_a = C.volume_render_with_depth(tree._spec(feats), rs, opt)
+    out_r, dep_r = C.volume_render_with_depth(tree._spec(feats, _with_accel=False), rs, opt)
+    assert torch.equal(dep_a, dep_r) and float((out_a - out_r).abs().max()) <= 1e-6
+    g = cu(np.random.default_rng(3).standard_normal((Q, D)).astype(np.float32), dev)
+    ga = C.volume_render_backward(tree._spec(feats), rs, opt, g, saved_out=out_a)
+    gr = C.volume_render_backward(tree._spec(feats, _with_accel=False), rs, opt, g, saved_out=out_r)
+    assert float((ga - gr).norm() / gr.norm()) <= 1e-5
+    T = orc.Tree(tr["child"], tr["data"])
+    n = 1024
+    o_ref, d_ref = orc.render_rays(T, f, o[:n], d[:n])
+    assert frac_within(out_a.cpu().numpy()[:n], o_ref) >= 0.999
+    assert float((np.abs(dep_a.cpu().numpy()[:n, 0] - d_ref) <= 1e-5).mean()) >= 0.999
+    g_ref = orc.render_rays_backward(T, f, o[:n], d[:n], g.cpu().numpy()[:n])
+    rs_n = sv.renderer._rays_spec_from_rays(sv.Rays(cu(o[:n], dev), cu(d[:n], dev), cu(d[:n], dev)))
+    g_n = C.volume_render_backward(tree._spec(feats), rs_n, opt, g[:n].contiguous(), saved_out=out_a[:n].contiguous())
+    assert rel_l2(g_n.cpu().numpy(), g_ref) <= 1e-4
+    # points query on the deep tree: leaf ids bit-exact with the oracle
+    pts = np.random.default_rng(4).random((5000, 3)).astype(np.float32)
+    _, nid, did = tree(feats, cu(pts, dev), want_node_ids=True, want_data_ids=True)
+    _, on, od, ov = orc.query(T, f, pts)
+    assert (nid.cpu().numpy() == on).all() and (did.cpu().numpy()[ov] == od[ov]).all()
