@@ -123,3 +123,34 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert not pat.search(src), f"{f} references the oracle"
+
+
+def test_loads_a_checkpoint_written_by_the_reference(tmp_path):
+    """tests/golden/ref_ckpt_L3.npz was written by the reference's own N3Tree.save (tests/golden/make_golden_ckpt.py).
+    load() must read it, the same construction through this package's refine() must give identical tensors, and
+    save() must write a file with the reference's keys / dtypes / shapes."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "ref_ckpt_L3.npz")
+    z = np.load(path)
+    t = sv.N3Tree.load(path)
+    assert (t.N, t.data_dim, t.depth_limit, t.filled, t.capacity) == (2, 5, 6, 76, 76)
+    assert repr(t.data_format) == "SH1" and torch.equal(t.extra_data, torch.arange(12.0).reshape(4, 3))
+    assert torch.allclose(t.invradius, torch.tensor([0.5 / 0.8, 0.5 / 0.5, 0.5 / 0.4]))
+    assert torch.allclose(t.offset, 0.5 * (1.0 - torch.tensor([0.1, 0.2, 0.3]) / torch.tensor([0.8, 0.5, 0.4])))
+    mine = sv.N3Tree(N=2, data_dim=5, init_reserve=2000, depth_limit=6, radius=[0.8, 0.5, 0.4], center=[0.1, 0.2, 0.3],
+                     data_format="SH1", extra_data=torch.arange(12.0).reshape(4, 3))
+    mine.refine()
+    mine.refine()
+    leaf = torch.tensor([[1, 0, 0, 0], [1, 0, 0, 1], [1, 1, 1, 1]])
+    mine.refine(sel=(*leaf.T,), leaf_node=leaf)
+    n = mine.filled
+    assert n == 76
+    assert torch.equal(mine.child[:n], t.child) and torch.equal(mine.data[:n], t.data)
+    assert torch.equal(mine.parent_depth[:n], t.parent_depth)
+    out = tmp_path / "again.npz"
+    mine.save(str(out))
+    z2 = np.load(out)
+    assert sorted(z2.files) == sorted(z.files)
+    for k in z.files:
+        assert z2[k].shape == z[k].shape and z2[k].dtype.kind == z[k].dtype.kind, k
+        assert np.array_equal(z2[k], z[k]), k
