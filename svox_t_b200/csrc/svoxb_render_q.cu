@@ -520,6 +520,13 @@ static int carveout_kb(size_t smem) {
     return kb;
 }
 
+// Short queues: spread the warps over the SMs (smaller CTAs) instead of filling a few SMs with 24 warps each.
+static int threads_for(int max_threads, int64_t queue_len) {
+    const int64_t warps_needed = (queue_len + CHUNK - 1) / CHUNK;
+    const int64_t per_sm = (warps_needed + sm_count() - 1) / sm_count();
+    return (int)max((int64_t)64, min((int64_t)max_threads, per_sm * 32));
+}
+
 static int pow2ceil(int n) {
     int l = 1;
     while (l < n) l <<= 1;
@@ -530,16 +537,17 @@ template <int LPR, int V4, bool ACCEL, bool IMAGE>
 static int launch_fwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
     using G = Quad<LPR, V4>;
-    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * G::NWARPS * 32 * LPR * V4;
+    const int threads = threads_for(G::THREADS, src.total);
+    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * (threads / 32) * 32 * LPR * V4;
     void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
     if (depth) kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, true>;
     else kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, false>;
     int grid = 0;
-    int rc = persistent_grid(kern, smem, src.total, grid, G::THREADS, carveout_kb(smem));
+    int rc = persistent_grid(kern, smem, src.total, grid, threads, carveout_kb(smem));
     if (rc) return rc;
     unsigned long long* counter = work_counter(st);
     if (!counter) return SVOXB_ECUDA;
-    kern<<<grid, G::THREADS, smem, st>>>(tr, src, m, out, depth, counter);
+    kern<<<grid, threads, smem, st>>>(tr, src, m, out, depth, counter);
     count_launch();
     return check_cuda(cudaGetLastError(), "march_fwd_quad_kernel launch");
 }
@@ -548,14 +556,15 @@ template <int LPR, int V4, bool ACCEL, bool IMAGE>
 static int launch_bwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const float* go, const float* so,
                         float* grad, cudaStream_t st) {
     using G = Quad<LPR, V4>;
-    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * G::NWARPS * 32 * G::DP;
+    const int threads = threads_for(G::THREADS, src.total);
+    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * (threads / 32) * 32 * G::DP;
     auto kern = march_bwd_quad_kernel<LPR, V4, ACCEL, IMAGE>;
     int grid = 0;
-    int rc = persistent_grid(kern, smem, src.total, grid, G::THREADS, carveout_kb(smem));
+    int rc = persistent_grid(kern, smem, src.total, grid, threads, carveout_kb(smem));
     if (rc) return rc;
     unsigned long long* counter = work_counter(st);
     if (!counter) return SVOXB_ECUDA;
-    kern<<<grid, G::THREADS, smem, st>>>(tr, src, m, go, so, grad, counter);
+    kern<<<grid, threads, smem, st>>>(tr, src, m, go, so, grad, counter);
     count_launch();
     return check_cuda(cudaGetLastError(), "march_bwd_quad_kernel launch");
 }
