@@ -17,7 +17,7 @@ def pytest_configure(config):
 
 def golden_files():
     """Fixtures of the main render path (volume_render / backward / depth / query)."""
-    return sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("x_", "y_")))
+    return sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("x_", "y_", "ref_")))
 
 
 def golden_variant_files():
