@@ -127,7 +127,13 @@ struct Quad {
 #ifndef SVOXB_THREADS32
 #define SVOXB_THREADS32 768
 #endif
-    static constexpr int THREADS = DP <= 32 ? SVOXB_THREADS32 : (DP <= 64 ? 512 : 256);
+#ifndef SVOXB_THREADS64
+#define SVOXB_THREADS64 640
+#endif
+#ifndef SVOXB_THREADS128
+#define SVOXB_THREADS128 384
+#endif
+    static constexpr int THREADS = DP <= 32 ? SVOXB_THREADS32 : (DP <= 64 ? SVOXB_THREADS64 : SVOXB_THREADS128);
     static constexpr int NWARPS = THREADS / 32;
 };
 
