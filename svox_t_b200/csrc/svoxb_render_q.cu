@@ -135,6 +135,12 @@ struct Quad {
 #endif
     static constexpr int THREADS = DP <= 32 ? SVOXB_THREADS32 : (DP <= 64 ? SVOXB_THREADS64 : SVOXB_THREADS128);
     static constexpr int NWARPS = THREADS / 32;
+    // The forward fits 72 registers without spills, so it takes 28 warps (7 per scheduler): 2.97 -> 2.81 ms. 26 and 30
+    // warps (uneven per scheduler) and 32 (64 registers, spills, smaller L1) are slower; the backward spills at 72.
+#ifndef SVOXB_FWD_THREADS32
+#define SVOXB_FWD_THREADS32 896
+#endif
+    static constexpr int FWD_THREADS = DP <= 32 ? SVOXB_FWD_THREADS32 : THREADS;
 };
 
 // V4 float4 of one row block. 256-bit form: LDG.E.256 (sm_100+), which carries its L2 eviction priority inline.
@@ -172,7 +178,7 @@ __device__ __forceinline__ RowBlk<V4> load_row_block(const char* p, uint64_t pol
 //   S4   flush finished rays, refill; the rows of batch 0 of the new candidates are requested first thing in the
 //        next iteration (S0), ahead of S1
 template <int LPR, int V4, bool ACCEL, bool IMAGE, bool DEPTH>
-__global__ void __launch_bounds__((Quad<LPR, V4>::THREADS), 1)
+__global__ void __launch_bounds__((Quad<LPR, V4>::FWD_THREADS), 1)
 march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
                       unsigned long long* counter) {
     using G = Quad<LPR, V4>;
@@ -543,7 +549,7 @@ template <int LPR, int V4, bool ACCEL, bool IMAGE>
 static int launch_fwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
     using G = Quad<LPR, V4>;
-    const int threads = threads_for(G::THREADS, src.total);
+    const int threads = threads_for(G::FWD_THREADS, src.total);
     const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * (threads / 32) * 32 * LPR * V4;
     void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
     if (depth) kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, true>;
