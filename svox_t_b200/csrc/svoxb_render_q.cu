@@ -178,7 +178,7 @@ __device__ __forceinline__ RowBlk<V4> load_row_block(const char* p, uint64_t pol
 //   S4   flush finished rays, refill; the rows of batch 0 of the new candidates are requested first thing in the
 //        next iteration (S0), ahead of S1
 template <int LPR, int V4, bool ACCEL, bool IMAGE, bool DEPTH>
-__global__ void __launch_bounds__((Quad<LPR, V4>::FWD_THREADS), 1)
+__global__ void __launch_bounds__((DEPTH ? Quad<LPR, V4>::THREADS : Quad<LPR, V4>::FWD_THREADS), 1)   // depth: 80 registers
 march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
                       unsigned long long* counter) {
     using G = Quad<LPR, V4>;
@@ -549,7 +549,7 @@ template <int LPR, int V4, bool ACCEL, bool IMAGE>
 static int launch_fwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
     using G = Quad<LPR, V4>;
-    const int threads = threads_for(G::FWD_THREADS, src.total);
+    const int threads = threads_for(depth ? G::THREADS : G::FWD_THREADS, src.total);
     const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * (threads / 32) * 32 * LPR * V4;
     void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
     if (depth) kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, true>;
