@@ -366,6 +366,8 @@ def main():
                           "frac": (b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9 / peak,
                           "bytes_per_ray": (b_fwd + b_bwd) / Q},
         "kernel_ms": {"fwd": fwd_ms, "bwd": bwd_ms},
+        "fwd_only": {"value": world * Q / (fwd_ms * 1e-3) / 1e6, "unit": "Mrays/s",
+                     "note": "forward feature render alone (BASELINE metric (i)), incl. the per-step activation + marking passes"},
         "counters_per_ray": {k: cnt[k] / cnt["Q"] for k in ("S", "LV", "V", "H")},
         "cpu_baseline": cpu_baseline,
     }
