@@ -23,7 +23,7 @@
 namespace svoxb {
 
 constexpr int MAXB = 25;      // basis functions per channel (SH degree 4)
-constexpr int MAXC = 32;      // output channels of the view-dependent / motion-feature renders
+constexpr int MAXC = 31;      // view-dependent output channels: C + 1 (opacity) values per ray are served by one warp
 
 struct FmtArgs {
     int format, B, C, min_comp, max_comp, extra_cols;
@@ -104,9 +104,9 @@ __device__ __forceinline__ void eval_basis_rotated(const FmtArgs& f, int idx, co
 // Shared memory per warp of the view-dependent kernels.
 struct FmtSmem {
     float basis[32][MAXB];     // basis of each lane's ray (odd stride: conflict-free lane-per-ray writes)
-    float acc[32][MAXC + 1];   // forward: partial outputs; backward: staged grad_out row (C+1 values)
+    float acc[32][MAXC + 2];   // forward: partial outputs; backward: staged grad_out row (C+1 values); odd stride
     float prod[128];           // per-hit products, coefficient order
-    float gch[MAXC];           // backward: per-channel w * s(1-s) * g
+    float gch[MAXC + 1];       // backward: per-channel w * s(1-s) * g
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -132,7 +132,6 @@ march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, floa
         comp[k] = (c < C * B && i >= fa.min_comp && i <= fa.max_comp) ? i : -1;
     }
     for (int r = 0; r < 32; ++r) sm.acc[r][lane] = 0.0f;
-    if (lane == 0) for (int r = 0; r < 32; ++r) sm.acc[r][MAXC] = 0.0f;
 
     Ray ray;
     ViewDir vd{0.f, 0.f, 0.f};
