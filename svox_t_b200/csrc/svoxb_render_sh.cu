@@ -123,14 +123,6 @@ march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, floa
     const int D = tr.D, B = fa.B, C = fa.C, Co = C + 1;
     const float* off = tr.offset;
     const float* scl = tr.scaling;
-    const char* fbase = reinterpret_cast<const char*>(tr.features + lane);
-    const unsigned row_bytes = (unsigned)D * 4u;
-    int comp[K];            // basis index of coefficient lane + 32k, or -1 when it takes no part
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int c = lane + 32 * k, i = c % B;
-        comp[k] = (c < C * B && i >= fa.min_comp && i <= fa.max_comp) ? i : -1;
-    }
     for (int r = 0; r < 32; ++r) sm.acc[r][lane] = 0.0f;
 
     Ray ray;
@@ -176,28 +168,18 @@ march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, floa
         }
         __syncwarp();
 
-        // ---- phase B: the warp serves the hits one after another (rt_kernel.cu:293-301) ---------------------------
-        unsigned hm = __ballot_sync(FULL, hit);
-        while (hm) {
-            const int r = __ffs(hm) - 1;
-            hm &= hm - 1;
-            const int idx_r = __shfl_sync(FULL, hidx, r);
-            const float w_r = __shfl_sync(FULL, w, r);
-            const float* rowp = row_ptr(fbase, idx_r, row_bytes);
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                float p = 0.0f;
-                if (comp[k] >= 0) p = sm.basis[r][comp[k]] * __ldg(rowp + 32 * k);
-                sm.prod[lane + 32 * k] = p;
-            }
-            __syncwarp();
-            if (lane < C) {
+        // ---- phase B (rt_kernel.cu:293-301): every lane evaluates its own hit -- C dot products of length <= B against
+        // its ray's basis (shared memory, lane-private slot) -- and adds to its ray's partial outputs. The B*C
+        // coefficients of a row are contiguous, so the lane's loads walk one or two 128-byte lines that stay in L1.
+        if (hit) {
+            const float* rowp = tr.features + (size_t)(unsigned)hidx * D;
+            for (int t = 0; t < C; ++t) {
                 float tmp = 0.0f;
-                for (int i = fa.min_comp; i <= fa.max_comp; ++i) tmp += sm.prod[lane * B + i];
-                sm.acc[r][lane] = fmaf(w_r, fast_sigmoid(tmp), sm.acc[r][lane]);
+                for (int i = fa.min_comp; i <= fa.max_comp; ++i) tmp += sm.basis[lane][i] * __ldg(rowp + t * B + i);
+                sm.acc[lane][t] = fmaf(w, fast_sigmoid(tmp), sm.acc[lane][t]);
             }
-            __syncwarp();
         }
+        __syncwarp();
 
         // ---- finished rays (rt_kernel.cu:313-326) -----------------------------------------------------------------
         unsigned fm = __ballot_sync(FULL, fin != 0);
@@ -641,11 +623,20 @@ static int launch_fmt_bwd(const TreeArgs& tr, const RaySource& src, const MarchO
         return SVOXB_EINVAL;                                                                              \
     } while (0)
 
+// svoxb_render_shrgb.cu: lane-private fast path for SH rows with three output channels
+bool sh_rgb_supported(int format, int B, int D);
+int sh_rgb_fwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, int B, int min_comp, int max_comp,
+               const float* tm, bool image, float* out, cudaStream_t st);
+int sh_rgb_bwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, int B, int min_comp, int max_comp,
+               const float* tm, bool image, const float* go, const float* so, float* grad, cudaStream_t st);
+
 // Entry points used by svoxb_render.cu when opt->format != RGBA.
 int fmt_render_fwd(const svoxb_tree* tree, const TreeArgs& tr, const RaySource& src, const MarchOpts& m,
                    const svoxb_render_options* opt, bool image, float* out, cudaStream_t st) {
     FmtArgs f;
     int rc = make_fmt(tree, opt, f); if (rc) return rc;
+    if (sh_rgb_supported(f.format, f.B, tr.D))
+        return sh_rgb_fwd(tr, src, m, f.B, f.min_comp, f.max_comp, f.tm, image, out, st);
     SVOXB_FMT_DISPATCH(launch_fmt_fwd, tr, src, m, f, out, st);
 }
 
@@ -654,6 +645,8 @@ int fmt_render_bwd(const svoxb_tree* tree, const TreeArgs& tr, const RaySource& 
                    cudaStream_t st) {
     FmtArgs f;
     int rc = make_fmt(tree, opt, f); if (rc) return rc;
+    if (sh_rgb_supported(f.format, f.B, tr.D))
+        return sh_rgb_bwd(tr, src, m, f.B, f.min_comp, f.max_comp, f.tm, image, go, so, grad, st);
     SVOXB_FMT_DISPATCH(launch_fmt_bwd, tr, src, m, f, go, so, grad, st);
 }
 

@@ -648,3 +648,47 @@ def test_deep_tree_three_stage_accelerator(dev):
     _, nid, did = tree(feats, cu(pts, dev), want_node_ids=True, want_data_ids=True)
     _, on, od, ov = orc.query(T, f, pts)
     assert (nid.cpu().numpy() == on).all() and (did.cpu().numpy()[ov] == od[ov]).all()
+
+
+@pytest.mark.parametrize("B", [1, 4, 9, 16, 25])
+def test_sh_rgb_fast_path_vs_oracle(dev, B):
+    """SH rows with three output channels take the lane-private kernels (svoxb_render_shrgb.cu): every degree, with
+    and without the packed accelerator, per-row rotations, a component window, thresholds, rays and camera images."""
+    tr = synth.synth_tree(5, "ball")
+    T = orc.Tree(tr["child"], tr["data"])
+    D, Q = 3 * B + 1, 1500
+    f = synth.synth_features(tr["M"], D, seed=B)
+    f[:, :-1] *= 0.6
+    rng = np.random.default_rng(B)
+    o, d = synth.synth_rays(Q, seed=2)
+    vd = (synth._unit(rng, Q) * rng.uniform(0.5, 1.5, (Q, 1))).astype(np.float32)
+    tm = np.zeros((tr["M"], 4, 4), np.float32)
+    for i in range(tr["M"]):
+        tm[i, :3, :3] = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+    g = rng.standard_normal((Q, 4)).astype(np.float32)
+    lo, hi = (1, B - 2) if B >= 4 else (0, B - 1)
+    for accel in (True, False):
+        for with_tm, (cmin, cmax), thr in ((False, (0, B - 1), 0.0), (True, (lo, hi), 0.0), (False, (0, B - 1), 1e-2)):
+            tree = _fmt_tree(tr, D, 1, B, None, dev, accel)
+            r = sv.VolumeRenderer(tree, min_comp=cmin, max_comp=cmax)
+            r.sigma_thresh, r.stop_thresh = thr, thr
+            feats = cu(f, dev).requires_grad_(True)
+            out = r(feats, sv.Rays(cu(o, dev), cu(d, dev), cu(vd, dev)),
+                    transformation_matrices=cu(tm, dev) if with_tm else None)
+            (out * cu(g, dev)).sum().backward()
+            kw = dict(tm=tm if with_tm else None, min_comp=cmin, max_comp=cmax)
+            o_ref = orc.render_rays_fmt(T, f, o, d, vd, orc.FORMAT_SH, B, sigma_thresh=thr, stop_thresh=thr, **kw)
+            g_ref = orc.render_rays_fmt_backward(T, f, o, d, vd, g, orc.FORMAT_SH, B, **kw)
+            assert frac_within(out.detach().cpu().numpy(), o_ref) >= 0.999, (B, accel, with_tm)
+            assert rel_l2(feats.grad.cpu().numpy(), g_ref) <= 1e-4, (B, accel, with_tm)
+    # camera image through the same kernels
+    W, H, fx = 40, 30, 45.0
+    c2w = synth.synth_cameras(1)[0]
+    tree = _fmt_tree(tr, D, 1, B, None, dev)
+    feats = cu(f, dev).requires_grad_(True)
+    img = sv.VolumeRenderer(tree).render_persp(feats, cu(c2w, dev), width=W, height=H, fx=fx)
+    gi = rng.standard_normal((H * W, 4)).astype(np.float32)
+    (img * cu(gi, dev).view(H, W, 4)).sum().backward()
+    oc, dc, vc = orc.camera_rays_ndc(c2w, fx, fx, W, H)
+    assert frac_within(img.detach().cpu().numpy().reshape(-1, 4), orc.render_rays_fmt(T, f, oc, dc, vc, orc.FORMAT_SH, B)) >= 0.999
+    assert rel_l2(feats.grad.cpu().numpy(), orc.render_rays_fmt_backward(T, f, oc, dc, vc, gi, orc.FORMAT_SH, B)) <= 1e-4
