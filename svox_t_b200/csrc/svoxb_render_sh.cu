@@ -10,11 +10,13 @@
 //   motion_feature_trace_ray (+ the backward it meant to be)    rt_kernel.cu:885-1064, 1525-1572
 //
 // Same skeleton as the scalar-lane RGBA kernels (svoxb_render.cu): persistent warps, lane = ray for the traversal,
-// finished lanes refilled from the global queue, and the per-hit ROW work done by the whole warp with coalesced row
-// reads (lane <-> coefficient c, c+32, ...). What differs is the per-hit arithmetic:
-//   view-dependent : lanes multiply their coefficients by the owner ray's basis values (kept in shared memory, one
-//                    25-float slot per ray), the products go through a shared scratch row and lane t < C sums the
-//                    B products of output channel t in the reference's order;
+// finished lanes refilled from the global queue. What differs is the per-hit arithmetic:
+//   view-dependent : LANE-private -- the owner lane evaluates its hit against its ray's basis (a 25-float slot in shared
+//                    memory, re-evaluated per hit when per-row rotations are given): C dot products of length <= B over
+//                    the row's contiguous coefficients, in the reference's order; the coefficient gradients
+//                    w g_t s_t(1-s_t) basis_i need no row data. (A first, warp-cooperative version that served the
+//                    32 hits of an iteration one after another was slower than the reference's thread-per-ray code.)
+//                    SH rows with three output channels take the register-only kernels of svoxb_render_shrgb.cu.
 //   motion feature : lane k < F accumulates sum_j w_j * JF[joint_j][k] (the joint table is a few KB, L1-resident);
 //                    the backward reduces dL/dJF in a per-CTA shared-memory table (J x F addresses receive every
 //                    contribution of every ray -- global atomics would serialise on them) and flushes it once.
@@ -105,8 +107,6 @@ __device__ __forceinline__ void eval_basis_rotated(const FmtArgs& f, int idx, co
 struct FmtSmem {
     float basis[32][MAXB];     // basis of each lane's ray (odd stride: conflict-free lane-per-ray writes)
     float acc[32][MAXC + 2];   // forward: partial outputs; backward: staged grad_out row (C+1 values); odd stride
-    float prod[128];           // per-hit products, coefficient order
-    float gch[MAXC + 1];       // backward: per-channel w * s(1-s) * g
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -222,16 +222,6 @@ march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, cons
     const int D = tr.D, B = fa.B, C = fa.C, Co = C + 1;
     const float* off = tr.offset;
     const float* scl = tr.scaling;
-    const char* fbase = reinterpret_cast<const char*>(tr.features + lane);
-    char* gbase = reinterpret_cast<char*>(grad + lane);
-    const unsigned row_bytes = (unsigned)D * 4u;
-    int comp[K], chan[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int c = lane + 32 * k, i = c % B;
-        comp[k] = (c < C * B && i >= fa.min_comp && i <= fa.max_comp) ? i : -1;
-        chan[k] = min(c / B, MAXC - 1);
-    }
 
     Ray ray;
     ViewDir vd{0.f, 0.f, 0.f};
@@ -292,47 +282,25 @@ march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, cons
         }
         __syncwarp();
 
-        unsigned hm = __ballot_sync(FULL, hit);
-        while (hm) {
-            const int r = __ffs(hm) - 1;
-            hm &= hm - 1;
-            const int idx_r = __shfl_sync(FULL, hidx, r);
-            const float w_r = __shfl_sync(FULL, w, r);
-            const float* rowp = row_ptr(fbase, idx_r, row_bytes);
-            float bas[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                float p = 0.0f;
-                bas[k] = 0.0f;
-                if (comp[k] >= 0) { bas[k] = sm.basis[r][comp[k]]; p = bas[k] * __ldg(rowp + 32 * k); }
-                sm.prod[lane + 32 * k] = p;
-            }
-            __syncwarp();
-            float cpart = 0.0f;
-            if (lane < C) {
+        // Every lane serves its own hit (lane-private basis / staged grad_out slots in shared memory): C dot products,
+        // the coefficient gradients w g_t s_t(1-s_t) basis_i need no row data and leave as they are found
+        // (rt_kernel.cu:403-417), then the sigma gradient (rt_kernel.cu:479-490).
+        if (hit) {
+            const float* rowp = tr.features + (size_t)(unsigned)hidx * D;
+            float* grow = grad + (size_t)(unsigned)hidx * D;
+            float c = 0.0f;
+            for (int t = 0; t < C; ++t) {
                 float tmp = 0.0f;
-                for (int i = fa.min_comp; i <= fa.max_comp; ++i) tmp += sm.prod[lane * B + i];
-                const float s = fast_sigmoid(tmp), gv = sm.acc[r][lane];
-                cpart = s * gv;                                                  // rt_kernel.cu:416
-                sm.gch[lane] = w_r * s * (1.0f - s) * gv;                        // rt_kernel.cu:409-413
+                for (int i = fa.min_comp; i <= fa.max_comp; ++i) tmp += sm.basis[lane][i] * __ldg(rowp + t * B + i);
+                const float s = fast_sigmoid(tmp), gv = sm.acc[lane][t];
+                c = fmaf(s, gv, c);
+                const float gs = w * s * (1.0f - s) * gv;
+                for (int i = fa.min_comp; i <= fa.max_comp; ++i) atomicAdd(grow + t * B + i, gs * sm.basis[lane][i]);
             }
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) cpart += __shfl_xor_sync(FULL, cpart, s);
-            float sgrad = 0.0f;
-            if (lane == r) {
-                accum -= w * cpart;                                              // rt_kernel.cu:479-480
-                sgrad = dd * (cpart * T - accum) + dd * gop * T_end;             // rt_kernel.cu:486-490
-            }
-            sgrad = __shfl_sync(FULL, sgrad, r);
-            __syncwarp();
-            float* grow = row_ptr(gbase, idx_r, row_bytes);
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                if (comp[k] >= 0) atomicAdd(grow + 32 * k, sm.gch[chan[k]] * bas[k]);
-                else if (lane + 32 * k == D - 1) atomicAdd(grow + 32 * k, sgrad);
-            }
-            __syncwarp();
+            accum -= w * c;
+            atomicAdd(grow + (D - 1), dd * (c * T - accum) + dd * gop * T_end);
         }
+        __syncwarp();
 
         const unsigned fm = __ballot_sync(FULL, fin);
         if (fm) {
