@@ -32,7 +32,8 @@ class _CTree(ctypes.Structure):
         ("offset", ctypes.c_void_p), ("scaling", ctypes.c_void_p), ("accel", ctypes.c_void_p),
         ("features_act", ctypes.c_void_p),
         ("extra_data", ctypes.c_void_p), ("extra_rows", ctypes.c_int32), ("extra_cols", ctypes.c_int32),
-        ("transformation_matrices", ctypes.c_void_p), ("accel_marks_current", ctypes.c_int32),
+        ("transformation_matrices", ctypes.c_void_p), ("features_act_stride", ctypes.c_int32),
+        ("accel_marks_current", ctypes.c_int32),
     ]
 
 
@@ -65,7 +66,7 @@ SYMBOLS = {
     "svoxb_accel_describe": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                             ctypes.POINTER(_I64)]),
     "svoxb_accel_mark_hits": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP]),
-    "svoxb_activate_features": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP]),
+    "svoxb_activate_features": (ctypes.c_int, [_VP, _I64, _I32, _VP, _I32, _VP]),
     "svoxb_query": (ctypes.c_int, [_PT, _VP, _I64, _VP, _VP, _VP, _VP, _VP]),
     "svoxb_leafset_scratch_bytes": (ctypes.c_size_t, [_I64]),
     "svoxb_leafset_scan": (ctypes.c_int, [_VP, _I64, _VP, _VP, _VP]),
@@ -109,7 +110,7 @@ def load_library():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.svoxb_abi_version() != 3:
+        if lib.svoxb_abi_version() != 4:
             raise ImportError("svox_t_b200: libsvoxb.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib
@@ -217,6 +218,7 @@ class TreeSpec:
             extra_rows=self.extra_data.shape[0] if self.extra_data is not None and self.extra_data.numel() else 0,
             extra_cols=self.extra_data.shape[1] if self.extra_data is not None and self.extra_data.numel() else 0,
             transformation_matrices=_ptr(self.transformation_matrices),
+            features_act_stride=act.table.shape[1] if act is not None else 0,
             accel_marks_current=1 if acc is not None and acc.marks_match(self.features) else 0)
         return c
 
@@ -326,10 +328,11 @@ class Activated:
         lib = load_library()
         _check_input(features, "features", torch.float32)
         self._key = self._make_key(features)
+        M, D = features.shape
+        stride = (D + 3) // 4 * 4                  # padded rows are 16-byte aligned: any D runs on the 128-bit kernels
         with torch.cuda.device(features.device):
-            self.table = torch.empty_like(features)
-            _check(lib.svoxb_activate_features(_ptr(features), features.shape[0], features.shape[1], _ptr(self.table),
-                                               _stream()))
+            self.table = torch.empty((M, stride), dtype=torch.float32, device=features.device)
+            _check(lib.svoxb_activate_features(_ptr(features), M, D, _ptr(self.table), stride, _stream()))
 
     @staticmethod
     def _make_key(f):

@@ -280,8 +280,8 @@ static int persistent_grid(Kern kern, size_t smem, int64_t queue_len, int& grid,
     return 0;
 }
 
-// Quad-lane kernels (svoxb_render_q.cu): feature width D % 4 == 0, 4 <= D <= 128.
-bool quad_supported(int D);
+// Quad-lane kernels (svoxb_render_q.cu): D % 4 == 0 (4 <= D <= 128), or any D <= 128 with the padded activated table.
+bool quad_supported(const TreeArgs& tr);
 int launch_fwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, float* out,
                     float* depth, cudaStream_t st);
 int launch_bwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, const float* grad_out,

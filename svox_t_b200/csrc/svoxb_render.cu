@@ -431,7 +431,7 @@ static int launch_bwd(const TreeArgs& tr, const RaySource& src, const MarchOpts&
 template <bool IMAGE>
 static int dispatch_fwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
-    if (quad_supported(tr.D)) return launch_fwd_quad(tr, src, m, IMAGE, out, depth, st);
+    if (quad_supported(tr)) return launch_fwd_quad(tr, src, m, IMAGE, out, depth, st);
     const int K = (tr.D + 31) / 32;
 #define SVOXB_FWD(KK)                                                                        \
     case KK:                                                                                 \
@@ -449,7 +449,7 @@ static int dispatch_fwd(const TreeArgs& tr, const RaySource& src, const MarchOpt
 template <bool IMAGE>
 static int dispatch_bwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const float* go,
                         const float* so, float* grad, cudaStream_t st) {
-    if (quad_supported(tr.D)) return launch_bwd_quad(tr, src, m, IMAGE, go, so, grad, st);
+    if (quad_supported(tr)) return launch_bwd_quad(tr, src, m, IMAGE, go, so, grad, st);
     const int K = (tr.D + 31) / 32;
 #define SVOXB_BWD(KK)                                                                        \
     case KK:                                                                                 \

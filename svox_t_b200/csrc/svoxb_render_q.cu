@@ -61,6 +61,9 @@ __device__ __forceinline__ void red_add_v4_hint(float* p, float a, float b, floa
 #else
 #define SVOXB_L1_HINT ""
 #endif
+__device__ __forceinline__ void red_add_f32_hint(float* p, float a, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(a), "l"(pol) : "memory");
+}
 __device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t pol) {
     float4 v;
     asm volatile("ld.global.nc" SVOXB_L1_HINT ".L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
@@ -109,6 +112,11 @@ __device__ __forceinline__ float quad_reduce(float (&v)[NB], int lane) {
 #pragma unroll
     for (int w = NB; w < LPR; w <<= 1) r += __shfl_xor_sync(FULL, r, w);
     return r;
+}
+
+// Component `e` (0..3, warp-uniform) of a float4.
+__device__ __forceinline__ float comp4(const float4& v, int e) {
+    return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w));
 }
 
 template <int BITS>
@@ -177,7 +185,10 @@ __device__ __forceinline__ RowBlk<V4> load_row_block(const char* p, uint64_t pol
 //   S2.b request rows of batch b, composite it            (b = 1 .. NBATCH-1; latency hides behind S3 / S2.b-1)
 //   S4   flush finished rays, refill; the rows of batch 0 of the new candidates are requested first thing in the
 //        next iteration (S0), ahead of S1
-template <int LPR, int V4, bool ACCEL, bool IMAGE, bool DEPTH>
+// AL (aligned): D % VEC == 0, rows are read in the caller's [M, D] layout (raw or activated). !AL: any other D -- the
+// rows come from the PADDED activated table (stride = D rounded up to a multiple of 4 floats, so they are 16-byte
+// aligned), sigma sits in the middle of its float4, and output rows are written channel by channel.
+template <int LPR, int V4, bool ACCEL, bool IMAGE, bool DEPTH, bool AL>
 __global__ void __launch_bounds__((DEPTH ? Quad<LPR, V4>::THREADS : Quad<LPR, V4>::FWD_THREADS), 1)   // depth: 80 registers
 march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
                       unsigned long long* counter) {
@@ -190,13 +201,15 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     const int lane = threadIdx.x & 31;
     // this warp's 32 x DP partial outputs: accs[(j * V4 + h) * 32] = float4 h of this lane's block of ray RPI*j + q
     float4* accs = reinterpret_cast<float4*>(smem_u32 + top_words) + (size_t)(threadIdx.x >> 5) * 32 * LPR * V4 + lane;
+    static_assert(AL || V4 == 1, "padded rows use 128-bit blocks");
     const int q = lane / LPR, c = lane % LPR;
-    const int D = tr.D, DV = D / VEC;
+    const int D = tr.D, DV = AL ? D / VEC : (D + VEC - 1) / VEC;
+    const int sig_e = AL ? 3 : (D - 1) & 3;              // component of sigma inside its float4
     const bool lane_ok = c < DV, is_sig = c == DV - 1;
     const int sig_src = (lane % RPI) * LPR + (DV - 1);   // lane that holds sigma of this owner lane's row
-    const bool act = tr.feat_act != nullptr;
+    const bool act = AL ? tr.feat_act != nullptr : true;
     const char* fbase = reinterpret_cast<const char*>(act ? tr.feat_act : tr.features) + 4 * VEC * min(c, DV - 1);
-    const unsigned row_bytes = (unsigned)D * 4u;
+    const unsigned row_bytes = AL ? (unsigned)D * 4u : (unsigned)tr.act_stride * 4u;
     const float* off = tr.offset;
     const float* scl = tr.scaling;
 
@@ -262,7 +275,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                 float sig = 0.0f;
 #pragma unroll
                 for (int jj = 0; jj < NB; ++jj) {
-                    const float v = __shfl_sync(FULL, x[jj].v[V4 - 1].w, sig_src);
+                    const float v = __shfl_sync(FULL, AL ? x[jj].v[V4 - 1].w : comp4(x[jj].v[0], sig_e), sig_src);
                     if (lane / RPI == b * NB + jj) sig = v;
                 }
                 float w = 0.0f;
@@ -324,9 +337,20 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                                 const float add = T_r * opt.bg;                           // rt_kernel.cu:323-325
                                 v.x += add; v.y += add; v.z += add; v.w += add;
                             }
-                            if (is_sig && h == V4 - 1) v.w = 1.0f - T_r;                  // rt_kernel.cu:317,326
-                            // written once, never re-read by this kernel: streaming store
-                            if (lane_ok) __stcs(reinterpret_cast<float4*>(out + (int64_t)row_r * D + VEC * c + 4 * h), v);
+                            if constexpr (AL) {
+                                if (is_sig && h == V4 - 1) v.w = 1.0f - T_r;              // rt_kernel.cu:317,326
+                                // written once, never re-read by this kernel: streaming store
+                                if (lane_ok) __stcs(reinterpret_cast<float4*>(out + (int64_t)row_r * D + VEC * c + 4 * h), v);
+                            } else {
+                                float* orow = out + (int64_t)row_r * D;
+                                const float ve[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int ch = 4 * c + e;
+                                    if (ch < D - 1) __stcs(orow + ch, ve[e]);
+                                    else if (ch == D - 1) __stcs(orow + ch, 1.0f - T_r);
+                                }
+                            }
                             accs[(j * V4 + h) * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                     }
@@ -338,7 +362,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     }
 }
 
-template <int LPR, int V4, bool ACCEL, bool IMAGE>
+template <int LPR, int V4, bool ACCEL, bool IMAGE, bool AL>
 __global__ void __launch_bounds__((Quad<LPR, V4>::THREADS), 1)
 march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restrict__ grad_out,
                       const float* __restrict__ saved_out, float* __restrict__ grad, unsigned long long* counter) {
@@ -352,16 +376,19 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
     // staged grad_out rows [32 rays][DP]; with 256-bit blocks the two float4 of a block swap places in the rows read
     // by lanes 4..7 of every quarter-warp, which keeps the 128-bit shared loads conflict-free
     float* gs = reinterpret_cast<float*>(smem_u32 + top_words) + (size_t)warp * 32 * DP;
+    static_assert(AL || V4 == 1, "padded rows use 128-bit blocks");
     const int q = lane / LPR, c = lane % LPR;
-    const int D = tr.D, DV = D / VEC;
+    const int D = tr.D, DV = AL ? D / VEC : (D + VEC - 1) / VEC;
+    const int sig_e = AL ? 3 : (D - 1) & 3;
     const bool lane_ok = c < DV, is_sig = c == DV - 1;
     const int sig_src = (lane % RPI) * LPR + (DV - 1);
     const int red_src = (lane % RPI) * LPR + ((lane / RPI) % NB);     // lane holding this owner's reduced dot product
     const int swz = V4 == 2 ? (lane >> 2) & 1 : 0;
-    const bool act = tr.feat_act != nullptr;
+    const bool act = AL ? tr.feat_act != nullptr : true;
     const char* fbase = reinterpret_cast<const char*>(act ? tr.feat_act : tr.features) + 4 * VEC * min(c, DV - 1);
     char* gbase = reinterpret_cast<char*>(grad) + 4 * VEC * c;
-    const unsigned row_bytes = (unsigned)D * 4u;
+    const unsigned row_bytes = AL ? (unsigned)D * 4u : (unsigned)tr.act_stride * 4u;   // feature rows
+    const unsigned grow_bytes = (unsigned)D * 4u;                                      // gradient rows: caller's layout
     const float* off = tr.offset;
     const float* scl = tr.scaling;
 
@@ -395,7 +422,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                     const float ov = (e < D) ? __ldcs(so + e) : 0.0f;
                     int slot = e >> 2;                                   // float4 slot inside the row
                     if (V4 == 2) slot ^= ((((r % RPI) * LPR + (e / VEC)) >> 2) & 1);   // reader lane = q*LPR + c
-                    gs[r * DP + 4 * slot + (e & 3)] = gv;
+                    gs[r * DP + 4 * slot + (e & 3)] = (!AL && e == D - 1) ? 0.0f : gv;   // padded rows: no masking later
                     if (e < D - 1) part = fmaf(gv, ov, part);
                     if (e == D - 1) { g_last = gv; o_last = ov; }
                 }
@@ -442,7 +469,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                 float sig = 0.0f;
 #pragma unroll
                 for (int jj = 0; jj < NB; ++jj) {
-                    const float v = __shfl_sync(FULL, x[jj].v[V4 - 1].w, sig_src);
+                    const float v = __shfl_sync(FULL, AL ? x[jj].v[V4 - 1].w : comp4(x[jj].v[0], sig_e), sig_src);
                     if (lane / RPI == b * NB + jj) sig = v;
                 }
                 float w = 0.0f, dd = 0.0f;
@@ -467,7 +494,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                             const float4 g4 = *reinterpret_cast<const float4*>(gs + r * DP + 4 * ((c * V4 + h) ^ swz));
                             const float4 s = activated(x[jj].v[h], act);
                             const float sx = s.x * g4.x, sy = s.y * g4.y, sz = s.z * g4.z, sw = s.w * g4.w;
-                            tot += (sx + sy) + (sz + ((is_sig && h == V4 - 1) ? 0.0f : sw));
+                            tot += (sx + sy) + (sz + ((AL && is_sig && h == V4 - 1) ? 0.0f : sw));   // !AL: g is 0 there
                             sv[jj].v[h] = make_float4(fmaf(-sx, s.x, sx), fmaf(-sy, s.y, sy), fmaf(-sz, s.z, sz),
                                                       fmaf(-sw, s.w, sw));               // s (1 - s) g
                         }
@@ -487,16 +514,27 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                         const float sg_j = __shfl_sync(FULL, sgrad, r);
                         const int idx_j = __shfl_sync(FULL, p_idx, r);
                         if (((hb >> r) & 1u) && lane_ok) {
-                            float* grow = reinterpret_cast<float*>(gbase + (size_t)(unsigned)idx_j * row_bytes);
+                            float* grow = reinterpret_cast<float*>(gbase + (size_t)(unsigned)idx_j * grow_bytes);
+                            if constexpr (AL) {
 #pragma unroll
-                            for (int h = 0; h < V4; ++h) {
-                                const float4 t = sv[jj].v[h];
-                                const float last = (is_sig && h == V4 - 1) ? sg_j : w_j * t.w;
+                                for (int h = 0; h < V4; ++h) {
+                                    const float4 t = sv[jj].v[h];
+                                    const float last = (is_sig && h == V4 - 1) ? sg_j : w_j * t.w;
 #if SVOXB_BWD_HINTS
-                                red_add_v4_hint(grow + 4 * h, w_j * t.x, w_j * t.y, w_j * t.z, last, pol_last);
+                                    red_add_v4_hint(grow + 4 * h, w_j * t.x, w_j * t.y, w_j * t.z, last, pol_last);
 #else
-                                red_add_v4(grow + 4 * h, w_j * t.x, w_j * t.y, w_j * t.z, last);
+                                    red_add_v4(grow + 4 * h, w_j * t.x, w_j * t.y, w_j * t.z, last);
 #endif
+                                }
+                            } else {        // rows of the caller's gradient table are not 16-byte aligned: scalar reductions
+                                const float4 t = sv[jj].v[0];
+                                const float te[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int ch = 4 * c + e;
+                                    if (ch < D - 1) red_add_f32_hint(grow + e, w_j * te[e], pol_last);
+                                    else if (ch == D - 1) red_add_f32_hint(grow + e, sg_j, pol_last);
+                                }
                             }
                         }
                     }
@@ -521,7 +559,12 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
-bool quad_supported(int D) { return D % 4 == 0 && D >= 4 && D <= 128; }
+// D % 4 == 0: always. Any other D: when the padded activated table is attached (its rows are 16-byte aligned).
+bool quad_supported(const TreeArgs& tr) {
+    if (tr.D < 2 || tr.D > 128) return false;
+    if (tr.D % 4 == 0) return true;
+    return tr.feat_act != nullptr && tr.act_stride % 4 == 0 && tr.act_stride >= tr.D && tr.act_stride < tr.D + 4;
+}
 
 // Shared memory this one-CTA-per-SM kernel needs (+1 KB the runtime reserves per CTA), in KB; the rest of the SM's
 // 228 KB stays L1, which is what bounds the number of row gathers in flight (measured: forcing the carve-out to the
@@ -545,15 +588,15 @@ static int pow2ceil(int n) {
     return l;
 }
 
-template <int LPR, int V4, bool ACCEL, bool IMAGE>
+template <int LPR, int V4, bool ACCEL, bool IMAGE, bool AL>
 static int launch_fwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
     using G = Quad<LPR, V4>;
     const int threads = threads_for(depth ? G::THREADS : G::FWD_THREADS, src.total);
     const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * (threads / 32) * 32 * LPR * V4;
     void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
-    if (depth) kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, true>;
-    else kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, false>;
+    if (depth) kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, true, AL>;
+    else kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, false, AL>;
     int grid = 0;
     int rc = persistent_grid(kern, smem, src.total, grid, threads, carveout_kb(smem));
     if (rc) return rc;
@@ -564,13 +607,13 @@ static int launch_fwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpt
     return check_cuda(cudaGetLastError(), "march_fwd_quad_kernel launch");
 }
 
-template <int LPR, int V4, bool ACCEL, bool IMAGE>
+template <int LPR, int V4, bool ACCEL, bool IMAGE, bool AL>
 static int launch_bwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const float* go, const float* so,
                         float* grad, cudaStream_t st) {
     using G = Quad<LPR, V4>;
     const int threads = threads_for(G::THREADS, src.total);
     const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * (threads / 32) * 32 * G::DP;
-    auto kern = march_bwd_quad_kernel<LPR, V4, ACCEL, IMAGE>;
+    auto kern = march_bwd_quad_kernel<LPR, V4, ACCEL, IMAGE, AL>;
     int grid = 0;
     int rc = persistent_grid(kern, smem, src.total, grid, threads, carveout_kb(smem));
     if (rc) return rc;
@@ -582,10 +625,16 @@ static int launch_bwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpt
 }
 
 #define SVOXB_Q_CASES(FN, L, V, ...)                                                                   \
-    case ((L) * 2 + (V)-1) * 4 + 0: return FN<L, V, false, false>(__VA_ARGS__);                        \
-    case ((L) * 2 + (V)-1) * 4 + 1: return FN<L, V, false, true>(__VA_ARGS__);                         \
-    case ((L) * 2 + (V)-1) * 4 + 2: return FN<L, V, true, false>(__VA_ARGS__);                         \
-    case ((L) * 2 + (V)-1) * 4 + 3: return FN<L, V, true, true>(__VA_ARGS__);
+    case ((L) * 2 + (V)-1) * 4 + 0: return FN<L, V, false, false, true>(__VA_ARGS__);                  \
+    case ((L) * 2 + (V)-1) * 4 + 1: return FN<L, V, false, true, true>(__VA_ARGS__);                   \
+    case ((L) * 2 + (V)-1) * 4 + 2: return FN<L, V, true, false, true>(__VA_ARGS__);                   \
+    case ((L) * 2 + (V)-1) * 4 + 3: return FN<L, V, true, true, true>(__VA_ARGS__);
+// padded rows (D % 4 != 0): 128-bit blocks, LPR = pow2ceil(ceil(D / 4))
+#define SVOXB_Q_PAD_CASES(FN, L, ...)                                                                  \
+    case (L) * 4 + 0: return FN<L, 1, false, false, false>(__VA_ARGS__);                               \
+    case (L) * 4 + 1: return FN<L, 1, false, true, false>(__VA_ARGS__);                                \
+    case (L) * 4 + 2: return FN<L, 1, true, false, false>(__VA_ARGS__);                                \
+    case (L) * 4 + 3: return FN<L, 1, true, true, false>(__VA_ARGS__);
 
 // Measured on B200 (C3): 256-bit row blocks execute 9 % (forward) / 18 % (backward) fewer instructions but run SLOWER
 // (fwd 2.98 -> 3.18 ms, bwd 6.14 -> 7.43 ms): the march is latency-bound, and eight small independent row groups per
@@ -605,6 +654,17 @@ static int launch_bwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpt
 // 256-bit row blocks when enabled and the rows allow it (D % 8 == 0, 32-byte aligned tables), else 128-bit blocks.
 #define SVOXB_Q_DISPATCH(FN, wide, ...)                                                                \
     do {                                                                                               \
+        if (tr.D % 4 != 0) {                                                                           \
+            const int lpr = pow2ceil((tr.D + 3) / 4);                                                  \
+            switch (lpr * 4 + ((tr.use_accel ? 2 : 0) | (image ? 1 : 0))) {                            \
+                SVOXB_Q_PAD_CASES(FN, 1, __VA_ARGS__) SVOXB_Q_PAD_CASES(FN, 2, __VA_ARGS__)            \
+                SVOXB_Q_PAD_CASES(FN, 4, __VA_ARGS__) SVOXB_Q_PAD_CASES(FN, 8, __VA_ARGS__)            \
+                SVOXB_Q_PAD_CASES(FN, 16, __VA_ARGS__) SVOXB_Q_PAD_CASES(FN, 32, __VA_ARGS__)          \
+                default: break;                                                                        \
+            }                                                                                          \
+            set_error("quad kernels: unsupported feature width D=%d", tr.D);                          \
+            return SVOXB_EINVAL;                                                                       \
+        }                                                                                              \
         const int v4 = (wide) ? 2 : 1;                                                                 \
         const int lpr = pow2ceil(tr.D / (4 * v4));                                                     \
         const int sel = (tr.use_accel ? 2 : 0) | (image ? 1 : 0);                                      \
@@ -624,16 +684,19 @@ int launch_fwd_quad(const TreeArgs& tr_in, const RaySource& src, const MarchOpts
                     float* depth, cudaStream_t st) {
     TreeArgs tr = tr_in;
     if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;     // the marks encode sigma > 0: too strict for this predicate
-    SVOXB_REQUIRE(((uintptr_t)tr.features & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)tr.feat_act & 15) == 0,
-                  "features/out must be 16-byte aligned");
+    if (tr.D % 4 == 0)
+        SVOXB_REQUIRE(((uintptr_t)tr.features & 15) == 0 && ((uintptr_t)out & 15) == 0, "features/out must be 16-byte aligned");
+    SVOXB_REQUIRE(((uintptr_t)tr.feat_act & 15) == 0, "the activated table must be 16-byte aligned");
     const bool wide = SVOXB_WIDE_ROWS && tr.D % 8 == 0 && (((uintptr_t)tr.features | (uintptr_t)tr.feat_act) & 31) == 0;
     SVOXB_Q_DISPATCH(launch_fwd_q, wide, tr, src, m, out, depth, st);
 }
 
 int launch_bwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, const float* grad_out,
                     const float* saved_out, float* grad, cudaStream_t st) {
-    SVOXB_REQUIRE(((uintptr_t)tr.features & 15) == 0 && ((uintptr_t)grad & 15) == 0 && ((uintptr_t)tr.feat_act & 15) == 0,
-                  "features/grad_features must be 16-byte aligned");
+    if (tr.D % 4 == 0)
+        SVOXB_REQUIRE(((uintptr_t)tr.features & 15) == 0 && ((uintptr_t)grad & 15) == 0,
+                      "features/grad_features must be 16-byte aligned");
+    SVOXB_REQUIRE(((uintptr_t)tr.feat_act & 15) == 0, "the activated table must be 16-byte aligned");
     const bool wide = SVOXB_WIDE_ROWS && tr.D % 8 == 0 && (((uintptr_t)tr.features | (uintptr_t)tr.feat_act) & 31) == 0;
     SVOXB_Q_DISPATCH(launch_bwd_q, wide, tr, src, m, grad_out, saved_out, grad, st);
 }

@@ -111,6 +111,10 @@ int make_tree_args(const svoxb_tree* t, TreeArgs& a) {
     a.child = t->child; a.data = t->data; a.offset = t->offset; a.scaling = t->scaling;
     a.use_accel = 0;
     a.feat_act = t->M > 0 ? t->features_act : nullptr;
+    a.act_stride = t->features_act_stride > 0 ? t->features_act_stride : t->D;
+    SVOXB_REQUIRE(a.feat_act == nullptr || a.act_stride == t->D || (a.act_stride % 4 == 0 && a.act_stride > t->D &&
+                  a.act_stride < t->D + 4), "features_act_stride=%d must be D or D rounded up to a multiple of 4",
+                  a.act_stride);
     a.acc_miss_mask = 0;
     memset(&a.acc, 0, sizeof(a.acc));
     if (t->accel) {
@@ -203,6 +207,22 @@ activate_kernel(const float* __restrict__ f, int64_t n, int D, float* __restrict
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float v = __ldg(f + i);
         out[i] = ((int)(i % D) == D - 1) ? v : fast_sigmoid(v);
+    }
+}
+
+// Padded output rows (stride S = D rounded up to a multiple of 4): one thread per output float, zeros in the padding.
+__global__ void __launch_bounds__(256)
+activate_padded_kernel(const float* __restrict__ f, int64_t M, int D, int S, float* __restrict__ out) {
+    const int64_t n = M * S;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / S;
+        const int c = (int)(i - r * S);
+        float v = 0.0f;
+        if (c < D) {
+            v = __ldg(f + r * D + c);
+            if (c < D - 1) v = fast_sigmoid(v);
+        }
+        out[i] = v;
     }
 }
 
@@ -551,13 +571,20 @@ extern "C" int svoxb_accel_mark_hits(svoxb_accel* a, const float* features, int6
     return 0;
 }
 
-extern "C" int svoxb_activate_features(const float* features, int64_t M, int32_t D, float* out, void* stream) {
+extern "C" int svoxb_activate_features(const float* features, int64_t M, int32_t D, float* out, int32_t out_stride,
+                                       void* stream) {
     SVOXB_REQUIRE(M >= 0 && D >= 2, "bad sizes");
+    if (out_stride <= 0) out_stride = D;
+    SVOXB_REQUIRE(out_stride == D || (out_stride % 4 == 0 && out_stride > D && out_stride < D + 4),
+                  "out_stride=%d must be D or D rounded up to a multiple of 4", out_stride);
     if (M == 0) return 0;
     SVOXB_REQUIRE(features && out, "NULL tensor");
     const int64_t n = M * D;
     cudaStream_t st = (cudaStream_t)stream;
-    if (D % 4 == 0 && (((uintptr_t)features | (uintptr_t)out) & 15) == 0) {
+    if (out_stride != D) {
+        const int grid = (int)min((M * out_stride + 255) / 256, (int64_t)sm_count() * 16);
+        activate_padded_kernel<<<grid, 256, 0, st>>>(features, M, D, out_stride, out);
+    } else if (D % 4 == 0 && (((uintptr_t)features | (uintptr_t)out) & 15) == 0) {
         const int grid = (int)min((n / 4 + 255) / 256, (int64_t)sm_count() * 16);
         activate4_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(features), n / 4, D / 4,
                                               reinterpret_cast<float4*>(out));

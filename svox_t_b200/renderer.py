@@ -144,8 +144,7 @@ class VolumeRenderer(nn.Module):
         keep the in-kernel sigmoid, for which one pass over the whole table would cost more than it saves."""
         ts = self.tree._spec(features, **kw)
         M, D = features.shape
-        if (self.data_format.format == DataFormat.RGBA and D % 4 == 0 and 4 <= D <= 128 and n_rays * 32 >= M
-                and features.is_cuda):
+        if self.data_format.format == DataFormat.RGBA and 2 <= D <= 128 and n_rays * 32 >= M and features.is_cuda:
             ts._act = self.tree.activated(features.detach())
             if ts._accel is not None:
                 ts._accel.mark_hits(features.detach())
