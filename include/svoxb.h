@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SVOXB_ABI_VERSION 4
+#define SVOXB_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define SVOXB_API __attribute__((visibility("default")))
@@ -99,6 +99,9 @@ typedef struct svoxb_camera {
     const float* c2w;           /* device, row-major [3 or 4, 4] camera-to-world, OpenGL convention   */
     float fx, fy;
     int32_t width, height;
+    int32_t row_begin, row_end; /* row_end > 0: render only image rows [row_begin, row_end) -- out / depth / grad_out   */
+                                /* then hold (row_end - row_begin) x width pixels. 0, 0 = the whole image. One camera   */
+                                /* frame split into row bands is how a single view shards over GPUs.        */
 } svoxb_camera;
 
 /* ---- housekeeping ------------------------------------------------------------------------------ */

@@ -49,7 +49,8 @@ class _COptions(ctypes.Structure):
 
 class _CCamera(ctypes.Structure):
     _fields_ = [("c2w", ctypes.c_void_p), ("fx", ctypes.c_float), ("fy", ctypes.c_float),
-                ("width", ctypes.c_int32), ("height", ctypes.c_int32)]
+                ("width", ctypes.c_int32), ("height", ctypes.c_int32),
+                ("row_begin", ctypes.c_int32), ("row_end", ctypes.c_int32)]
 
 
 # Every symbol include/svoxb.h declares: (restype, argtypes). tests/test_cabi.py checks the list against the header.
@@ -110,7 +111,7 @@ def load_library():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.svoxb_abi_version() != 4:
+        if lib.svoxb_abi_version() != 5:
             raise ImportError("svox_t_b200: libsvoxb.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib
@@ -230,6 +231,8 @@ class CameraSpec:
         self.fy = 0.0
         self.width = 0
         self.height = 0
+        self.row_begin = 0          # svox_t_b200 extension: render only rows [row_begin, row_end) (0, 0 = all)
+        self.row_end = 0
 
     def check(self):
         _check_input(self.c2w, "c2w", torch.float32)
@@ -239,7 +242,12 @@ class CameraSpec:
     def _c(self):
         self.check()
         return _CCamera(c2w=_ptr(self.c2w), fx=float(self.fx), fy=float(self.fy), width=int(self.width),
-                        height=int(self.height))
+                        height=int(self.height), row_begin=int(self.row_begin), row_end=int(self.row_end))
+
+    @property
+    def rows(self):
+        """Number of image rows the kernels write (the band, or the whole image)."""
+        return int(self.row_end - self.row_begin) if self.row_end > 0 else int(self.height)
 
 
 class RenderOptions:
@@ -473,8 +481,8 @@ def _render_image_fwd(tree, cam, opt, want_depth):
     if want_depth and opt.format != FORMAT_RGBA:
         raise RuntimeError("svox_t_b200.csrc: fused image depth is only available for the RGBA format")
     with torch.cuda.device(dev):
-        out = torch.empty((cam.height, cam.width, D), dtype=torch.float32, device=dev)
-        depth = torch.empty((cam.height, cam.width, 1), dtype=torch.float32, device=dev) if want_depth else None
+        out = torch.empty((cam.rows, cam.width, D), dtype=torch.float32, device=dev)
+        depth = torch.empty((cam.rows, cam.width, 1), dtype=torch.float32, device=dev) if want_depth else None
         _check(lib.svoxb_render_image_fwd(ctypes.byref(ct), ctypes.byref(cc), ctypes.byref(opt._c()), _ptr(out),
                                           _ptr(depth), _stream()))
         _accumulate_weights(tree, ct, None, cc, opt)

@@ -21,6 +21,7 @@ struct RaySource {
     float fx, fy;
     int width, height;
     int tiles_x;
+    int row_begin, row_end;        // camera rays: image rows [row_begin, row_end) are rendered (a band of the image)
     int64_t total;                 // queue length: Q, or n_tiles * 64
     const float* vdirs;            // explicit rays: [Q,3] view directions (view-dependent formats only)
     int ndc_w, ndc_h;              // camera rays: NDC conversion when ndc_w >= 0 (rt_kernel.cu:1168-1191)
@@ -125,11 +126,11 @@ __device__ __forceinline__ unsigned refill(const RaySource& src, const float* of
             if (IMAGE) {
                 const int tile = (int)(id >> 6), in = (int)(id & 63);
                 const int px = (tile % src.tiles_x) * 8 + (in & 7);
-                const int py = (tile / src.tiles_x) * 8 + (in >> 3);
-                valid = px < src.width && py < src.height;
+                const int py = src.row_begin + (tile / src.tiles_x) * 8 + (in >> 3);
+                valid = px < src.width && py < src.row_end;
                 if (valid) {
                     camera_ray(src, px, py, ox, oy, oz, dx, dy, dz);
-                    row = py * src.width + px;
+                    row = (py - src.row_begin) * src.width + px;      // output rows start at the band
                     if (VDIR) { vd->x = dx; vd->y = dy; vd->z = dz; }
                     if (src.ndc_w >= 0) world2ndc(src, ox, oy, oz, dx, dy, dz);
                 }

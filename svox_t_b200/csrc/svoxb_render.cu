@@ -388,8 +388,14 @@ static int make_source(const float* origins, const float* dirs, const float* vdi
         SVOXB_REQUIRE(cam->c2w != nullptr && cam->width > 0 && cam->height > 0, "bad camera spec");
         SVOXB_REQUIRE((int64_t)cam->width * cam->height < (1ll << 31), "image too large");
         s.c2w = cam->c2w; s.fx = cam->fx; s.fy = cam->fy; s.width = cam->width; s.height = cam->height;
+        s.row_begin = 0; s.row_end = cam->height;
+        if (cam->row_end > 0) {
+            SVOXB_REQUIRE(cam->row_begin >= 0 && cam->row_begin < cam->row_end && cam->row_end <= cam->height,
+                          "bad image band [%d, %d) for height %d", cam->row_begin, cam->row_end, cam->height);
+            s.row_begin = cam->row_begin; s.row_end = cam->row_end;
+        }
         s.tiles_x = (cam->width + 7) / 8;
-        s.total = (int64_t)s.tiles_x * ((cam->height + 7) / 8) * 64;
+        s.total = (int64_t)s.tiles_x * ((s.row_end - s.row_begin + 7) / 8) * 64;
     } else {
         SVOXB_REQUIRE(Q >= 0 && Q < (1ll << 31), "ray count out of range");
         SVOXB_REQUIRE(Q == 0 || (origins && dirs), "origins/dirs are NULL");

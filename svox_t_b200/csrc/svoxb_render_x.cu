@@ -135,11 +135,11 @@ motion_kernel(TreeArgs tr, const float* __restrict__ origins, const float* __res
 template <bool IMAGE>
 __global__ void __launch_bounds__(BLOCK)
 weight_accum_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ weight_accum) {
-    const int64_t total = IMAGE ? (int64_t)src.width * src.height : src.total;
+    const int64_t total = IMAGE ? (int64_t)src.width * (src.row_end - src.row_begin) : src.total;
     for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
         float ox, oy, oz, dx, dy, dz;
         if (IMAGE) {
-            camera_ray(src, (int)(id % src.width), (int)(id / src.width), ox, oy, oz, dx, dy, dz);
+            camera_ray(src, (int)(id % src.width), src.row_begin + (int)(id / src.width), ox, oy, oz, dx, dy, dz);
             if (src.ndc_w >= 0) world2ndc(src, ox, oy, oz, dx, dy, dz);
         } else {
             ox = __ldg(src.origins + 3 * id); oy = __ldg(src.origins + 3 * id + 1); oz = __ldg(src.origins + 3 * id + 2);
@@ -243,8 +243,13 @@ extern "C" int svoxb_accumulate_weights(const svoxb_tree* tree, const float* ori
     if (cam) {
         SVOXB_REQUIRE(cam->c2w != nullptr && cam->width > 0 && cam->height > 0, "bad camera spec");
         src.c2w = cam->c2w; src.fx = cam->fx; src.fy = cam->fy; src.width = cam->width; src.height = cam->height;
+        src.row_begin = 0; src.row_end = cam->height;
+        if (cam->row_end > 0) {
+            SVOXB_REQUIRE(cam->row_begin >= 0 && cam->row_begin < cam->row_end && cam->row_end <= cam->height, "bad image band");
+            src.row_begin = cam->row_begin; src.row_end = cam->row_end;
+        }
         if (opt->ndc_width >= 0) { src.ndc_w = opt->ndc_width; src.ndc_h = opt->ndc_height; src.ndc_focal = opt->ndc_focal; }
-        total = (int64_t)cam->width * cam->height;
+        total = (int64_t)cam->width * (src.row_end - src.row_begin);
     } else {
         SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (origins && dirs)), "bad ray batch");
         src.origins = origins; src.dirs = dirs; src.total = Q;

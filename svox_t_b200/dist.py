@@ -79,3 +79,38 @@ def render_step_sharded(renderer, features, rays, loss_fn, rank, world):
     loss.backward()
     all_reduce_leaf_grads(features.grad)
     return loss.detach(), features.grad
+
+
+def render_image_bands(renderer, features, c2w, width, height, fx, fy=None, rank=0, world=1, gather=True):
+    """One camera frame sharded over the ranks by horizontal bands (aligned to the kernels' 8-row tiles): every rank
+    renders rows [y0, y1) with the tree and features it holds; ``gather=True`` all-gathers the bands so that every rank
+    returns the full (height, width, D) image, else this rank's band and its (y0, y1). Inference path (no autograd
+    through the gather)."""
+    from . import csrc as _C
+    y0, y1 = shard_image_rows(height, rank, world)
+    D = _C._out_dim(renderer.tree._spec(features, _with_accel=False), renderer._get_options())
+    with torch.no_grad():
+        if y1 > y0:
+            band = renderer.render_persp(features, c2w, width=width, height=height, fx=fx, fy=fy, rows=(y0, y1))
+        else:                                          # more ranks than 8-row tiles
+            band = features.new_empty((0, width, D))
+    if not gather:
+        return band, (y0, y1)
+    if world == 1 or not dist.is_initialized():
+        return band
+    bounds = [shard_image_rows(height, r, world) for r in range(world)]
+    most = max(b1 - b0 for b0, b1 in bounds)            # all_gather wants equal shapes: pad the bands to the tallest
+    padded = features.new_zeros((most, width, D))
+    padded[: y1 - y0] = band
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    return torch.cat([p[: b1 - b0] for p, (b0, b1) in zip(parts, bounds)], dim=0)
+
+
+def render_views_sharded(renderer, features, cams, width, height, fx, fy=None, rank=0, world=1):
+    """A batch of views split across the ranks (whole views per GPU): returns the images of this
+    rank's contiguous share of ``cams`` (list of c2w tensors) and the share's (lo, hi)."""
+    lo, hi = shard_range(len(cams), rank, world)
+    with torch.no_grad():
+        imgs = [renderer.render_persp(features, cams[v], width=width, height=height, fx=fx, fy=fy) for v in range(lo, hi)]
+    return imgs, (lo, hi)

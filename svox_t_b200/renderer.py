@@ -30,13 +30,15 @@ def _rays_spec_from_rays(rays):
     return spec
 
 
-def _make_camera_spec(c2w, width, height, fx, fy):
+def _make_camera_spec(c2w, width, height, fx, fy, rows=None):
     spec = _C.CameraSpec()
     spec.c2w = c2w
     spec.width = width
     spec.height = height
     spec.fx = fx
     spec.fy = fy
+    if rows is not None:
+        spec.row_begin, spec.row_end = int(rows[0]), int(rows[1])
     return spec
 
 
@@ -170,12 +172,16 @@ class VolumeRenderer(nn.Module):
         return _VolumeRenderFunction.apply(features, self._render_spec(features, rays.origins.shape[0]),
                                            _rays_spec_from_rays(rays), self._get_options(fast), True)
 
-    def render_persp(self, features, c2w, width=800, height=800, fx=1111.111, fy=None, cuda=True, fast=False):
-        """Perspective image -> (height, width, D). Differentiable (renderer.py:310-366)."""
+    def render_persp(self, features, c2w, width=800, height=800, fx=1111.111, fy=None, cuda=True, fast=False,
+                     rows=None):
+        """Perspective image -> (height, width, D). Differentiable (renderer.py:310-366).
+        ``rows=(y0, y1)`` (svox_t_b200 extension) renders only that band of image rows -> (y1 - y0, width, D): one
+        frame split over several GPUs (svox_t_b200.dist.render_image_bands)."""
         self._require_cuda(cuda)
         fy = fx if fy is None else fy
-        return _VolumeRenderImageFunction.apply(features, self._render_spec(features, width * height),
-                                                _make_camera_spec(c2w, width, height, fx, fy),
+        n_rows = height if rows is None else rows[1] - rows[0]
+        return _VolumeRenderImageFunction.apply(features, self._render_spec(features, width * n_rows),
+                                                _make_camera_spec(c2w, width, height, fx, fy, rows),
                                                 self._get_options(fast), False)
 
     def render_persp_with_depth(self, features, c2w, width=800, height=800, fx=1111.111, fy=None, fast=False):

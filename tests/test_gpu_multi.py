@@ -39,6 +39,12 @@ def _worker(rank, world, port, q):
     r = sv.VolumeRenderer(tree)
     loss, grad = svd.render_step_sharded(r, feats, rays, lambda out, lo, hi: (out * g_t[lo:hi]).sum(), rank, world)
     torch.cuda.synchronize()
+    # one frame sharded by row bands, gathered on every rank == the frame rendered by one GPU
+    cam = torch.from_numpy(synth.synth_cameras(1)[0]).to(dev)
+    frame = svd.render_image_bands(r, feats.detach(), cam, 90, 61, 100.0, rank=rank, world=world)
+    frame_ok = bool(torch.equal(frame, r.render_persp(feats.detach(), cam, width=90, height=61, fx=100.0)))
+    imgs, (lo, hi) = svd.render_views_sharded(r, feats.detach(), [cam] * 3, 32, 24, 40.0, rank=rank, world=world)
+    assert len(imgs) == hi - lo and frame_ok
     if rank == 0:
         full = feats.detach().clone().requires_grad_(True)
         (r(full, rays) * g_t).sum().backward()

@@ -692,3 +692,32 @@ def test_sh_rgb_fast_path_vs_oracle(dev, B):
     oc, dc, vc = orc.camera_rays_ndc(c2w, fx, fx, W, H)
     assert frac_within(img.detach().cpu().numpy().reshape(-1, 4), orc.render_rays_fmt(T, f, oc, dc, vc, orc.FORMAT_SH, B)) >= 0.999
     assert rel_l2(feats.grad.cpu().numpy(), orc.render_rays_fmt_backward(T, f, oc, dc, vc, gi, orc.FORMAT_SH, B)) <= 1e-4
+
+
+def test_image_bands_tile_the_full_frame(dev):
+    """rows=(y0, y1) renders a band of the frame: bands tile the full image bit for bit (outputs and depth), and the
+    gradient of a band loss is the gradient of the same loss on those rows of the full frame."""
+    from svox_t_b200 import dist as svd
+    tr = synth.synth_tree(5, "ball")
+    D, W, H, fx = 8, 70, 53, 80.0
+    tree = make_tree(tr, D, dev)
+    feats = cu(synth.synth_features(tr["M"], D), dev)
+    cam = cu(synth.synth_cameras(1)[0], dev)
+    r = sv.VolumeRenderer(tree)
+    full = r.render_persp(feats, cam, width=W, height=H, fx=fx)
+    bounds = [svd.shard_image_rows(H, k, 3) for k in range(3)]
+    assert bounds[0][0] == 0 and bounds[-1][1] == H and all(b[0] % 8 == 0 for b in bounds)
+    bands = [r.render_persp(feats, cam, width=W, height=H, fx=fx, rows=b) for b in bounds]
+    assert torch.equal(torch.cat(bands, 0), full)
+    assert torch.equal(svd.render_image_bands(r, feats, cam, W, H, fx), full)           # one rank: the whole frame
+    y0, y1 = bounds[1]
+    g = torch.randn(y1 - y0, W, D, device=dev)
+    fa = feats.clone().requires_grad_(True)
+    (r.render_persp(fa, cam, width=W, height=H, fx=fx, rows=(y0, y1)) * g).sum().backward()
+    fb = feats.clone().requires_grad_(True)
+    gfull = torch.zeros(H, W, D, device=dev)
+    gfull[y0:y1] = g
+    (r.render_persp(fb, cam, width=W, height=H, fx=fx) * gfull).sum().backward()
+    assert float((fa.grad - fb.grad).norm() / fb.grad.norm()) < 1e-5
+    with pytest.raises(RuntimeError):
+        r.render_persp(feats, cam, width=W, height=H, fx=fx, rows=(8, H + 1))
