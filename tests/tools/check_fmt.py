@@ -1,14 +1,14 @@
 """Dev check on a B200: view-dependent formats + motion-feature render, CUDA path vs CPU oracle (and the golden fixture
 if present). Run: gpurun -- python tools/check_fmt.py [fixture.npz]"""
 import os, sys
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import numpy as np, torch
 import svox_t_b200 as sv
 from svox_t_b200 import csrc as C
 from oracle import oracle as orc
 
 dev = torch.device("cuda:0"); torch.cuda.set_device(0)
-path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "y_fmt_ball_L4.npz")
+path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(__file__), "..", "golden", "y_fmt_ball_L4.npz")
 z = np.load(path)
 cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 T = orc.Tree(z["child"], z["data"])

@@ -1,6 +1,6 @@
 """Per-step wall time vs GPU time of the e2e loop (dev tool)."""
 import os, sys, time, subprocess
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import numpy as np, torch
 import svox_t_b200 as sv
 from svox_t_b200 import synth

@@ -1,8 +1,8 @@
 """Config C4 (BASELINE.json): animated frame = LBS warp of 2^20 voxel centres + p2v splat (256^3) + octree rebuild
 to depth 8 from the warped points + 1920x1080 render with opacity and depth. Per-stage and total latency."""
 import os, sys, json
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
 import numpy as np, torch
 import svox_t_b200 as sv
 from svox_t_b200 import synth, csrc as C

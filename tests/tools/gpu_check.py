@@ -1,8 +1,8 @@
 """Development check on a B200: parity of the CUDA path against the C oracle and the compiled reference,
 plus first timings. Run: gpurun -- python tools/gpu_check.py"""
 import os, sys, time, json
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
 import numpy as np, torch
 import svox_t_b200 as sv
 from svox_t_b200 import synth, csrc as C

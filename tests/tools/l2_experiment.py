@@ -1,7 +1,7 @@
 """How fast are the march kernels when the feature / gradient tables fit in L2?  Same leaf size (depth 8), same ray
 recipe, smaller balls: r = 0.30 (C3: 243 MB table), 0.20, 0.15 (30 MB), 0.10. Prints ms and ns per hit sample."""
 import os, sys
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import numpy as np, torch
 import svox_t_b200 as sv
 from svox_t_b200 import synth, csrc as C

@@ -1,6 +1,6 @@
 """Small fixed workload for ncu: C3 tree (L=8 ball, D=32), Q random rays, fwd + bwd via the C-ABI mirror."""
 import os, sys
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import numpy as np, torch
 import svox_t_b200 as sv
 from svox_t_b200 import synth, csrc as C

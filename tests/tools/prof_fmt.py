@@ -1,7 +1,7 @@
 """Timing of the view-dependent (SH9) render on the C3 tree against the reference's CUDA kernels (dev tool)."""
 import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
 import numpy as np, torch
 import svox_t_b200 as sv
 from svox_t_b200 import synth

@@ -1,7 +1,7 @@
 """Odd feature widths (scalar-lane kernels) against the reference's CUDA kernels, C3 tree (dev tool)."""
 import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
 import numpy as np, torch
 import svox_t_b200 as sv
 from svox_t_b200 import synth, csrc as C

@@ -1,8 +1,8 @@
 """Timing of the render variants against the reference's CUDA kernels on the C3 tree (dev tool): motion-feature render,
 opacity render, depth, motion render, SG format, point query."""
 import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
 import numpy as np, torch
 import svox_t_b200 as sv
 from svox_t_b200 import synth, csrc as C

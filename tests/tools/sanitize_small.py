@@ -1,6 +1,6 @@
 """Small end-to-end run for compute-sanitizer: every kernel family once on tiny inputs."""
 import os, sys
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import numpy as np, torch
 import svox_t_b200 as sv
 from svox_t_b200 import synth, csrc as C

@@ -1,7 +1,7 @@
 """Config C5 (BASELINE.json): depth-10 shell octree (~30M leaves), 64-channel features, 1920x1080 views.
 Checks a ray sample against the oracle and times image renders + a random-ray fwd/bwd step."""
 import os, sys, time, json
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import numpy as np, torch
 import svox_t_b200 as sv
 from svox_t_b200 import synth, csrc as C
