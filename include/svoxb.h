@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SVOXB_ABI_VERSION 5
+#define SVOXB_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define SVOXB_API __attribute__((visibility("default")))
@@ -72,8 +72,9 @@ typedef struct svoxb_tree {
     int32_t extra_cols;
     const float* transformation_matrices; /* optional [M,4,4]: per-row rotation of the view direction before the     */
                                 /* basis is evaluated (rt_kernel.cu:283-291). No effect for RGBA.                    */
-    int32_t features_act_stride;/* row stride of features_act in floats: 0 or D, or D rounded up to a multiple of 4 -- */
-                                /* the padded form lets widths with D % 4 != 0 use the 128-bit row kernels        */
+    int32_t features_act_stride;/* row stride of features_act in floats: 0 or D; for D % 4 != 0 the table holds the D-1   */
+                                /* payload channels only, stride = D-1 rounded up to a multiple of 4 (aligned rows)   */
+    const float* features_sigma;/* ... and the sigma channel travels as this compact [M] array (svoxb_activate_features)*/
     int32_t accel_marks_current;/* non-zero: the caller asserts that svoxb_accel_mark_hits(accel, features, ...) ran     */
                                 /* after the last change of `features`; the march then skips rows marked sigma <= 0   */
 } svoxb_tree;
@@ -130,11 +131,13 @@ SVOXB_API int svoxb_accel_mark_hits(svoxb_accel* accel, const float* features, i
 /* out[i, c] = sigmoid(features[i, c]) for c < D-1, out[i, D-1] = features[i, D-1] (sigma stays raw). A leaf row is
  * visited by ~77 rays in the reference's headline configuration, so applying the sigmoid once per row instead of once
  * per visit removes almost all transcendental work from the march. One streaming pass over the table. */
-/* out_stride (floats): 0 or D for the plain [M, D] layout; D rounded up to a multiple of 4 writes 16-byte aligned rows
- * with zero padding (pass the same value in svoxb_tree.features_act_stride): with it, widths with D % 4 != 0 run on the
- * 128-bit row kernels (D = 33: 3.5x faster than the scalar-lane kernels). */
+/* out_stride (floats): 0 or D writes the plain [M, D] layout (sigma_out ignored). For D % 4 != 0 pass
+ * out_stride = D-1 rounded up to a multiple of 4 and sigma_out[M]: the table then holds the activated payload channels
+ * in 16-byte aligned, zero-padded rows and sigma goes to the compact array (svoxb_tree.features_act_stride /
+ * features_sigma). With them every width runs on the 128-bit row kernels: D = 33 costs what D = 32 costs plus one
+ * 4-byte gather per sample, instead of 4x as much on the scalar-lane kernels. */
 SVOXB_API int svoxb_activate_features(const float* features, int64_t M, int32_t D, float* out, int32_t out_stride,
-                            void* stream);
+                            float* sigma_out, void* stream);
 
 /* ---- octree descent ---------------------------------------------------------------------------- */
 /* query_vertical, first kernel (svox_kernel.cu:66-81, 274-302): per point p (world coords) the leaf's packed

@@ -33,7 +33,7 @@ class _CTree(ctypes.Structure):
         ("features_act", ctypes.c_void_p),
         ("extra_data", ctypes.c_void_p), ("extra_rows", ctypes.c_int32), ("extra_cols", ctypes.c_int32),
         ("transformation_matrices", ctypes.c_void_p), ("features_act_stride", ctypes.c_int32),
-        ("accel_marks_current", ctypes.c_int32),
+        ("features_sigma", ctypes.c_void_p), ("accel_marks_current", ctypes.c_int32),
     ]
 
 
@@ -67,7 +67,7 @@ SYMBOLS = {
     "svoxb_accel_describe": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                             ctypes.POINTER(_I64)]),
     "svoxb_accel_mark_hits": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP]),
-    "svoxb_activate_features": (ctypes.c_int, [_VP, _I64, _I32, _VP, _I32, _VP]),
+    "svoxb_activate_features": (ctypes.c_int, [_VP, _I64, _I32, _VP, _I32, _VP, _VP]),
     "svoxb_query": (ctypes.c_int, [_PT, _VP, _I64, _VP, _VP, _VP, _VP, _VP]),
     "svoxb_leafset_scratch_bytes": (ctypes.c_size_t, [_I64]),
     "svoxb_leafset_scan": (ctypes.c_int, [_VP, _I64, _VP, _VP, _VP]),
@@ -111,7 +111,7 @@ def load_library():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.svoxb_abi_version() != 5:
+        if lib.svoxb_abi_version() != 6:
             raise ImportError("svox_t_b200: libsvoxb.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib
@@ -220,6 +220,7 @@ class TreeSpec:
             extra_cols=self.extra_data.shape[1] if self.extra_data is not None and self.extra_data.numel() else 0,
             transformation_matrices=_ptr(self.transformation_matrices),
             features_act_stride=act.table.shape[1] if act is not None else 0,
+            features_sigma=_ptr(act.sigma) if act is not None else ctypes.c_void_p(0),
             accel_marks_current=1 if acc is not None and acc.marks_match(self.features) else 0)
         return c
 
@@ -337,10 +338,16 @@ class Activated:
         _check_input(features, "features", torch.float32)
         self._key = self._make_key(features)
         M, D = features.shape
-        stride = (D + 3) // 4 * 4                  # padded rows are 16-byte aligned: any D runs on the 128-bit kernels
         with torch.cuda.device(features.device):
-            self.table = torch.empty((M, stride), dtype=torch.float32, device=features.device)
-            _check(lib.svoxb_activate_features(_ptr(features), M, D, _ptr(self.table), stride, _stream()))
+            if D % 4 == 0:
+                self.table, self.sigma = torch.empty_like(features), None
+                stride = D
+            else:       # payload-only aligned rows + compact sigma: every width runs on the 128-bit row kernels
+                stride = (D - 1 + 3) // 4 * 4
+                self.table = torch.empty((M, stride), dtype=torch.float32, device=features.device)
+                self.sigma = torch.empty((M,), dtype=torch.float32, device=features.device)
+            _check(lib.svoxb_activate_features(_ptr(features), M, D, _ptr(self.table), stride, _ptr(self.sigma),
+                                               _stream()))
 
     @staticmethod
     def _make_key(f):

@@ -78,7 +78,8 @@ struct TreeArgs {
     AccelView acc;
     int use_accel;
     const float* feat_act;   // optional pre-activated table (sigmoid applied to channels 0..D-2), or nullptr
-    int act_stride;          // its row stride in floats: D, or D rounded up to a multiple of 4 (padded, D % 4 != 0)
+    int act_stride;          // its row stride in floats: D (D % 4 == 0), else D-1 rounded up to a multiple of 4 (payload only)
+    const float* sigma_c;    // D % 4 != 0: compact sigma[M] that goes with the payload-only activated table
     uint32_t acc_miss_mask;  // ACC_MISS when the accelerator's hit marks are current for `features`, else 0
 };
 

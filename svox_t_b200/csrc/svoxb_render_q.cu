@@ -114,11 +114,6 @@ __device__ __forceinline__ float quad_reduce(float (&v)[NB], int lane) {
     return r;
 }
 
-// Component `e` (0..3, warp-uniform) of a float4.
-__device__ __forceinline__ float comp4(const float4& v, int e) {
-    return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w));
-}
-
 template <int BITS>
 __device__ __forceinline__ constexpr unsigned low_mask() { return BITS >= 32 ? 0xffffffffu : ((1u << (BITS & 31)) - 1u); }
 
@@ -186,10 +181,12 @@ __device__ __forceinline__ RowBlk<V4> load_row_block(const char* p, uint64_t pol
 //   S4   flush finished rays, refill; the rows of batch 0 of the new candidates are requested first thing in the
 //        next iteration (S0), ahead of S1
 // AL (aligned): D % VEC == 0, rows are read in the caller's [M, D] layout (raw or activated). !AL: any other D -- the
-// rows come from the PADDED activated table (stride = D rounded up to a multiple of 4 floats, so they are 16-byte
-// aligned), sigma sits in the middle of its float4, and output rows are written channel by channel.
+// rows come from the PADDED activated table, which holds the D-1 payload channels only (stride = D-1 rounded up to a
+// multiple of 4 floats: 16-byte aligned rows, D = 33 is served like D = 32), sigma comes from the compact sigma[M]
+// array next to it (one 4-byte gather per candidate, L2-resident), and the output rows / gradient rows of the
+// caller's unaligned [M, D] layout are written channel by channel.
 template <int LPR, int V4, bool ACCEL, bool IMAGE, bool DEPTH, bool AL>
-__global__ void __launch_bounds__((DEPTH ? Quad<LPR, V4>::THREADS : Quad<LPR, V4>::FWD_THREADS), 1)   // depth: 80 registers
+__global__ void __launch_bounds__(((DEPTH || !AL) ? Quad<LPR, V4>::THREADS : Quad<LPR, V4>::FWD_THREADS), 1)   // 80 registers
 march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
                       unsigned long long* counter) {
     using G = Quad<LPR, V4>;
@@ -203,9 +200,8 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     float4* accs = reinterpret_cast<float4*>(smem_u32 + top_words) + (size_t)(threadIdx.x >> 5) * 32 * LPR * V4 + lane;
     static_assert(AL || V4 == 1, "padded rows use 128-bit blocks");
     const int q = lane / LPR, c = lane % LPR;
-    const int D = tr.D, DV = AL ? D / VEC : (D + VEC - 1) / VEC;
-    const int sig_e = AL ? 3 : (D - 1) & 3;              // component of sigma inside its float4
-    const bool lane_ok = c < DV, is_sig = c == DV - 1;
+    const int D = tr.D, DV = AL ? D / VEC : (D - 1 + VEC - 1) / VEC;
+    const bool lane_ok = c < DV, is_sig = AL && c == DV - 1;
     const int sig_src = (lane % RPI) * LPR + (DV - 1);   // lane that holds sigma of this owner lane's row
     const bool act = AL ? tr.feat_act != nullptr : true;
     const char* fbase = reinterpret_cast<const char*>(act ? tr.feat_act : tr.features) + 4 * VEC * min(c, DV - 1);
@@ -247,6 +243,8 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             const int idx = max(__shfl_sync(FULL, p_idx, RPI * jj + q), 0);
             x[jj] = load_row_block<V4, false>(fbase + (size_t)(unsigned)idx * row_bytes, 0);
         }
+        float sig_own = 0.0f;                                   // !AL: sigma of this lane's pending candidate
+        if constexpr (!AL) sig_own = __ldg(tr.sigma_c + max(p_idx, 0));
 
         // ---- S1 -------------------------------------------------------------------------------------------------
         bool trav = active && !trav_done;
@@ -272,11 +270,13 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             // ---- S2.b: composite ---------------------------------------------------------------------------------
             const unsigned bm = NBATCH == 1 ? pm : (pm >> ((RPB * b) & 31)) & low_mask<RPB>();
             if (bm) {
-                float sig = 0.0f;
+                float sig = sig_own;
+                if constexpr (AL) {
 #pragma unroll
-                for (int jj = 0; jj < NB; ++jj) {
-                    const float v = __shfl_sync(FULL, AL ? x[jj].v[V4 - 1].w : comp4(x[jj].v[0], sig_e), sig_src);
-                    if (lane / RPI == b * NB + jj) sig = v;
+                    for (int jj = 0; jj < NB; ++jj) {
+                        const float v = __shfl_sync(FULL, x[jj].v[V4 - 1].w, sig_src);
+                        if (lane / RPI == b * NB + jj) sig = v;
+                    }
                 }
                 float w = 0.0f;
                 if ((NBATCH == 1 || lane / RPB == b) && p_idx >= 0 && sig > opt.sigma_thresh) {
@@ -345,18 +345,18 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                                 float* orow = out + (int64_t)row_r * D;
                                 const float ve[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const int ch = 4 * c + e;
-                                    if (ch < D - 1) __stcs(orow + ch, ve[e]);
-                                    else if (ch == D - 1) __stcs(orow + ch, 1.0f - T_r);
-                                }
+                                for (int e = 0; e < 4; ++e)
+                                    if (4 * c + e < D - 1) __stcs(orow + 4 * c + e, ve[e]);
                             }
                             accs[(j * V4 + h) * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                     }
                 }
             }
-            if (fin != 0) active = false;
+            if (fin != 0) {
+                if constexpr (!AL) __stcs(out + (int64_t)row * D + (D - 1), 1.0f - T);   // opacity, by the owner lane
+                active = false;
+            }
             need = fm;
         }
     }
@@ -365,7 +365,11 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
 template <int LPR, int V4, bool ACCEL, bool IMAGE, bool AL>
 __global__ void __launch_bounds__((Quad<LPR, V4>::THREADS), 1)
 march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restrict__ grad_out,
-                      const float* __restrict__ saved_out, float* __restrict__ grad, unsigned long long* counter) {
+                      const float* __restrict__ saved_out, float* __restrict__ grad, float* __restrict__ grad_sigma,
+                      unsigned long long* counter) {
+    // AL: `grad` is the caller's [M, D] table. !AL: `grad` is a scratch table in the layout of the payload-only
+    // activated table (aligned rows of tr.act_stride floats -> red.v4) and `grad_sigma` a compact [M] array; the
+    // launcher folds both into the caller's table afterwards.
     using G = Quad<LPR, V4>;
     constexpr int RPI = G::RPI, NB = G::NB, NBATCH = G::NBATCH, RPB = G::RAYS_PER_BATCH, VEC = G::VEC, DP = G::DP;
     extern __shared__ uint32_t smem_u32[];
@@ -378,9 +382,8 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
     float* gs = reinterpret_cast<float*>(smem_u32 + top_words) + (size_t)warp * 32 * DP;
     static_assert(AL || V4 == 1, "padded rows use 128-bit blocks");
     const int q = lane / LPR, c = lane % LPR;
-    const int D = tr.D, DV = AL ? D / VEC : (D + VEC - 1) / VEC;
-    const int sig_e = AL ? 3 : (D - 1) & 3;
-    const bool lane_ok = c < DV, is_sig = c == DV - 1;
+    const int D = tr.D, DV = AL ? D / VEC : (D - 1 + VEC - 1) / VEC;
+    const bool lane_ok = c < DV, is_sig = AL && c == DV - 1;
     const int sig_src = (lane % RPI) * LPR + (DV - 1);
     const int red_src = (lane % RPI) * LPR + ((lane / RPI) % NB);     // lane holding this owner's reduced dot product
     const int swz = V4 == 2 ? (lane >> 2) & 1 : 0;
@@ -388,7 +391,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
     const char* fbase = reinterpret_cast<const char*>(act ? tr.feat_act : tr.features) + 4 * VEC * min(c, DV - 1);
     char* gbase = reinterpret_cast<char*>(grad) + 4 * VEC * c;
     const unsigned row_bytes = AL ? (unsigned)D * 4u : (unsigned)tr.act_stride * 4u;   // feature rows
-    const unsigned grow_bytes = (unsigned)D * 4u;                                      // gradient rows: caller's layout
+    const unsigned grow_bytes = row_bytes;                                             // gradient rows: same layout
     const float* off = tr.offset;
     const float* scl = tr.scaling;
 
@@ -417,19 +420,25 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                 const float* g = grad_out + (int64_t)row_r * D;
                 const float* so = saved_out + (int64_t)row_r * D;
                 float part = 0.0f, g_last = 0.0f, o_last = 0.0f;
+                const int DG = AL ? D : D - 1;                           // staged channels: !AL keeps the payload only
                 for (int e = lane; e < DP; e += 32) {
-                    const float gv = (e < D) ? __ldcs(g + e) : 0.0f;      // read once: do not let them displace the tables
-                    const float ov = (e < D) ? __ldcs(so + e) : 0.0f;
+                    const float gv = (e < DG) ? __ldcs(g + e) : 0.0f;     // read once: do not let them displace the tables
+                    const float ov = (e < DG) ? __ldcs(so + e) : 0.0f;
                     int slot = e >> 2;                                   // float4 slot inside the row
                     if (V4 == 2) slot ^= ((((r % RPI) * LPR + (e / VEC)) >> 2) & 1);   // reader lane = q*LPR + c
-                    gs[r * DP + 4 * slot + (e & 3)] = (!AL && e == D - 1) ? 0.0f : gv;   // padded rows: no masking later
+                    gs[r * DP + 4 * slot + (e & 3)] = gv;
                     if (e < D - 1) part = fmaf(gv, ov, part);
                     if (e == D - 1) { g_last = gv; o_last = ov; }
                 }
 #pragma unroll
                 for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(FULL, part, s);
-                g_last = __shfl_sync(FULL, g_last, (D - 1) & 31);
-                o_last = __shfl_sync(FULL, o_last, (D - 1) & 31);
+                if constexpr (AL) {
+                    g_last = __shfl_sync(FULL, g_last, (D - 1) & 31);
+                    o_last = __shfl_sync(FULL, o_last, (D - 1) & 31);
+                } else {
+                    g_last = __ldcs(g + (D - 1));
+                    o_last = __ldcs(so + (D - 1));
+                }
                 if (lane == r) { accum = part; T_end = 1.0f - o_last; gop = g_last; }
             }
             __syncwarp();
@@ -442,6 +451,8 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
             const int idx = max(__shfl_sync(FULL, p_idx, RPI * jj + q), 0);
             x[jj] = load_row_block<V4, SVOXB_BWD_HINTS != 0>(fbase + (size_t)(unsigned)idx * row_bytes, pol_first);
         }
+        float sig_own = 0.0f;
+        if constexpr (!AL) sig_own = __ldg(tr.sigma_c + max(p_idx, 0));
 
         // ---- S1 -------------------------------------------------------------------------------------------------
         bool trav = active && !trav_done;
@@ -466,11 +477,13 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
             // ---- S2.b: gradient of batch b of the pending candidates ------------------------------------------------
             const unsigned bm = NBATCH == 1 ? pm : (pm >> ((RPB * b) & 31)) & low_mask<RPB>();
             if (bm) {
-                float sig = 0.0f;
+                float sig = sig_own;
+                if constexpr (AL) {
 #pragma unroll
-                for (int jj = 0; jj < NB; ++jj) {
-                    const float v = __shfl_sync(FULL, AL ? x[jj].v[V4 - 1].w : comp4(x[jj].v[0], sig_e), sig_src);
-                    if (lane / RPI == b * NB + jj) sig = v;
+                    for (int jj = 0; jj < NB; ++jj) {
+                        const float v = __shfl_sync(FULL, x[jj].v[V4 - 1].w, sig_src);
+                        if (lane / RPI == b * NB + jj) sig = v;
+                    }
                 }
                 float w = 0.0f, dd = 0.0f;
                 const bool hit = (NBATCH == 1 || lane / RPB == b) && p_idx >= 0 && sig > 0.0f;   // rt_kernel.cu:382,456
@@ -506,6 +519,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                     if (hit) {
                         accum -= w * c_own;                                              // rt_kernel.cu:479-480
                         sgrad = dd * (c_own * T - accum) + dd * gop * T_end;             // rt_kernel.cu:486-490
+                        if constexpr (!AL) red_add_f32_hint(grad_sigma + p_idx, sgrad, pol_last);   // by the owner lane
                     }
 #pragma unroll
                     for (int jj = 0; jj < NB; ++jj) {
@@ -526,15 +540,9 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                                     red_add_v4(grow + 4 * h, w_j * t.x, w_j * t.y, w_j * t.z, last);
 #endif
                                 }
-                            } else {        // rows of the caller's gradient table are not 16-byte aligned: scalar reductions
+                            } else {        // payload-only scratch rows: padding lanes carry zeros (g is 0 there)
                                 const float4 t = sv[jj].v[0];
-                                const float te[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const int ch = 4 * c + e;
-                                    if (ch < D - 1) red_add_f32_hint(grow + e, w_j * te[e], pol_last);
-                                    else if (ch == D - 1) red_add_f32_hint(grow + e, sg_j, pol_last);
-                                }
+                                red_add_v4_hint(grow, w_j * t.x, w_j * t.y, w_j * t.z, w_j * t.w, pol_last);
                             }
                         }
                     }
@@ -563,7 +571,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
 bool quad_supported(const TreeArgs& tr) {
     if (tr.D < 2 || tr.D > 128) return false;
     if (tr.D % 4 == 0) return true;
-    return tr.feat_act != nullptr && tr.act_stride % 4 == 0 && tr.act_stride >= tr.D && tr.act_stride < tr.D + 4;
+    return tr.feat_act != nullptr && tr.sigma_c != nullptr && tr.act_stride == (tr.D - 1 + 3) / 4 * 4;
 }
 
 // Shared memory this one-CTA-per-SM kernel needs (+1 KB the runtime reserves per CTA), in KB; the rest of the SM's
@@ -592,7 +600,7 @@ template <int LPR, int V4, bool ACCEL, bool IMAGE, bool AL>
 static int launch_fwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
     using G = Quad<LPR, V4>;
-    const int threads = threads_for(depth ? G::THREADS : G::FWD_THREADS, src.total);
+    const int threads = threads_for((depth || !AL) ? G::THREADS : G::FWD_THREADS, src.total);
     const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * (threads / 32) * 32 * LPR * V4;
     void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
     if (depth) kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, true, AL>;
@@ -607,6 +615,21 @@ static int launch_fwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpt
     return check_cuda(cudaGetLastError(), "march_fwd_quad_kernel launch");
 }
 
+// grad[M, D] += (payload scratch rows, compact sigma gradients): folds the !AL backward's aligned scratch into the
+// caller's table. One thread per element of the caller's table.
+__global__ void __launch_bounds__(256)
+merge_padded_grad_kernel(const float* __restrict__ gpay, const float* __restrict__ gsig, int64_t M, int D, int S,
+                         float* __restrict__ grad) {
+    const int64_t n = M * D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / D;
+        const int c = (int)(i - r * D);
+        grad[i] += c < D - 1 ? gpay[r * S + c] : gsig[r];
+    }
+}
+
+int scratch_alloc(void** p, size_t bytes, cudaStream_t st);   // svoxb_tree.cu: stream-ordered pool
+
 template <int LPR, int V4, bool ACCEL, bool IMAGE, bool AL>
 static int launch_bwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const float* go, const float* so,
                         float* grad, cudaStream_t st) {
@@ -619,9 +642,28 @@ static int launch_bwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpt
     if (rc) return rc;
     unsigned long long* counter = work_counter(st);
     if (!counter) return SVOXB_ECUDA;
-    kern<<<grid, threads, smem, st>>>(tr, src, m, go, so, grad, counter);
-    count_launch();
-    return check_cuda(cudaGetLastError(), "march_bwd_quad_kernel launch");
+    if constexpr (AL) {
+        kern<<<grid, threads, smem, st>>>(tr, src, m, go, so, grad, nullptr, counter);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "march_bwd_quad_kernel launch");
+    } else {
+        // The caller's rows (D floats) are not 16-byte aligned: reduce into an aligned scratch copy (stream-ordered
+        // pool memory, released in stream order) with red.v4, then fold it into the caller's table in one pass.
+        const size_t pay = sizeof(float) * (size_t)tr.M * tr.act_stride, sig = sizeof(float) * (size_t)tr.M;
+        float* scratch = nullptr;
+        if ((rc = scratch_alloc((void**)&scratch, pay + sig, st))) return rc;
+        float* gsig = scratch + (size_t)tr.M * tr.act_stride;
+        cudaError_t e = cudaMemsetAsync(scratch, 0, pay + sig, st);
+        if (e == cudaSuccess) {
+            kern<<<grid, threads, smem, st>>>(tr, src, m, go, so, scratch, gsig, counter);
+            const int mg = (int)min(((int64_t)tr.M * tr.D + 255) / 256, (int64_t)sm_count() * 16);
+            merge_padded_grad_kernel<<<mg, 256, 0, st>>>(scratch, gsig, tr.M, tr.D, tr.act_stride, grad);
+            count_launch(2);
+            e = cudaGetLastError();
+        }
+        cudaFreeAsync(scratch, st);
+        return check_cuda(e, "march_bwd_quad_kernel (padded) launch");
+    }
 }
 
 #define SVOXB_Q_CASES(FN, L, V, ...)                                                                   \
@@ -655,7 +697,7 @@ static int launch_bwd_q(const TreeArgs& tr, const RaySource& src, const MarchOpt
 #define SVOXB_Q_DISPATCH(FN, wide, ...)                                                                \
     do {                                                                                               \
         if (tr.D % 4 != 0) {                                                                           \
-            const int lpr = pow2ceil((tr.D + 3) / 4);                                                  \
+            const int lpr = pow2ceil((tr.D - 1 + 3) / 4);                                              \
             switch (lpr * 4 + ((tr.use_accel ? 2 : 0) | (image ? 1 : 0))) {                            \
                 SVOXB_Q_PAD_CASES(FN, 1, __VA_ARGS__) SVOXB_Q_PAD_CASES(FN, 2, __VA_ARGS__)            \
                 SVOXB_Q_PAD_CASES(FN, 4, __VA_ARGS__) SVOXB_Q_PAD_CASES(FN, 8, __VA_ARGS__)            \

@@ -112,9 +112,15 @@ int make_tree_args(const svoxb_tree* t, TreeArgs& a) {
     a.use_accel = 0;
     a.feat_act = t->M > 0 ? t->features_act : nullptr;
     a.act_stride = t->features_act_stride > 0 ? t->features_act_stride : t->D;
-    SVOXB_REQUIRE(a.feat_act == nullptr || a.act_stride == t->D || (a.act_stride % 4 == 0 && a.act_stride > t->D &&
-                  a.act_stride < t->D + 4), "features_act_stride=%d must be D or D rounded up to a multiple of 4",
-                  a.act_stride);
+    a.sigma_c = t->M > 0 ? t->features_sigma : nullptr;
+    if (a.feat_act != nullptr) {
+        if (t->D % 4 == 0)
+            SVOXB_REQUIRE(a.act_stride == t->D, "features_act_stride=%d must be D=%d", a.act_stride, t->D);
+        else
+            SVOXB_REQUIRE(a.act_stride == (t->D - 1 + 3) / 4 * 4 && a.sigma_c != nullptr,
+                          "D %% 4 != 0: features_act must be the payload-only table (stride %d) with features_sigma",
+                          (t->D - 1 + 3) / 4 * 4);
+    }
     a.acc_miss_mask = 0;
     memset(&a.acc, 0, sizeof(a.acc));
     if (t->accel) {
@@ -210,19 +216,17 @@ activate_kernel(const float* __restrict__ f, int64_t n, int D, float* __restrict
     }
 }
 
-// Padded output rows (stride S = D rounded up to a multiple of 4): one thread per output float, zeros in the padding.
+// Payload-only rows (stride S = D-1 rounded up to a multiple of 4, zeros in the padding) + the compact sigma array:
+// one thread per output float.
 __global__ void __launch_bounds__(256)
-activate_padded_kernel(const float* __restrict__ f, int64_t M, int D, int S, float* __restrict__ out) {
+activate_padded_kernel(const float* __restrict__ f, int64_t M, int D, int S, float* __restrict__ out,
+                       float* __restrict__ sigma) {
     const int64_t n = M * S;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / S;
         const int c = (int)(i - r * S);
-        float v = 0.0f;
-        if (c < D) {
-            v = __ldg(f + r * D + c);
-            if (c < D - 1) v = fast_sigmoid(v);
-        }
-        out[i] = v;
+        out[i] = c < D - 1 ? fast_sigmoid(__ldg(f + r * D + c)) : 0.0f;
+        if (c == 0) sigma[r] = __ldg(f + r * D + (D - 1));
     }
 }
 
@@ -429,6 +433,10 @@ static int pool_alloc(void** p, size_t bytes, cudaStream_t st) {
     return check_cuda(cudaMallocAsync(p, bytes ? bytes : 4, st), "cudaMallocAsync");
 }
 
+namespace svoxb {
+int scratch_alloc(void** p, size_t bytes, cudaStream_t st) { return pool_alloc(p, bytes, st); }
+}  // namespace svoxb
+
 static int* pinned_scalars() {
     static thread_local int* h = nullptr;
     if (!h && cudaHostAlloc(&h, sizeof(int) * 8, cudaHostAllocDefault) != cudaSuccess) h = nullptr;
@@ -572,18 +580,19 @@ extern "C" int svoxb_accel_mark_hits(svoxb_accel* a, const float* features, int6
 }
 
 extern "C" int svoxb_activate_features(const float* features, int64_t M, int32_t D, float* out, int32_t out_stride,
-                                       void* stream) {
+                                       float* sigma_out, void* stream) {
     SVOXB_REQUIRE(M >= 0 && D >= 2, "bad sizes");
     if (out_stride <= 0) out_stride = D;
-    SVOXB_REQUIRE(out_stride == D || (out_stride % 4 == 0 && out_stride > D && out_stride < D + 4),
-                  "out_stride=%d must be D or D rounded up to a multiple of 4", out_stride);
+    const int payload = (D - 1 + 3) / 4 * 4;
+    SVOXB_REQUIRE(out_stride == D || (out_stride == payload && sigma_out != nullptr),
+                  "out_stride=%d must be D, or %d (payload only) together with sigma_out", out_stride, payload);
     if (M == 0) return 0;
     SVOXB_REQUIRE(features && out, "NULL tensor");
     const int64_t n = M * D;
     cudaStream_t st = (cudaStream_t)stream;
-    if (out_stride != D) {
+    if (sigma_out != nullptr && out_stride == payload) {
         const int grid = (int)min((M * out_stride + 255) / 256, (int64_t)sm_count() * 16);
-        activate_padded_kernel<<<grid, 256, 0, st>>>(features, M, D, out_stride, out);
+        activate_padded_kernel<<<grid, 256, 0, st>>>(features, M, D, out_stride, out, sigma_out);
     } else if (D % 4 == 0 && (((uintptr_t)features | (uintptr_t)out) & 15) == 0) {
         const int grid = (int)min((n / 4 + 255) / 256, (int64_t)sm_count() * 16);
         activate4_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(features), n / 4, D / 4,

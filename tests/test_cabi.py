@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), f"{name} declared in include/svoxb.h but not exported by libsvoxb.so"
     assert sorted(C.SYMBOLS) == declared_symbols(), "python prototypes out of sync with include/svoxb.h"
-    assert lib.svoxb_abi_version() == 5
+    assert lib.svoxb_abi_version() == 6
 
 
 def test_struct_layouts_match_header():
@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     assert [f[0] for f in C._COptions._fields_] == ["step_size", "background_brightness", "format", "basis_dim",
                                                     "ndc_width", "ndc_height", "ndc_focal", "min_comp", "max_comp",
                                                     "sigma_thresh", "stop_thresh"]
-    assert ctypes.sizeof(C._CTree) == 128 and ctypes.sizeof(C._CCamera) == 32
+    assert ctypes.sizeof(C._CTree) == 144 and ctypes.sizeof(C._CCamera) == 32
 
 
 def test_ctypes_structs_match_the_header_as_gcc_lays_it_out(tmp_path):
