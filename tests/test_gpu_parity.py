@@ -721,3 +721,38 @@ def test_image_bands_tile_the_full_frame(dev):
     assert float((fa.grad - fb.grad).norm() / fb.grad.norm()) < 1e-5
     with pytest.raises(RuntimeError):
         r.render_persp(feats, cam, width=W, height=H, fx=fx, rows=(8, H + 1))
+
+
+@pytest.mark.parametrize("D", [2, 3, 5, 6, 7, 9, 13, 17, 31, 33, 63, 65, 127, 128])
+def test_every_width_rays_and_images_vs_oracle(dev, D):
+    """Sweep of feature widths through the large-batch path (activated table, hit marks; D % 4 != 0: payload-only table,
+    compact sigma, scratch gradients): explicit rays and camera images, default and `fast` thresholds, depth."""
+    tr = synth.synth_tree(5, "ball")
+    T = orc.Tree(tr["child"], tr["data"])
+    f = synth.synth_features(tr["M"], D, seed=D)
+    tree = make_tree(tr, D, dev)
+    r = sv.VolumeRenderer(tree, background_brightness=0.4)
+    rng = np.random.default_rng(D)
+    Q = 2048                                                   # Q * 32 >= M: the renderer attaches the derived tables
+    o, d = synth.synth_rays(Q, seed=D)
+    g = rng.standard_normal((Q, D)).astype(np.float32)
+    for fast in (False, True):
+        thr = 1e-2 if fast else 0.0
+        feats = cu(f, dev).requires_grad_(True)
+        out, depth = r.forward_with_depth(feats, sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev)), fast=fast)
+        (out * cu(g, dev)).sum().backward()
+        o_ref, d_ref = orc.render_rays(T, f, o, d, background_brightness=0.4, sigma_thresh=thr, stop_thresh=thr)
+        g_ref = orc.render_rays_backward(T, f, o, d, g, background_brightness=0.4)
+        assert_render_parity(out.detach().cpu().numpy(), depth.cpu().numpy()[:, 0], feats.grad.cpu().numpy(),
+                             o_ref, d_ref, g_ref)
+    W, H, fx = 61, 43, 70.0
+    c2w = synth.synth_cameras(1)[0]
+    oc, dc = orc.camera_rays(c2w, fx, fx, W, H)
+    gi = rng.standard_normal((H * W, D)).astype(np.float32)
+    feats = cu(f, dev).requires_grad_(True)
+    img, dep = r.render_persp_with_depth(feats, cu(c2w, dev), width=W, height=H, fx=fx)
+    (img * cu(gi, dev).view(H, W, D)).sum().backward()
+    o_ref, d_ref = orc.render_rays(T, f, oc, dc, background_brightness=0.4)
+    assert_render_parity(img.detach().cpu().numpy().reshape(-1, D), dep.cpu().numpy().reshape(-1),
+                         feats.grad.cpu().numpy(), o_ref, d_ref,
+                         orc.render_rays_backward(T, f, oc, dc, gi, background_brightness=0.4))
