@@ -7,6 +7,7 @@
 // exact because *2 / floor / subtract are exact in binary floating point).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdint.h>
 #include "../../include/svoxb.h"
 
@@ -85,6 +86,14 @@ struct TreeArgs {
 
 // ---- device math ----------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// Debug build (make debug / -DSVOXB_DEBUG): index checks that trap the kernel. compute-sanitizer is not available on
+// the target pool, so the test-suite is run once against this build instead (tests/tools/README in DESIGN.md section 2).
+#ifdef SVOXB_DEBUG
+#define SVOXB_DBG(cond) do { if (!(cond)) { printf("svoxb: check failed %s:%d: %s\n", __FILE__, __LINE__, #cond); __trap(); } } while (0)
+#else
+#define SVOXB_DBG(cond) do { } while (0)
+#endif
 
 // include/common.cuh:37-42. The reference clamps in double against 1.0 - 1e-6 and rounds back to float;
 // for float inputs that is exactly min(q, (float)(1.0 - 1e-6)) followed by max(0, .).

@@ -244,6 +244,7 @@ __device__ __forceinline__ void probe_end(const TreeArgs& tr, const Probe& pb, c
         }
         const int d = (int)(cell >> ACC_DEPTH_SHIFT) & 0xf;
         const uint32_t ci = cell & ACC_IDX_MASK;
+        SVOXB_DBG(!(cell & ACC_PTR) && (ci == ACC_EMPTY || (int64_t)ci < tr.M));
         // rows marked "sigma <= 0" are not candidates: no row fetch, exactly what the hit predicate would decide
         idx = (ci == ACC_EMPTY || (cell & tr.acc_miss_mask)) ? -1 : (int)ci;
         const float sc = __int_as_float((127 + d) << 23);

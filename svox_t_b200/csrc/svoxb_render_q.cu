@@ -241,6 +241,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
 #pragma unroll
         for (int jj = 0; jj < NB; ++jj) {
             const int idx = max(__shfl_sync(FULL, p_idx, RPI * jj + q), 0);
+            SVOXB_DBG((int64_t)idx < max(tr.M, (int64_t)1));
             x[jj] = load_row_block<V4, false>(fbase + (size_t)(unsigned)idx * row_bytes, 0);
         }
         float sig_own = 0.0f;                                   // !AL: sigma of this lane's pending candidate
@@ -264,6 +265,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
 #pragma unroll
                 for (int jj = 0; jj < NB; ++jj) {
                     const int idx = max(__shfl_sync(FULL, p_idx, RPI * (b * NB + jj) + q), 0);
+                    SVOXB_DBG((int64_t)idx < max(tr.M, (int64_t)1));
                     x[jj] = load_row_block<V4, false>(fbase + (size_t)(unsigned)idx * row_bytes, 0);
                 }
             }
@@ -326,6 +328,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                     const float T_r = __shfl_sync(FULL, T, r);
                     const int fin_r = __shfl_sync(FULL, fin, r);
                     const int row_r = __shfl_sync(FULL, row, r);
+                    SVOXB_DBG(fin_r == 0 || (row_r >= 0 && (IMAGE ? row_r < src.width * (src.row_end - src.row_begin) : row_r < src.total)));
                     if (fin_r != 0) {
 #pragma unroll
                         for (int h = 0; h < V4; ++h) {
@@ -449,6 +452,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
 #pragma unroll
         for (int jj = 0; jj < NB; ++jj) {
             const int idx = max(__shfl_sync(FULL, p_idx, RPI * jj + q), 0);
+            SVOXB_DBG((int64_t)idx < max(tr.M, (int64_t)1));
             x[jj] = load_row_block<V4, SVOXB_BWD_HINTS != 0>(fbase + (size_t)(unsigned)idx * row_bytes, pol_first);
         }
         float sig_own = 0.0f;
@@ -471,6 +475,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
 #pragma unroll
                 for (int jj = 0; jj < NB; ++jj) {
                     const int idx = max(__shfl_sync(FULL, p_idx, RPI * (b * NB + jj) + q), 0);
+                    SVOXB_DBG((int64_t)idx < max(tr.M, (int64_t)1));
                     x[jj] = load_row_block<V4, SVOXB_BWD_HINTS != 0>(fbase + (size_t)(unsigned)idx * row_bytes, pol_first);
                 }
             }
@@ -528,6 +533,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                         const float sg_j = __shfl_sync(FULL, sgrad, r);
                         const int idx_j = __shfl_sync(FULL, p_idx, r);
                         if (((hb >> r) & 1u) && lane_ok) {
+                            SVOXB_DBG(idx_j >= 0 && (int64_t)idx_j < tr.M);
                             float* grow = reinterpret_cast<float*>(gbase + (size_t)(unsigned)idx_j * grow_bytes);
                             if constexpr (AL) {
 #pragma unroll

@@ -5,10 +5,11 @@ import numpy as np, torch
 import svox_t_b200 as sv
 from svox_t_b200 import synth, csrc as C
 dev = torch.device("cuda:0"); torch.cuda.set_device(0)
-for (L, shape, D, accel) in [(4, "ball", 32, True), (3, "ball", 16, False), (4, "ball", 64, True), (3, "ball", 9, True), (5, "shell", 100, True)]:
+for (L, shape, D, accel) in [(4, "ball", 32, True), (3, "ball", 16, False), (4, "ball", 64, True), (3, "ball", 9, True),
+                             (5, "shell", 100, True), (4, "ball", 33, True), (4, "ball", 2, True), (4, "ball", 127, False)]:
     tr = synth.synth_tree(L, shape, r_out=0.45, r_in=0.2)
     f = synth.synth_features(tr["M"], D)
-    o, d = synth.synth_rays(700)
+    o, d = synth.synth_rays(2100)          # > M / 32: the renderer attaches the activated table and the hit marks
     tree = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=D, map_location=dev)
     tree.extra_data = torch.rand(4, 3, device=dev)
     feats = torch.from_numpy(f).to(dev).requires_grad_(True)
@@ -31,5 +32,24 @@ t3.construct_tree(pts)
 Tm, w, ji = synth.synth_skeleton(3000)
 wv, mats = sv.warp_vertices(torch.from_numpy(Tm).to(dev), pts, torch.from_numpy(w).to(dev), torch.from_numpy(ji).to(dev))
 sv.voxelize(wv, torch.rand(3000, 4, device=dev), torch.zeros(3, device=dev), torch.ones(3, device=dev), 32, 0.05, 0.07)
+# view-dependent formats, motion feature, weight accumulation, image bands
+tr = synth.synth_tree(4, "ball"); M = tr["M"]
+o, d = synth.synth_rays(900)
+rays = sv.Rays(*(torch.from_numpy(a).to(dev) for a in (o, d, d)))
+for fmt, D in (("SH9", 28), ("SH4", 13), ("SG3", 10), ("SH4", 21)):
+    tree = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=D, data_format=fmt, map_location=dev)
+    tree.extra_data = torch.rand(3, 4, device=dev) + 0.5
+    feats = torch.randn(M, D, device=dev, requires_grad=True)
+    r = sv.VolumeRenderer(tree)
+    r(feats, rays, transformation_matrices=torch.eye(4, device=dev).repeat(M, 1, 1).contiguous()).sum().backward()
+    r.render_persp(feats, torch.from_numpy(synth.synth_cameras(1)[0]).to(dev), width=29, height=19, fx=25.0, rows=(8, 19)).sum().backward()
+tree = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=6, map_location=dev)
+feats = torch.randn(M, 6, device=dev)
+r = sv.VolumeRenderer(tree)
+jf = torch.randn(5, 7, device=dev, requires_grad=True)
+sw = torch.rand(M, 3, device=dev); ji = torch.randint(0, 5, (M, 3), device=dev, dtype=torch.int32)
+r.motion_feature_render(feats, jf, sw, ji, rays).sum().backward()
+with tree.accumulate_weights() as acc:
+    r(feats, rays); r.render_persp(feats, torch.from_numpy(synth.synth_cameras(1)[0]).to(dev), width=29, height=19, fx=25.0)
 torch.cuda.synchronize()
 print("sanitize_small done, launches", C.launch_count())
