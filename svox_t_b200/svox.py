@@ -322,6 +322,60 @@ class N3Tree(nn.Module):
             ts._accel = self.accel(features)
         return ts
 
+    # ---- copies / small accessors (svox.py:288-350, 600-645, 784-803) ------------------------------------------
+    def snap(self, indices):
+        """Lowest corner (world space) of the leaf that holds each point (svox.py:288-297)."""
+        view = self[indices]
+        per_leaf = view.corners                                   # one row per unique leaf, increasing slot order
+        packed = self._pack_index(view.unique_leaf_node)
+        return per_leaf[torch.searchsorted(packed, view.leaf_node_id)]
+
+    def clone(self, device=None):
+        """Deep copy, optionally onto another device (svox.py:299-350; the data channels of this fork are row indices,
+        so the reference's channel selector of partial() has nothing to select and is not offered)."""
+        dev = self.data.device if device is None else device
+        t2 = N3Tree(N=self.N, data_dim=self.data_dim, depth_limit=self.depth_limit, geom_resize_fact=self.geom_resize_fact,
+                    data_format=repr(self.data_format) if self.data_format is not None else None,
+                    extra_data=self.extra_data.clone() if self.extra_data is not None else None, map_location=dev)
+        for name in ("child", "data", "parent_depth", "invradius", "offset", "_n_internal", "_n_free"):
+            setattr(t2, name, getattr(self, name).detach().clone().to(dev))
+        t2.features = nn.Parameter(self.features.detach().clone().to(dev))
+        t2.filled = self.filled
+        t2._invalidate()
+        return t2
+
+    def partial(self, data_sel=None, device=None):
+        if data_sel is not None:
+            raise RuntimeError("svox_t_b200: partial(data_sel) selects float data channels, which this fork's index-valued "
+                               "`data` tensor does not have; use clone()")
+        return self.clone(device)
+
+    def shrink_to_fit(self):
+        """Drop the unused capacity of child / data / parent_depth (svox.py:600-643). Returns True if anything shrank.
+        (This implementation never frees nodes, so there is no fragmentation to compact.)"""
+        if self._lock_tree_structure:
+            raise RuntimeError("Tree locked")
+        n = self.filled
+        if n >= self.capacity:
+            return False
+        self.child, self.data, self.parent_depth = (t[:n].contiguous() for t in (self.child, self.data, self.parent_depth))
+        self._invalidate()
+        return True
+
+    @property
+    def ndim(self):
+        return 2
+
+    @property
+    def shape(self):
+        return torch.Size((self.n_leaves, self.data_dim))
+
+    def size(self, dim):
+        return self.data_dim if dim == 1 else self.n_leaves
+
+    def numel(self):
+        return self.data_dim * self.n_leaves
+
     def accumulate_weights(self):
         """``with tree.accumulate_weights() as accum: render(...)`` then ``accum()`` -> per-leaf sum of the compositing
         weights of every ray rendered inside the block, in ``tree[:]`` order (svox.py:664-677, 948-970)."""

@@ -756,3 +756,18 @@ def test_every_width_rays_and_images_vs_oracle(dev, D):
     assert_render_parity(img.detach().cpu().numpy().reshape(-1, D), dep.cpu().numpy().reshape(-1),
                          feats.grad.cpu().numpy(), o_ref, d_ref,
                          orc.render_rays_backward(T, f, oc, dc, gi, background_brightness=0.4))
+
+
+def test_snap_and_clone_on_device(dev):
+    tr = synth.synth_tree(4, "ball")
+    tree = make_tree(tr, 4, dev)
+    pts = torch.rand(500, 3, device=dev)
+    corners = tree.snap(pts)
+    view = tree[pts]
+    lengths = view.lengths[torch.searchsorted(tree._pack_index(view.unique_leaf_node), view.leaf_node_id)]
+    assert corners.shape == (500, 3)
+    assert bool(((pts >= corners - 1e-6) & (pts < corners + lengths + 1e-6)).all())
+    c2 = tree.clone()
+    assert c2.child.is_cuda and torch.equal(c2.child, tree.child) and c2.child.data_ptr() != tree.child.data_ptr()
+    cpu = tree.clone(device="cpu")
+    assert not cpu.child.is_cuda and torch.equal(cpu.data, tree.data.cpu())

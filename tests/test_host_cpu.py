@@ -154,3 +154,18 @@ def test_loads_a_checkpoint_written_by_the_reference(tmp_path):
     for k in z.files:
         assert z2[k].shape == z[k].shape and z2[k].dtype.kind == z[k].dtype.kind, k
         assert np.array_equal(z2[k], z[k]), k
+
+
+def test_clone_shrink_and_shape_accessors():
+    t = sv.N3Tree(N=2, data_dim=6, init_reserve=100, extra_data=torch.ones(2, 3))
+    t.refine()
+    t.refine()
+    assert t.capacity == 100 and t.filled == 73 and (t.ndim, tuple(t.shape), t.size(0), t.size(1), t.numel()) == (2, (512, 6), 512, 6, 3072)
+    u = t.clone()
+    assert u is not t and u.filled == t.filled and torch.equal(u.child, t.child) and torch.equal(u.data, t.data)
+    assert torch.equal(u.extra_data, t.extra_data) and u.features.data_ptr() != t.features.data_ptr()
+    u.refine()
+    assert u.filled > t.filled                                  # the copy is independent
+    assert t.shrink_to_fit() and t.capacity == t.filled == 73 and not t.shrink_to_fit()
+    with pytest.raises(RuntimeError):
+        t.partial(data_sel=-1)
