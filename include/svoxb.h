@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SVOXB_ABI_VERSION 6
+#define SVOXB_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define SVOXB_API __attribute__((visibility("default")))
@@ -160,6 +160,25 @@ SVOXB_API int svoxb_leafset_emit(const uint8_t* slot_mask, int64_t n_slots, int3
 /* construct_tree (svox_kernel.cu:110-121, 341-352): data[leaf(p_i)] = i. data_mut aliases tree->data. */
 SVOXB_API int svoxb_construct_tree(const svoxb_tree* tree, int32_t* data_mut, const float* pts, int64_t P, void* stream);
 
+/* query_vertical_backward (svox_kernel.cu:83-95, 380-403): grad_data[row(p_q), 0:K] += grad_out[q, 0:K] for every
+ * point whose leaf holds a row; grad_data[M, K] is accumulated into (the caller zero-fills it, as the reference's
+ * torch::zeros does). The reference's own kernel faults on a null data_id (svox_kernel.cu:61-62); this is the
+ * computation its source states. */
+SVOXB_API int svoxb_query_bwd(const svoxb_tree* tree, const float* pts, int64_t Q, const float* grad_out, int32_t K,
+                    float* grad_data, void* stream);
+
+/* assign_vertical (svox_kernel.cu:97-108, 326-339): features[row(p_q), 0:K] = values[q, 0:K], K <= D. features_mut
+ * aliases tree->features. Where the reference lets racing threads interleave ("only one of them will be taken",
+ * svox.py:172-173) the largest point index wins a shared leaf here, whole rows at a time (M ints of stream-ordered
+ * scratch). */
+SVOXB_API int svoxb_assign(const svoxb_tree* tree, float* features_mut, const float* pts, int64_t Q,
+                 const float* values, int32_t K, void* stream);
+
+/* calc_corners (svox_kernel.cu:213-237, 436-457): lower corner, in tree coordinates [0,1)^3, of each cell
+ * indexer[q] = [node, i, j, k] (int64), walking parent_depth[n_nodes, 2] up to the root. out[Q, 3]. */
+SVOXB_API int svoxb_calc_corners(const int32_t* parent_depth, int32_t N, int64_t n_nodes, const int64_t* indexer,
+                       int64_t Q, float* out, void* stream);
+
 /* ---- ray march --------------------------------------------------------------------------------- */
 /* volume_render (rt_kernel.cu:654-671, 1362-1379) fused with render_depth (rt_kernel.cu:865-882, 1506-1523):
  * out[Q, Do] with Do = svoxb_out_data_dim(): RGBA: D-1 composited sigmoid features + opacity (1 - T);
@@ -229,6 +248,15 @@ SVOXB_API int svoxb_motion_feature_render_bwd(const svoxb_tree* tree, const floa
                                     const svoxb_render_options* opt, const float* joint_features,
                                     const float* skinning_weights, const int32_t* joint_index, int32_t J, int32_t F,
                                     int32_t B, const float* grad_out, float* grad_joint_features, void* stream);
+
+/* grid_weight_render (rt_kernel.cu:1240-1344, 1454-1478): the camera's pixel rays (NDC when opt->ndc_width >= 0)
+ * marched through a dense sigma grid[reso, reso, reso] spanning the tree cube; grid_weight[cell] = max compositing
+ * weight T (1 - exp(-delta sigma)) any ray left in the cell, grid_hit[cell] = number of hits (sigma > sigma_thresh).
+ * Both outputs are accumulated into (caller zero-fills, as the reference's zeros_like). Only step_size, sigma_thresh
+ * and ndc_* of the options are read; cam->row_begin/row_end are ignored. */
+SVOXB_API int svoxb_grid_weight_render(const float* grid, int32_t reso, const svoxb_camera* cam,
+                             const svoxb_render_options* opt, const float* offset, const float* scaling,
+                             float* grid_weight, float* grid_hit, void* stream);
 
 /* ---- animated-frame rebuild -------------------------------------------------------------------- */
 /* warp_vertices (svox_kernel.cu:123-154, 354-378): linear blend skinning. T[J,4,4], coords[P,3], w[P,B],

@@ -356,3 +356,53 @@ def accumulate_weights(tree, features, origins, dirs, step_size=1e-3, sigma_thre
     getattr(lib(), "orc_accumulate_weights" + sfx)(*targs, _p(o), _p(d), ctypes.c_int64(o.shape[0]), cr(step_size),
                                                     cr(sigma_thresh), cr(stop_thresh), _p(wa))
     return wa
+
+
+def query_backward(tree, M, pts, grad_out, dtype=np.float32):
+    """query_vertical_backward as the reference's source states it -> grad_data[M,K]."""
+    sfx, _ = _sfx(dtype)
+    pts, g = _c(pts, dtype), _c(grad_out, dtype)
+    off, sc = _c(tree.offset, dtype), _c(tree.scaling, dtype)
+    out = np.zeros((M, g.shape[1]), dtype=dtype)
+    getattr(lib(), "orc_query_backward" + sfx)(_p(tree.child), _p(tree.data), ctypes.c_int(tree.N), ctypes.c_int64(M),
+                                                _p(off), _p(sc), _p(pts), ctypes.c_int64(len(pts)), _p(g),
+                                                ctypes.c_int(g.shape[1]), _p(out))
+    return out
+
+
+def assign(tree, features, pts, values, dtype=np.float32):
+    """assign_vertical (highest point index wins a shared leaf) -> the updated copy of features."""
+    sfx, _ = _sfx(dtype)
+    f = np.array(features, dtype=dtype, order="C", copy=True)
+    pts, v = _c(pts, dtype), _c(values, dtype)
+    off, sc = _c(tree.offset, dtype), _c(tree.scaling, dtype)
+    getattr(lib(), "orc_assign" + sfx)(_p(tree.child), _p(tree.data), ctypes.c_int(tree.N), _p(f),
+                                        ctypes.c_int64(f.shape[0]), ctypes.c_int(f.shape[1]), _p(off), _p(sc),
+                                        _p(pts), ctypes.c_int64(len(pts)), _p(v), ctypes.c_int(v.shape[1]))
+    return f
+
+
+def calc_corners(parent_depth, N, indexer, dtype=np.float32):
+    sfx, _ = _sfx(dtype)
+    pd, ix = _c(parent_depth, np.int32), _c(indexer, np.int64)
+    out = np.zeros((len(ix), 3), dtype=dtype)
+    getattr(lib(), "orc_calc_corners" + sfx)(_p(pd), ctypes.c_int(N), _p(ix), ctypes.c_int64(len(ix)), _p(out))
+    return out
+
+
+def grid_weight_render(grid, c2w, fx, fy, width, height, offset=(0.0, 0.0, 0.0), scaling=(1.0, 1.0, 1.0),
+                       step_size=1e-3, sigma_thresh=0.0, ndc_width=-1, ndc_height=-1, ndc_focal=0.0,
+                       dtype=np.float32):
+    """-> grid_weight[r,r,r], grid_hit[r,r,r]."""
+    sfx, ct = _sfx(dtype)
+    g = _c(grid, dtype)
+    c = np.zeros((4, 4), dtype=dtype)
+    c2w = np.asarray(c2w, dtype=dtype)
+    c[:c2w.shape[0]] = c2w
+    off, sc = _c(np.asarray(offset), dtype), _c(np.asarray(scaling), dtype)
+    gw, gh = np.zeros_like(g), np.zeros_like(g)
+    getattr(lib(), "orc_grid_weight_render" + sfx)(
+        _p(g), ctypes.c_int(g.shape[0]), _p(c), ct(fx), ct(fy), ctypes.c_int(width), ctypes.c_int(height),
+        ctypes.c_int(ndc_width), ctypes.c_int(ndc_height), ct(ndc_focal), _p(off), _p(sc), ct(step_size),
+        ct(sigma_thresh), _p(gw), _p(gh))
+    return gw, gh

@@ -73,6 +73,10 @@ SYMBOLS = {
     "svoxb_leafset_scan": (ctypes.c_int, [_VP, _I64, _VP, _VP, _VP]),
     "svoxb_leafset_emit": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP, _VP]),
     "svoxb_construct_tree": (ctypes.c_int, [_PT, _VP, _VP, _I64, _VP]),
+    "svoxb_query_bwd": (ctypes.c_int, [_PT, _VP, _I64, _VP, _I32, _VP, _VP]),
+    "svoxb_assign": (ctypes.c_int, [_PT, _VP, _VP, _I64, _VP, _I32, _VP]),
+    "svoxb_calc_corners": (ctypes.c_int, [_VP, _I32, _I64, _VP, _I64, _VP, _VP]),
+    "svoxb_grid_weight_render": (ctypes.c_int, [_VP, _I32, _PC, _PO, _VP, _VP, _VP, _VP, _VP]),
     "svoxb_render_rays_fwd": (ctypes.c_int, [_PT, _VP, _VP, _VP, _I64, _PO, _VP, _VP, _VP]),
     "svoxb_out_data_dim": (ctypes.c_int, [_I32, _I32, _I32]),
     "svoxb_render_rays_bwd": (ctypes.c_int, [_PT, _VP, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _VP]),
@@ -111,7 +115,7 @@ def load_library():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.svoxb_abi_version() != 6:
+        if lib.svoxb_abi_version() != 7:
             raise ImportError("svox_t_b200: libsvoxb.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib
@@ -733,10 +737,74 @@ def _unsupported(name, why):
     return f
 
 
-# Reference entry points outside the hot path: present so that
-# `hasattr(_C, name)` behaves, but they raise instead of silently doing something else.
-query_vertical_backward = _unsupported("query_vertical_backward", "faults in the reference (Appendix B1); out of scope")
-assign_vertical = _unsupported("assign_vertical", "faults in the reference (Appendix B1); out of scope")
-calc_corners = _unsupported("calc_corners", "dtype bug in the reference (Appendix B4); out of scope")
-grid_weight_render = _unsupported("grid_weight_render", "no caller in the reference; out of scope")
+def query_vertical_backward(tree, indices, grad_output):
+    """grad_data[M, K]: row scatter-add of ``grad_output[Q, K]`` into the rows the points fall in
+    (svox_kernel.cu:380-403; the reference's kernel faults, Appendix B1 -- this is what its source states)."""
+    lib = load_library()
+    _check_input(indices, "indices", torch.float32)
+    _check_input(grad_output, "grad_output", torch.float32)
+    if indices.dim() != 2 or indices.shape[1] != 3 or grad_output.dim() != 2 or grad_output.shape[0] != indices.shape[0]:
+        raise RuntimeError("indices must be [Q, 3] and grad_output [Q, K]")
+    ct = tree._c()
+    dev = indices.device
+    with torch.cuda.device(dev):
+        grad = torch.zeros((tree.features.shape[0], grad_output.shape[1]), dtype=torch.float32, device=dev)
+        _check(lib.svoxb_query_bwd(ctypes.byref(ct), _ptr(indices), indices.shape[0], _ptr(grad_output),
+                                   grad_output.shape[1], _ptr(grad), _stream()))
+    return grad
+
+
+def assign_vertical(tree, indices, values):
+    """features[row(p_q), :K] = values[q], in place (svox_kernel.cu:326-339). Deterministic: the largest q wins a
+    shared leaf."""
+    lib = load_library()
+    _check_input(indices, "indices", torch.float32)
+    _check_input(values, "values", torch.float32)
+    if indices.dim() != 2 or indices.shape[1] != 3 or values.dim() != 2 or values.shape[0] != indices.shape[0]:
+        raise RuntimeError("indices must be [Q, 3] and values [Q, K]")
+    ct = tree._c()
+    with torch.cuda.device(indices.device):
+        _check(lib.svoxb_assign(ctypes.byref(ct), _ptr(tree.features), _ptr(indices), indices.shape[0], _ptr(values),
+                                values.shape[1], _stream()))
+    # the kernel wrote through the raw pointer: bump the tensor version so that activated tables / hit marks derived
+    # from the old rows are rebuilt
+    torch.autograd.graph.increment_version(tree.features)
+
+
+def calc_corners(tree, indexer):
+    """[Q, 3] lower corners (tree coordinates) of the cells ``indexer[Q, 4] = [node, i, j, k]``
+    (svox_kernel.cu:436-457; the reference dispatches on its int32 ``data`` tensor and raises, Appendix B4)."""
+    lib = load_library()
+    _check_input(indexer, "indexer", torch.int64)
+    if indexer.dim() != 2 or indexer.shape[1] != 4:
+        raise RuntimeError("indexer must be [Q, 4]")
+    _check_input(tree.parent_depth, "parent_depth", torch.int32)
+    dev = indexer.device
+    with torch.cuda.device(dev):
+        out = torch.empty((indexer.shape[0], 3), dtype=torch.float32, device=dev)
+        _check(lib.svoxb_calc_corners(_ptr(tree.parent_depth), tree.child.shape[1], int(tree.n_internal),
+                                      _ptr(indexer), indexer.shape[0], _ptr(out), _stream()))
+    return out
+
+
+def grid_weight_render(data, cam, opt, offset, scaling):
+    """[grid_weight, grid_hit], both shaped like the dense sigma grid ``data[r, r, r]``: per cell the largest compositing
+    weight any pixel ray of ``cam`` leaves there and the number of hits (rt_kernel.cu:1454-1478)."""
+    lib = load_library()
+    for t, n in ((data, "data"), (offset, "offset"), (scaling, "scaling")):
+        _check_input(t, n, torch.float32)
+    if data.dim() != 3 or data.shape[0] != data.shape[1] or data.shape[0] != data.shape[2]:
+        raise RuntimeError("data must be a cubic [r, r, r] grid")
+    cam.check()
+    cc = cam._c()
+    dev = data.device
+    with torch.cuda.device(dev):
+        gw, gh = torch.zeros_like(data), torch.zeros_like(data)
+        _check(lib.svoxb_grid_weight_render(_ptr(data), data.shape[0], ctypes.byref(cc), ctypes.byref(opt._c()),
+                                            _ptr(offset), _ptr(scaling), _ptr(gw), _ptr(gh), _stream()))
+    return [gw, gh]
+
+
+# The one reference entry point that stays out (SURVEY.md section 2): present so that `hasattr(_C, name)` behaves, but
+# it raises instead of silently doing something else.
 quantize_median_cut = _unsupported("quantize_median_cut", "CPU-only PlenOctree leftover; out of scope")

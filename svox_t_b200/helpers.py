@@ -80,24 +80,43 @@ class N3TreeView:
 
     @property
     def corners_local(self):
-        """Lower corner of each selected leaf in tree space, walking parent_depth upward (svox.py:808-826)."""
+        """Lower corner of each selected leaf in tree space (svox.py:804-826 -> calc_corners)."""
         self._check_ver()
-        tree = self.tree
-        curr = self.unique_leaf_node.clone()
-        out = torch.zeros(curr.shape[0], 3, device=curr.device, dtype=torch.float32)
-        alive = torch.ones(curr.shape[0], dtype=torch.bool, device=curr.device)
-        while True:
-            out[alive] = (out[alive] + curr[alive, 1:].float()) / tree.N
-            alive = alive & (curr[:, 0] != 0)
-            if not bool(alive.any()):
-                break
-            packed = tree.parent_depth[curr[alive, 0], 0].long()
-            curr[alive] = tree._unpack_index(packed)
-        return out
+        return self.tree._calc_corners(self.unique_leaf_node)
 
     @property
     def corners(self):
         return self.tree.tree2world(self.corners_local)
+
+    def _rows(self):
+        self._check_ver()
+        idx = self.tree.data[self.key][..., 0].long()
+        return idx, idx < self.tree.features.shape[0]
+
+    @property
+    def values(self):
+        """Feature rows of the selected leaves, (n_leaves, data_dim), autograd enabled; zeros for empty leaves. (The
+        reference's accessor, helpers.py:111-120, still indexes ``tree.data`` as if it held the floats.)"""
+        idx, valid = self._rows()
+        f = self.tree.features
+        out = f.new_zeros((idx.shape[0], f.shape[1]))
+        out[valid] = f[idx[valid]]
+        return out
+
+    @property
+    def values_nograd(self):
+        with torch.no_grad():
+            return self.values
+
+    def set(self, value):
+        """Overwrite the feature rows of the selected leaves (helpers.py:267-270); empty leaves are skipped."""
+        idx, valid = self._rows()
+        f = self.tree.features
+        value = torch.as_tensor(value, dtype=f.dtype, device=f.device)
+        if value.ndim == 2 and value.shape[0] == idx.shape[0]:
+            value = value[valid]
+        with torch.no_grad():
+            f[idx[valid]] = value
 
     def aux(self, arr):
         """Index an auxiliary per-slot array of shape (capacity, N, N, N, ...) with this view (helpers.py:239-244)."""

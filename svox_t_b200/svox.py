@@ -26,25 +26,22 @@ EMPTY = int(np.array(int(1e10)).astype(np.int32))  # 1410065408, the reference's
 
 
 class _QueryVerticalFunction(autograd.Function):
-    """svox.py:38-56. The reference's backward faults (Appendix B1); here it is a plain row scatter-add."""
+    """svox.py:38-56. The backward is the row scatter-add the reference's query_vertical_backward states (its own
+    kernel faults, Appendix B1)."""
 
     @staticmethod
     def forward(ctx, data, tree_spec, indices):
         out, node_ids, data_ids, leaf_node = _C.query_vertical(tree_spec, indices)
         ctx.mark_non_differentiable(node_ids, data_ids, leaf_node)
-        ctx.save_for_backward(data_ids)
-        ctx.feat_shape = tuple(data.shape)
+        ctx.tree_spec = tree_spec
+        ctx.save_for_backward(indices)
         return out, node_ids, data_ids, leaf_node
 
     @staticmethod
     def backward(ctx, grad_out, *_unused):
         if not ctx.needs_input_grad[0]:
             return None, None, None
-        (data_ids,) = ctx.saved_tensors
-        valid = data_ids >= 0
-        grad = torch.zeros(ctx.feat_shape, dtype=grad_out.dtype, device=grad_out.device)
-        grad.index_add_(0, data_ids[valid], grad_out.contiguous()[valid])
-        return grad, None, None
+        return _C.query_vertical_backward(ctx.tree_spec, ctx.saved_tensors[0], grad_out.contiguous()), None, None
 
 
 class _WarpVerticalFunction(autograd.Function):
@@ -150,6 +147,24 @@ class N3Tree(nn.Module):
         """data[leaf(p_i)] = i: point i becomes the feature row of its leaf (svox.py:160-161)."""
         _C.construct_tree(self._spec(self.features), indices)
         self._invalidate()
+
+    def set(self, indices, values, cuda=True):
+        """features[row of leaf(p_q), :K] = values[q] (svox.py:164-214 -> assign_vertical). Where several points share
+        a leaf the last one (largest q) is taken. No autograd through ``indices`` or ``values``."""
+        assert len(indices.shape) == 2
+        assert not indices.requires_grad and not values.requires_grad
+        if not cuda or not self.data.is_cuda:
+            raise RuntimeError("svox_t_b200 has no CPU assignment path: the tree must be on a CUDA device")
+        indices = indices.to(device=self.data.device, dtype=torch.float32).contiguous()
+        values = values.to(device=self.data.device, dtype=torch.float32).contiguous()
+        _C.assign_vertical(self._spec(self.features, _with_accel=False), indices, values)
+
+    def _calc_corners(self, nodes, cuda=True):
+        """Lower corners (tree coordinates) of the cells ``nodes[Q, 4] = [node, i, j, k]`` (svox.py:804-826)."""
+        if not cuda or not self.data.is_cuda:
+            raise RuntimeError("svox_t_b200 has no CPU path: the tree must be on a CUDA device")
+        return _C.calc_corners(self._spec(self.features, _with_accel=False),
+                               nodes.to(device=self.data.device, dtype=torch.int64).contiguous())
 
     def forward(self, features, indices, cuda=True, want_node_ids=False, world=True, want_data_ids=False,
                 want_leaf_node=False):
@@ -431,6 +446,16 @@ class N3Tree(nn.Module):
 
     def __getitem__(self, key):
         return N3TreeView(self, key)
+
+    def __setitem__(self, key, val):
+        """``tree[pts] = values``: row assignment at world points (svox.py:767-768)."""
+        if torch.is_tensor(key) and key.ndim == 2 and key.shape[1] == 3:
+            val = torch.as_tensor(val, dtype=torch.float32, device=self.data.device)
+            if val.ndim < 2:
+                val = val.expand(key.shape[0], val.shape[0] if val.ndim == 1 else self.data_dim)
+            self.set(key, val)
+        else:
+            N3TreeView(self, key).set(val)
 
     def __len__(self):
         return self.n_leaves

@@ -771,3 +771,102 @@ def test_snap_and_clone_on_device(dev):
     assert c2.child.is_cuda and torch.equal(c2.child, tree.child) and c2.child.data_ptr() != tree.child.data_ptr()
     cpu = tree.clone(device="cpu")
     assert not cpu.child.is_cuda and torch.equal(cpu.data, tree.data.cpu())
+
+
+# ---- the remaining point-wise operators of svox_t.csrc (svoxb_vertical.cu) -----------------------------------------
+def test_query_backward_and_assign_vs_oracle(dev):
+    """query_vertical_backward / assign_vertical (svox_kernel.cu:83-108): the reference's kernels fault (Appendix B1),
+    so parity is against the oracle's restatement of their source and against torch index arithmetic."""
+    tr = synth.synth_tree(5, "ball")
+    D, Q = 19, 5000
+    f = synth.synth_features(tr["M"], D)
+    T = orc.Tree(tr["child"], tr["data"])
+    rng = np.random.default_rng(21)
+    pts = (rng.random((Q, 3)) * 1.1 - 0.05).astype(np.float32)          # some outside the cube, many in empty leaves
+    tree = make_tree(tr, D, dev)
+    feats = cu(f, dev).requires_grad_(True)
+    vals = tree(feats, cu(pts, dev))
+    g = rng.standard_normal((Q, D)).astype(np.float32)
+    n0 = C.launch_count()
+    (vals * cu(g, dev)).sum().backward()
+    assert C.launch_count() > n0                                          # the backward is one of our kernels
+    ref = orc.query_backward(T, tr["M"], pts, g, dtype=np.float64)
+    assert ref.any() and rel_l2(feats.grad.cpu().numpy(), ref) <= 1e-6
+    # K != D through the operator module directly
+    g5 = np.ascontiguousarray(g[:, :5])
+    got = C.query_vertical_backward(tree._spec(feats.detach()), cu(pts, dev), cu(g5, dev)).cpu().numpy()
+    assert got.shape == (tr["M"], 5) and rel_l2(got, orc.query_backward(T, tr["M"], pts, g5, dtype=np.float64)) <= 1e-6
+
+    # assignment: whole rows, and the leading K channels only; duplicates resolved towards the largest point index
+    pts2 = np.concatenate([pts, pts[:700]])                                # 700 leaves are hit (at least) twice
+    for K in (D, 4):
+        v = rng.standard_normal((len(pts2), K)).astype(np.float32)
+        tree.features = torch.nn.Parameter(cu(f, dev))
+        ver = tree.features._version
+        tree.set(cu(pts2, dev), cu(v, dev))
+        assert tree.features._version > ver
+        assert np.array_equal(tree.features.detach().cpu().numpy(), orc.assign(T, f, pts2, v))
+    tree.features = torch.nn.Parameter(cu(f, dev))
+    tree[cu(pts2, dev)] = cu(v, dev)
+    assert np.array_equal(tree.features.detach().cpu().numpy(), orc.assign(T, f, pts2, v))
+    # empty batches are no-ops
+    tree.set(torch.zeros((0, 3), device=dev), torch.zeros((0, D), device=dev))
+    assert C.query_vertical_backward(tree._spec(feats.detach()), torch.zeros((0, 3), device=dev),
+                                     torch.zeros((0, D), device=dev)).abs().sum().item() == 0.0
+
+
+@pytest.mark.parametrize("N", [2, 3])
+def test_calc_corners_vs_oracle_and_query(dev, N):
+    """calc_corners (svox_kernel.cu:213-237; raises in the reference, Appendix B4): bit-exact against the oracle, and
+    every corner + half a cell must query back into the same leaf."""
+    tree = sv.N3Tree(N=N, data_dim=4, init_reserve=64, map_location=dev)
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    for _ in range(3):
+        pts = torch.rand(40, 3, generator=gen).to(dev)
+        tree[pts].refine()
+    view = tree[:]
+    leaves = view.unique_leaf_node.contiguous()
+    got = C.calc_corners(tree._spec(tree.features), leaves)
+    ref = orc.calc_corners(tree.parent_depth.cpu().numpy(), N, leaves.cpu().numpy())
+    assert np.array_equal(got.cpu().numpy(), ref)
+    assert torch.equal(view.corners_local, got)
+    centre = got + 0.5 * view.lengths_local[:, None]
+    _, nid = tree(tree.features, tree.tree2world(centre).contiguous(), want_node_ids=True)
+    assert torch.equal(nid, tree._pack_index(leaves))
+    assert C.calc_corners(tree._spec(tree.features), leaves[:0]).shape == (0, 3)
+
+
+def _grid_case(ndc):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_grid", os.path.join(GOLDEN_DIR, "make_golden_grid.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.grid_case(ndc)
+
+
+@pytest.mark.parametrize("ndc", [False, True], ids=["world", "ndc"])
+def test_grid_weight_render_vs_oracle_and_reference(dev, ndc):
+    """grid_weight_render (rt_kernel.cu:1240-1344): hit counts bit-exact but for threshold ties, maximum weights within
+    the float tolerance; against the oracle and, when oracle/_ref is on the box, the reference's own kernel."""
+    grid, c2w, W, H, fx, off, inv, kw = _grid_case(ndc)
+    cam = C.CameraSpec()
+    cam.c2w, cam.fx, cam.fy, cam.width, cam.height = cu(c2w, dev), fx, fx, W, H
+    opt = C.RenderOptions()
+    opt.step_size, opt.sigma_thresh = 1e-3, 0.5
+    for k, v in kw.items():
+        setattr(opt, k, v)
+    gw, gh = C.grid_weight_render(cu(grid, dev), cam, opt, cu(off, dev), cu(inv, dev))
+    gw, gh = gw.cpu().numpy(), gh.cpu().numpy()
+    rw, rh = orc.grid_weight_render(grid, c2w, fx, fx, W, H, off, inv, step_size=1e-3, sigma_thresh=0.5, **kw)
+    assert rh.sum() > 1000 and (gh[grid <= 0.5] == 0).all()
+    assert float((gh == rh).mean()) >= 0.999 and abs(gh.sum() - rh.sum()) <= 1e-3 * rh.sum()
+    assert frac_within(gw, rw, atol=1e-5) >= 0.999
+    if refdrv.available():
+        m = refdrv.module()
+        rc, ro = m.CameraSpec(), refdrv.options(sigma_thresh=0.5)
+        rc.c2w, rc.fx, rc.fy, rc.width, rc.height = cu(c2w, dev), fx, fx, W, H
+        for k, v in kw.items():
+            setattr(ro, k, v)
+        xw, xh = m.grid_weight_render(cu(grid, dev), rc, ro, cu(off, dev), cu(inv, dev))
+        assert float((gh == xh.cpu().numpy()).mean()) >= 0.999
+        assert frac_within(gw, xw.cpu().numpy(), atol=1e-5) >= 0.999

@@ -388,3 +388,59 @@ def test_ndc_camera_rays():
 
 def test_golden_fixtures_present():
     assert len(golden_files()) >= 3, "tests/golden/*.npz missing: run tests/golden/make_golden.py on a GPU box"
+
+
+def test_query_backward_and_assign_restatements():
+    """orc_query_backward / orc_assign (svox_kernel.cu:83-108) against plain numpy on the rows orc_query reports."""
+    tr = synth.synth_tree(4, "ball")
+    D, Q = 7, 3000
+    f = synth.synth_features(tr["M"], D)
+    T = orc.Tree(tr["child"], tr["data"])
+    rng = np.random.default_rng(2)
+    pts = (rng.random((Q, 3)) * 1.1 - 0.05).astype(np.float32)
+    _, _, ids, valid = orc.query(T, f, pts)
+    assert 0.05 < valid.mean() < 0.95
+    g = rng.standard_normal((Q, D))
+    want = np.zeros((tr["M"], D))
+    np.add.at(want, ids[valid], g[valid])
+    assert np.allclose(orc.query_backward(T, tr["M"], pts, g, dtype=np.float64), want, atol=1e-12)
+    v = rng.standard_normal((Q, 3)).astype(np.float32)
+    want = f.copy()
+    for q in np.nonzero(valid)[0]:               # serial order: the highest point index wins a shared leaf
+        want[ids[q], :3] = v[q]
+    got = orc.assign(T, f, pts, v)
+    assert np.array_equal(got, want) and not np.array_equal(got, f)
+
+
+def test_calc_corners_restatement():
+    """orc_calc_corners (svox_kernel.cu:213-237): on the generated trees the corner of a leaf cell is known in closed
+    form -- a point query at (corner + half a cell) must return the same slot."""
+    tr = synth.synth_tree(4, "ball")
+    T = orc.Tree(tr["child"], tr["data"])
+    child = tr["child"]
+    leaves = np.argwhere(child == 0)                                    # [n, 4] = node, i, j, k
+    leaves = leaves[:: max(1, len(leaves) // 500)].astype(np.int64)
+    corners = orc.calc_corners(tr["parent_depth"], 2, leaves)
+    depth = tr["parent_depth"][leaves[:, 0], 1]
+    half = 0.5 ** (depth + 2.0)
+    pts = (corners + half[:, None]).astype(np.float32)
+    _, node_ids, _, _ = orc.query(T, np.zeros((tr["M"], 2), np.float32), pts)
+    assert np.array_equal(node_ids, ((leaves[:, 0] * 2 + leaves[:, 1]) * 2 + leaves[:, 2]) * 2 + leaves[:, 3])
+    assert np.array_equal(corners * 2.0 ** (depth[:, None] + 1), np.floor(corners * 2.0 ** (depth[:, None] + 1)))
+
+
+def test_grid_weight_oracle_matches_reference_golden():
+    """orc_grid_weight_render against the reference's own kernel (tests/golden/make_golden_grid.py, run on a B200)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_grid", os.path.join(GOLDEN_DIR, "make_golden_grid.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    z = np.load(os.path.join(GOLDEN_DIR, "y_grid_weight.npz"))
+    for tag, ndc in (("world", False), ("ndc", True)):
+        grid, c2w, W, H, fx, off, inv, kw = mod.grid_case(ndc)
+        assert np.array_equal(grid, z["grid"])
+        gw, gh = orc.grid_weight_render(grid, c2w, fx, fx, W, H, off, inv, step_size=1e-3, sigma_thresh=0.5, **kw)
+        ref_h = z[tag + "_hit"].astype(np.float32)
+        assert float((gh == ref_h).mean()) >= 0.999 and abs(gh.sum() - ref_h.sum()) <= 1e-3 * ref_h.sum()
+        assert float((np.abs(gw - z[tag + "_weight"]) <= 1e-5 + 1e-3 * z[tag + "_weight"]).mean()) >= 0.999
+        assert (gh[grid <= 0.5] == 0).all() and gw.max() > 0.3
