@@ -158,10 +158,37 @@ __device__ __forceinline__ unsigned refill(const RaySource& src, const float* of
     return got;
 }
 
+// Stage the accelerator's top grid (8^bits[0] tagged words, <= 16 KB) in shared memory with ONE bulk asynchronous copy
+// (TMA, cp.async.bulk global -> shared, completion on an mbarrier) issued by thread 0; every thread then waits on
+// the barrier's phase. `top` must be the 16-byte aligned start of the dynamic shared memory; the grid is a
+// stream-ordered pool allocation (256-byte aligned) whose size is a multiple of 32 bytes.
+#ifndef SVOXB_TOP_TMA
+#define SVOXB_TOP_TMA 1
+#endif
 __device__ __forceinline__ void load_top(const TreeArgs& tr, uint32_t* top) {
+#if !SVOXB_TOP_TMA
     const int n = 1 << (3 * tr.acc.bits[0]);
     for (int i = threadIdx.x; i < n; i += blockDim.x) top[i] = __ldg(tr.acc.cells[0] + i);
     __syncthreads();
+    return;
+#endif
+    __shared__ __align__(8) unsigned long long top_bar;
+    const uint32_t bytes = 4u << (3 * tr.acc.bits[0]);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&top_bar), dst = (uint32_t)__cvta_generic_to_shared(top);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(tr.acc.cells[0]), "r"(bytes), "r"(bar) : "memory");
+    }
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar) : "memory");
 }
 
 // One march sample of the lane's ray (rt_kernel.cu:261-277): returns the leaf row (or -1), delta_t and sigma.
@@ -267,7 +294,7 @@ __device__ __forceinline__ void probe_end(const TreeArgs& tr, const Probe& pb, c
 template <typename Kern>
 static int persistent_grid(Kern kern, size_t smem, int64_t queue_len, int& grid, int threads = BLOCK,
                            int carveout_kb = 0) {
-    if (smem > 48 * 1024)
+    if (smem + 1024 > 48 * 1024)      // static shared memory (the top grid's mbarrier) counts against the 48 KB default
         SVOXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (carveout_kb > 0)
         SVOXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,

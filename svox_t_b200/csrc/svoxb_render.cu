@@ -31,7 +31,7 @@ template <int K, bool ACCEL, bool IMAGE>
 __global__ void __launch_bounds__(BLOCK)
 march_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
                  unsigned long long* counter) {
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(128) uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31;
@@ -157,7 +157,7 @@ template <int K, bool ACCEL, bool IMAGE>
 __global__ void __launch_bounds__(BLOCK)
 march_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __restrict__ grad_out,
                  const float* __restrict__ saved_out, float* __restrict__ grad, unsigned long long* counter) {
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(128) uint32_t smem_u32[];
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     uint32_t* top = smem_u32;
     float* gs_all = reinterpret_cast<float*>(smem_u32 + top_words);      // [WARPS][32][32*K]
@@ -335,7 +335,7 @@ template <bool ACCEL>
 __global__ void __launch_bounds__(BLOCK)
 depth_kernel(TreeArgs tr, const float* __restrict__ origins, const float* __restrict__ dirs, int64_t Q,
              MarchOpts opt, float* __restrict__ depth) {
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(128) uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     if (ACCEL) load_top(tr, top);
     const float* off = tr.offset;

@@ -191,7 +191,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                       unsigned long long* counter) {
     using G = Quad<LPR, V4>;
     constexpr int RPI = G::RPI, NB = G::NB, NBATCH = G::NBATCH, RPB = G::RAYS_PER_BATCH, VEC = G::VEC;
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(128) uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     if (ACCEL) load_top(tr, top);
@@ -375,7 +375,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
     // launcher folds both into the caller's table afterwards.
     using G = Quad<LPR, V4>;
     constexpr int RPI = G::RPI, NB = G::NB, NBATCH = G::NBATCH, RPB = G::RAYS_PER_BATCH, VEC = G::VEC, DP = G::DP;
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(128) uint32_t smem_u32[];
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     uint32_t* top = smem_u32;
     if (ACCEL) load_top(tr, top);

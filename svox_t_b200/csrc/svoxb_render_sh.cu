@@ -114,7 +114,7 @@ template <int K, bool ACCEL, bool IMAGE>
 __global__ void __launch_bounds__(BLOCK)
 march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, float* __restrict__ out,
                      unsigned long long* counter) {
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(128) uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     if (ACCEL) load_top(tr, top);
@@ -213,7 +213,7 @@ template <int K, bool ACCEL, bool IMAGE>
 __global__ void __launch_bounds__(BLOCK)
 march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, const float* __restrict__ grad_out,
                      const float* __restrict__ saved_out, float* __restrict__ grad, unsigned long long* counter) {
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(128) uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     if (ACCEL) load_top(tr, top);
@@ -335,7 +335,7 @@ template <bool ACCEL>
 __global__ void __launch_bounds__(BLOCK)
 motion_feature_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, float* __restrict__ out,
                           unsigned long long* counter) {
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(128) uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     if (ACCEL) load_top(tr, top);
@@ -425,7 +425,7 @@ template <bool ACCEL>
 __global__ void __launch_bounds__(BLOCK)
 motion_feature_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, const float* __restrict__ grad_out,
                           float* __restrict__ grad_jf, int use_table, unsigned long long* counter) {
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(128) uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     if (ACCEL) load_top(tr, top);

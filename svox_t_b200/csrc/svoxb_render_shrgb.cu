@@ -99,7 +99,7 @@ __device__ __forceinline__ void sh_dots(const float (&v)[3 * B + 1], const float
 template <int B, bool VEC, bool ACCEL, bool IMAGE>
 __global__ void __launch_bounds__(BLOCK)
 sh_rgb_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, float* __restrict__ out, unsigned long long* counter) {
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(128) uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31;
@@ -175,7 +175,7 @@ template <int B, bool VEC, bool ACCEL, bool IMAGE>
 __global__ void __launch_bounds__(BLOCK)
 sh_rgb_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, const float* __restrict__ grad_out,
                   const float* __restrict__ saved_out, float* __restrict__ grad, unsigned long long* counter) {
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(128) uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31;

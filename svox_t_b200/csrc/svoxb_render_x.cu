@@ -33,7 +33,7 @@ template <bool ACCEL>
 __global__ void __launch_bounds__(BLOCK)
 opacity_fwd_kernel(TreeArgs tr, const float* __restrict__ origins, const float* __restrict__ dirs, int64_t Q,
                    MarchOpts opt, float* __restrict__ out) {
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(128) uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     if (ACCEL) load_top(tr, top);
     for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < Q; id += (int64_t)gridDim.x * blockDim.x) {
@@ -58,7 +58,7 @@ template <bool ACCEL>
 __global__ void __launch_bounds__(BLOCK)
 opacity_bwd_kernel(TreeArgs tr, const float* __restrict__ origins, const float* __restrict__ dirs, int64_t Q,
                    MarchOpts opt, const float* __restrict__ grad_out, float* __restrict__ grad) {
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(128) uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     if (ACCEL) load_top(tr, top);
     for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < Q; id += (int64_t)gridDim.x * blockDim.x) {
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(BLOCK)
 motion_kernel(TreeArgs tr, const float* __restrict__ origins, const float* __restrict__ dirs, int64_t Q, MarchOpts opt,
               const float* __restrict__ extra, int J, float* __restrict__ out, float* __restrict__ depth,
               float* __restrict__ hit_point, int64_t* __restrict__ data_idx) {
-    extern __shared__ uint32_t smem_u32[];
+    extern __shared__ __align__(128) uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     if (ACCEL) load_top(tr, top);
     const float o0 = __ldg(tr.offset), o1 = __ldg(tr.offset + 1), o2 = __ldg(tr.offset + 2);
