@@ -516,6 +516,295 @@ motion_feature_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs j
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Motion-feature render, staged form (the one the entry points launch whenever the joint table fits shared memory).
+// Same arithmetic as the kernels above; what changes is where the per-hit operands live:
+//   * jf[J,F] sits in shared memory for the whole kernel (one copy per CTA; J*F floats);
+//   * the march is software-pipelined like the feature render: a candidate found in iteration i is composited in
+//     iteration i+1, its sigma / skinning row / joint-index row are requested (lane-private gathers) BEFORE the traversal
+//     step of iteration i+1 and consumed after it; rows the accelerator marks "sigma <= 0" never become candidates;
+//   * the owner lane stages (weights clamped at 0 -- the reference skips w <= 0, rt_kernel.cu:955 --, joint row offsets,
+//     compositing weight) in a per-warp shared-memory slot, the warp then serves one hit at a time with lane = channel:
+//     broadcast LDS of the staged operands, NB LDS + FMA from the joint table, one sigmoid;
+//   * backward: every warp reduces dL/dJF into ITS OWN [J,F] table in shared memory with plain read-modify-writes (lane k
+//     owns column k, hits are served one at a time, so no two lanes ever touch one address) -- shared-memory float
+//     atomics are a compare-and-swap loop on this architecture (ATOMS.CAST.SPIN) -- and flushes it once at the end.
+// NB4: NB == 4 with 16-byte aligned rows -> the operands travel as one float4 + one int4 per lane.
+struct MfSmem {
+    uint32_t* top; float* jf; float* rows; float* st_w; int* st_j; float* st_ww; float* table;
+};
+
+template <bool BWD>
+__device__ __forceinline__ MfSmem mf_carve(uint32_t* base, int top_words, int JF, int NB, int warp) {
+    MfSmem m;
+    m.top = base;
+    m.jf = reinterpret_cast<float*>(base + top_words);
+    const int jf_pad = (JF + 3) & ~3, nb_pad = (NB + 3) & ~3;
+    float* w0 = m.jf + jf_pad;                                       // per-warp regions follow, 16-byte aligned
+    const int per_warp = 32 * 32 + 2 * 32 * nb_pad + 32 + (BWD ? jf_pad : 0);
+    float* mine = w0 + (size_t)warp * per_warp;
+    m.rows = mine;                                                   // fwd: partial outputs [32][32]; bwd: grad_out rows
+    m.st_w = mine + 32 * 32;
+    m.st_j = reinterpret_cast<int*>(m.st_w + 32 * nb_pad);
+    m.st_ww = reinterpret_cast<float*>(m.st_j + 32 * nb_pad);
+    m.table = m.st_ww + 32;
+    return m;
+}
+
+static size_t mf_smem_bytes(bool bwd, int top_words, int JF, int NB, int warps) {
+    const int jf_pad = (JF + 3) & ~3, nb_pad = (NB + 3) & ~3;
+    const size_t per_warp = 32 * 32 + 2 * 32 * nb_pad + 32 + (bwd ? jf_pad : 0);
+    return sizeof(float) * ((size_t)top_words + jf_pad + per_warp * warps);
+}
+
+// The owner lane's operands of its pending candidate -> this warp's staging slot.
+template <bool NB4>
+__device__ __forceinline__ void mf_stage(const MfSmem& sm, const JointArgs& ja, int lane, int idx, float w,
+                                         const float4& wv, const int4& jv) {
+    const int nb_pad = (ja.NB + 3) & ~3, F = ja.F, jmax = ja.J - 1;
+    sm.st_ww[lane] = w;
+    if (NB4) {
+        reinterpret_cast<float4*>(sm.st_w)[lane] = make_float4(fmaxf(wv.x, 0.f), fmaxf(wv.y, 0.f), fmaxf(wv.z, 0.f), fmaxf(wv.w, 0.f));
+        reinterpret_cast<int4*>(sm.st_j)[lane] = make_int4(min(max(jv.x, 0), jmax) * F, min(max(jv.y, 0), jmax) * F,
+                                                           min(max(jv.z, 0), jmax) * F, min(max(jv.w, 0), jmax) * F);
+    } else {
+        const float* swr = ja.sw + (size_t)(unsigned)idx * ja.NB;
+        const int32_t* jir = ja.ji + (size_t)(unsigned)idx * ja.NB;
+        for (int b = 0; b < ja.NB; ++b) {
+            sm.st_w[lane * nb_pad + b] = fmaxf(__ldg(swr + b), 0.0f);
+            sm.st_j[lane * nb_pad + b] = min(max(__ldg(jir + b), 0), jmax) * F;
+        }
+    }
+}
+
+// pos_joint_feature[lane] of the hit staged by lane r (rt_kernel.cu:953-958).
+template <bool NB4>
+__device__ __forceinline__ float mf_blend(const MfSmem& sm, int NB, int r, int lane) {
+    if (NB4) {
+        const float4 w = reinterpret_cast<const float4*>(sm.st_w)[r];
+        const int4 j = reinterpret_cast<const int4*>(sm.st_j)[r];
+        return fmaf(w.w, sm.jf[j.w + lane], fmaf(w.z, sm.jf[j.z + lane], fmaf(w.y, sm.jf[j.y + lane], w.x * sm.jf[j.x + lane])));
+    }
+    const int nb_pad = (NB + 3) & ~3;
+    float pj = 0.0f;
+    for (int b = 0; b < NB; ++b) pj = fmaf(sm.st_w[r * nb_pad + b], sm.jf[sm.st_j[r * nb_pad + b] + lane], pj);
+    return pj;
+}
+
+template <bool ACCEL, bool NB4>
+__global__ void __launch_bounds__(BLOCK)
+mf_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, float* __restrict__ out,
+              unsigned long long* counter) {
+    extern __shared__ __align__(128) uint32_t smem_u32[];
+    const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
+    if (ACCEL) load_top(tr, smem_u32);
+    const int lane = threadIdx.x & 31, F = ja.F, JF = ja.J * ja.F;
+    const MfSmem sm = mf_carve<false>(smem_u32, top_words, JF, ja.NB, threadIdx.x >> 5);
+    for (int i = threadIdx.x; i < JF; i += blockDim.x) sm.jf[i] = __ldg(ja.jf + i);
+    for (int r = 0; r < 32; ++r) sm.rows[r * 32 + lane] = 0.0f;
+    __syncthreads();
+    const float* off = tr.offset;
+    const float* scl = tr.scaling;
+    const size_t sig_stride = (size_t)tr.D;
+    const float* sig_base = tr.features + (tr.D - 1);
+
+    Ray ray;
+    float T = 1.0f, p_dt = 0.0f;
+    int row = 0, p_idx = -1;
+    bool active = false, missed = false, trav_done = true;
+    Queue q{0, 0, false};
+    unsigned need = FULL;
+
+    while (true) {
+        if (need) {
+            const unsigned got = refill<false>(src, off, scl, counter, q, need, lane, ray, row);
+            if ((got >> lane) & 1u) {
+                active = true; trav_done = false; T = 1.0f;
+                float a, b;                                      // a ray that misses the cube returns zeros, not the
+                dda_unit(ray.ox, ray.oy, ray.oz, ray.ix, ray.iy, ray.iz, a, b);   // background (rt_kernel.cu:911-916)
+                missed = b < 0.0f || a > b;
+            }
+            need = 0;
+        }
+        if (__ballot_sync(FULL, active) == 0u) break;
+
+        // S0: operands of the pending candidate (row 0 stands in for "none": unconditional loads, see svoxb_render_q.cu)
+        const int pi = max(p_idx, 0);
+        const float sig = __ldg(sig_base + (size_t)(unsigned)pi * sig_stride);
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        int4 jv = make_int4(0, 0, 0, 0);
+        if (NB4) {
+            wv = __ldg(reinterpret_cast<const float4*>(ja.sw) + pi);
+            jv = __ldg(reinterpret_cast<const int4*>(ja.ji) + pi);
+        }
+        // S1: next sample of the traversal
+        int n_idx = -1;
+        float n_dt = 0.0f;
+        if (active && !trav_done) {
+            if (!(ray.t < ray.tmax)) trav_done = true;
+            else {
+                Probe pb;
+                probe_begin<ACCEL>(tr, sm.top, ray, pb);
+                probe_end<ACCEL>(tr, pb, ray, opt.step, n_idx, n_dt);
+                ray.t += n_dt;
+                if (!(ray.t < ray.tmax)) trav_done = true;
+            }
+        }
+        // S2: composite the pending candidate
+        bool hit = false, stopped = false;
+        if (p_idx >= 0 && sig > opt.sigma_thresh) {
+            const float att = expf(-p_dt * ray.ds * sig);
+            mf_stage<NB4>(sm, ja, lane, p_idx, T * (1.0f - att), wv, jv);
+            hit = true;
+            T *= att;
+            if (T <= opt.stop_thresh) stopped = true;
+        }
+        unsigned hm = __ballot_sync(FULL, hit);
+        if (hm) {
+            __syncwarp();
+            while (hm) {
+                const int r = __ffs(hm) - 1;
+                hm &= hm - 1;
+                if (lane < F)
+                    sm.rows[r * 32 + lane] = fmaf(sm.st_ww[r], fast_sigmoid(mf_blend<NB4>(sm, ja.NB, r, lane)), sm.rows[r * 32 + lane]);
+            }
+            __syncwarp();
+        }
+        if (stopped) { n_idx = -1; trav_done = true; }
+        p_idx = n_idx; p_dt = n_dt;
+        const int fin = (active && trav_done && p_idx < 0) ? (missed ? 3 : (stopped ? 2 : 1)) : 0;
+
+        unsigned fm = __ballot_sync(FULL, fin != 0);
+        if (fm) {
+            need = fm;
+            if (fin != 0) active = false;
+            while (fm) {
+                const int r = __ffs(fm) - 1;
+                fm &= fm - 1;
+                const float T_r = __shfl_sync(FULL, T, r);
+                const int fin_r = __shfl_sync(FULL, fin, r);
+                const int row_r = __shfl_sync(FULL, row, r);
+                if (lane < F) {
+                    float v = sm.rows[r * 32 + lane];
+                    if (fin_r == 2) v *= (float)(1.0 / (1.0 - (double)T_r));     // rt_kernel.cu:966-970
+                    else if (fin_r == 1) v += T_r * opt.bg;                      // rt_kernel.cu:975-977
+                    else v = 0.0f;
+                    __stcs(out + (int64_t)row_r * F + lane, v);
+                    sm.rows[r * 32 + lane] = 0.0f;
+                }
+            }
+        }
+    }
+}
+
+template <bool ACCEL, bool NB4>
+__global__ void __launch_bounds__(BLOCK)
+mf_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, const float* __restrict__ grad_out,
+              float* __restrict__ grad_jf, unsigned long long* counter) {
+    extern __shared__ __align__(128) uint32_t smem_u32[];
+    const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
+    if (ACCEL) load_top(tr, smem_u32);
+    const int lane = threadIdx.x & 31, F = ja.F, JF = ja.J * ja.F;
+    const MfSmem sm = mf_carve<true>(smem_u32, top_words, JF, ja.NB, threadIdx.x >> 5);
+    for (int i = threadIdx.x; i < JF; i += blockDim.x) sm.jf[i] = __ldg(ja.jf + i);
+    for (int i = lane; i < JF; i += 32) sm.table[i] = 0.0f;
+    __syncthreads();
+    const float* off = tr.offset;
+    const float* scl = tr.scaling;
+    const size_t sig_stride = (size_t)tr.D;
+    const float* sig_base = tr.features + (tr.D - 1);
+
+    Ray ray;
+    float T = 1.0f, p_dt = 0.0f;
+    int row = 0, p_idx = -1;
+    bool active = false, trav_done = true;
+    Queue q{0, 0, false};
+    unsigned need = FULL;
+
+    while (true) {
+        if (need) {
+            unsigned got = refill<false>(src, off, scl, counter, q, need, lane, ray, row);
+            if ((got >> lane) & 1u) { active = true; trav_done = false; T = 1.0f; }
+            need = 0;
+            while (got) {
+                const int r = __ffs(got) - 1;
+                got &= got - 1;
+                const int row_r = __shfl_sync(FULL, row, r);
+                sm.rows[r * 32 + lane] = lane < F ? __ldcs(grad_out + (int64_t)row_r * F + lane) : 0.0f;
+            }
+            __syncwarp();
+        }
+        if (__ballot_sync(FULL, active) == 0u) break;
+
+        const int pi = max(p_idx, 0);
+        const float sig = __ldg(sig_base + (size_t)(unsigned)pi * sig_stride);
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        int4 jv = make_int4(0, 0, 0, 0);
+        if (NB4) {
+            wv = __ldg(reinterpret_cast<const float4*>(ja.sw) + pi);
+            jv = __ldg(reinterpret_cast<const int4*>(ja.ji) + pi);
+        }
+        int n_idx = -1;
+        float n_dt = 0.0f;
+        if (active && !trav_done) {
+            if (!(ray.t < ray.tmax)) trav_done = true;
+            else {
+                Probe pb;
+                probe_begin<ACCEL>(tr, sm.top, ray, pb);
+                probe_end<ACCEL>(tr, pb, ray, opt.step, n_idx, n_dt);
+                ray.t += n_dt;
+                if (!(ray.t < ray.tmax)) trav_done = true;
+            }
+        }
+        bool hit = false;
+        if (p_idx >= 0 && sig > 0.0f) {                                           // rt_kernel.cu:1029
+            const float att = expf(-p_dt * sig * ray.ds);
+            mf_stage<NB4>(sm, ja, lane, p_idx, T * (1.0f - att), wv, jv);
+            hit = true;
+            T *= att;
+        }
+        unsigned hm = __ballot_sync(FULL, hit);
+        if (hm) {
+            __syncwarp();
+            while (hm) {
+                const int r = __ffs(hm) - 1;
+                hm &= hm - 1;
+                if (lane < F) {
+                    const float s = fast_sigmoid(mf_blend<NB4>(sm, ja.NB, r, lane));
+                    const float sg = s * sm.rows[r * 32 + lane];
+                    const float gt = sm.st_ww[r] * fmaf(-sg, s, sg);              // weight * s (1 - s) * g
+                    if (NB4) {
+                        const float4 w = reinterpret_cast<const float4*>(sm.st_w)[r];
+                        const int4 j = reinterpret_cast<const int4*>(sm.st_j)[r];
+                        sm.table[j.x + lane] = fmaf(w.x, gt, sm.table[j.x + lane]);     // in order: a joint may repeat
+                        sm.table[j.y + lane] = fmaf(w.y, gt, sm.table[j.y + lane]);
+                        sm.table[j.z + lane] = fmaf(w.z, gt, sm.table[j.z + lane]);
+                        sm.table[j.w + lane] = fmaf(w.w, gt, sm.table[j.w + lane]);
+                    } else {
+                        const int nb_pad = (ja.NB + 3) & ~3;
+                        for (int b = 0; b < ja.NB; ++b) {
+                            float* t = sm.table + sm.st_j[r * nb_pad + b] + lane;
+                            *t = fmaf(sm.st_w[r * nb_pad + b], gt, *t);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        p_idx = n_idx; p_dt = n_dt;
+        const bool fin = active && trav_done && p_idx < 0;
+        const unsigned fm = __ballot_sync(FULL, fin);
+        if (fm) {
+            if (fin) active = false;
+            need = fm;
+        }
+    }
+    for (int i = lane; i < JF; i += 32) {
+        const float v = sm.table[i];
+        if (v != 0.0f) atomicAdd(grad_jf + i, v);
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 int make_tree_args(const svoxb_tree* t, TreeArgs& a);   // svoxb_tree.cu
 
@@ -627,6 +916,16 @@ static int make_joint_args(const svoxb_tree* tree, const float* jf, const float*
     return 0;
 }
 
+// The staged kernels need the joint table (and, backward, one gradient table per warp) in shared memory next to the
+// top grid and the per-warp rows; two CTAs per SM should still fit.
+static bool mf_staged_ok(const TreeArgs& tr, const JointArgs& ja, bool bwd) {
+    const int top_words = tr.use_accel ? (1 << (3 * tr.acc.bits[0])) : 0;
+    return ja.NB <= 16 && mf_smem_bytes(bwd, top_words, ja.J * ja.F, ja.NB, WARPS) <= 100 * 1024;
+}
+static bool mf_nb4(const JointArgs& ja) {
+    return ja.NB == 4 && (((uintptr_t)ja.sw | (uintptr_t)ja.ji) & 15) == 0;
+}
+
 }  // namespace svoxb
 
 using namespace svoxb;
@@ -649,6 +948,23 @@ extern "C" int svoxb_motion_feature_render_fwd(const svoxb_tree* tree, const flo
     MarchOpts m{opt->step_size, opt->background_brightness, opt->sigma_thresh, opt->stop_thresh};
     RaySource src{}; src.origins = origins; src.dirs = dirs; src.total = Q; src.ndc_w = -1;
     cudaStream_t st = (cudaStream_t)stream;
+    if (mf_staged_ok(tr, ja, false)) {
+        if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;      // the marks encode sigma > 0: too strict for this predicate
+        const int top_words = tr.use_accel ? (1 << (3 * tr.acc.bits[0])) : 0;
+        const size_t smem2 = mf_smem_bytes(false, top_words, J * F, B, WARPS);
+        const bool nb4 = mf_nb4(ja);
+        void (*k2)(TreeArgs, RaySource, MarchOpts, JointArgs, float*, unsigned long long*) =
+            tr.use_accel ? (nb4 ? mf_fwd_kernel<true, true> : mf_fwd_kernel<true, false>)
+                         : (nb4 ? mf_fwd_kernel<false, true> : mf_fwd_kernel<false, false>);
+        int grid2 = 0;
+        rc = persistent_grid(k2, smem2, Q, grid2); if (rc) return rc;
+        unsigned long long* counter2 = work_counter(st);
+        if (!counter2) return SVOXB_ECUDA;
+        k2<<<grid2, BLOCK, smem2, st>>>(tr, src, m, ja, out, counter2);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "mf_fwd_kernel launch");
+    }
+    tr.acc_miss_mask = 0;                                     // the one-hit-at-a-time kernels fetch sigma themselves
     const size_t smem = (tr.use_accel ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * WARPS * 32 * 32;
     void (*kern)(TreeArgs, RaySource, MarchOpts, JointArgs, float*, unsigned long long*) =
         tr.use_accel ? motion_feature_fwd_kernel<true> : motion_feature_fwd_kernel<false>;
@@ -677,6 +993,22 @@ extern "C" int svoxb_motion_feature_render_bwd(const svoxb_tree* tree, const flo
     if (Q == 0) return 0;
     MarchOpts m{opt->step_size, opt->background_brightness, opt->sigma_thresh, opt->stop_thresh};
     RaySource src{}; src.origins = origins; src.dirs = dirs; src.total = Q; src.ndc_w = -1;
+    if (mf_staged_ok(tr, ja, true)) {
+        const int top_words = tr.use_accel ? (1 << (3 * tr.acc.bits[0])) : 0;
+        const size_t smem2 = mf_smem_bytes(true, top_words, J * F, B, WARPS);
+        const bool nb4 = mf_nb4(ja);
+        void (*k2)(TreeArgs, RaySource, MarchOpts, JointArgs, const float*, float*, unsigned long long*) =
+            tr.use_accel ? (nb4 ? mf_bwd_kernel<true, true> : mf_bwd_kernel<true, false>)
+                         : (nb4 ? mf_bwd_kernel<false, true> : mf_bwd_kernel<false, false>);
+        int grid2 = 0;
+        rc = persistent_grid(k2, smem2, Q, grid2); if (rc) return rc;
+        unsigned long long* counter2 = work_counter(st);
+        if (!counter2) return SVOXB_ECUDA;
+        k2<<<grid2, BLOCK, smem2, st>>>(tr, src, m, ja, grad_out, grad_joint_features, counter2);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "mf_bwd_kernel launch");
+    }
+    tr.acc_miss_mask = 0;
     const size_t table = sizeof(float) * (size_t)J * F;
     const int use_table = table <= 96 * 1024;
     const size_t smem = (tr.use_accel ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * WARPS * 32 * 32 +

@@ -208,9 +208,10 @@ class VolumeRenderer(nn.Module):
         """Composited per-joint features (B, F): every hit blends ``joint_features`` [J,F] with the hit row's
         ``skinning_weights`` / ``joint_index`` [M,B]. Differentiable w.r.t. ``joint_features`` (renderer.py:384-396)."""
         self._require_cuda(cuda)
-        return _MotionFeatureRenderFunction.apply(
-            joint_features, self.tree._spec(features, joint_features, skinning_weights, joint_index),
-            _rays_spec_from_rays(rays), self._get_options(fast))
+        ts = self.tree._spec(features, joint_features, skinning_weights, joint_index)
+        if ts._accel is not None and rays.origins.shape[0] * 32 >= features.shape[0]:
+            ts._accel.mark_hits(features.detach())       # rows with sigma <= 0 never become candidates of the march
+        return _MotionFeatureRenderFunction.apply(joint_features, ts, _rays_spec_from_rays(rays), self._get_options(fast))
 
     def opacity_render(self, features, rays: Rays, cuda=True, fast=False):
         """Opacity only (B, 1); differentiable w.r.t. the sigma channel of ``features`` (renderer.py:397-406)."""

@@ -486,6 +486,20 @@ def test_motion_feature_render_forward_reference_backward_oracle(dev):
     out = sv.VolumeRenderer(tree, background_brightness=0.5).motion_feature_render(
         cu(f4, dev), cu(jf, dev), cu(sw, dev), cu(ji, dev), sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev)))
     assert not out[0].any() and out[1].any()
+    # B != 4 (scalar staging), with a negative weight (skipped, rt_kernel.cu:955) and a repeated joint per row
+    sw3, ji3 = np.ascontiguousarray(sw[:, :3]).copy(), np.ascontiguousarray(ji[:, :3]).copy()
+    sw3[::7, 1] = -0.25
+    ji3[::5, 2] = ji3[::5, 0]
+    for accel in (True, False):
+        jft = cu(jf, dev).requires_grad_(True)
+        ts = tree._spec(cu(f4, dev), jft, cu(sw3, dev), cu(ji3, dev), _with_accel=accel)
+        rs, opt = sv.renderer._rays_spec_from_rays(rays), sv.VolumeRenderer(tree)._get_options()
+        out = C.motion_feature_render(ts, rs, opt)
+        g = np.random.default_rng(2).standard_normal(tuple(out.shape)).astype(np.float32)
+        gj = C.motion_feature_render_backward(ts, rs, opt, cu(g, dev))
+        assert frac_within(out.cpu().numpy(), orc.motion_feature_render(T, f4, z["origins"], z["dirs"], jf, sw3, ji3)) >= 0.999
+        assert rel_l2(gj.cpu().numpy(),
+                      orc.motion_feature_render_backward(T, f4, z["origins"], z["dirs"], jf, sw3, ji3, g)) <= 1e-4
     # many joints: the per-CTA gradient table no longer fits shared memory -> global atomics
     J2 = 2000
     rng = np.random.default_rng(3)
@@ -870,3 +884,29 @@ def test_grid_weight_render_vs_oracle_and_reference(dev, ndc):
         xw, xh = m.grid_weight_render(cu(grid, dev), rc, ro, cu(off, dev), cu(inv, dev))
         assert float((gh == xh.cpu().numpy()).mean()) >= 0.999
         assert frac_within(gw, xw.cpu().numpy(), atol=1e-5) >= 0.999
+
+
+def test_view_values_and_set(dev):
+    """N3TreeView.values / .set on feature rows (the reference's accessors still index `data` as floats)."""
+    tr = synth.synth_tree(4, "ball")
+    D = 6
+    f = synth.synth_features(tr["M"], D)
+    tree = make_tree(tr, D, dev)
+    tree.features = torch.nn.Parameter(cu(f, dev))
+    pts = torch.rand(300, 3, device=dev)
+    view = tree[pts]
+    rows = tree.data[view.key][..., 0].long()
+    ok = rows < tr["M"]
+    assert 0 < int(ok.sum()) < len(view)
+    vals = view.values
+    assert torch.equal(vals[ok], tree.features[rows[ok]]) and float(vals[~ok].abs().sum()) == 0.0
+    vals.sum().backward()
+    want = torch.zeros(tr["M"], device=dev)
+    want[rows[ok]] = 1.0
+    assert torch.equal(tree.features.grad[:, 0], want)
+    view.set(torch.full((len(view), D), 7.0, device=dev))
+    assert float(tree.features.detach()[rows[ok]].min()) == 7.0
+    assert int((tree.features.detach() == 7.0).all(dim=1).sum()) == int(ok.sum())
+    tree[pts[:5]] = 3.0                                           # scalar broadcast through assign_vertical
+    got = tree(tree.features.detach(), pts[:5], want_data_ids=True)
+    assert bool(((got[0] == 3.0).all(dim=1) | (got[1] < 0)).all())
