@@ -519,76 +519,89 @@ motion_feature_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs j
 // ------------------------------------------------------------------------------------------------------------
 // Motion-feature render, staged form (the one the entry points launch whenever the joint table fits shared memory).
 // Same arithmetic as the kernels above; what changes is where the per-hit operands live:
-//   * jf[J,F] sits in shared memory for the whole kernel (one copy per CTA; J*F floats);
+//   * jf[J,F] sits in shared memory for the whole kernel (one copy per CTA), rows padded to FP = 4 * LPR floats,
+//     LPR = pow2ceil(F / 4) lanes x float4 covering a row;
 //   * the march is software-pipelined like the feature render: a candidate found in iteration i is composited in
 //     iteration i+1, its sigma / skinning row / joint-index row are requested (lane-private gathers) BEFORE the traversal
 //     step of iteration i+1 and consumed after it; rows the accelerator marks "sigma <= 0" never become candidates;
-//   * the owner lane stages (weights clamped at 0 -- the reference skips w <= 0, rt_kernel.cu:955 --, joint row offsets,
-//     compositing weight) in a per-warp shared-memory slot, the warp then serves one hit at a time with lane = channel:
-//     broadcast LDS of the staged operands, NB LDS + FMA from the joint table, one sigmoid;
-//   * backward: every warp reduces dL/dJF into ITS OWN [J,F] table in shared memory with plain read-modify-writes (lane k
-//     owns column k, hits are served one at a time, so no two lanes ever touch one address) -- shared-memory float
-//     atomics are a compare-and-swap loop on this architecture (ATOMS.CAST.SPIN) -- and flushes it once at the end.
+//   * the owner lane of a hit stages (weights clamped at 0 -- the reference skips w <= 0, rt_kernel.cu:955 --, joint row
+//     offsets, compositing weight, its lane id) in the warp's shared-memory slot number rank = #hits in lower lanes:
+//     the hits of an iteration form a dense list, served without any ballot / find-first-set bookkeeping;
+//   * forward, NB == 4: 32 / LPR hits are served at once, LPR lanes x float4 each (4 hits x 8 lanes at F = 32): operands
+//     by broadcast LDS.128, four LDS.128 from the joint table, 16 FMA, 4 sigmoids, one float4 read-modify-write of the
+//     ray's partial output row;
+//   * backward: lane = channel, one hit at a time; every warp reduces dL/dJF into ITS OWN [J,FP] table in shared memory
+//     with plain read-modify-writes (lane k owns column k, so no two lanes ever touch one address) -- shared-memory
+//     float atomics are a compare-and-swap loop on this architecture (ATOMS.CAST.SPIN) -- and flushes it at the end.
 // NB4: NB == 4 with 16-byte aligned rows -> the operands travel as one float4 + one int4 per lane.
 struct MfSmem {
-    uint32_t* top; float* jf; float* rows; float* st_w; int* st_j; float* st_ww; float* table;
+    uint32_t* top; float* jf; float* rows; float* st_w; int* st_j; float2* st_wr; float* table;
 };
 
+__host__ __device__ __forceinline__ int mf_lpr(int F) { return F <= 4 ? 1 : (F <= 8 ? 2 : (F <= 16 ? 4 : 8)); }
+
 template <bool BWD>
-__device__ __forceinline__ MfSmem mf_carve(uint32_t* base, int top_words, int JF, int NB, int warp) {
+__device__ __forceinline__ MfSmem mf_carve(uint32_t* base, int top_words, int JFP, int NB, int warp) {
     MfSmem m;
     m.top = base;
     m.jf = reinterpret_cast<float*>(base + top_words);
-    const int jf_pad = (JF + 3) & ~3, nb_pad = (NB + 3) & ~3;
-    float* w0 = m.jf + jf_pad;                                       // per-warp regions follow, 16-byte aligned
-    const int per_warp = 32 * 32 + 2 * 32 * nb_pad + 32 + (BWD ? jf_pad : 0);
+    const int nb_pad = (NB + 3) & ~3;
+    float* w0 = m.jf + JFP;                                          // per-warp regions follow, 16-byte aligned
+    const int per_warp = 32 * 32 + 2 * 32 * nb_pad + 64 + (BWD ? JFP : 0);
     float* mine = w0 + (size_t)warp * per_warp;
     m.rows = mine;                                                   // fwd: partial outputs [32][32]; bwd: grad_out rows
     m.st_w = mine + 32 * 32;
     m.st_j = reinterpret_cast<int*>(m.st_w + 32 * nb_pad);
-    m.st_ww = reinterpret_cast<float*>(m.st_j + 32 * nb_pad);
-    m.table = m.st_ww + 32;
+    m.st_wr = reinterpret_cast<float2*>(m.st_j + 32 * nb_pad);
+    m.table = reinterpret_cast<float*>(m.st_wr + 32);
     return m;
 }
 
-static size_t mf_smem_bytes(bool bwd, int top_words, int JF, int NB, int warps) {
-    const int jf_pad = (JF + 3) & ~3, nb_pad = (NB + 3) & ~3;
-    const size_t per_warp = 32 * 32 + 2 * 32 * nb_pad + 32 + (bwd ? jf_pad : 0);
-    return sizeof(float) * ((size_t)top_words + jf_pad + per_warp * warps);
+static size_t mf_smem_bytes(bool bwd, int top_words, int J, int F, int NB, int warps) {
+    const int JFP = J * 4 * mf_lpr(F), nb_pad = (NB + 3) & ~3;
+    const size_t per_warp = 32 * 32 + 2 * 32 * nb_pad + 64 + (bwd ? JFP : 0);
+    return sizeof(float) * ((size_t)top_words + JFP + per_warp * warps);
 }
 
-// The owner lane's operands of its pending candidate -> this warp's staging slot.
+// The owner lane's operands of its pending candidate -> slot `slot` of this warp's hit list.
 template <bool NB4>
-__device__ __forceinline__ void mf_stage(const MfSmem& sm, const JointArgs& ja, int lane, int idx, float w,
-                                         const float4& wv, const int4& jv) {
-    const int nb_pad = (ja.NB + 3) & ~3, F = ja.F, jmax = ja.J - 1;
-    sm.st_ww[lane] = w;
+__device__ __forceinline__ void mf_stage(const MfSmem& sm, const JointArgs& ja, int FP, int slot, int lane, int idx,
+                                         float w, const float4& wv, const int4& jv) {
+    const int nb_pad = (ja.NB + 3) & ~3, jmax = ja.J - 1;
+    sm.st_wr[slot] = make_float2(w, __int_as_float(lane));
     if (NB4) {
-        reinterpret_cast<float4*>(sm.st_w)[lane] = make_float4(fmaxf(wv.x, 0.f), fmaxf(wv.y, 0.f), fmaxf(wv.z, 0.f), fmaxf(wv.w, 0.f));
-        reinterpret_cast<int4*>(sm.st_j)[lane] = make_int4(min(max(jv.x, 0), jmax) * F, min(max(jv.y, 0), jmax) * F,
-                                                           min(max(jv.z, 0), jmax) * F, min(max(jv.w, 0), jmax) * F);
+        reinterpret_cast<float4*>(sm.st_w)[slot] = make_float4(fmaxf(wv.x, 0.f), fmaxf(wv.y, 0.f), fmaxf(wv.z, 0.f), fmaxf(wv.w, 0.f));
+        reinterpret_cast<int4*>(sm.st_j)[slot] = make_int4(min(max(jv.x, 0), jmax) * FP, min(max(jv.y, 0), jmax) * FP,
+                                                           min(max(jv.z, 0), jmax) * FP, min(max(jv.w, 0), jmax) * FP);
     } else {
         const float* swr = ja.sw + (size_t)(unsigned)idx * ja.NB;
         const int32_t* jir = ja.ji + (size_t)(unsigned)idx * ja.NB;
         for (int b = 0; b < ja.NB; ++b) {
-            sm.st_w[lane * nb_pad + b] = fmaxf(__ldg(swr + b), 0.0f);
-            sm.st_j[lane * nb_pad + b] = min(max(__ldg(jir + b), 0), jmax) * F;
+            sm.st_w[slot * nb_pad + b] = fmaxf(__ldg(swr + b), 0.0f);
+            sm.st_j[slot * nb_pad + b] = min(max(__ldg(jir + b), 0), jmax) * FP;
         }
     }
 }
 
-// pos_joint_feature[lane] of the hit staged by lane r (rt_kernel.cu:953-958).
+// pos_joint_feature[lane] of the hit in slot `slot` (rt_kernel.cu:953-958); jfl = joint table + lane.
 template <bool NB4>
-__device__ __forceinline__ float mf_blend(const MfSmem& sm, int NB, int r, int lane) {
+__device__ __forceinline__ float mf_blend(const MfSmem& sm, const float* jfl, int NB, int slot) {
     if (NB4) {
-        const float4 w = reinterpret_cast<const float4*>(sm.st_w)[r];
-        const int4 j = reinterpret_cast<const int4*>(sm.st_j)[r];
-        return fmaf(w.w, sm.jf[j.w + lane], fmaf(w.z, sm.jf[j.z + lane], fmaf(w.y, sm.jf[j.y + lane], w.x * sm.jf[j.x + lane])));
+        const float4 w = reinterpret_cast<const float4*>(sm.st_w)[slot];
+        const int4 j = reinterpret_cast<const int4*>(sm.st_j)[slot];
+        return fmaf(w.w, jfl[j.w], fmaf(w.z, jfl[j.z], fmaf(w.y, jfl[j.y], w.x * jfl[j.x])));
     }
     const int nb_pad = (NB + 3) & ~3;
     float pj = 0.0f;
-    for (int b = 0; b < NB; ++b) pj = fmaf(sm.st_w[r * nb_pad + b], sm.jf[sm.st_j[r * nb_pad + b] + lane], pj);
+    for (int b = 0; b < NB; ++b) pj = fmaf(sm.st_w[slot * nb_pad + b], jfl[sm.st_j[slot * nb_pad + b]], pj);
     return pj;
+}
+
+__device__ __forceinline__ void mf_load_jf(const MfSmem& sm, const JointArgs& ja, int FP) {
+    for (int i = threadIdx.x; i < ja.J * FP; i += blockDim.x) {
+        const int j = i / FP, k = i - j * FP;
+        sm.jf[i] = k < ja.F ? __ldg(ja.jf + j * ja.F + k) : 0.0f;
+    }
 }
 
 template <bool ACCEL, bool NB4>
@@ -598,26 +611,30 @@ mf_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, float* __
     extern __shared__ __align__(128) uint32_t smem_u32[];
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     if (ACCEL) load_top(tr, smem_u32);
-    const int lane = threadIdx.x & 31, F = ja.F, JF = ja.J * ja.F;
-    const MfSmem sm = mf_carve<false>(smem_u32, top_words, JF, ja.NB, threadIdx.x >> 5);
-    for (int i = threadIdx.x; i < JF; i += blockDim.x) sm.jf[i] = __ldg(ja.jf + i);
+    const int lane = threadIdx.x & 31, F = ja.F, lpr = mf_lpr(F), FP = 4 * lpr;
+    const MfSmem sm = mf_carve<false>(smem_u32, top_words, ja.J * FP, ja.NB, threadIdx.x >> 5);
+    mf_load_jf(sm, ja, FP);
     for (int r = 0; r < 32; ++r) sm.rows[r * 32 + lane] = 0.0f;
     __syncthreads();
     const float* off = tr.offset;
     const float* scl = tr.scaling;
     const size_t sig_stride = (size_t)tr.D;
     const float* sig_base = tr.features + (tr.D - 1);
+    const float* jfl = sm.jf + lane;
+    const int q = lane / lpr, c = lane - q * lpr, rpi = 32 / lpr;
+    const float4* jf4 = reinterpret_cast<const float4*>(sm.jf) + c;     // float4 block c of every joint row
+    float4* rows4 = reinterpret_cast<float4*>(sm.rows) + c;             // ... and of every partial output row
 
     Ray ray;
     float T = 1.0f, p_dt = 0.0f;
     int row = 0, p_idx = -1;
     bool active = false, missed = false, trav_done = true;
-    Queue q{0, 0, false};
+    Queue qu{0, 0, false};
     unsigned need = FULL;
 
     while (true) {
         if (need) {
-            const unsigned got = refill<false>(src, off, scl, counter, q, need, lane, ray, row);
+            const unsigned got = refill<false>(src, off, scl, counter, qu, need, lane, ray, row);
             if ((got >> lane) & 1u) {
                 active = true; trav_done = false; T = 1.0f;
                 float a, b;                                      // a ray that misses the cube returns zeros, not the
@@ -650,23 +667,44 @@ mf_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, float* __
                 if (!(ray.t < ray.tmax)) trav_done = true;
             }
         }
-        // S2: composite the pending candidate
-        bool hit = false, stopped = false;
-        if (p_idx >= 0 && sig > opt.sigma_thresh) {
-            const float att = expf(-p_dt * ray.ds * sig);
-            mf_stage<NB4>(sm, ja, lane, p_idx, T * (1.0f - att), wv, jv);
-            hit = true;
-            T *= att;
-            if (T <= opt.stop_thresh) stopped = true;
-        }
-        unsigned hm = __ballot_sync(FULL, hit);
+        // S2: composite the pending candidates
+        const bool hit = p_idx >= 0 && sig > opt.sigma_thresh;
+        const unsigned hm = __ballot_sync(FULL, hit);
+        bool stopped = false;
         if (hm) {
+            if (hit) {
+                const float att = expf(-p_dt * ray.ds * sig);
+                mf_stage<NB4>(sm, ja, FP, __popc(hm & ((1u << lane) - 1u)), lane, p_idx, T * (1.0f - att), wv, jv);
+                T *= att;
+                if (T <= opt.stop_thresh) stopped = true;
+            }
             __syncwarp();
-            while (hm) {
-                const int r = __ffs(hm) - 1;
-                hm &= hm - 1;
-                if (lane < F)
-                    sm.rows[r * 32 + lane] = fmaf(sm.st_ww[r], fast_sigmoid(mf_blend<NB4>(sm, ja.NB, r, lane)), sm.rows[r * 32 + lane]);
+            const int nh = __popc(hm);
+            if (NB4) {
+                for (int slot = q; slot < nh; slot += rpi) {
+                    const float4 w = reinterpret_cast<const float4*>(sm.st_w)[slot];
+                    const int4 j = reinterpret_cast<const int4*>(sm.st_j)[slot];
+                    const float2 wr = sm.st_wr[slot];
+                    const float4 a0 = jf4[j.x >> 2], a1 = jf4[j.y >> 2], a2 = jf4[j.z >> 2], a3 = jf4[j.w >> 2];
+                    float4 pj;
+                    pj.x = fmaf(w.w, a3.x, fmaf(w.z, a2.x, fmaf(w.y, a1.x, w.x * a0.x)));
+                    pj.y = fmaf(w.w, a3.y, fmaf(w.z, a2.y, fmaf(w.y, a1.y, w.x * a0.y)));
+                    pj.z = fmaf(w.w, a3.z, fmaf(w.z, a2.z, fmaf(w.y, a1.z, w.x * a0.z)));
+                    pj.w = fmaf(w.w, a3.w, fmaf(w.z, a2.w, fmaf(w.y, a1.w, w.x * a0.w)));
+                    float4* ar = rows4 + __float_as_int(wr.y) * 8;
+                    float4 acc = *ar;
+                    acc.x = fmaf(wr.x, fast_sigmoid(pj.x), acc.x);
+                    acc.y = fmaf(wr.x, fast_sigmoid(pj.y), acc.y);
+                    acc.z = fmaf(wr.x, fast_sigmoid(pj.z), acc.z);
+                    acc.w = fmaf(wr.x, fast_sigmoid(pj.w), acc.w);
+                    *ar = acc;
+                }
+            } else if (lane < F) {
+                for (int slot = 0; slot < nh; ++slot) {
+                    const float2 wr = sm.st_wr[slot];
+                    float* ar = sm.rows + __float_as_int(wr.y) * 32 + lane;
+                    *ar = fmaf(wr.x, fast_sigmoid(mf_blend<false>(sm, jfl, ja.NB, slot)), *ar);
+                }
             }
             __syncwarp();
         }
@@ -684,15 +722,16 @@ mf_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, float* __
                 const float T_r = __shfl_sync(FULL, T, r);
                 const int fin_r = __shfl_sync(FULL, fin, r);
                 const int row_r = __shfl_sync(FULL, row, r);
+                float v = sm.rows[r * 32 + lane];
+                sm.rows[r * 32 + lane] = 0.0f;                                   // padding channels included
                 if (lane < F) {
-                    float v = sm.rows[r * 32 + lane];
                     if (fin_r == 2) v *= (float)(1.0 / (1.0 - (double)T_r));     // rt_kernel.cu:966-970
                     else if (fin_r == 1) v += T_r * opt.bg;                      // rt_kernel.cu:975-977
                     else v = 0.0f;
                     __stcs(out + (int64_t)row_r * F + lane, v);
-                    sm.rows[r * 32 + lane] = 0.0f;
                 }
             }
+            __syncwarp();
         }
     }
 }
@@ -704,26 +743,29 @@ mf_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, const flo
     extern __shared__ __align__(128) uint32_t smem_u32[];
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     if (ACCEL) load_top(tr, smem_u32);
-    const int lane = threadIdx.x & 31, F = ja.F, JF = ja.J * ja.F;
-    const MfSmem sm = mf_carve<true>(smem_u32, top_words, JF, ja.NB, threadIdx.x >> 5);
-    for (int i = threadIdx.x; i < JF; i += blockDim.x) sm.jf[i] = __ldg(ja.jf + i);
-    for (int i = lane; i < JF; i += 32) sm.table[i] = 0.0f;
+    const int lane = threadIdx.x & 31, F = ja.F, FP = 4 * mf_lpr(F), JFP = ja.J * FP;
+    const MfSmem sm = mf_carve<true>(smem_u32, top_words, JFP, ja.NB, threadIdx.x >> 5);
+    mf_load_jf(sm, ja, FP);
+    for (int i = lane; i < JFP; i += 32) sm.table[i] = 0.0f;
     __syncthreads();
     const float* off = tr.offset;
     const float* scl = tr.scaling;
     const size_t sig_stride = (size_t)tr.D;
     const float* sig_base = tr.features + (tr.D - 1);
+    const float* jfl = sm.jf + lane;
+    float* tbl = sm.table + lane;
+    const float* gl = sm.rows + lane;
 
     Ray ray;
     float T = 1.0f, p_dt = 0.0f;
     int row = 0, p_idx = -1;
     bool active = false, trav_done = true;
-    Queue q{0, 0, false};
+    Queue qu{0, 0, false};
     unsigned need = FULL;
 
     while (true) {
         if (need) {
-            unsigned got = refill<false>(src, off, scl, counter, q, need, lane, ray, row);
+            unsigned got = refill<false>(src, off, scl, counter, qu, need, lane, ray, row);
             if ((got >> lane) & 1u) { active = true; trav_done = false; T = 1.0f; }
             need = 0;
             while (got) {
@@ -756,35 +798,43 @@ mf_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, const flo
                 if (!(ray.t < ray.tmax)) trav_done = true;
             }
         }
-        bool hit = false;
-        if (p_idx >= 0 && sig > 0.0f) {                                           // rt_kernel.cu:1029
-            const float att = expf(-p_dt * sig * ray.ds);
-            mf_stage<NB4>(sm, ja, lane, p_idx, T * (1.0f - att), wv, jv);
-            hit = true;
-            T *= att;
-        }
-        unsigned hm = __ballot_sync(FULL, hit);
+        const bool hit = p_idx >= 0 && sig > 0.0f;                                // rt_kernel.cu:1029
+        const unsigned hm = __ballot_sync(FULL, hit);
         if (hm) {
+            if (hit) {
+                const float att = expf(-p_dt * sig * ray.ds);
+                mf_stage<NB4>(sm, ja, FP, __popc(hm & ((1u << lane) - 1u)), lane, p_idx, T * (1.0f - att), wv, jv);
+                T *= att;
+            }
             __syncwarp();
-            while (hm) {
-                const int r = __ffs(hm) - 1;
-                hm &= hm - 1;
-                if (lane < F) {
-                    const float s = fast_sigmoid(mf_blend<NB4>(sm, ja.NB, r, lane));
-                    const float sg = s * sm.rows[r * 32 + lane];
-                    const float gt = sm.st_ww[r] * fmaf(-sg, s, sg);              // weight * s (1 - s) * g
+            const int nh = __popc(hm);
+            if (lane < F) {
+                for (int slot = 0; slot < nh; ++slot) {
+                    const float2 wr = sm.st_wr[slot];
+                    const float s = fast_sigmoid(mf_blend<NB4>(sm, jfl, ja.NB, slot));
+                    const float sg = s * gl[__float_as_int(wr.y) * 32];
+                    const float gt = wr.x * fmaf(-sg, s, sg);                     // weight * s (1 - s) * g
                     if (NB4) {
-                        const float4 w = reinterpret_cast<const float4*>(sm.st_w)[r];
-                        const int4 j = reinterpret_cast<const int4*>(sm.st_j)[r];
-                        sm.table[j.x + lane] = fmaf(w.x, gt, sm.table[j.x + lane]);     // in order: a joint may repeat
-                        sm.table[j.y + lane] = fmaf(w.y, gt, sm.table[j.y + lane]);
-                        sm.table[j.z + lane] = fmaf(w.z, gt, sm.table[j.z + lane]);
-                        sm.table[j.w + lane] = fmaf(w.w, gt, sm.table[j.w + lane]);
+                        const float4 w = reinterpret_cast<const float4*>(sm.st_w)[slot];
+                        const int4 j = reinterpret_cast<const int4*>(sm.st_j)[slot];
+                        const bool distinct = j.x != j.y && j.x != j.z && j.x != j.w && j.y != j.z && j.y != j.w && j.z != j.w;
+                        if (distinct) {           // four independent read-modify-writes: loads first, then the stores
+                            const float t0 = tbl[j.x], t1 = tbl[j.y], t2 = tbl[j.z], t3 = tbl[j.w];
+                            tbl[j.x] = fmaf(w.x, gt, t0);
+                            tbl[j.y] = fmaf(w.y, gt, t1);
+                            tbl[j.z] = fmaf(w.z, gt, t2);
+                            tbl[j.w] = fmaf(w.w, gt, t3);
+                        } else {                  // a joint repeats within the row: keep the updates in order
+                            tbl[j.x] = fmaf(w.x, gt, tbl[j.x]);
+                            tbl[j.y] = fmaf(w.y, gt, tbl[j.y]);
+                            tbl[j.z] = fmaf(w.z, gt, tbl[j.z]);
+                            tbl[j.w] = fmaf(w.w, gt, tbl[j.w]);
+                        }
                     } else {
                         const int nb_pad = (ja.NB + 3) & ~3;
                         for (int b = 0; b < ja.NB; ++b) {
-                            float* t = sm.table + sm.st_j[r * nb_pad + b] + lane;
-                            *t = fmaf(sm.st_w[r * nb_pad + b], gt, *t);
+                            float* t = tbl + sm.st_j[slot * nb_pad + b];
+                            *t = fmaf(sm.st_w[slot * nb_pad + b], gt, *t);
                         }
                     }
                 }
@@ -799,9 +849,10 @@ mf_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, const flo
             need = fm;
         }
     }
-    for (int i = lane; i < JF; i += 32) {
+    for (int i = lane; i < JFP; i += 32) {
+        const int j = i / FP, k = i - j * FP;
         const float v = sm.table[i];
-        if (v != 0.0f) atomicAdd(grad_jf + i, v);
+        if (k < F && v != 0.0f) atomicAdd(grad_jf + j * F + k, v);
     }
 }
 
@@ -920,7 +971,7 @@ static int make_joint_args(const svoxb_tree* tree, const float* jf, const float*
 // top grid and the per-warp rows; two CTAs per SM should still fit.
 static bool mf_staged_ok(const TreeArgs& tr, const JointArgs& ja, bool bwd) {
     const int top_words = tr.use_accel ? (1 << (3 * tr.acc.bits[0])) : 0;
-    return ja.NB <= 16 && mf_smem_bytes(bwd, top_words, ja.J * ja.F, ja.NB, WARPS) <= 100 * 1024;
+    return ja.NB <= 16 && mf_smem_bytes(bwd, top_words, ja.J, ja.F, ja.NB, WARPS) <= 100 * 1024;
 }
 static bool mf_nb4(const JointArgs& ja) {
     return ja.NB == 4 && (((uintptr_t)ja.sw | (uintptr_t)ja.ji) & 15) == 0;
@@ -951,7 +1002,7 @@ extern "C" int svoxb_motion_feature_render_fwd(const svoxb_tree* tree, const flo
     if (mf_staged_ok(tr, ja, false)) {
         if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;      // the marks encode sigma > 0: too strict for this predicate
         const int top_words = tr.use_accel ? (1 << (3 * tr.acc.bits[0])) : 0;
-        const size_t smem2 = mf_smem_bytes(false, top_words, J * F, B, WARPS);
+        const size_t smem2 = mf_smem_bytes(false, top_words, J, F, B, WARPS);
         const bool nb4 = mf_nb4(ja);
         void (*k2)(TreeArgs, RaySource, MarchOpts, JointArgs, float*, unsigned long long*) =
             tr.use_accel ? (nb4 ? mf_fwd_kernel<true, true> : mf_fwd_kernel<true, false>)
@@ -995,7 +1046,7 @@ extern "C" int svoxb_motion_feature_render_bwd(const svoxb_tree* tree, const flo
     RaySource src{}; src.origins = origins; src.dirs = dirs; src.total = Q; src.ndc_w = -1;
     if (mf_staged_ok(tr, ja, true)) {
         const int top_words = tr.use_accel ? (1 << (3 * tr.acc.bits[0])) : 0;
-        const size_t smem2 = mf_smem_bytes(true, top_words, J * F, B, WARPS);
+        const size_t smem2 = mf_smem_bytes(true, top_words, J, F, B, WARPS);
         const bool nb4 = mf_nb4(ja);
         void (*k2)(TreeArgs, RaySource, MarchOpts, JointArgs, const float*, float*, unsigned long long*) =
             tr.use_accel ? (nb4 ? mf_bwd_kernel<true, true> : mf_bwd_kernel<true, false>)
