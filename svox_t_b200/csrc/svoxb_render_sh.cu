@@ -20,6 +20,7 @@
 //   motion feature : lane k < F accumulates sum_j w_j * JF[joint_j][k] (the joint table is a few KB, L1-resident);
 //                    the backward reduces dL/dJF in a per-CTA shared-memory table (J x F addresses receive every
 //                    contribution of every ray -- global atomics would serialise on them) and flushes it once.
+#include <stdlib.h>
 #include "svoxb_march.cuh"
 
 namespace svoxb {
@@ -540,14 +541,14 @@ struct MfSmem {
 
 __host__ __device__ __forceinline__ int mf_lpr(int F) { return F <= 4 ? 1 : (F <= 8 ? 2 : (F <= 16 ? 4 : 8)); }
 
-template <bool BWD>
+template <int TABLES>       // gradient tables per warp (0 in the forward)
 __device__ __forceinline__ MfSmem mf_carve(uint32_t* base, int top_words, int JFP, int NB, int warp) {
     MfSmem m;
     m.top = base;
     m.jf = reinterpret_cast<float*>(base + top_words);
     const int nb_pad = (NB + 3) & ~3;
     float* w0 = m.jf + JFP;                                          // per-warp regions follow, 16-byte aligned
-    const int per_warp = 32 * 32 + 2 * 32 * nb_pad + 64 + (BWD ? JFP : 0);
+    const int per_warp = 32 * 32 + 2 * 32 * nb_pad + 64 + TABLES * JFP;
     float* mine = w0 + (size_t)warp * per_warp;
     m.rows = mine;                                                   // fwd: partial outputs [32][32]; bwd: grad_out rows
     m.st_w = mine + 32 * 32;
@@ -557,9 +558,9 @@ __device__ __forceinline__ MfSmem mf_carve(uint32_t* base, int top_words, int JF
     return m;
 }
 
-static size_t mf_smem_bytes(bool bwd, int top_words, int J, int F, int NB, int warps) {
+static size_t mf_smem_bytes(int tables, int top_words, int J, int F, int NB, int warps) {
     const int JFP = J * 4 * mf_lpr(F), nb_pad = (NB + 3) & ~3;
-    const size_t per_warp = 32 * 32 + 2 * 32 * nb_pad + 64 + (bwd ? JFP : 0);
+    const size_t per_warp = 32 * 32 + 2 * 32 * nb_pad + 64 + (size_t)tables * JFP;
     return sizeof(float) * ((size_t)top_words + JFP + per_warp * warps);
 }
 
@@ -612,7 +613,7 @@ mf_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, float* __
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     if (ACCEL) load_top(tr, smem_u32);
     const int lane = threadIdx.x & 31, F = ja.F, lpr = mf_lpr(F), FP = 4 * lpr;
-    const MfSmem sm = mf_carve<false>(smem_u32, top_words, ja.J * FP, ja.NB, threadIdx.x >> 5);
+    const MfSmem sm = mf_carve<0>(smem_u32, top_words, ja.J * FP, ja.NB, threadIdx.x >> 5);
     mf_load_jf(sm, ja, FP);
     for (int r = 0; r < 32; ++r) sm.rows[r * 32 + lane] = 0.0f;
     __syncthreads();
@@ -736,7 +737,28 @@ mf_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, float* __
     }
 }
 
-template <bool ACCEL, bool NB4>
+// HP = hits served at once in the backward = private gradient tables per warp: 1 (lane = channel), or -- NB == 4 and
+// 16 < F <= 32 -- 2 / 4 with 16 / 8 lanes x float2 / float4 per hit.
+template <int HP> struct MfVec;
+template <> struct MfVec<2> { using T = float2; };
+template <> struct MfVec<4> { using T = float4; };
+__device__ __forceinline__ float2 mf_axpy(float a, float2 x, float2 y) { return make_float2(fmaf(a, x.x, y.x), fmaf(a, x.y, y.y)); }
+__device__ __forceinline__ float4 mf_axpy(float a, float4 x, float4 y) {
+    return make_float4(fmaf(a, x.x, y.x), fmaf(a, x.y, y.y), fmaf(a, x.z, y.z), fmaf(a, x.w, y.w));
+}
+__device__ __forceinline__ float2 mf_scale(float a, float2 x) { return make_float2(a * x.x, a * x.y); }
+__device__ __forceinline__ float4 mf_scale(float a, float4 x) { return make_float4(a * x.x, a * x.y, a * x.z, a * x.w); }
+// weight * s (1 - s) * g per component, s = sigmoid(pj)
+__device__ __forceinline__ float mf_gt1(float wgt, float pj, float g) {
+    const float s = fast_sigmoid(pj), sg = s * g;
+    return wgt * fmaf(-sg, s, sg);
+}
+__device__ __forceinline__ float2 mf_gt(float wgt, float2 pj, float2 g) { return make_float2(mf_gt1(wgt, pj.x, g.x), mf_gt1(wgt, pj.y, g.y)); }
+__device__ __forceinline__ float4 mf_gt(float wgt, float4 pj, float4 g) {
+    return make_float4(mf_gt1(wgt, pj.x, g.x), mf_gt1(wgt, pj.y, g.y), mf_gt1(wgt, pj.z, g.z), mf_gt1(wgt, pj.w, g.w));
+}
+
+template <bool ACCEL, bool NB4, int HP>
 __global__ void __launch_bounds__(BLOCK)
 mf_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, const float* __restrict__ grad_out,
               float* __restrict__ grad_jf, unsigned long long* counter) {
@@ -744,9 +766,9 @@ mf_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, const flo
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     if (ACCEL) load_top(tr, smem_u32);
     const int lane = threadIdx.x & 31, F = ja.F, FP = 4 * mf_lpr(F), JFP = ja.J * FP;
-    const MfSmem sm = mf_carve<true>(smem_u32, top_words, JFP, ja.NB, threadIdx.x >> 5);
+    const MfSmem sm = mf_carve<HP>(smem_u32, top_words, JFP, ja.NB, threadIdx.x >> 5);
     mf_load_jf(sm, ja, FP);
-    for (int i = lane; i < JFP; i += 32) sm.table[i] = 0.0f;
+    for (int i = lane; i < HP * JFP; i += 32) sm.table[i] = 0.0f;
     __syncthreads();
     const float* off = tr.offset;
     const float* scl = tr.scaling;
@@ -808,6 +830,35 @@ mf_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, const flo
             }
             __syncwarp();
             const int nh = __popc(hm);
+            if constexpr (HP > 1) {
+                using V = typename MfVec<HP>::T;
+                constexpr int LPH = 32 / HP;                                      // lanes per hit; FP == 32 == LPH * HP
+                const int h = lane / LPH, c = lane % LPH;
+                const V* jfv = reinterpret_cast<const V*>(sm.jf) + c;
+                const V* gv = reinterpret_cast<const V*>(sm.rows) + c;
+                V* tb = reinterpret_cast<V*>(sm.table + h * JFP) + c;             // this hit slot's private table
+                for (int slot = h; slot < nh; slot += HP) {
+                    const float2 wr = sm.st_wr[slot];
+                    const float4 w = reinterpret_cast<const float4*>(sm.st_w)[slot];
+                    int4 j = reinterpret_cast<const int4*>(sm.st_j)[slot];
+                    j.x /= HP; j.y /= HP; j.z /= HP; j.w /= HP;                   // float offsets -> vector offsets
+                    const V pj = mf_axpy(w.w, jfv[j.w], mf_axpy(w.z, jfv[j.z], mf_axpy(w.y, jfv[j.y], mf_scale(w.x, jfv[j.x]))));
+                    const V gt = mf_gt(wr.x, pj, gv[__float_as_int(wr.y) * LPH]);
+                    const bool distinct = j.x != j.y && j.x != j.z && j.x != j.w && j.y != j.z && j.y != j.w && j.z != j.w;
+                    if (distinct) {
+                        const V t0 = tb[j.x], t1 = tb[j.y], t2 = tb[j.z], t3 = tb[j.w];
+                        tb[j.x] = mf_axpy(w.x, gt, t0);
+                        tb[j.y] = mf_axpy(w.y, gt, t1);
+                        tb[j.z] = mf_axpy(w.z, gt, t2);
+                        tb[j.w] = mf_axpy(w.w, gt, t3);
+                    } else {
+                        tb[j.x] = mf_axpy(w.x, gt, tb[j.x]);
+                        tb[j.y] = mf_axpy(w.y, gt, tb[j.y]);
+                        tb[j.z] = mf_axpy(w.z, gt, tb[j.z]);
+                        tb[j.w] = mf_axpy(w.w, gt, tb[j.w]);
+                    }
+                }
+            } else
             if (lane < F) {
                 for (int slot = 0; slot < nh; ++slot) {
                     const float2 wr = sm.st_wr[slot];
@@ -849,11 +900,200 @@ mf_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, const flo
             need = fm;
         }
     }
+    __syncwarp();
     for (int i = lane; i < JFP; i += 32) {
         const int j = i / FP, k = i - j * FP;
-        const float v = sm.table[i];
+        float v = sm.table[i];
+#pragma unroll
+        for (int t = 1; t < HP; ++t) v += sm.table[t * JFP + i];
         if (k < F && v != 0.0f) atomicAdd(grad_jf + j * F + k, v);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Motion-feature render, table form (large ray batches). The blended joint feature of a hit depends on the leaf row
+// only: pos_joint_feature[idx][k] = sum_b sw[idx][b] jf[ji[idx][b]][k] (rt_kernel.cu:953-958). With Q * 32 >= M rays a
+// row is hit many times (77 at C3), so the blend + sigmoid is evaluated ONCE PER ROW into a table laid out exactly like
+// the pre-activated feature table of the RGBA render ([M, F+1] rows with the raw sigma last when (F+1) % 4 == 0, else
+// payload rows padded to a multiple of 4 floats + a compact sigma array) and the march itself is the feature render's
+// quad kernel on that table. Backward: the quad backward reduces dL/d(pre-sigmoid blend) per row (its sigma gradients
+// are computed into a column nobody reads), and one pass over the rows folds them into dL/dJF through the rows'
+// skinning weights -- M * NB * F multiply-adds instead of (#hits) * NB * F.
+__global__ void __launch_bounds__(256)
+mf_table_kernel(JointArgs ja, const float* __restrict__ features, int64_t M, int D, int stride, int full_rows,
+                float* __restrict__ table, float* __restrict__ sigma) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < M; r += warps_total) {
+        const float* swr = ja.sw + r * ja.NB;
+        const int32_t* jir = ja.ji + r * ja.NB;
+        for (int k = lane; k < stride; k += 32) {
+            float v = 0.0f;
+            if (k < ja.F) {
+                float pj = 0.0f;
+                for (int b = 0; b < ja.NB; ++b) {
+                    const float w = __ldg(swr + b);
+                    if (w > 0.0f) pj += w * __ldg(ja.jf + (size_t)min(max(__ldg(jir + b), 0), ja.J - 1) * ja.F + k);
+                }
+                v = fast_sigmoid(pj);
+            } else if (full_rows && k == ja.F) {
+                v = __ldg(features + r * D + (D - 1));
+            }
+            table[r * stride + k] = v;
+        }
+        if (!full_rows && lane == 0) sigma[r] = __ldg(features + r * D + (D - 1));
+    }
+}
+
+// out[q, 0:F] = tmp[q, 0:F], zeros for rays that miss the cube (rt_kernel.cu:911-916).
+__global__ void __launch_bounds__(256)
+mf_finish_kernel(const float* __restrict__ tmp, const float* __restrict__ origins, const float* __restrict__ dirs,
+                 const float* __restrict__ off, const float* __restrict__ scl, int64_t Q, int F, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < Q; q += warps_total) {
+        Ray ray;
+        ray_setup(off, scl, __ldg(origins + 3 * q), __ldg(origins + 3 * q + 1), __ldg(origins + 3 * q + 2),
+                  __ldg(dirs + 3 * q), __ldg(dirs + 3 * q + 1), __ldg(dirs + 3 * q + 2), ray);
+        float a, b;
+        dda_unit(ray.ox, ray.oy, ray.oz, ray.ix, ray.iy, ray.iz, a, b);
+        const bool missed = b < 0.0f || a > b;
+        for (int k = lane; k < F; k += 32) __stcs(out + q * F + k, missed ? 0.0f : __ldcs(tmp + q * (F + 1) + k));
+    }
+}
+
+// gpad[q, 0:F] = grad_out[q, 0:F], gpad[q, F] = 0 (no gradient enters through the opacity column).
+__global__ void __launch_bounds__(256)
+mf_pad_grad_kernel(const float* __restrict__ g, int64_t Q, int F, float* __restrict__ gpad) {
+    const int64_t n = Q * (F + 1);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = i / (F + 1);
+        const int k = (int)(i - q * (F + 1));
+        gpad[i] = k < F ? __ldcs(g + q * F + k) : 0.0f;
+    }
+}
+
+// grad_jf[ji[r][b]][k] += sw[r][b] * gpre[r][k]: lane = channel, one [J,F] table per warp in shared memory (plain
+// read-modify-writes), flushed with one atomic per entry and warp. use_table == 0: global atomics per contribution.
+__global__ void __launch_bounds__(256)
+mf_fold_kernel(JointArgs ja, const float* __restrict__ gpre, int64_t M, int D2, int use_table, float* __restrict__ grad_jf) {
+    extern __shared__ __align__(16) float fold_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, JF = ja.J * ja.F;
+    float* tbl = use_table ? fold_smem + (size_t)warp * JF : grad_jf;
+    if (use_table) for (int i = lane; i < JF; i += 32) tbl[i] = 0.0f;
+    __syncwarp();
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < M; r += warps_total) {
+        const float* swr = ja.sw + r * ja.NB;
+        const int32_t* jir = ja.ji + r * ja.NB;
+        for (int k = lane; k < ja.F; k += 32) {
+            const float g = __ldcs(gpre + r * D2 + k);
+            if (g == 0.0f) continue;
+            for (int b = 0; b < ja.NB; ++b) {
+                const float w = __ldg(swr + b);
+                if (!(w > 0.0f)) continue;
+                float* t = tbl + (size_t)min(max(__ldg(jir + b), 0), ja.J - 1) * ja.F + k;
+                if (use_table) *t = fmaf(w, g, *t);
+                else atomicAdd(t, w * g);
+            }
+        }
+    }
+    if (use_table) {
+        __syncwarp();
+        for (int i = lane; i < JF; i += 32)
+            if (tbl[i] != 0.0f) atomicAdd(grad_jf + i, tbl[i]);
+    }
+}
+
+int scratch_alloc(void** p, size_t bytes, cudaStream_t st);   // svoxb_tree.cu: stream-ordered pool
+
+// Worth it when every row is visited many times (the same rule the renderer uses for the activated table).
+static bool mf_table_route(const TreeArgs& tr, const JointArgs& ja, int64_t Q) {
+    static const int force = getenv("SVOXB_MF_TABLE") ? atoi(getenv("SVOXB_MF_TABLE")) : -1;
+    if (force >= 0) return force != 0 && ja.F + 1 <= 128;
+    return ja.F + 1 <= 128 && tr.M > 0 && Q * 32 >= tr.M;
+}
+
+struct MfTable {
+    TreeArgs tr2;        // the tree as the quad kernels see it: D = F + 1, rows = blend table
+    float* mem = nullptr;
+};
+
+static int mf_make_table(const TreeArgs& tr, const JointArgs& ja, cudaStream_t st, MfTable& t) {
+    const int D2 = ja.F + 1;
+    const bool full = D2 % 4 == 0;
+    const int stride = full ? D2 : (ja.F + 3) / 4 * 4;
+    const size_t n_tab = (size_t)tr.M * stride, n_sig = full ? 0 : (size_t)tr.M;
+    int rc = scratch_alloc((void**)&t.mem, sizeof(float) * (n_tab + n_sig), st);
+    if (rc) return rc;
+    const int grid = (int)min((tr.M * 32 + 255) / 256, (int64_t)sm_count() * 16);
+    mf_table_kernel<<<grid, 256, 0, st>>>(ja, tr.features, tr.M, tr.D, stride, full ? 1 : 0, t.mem, t.mem + n_tab);
+    count_launch();
+    t.tr2 = tr;
+    t.tr2.D = D2;
+    t.tr2.features = t.mem;
+    t.tr2.feat_act = t.mem;
+    t.tr2.act_stride = stride;
+    t.tr2.sigma_c = full ? nullptr : t.mem + n_tab;
+    return check_cuda(cudaGetLastError(), "mf_table_kernel launch");
+}
+
+static int mf_table_fwd(const TreeArgs& tr, const JointArgs& ja, const RaySource& src, const MarchOpts& m, float* out,
+                        cudaStream_t st) {
+    MfTable t;
+    int rc = mf_make_table(tr, ja, st, t);
+    if (rc) return rc;
+    float* tmp = nullptr;
+    rc = scratch_alloc((void**)&tmp, sizeof(float) * (size_t)src.total * (ja.F + 1), st);
+    if (rc == 0) rc = launch_fwd_quad(t.tr2, src, m, false, tmp, nullptr, st);
+    if (rc == 0) {
+        const int grid = (int)min((src.total * 32 + 255) / 256, (int64_t)sm_count() * 16);
+        mf_finish_kernel<<<grid, 256, 0, st>>>(tmp, src.origins, src.dirs, tr.offset, tr.scaling, src.total, ja.F, out);
+        count_launch();
+        rc = check_cuda(cudaGetLastError(), "mf_finish_kernel launch");
+    }
+    if (tmp) cudaFreeAsync(tmp, st);
+    cudaFreeAsync(t.mem, st);
+    return rc;
+}
+
+static int mf_table_bwd(const TreeArgs& tr, const JointArgs& ja, const RaySource& src, const MarchOpts& m,
+                        const float* grad_out, float* grad_jf, cudaStream_t st) {
+    MfTable t;
+    int rc = mf_make_table(tr, ja, st, t);
+    if (rc) return rc;
+    const int D2 = ja.F + 1;
+    const size_t n_pad = (size_t)src.total * D2, n_pre = (size_t)tr.M * D2;
+    float* buf = nullptr;
+    rc = scratch_alloc((void**)&buf, sizeof(float) * (n_pad + n_pre), st);
+    if (rc == 0) {
+        float* gpad = buf;
+        float* gpre = buf + n_pad;
+        rc = check_cuda(cudaMemsetAsync(gpre, 0, sizeof(float) * n_pre, st), "memset");
+        if (rc == 0) {
+            const int grid = (int)min(((int64_t)n_pad + 255) / 256, (int64_t)sm_count() * 16);
+            mf_pad_grad_kernel<<<grid, 256, 0, st>>>(grad_out, src.total, ja.F, gpad);
+            count_launch();
+            // saved_out only feeds the sigma gradients, which land in a column nobody reads: any finite rows will do
+            rc = launch_bwd_quad(t.tr2, src, m, false, gpad, gpad, gpre, st);
+        }
+        if (rc == 0) {
+            const size_t tab = sizeof(float) * (size_t)ja.J * ja.F * 8;
+            const int use_table = tab <= 96 * 1024;
+            auto kern = mf_fold_kernel;
+            if (use_table && tab > 47 * 1024)
+                rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab), "smem opt-in");
+            if (rc == 0) {
+                const int grid = (int)min((tr.M * 32 + 255) / 256, (int64_t)sm_count() * 4);
+                kern<<<grid, 256, use_table ? tab : 0, st>>>(ja, gpre, tr.M, D2, use_table, grad_jf);
+                count_launch();
+                rc = check_cuda(cudaGetLastError(), "mf_fold_kernel launch");
+            }
+        }
+    }
+    if (buf) cudaFreeAsync(buf, st);
+    cudaFreeAsync(t.mem, st);
+    return rc;
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -961,7 +1201,7 @@ int fmt_render_bwd(const svoxb_tree* tree, const TreeArgs& tr, const RaySource& 
 static int make_joint_args(const svoxb_tree* tree, const float* jf, const float* sw, const int32_t* ji, int J, int F,
                            int NB, JointArgs& ja) {
     SVOXB_REQUIRE(jf && sw && ji, "joint_features / skinning_weights / joint_index are NULL");
-    SVOXB_REQUIRE(J >= 1 && F >= 1 && F <= 32 && NB >= 1, "motion feature render: J=%d, F=%d (max 32), B=%d", J, F, NB);
+    SVOXB_REQUIRE(J >= 1 && F >= 1 && F <= 127 && NB >= 1, "motion feature render: J=%d, F=%d (max 127), B=%d", J, F, NB);
     (void)tree;
     ja.jf = jf; ja.sw = sw; ja.ji = ji; ja.J = J; ja.F = F; ja.NB = NB;
     return 0;
@@ -969,9 +1209,10 @@ static int make_joint_args(const svoxb_tree* tree, const float* jf, const float*
 
 // The staged kernels need the joint table (and, backward, one gradient table per warp) in shared memory next to the
 // top grid and the per-warp rows; two CTAs per SM should still fit.
-static bool mf_staged_ok(const TreeArgs& tr, const JointArgs& ja, bool bwd) {
+static bool mf_staged_ok(const TreeArgs& tr, const JointArgs& ja, int tables) {
     const int top_words = tr.use_accel ? (1 << (3 * tr.acc.bits[0])) : 0;
-    return ja.NB <= 16 && mf_smem_bytes(bwd, top_words, ja.J, ja.F, ja.NB, WARPS) <= 100 * 1024;
+    static const int limit_kb = getenv("SVOXB_MF_SMEM_KB") ? atoi(getenv("SVOXB_MF_SMEM_KB")) : 110;   // two CTAs per SM
+    return ja.NB <= 16 && mf_smem_bytes(tables, top_words, ja.J, ja.F, ja.NB, WARPS) <= (size_t)limit_kb * 1024;
 }
 static bool mf_nb4(const JointArgs& ja) {
     return ja.NB == 4 && (((uintptr_t)ja.sw | (uintptr_t)ja.ji) & 15) == 0;
@@ -999,10 +1240,13 @@ extern "C" int svoxb_motion_feature_render_fwd(const svoxb_tree* tree, const flo
     MarchOpts m{opt->step_size, opt->background_brightness, opt->sigma_thresh, opt->stop_thresh};
     RaySource src{}; src.origins = origins; src.dirs = dirs; src.total = Q; src.ndc_w = -1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (mf_staged_ok(tr, ja, false)) {
+    if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;          // the marks encode sigma > 0: too strict for this predicate
+    if (mf_table_route(tr, ja, Q)) return mf_table_fwd(tr, ja, src, m, out, st);
+    SVOXB_REQUIRE(F <= 32, "motion feature render: F=%d > 32 needs a large ray batch (Q * 32 >= M, the table form)", F);
+    if (mf_staged_ok(tr, ja, 0)) {
         if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;      // the marks encode sigma > 0: too strict for this predicate
         const int top_words = tr.use_accel ? (1 << (3 * tr.acc.bits[0])) : 0;
-        const size_t smem2 = mf_smem_bytes(false, top_words, J, F, B, WARPS);
+        const size_t smem2 = mf_smem_bytes(0, top_words, J, F, B, WARPS);
         const bool nb4 = mf_nb4(ja);
         void (*k2)(TreeArgs, RaySource, MarchOpts, JointArgs, float*, unsigned long long*) =
             tr.use_accel ? (nb4 ? mf_fwd_kernel<true, true> : mf_fwd_kernel<true, false>)
@@ -1044,13 +1288,23 @@ extern "C" int svoxb_motion_feature_render_bwd(const svoxb_tree* tree, const flo
     if (Q == 0) return 0;
     MarchOpts m{opt->step_size, opt->background_brightness, opt->sigma_thresh, opt->stop_thresh};
     RaySource src{}; src.origins = origins; src.dirs = dirs; src.total = Q; src.ndc_w = -1;
-    if (mf_staged_ok(tr, ja, true)) {
+    if (mf_table_route(tr, ja, Q)) return mf_table_bwd(tr, ja, src, m, grad_out, grad_joint_features, st);
+    SVOXB_REQUIRE(F <= 32, "motion feature render: F=%d > 32 needs a large ray batch (Q * 32 >= M, the table form)", F);
+    if (mf_staged_ok(tr, ja, 1)) {
         const int top_words = tr.use_accel ? (1 << (3 * tr.acc.bits[0])) : 0;
-        const size_t smem2 = mf_smem_bytes(true, top_words, J, F, B, WARPS);
         const bool nb4 = mf_nb4(ja);
-        void (*k2)(TreeArgs, RaySource, MarchOpts, JointArgs, const float*, float*, unsigned long long*) =
-            tr.use_accel ? (nb4 ? mf_bwd_kernel<true, true> : mf_bwd_kernel<true, false>)
-                         : (nb4 ? mf_bwd_kernel<false, true> : mf_bwd_kernel<false, false>);
+        // hits served at once = private tables per warp: as many as still leave two CTAs per SM
+        int hp = 1;
+        if (nb4 && F > 16) {
+            static const int want = getenv("SVOXB_MF_HP") ? atoi(getenv("SVOXB_MF_HP")) : 2;
+            for (hp = want; hp > 1 && !mf_staged_ok(tr, ja, hp); hp >>= 1) {}
+        }
+        const size_t smem2 = mf_smem_bytes(hp, top_words, J, F, B, WARPS);
+        void (*k2)(TreeArgs, RaySource, MarchOpts, JointArgs, const float*, float*, unsigned long long*);
+        if (hp == 4) k2 = tr.use_accel ? mf_bwd_kernel<true, true, 4> : mf_bwd_kernel<false, true, 4>;
+        else if (hp == 2) k2 = tr.use_accel ? mf_bwd_kernel<true, true, 2> : mf_bwd_kernel<false, true, 2>;
+        else k2 = tr.use_accel ? (nb4 ? mf_bwd_kernel<true, true, 1> : mf_bwd_kernel<true, false, 1>)
+                               : (nb4 ? mf_bwd_kernel<false, true, 1> : mf_bwd_kernel<false, false, 1>);
         int grid2 = 0;
         rc = persistent_grid(k2, smem2, Q, grid2); if (rc) return rc;
         unsigned long long* counter2 = work_counter(st);

@@ -465,41 +465,58 @@ def test_view_dependent_formats_against_reference_golden(dev, accel):
 
 
 def test_motion_feature_render_forward_reference_backward_oracle(dev):
+    """Both forms of the motion-feature render: the table form (large batches: Q * 32 >= M, blend + sigmoid once per row,
+    the feature render's quad kernels on that table) and the staged kernels (small batches)."""
     z = np.load(golden_fmt_file())
     f4, jf, sw, ji = z["mf_features"], z["mf_jf"], z["mf_sw"], z["mf_ji"]
     T = orc.Tree(z["child"], z["data"])
     tree = make_tree(z, 4, dev)
+    M = f4.shape[0]
+    for nq in (M // 32 - 1, len(z["origins"])):                    # staged kernels / table form
+        o_np, d_np = z["origins"][:nq], z["dirs"][:nq]
+        rays = sv.Rays(cu(o_np, dev), cu(d_np, dev), cu(d_np, dev))
+        for tag, thr in (("default", 0.0), ("fast", 1e-2)):
+            r = sv.VolumeRenderer(tree, background_brightness=0.5)
+            r.sigma_thresh, r.stop_thresh = thr, thr
+            jft = cu(jf, dev).requires_grad_(True)
+            out = r.motion_feature_render(cu(f4, dev), jft, cu(sw, dev), cu(ji, dev), rays)
+            assert frac_within(out.detach().cpu().numpy(), z["mf_ref_out_" + tag][:nq]) >= 0.999
+            g = np.random.default_rng(1).standard_normal(tuple(out.shape)).astype(np.float32)
+            (out * cu(g, dev)).sum().backward()
+            g_ref = orc.motion_feature_render_backward(T, f4, o_np, d_np, jf, sw, ji, g)
+            assert rel_l2(jft.grad.cpu().numpy(), g_ref) <= 1e-4
+        # B != 4 (scalar staging), with a negative weight (skipped, rt_kernel.cu:955) and a repeated joint per row
+        sw3, ji3 = np.ascontiguousarray(sw[:, :3]).copy(), np.ascontiguousarray(ji[:, :3]).copy()
+        sw3[::7, 1] = -0.25
+        ji3[::5, 2] = ji3[::5, 0]
+        for accel in (True, False):
+            ts = tree._spec(cu(f4, dev), cu(jf, dev), cu(sw3, dev), cu(ji3, dev), _with_accel=accel)
+            rs, opt = sv.renderer._rays_spec_from_rays(rays), sv.VolumeRenderer(tree)._get_options()
+            out = C.motion_feature_render(ts, rs, opt)
+            g = np.random.default_rng(2).standard_normal(tuple(out.shape)).astype(np.float32)
+            gj = C.motion_feature_render_backward(ts, rs, opt, cu(g, dev))
+            assert frac_within(out.cpu().numpy(), orc.motion_feature_render(T, f4, o_np, d_np, jf, sw3, ji3)) >= 0.999
+            assert rel_l2(gj.cpu().numpy(), orc.motion_feature_render_backward(T, f4, o_np, d_np, jf, sw3, ji3, g)) <= 1e-4
+        # feature widths on either side of the float4 layouts: F + 1 a multiple of 4 (full rows) and not
+        for F2 in (3, 7, 9):
+            jf2 = np.random.default_rng(F2).standard_normal((jf.shape[0], F2)).astype(np.float32)
+            ts = tree._spec(cu(f4, dev), cu(jf2, dev), cu(sw, dev), cu(ji, dev))
+            out = C.motion_feature_render(ts, rs, opt)
+            g = np.random.default_rng(4).standard_normal(tuple(out.shape)).astype(np.float32)
+            gj = C.motion_feature_render_backward(ts, rs, opt, cu(g, dev))
+            assert frac_within(out.cpu().numpy(), orc.motion_feature_render(T, f4, o_np, d_np, jf2, sw, ji)) >= 0.999
+            assert rel_l2(gj.cpu().numpy(), orc.motion_feature_render_backward(T, f4, o_np, d_np, jf2, sw, ji, g)) <= 1e-4
     rays = sv.Rays(cu(z["origins"], dev), cu(z["dirs"], dev), cu(z["dirs"], dev))
-    for tag, thr in (("default", 0.0), ("fast", 1e-2)):
-        r = sv.VolumeRenderer(tree, background_brightness=0.5)
-        r.sigma_thresh, r.stop_thresh = thr, thr
-        jft = cu(jf, dev).requires_grad_(True)
-        out = r.motion_feature_render(cu(f4, dev), jft, cu(sw, dev), cu(ji, dev), rays)
-        assert frac_within(out.detach().cpu().numpy(), z["mf_ref_out_" + tag]) >= 0.999
-        g = np.random.default_rng(1).standard_normal(tuple(out.shape)).astype(np.float32)
-        (out * cu(g, dev)).sum().backward()
-        g_ref = orc.motion_feature_render_backward(T, f4, z["origins"], z["dirs"], jf, sw, ji, g)
-        assert rel_l2(jft.grad.cpu().numpy(), g_ref) <= 1e-4
     # rays that miss the cube return zeros, not the background (rt_kernel.cu:911-916)
     o = np.array([[3, 3, 3], [0.5, 0.5, -1.0]], np.float32)
     d = np.array([[0, 1, 0], [0, 0, 1]], np.float32)
     out = sv.VolumeRenderer(tree, background_brightness=0.5).motion_feature_render(
         cu(f4, dev), cu(jf, dev), cu(sw, dev), cu(ji, dev), sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev)))
     assert not out[0].any() and out[1].any()
-    # B != 4 (scalar staging), with a negative weight (skipped, rt_kernel.cu:955) and a repeated joint per row
-    sw3, ji3 = np.ascontiguousarray(sw[:, :3]).copy(), np.ascontiguousarray(ji[:, :3]).copy()
-    sw3[::7, 1] = -0.25
-    ji3[::5, 2] = ji3[::5, 0]
-    for accel in (True, False):
-        jft = cu(jf, dev).requires_grad_(True)
-        ts = tree._spec(cu(f4, dev), jft, cu(sw3, dev), cu(ji3, dev), _with_accel=accel)
-        rs, opt = sv.renderer._rays_spec_from_rays(rays), sv.VolumeRenderer(tree)._get_options()
-        out = C.motion_feature_render(ts, rs, opt)
-        g = np.random.default_rng(2).standard_normal(tuple(out.shape)).astype(np.float32)
-        gj = C.motion_feature_render_backward(ts, rs, opt, cu(g, dev))
-        assert frac_within(out.cpu().numpy(), orc.motion_feature_render(T, f4, z["origins"], z["dirs"], jf, sw3, ji3)) >= 0.999
-        assert rel_l2(gj.cpu().numpy(),
-                      orc.motion_feature_render_backward(T, f4, z["origins"], z["dirs"], jf, sw3, ji3, g)) <= 1e-4
+    o2, d2 = np.concatenate([z["origins"], o]), np.concatenate([z["dirs"], d])          # the same two in a table-form batch
+    out = sv.VolumeRenderer(tree, background_brightness=0.5).motion_feature_render(
+        cu(f4, dev), cu(jf, dev), cu(sw, dev), cu(ji, dev), sv.Rays(cu(o2, dev), cu(d2, dev), cu(d2, dev)))
+    assert not out[-2].any() and out[-1].any()
     # many joints: the per-CTA gradient table no longer fits shared memory -> global atomics
     J2 = 2000
     rng = np.random.default_rng(3)
