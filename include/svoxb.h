@@ -235,7 +235,8 @@ SVOXB_API int svoxb_accumulate_weights(const svoxb_tree* tree, const float* orig
 
 /* motion_feature_render (rt_kernel.cu:885-979, 1525-1543): out[Q, F] += weight * sigmoid(sum_j w_j * JF[joint_j][k]) at
  * every hit, where (w_j, joint_j) are the B skinning weights / joint indices of the hit ROW (skinning_weights[M,B],
- * joint_index[M,B]) and JF = joint_features[J,F], F <= 32. No opacity channel; rays that miss the cube return 0. */
+ * joint_index[M,B]) and JF = joint_features[J,F]; F <= 127 for large batches (Q * 32 >= M: blend + sigmoid are tabulated once per row and the
+ * feature render's kernels march that table), F <= 32 otherwise. No opacity channel; rays that miss the cube return 0. */
 SVOXB_API int svoxb_motion_feature_render_fwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
                                     const svoxb_render_options* opt, const float* joint_features,
                                     const float* skinning_weights, const int32_t* joint_index, int32_t J, int32_t F,
