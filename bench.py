@@ -396,6 +396,42 @@ def extras(sv, C, synth, tree, feats, renderer, opt, ts, rs, o_t, d_t, g_t, dev,
     cs = sv.renderer._make_camera_spec(cam, 800, 800, 1111.111, 1111.111)
     ms = best(lambda: C.volume_render_image_with_depth(ts, cs, opt))
     ex["c2_image_800x800_fwd_with_depth"] = {"ms": ms, "Mrays/s": 0.64 / (ms * 1e-3)}
+    try:   # motion-feature render on the same tree and rays: J = 24 joints, F = 32, B = 4
+        rng = np.random.default_rng(0)
+        M = feats.shape[0]
+        jf = torch.randn(24, 32, device=dev, requires_grad=True)
+        sw = torch.from_numpy(rng.dirichlet(np.ones(4), M).astype(np.float32)).to(dev)
+        ji = torch.from_numpy(rng.integers(0, 24, (M, 4)).astype(np.int32)).to(dev)
+        rays = sv.Rays(o_t, d_t, d_t)
+        gm = torch.randn(o_t.shape[0], 32, device=dev)
+        f_ms = best(lambda: renderer.motion_feature_render(feats, jf.detach(), sw, ji, rays), 1, 3)
+
+        def fb():
+            jf.grad = None
+            renderer.motion_feature_render(feats, jf, sw, ji, rays).backward(gm)
+        ex["motion_feature_render_J24_F32_B4"] = {"fwd_ms": f_ms, "fwd_bwd_ms": best(fb, 1, 3)}
+        del jf, sw, ji, gm
+    except Exception as e:
+        ex["motion_feature_render_J24_F32_B4"] = {"unavailable": str(e)[:200]}
+    try:   # config C4: animated frame = LBS warp of 2^20 points + p2v splat (256^3) + octree rebuild to depth 8 + accelerator
+        P = 1 << 20   #            + 1920x1080 render with opacity and depth; per-frame latency, CUDA events around the frame
+        vox = synth._occupied_keys(8, "ball")
+        pts = synth.voxel_centers(vox[np.random.default_rng(2).permutation(len(vox))[:P]], 8)
+        Tm, w4, j4 = synth.synth_skeleton(P)
+        p_t, Tm_t, w_t, j_t = (torch.from_numpy(a).to(dev) for a in (pts, Tm, w4, j4))
+        f4 = torch.from_numpy(synth.synth_features(P, 32)).to(dev)
+        corner, size = torch.zeros(3, device=dev), torch.ones(3, device=dev)
+        tree4 = sv.N3Tree(N=2, data_dim=32, map_location=dev)
+        r4 = sv.VolumeRenderer(tree4)
+
+        def frame():
+            warped, _ = sv.warp_vertices(Tm_t, p_t, w_t, j_t)
+            sv.voxelize(warped, f4, corner, size, 256, 1.5 / 256, 2.0 / 256)
+            tree4.build_from_points(warped, 8)
+            r4.render_persp_with_depth(f4, cam, width=1920, height=1080, fx=1500.0)
+        ex["c4_animated_frame_1080p"] = {"ms_per_frame": best(frame, 2, 5), "points": P, "nodes": int(tree4.filled)}
+    except Exception as e:
+        ex["c4_animated_frame_1080p"] = {"unavailable": str(e)[:200]}
     try:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import refdrv
