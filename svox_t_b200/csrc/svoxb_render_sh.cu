@@ -922,43 +922,53 @@ mf_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, const flo
 __global__ void __launch_bounds__(256)
 mf_table_kernel(JointArgs ja, const float* __restrict__ features, int64_t M, int D, int stride, int full_rows,
                 float* __restrict__ table, float* __restrict__ sigma) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < M; r += warps_total) {
-        const float* swr = ja.sw + r * ja.NB;
-        const int32_t* jir = ja.ji + r * ja.NB;
-        for (int k = lane; k < stride; k += 32) {
-            float v = 0.0f;
-            if (k < ja.F) {
-                float pj = 0.0f;
-                for (int b = 0; b < ja.NB; ++b) {
-                    const float w = __ldg(swr + b);
-                    if (w > 0.0f) pj += w * __ldg(ja.jf + (size_t)min(max(__ldg(jir + b), 0), ja.J - 1) * ja.F + k);
-                }
-                v = fast_sigmoid(pj);
-            } else if (full_rows && k == ja.F) {
-                v = __ldg(features + r * D + (D - 1));
+    // one thread per table element: the threads of a row re-read its NB weights / joint indices through L1
+    const int64_t n = M * stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / stride;
+        const int k = (int)(i - r * stride);
+        float v = 0.0f;
+        if (k < ja.F) {
+            const float* swr = ja.sw + r * ja.NB;
+            const int32_t* jir = ja.ji + r * ja.NB;
+            float pj = 0.0f;
+            for (int b = 0; b < ja.NB; ++b) {
+                const float w = __ldg(swr + b);
+                if (w > 0.0f) pj += w * __ldg(ja.jf + (size_t)min(max(__ldg(jir + b), 0), ja.J - 1) * ja.F + k);
             }
-            table[r * stride + k] = v;
+            v = fast_sigmoid(pj);
+        } else if (full_rows && k == ja.F) {
+            v = __ldg(features + r * D + (D - 1));
         }
-        if (!full_rows && lane == 0) sigma[r] = __ldg(features + r * D + (D - 1));
+        table[i] = v;
+        if (!full_rows && k == 0) sigma[r] = __ldg(features + r * D + (D - 1));
     }
 }
 
-// out[q, 0:F] = tmp[q, 0:F], zeros for rays that miss the cube (rt_kernel.cu:911-916).
+// out[q, 0:F] = tmp[q, 0:F], zeros for rays that miss the cube (rt_kernel.cu:911-916). Lane l tests ray base + l (the
+// set-up divides in double precision: once per ray, not once per lane), then the warp copies the 32 rows.
 __global__ void __launch_bounds__(256)
 mf_finish_kernel(const float* __restrict__ tmp, const float* __restrict__ origins, const float* __restrict__ dirs,
                  const float* __restrict__ off, const float* __restrict__ scl, int64_t Q, int F, float* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < Q; q += warps_total) {
-        Ray ray;
-        ray_setup(off, scl, __ldg(origins + 3 * q), __ldg(origins + 3 * q + 1), __ldg(origins + 3 * q + 2),
-                  __ldg(dirs + 3 * q), __ldg(dirs + 3 * q + 1), __ldg(dirs + 3 * q + 2), ray);
-        float a, b;
-        dda_unit(ray.ox, ray.oy, ray.oz, ray.ix, ray.iy, ray.iz, a, b);
-        const bool missed = b < 0.0f || a > b;
-        for (int k = lane; k < F; k += 32) __stcs(out + q * F + k, missed ? 0.0f : __ldcs(tmp + q * (F + 1) + k));
+    for (int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < Q; base += warps_total * 32) {
+        const int64_t q = base + lane;
+        bool missed = true;
+        if (q < Q) {
+            Ray ray;
+            ray_setup(off, scl, __ldg(origins + 3 * q), __ldg(origins + 3 * q + 1), __ldg(origins + 3 * q + 2),
+                      __ldg(dirs + 3 * q), __ldg(dirs + 3 * q + 1), __ldg(dirs + 3 * q + 2), ray);
+            float a, b;
+            dda_unit(ray.ox, ray.oy, ray.oz, ray.ix, ray.iy, ray.iz, a, b);
+            missed = b < 0.0f || a > b;
+        }
+        const unsigned mm = __ballot_sync(FULL, missed);
+        const int nr = (int)min((int64_t)32, Q - base);
+        for (int e = lane; e < nr * F; e += 32) {           // the 32 output rows are one contiguous span
+            const int rr = e / F, k = e - rr * F;
+            __stcs(out + base * F + e, ((mm >> rr) & 1u) ? 0.0f : __ldcs(tmp + (base + rr) * (F + 1) + k));
+        }
     }
 }
 
@@ -978,23 +988,44 @@ mf_pad_grad_kernel(const float* __restrict__ g, int64_t Q, int F, float* __restr
 __global__ void __launch_bounds__(256)
 mf_fold_kernel(JointArgs ja, const float* __restrict__ gpre, int64_t M, int D2, int use_table, float* __restrict__ grad_jf) {
     extern __shared__ __align__(16) float fold_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, JF = ja.J * ja.F;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, JF = ja.J * ja.F, NB = ja.NB;
     float* tbl = use_table ? fold_smem + (size_t)warp * JF : grad_jf;
     if (use_table) for (int i = lane; i < JF; i += 32) tbl[i] = 0.0f;
     __syncwarp();
+    constexpr int R = 4;                                     // rows in flight per warp: their loads are independent
     const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < M; r += warps_total) {
-        const float* swr = ja.sw + r * ja.NB;
-        const int32_t* jir = ja.ji + r * ja.NB;
-        for (int k = lane; k < ja.F; k += 32) {
-            const float g = __ldcs(gpre + r * D2 + k);
-            if (g == 0.0f) continue;
-            for (int b = 0; b < ja.NB; ++b) {
-                const float w = __ldg(swr + b);
-                if (!(w > 0.0f)) continue;
-                float* t = tbl + (size_t)min(max(__ldg(jir + b), 0), ja.J - 1) * ja.F + k;
-                if (use_table) *t = fmaf(w, g, *t);
-                else atomicAdd(t, w * g);
+    for (int64_t r0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R; r0 < M; r0 += warps_total * R) {
+        for (int k0 = 0; k0 < ja.F; k0 += 32) {
+            const int k = k0 + lane;
+            float g[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) g[i] = (k < ja.F && r0 + i < M) ? __ldcs(gpre + (r0 + i) * D2 + k) : 0.0f;
+            // the R rows' weights / joint indices are one contiguous span of R * NB entries: lane l fetches entry l
+            const bool lanes_hold = R * NB <= 32;
+            float w_l = 0.0f;
+            int j_l = 0;
+            if (lanes_hold && lane < R * NB && r0 * NB + lane < M * NB) {
+                w_l = __ldg(ja.sw + r0 * NB + lane);
+                j_l = min(max(__ldg(ja.ji + r0 * NB + lane), 0), ja.J - 1);
+            }
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                if (r0 + i >= M) break;
+                for (int b = 0; b < NB; ++b) {
+                    float w;
+                    int j;
+                    if (lanes_hold) {
+                        w = __shfl_sync(FULL, w_l, i * NB + b);
+                        j = __shfl_sync(FULL, j_l, i * NB + b);
+                    } else {
+                        w = __ldg(ja.sw + (r0 + i) * NB + b);
+                        j = min(max(__ldg(ja.ji + (r0 + i) * NB + b), 0), ja.J - 1);
+                    }
+                    if (!(w > 0.0f) || k >= ja.F || g[i] == 0.0f) continue;
+                    float* t = tbl + (size_t)j * ja.F + k;
+                    if (use_table) *t = fmaf(w, g[i], *t);
+                    else atomicAdd(t, w * g[i]);
+                }
             }
         }
     }
@@ -1026,7 +1057,7 @@ static int mf_make_table(const TreeArgs& tr, const JointArgs& ja, cudaStream_t s
     const size_t n_tab = (size_t)tr.M * stride, n_sig = full ? 0 : (size_t)tr.M;
     int rc = scratch_alloc((void**)&t.mem, sizeof(float) * (n_tab + n_sig), st);
     if (rc) return rc;
-    const int grid = (int)min((tr.M * 32 + 255) / 256, (int64_t)sm_count() * 16);
+    const int grid = (int)min(((int64_t)n_tab + 255) / 256, (int64_t)sm_count() * 32);
     mf_table_kernel<<<grid, 256, 0, st>>>(ja, tr.features, tr.M, tr.D, stride, full ? 1 : 0, t.mem, t.mem + n_tab);
     count_launch();
     t.tr2 = tr;
@@ -1047,7 +1078,7 @@ static int mf_table_fwd(const TreeArgs& tr, const JointArgs& ja, const RaySource
     rc = scratch_alloc((void**)&tmp, sizeof(float) * (size_t)src.total * (ja.F + 1), st);
     if (rc == 0) rc = launch_fwd_quad(t.tr2, src, m, false, tmp, nullptr, st);
     if (rc == 0) {
-        const int grid = (int)min((src.total * 32 + 255) / 256, (int64_t)sm_count() * 16);
+        const int grid = (int)min((src.total + 255) / 256, (int64_t)sm_count() * 16);
         mf_finish_kernel<<<grid, 256, 0, st>>>(tmp, src.origins, src.dirs, tr.offset, tr.scaling, src.total, ja.F, out);
         count_launch();
         rc = check_cuda(cudaGetLastError(), "mf_finish_kernel launch");
@@ -1084,7 +1115,7 @@ static int mf_table_bwd(const TreeArgs& tr, const JointArgs& ja, const RaySource
             if (use_table && tab > 47 * 1024)
                 rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab), "smem opt-in");
             if (rc == 0) {
-                const int grid = (int)min((tr.M * 32 + 255) / 256, (int64_t)sm_count() * 4);
+                const int grid = (int)min((tr.M * 8 + 255) / 256, (int64_t)sm_count() * 8);
                 kern<<<grid, 256, use_table ? tab : 0, st>>>(ja, gpre, tr.M, D2, use_table, grad_jf);
                 count_launch();
                 rc = check_cuda(cudaGetLastError(), "mf_fold_kernel launch");
