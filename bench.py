@@ -396,6 +396,13 @@ def extras(sv, C, synth, tree, feats, renderer, opt, ts, rs, o_t, d_t, g_t, dev,
     cs = sv.renderer._make_camera_spec(cam, 800, 800, 1111.111, 1111.111)
     ms = best(lambda: C.volume_render_image_with_depth(ts, cs, opt))
     ex["c2_image_800x800_fwd_with_depth"] = {"ms": ms, "Mrays/s": 0.64 / (ms * 1e-3)}
+    try:   # secondary forward-only series of SURVEY 8d: fast=True thresholds (sigma_thresh = stop_thresh = 1e-2)
+        fast = renderer._get_options(True)
+        ms = best(lambda: C.volume_render(ts, rs, fast))
+        ex["c3_fwd_fast_thresholds"] = {"ms": ms, "Mrays/s": o_t.shape[0] / (ms * 1e-3) / 1e6,
+                                        "sigma_thresh": fast.sigma_thresh, "stop_thresh": fast.stop_thresh}
+    except Exception as e:
+        ex["c3_fwd_fast_thresholds"] = {"unavailable": str(e)[:200]}
     try:   # motion-feature render on the same tree and rays: J = 24 joints, F = 32, B = 4
         rng = np.random.default_rng(0)
         M = feats.shape[0]

@@ -118,6 +118,48 @@ class N3TreeView:
         with torch.no_grad():
             f[idx[valid]] = value
 
+    # In-place element-wise updates of the selected leaves' feature rows (helpers.py:246-306; the reference still applies
+    # them to ``tree.data``, which holds row indices in this fork). Empty leaves have no row and are skipped.
+    def _apply_(self, fn):
+        idx, valid = self._rows()
+        f = self.tree.features
+        rows = idx[valid]
+        with torch.no_grad():
+            f[rows] = fn(f[rows])
+
+    def normal_(self, mean=0.0, std=1.0):
+        self._apply_(lambda v: torch.randn_like(v) * std + mean)
+
+    def uniform_(self, min=0.0, max=1.0):
+        self._apply_(lambda v: torch.rand_like(v) * (max - min) + min)
+
+    def clamp_(self, min=None, max=None):
+        self._apply_(lambda v: v.clamp(min, max))
+
+    def relu_(self):
+        self._apply_(torch.relu)
+
+    def sigmoid_(self):
+        self._apply_(torch.sigmoid)
+
+    def nan_to_num_(self, inf_val=2e4):
+        self._apply_(lambda v: torch.nan_to_num(v, nan=0.0, posinf=inf_val, neginf=-inf_val))
+
+    @property
+    def shape(self):
+        self._check_ver()
+        return torch.Size((len(self), self.tree.features.shape[1]))
+
+    @property
+    def ndim(self):
+        return 2
+
+    def _indexer(self):
+        return torch.stack(self.key[:4], dim=-1)
+
+    def __repr__(self):
+        return f"N3TreeView({len(self)} leaves of {self.tree!r})"
+
     def aux(self, arr):
         """Index an auxiliary per-slot array of shape (capacity, N, N, N, ...) with this view (helpers.py:239-244)."""
         self._check_ver()

@@ -924,6 +924,14 @@ def test_view_values_and_set(dev):
     view.set(torch.full((len(view), D), 7.0, device=dev))
     assert float(tree.features.detach()[rows[ok]].min()) == 7.0
     assert int((tree.features.detach() == 7.0).all(dim=1).sum()) == int(ok.sum())
+    view.clamp_(min=8.0)
+    assert float(tree.features.detach()[rows[ok]].min()) == 8.0 and view.shape == (len(view), D) and view.ndim == 2
+    view.sigmoid_(); view.relu_(); view.nan_to_num_(); view.uniform_(2.0, 3.0)
+    got = tree.features.detach()[rows[ok]]
+    assert float(got.min()) >= 2.0 and float(got.max()) <= 3.0 and "leaves" in repr(view)
+    untouched = torch.ones(tr["M"], dtype=torch.bool, device=dev)
+    untouched[rows[ok]] = False
+    assert torch.equal(tree.features.detach()[untouched], cu(f, dev)[untouched])
     tree[pts[:5]] = 3.0                                           # scalar broadcast through assign_vertical
     got = tree(tree.features.detach(), pts[:5], want_data_ids=True)
     assert bool(((got[0] == 3.0).all(dim=1) | (got[1] < 0)).all())
