@@ -569,6 +569,7 @@ template <bool NB4>
 __device__ __forceinline__ void mf_stage(const MfSmem& sm, const JointArgs& ja, int FP, int slot, int lane, int idx,
                                          float w, const float4& wv, const int4& jv) {
     const int nb_pad = (ja.NB + 3) & ~3, jmax = ja.J - 1;
+    SVOXB_DBG(slot >= 0 && slot < 32 && idx >= 0);
     sm.st_wr[slot] = make_float2(w, __int_as_float(lane));
     if (NB4) {
         reinterpret_cast<float4*>(sm.st_w)[slot] = make_float4(fmaxf(wv.x, 0.f), fmaxf(wv.y, 0.f), fmaxf(wv.z, 0.f), fmaxf(wv.w, 0.f));
@@ -648,6 +649,7 @@ mf_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, float* __
 
         // S0: operands of the pending candidate (row 0 stands in for "none": unconditional loads, see svoxb_render_q.cu)
         const int pi = max(p_idx, 0);
+        SVOXB_DBG((int64_t)pi < max(tr.M, (int64_t)1));
         const float sig = __ldg(sig_base + (size_t)(unsigned)pi * sig_stride);
         float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
         int4 jv = make_int4(0, 0, 0, 0);
@@ -801,6 +803,7 @@ mf_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs ja, const flo
         if (__ballot_sync(FULL, active) == 0u) break;
 
         const int pi = max(p_idx, 0);
+        SVOXB_DBG((int64_t)pi < max(tr.M, (int64_t)1));
         const float sig = __ldg(sig_base + (size_t)(unsigned)pi * sig_stride);
         float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
         int4 jv = make_int4(0, 0, 0, 0);

@@ -65,6 +65,7 @@ assign_kernel(TreeArgs tr, float* __restrict__ features_mut, const float* __rest
             const int r = __ffs(vm) - 1;
             vm &= vm - 1;
             const int idx_r = __shfl_sync(FULL, idx, r);
+            SVOXB_DBG(idx_r >= 0 && idx_r < tr.M && base + r < Q);
             const float* src = values + (base + r) * K;
             float* dst = features_mut + (int64_t)idx_r * tr.D;
             for (int c = lane; c < K; c += 32) dst[c] = __ldg(src + c);
@@ -120,6 +121,7 @@ grid_weight_kernel(const float* __restrict__ grid, int reso, RaySource src, cons
             const float fu = floorf(x), fv = floorf(y), fw = floorf(z);
             x -= fu; y -= fv; z -= fw;
             const int64_t cell = ((int64_t)(int)fu * reso + (int)fv) * reso + (int)fw;
+            SVOXB_DBG(cell >= 0 && cell < (int64_t)reso * reso * reso);
             float smin, smax;
             dda_unit(x, y, z, r.ix, r.iy, r.iz, smin, smax);
             const float delta_t = (smax - smin) / fr + step;
