@@ -7,7 +7,9 @@ rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 keep = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors.sum", "lts__t_sectors_srcunit_tex_op_read.sum", "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.per_cycle_active", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
