@@ -935,3 +935,38 @@ def test_view_values_and_set(dev):
     tree[pts[:5]] = 3.0                                           # scalar broadcast through assign_vertical
     got = tree(tree.features.detach(), pts[:5], want_data_ids=True)
     assert bool(((got[0] == 3.0).all(dim=1) | (got[1] < 0)).all())
+
+
+def test_training_step_is_cuda_graph_capturable(dev):
+    """The forward + autograd backward issue no synchronisation and allocate only stream-ordered memory, so a step can be
+    captured once and replayed (new rays are copied into the captured buffers)."""
+    tr = synth.synth_tree(4, "ball")
+    D, Q = 16, 2048
+    tree = make_tree(tr, D, dev)
+    feats = cu(synth.synth_features(tr["M"], D), dev).requires_grad_(True)
+    o, d = synth.synth_rays(Q)
+    rays = sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev))
+    r = sv.VolumeRenderer(tree)
+    g = torch.randn(Q, D, device=dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                      # warm-up off the default stream: accelerator, activated table
+        for _ in range(2):
+            feats.grad = None
+            r(feats, rays).backward(g)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    feats.grad = None
+    with torch.cuda.graph(graph):
+        out_g = r(feats, rays)
+        out_g.backward(g)
+    o2, d2 = synth.synth_rays(Q, seed=9)
+    rays.origins.copy_(cu(o2, dev)); rays.dirs.copy_(cu(d2, dev))
+    graph.replay()
+    torch.cuda.synchronize()
+    got_out, got_grad = out_g.detach().clone(), feats.grad.clone()
+    feats.grad = None
+    ref = r(feats, rays)
+    ref.backward(g)
+    assert torch.equal(got_out, ref.detach())
+    assert float((got_grad - feats.grad).norm() / feats.grad.norm()) < 1e-5
