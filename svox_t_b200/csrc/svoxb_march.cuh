@@ -12,7 +12,11 @@ namespace svoxb {
 #endif
 constexpr int BLOCK = SVOXB_BLOCK;
 constexpr int WARPS = BLOCK / 32;
-constexpr int CHUNK = 64;          // rays fetched from the global queue per atomic; one 8x8 pixel tile for images
+constexpr int CHUNK = 64;          // image queue entry: one 8x8 pixel tile (coherent lanes)
+#ifndef SVOXB_RAY_CHUNK
+#define SVOXB_RAY_CHUNK 32
+#endif
+constexpr int RAY_CHUNK = SVOXB_RAY_CHUNK;      // explicit-ray queue entry: one ray per lane (measured against 8 / 16 / 64, svoxb_render_q.cu)
 
 struct RaySource {
     const float* origins;          // explicit rays: [Q,3] world space
@@ -26,6 +30,7 @@ struct RaySource {
     const float* vdirs;            // explicit rays: [Q,3] view directions (view-dependent formats only)
     int ndc_w, ndc_h;              // camera rays: NDC conversion when ndc_w >= 0 (rt_kernel.cu:1168-1191)
     float ndc_focal;
+    int chunk;                     // explicit rays: rays fetched from the queue per atomic (0 = RAY_CHUNK)
 };
 
 struct ViewDir {
@@ -110,11 +115,12 @@ __device__ __forceinline__ unsigned refill(const RaySource& src, const float* of
         if (q.next >= q.end) {
             if (q.exhausted) break;
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(counter, (unsigned long long)CHUNK);
+            const int chunk = IMAGE ? CHUNK : (src.chunk > 0 ? src.chunk : RAY_CHUNK);
+            if (lane == 0) base = atomicAdd(counter, (unsigned long long)chunk);
             base = __shfl_sync(FULL, base, 0);
             if ((int64_t)base >= src.total) { q.exhausted = true; break; }
             q.next = (int)base;
-            q.end = (int)min((int64_t)base + CHUNK, src.total);
+            q.end = (int)min((int64_t)base + chunk, src.total);
         }
         const int avail = q.end - q.next;
         const int rank = __popc(need & ((1u << lane) - 1u));
@@ -293,7 +299,7 @@ __device__ __forceinline__ void probe_end(const TreeArgs& tr, const Probe& pb, c
 // much shared memory per SM, so that everything else of the 228 KB stays L1 (see svoxb_render_q.cu).
 template <typename Kern>
 static int persistent_grid(Kern kern, size_t smem, int64_t queue_len, int& grid, int threads = BLOCK,
-                           int carveout_kb = 0) {
+                           int carveout_kb = 0, int chunk = RAY_CHUNK) {
     if (smem + 1024 > 48 * 1024)      // static shared memory (the top grid's mbarrier) counts against the 48 KB default
         SVOXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (carveout_kb > 0)
@@ -303,7 +309,7 @@ static int persistent_grid(Kern kern, size_t smem, int64_t queue_len, int& grid,
     SVOXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     SVOXB_REQUIRE(per_sm > 0, "kernel does not fit on an SM (smem %zu)", smem);
     const int warps = threads / 32;
-    const int64_t warps_needed = (queue_len + CHUNK - 1) / CHUNK;
+    const int64_t warps_needed = (queue_len + chunk - 1) / chunk;
     const int64_t want = (warps_needed + warps - 1) / warps;
     grid = (int)max((int64_t)1, min((int64_t)per_sm * sm_count(), want));
     return 0;
