@@ -1205,12 +1205,14 @@ static int launch_fmt_bwd(const TreeArgs& tr, const RaySource& src, const MarchO
         return SVOXB_EINVAL;                                                                              \
     } while (0)
 
-// svoxb_render_shrgb.cu: lane-private fast path for SH rows with three output channels
+// svoxb_render_shrgb.cu: lane-private fast path for SH / SG / ASG rows with three output channels
 bool sh_rgb_supported(int format, int B, int D);
 int sh_rgb_fwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, int B, int min_comp, int max_comp,
-               const float* tm, bool image, float* out, cudaStream_t st);
+               const float* tm, int format, const float* extra, int extra_cols, bool image, float* out,
+               cudaStream_t st);
 int sh_rgb_bwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, int B, int min_comp, int max_comp,
-               const float* tm, bool image, const float* go, const float* so, float* grad, cudaStream_t st);
+               const float* tm, int format, const float* extra, int extra_cols, bool image, const float* go,
+               const float* so, float* grad, cudaStream_t st);
 
 // Entry points used by svoxb_render.cu when opt->format != RGBA.
 int fmt_render_fwd(const svoxb_tree* tree, const TreeArgs& tr, const RaySource& src, const MarchOpts& m,
@@ -1218,7 +1220,7 @@ int fmt_render_fwd(const svoxb_tree* tree, const TreeArgs& tr, const RaySource& 
     FmtArgs f;
     int rc = make_fmt(tree, opt, f); if (rc) return rc;
     if (sh_rgb_supported(f.format, f.B, tr.D))
-        return sh_rgb_fwd(tr, src, m, f.B, f.min_comp, f.max_comp, f.tm, image, out, st);
+        return sh_rgb_fwd(tr, src, m, f.B, f.min_comp, f.max_comp, f.tm, f.format, f.extra, f.extra_cols, image, out, st);
     SVOXB_FMT_DISPATCH(launch_fmt_fwd, tr, src, m, f, out, st);
 }
 
@@ -1228,7 +1230,7 @@ int fmt_render_bwd(const svoxb_tree* tree, const TreeArgs& tr, const RaySource& 
     FmtArgs f;
     int rc = make_fmt(tree, opt, f); if (rc) return rc;
     if (sh_rgb_supported(f.format, f.B, tr.D))
-        return sh_rgb_bwd(tr, src, m, f.B, f.min_comp, f.max_comp, f.tm, image, go, so, grad, st);
+        return sh_rgb_bwd(tr, src, m, f.B, f.min_comp, f.max_comp, f.tm, f.format, f.extra, f.extra_cols, image, go, so, grad, st);
     SVOXB_FMT_DISPATCH(launch_fmt_bwd, tr, src, m, f, go, so, grad, st);
 }
 

@@ -18,6 +18,9 @@ namespace svoxb {
 struct ShArgs {
     int min_comp, max_comp;
     const float* tm;          // [M,4,4] per-row view rotation or nullptr
+    int format;               // SVOXB_FORMAT_SH / _SG / _ASG: only the per-ray basis differs (rt_kernel.cu:109-185)
+    const float* extra;       // SG [B,>=4]: (lambda, mu) ; ASG [B,>=11]: (a, b, x, y, z)
+    int extra_cols;
 };
 
 template <int B>
@@ -58,10 +61,34 @@ __device__ __forceinline__ void sh_basis(float x, float y, float z, float (&out)
     }
 }
 
+// The ray's B basis values for any of the three view-dependent formats (the format is uniform over the launch).
+template <int B>
+__device__ __forceinline__ void fmt_basis(const ShArgs& sa, float x, float y, float z, float (&out)[B]) {
+    if (sa.format == SVOXB_FORMAT_SH) {
+        sh_basis<B>(x, y, z, out);
+    } else if (sa.format == SVOXB_FORMAT_SG) {                             // rt_kernel.cu:116-124
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+            const float* p = sa.extra + (size_t)i * sa.extra_cols;
+            const float dt = x * __ldg(p + 1) + y * __ldg(p + 2) + z * __ldg(p + 3);
+            out[i] = expf(__ldg(p) * (dt - 1.0f)) / (float)B;
+        }
+    } else {                                                               // ASG, rt_kernel.cu:125-140
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+            const float* p = sa.extra + (size_t)i * sa.extra_cols;
+            const float S = x * __ldg(p + 8) + y * __ldg(p + 9) + z * __ldg(p + 10);
+            const float dx = x * __ldg(p + 2) + y * __ldg(p + 3) + z * __ldg(p + 4);
+            const float dy = x * __ldg(p + 5) + y * __ldg(p + 6) + z * __ldg(p + 7);
+            out[i] = S * expf(-__ldg(p) * dx * dx - __ldg(p + 1) * dy * dy) / (float)B;
+        }
+    }
+}
+
 template <int B>
 __device__ __forceinline__ void sh_basis_row(const ShArgs& sa, int idx, const ViewDir& v, float (&out)[B]) {
     const float* m = sa.tm + (size_t)(unsigned)idx * 16;                 // rt_kernel.cu:283-291
-    sh_basis<B>(__ldg(m + 0) * v.x + __ldg(m + 1) * v.y + __ldg(m + 2) * v.z,
+    fmt_basis<B>(sa, __ldg(m + 0) * v.x + __ldg(m + 1) * v.y + __ldg(m + 2) * v.z,
                 __ldg(m + 4) * v.x + __ldg(m + 5) * v.y + __ldg(m + 6) * v.z,
                 __ldg(m + 8) * v.x + __ldg(m + 9) * v.y + __ldg(m + 10) * v.z, out);
 }
@@ -121,7 +148,7 @@ sh_rgb_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, float* _
             const unsigned got = refill<IMAGE, true>(src, off, scl, counter, q, need, lane, ray, row, &vd);
             if ((got >> lane) & 1u) {
                 active = true; T = 1.0f; a0 = a1 = a2 = 0.0f;
-                sh_basis<B>(vd.x, vd.y, vd.z, basis);
+                fmt_basis<B>(sa, vd.x, vd.y, vd.z, basis);
             }
             need = 0;
         }
@@ -197,7 +224,7 @@ sh_rgb_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, const fl
             const unsigned got = refill<IMAGE, true>(src, off, scl, counter, q, need, lane, ray, row, &vd);
             if ((got >> lane) & 1u) {
                 active = true; T = 1.0f;
-                sh_basis<B>(vd.x, vd.y, vd.z, basis);
+                fmt_basis<B>(sa, vd.x, vd.y, vd.z, basis);
                 const float4 g = __ldcs(reinterpret_cast<const float4*>(grad_out) + row);
                 const float4 so = __ldcs(reinterpret_cast<const float4*>(saved_out) + row);
                 g0 = g.x; g1 = g.y; g2 = g.z; gop = g.w;
@@ -297,12 +324,14 @@ static int launch_sh_bwd(const TreeArgs& tr, const RaySource& src, const MarchOp
 
 // True when (format, basis_dim, D) is the SH-RGB layout these kernels cover.
 bool sh_rgb_supported(int format, int B, int D) {
-    return format == SVOXB_FORMAT_SH && (B == 1 || B == 4 || B == 9 || B == 16 || B == 25) && D == 3 * B + 1;
+    return (format == SVOXB_FORMAT_SH || format == SVOXB_FORMAT_SG || format == SVOXB_FORMAT_ASG) &&
+           (B == 1 || B == 4 || B == 9 || B == 16 || B == 25) && D == 3 * B + 1;
 }
 
 int sh_rgb_fwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, int B, int min_comp, int max_comp,
-               const float* tm, bool image, float* out, cudaStream_t st) {
-    const ShArgs sa{min_comp, max_comp, tm};
+               const float* tm, int format, const float* extra, int extra_cols, bool image, float* out,
+               cudaStream_t st) {
+    const ShArgs sa{min_comp, max_comp, tm, format, extra, extra_cols};
     const bool al = (((uintptr_t)tr.features | (uintptr_t)out) & 15) == 0;
     SVOXB_REQUIRE(((uintptr_t)out & 15) == 0, "out must be 16-byte aligned");
     switch (B) {
@@ -318,8 +347,9 @@ int sh_rgb_fwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, int
 }
 
 int sh_rgb_bwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, int B, int min_comp, int max_comp,
-               const float* tm, bool image, const float* go, const float* so, float* grad, cudaStream_t st) {
-    const ShArgs sa{min_comp, max_comp, tm};
+               const float* tm, int format, const float* extra, int extra_cols, bool image, const float* go,
+               const float* so, float* grad, cudaStream_t st) {
+    const ShArgs sa{min_comp, max_comp, tm, format, extra, extra_cols};
     SVOXB_REQUIRE((((uintptr_t)go | (uintptr_t)so) & 15) == 0, "grad_out / saved_out must be 16-byte aligned");
     const bool al = (((uintptr_t)tr.features | (uintptr_t)grad) & 15) == 0;
     switch (B) {

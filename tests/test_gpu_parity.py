@@ -970,3 +970,39 @@ def test_training_step_is_cuda_graph_capturable(dev):
     ref.backward(g)
     assert torch.equal(got_out, ref.detach())
     assert float((got_grad - feats.grad).norm() / feats.grad.norm()) < 1e-5
+
+
+@pytest.mark.parametrize("fmt,B", [(2, 4), (2, 9), (3, 4), (3, 16)], ids=["SG4", "SG9", "ASG4", "ASG16"])
+def test_sg_asg_rgb_fast_path_vs_oracle(dev, fmt, B):
+    """SG / ASG rows with three output channels and B in {1, 4, 9, 16, 25} share the lane-private kernels of the SH-RGB
+    layout (only the per-ray basis differs, rt_kernel.cu:116-140): with and without per-row rotations, both tree walks."""
+    tr = synth.synth_tree(5, "ball")
+    T = orc.Tree(tr["child"], tr["data"])
+    D, Q = 3 * B + 1, 1200
+    rng = np.random.default_rng(10 * fmt + B)
+    f = synth.synth_features(tr["M"], D, seed=B)
+    f[:, :-1] *= 0.6
+    o, d = synth.synth_rays(Q, seed=3)
+    vd = synth._unit(rng, Q).astype(np.float32)
+    if fmt == 2:
+        extra = np.concatenate([rng.uniform(1, 5, (B, 1)), synth._unit(rng, B)], 1).astype(np.float32)
+    else:
+        frames = np.stack([np.linalg.qr(rng.standard_normal((3, 3)))[0] for _ in range(B)])       # rows x, y, z
+        extra = np.concatenate([rng.uniform(0.5, 3, (B, 2)), frames.reshape(B, 9)], 1).astype(np.float32)
+    tm = np.zeros((tr["M"], 4, 4), np.float32)
+    for i in range(tr["M"]):
+        tm[i, :3, :3] = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+    g = rng.standard_normal((Q, 4)).astype(np.float32)
+    for accel in (True, False):
+        for with_tm in (False, True):
+            tree = _fmt_tree(tr, D, fmt, B, extra, dev, accel)
+            feats = cu(f, dev).requires_grad_(True)
+            out = sv.VolumeRenderer(tree)(feats, sv.Rays(cu(o, dev), cu(d, dev), cu(vd, dev)),
+                                          transformation_matrices=cu(tm, dev) if with_tm else None)
+            (out * cu(g, dev)).sum().backward()
+            kw = dict(extra=extra, tm=tm if with_tm else None)
+            o_ref = orc.render_rays_fmt(T, f, o, d, vd, fmt, B, **kw)
+            g_ref = orc.render_rays_fmt_backward(T, f, o, d, vd, g, fmt, B, **kw)
+            assert np.abs(o_ref[:, :3]).max() > 0.05
+            assert frac_within(out.detach().cpu().numpy(), o_ref) >= 0.999, (accel, with_tm)
+            assert rel_l2(feats.grad.cpu().numpy(), g_ref) <= 1e-4, (accel, with_tm)
