@@ -134,12 +134,16 @@ sh_rgb_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, float* _
     const float* off = tr.offset;
     const float* scl = tr.scaling;
 
+    // Software pipeline (as in svoxb_render_q.cu): the candidate found in iteration i is composited in iteration i+1; its
+    // row is requested at the top of that iteration, the brick lookup of the next sample is issued right after it and
+    // consumed after the compositing -- the two dependent load chains of a sample run side by side. Rows the accelerator
+    // marks "sigma <= 0" never become candidates.
     Ray ray;
     ViewDir vd{0.f, 0.f, 0.f};
     float basis[B];
-    float T = 1.0f, a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-    int row = 0;
-    bool active = false;
+    float T = 1.0f, a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, p_dt = 0.0f;
+    int row = 0, p_idx = -1;
+    bool active = false, trav_done = true;
     Queue q{0, 0, false};
     unsigned need = FULL;
 
@@ -147,41 +151,49 @@ sh_rgb_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, float* _
         if (need) {
             const unsigned got = refill<IMAGE, true>(src, off, scl, counter, q, need, lane, ray, row, &vd);
             if ((got >> lane) & 1u) {
-                active = true; T = 1.0f; a0 = a1 = a2 = 0.0f;
+                active = true; trav_done = false; T = 1.0f; a0 = a1 = a2 = 0.0f;
                 fmt_basis<B>(sa, vd.x, vd.y, vd.z, basis);
             }
             need = 0;
         }
         if (__ballot_sync(FULL, active) == 0u) break;
 
-        int fin = 0;                 // 1 = ray left the volume, 2 = stopped early
-        if (active) {
-            if (!(ray.t < ray.tmax)) {
-                fin = 1;
-            } else {
-                int idx; float delta_t;
-                traverse<ACCEL>(tr, top, ray, opt.step, idx, delta_t);
-                if (idx >= 0) {
-                    const float* rowp = tr.features + (size_t)(unsigned)idx * D;
-                    const float sigma = __ldg(rowp + (D - 1));
-                    if (sigma > opt.sigma_thresh) {                                   // rt_kernel.cu:279-320
-                        float v[D], tmp[3];
-                        load_row<B, VEC>(rowp, v);
-                        const float att = expf(-delta_t * ray.ds * sigma);
-                        const float w = T * (1.0f - att);
-                        if (sa.tm) sh_basis_row<B>(sa, idx, vd, basis);
-                        sh_dots<B>(v, basis, sa.min_comp, sa.max_comp, tmp);
-                        a0 = fmaf(w, fast_sigmoid(tmp[0]), a0);
-                        a1 = fmaf(w, fast_sigmoid(tmp[1]), a1);
-                        a2 = fmaf(w, fast_sigmoid(tmp[2]), a2);
-                        T *= att;
-                        if (T <= opt.stop_thresh) fin = 2;
-                    }
-                }
-                ray.t += delta_t;
-                if (fin == 0 && !(ray.t < ray.tmax)) fin = 1;
-            }
+        // S0: row of the pending candidate (row 0 stands in for "none": unconditional loads)
+        float v[D];
+        SVOXB_DBG((int64_t)max(p_idx, 0) < max(tr.M, (int64_t)1));
+        load_row<B, VEC>(tr.features + (size_t)(unsigned)max(p_idx, 0) * D, v);
+        // S1: next sample, brick lookup issued
+        bool trav = active && !trav_done;
+        Probe pb;
+        if (trav) {
+            if (!(ray.t < ray.tmax)) { trav_done = true; trav = false; }
+            else probe_begin<ACCEL>(tr, top, ray, pb);
         }
+        // S2: composite the pending candidate
+        bool stopped = false;
+        if (p_idx >= 0 && v[D - 1] > opt.sigma_thresh) {                              // rt_kernel.cu:279-320
+            float tmp[3];
+            const float att = expf(-p_dt * ray.ds * v[D - 1]);
+            const float w = T * (1.0f - att);
+            if (sa.tm) sh_basis_row<B>(sa, p_idx, vd, basis);
+            sh_dots<B>(v, basis, sa.min_comp, sa.max_comp, tmp);
+            a0 = fmaf(w, fast_sigmoid(tmp[0]), a0);
+            a1 = fmaf(w, fast_sigmoid(tmp[1]), a1);
+            a2 = fmaf(w, fast_sigmoid(tmp[2]), a2);
+            T *= att;
+            if (T <= opt.stop_thresh) stopped = true;
+        }
+        // S3: brick word consumed -> next candidate
+        int n_idx = -1;
+        float n_dt = 0.0f;
+        if (trav) {
+            probe_end<ACCEL>(tr, pb, ray, opt.step, n_idx, n_dt);
+            ray.t += n_dt;
+            if (!(ray.t < ray.tmax)) trav_done = true;
+        }
+        if (stopped) { n_idx = -1; trav_done = true; }
+        p_idx = n_idx; p_dt = n_dt;
+        const int fin = (active && trav_done && p_idx < 0) ? (stopped ? 2 : 1) : 0;   // 1 = left the volume, 2 = stopped early
         if (fin != 0) {                                                              // rt_kernel.cu:313-326
             float4 o;
             if (fin == 2) {
@@ -213,9 +225,9 @@ sh_rgb_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, const fl
     Ray ray;
     ViewDir vd{0.f, 0.f, 0.f};
     float basis[B];
-    float T = 1.0f, accum = 0.0f, T_end = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, gop = 0.0f;
-    int row = 0;
-    bool active = false;
+    float T = 1.0f, accum = 0.0f, T_end = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, gop = 0.0f, p_dt = 0.0f;
+    int row = 0, p_idx = -1;
+    bool active = false, trav_done = true;
     Queue q{0, 0, false};
     unsigned need = FULL;
 
@@ -223,7 +235,7 @@ sh_rgb_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, const fl
         if (need) {
             const unsigned got = refill<IMAGE, true>(src, off, scl, counter, q, need, lane, ray, row, &vd);
             if ((got >> lane) & 1u) {
-                active = true; T = 1.0f;
+                active = true; trav_done = false; T = 1.0f;
                 fmt_basis<B>(sa, vd.x, vd.y, vd.z, basis);
                 const float4 g = __ldcs(reinterpret_cast<const float4*>(grad_out) + row);
                 const float4 so = __ldcs(reinterpret_cast<const float4*>(saved_out) + row);
@@ -235,53 +247,59 @@ sh_rgb_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, const fl
         }
         if (__ballot_sync(FULL, active) == 0u) break;
 
-        bool fin = false;
-        if (active) {
-            if (!(ray.t < ray.tmax)) {
-                fin = true;
+        // S0 / S1 as in the forward kernel
+        float v[D];
+        SVOXB_DBG((int64_t)max(p_idx, 0) < max(tr.M, (int64_t)1));
+        load_row<B, VEC>(tr.features + (size_t)(unsigned)max(p_idx, 0) * D, v);
+        bool trav = active && !trav_done;
+        Probe pb;
+        if (trav) {
+            if (!(ray.t < ray.tmax)) { trav_done = true; trav = false; }
+            else probe_begin<ACCEL>(tr, top, ray, pb);
+        }
+        // S2: gradient of the pending candidate
+        if (p_idx >= 0 && v[D - 1] > 0.0f) {                                          // rt_kernel.cu:382,456
+            float tmp[3];
+            const float sigma = v[D - 1];
+            const float att = expf(-p_dt * sigma * ray.ds);
+            const float w = T * (1.0f - att), dd = p_dt * ray.ds;
+            if (sa.tm) sh_basis_row<B>(sa, p_idx, vd, basis);
+            sh_dots<B>(v, basis, sa.min_comp, sa.max_comp, tmp);
+            const float s0 = fast_sigmoid(tmp[0]), s1 = fast_sigmoid(tmp[1]), s2 = fast_sigmoid(tmp[2]);
+            const float c = s0 * g0 + s1 * g1 + s2 * g2;                              // rt_kernel.cu:416
+            float gs[3] = {w * s0 * (1.0f - s0) * g0, w * s1 * (1.0f - s1) * g1, w * s2 * (1.0f - s2) * g2};
+            T *= att;
+            accum -= w * c;                                                          // rt_kernel.cu:479-480
+            const float sgrad = dd * (c * T - accum) + dd * gop * T_end;              // rt_kernel.cu:486-490
+            // row gradient: d/d coef[t*B+i] = gs_t * basis_i inside the component window; sigma last
+#pragma unroll
+            for (int k = 0; k < D - 1; ++k) {
+                const int i = k % B;
+                v[k] = (i >= sa.min_comp && i <= sa.max_comp) ? gs[k / B] * basis[i] : 0.0f;
+            }
+            v[D - 1] = sgrad;
+            float* grow = grad + (size_t)(unsigned)p_idx * D;
+            if constexpr (VEC) {
+#pragma unroll
+                for (int k = 0; k < D / 4; ++k)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(grow + 4 * k), "f"(v[4 * k]),
+                                 "f"(v[4 * k + 1]), "f"(v[4 * k + 2]), "f"(v[4 * k + 3]) : "memory");
             } else {
-                int idx; float delta_t;
-                traverse<ACCEL>(tr, top, ray, opt.step, idx, delta_t);
-                if (idx >= 0) {
-                    const float* rowp = tr.features + (size_t)(unsigned)idx * D;
-                    const float sigma = __ldg(rowp + (D - 1));
-                    if (sigma > 0.0f) {                                              // rt_kernel.cu:382,456
-                        float v[D], tmp[3];
-                        load_row<B, VEC>(rowp, v);
-                        const float att = expf(-delta_t * sigma * ray.ds);
-                        const float w = T * (1.0f - att), dd = delta_t * ray.ds;
-                        if (sa.tm) sh_basis_row<B>(sa, idx, vd, basis);
-                        sh_dots<B>(v, basis, sa.min_comp, sa.max_comp, tmp);
-                        const float s0 = fast_sigmoid(tmp[0]), s1 = fast_sigmoid(tmp[1]), s2 = fast_sigmoid(tmp[2]);
-                        const float c = s0 * g0 + s1 * g1 + s2 * g2;                  // rt_kernel.cu:416
-                        float gs[3] = {w * s0 * (1.0f - s0) * g0, w * s1 * (1.0f - s1) * g1, w * s2 * (1.0f - s2) * g2};
-                        T *= att;
-                        accum -= w * c;                                              // rt_kernel.cu:479-480
-                        const float sgrad = dd * (c * T - accum) + dd * gop * T_end;  // rt_kernel.cu:486-490
-                        // row gradient: d/d coef[t*B+i] = gs_t * basis_i inside the component window; sigma last
 #pragma unroll
-                        for (int k = 0; k < D - 1; ++k) {
-                            const int i = k % B;
-                            v[k] = (i >= sa.min_comp && i <= sa.max_comp) ? gs[k / B] * basis[i] : 0.0f;
-                        }
-                        v[D - 1] = sgrad;
-                        float* grow = grad + (size_t)(unsigned)idx * D;
-                        if constexpr (VEC) {
-#pragma unroll
-                            for (int k = 0; k < D / 4; ++k)
-                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(grow + 4 * k), "f"(v[4 * k]),
-                                             "f"(v[4 * k + 1]), "f"(v[4 * k + 2]), "f"(v[4 * k + 3]) : "memory");
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < D; ++k)
-                                if (v[k] != 0.0f) atomicAdd(grow + k, v[k]);
-                        }
-                    }
-                }
-                ray.t += delta_t;
-                if (!(ray.t < ray.tmax)) fin = true;
+                for (int k = 0; k < D; ++k)
+                    if (v[k] != 0.0f) atomicAdd(grow + k, v[k]);
             }
         }
+        // S3
+        int n_idx = -1;
+        float n_dt = 0.0f;
+        if (trav) {
+            probe_end<ACCEL>(tr, pb, ray, opt.step, n_idx, n_dt);
+            ray.t += n_dt;
+            if (!(ray.t < ray.tmax)) trav_done = true;
+        }
+        p_idx = n_idx; p_dt = n_dt;
+        const bool fin = active && trav_done && p_idx < 0;
         if (fin) active = false;
         need = __ballot_sync(FULL, fin);
     }
@@ -289,8 +307,10 @@ sh_rgb_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, const fl
 
 // ---- host side ---------------------------------------------------------------------------------------------------
 template <int B, bool VEC, bool ACCEL, bool IMAGE>
-static int launch_sh_fwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const ShArgs& sa, float* out,
+static int launch_sh_fwd(const TreeArgs& tr_in, const RaySource& src, const MarchOpts& m, const ShArgs& sa, float* out,
                          cudaStream_t st) {
+    TreeArgs tr = tr_in;
+    if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;     // the marks encode sigma > 0: too strict for this predicate
     const size_t smem = ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0;
     auto kern = sh_rgb_fwd_kernel<B, VEC, ACCEL, IMAGE>;
     int grid = 0;

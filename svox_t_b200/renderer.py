@@ -146,9 +146,10 @@ class VolumeRenderer(nn.Module):
         keep the in-kernel sigmoid, for which one pass over the whole table would cost more than it saves."""
         ts = self.tree._spec(features, **kw)
         M, D = features.shape
-        if self.data_format.format == DataFormat.RGBA and 2 <= D <= 128 and n_rays * 32 >= M and features.is_cuda:
-            ts._act = self.tree.activated(features.detach())
-            if ts._accel is not None:
+        if n_rays * 32 >= M and features.is_cuda:
+            if self.data_format.format == DataFormat.RGBA and 2 <= D <= 128:
+                ts._act = self.tree.activated(features.detach())
+            if ts._accel is not None:       # every format keeps sigma in the last channel: dead rows are never fetched
                 ts._accel.mark_hits(features.detach())
         return ts
 
