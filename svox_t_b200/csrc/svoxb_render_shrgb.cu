@@ -15,6 +15,14 @@
 
 namespace svoxb {
 
+// L2 eviction priority of the gradient table (read-modify-written: a miss costs a DRAM read and a write-back), as in the
+// quad backward (svoxb_render_q.cu).
+__device__ __forceinline__ uint64_t sh_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
 struct ShArgs {
     int min_comp, max_comp;
     const float* tm;          // [M,4,4] per-row view rotation or nullptr
@@ -219,6 +227,8 @@ sh_rgb_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, const fl
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31;
     constexpr int D = 3 * B + 1;
+    float* stage = reinterpret_cast<float*>(smem_u32 + (ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0)) + (threadIdx.x >> 5) * 32 * D;
+    const uint64_t pol_last = sh_policy_evict_last();
     const float* off = tr.offset;
     const float* scl = tr.scaling;
 
@@ -258,6 +268,7 @@ sh_rgb_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, const fl
             else probe_begin<ACCEL>(tr, top, ray, pb);
         }
         // S2: gradient of the pending candidate
+        int hit_idx = -1;
         if (p_idx >= 0 && v[D - 1] > 0.0f) {                                          // rt_kernel.cu:382,456
             float tmp[3];
             const float sigma = v[D - 1];
@@ -278,17 +289,42 @@ sh_rgb_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, const fl
                 v[k] = (i >= sa.min_comp && i <= sa.max_comp) ? gs[k / B] * basis[i] : 0.0f;
             }
             v[D - 1] = sgrad;
-            float* grow = grad + (size_t)(unsigned)p_idx * D;
+            hit_idx = p_idx;
             if constexpr (VEC) {
 #pragma unroll
                 for (int k = 0; k < D / 4; ++k)
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(grow + 4 * k), "f"(v[4 * k]),
-                                 "f"(v[4 * k + 1]), "f"(v[4 * k + 2]), "f"(v[4 * k + 3]) : "memory");
+                    reinterpret_cast<float4*>(stage + lane * D)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
             } else {
 #pragma unroll
-                for (int k = 0; k < D; ++k)
-                    if (v[k] != 0.0f) atomicAdd(grow + k, v[k]);
+                for (int k = 0; k < D; ++k) stage[lane * D + k] = v[k];
             }
+        }
+        // The 32 lanes' gradient rows leave through shared memory: consecutive lanes reduce consecutive pieces of a row, so
+        // one instruction covers 32 / (D/4) whole rows (full sectors) instead of one 16-byte piece of 32 different rows.
+        const unsigned hm = __ballot_sync(FULL, hit_idx >= 0);
+        if (hm) {
+            __syncwarp();
+            constexpr int PR = VEC ? D / 4 : D;                       // pieces per row
+#pragma unroll
+            for (int i = 0; i < PR; ++i) {
+                const int e = lane + 32 * i, r = e / PR, k = e - r * PR;
+                const int idx_r = __shfl_sync(FULL, hit_idx, r);
+                if (idx_r >= 0) {
+                    SVOXB_DBG((int64_t)idx_r < tr.M);
+                    float* grow = grad + (size_t)(unsigned)idx_r * D;
+                    if constexpr (VEC) {
+                        const float4 t = reinterpret_cast<const float4*>(stage)[e];
+                        asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(grow + 4 * k),
+                                     "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w), "l"(pol_last) : "memory");
+                    } else {
+                        const float t = stage[e];
+                        if (t != 0.0f)
+                            asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(grow + k), "f"(t), "l"(pol_last)
+                                         : "memory");
+                    }
+                }
+            }
+            __syncwarp();
         }
         // S3
         int n_idx = -1;
@@ -326,7 +362,7 @@ static int launch_sh_fwd(const TreeArgs& tr_in, const RaySource& src, const Marc
 template <int B, bool VEC, bool ACCEL, bool IMAGE>
 static int launch_sh_bwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const ShArgs& sa, const float* go,
                          const float* so, float* grad, cudaStream_t st) {
-    const size_t smem = ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0;
+    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * WARPS * 32 * (3 * B + 1);
     auto kern = sh_rgb_bwd_kernel<B, VEC, ACCEL, IMAGE>;
     int grid = 0;
     int rc = persistent_grid(kern, smem, src.total, grid);
