@@ -49,6 +49,27 @@ r = sv.VolumeRenderer(tree)
 jf = torch.randn(5, 7, device=dev, requires_grad=True)
 sw = torch.rand(M, 3, device=dev); ji = torch.randint(0, 5, (M, 3), device=dev, dtype=torch.int32)
 r.motion_feature_render(feats, jf, sw, ji, rays).sum().backward()
+# motion feature: table form (900 rays * 32 >= M) above; staged kernels (few rays) with B = 4 and B = 3, F = 32 / 7 / 17
+few = sv.Rays(*(t[:7].contiguous() for t in rays))
+for F, B in ((32, 4), (7, 3), (17, 4), (32, 5)):
+    jf = torch.randn(6, F, device=dev, requires_grad=True)
+    sw = torch.rand(M, B, device=dev); ji = torch.randint(0, 6, (M, B), device=dev, dtype=torch.int32)
+    r.motion_feature_render(feats, jf, sw, ji, few).sum().backward()
+    r.motion_feature_render(feats, jf, sw, ji, rays).sum().backward()
+# SG / ASG rows with three channels (lane-private RGB kernels), the point-wise operators, the dense-grid render
+for fmt, D, cols in (("SG4", 13, 4), ("ASG9", 28, 11)):
+    t4 = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=D, data_format=fmt, map_location=dev)
+    t4.extra_data = torch.rand(int(fmt[-1]), cols, device=dev) + 0.5
+    fx = torch.randn(M, D, device=dev, requires_grad=True)
+    sv.VolumeRenderer(t4)(fx, rays).sum().backward()
+    sv.VolumeRenderer(t4)(fx, few).sum().backward()
+q = torch.rand(777, 3, device=dev) * 1.2 - 0.1
+fq = torch.randn(M, 6, device=dev, requires_grad=True)
+tree(fq, q).sum().backward()
+tree.set(q, torch.randn(777, 6, device=dev)); tree.set(q, torch.randn(777, 2, device=dev))
+tree[:].corners; tree.snap(q)
+cam = C.CameraSpec(); cam.c2w = torch.from_numpy(synth.synth_cameras(1)[0]).to(dev); cam.fx = cam.fy = 31.0; cam.width, cam.height = 33, 19
+C.grid_weight_render(torch.rand(17, 17, 17, device=dev) * 9 - 3, cam, r._get_options(), torch.zeros(3, device=dev), torch.ones(3, device=dev))
 with tree.accumulate_weights() as acc:
     r(feats, rays); r.render_persp(feats, torch.from_numpy(synth.synth_cameras(1)[0]).to(dev), width=29, height=19, fx=25.0)
 torch.cuda.synchronize()
