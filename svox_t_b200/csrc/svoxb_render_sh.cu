@@ -226,9 +226,9 @@ march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, cons
 
     Ray ray;
     ViewDir vd{0.f, 0.f, 0.f};
-    float T = 1.0f, accum = 0.0f, T_end = 0.0f, gop = 0.0f;
-    int row = 0;
-    bool active = false;
+    float T = 1.0f, accum = 0.0f, T_end = 0.0f, gop = 0.0f, p_dt = 0.0f;
+    int row = 0, p_idx = -1;
+    bool active = false, trav_done = true;
     Queue q{0, 0, false};
     unsigned need = FULL;
 
@@ -236,7 +236,7 @@ march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, cons
         if (need) {
             unsigned got = refill<IMAGE, true>(src, off, scl, counter, q, need, lane, ray, row, &vd);
             if ((got >> lane) & 1u) {
-                active = true; T = 1.0f;
+                active = true; trav_done = false; T = 1.0f;
                 eval_basis(fa, vd.x, vd.y, vd.z, sm.basis[lane]);
             }
             need = 0;
@@ -260,27 +260,33 @@ march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, cons
         }
         if (__ballot_sync(FULL, active) == 0u) break;
 
-        bool hit = false, fin = false;
-        float w = 0.0f, dd = 0.0f;
-        int hidx = 0;
-        if (active) {
-            if (!(ray.t < ray.tmax)) {
-                fin = true;
-            } else {
-                int64_t idx; float delta_t, sigma;
-                sample<ACCEL>(tr, top, ray, opt.step, idx, delta_t, sigma);
-                if (sigma > 0.0f) {                                              // rt_kernel.cu:382,456
-                    const float att = expf(-delta_t * sigma * ray.ds);
-                    w = T * (1.0f - att);
-                    dd = delta_t * ray.ds;
-                    hit = true; hidx = (int)idx;
-                    if (fa.tm) eval_basis_rotated(fa, hidx, vd, sm.basis[lane]);
-                    T *= att;
-                }
-                ray.t += delta_t;
-                if (!(ray.t < ray.tmax)) fin = true;
+        // software-pipelined like the forward kernel: pending candidate, sigma requested ahead of the traversal step
+        const float sig = __ldg(tr.features + (size_t)(unsigned)max(p_idx, 0) * D + (D - 1));
+        int n_idx = -1;
+        float n_dt = 0.0f;
+        if (active && !trav_done) {
+            if (!(ray.t < ray.tmax)) trav_done = true;
+            else {
+                Probe pb;
+                probe_begin<ACCEL>(tr, top, ray, pb);
+                probe_end<ACCEL>(tr, pb, ray, opt.step, n_idx, n_dt);
+                ray.t += n_dt;
+                if (!(ray.t < ray.tmax)) trav_done = true;
             }
         }
+        bool hit = false;
+        float w = 0.0f, dd = 0.0f;
+        int hidx = 0;
+        if (p_idx >= 0 && sig > 0.0f) {                                          // rt_kernel.cu:382,456
+            const float att = expf(-p_dt * sig * ray.ds);
+            w = T * (1.0f - att);
+            dd = p_dt * ray.ds;
+            hit = true; hidx = p_idx;
+            if (fa.tm) eval_basis_rotated(fa, hidx, vd, sm.basis[lane]);
+            T *= att;
+        }
+        p_idx = n_idx; p_dt = n_dt;
+        const bool fin = active && trav_done && p_idx < 0;
         __syncwarp();
 
         // Every lane serves its own hit (lane-private basis / staged grad_out slots in shared memory): C dot products,
@@ -1157,8 +1163,10 @@ static int make_fmt(const svoxb_tree* tree, const svoxb_render_options* opt, Fmt
 }
 
 template <int K, bool ACCEL, bool IMAGE>
-static int launch_fmt_fwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const FmtArgs& f, float* out,
+static int launch_fmt_fwd(const TreeArgs& tr_in, const RaySource& src, const MarchOpts& m, const FmtArgs& f, float* out,
                           cudaStream_t st) {
+    TreeArgs tr = tr_in;
+    if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;     // the marks encode sigma > 0: too strict for this predicate
     const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(FmtSmem) * WARPS;
     auto kern = march_fmt_fwd_kernel<K, ACCEL, IMAGE>;
     int grid = 0;
