@@ -191,3 +191,32 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in j["config"] and "model" not in j["config"]
+
+
+def test_view_row_accessors_on_cpu_tensors():
+    """N3TreeView.values / set / in-place row ops are plain tensor indexing over `features` (no kernel involved), so they
+    are checked here on a CPU tree assembled from the generator's tensors; anything that needs a kernel still raises."""
+    import svox_t_b200 as sv
+    tr = synth.synth_tree(3, "ball", r_out=0.45)
+    D = 5
+    tree = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=D, map_location="cpu")
+    f = torch.from_numpy(synth.synth_features(tr["M"], D))
+    tree.features = torch.nn.Parameter(f.clone())
+    view = tree[:]
+    idx = tree.data[view.key][..., 0].long()
+    ok = idx < tr["M"]
+    assert 0 < int(ok.sum()) < len(view) and view.shape == (len(view), D) and view.ndim == 2
+    vals = view.values
+    assert torch.equal(vals[ok].detach(), f[idx[ok]]) and float(vals[~ok].detach().abs().sum()) == 0.0
+    view.clamp_(min=0.25)
+    assert float(tree.features.detach()[idx[ok]].min()) >= 0.25
+    view.set(torch.full((len(view), D), 2.0))
+    assert bool((tree.features.detach()[idx[ok]] == 2.0).all())
+    view.uniform_(3.0, 4.0); view.relu_(); view.nan_to_num_()
+    got = tree.features.detach()[idx[ok]]
+    assert float(got.min()) >= 3.0 and float(got.max()) <= 4.0
+    assert view._indexer().shape == (len(view), 4) and "leaves" in repr(view)
+    with pytest.raises(RuntimeError):
+        view.corners_local                       # calc_corners is a CUDA kernel: no CPU fallback
+    with pytest.raises(RuntimeError):
+        tree.set(torch.rand(4, 3), torch.rand(4, D))
