@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SVOXB_ABI_VERSION 7
+#define SVOXB_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define SVOXB_API __attribute__((visibility("default")))
@@ -114,7 +114,8 @@ SVOXB_API int svoxb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* ---- acceleration structure (no reference counterpart; derived data, rebuilt when child/data change) */
 /* max_depth <= 0: derive it from parent_depth (must then be non-NULL). Synchronises the stream (one small read-back
  * per stage). Memory comes from the device's default stream-ordered pool on `stream`; svoxb_accel_destroy releases it
- * in stream order on that same stream, so work reading the accelerator on OTHER streams must have completed. */
+ * in stream order on that same stream, after the work this library launched with the accelerator on other streams
+ * (the four most recent distinct streams are remembered and waited for with an event each). */
 SVOXB_API int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* stream, svoxb_accel** out);
 SVOXB_API void svoxb_accel_destroy(svoxb_accel* accel);
 SVOXB_API int64_t svoxb_accel_bytes(const svoxb_accel* accel);
@@ -191,8 +192,14 @@ SVOXB_API int svoxb_render_rays_fwd(const svoxb_tree* tree, const float* origins
 /* volume_render_backward (rt_kernel.cu:674-694, 1402-1426): grad_features[M, D] += dL/dfeatures.
  * One re-march instead of the reference's two: saved_out[Q, D] is the forward output computed with
  * sigma_thresh = 0 and stop_thresh < 0 (the backward's own hit predicate, rt_kernel.cu:382,456); with the
- * default options that is exactly what svoxb_render_rays_fwd returned. The caller zero-fills
- * grad_features (the reference allocates zeros_like(features), rt_kernel.cu:1415). */
+ * default options that is exactly what svoxb_render_rays_fwd returned. It MUST be that unmodified output for the same
+ * tree, features, rays and options: the kernel takes T_end = 1 - saved_out[q, D-1] and <grad_out[q], saved_out[q]>
+ * from it and cannot tell a stale or foreign buffer from the right one (the result would be plausible, wrong sigma
+ * gradients). When in doubt, render again with those options and pass the fresh output. The caller zero-fills
+ * grad_features (the reference allocates zeros_like(features), rt_kernel.cu:1415).
+ * Limits of this build (stated once for every march entry point): float32 only -- the reference also instantiates
+ * float64 (AT_DISPATCH_FLOATING_TYPES, rt_kernel.cu:1373); 2 <= D <= 128 -- the reference loops over any width
+ * (rt_kernel.cu:302-306); wider tables fail with SVOXB_EINVAL ("feature width D=... is not supported"). */
 SVOXB_API int svoxb_render_rays_bwd(const svoxb_tree* tree, const float* origins, const float* dirs, const float* vdirs,
                           int64_t Q, const svoxb_render_options* opt, const float* grad_out, const float* saved_out,
                           float* grad_features, void* stream);
@@ -295,6 +302,28 @@ SVOXB_API int svoxb_build_octree_count(const float* pts, int64_t P, int32_t L, c
                              void* work, int64_t* n_nodes_host, void* stream);
 SVOXB_API int svoxb_build_octree_emit(int64_t P, int32_t L, const void* work, int64_t n_nodes,
                             int32_t* child, int32_t* data, int32_t* parent_depth, void* stream);
+
+/* ---- multi-GPU exchange (no reference counterpart: the reference is single-GPU) --------------- */
+/* The path's one exchange step: the leaf-gradient table grad[M, D] -- the reference's
+ * zeros_like(features), rt_kernel.cu:1415 -- summed over the GPUs of one node, IN PLACE, by one kernel per rank over a
+ * symmetric allocation (the same buffer mapped into every rank's address space, optionally with an NVSwitch multicast
+ * mapping). The caller owns the allocation and the rendezvous (svox_t_b200/dist.py uses
+ * torch.distributed._symmetric_memory); this struct carries raw addresses only. Every rank must call with the same
+ * n_floats, blocks and epoch sequence, on a stream whose earlier work has produced the rank's table. */
+typedef struct svoxb_peer_group {
+    int32_t rank, world;        /* world <= 16 (one NVSwitch domain)                                            */
+    void* const* buffers;       /* HOST array [world]: this process's mapping of every rank's buffer            */
+    void* multicast;            /* multicast mapping of the buffer (multimem.ld_reduce / multimem.st), or NULL: */
+                                /* the kernel then reads / writes the peers' mappings directly                  */
+    int64_t table_offset;       /* byte offset of the float table inside the buffer (16-byte aligned)           */
+    int64_t flags_offset;       /* byte offset of blocks * world uint32 flag words, zero at set-up              */
+    int64_t status_offset;      /* byte offset of one uint32: 0, or 1 + the rank a barrier gave up waiting for  */
+    int32_t blocks;             /* CTAs per rank (<= SM count: block b of every rank meets block b of the others) */
+    uint32_t epoch;             /* first call 1, then += 2 per call (the call's two barriers use epoch, epoch+1) */
+} svoxb_peer_group;
+
+SVOXB_API int svoxb_exchange_max_blocks(void);
+SVOXB_API int svoxb_exchange_sum(const svoxb_peer_group* group, int64_t n_floats, void* stream);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,12 @@ class _COptions(ctypes.Structure):
     ]
 
 
+class _CPeerGroup(ctypes.Structure):
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("buffers", ctypes.POINTER(ctypes.c_void_p)),
+                ("multicast", ctypes.c_void_p), ("table_offset", ctypes.c_int64), ("flags_offset", ctypes.c_int64),
+                ("status_offset", ctypes.c_int64), ("blocks", ctypes.c_int32), ("epoch", ctypes.c_uint32)]
+
+
 class _CCamera(ctypes.Structure):
     _fields_ = [("c2w", ctypes.c_void_p), ("fx", ctypes.c_float), ("fy", ctypes.c_float),
                 ("width", ctypes.c_int32), ("height", ctypes.c_int32),
@@ -94,6 +100,8 @@ SYMBOLS = {
     "svoxb_warp_vertices_bwd": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _I32, _I32, _VP, _VP, _VP, _VP]),
     "svoxb_p2v_bwd": (ctypes.c_int, [_VP, _VP, _VP, _I64, _I32, _VP, _VP, _I32, _F, _F, _VP, _VP, _VP]),
     "svoxb_p2v": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP, _VP, _I32, _F, _F, _VP, _VP]),
+    "svoxb_exchange_max_blocks": (ctypes.c_int, []),
+    "svoxb_exchange_sum": (ctypes.c_int, [ctypes.POINTER(_CPeerGroup), _I64, _VP]),
     "svoxb_build_work_bytes": (ctypes.c_size_t, [_I64, _I32]),
     "svoxb_build_octree_count": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP, _VP, ctypes.POINTER(_I64), _VP]),
     "svoxb_build_octree_emit": (ctypes.c_int, [_I64, _I32, _VP, _I64, _VP, _VP, _VP, _VP]),
@@ -115,7 +123,7 @@ def load_library():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.svoxb_abi_version() != 7:
+        if lib.svoxb_abi_version() != 8:
             raise ImportError("svox_t_b200: libsvoxb.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib
@@ -154,6 +162,27 @@ def _check_input(t, name, dtype=None):
         raise RuntimeError(f"{name} must be contiguous")
     if dtype is not None and t.dtype != dtype:
         raise RuntimeError(f"{name} must be {dtype} (got {t.dtype}); only float32 features/rays are implemented")
+
+
+class _TensorIdentity:
+    """What a derived table (activated features, hit marks, accelerator) was computed from: the tensor's STORAGE object,
+    held strongly -- so its address cannot be handed to another tensor while this key is alive -- plus offset, shape,
+    strides and the version counter. A fresh tensor that happens to reuse a freed block at the same address (every
+    training step, with the caching allocator) is a different storage and never matches; views / ``detach()`` of the
+    same tensor do. Writes through ``.data`` or a raw pointer bypass the version counter and cannot be seen: callers
+    that do that must bump it (``torch.autograd.graph.increment_version``) -- the library's own in-place kernels do."""
+    __slots__ = ("storage", "key")
+
+    def __init__(self, t):
+        self.storage = t.untyped_storage()
+        self.key = self._key(t, self.storage)
+
+    @staticmethod
+    def _key(t, st):
+        return (st._cdata, t.storage_offset(), tuple(t.shape), tuple(t.stride()), t._version)
+
+    def matches(self, t):
+        return t is not None and self._key(t, t.untyped_storage()) == self.key
 
 
 # ---- spec records (field names of svox.cpp:74-117) --------------------------------------------------------------
@@ -299,11 +328,12 @@ class Accel:
 
     @staticmethod
     def _make_key(ts):
-        return (ts.child.data_ptr(), ts.data.data_ptr(), ts.child._version, ts.data._version,
-                tuple(ts.child.shape), int(ts.features.shape[0]), int(ts.n_internal))
+        return (_TensorIdentity(ts.child), _TensorIdentity(ts.data), int(ts.features.shape[0]), int(ts.n_internal))
 
     def matches(self, ts):
-        return self.handle and self._key == self._make_key(ts)
+        k = self._key
+        return bool(self.handle) and k[0].matches(ts.child) and k[1].matches(ts.data) and \
+            k[2:] == (int(ts.features.shape[0]), int(ts.n_internal))
 
     def mark_hits(self, features):
         """Refresh the per-leaf "sigma <= 0" marks for this exact (storage, version) of ``features``; the march then
@@ -314,10 +344,11 @@ class Accel:
         with torch.cuda.device(features.device):
             _check(self._lib.svoxb_accel_mark_hits(self.handle, _ptr(features), features.shape[0], features.shape[1],
                                                    _stream()))
-        self._marks_key = Activated._make_key(features)
+        self._marks_key = _TensorIdentity(features)
 
     def marks_match(self, features):
-        return getattr(self, "_marks_key", None) == Activated._make_key(features)
+        k = getattr(self, "_marks_key", None)
+        return k is not None and k.matches(features)
 
     @property
     def nbytes(self):
@@ -341,12 +372,13 @@ class Accel:
 
 class Activated:
     """features with the sigmoid applied once per row to the payload channels (svoxb_activate_features). Valid for
-    exactly one (storage, version, shape) of ``features``; the renderer rebuilds it whenever features change."""
+    exactly one (storage object, version, layout) of ``features`` (_TensorIdentity); the renderer rebuilds it whenever
+    features change or another tensor is passed -- also one that reuses the address of a freed one."""
 
     def __init__(self, features):
         lib = load_library()
         _check_input(features, "features", torch.float32)
-        self._key = self._make_key(features)
+        self._key = _TensorIdentity(features)
         M, D = features.shape
         with torch.cuda.device(features.device):
             if D % 4 == 0:
@@ -359,12 +391,8 @@ class Activated:
             _check(lib.svoxb_activate_features(_ptr(features), M, D, _ptr(self.table), stride, _ptr(self.sigma),
                                                _stream()))
 
-    @staticmethod
-    def _make_key(f):
-        return (f.data_ptr(), f._version, tuple(f.shape))
-
     def matches(self, features):
-        return self._key == self._make_key(features)
+        return self._key.matches(features)
 
 
 # ---- functions (svox.cpp:119-144) -----------------------------------------------------------------------------------
@@ -458,10 +486,15 @@ def volume_render_with_depth(tree, rays, opt):
     return _render_fwd(tree, rays, opt, True)
 
 
-def _saved_out_for_backward(tree, opt, fwd_out, render_again):
+def _saved_out_for_backward(tree, opt, fwd_out, render_again, expect_shape=None):
     # The backward's hit predicate is sigma > 0 with no early stop (rt_kernel.cu:382,456). With the default
     # options the forward output IS the backward's saved state; otherwise re-render with those semantics.
-    if fwd_out is not None and opt.sigma_thresh == 0.0 and opt.stop_thresh <= 0.0:
+    # ``fwd_out`` must be the UNMODIFIED output of the forward for the same tree, features, rays and options: the
+    # backward reads T_end = 1 - out[:, D-1] and <grad_out, out> from it. Anything else (None, another shape, another
+    # dtype / device) is not trusted and the state is re-rendered.
+    if (fwd_out is not None and expect_shape is not None and tuple(fwd_out.shape) == tuple(expect_shape)
+            and fwd_out.dtype == torch.float32 and fwd_out.is_cuda and fwd_out.is_contiguous()
+            and opt.sigma_thresh == 0.0 and opt.stop_thresh <= 0.0):
         return fwd_out
     return render_again()
 
@@ -483,7 +516,7 @@ def volume_render_backward(tree, rays, opt, grad_output, saved_out=None):
         return o
 
     with torch.cuda.device(dev):
-        so = _saved_out_for_backward(tree, opt, saved_out, again)
+        so = _saved_out_for_backward(tree, opt, saved_out, again, grad_output.shape)
         grad = torch.zeros_like(tree.features)
         _check(lib.svoxb_render_rays_bwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), _ptr(rays.vdirs), Q,
                                          ctypes.byref(bopt), _ptr(grad_output), _ptr(so), _ptr(grad), _stream()))
@@ -529,7 +562,7 @@ def volume_render_image_backward(tree, cam, opt, grad_output, saved_out=None):
         return o
 
     with torch.cuda.device(dev):
-        so = _saved_out_for_backward(tree, opt, saved_out, again)
+        so = _saved_out_for_backward(tree, opt, saved_out, again, grad_output.shape)
         grad = torch.zeros_like(tree.features)
         _check(lib.svoxb_render_image_bwd(ctypes.byref(ct), ctypes.byref(cc), ctypes.byref(bopt), _ptr(grad_output),
                                           _ptr(so), _ptr(grad), _stream()))

@@ -31,6 +31,7 @@ struct RaySource {
     int ndc_w, ndc_h;              // camera rays: NDC conversion when ndc_w >= 0 (rt_kernel.cu:1168-1191)
     float ndc_focal;
     int chunk;                     // explicit rays: rays fetched from the queue per atomic (0 = RAY_CHUNK)
+    const int* order;              // explicit rays, optional: queue position -> ray index (svoxb_order.cu: longest first)
 };
 
 struct ViewDir {
@@ -127,9 +128,10 @@ __device__ __forceinline__ unsigned refill(const RaySource& src, const float* of
         const bool take = ((need >> lane) & 1u) && rank < avail;
         bool valid = false;
         if (take) {
-            const int id = q.next + rank;
+            const int pos = q.next + rank;
             float ox, oy, oz, dx, dy, dz;
             if (IMAGE) {
+                const int id = pos;
                 const int tile = (int)(id >> 6), in = (int)(id & 63);
                 const int px = (tile % src.tiles_x) * 8 + (in & 7);
                 const int py = src.row_begin + (tile / src.tiles_x) * 8 + (in >> 3);
@@ -142,6 +144,7 @@ __device__ __forceinline__ unsigned refill(const RaySource& src, const float* of
                 }
             } else {
                 valid = true;
+                const int id = src.order ? __ldg(src.order + pos) : pos;
                 const float* o = src.origins + (int64_t)id * 3;
                 const float* d = src.dirs + (int64_t)id * 3;
                 ox = __ldg(o); oy = __ldg(o + 1); oz = __ldg(o + 2);
@@ -317,6 +320,10 @@ static int persistent_grid(Kern kern, size_t smem, int64_t queue_len, int& grid,
 
 // Quad-lane kernels (svoxb_render_q.cu): D % 4 == 0 (4 <= D <= 128), or any D <= 128 with the padded activated table.
 bool quad_supported(const TreeArgs& tr);
+// svoxb_order.cu: longest-first order of a short explicit ray batch (stream-ordered scratch, released by the caller)
+bool want_ray_order(const TreeArgs& tr, int64_t Q);
+int build_ray_order(const TreeArgs& tr, const float* origins, const float* dirs, int64_t Q, float step, int** order,
+                    cudaStream_t st);
 int launch_fwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, float* out,
                     float* depth, cudaStream_t st);
 int launch_bwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, const float* grad_out,

@@ -356,7 +356,7 @@ depth_kernel(TreeArgs tr, const float* __restrict__ origins, const float* __rest
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
-int make_tree_args(const svoxb_tree* t, TreeArgs& a);   // svoxb_tree.cu
+int make_tree_args(const svoxb_tree* t, TreeArgs& a, void* use_stream);   // svoxb_tree.cu
 
 // svoxb_render_sh.cu: the view-dependent formats (SH / SG / ASG)
 int fmt_render_fwd(const svoxb_tree* tree, const TreeArgs& tr, const RaySource& src, const MarchOpts& m,
@@ -478,7 +478,7 @@ extern "C" int svoxb_render_rays_fwd(const svoxb_tree* tree, const float* origin
                                      const float* vdirs, int64_t Q, const svoxb_render_options* opt, float* out,
                                      float* depth, void* stream) {
     TreeArgs tr; MarchOpts m; RaySource src;
-    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = check_opts(opt, m); if (rc) return rc;
     rc = make_source(origins, dirs, vdirs, Q, nullptr, opt, src); if (rc) return rc;
     SVOXB_REQUIRE(Q == 0 || out != nullptr, "out is NULL");
@@ -486,31 +486,44 @@ extern "C" int svoxb_render_rays_fwd(const svoxb_tree* tree, const float* origin
     if (opt->format != SVOXB_FORMAT_RGBA) {
         SVOXB_REQUIRE(vdirs != nullptr, "view-dependent formats need vdirs");
         SVOXB_REQUIRE(depth == nullptr, "fused depth is only available for the RGBA format; call svoxb_render_depth");
-        return fmt_render_fwd(tree, tr, src, m, opt, false, out, (cudaStream_t)stream);
     }
-    return dispatch_fwd<false>(tr, src, m, out, depth, (cudaStream_t)stream);
+    // short batches: hand the rays out longest first (svoxb_order.cu)
+    cudaStream_t st = (cudaStream_t)stream;
+    int* order = nullptr;
+    if (want_ray_order(tr, Q)) { rc = build_ray_order(tr, origins, dirs, Q, m.step, &order, st); if (rc) return rc; }
+    src.order = order;
+    if (opt->format != SVOXB_FORMAT_RGBA) rc = fmt_render_fwd(tree, tr, src, m, opt, false, out, st);
+    else rc = dispatch_fwd<false>(tr, src, m, out, depth, st);
+    if (order) cudaFreeAsync(order, st);
+    return rc;
 }
 
 extern "C" int svoxb_render_rays_bwd(const svoxb_tree* tree, const float* origins, const float* dirs,
                                      const float* vdirs, int64_t Q, const svoxb_render_options* opt,
                                      const float* grad_out, const float* saved_out, float* grad_features, void* stream) {
     TreeArgs tr; MarchOpts m; RaySource src;
-    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = check_opts(opt, m); if (rc) return rc;
     rc = make_source(origins, dirs, vdirs, Q, nullptr, opt, src); if (rc) return rc;
     SVOXB_REQUIRE(Q == 0 || (grad_out && saved_out && grad_features), "grad_out/saved_out/grad_features NULL");
     if (Q == 0) return 0;
     if (opt->format != SVOXB_FORMAT_RGBA) {
         SVOXB_REQUIRE(vdirs != nullptr, "view-dependent formats need vdirs");
-        return fmt_render_bwd(tree, tr, src, m, opt, false, grad_out, saved_out, grad_features, (cudaStream_t)stream);
     }
-    return dispatch_bwd<false>(tr, src, m, grad_out, saved_out, grad_features, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    int* order = nullptr;
+    if (want_ray_order(tr, Q)) { rc = build_ray_order(tr, origins, dirs, Q, m.step, &order, st); if (rc) return rc; }
+    src.order = order;
+    if (opt->format != SVOXB_FORMAT_RGBA) rc = fmt_render_bwd(tree, tr, src, m, opt, false, grad_out, saved_out, grad_features, st);
+    else rc = dispatch_bwd<false>(tr, src, m, grad_out, saved_out, grad_features, st);
+    if (order) cudaFreeAsync(order, st);
+    return rc;
 }
 
 extern "C" int svoxb_render_image_fwd(const svoxb_tree* tree, const svoxb_camera* cam,
                                       const svoxb_render_options* opt, float* out, float* depth, void* stream) {
     TreeArgs tr; MarchOpts m; RaySource src;
-    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = check_opts(opt, m); if (rc) return rc;
     SVOXB_REQUIRE(cam != nullptr && out != nullptr, "camera/out NULL");
     rc = make_source(nullptr, nullptr, nullptr, 0, cam, opt, src); if (rc) return rc;
@@ -525,7 +538,7 @@ extern "C" int svoxb_render_image_bwd(const svoxb_tree* tree, const svoxb_camera
                                       const svoxb_render_options* opt, const float* grad_out,
                                       const float* saved_out, float* grad_features, void* stream) {
     TreeArgs tr; MarchOpts m; RaySource src;
-    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = check_opts(opt, m); if (rc) return rc;
     SVOXB_REQUIRE(cam && grad_out && saved_out && grad_features, "camera/grad_out/saved_out/grad_features NULL");
     rc = make_source(nullptr, nullptr, nullptr, 0, cam, opt, src); if (rc) return rc;
@@ -537,7 +550,7 @@ extern "C" int svoxb_render_image_bwd(const svoxb_tree* tree, const svoxb_camera
 extern "C" int svoxb_render_depth(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
                                   const svoxb_render_options* opt, float* depth, void* stream) {
     TreeArgs tr; MarchOpts m;
-    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = check_opts(opt, m); if (rc) return rc;
     SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (origins && dirs && depth)), "bad ray batch");
     if (Q == 0) return 0;

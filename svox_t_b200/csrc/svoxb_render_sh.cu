@@ -1137,7 +1137,7 @@ static int mf_table_bwd(const TreeArgs& tr, const JointArgs& ja, const RaySource
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
-int make_tree_args(const svoxb_tree* t, TreeArgs& a);   // svoxb_tree.cu
+int make_tree_args(const svoxb_tree* t, TreeArgs& a, void* use_stream);   // svoxb_tree.cu
 
 static int make_fmt(const svoxb_tree* tree, const svoxb_render_options* opt, FmtArgs& f) {
     const int D = tree->D, B = opt->basis_dim;
@@ -1276,7 +1276,7 @@ extern "C" int svoxb_motion_feature_render_fwd(const svoxb_tree* tree, const flo
                                                const float* skinning_weights, const int32_t* joint_index, int32_t J,
                                                int32_t F, int32_t B, float* out, void* stream) {
     TreeArgs tr; JointArgs ja;
-    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     SVOXB_REQUIRE(opt != nullptr, "render options are NULL");
     rc = make_joint_args(tree, joint_features, skinning_weights, joint_index, J, F, B, ja); if (rc) return rc;
     SVOXB_REQUIRE(Q >= 0 && Q < (1ll << 31) && (Q == 0 || (origins && dirs && out)), "bad ray batch");
@@ -1322,7 +1322,7 @@ extern "C" int svoxb_motion_feature_render_bwd(const svoxb_tree* tree, const flo
                                                int32_t F, int32_t B, const float* grad_out, float* grad_joint_features,
                                                void* stream) {
     TreeArgs tr; JointArgs ja;
-    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     SVOXB_REQUIRE(opt != nullptr, "render options are NULL");
     rc = make_joint_args(tree, joint_features, skinning_weights, joint_index, J, F, B, ja); if (rc) return rc;
     SVOXB_REQUIRE(grad_joint_features != nullptr, "grad_joint_features is NULL");

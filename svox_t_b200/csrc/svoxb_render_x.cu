@@ -167,7 +167,7 @@ weight_accum_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict
     }
 }
 
-int make_tree_args(const svoxb_tree* t, TreeArgs& a);
+int make_tree_args(const svoxb_tree* t, TreeArgs& a, void* use_stream);   // svoxb_tree.cu
 
 static int simple_opts(const svoxb_render_options* opt, MarchOpts& m) {
     SVOXB_REQUIRE(opt != nullptr, "render options are NULL");
@@ -197,7 +197,7 @@ using namespace svoxb;
 extern "C" int svoxb_opacity_render_fwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
                                         const svoxb_render_options* opt, float* out, void* stream) {
     TreeArgs tr; MarchOpts m;
-    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = simple_opts(opt, m); if (rc) return rc;
     SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (origins && dirs && out)), "bad ray batch");
     if (Q == 0) return 0;
@@ -209,7 +209,7 @@ extern "C" int svoxb_opacity_render_bwd(const svoxb_tree* tree, const float* ori
                                         const svoxb_render_options* opt, const float* grad_out, float* grad_features,
                                         void* stream) {
     TreeArgs tr; MarchOpts m;
-    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = simple_opts(opt, m); if (rc) return rc;
     SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (origins && dirs && grad_out && grad_features)), "bad arguments");
     if (Q == 0) return 0;
@@ -221,7 +221,7 @@ extern "C" int svoxb_motion_render(const svoxb_tree* tree, const float* origins,
                                    const svoxb_render_options* opt, const float* extra_data, int32_t J, float* out,
                                    float* depth, float* hit_point, int64_t* data_idx, void* stream) {
     TreeArgs tr; MarchOpts m;
-    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = simple_opts(opt, m); if (rc) return rc;
     SVOXB_REQUIRE(J >= 0 && (J == 0 || extra_data), "extra_data is NULL");
     SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (origins && dirs && depth && hit_point && data_idx && (J == 0 || out))), "bad arguments");
@@ -234,7 +234,7 @@ extern "C" int svoxb_accumulate_weights(const svoxb_tree* tree, const float* ori
                                         const svoxb_camera* cam, const svoxb_render_options* opt, float* weight_accum,
                                         void* stream) {
     TreeArgs tr; MarchOpts m;
-    int rc = make_tree_args(tree, tr); if (rc) return rc;
+    int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = simple_opts(opt, m); if (rc) return rc;
     SVOXB_REQUIRE(weight_accum != nullptr, "weight_accum is NULL");
     RaySource src{};

@@ -11,6 +11,7 @@
 #include <string.h>
 #include <atomic>
 #include <mutex>
+#include <vector>
 #include "svoxb_common.cuh"
 
 namespace svoxb {
@@ -46,26 +47,38 @@ int sm_count() {
     return cached[dev];
 }
 
-// Ring of 64-bit work counters per device; each launch gets the next slot, zeroed in stream order.
+// A ring of 64-bit work counters per (device, stream); each launch gets the next slot of ITS stream's ring, zeroed in
+// that stream's order. A slot is reused after N_COUNTERS later launches on the same stream, which stream order places
+// after the kernel that owned it; launches on other streams never touch it (a ring shared by all streams would let 256
+// short launches on stream B reset the queue of a long persistent march on stream A).
 static constexpr int N_COUNTERS = 256;
-static unsigned long long* g_counters[64] = {nullptr};
-static std::atomic<unsigned> g_counter_next{0};
+struct CounterRing {
+    int dev;
+    cudaStream_t stream;
+    unsigned long long* base;
+    unsigned next;
+};
+static std::vector<CounterRing> g_rings;
 static std::mutex g_counter_mu;
 
 unsigned long long* work_counter(cudaStream_t stream) {
     int dev = 0;
     if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return nullptr;
-    if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return nullptr; }
-    if (!g_counters[dev]) {
+    unsigned long long* c = nullptr;
+    {
         std::lock_guard<std::mutex> lk(g_counter_mu);
-        if (!g_counters[dev]) {
+        CounterRing* ring = nullptr;
+        for (auto& r : g_rings)
+            if (r.dev == dev && r.stream == stream) { ring = &r; break; }
+        if (!ring) {
             unsigned long long* p = nullptr;
             if (check_cuda(cudaMalloc(&p, sizeof(unsigned long long) * N_COUNTERS), "cudaMalloc(work counters)"))
                 return nullptr;
-            g_counters[dev] = p;
+            g_rings.push_back(CounterRing{dev, stream, p, 0u});
+            ring = &g_rings.back();
         }
+        c = ring->base + (ring->next++ % N_COUNTERS);
     }
-    unsigned long long* c = g_counters[dev] + (g_counter_next.fetch_add(1) % N_COUNTERS);
     if (check_cuda(cudaMemsetAsync(c, 0, sizeof(unsigned long long), stream), "cudaMemsetAsync(work counter)"))
         return nullptr;
     return c;
@@ -85,9 +98,32 @@ struct svoxb_accel {
     cudaStream_t stream;    // creation stream: the stream-ordered allocations are released on it
     const float* marks_features;   // table the ACC_MISS bits were last computed from (svoxb_accel_mark_hits), or NULL
     int marks_D;
+    cudaStream_t used[4];   // streams other than `stream` that kernels reading the cells were launched on (the most
+    int n_used;             // recent four): svoxb_accel_destroy orders the release after their work
 };
 
 namespace svoxb {
+
+int make_tree_args(const svoxb_tree* t, TreeArgs& a);
+
+// Entry points that launch on `use_stream` kernels reading the accelerator: also notes the stream in the accelerator,
+// so that its stream-ordered release waits for them.
+int make_tree_args(const svoxb_tree* t, TreeArgs& a, void* use_stream) {
+    const int rc = make_tree_args(t, a);
+    if (rc == 0 && t->accel) {
+        svoxb_accel* acc = const_cast<svoxb_accel*>(t->accel);
+        cudaStream_t st = static_cast<cudaStream_t>(use_stream);
+        if (st != acc->stream) {
+            bool seen = false;
+            for (int i = 0; i < acc->n_used; ++i) seen |= acc->used[i] == st;
+            if (!seen) {
+                if (acc->n_used == 4) { for (int i = 0; i < 3; ++i) acc->used[i] = acc->used[i + 1]; acc->n_used = 3; }
+                acc->used[acc->n_used++] = st;
+            }
+        }
+    }
+    return rc;
+}
 
 int make_tree_args(const svoxb_tree* t, TreeArgs& a) {
     SVOXB_REQUIRE(t != nullptr, "tree is NULL");
@@ -446,7 +482,14 @@ static int* pinned_scalars() {
 extern "C" void svoxb_accel_destroy(svoxb_accel* a) {
     if (!a) return;
     // released in stream order on the creation stream: work that still reads the accelerator on that stream
-    // finishes first. Callers using it on other streams must have synchronised them (documented in svoxb.h).
+    // finishes first; work launched through this library on other streams is waited for with an event each.
+    for (int i = 0; i < a->n_used; ++i) {
+        cudaEvent_t ev;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) continue;
+        if (cudaEventRecord(ev, a->used[i]) == cudaSuccess) cudaStreamWaitEvent(a->stream, ev, 0);
+        else cudaGetLastError();        // the stream no longer exists: its work has finished
+        cudaEventDestroy(ev);
+    }
     for (int s = 0; s < MAX_STAGES; ++s)
         if (a->cells[s]) cudaFreeAsync(a->cells[s], a->stream);
     delete a;

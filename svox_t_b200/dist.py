@@ -4,6 +4,7 @@ for the plumbing (NCCL over NVLink/NVSwitch on the B200 box, gloo on CPU for the
 
 The reference has no multi-GPU support at all; this module is new.
 """
+import ctypes
 import os
 
 import torch
@@ -53,6 +54,106 @@ def all_reduce_leaf_grads(grad, group=None, async_op=False):
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return None
     return dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+class LeafGradExchange:
+    """The leaf-gradient table of one training step, held in SYMMETRIC memory so that the exchange is one hand-written
+    kernel (csrc/svoxb_exchange.cu: flag barrier -> in-switch reduction with multimem.ld_reduce / multimem.st over the
+    NVSwitch multicast mapping, or peer loads/stores when the fabric offers no multicast -> flag barrier), in place.
+
+        xchg = LeafGradExchange(M, D, device)      # collective: every rank of the group
+        grad = xchg.zeroed_table()                 # [M, D] view, zero-filled on the current stream
+        ... backward kernels reduce into grad ...
+        xchg.all_reduce_()                         # grad now holds the sum over the ranks, on every rank
+
+    torch.distributed._symmetric_memory is the plumbing (allocation + address exchange); the kernel sees raw addresses
+    through the C ABI (svoxb_peer_group). Falls back to NCCL's all-reduce on an ordinary tensor when symmetric memory
+    is not available (``backend == "nccl"``); a world of one needs neither."""
+
+    FLAG_BYTES = 1 << 16
+
+    def __init__(self, M, D, device, group=None, blocks=None, force_backend=None):
+        from . import csrc as _C
+        self._C = _C
+        self.M, self.D, self.device = int(M), int(D), torch.device(device)
+        self.group = group if group is not None else (dist.group.WORLD if dist.is_initialized() else None)
+        self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        n = self.M * self.D
+        self.n_floats = (n + 3) // 4 * 4
+        self.backend = "local"
+        self._hdl = None
+        if self.world > 1:
+            self.backend = force_backend or os.environ.get("SVOXB_EXCHANGE", "auto")
+            if self.backend in ("auto", "nvls", "p2p"):
+                try:
+                    self._setup_symmetric(blocks)
+                except Exception as e:                              # no symmetric memory on this fabric / build
+                    if self.backend != "auto":
+                        raise
+                    self._why_nccl = f"{type(e).__name__}: {e}"
+                    self.backend = "nccl"
+        if self._hdl is None:
+            self._buf = torch.zeros(self.n_floats, dtype=torch.float32, device=self.device)
+        self.table = self._buf[:n].view(self.M, self.D)
+
+    def _setup_symmetric(self, blocks):
+        import torch.distributed._symmetric_memory as symm
+        lib = self._C.load_library()
+        self.blocks = int(blocks or os.environ.get("SVOXB_EXCHANGE_BLOCKS", 0) or lib.svoxb_exchange_max_blocks())
+        assert self.blocks * self.world * 4 + 4 <= self.FLAG_BYTES
+        total = self.n_floats + self.FLAG_BYTES // 4
+        with torch.cuda.device(self.device):
+            buf = symm.empty(total, dtype=torch.float32, device=self.device)
+            hdl = symm.rendezvous(buf, self.group)
+            buf.zero_()
+            torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)                                     # every rank's flags are zero before the first use
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)                # 0: the fabric offers no multicast mapping
+        if self.backend == "p2p":
+            mc = 0
+        elif self.backend == "nvls" and not mc:
+            raise RuntimeError("SVOXB_EXCHANGE=nvls but the symmetric allocation has no multicast mapping")
+        self.backend = "nvls" if mc else "p2p"
+        self._buf, self._hdl = buf, hdl
+        self._ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+        self._pg = self._C._CPeerGroup(
+            rank=self.rank, world=self.world, buffers=ctypes.cast(self._ptrs, ctypes.POINTER(ctypes.c_void_p)),
+            multicast=ctypes.c_void_p(mc), table_offset=0, flags_offset=self.n_floats * 4,
+            status_offset=self.n_floats * 4 + self.FLAG_BYTES - 4, blocks=self.blocks, epoch=1)
+
+    def zeroed_table(self):
+        """The [M, D] table, zero-filled in stream order (the reference's zeros_like(features), rt_kernel.cu:1415)."""
+        self.table.zero_()
+        return self.table
+
+    def all_reduce_(self):
+        """Sum the table over the ranks, in place, in stream order on the current stream. Collective."""
+        if self.world == 1:
+            return self.table
+        if self._hdl is None:
+            dist.all_reduce(self.table, op=dist.ReduceOp.SUM, group=self.group)
+            return self.table
+        with torch.cuda.device(self.device):
+            self._C._check(self._C.load_library().svoxb_exchange_sum(ctypes.byref(self._pg), self.n_floats,
+                                                                     self._C._stream()))
+        self._pg.epoch = (self._pg.epoch + 2) & 0xFFFFFFFF
+        return self.table
+
+    def status(self):
+        """0, or 1 + the rank a flag barrier gave up waiting for (synchronises)."""
+        if self._hdl is None:
+            return 0
+        word = self._buf[self.n_floats + self.FLAG_BYTES // 4 - 1:].view(torch.int32)
+        return int(word.item())
+
+    def describe(self):
+        d = {"backend": self.backend, "world": self.world, "bytes": self.n_floats * 4}
+        if self._hdl is not None:
+            d["blocks"] = self.blocks
+        if hasattr(self, "_why_nccl"):
+            d["fallback_reason"] = self._why_nccl[:200]
+        return d
 
 
 def barrier():

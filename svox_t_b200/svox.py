@@ -145,7 +145,7 @@ class N3Tree(nn.Module):
 
     def construct_tree(self, indices):
         """data[leaf(p_i)] = i: point i becomes the feature row of its leaf (svox.py:160-161)."""
-        _C.construct_tree(self._spec(self.features), indices)
+        _C.construct_tree(self._spec(self.features, _with_accel=False), indices)   # walks child/data (descend_ref)
         self._invalidate()
 
     def set(self, indices, values, cuda=True):
@@ -174,7 +174,7 @@ class N3Tree(nn.Module):
         if not cuda or not self.data.is_cuda:
             raise RuntimeError("svox_t_b200 has no CPU query path: the tree and the points must be on a CUDA device")
         result, node_ids, data_ids, leaf_node = _QueryVerticalFunction.apply(
-            features, self._spec(features, world=world), indices)
+            features, self._spec(features, world=world, _with_accel=False), indices)   # the point query walks child/data
         ret = [result, node_ids] if want_node_ids else result
         if want_data_ids:
             ret = ret if isinstance(ret, list) else [ret]
@@ -188,14 +188,19 @@ class N3Tree(nn.Module):
         """Split the selected leaves (all leaves below depth_limit by default); svox.py:488-560.
 
         ``sel``: tuple of 4 index tensors (node, i, j, k) of unique leaves, ``leaf_node``: the same as [n,4].
-        Returns True iff capacity grew. Unlike the reference (Appendix B5) ``repeats > 1`` works.
+        Returns True iff capacity grew. Unlike the reference (Appendix B5) ``repeats > 1`` works: without a selection
+        every pass splits every leaf below depth_limit; with one, later passes split the children the previous pass
+        created (all N^3 slots of the new nodes).
         """
         if self._lock_tree_structure:
             raise RuntimeError("Tree locked")
         resized = False
+        explicit = sel is not None or leaf_node is not None
         with torch.no_grad():
             for repeat_id in range(repeats):
                 filled = self.filled
+                if sel is None and leaf_node is not None:
+                    sel = (*leaf_node.T,)
                 if sel is None:
                     leaves = self._all_leaves().to(self.data.device)
                     depths = self.parent_depth[leaves[:, 0], 1]
@@ -222,7 +227,20 @@ class N3Tree(nn.Module):
                 self._n_internal += num_nc
                 self.filled += num_nc
                 self._invalidate()
-                sel = leaf_node = node_id = None        # further repeats refine every (new) leaf
+                if repeat_id + 1 < repeats:
+                    if explicit:
+                        # further repeats split the children just created (nodes [filled, new_filled)), as the
+                        # reference infers its selector (svox.py:540-550), not every leaf of the tree
+                        N = self.N
+                        kids = torch.arange(filled, new_filled, device=self.data.device, dtype=torch.int64)
+                        kids = kids[self.parent_depth[kids, 1] < self.depth_limit]
+                        grid = torch.stack(torch.meshgrid(*(torch.arange(N, device=self.data.device),) * 3,
+                                                          indexing="ij"), dim=-1).reshape(-1, 3)
+                        leaf_node = torch.cat((kids.repeat_interleave(N ** 3)[:, None], grid.repeat(kids.shape[0], 1)), dim=1)
+                        sel = (*leaf_node.T,)
+                    else:
+                        sel = leaf_node = None          # whole-tree refinement: every leaf again
+                    node_id = None
         return resized
 
     # ---- bookkeeping -----------------------------------------------------------------------------------------
