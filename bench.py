@@ -5,18 +5,28 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W
 
-Workload (config C3 of BASELINE.json, the configuration the metric is quoted on): depth-8 ball octree
-(1 897 408 leaf rows x 32 channels), 2^20 random rays PER GPU, one step = forward feature render + backward into
-the leaf feature table (+ NCCL all-reduce of the leaf gradients when N > 1). Weak scaling: rays shard across
-ranks with a fixed per-GPU batch, tree and features replicated, the only exchange is the gradient sum.
+Workload = config C3 of BASELINE.json AS WRITTEN: ONE training step over ONE global batch of 2^20 random rays through
+the depth-8 ball octree (1 897 408 leaf rows x 32 channels): forward feature render + backward into the leaf feature
+table. With N GPUs the batch is split into N contiguous slices (`dist.shard_range`), tree and features are replicated,
+and the step ends with the sum of the leaf-gradient tables over the GPUs -- STRONG scaling: total work is fixed, so
+`value` at N GPUs against `value` at 1 GPU is the speed-up of that one step. (The weak-scaling number of round 1,
+2^20 rays PER GPU, is kept under `extras.weak_scaling`.)
+
+A step on every rank: per-row activation pass + hit marks (the features change every training step) -> forward march
+-> zero-fill of the gradient table -> backward march -> exchange (svox_t_b200.dist.LeafGradExchange: one hand-written
+kernel over symmetric memory, NVSwitch multicast reduction; NCCL all-reduce only as the fallback).
 
 One JSON line on stdout (rank 0). `value` = whole-job Mrays/s with inputs resident in HBM; `e2e` = the same step
-through the public API (VolumeRenderer + autograd) with rays and targets coming from pinned host memory and the
-loss read back every step; `roofline` = the dominant kernel (backward march) against the measured HBM peak;
-`cpu_baseline` = the CPU oracle (a port of the reference's CUDA algorithm; the reference has no working CPU path)
-timed on this box's cores on a bounded ray sample. `--impl reference` times that CPU port as its own arm.
+through the public API (VolumeRenderer + autograd) with each rank's rays and targets coming from pinned host memory and
+the loss read back every step; `roofline` = the dominant kernel (backward march) against the measured HBM peak with
+SURVEY 8(d)'s algorithmic bytes, `roofline_design` = the same with the bytes THIS design moves (no per-level child
+lookups, dead rows never fetched); `cpu_baseline` = the CPU oracle (a port of the reference's CUDA algorithm; the
+reference has no working CPU path) on this box's cores on a bounded ray sample; `dist_parity_rel_l2` (N > 1) = the
+sharded + exchanged gradient of a 65 536-ray sample against the same sample rendered by rank 0 alone (the run FAILS
+above 1e-5). `--impl reference` times the CPU port as its own arm, with the same `config`.
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -39,10 +49,12 @@ def emit(obj):
 import numpy as np  # noqa: E402
 
 L_TREE, SHAPE, D_FEAT = 8, "ball", 32
-Q_PER_GPU = 1 << 20
+Q_GLOBAL = 1 << 20
 CPU_SAMPLE = 32768          # rays per CPU-baseline measurement / per reference-arm step
-WORKLOAD = ("C3 training step: depth-8 ball octree (1897408 leaf rows x 32 ch, 281697 nodes), 2^20 random rays per "
-            "GPU, fwd feature render + bwd into leaf features")
+PARITY_SAMPLE = 65536       # rays of the N > 1 gradient parity check
+WORKLOAD = ("C3 training step: depth-8 ball octree (1897408 leaf rows x 32 ch, 281697 nodes), ONE global batch of 2^20 "
+            "random rays split over the GPUs, fwd feature render + bwd into leaf features + leaf-gradient sum")
+METRIC = "Mrays/s fwd+bwd feature render"
 
 
 def log(*a):
@@ -59,13 +71,36 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def algorithmic_bytes(cnt, D, M, explicit_rays=True, depth=False):
+def bench_config(world, tr):
+    """The `config` object: identical in the native and the reference arm for the same N."""
+    return {"workload": WORKLOAD, "global_rays": Q_GLOBAL, "rays_per_gpu": Q_GLOBAL // world, "D": D_FEAT,
+            "leaf_rows": int(tr["M"]), "nodes": int(tr["n_nodes"]),
+            "options": "step_size=1e-3, background=1, sigma_thresh=stop_thresh=0",
+            "parallelism": f"one global ray batch split x{world} (contiguous slices), tree+features replicated, "
+                           "sum of grad[M,D] over the GPUs",
+            "l2": "inputs larger than L2: features 243 MB + activated table 243 MB + grad 243 MB vs 126 MB of L2"}
+
+
+def algorithmic_bytes(cnt, D, M, explicit_rays=True, depth=False, zero_fill=True):
     """bytes per launch from the oracle's counters (S samples, LV child lookups, V valid rows, H hits)."""
     Q, S, LV, V, H = cnt["Q"], cnt["S"], cnt["LV"], cnt["V"], cnt["H"]
     r_in = 36 if explicit_rays else 0
     d_out = 4 * D + (4 if depth else 0)
     b_fwd = Q * (r_in + d_out) + 4 * LV + 4 * S + 4 * V + 4 * (D - 1) * H
-    b_bwd = Q * (r_in + 8 * D) + 4 * LV + 4 * S + 4 * V + 4 * (D - 1) * H + 4 * D * H + 4 * M * D
+    b_bwd = Q * (r_in + 8 * D) + 4 * LV + 4 * S + 4 * V + 4 * (D - 1) * H + 4 * D * H + (4 * M * D if zero_fill else 0)
+    return b_fwd, b_bwd
+
+
+def design_bytes(cnt, D, M, stages, explicit_rays=True, depth=False, zero_fill=True):
+    """Bytes THIS design moves per launch: the reference's per-level child lookups (4 LV) and data-slot reads (4 S) become
+    at most one brick word per sample and stage below the shared-memory top grid; a hit's row arrives whole (sigma
+    included, 4 D H) and rows whose sigma <= 0 are never fetched (the hit marks), so the 4 V sigma probes go too."""
+    Q, S, H = cnt["Q"], cnt["S"], cnt["H"]
+    r_in = 36 if explicit_rays else 0
+    d_out = 4 * D + (4 if depth else 0)
+    look = 4 * S * max(stages - 1, 0)
+    b_fwd = Q * (r_in + d_out) + look + 4 * D * H
+    b_bwd = Q * (r_in + 8 * D) + look + 4 * D * H + 4 * D * H + (4 * M * D if zero_fill else 0)
     return b_fwd, b_bwd
 
 
@@ -79,7 +114,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50", "-i", uuid],
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20", "-i", uuid],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -90,15 +125,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def stop(self, t0, t1):
+    def stop(self, windows):
+        """windows: [(t0, t1), ...] wall-clock intervals of the timed regions."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, line in self.rows:
-            if ts < t0 - 0.05 or ts > t1 + 0.05:
+            if not any(t0 - 0.03 <= ts <= t1 + 0.03 for t0, t1 in windows):
                 continue
             f = [x.strip() for x in line.split(",")]
             try:
@@ -112,19 +148,24 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def scene_numpy(seed_rays):
+def scene_numpy():
+    """The C3 scene on the host: tree, features (seed 0) and the GLOBAL ray batch (seed 1), identical on every rank."""
     from svox_t_b200 import synth
     tr = synth.synth_tree(L_TREE, SHAPE)
     f = synth.synth_features(tr["M"], D_FEAT, seed=0)
-    o, d = synth.synth_rays(Q_PER_GPU, seed=seed_rays)
+    o, d = synth.synth_rays(Q_GLOBAL, seed=1)
     return tr, f, o, d
 
 
-def host_threads():
-    """The CPU legs use every host core; torchrun injects OMP_NUM_THREADS=1, which would silently serialise them."""
-    n = os.cpu_count() or 1
+def host_threads(orc):
+    """The CPU legs use every host core this process may run on. torchrun exports OMP_NUM_THREADS=1 and the OpenMP
+    runtime has read it long before this point, so the thread count is set through the runtime itself."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
     os.environ["OMP_NUM_THREADS"] = str(n)
-    return n
+    return int(orc.set_threads(n))
 
 
 def cpu_port_step(T, f, o, d, g, orc):
@@ -137,34 +178,47 @@ def cpu_port_step(T, f, o, d, g, orc):
 
 def run_reference_arm(args):
     """The reference's algorithm on the host cores (CPU port = the oracle; the reference itself has no runnable CPU
-    path and its CUDA extension is not a CPU baseline). Rank 0 only."""
+    path and its CUDA extension is not a CPU baseline). Rank 0 only; the other ranks exit without work."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    cores = host_threads()
     from oracle import oracle as orc
-    tr, f, o, d = scene_numpy(1)
+    cores = host_threads(orc)
+    tr, f, o, d = scene_numpy()
     T = orc.Tree(tr["child"], tr["data"])
     rng = np.random.default_rng(5)
     n = CPU_SAMPLE
     times = []
     for s in range(args.warmup + args.steps):
-        lo = (s * n) % (Q_PER_GPU - n)
+        lo = (s * n) % (Q_GLOBAL - n)
         g = rng.standard_normal((n, D_FEAT)).astype(np.float32)
         dt, _ = cpu_port_step(T, f, o[lo:lo + n], d[lo:lo + n], g, orc)
         if s >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     val = n / (ms * 1e-3) / 1e6
-    sample = f"each step = fwd+bwd of a {n}-ray slice of the 2^20-ray batch (C oracle, OpenMP over rays)"
+    sample = (f"each step = fwd+bwd of a {n}-ray slice of the 2^20-ray batch (C oracle, OpenMP over rays, {cores} threads); "
+              "Mrays/s is per ray, so the slice rate is the batch rate")
     emit({
-        "impl": "reference", "metric": "Mrays/s fwd+bwd feature render", "value": val, "unit": "Mrays/s",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_step": n},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": bench_config(args.gpus, tr),
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
+
+
+def latest_traffic():
+    """DRAM bytes per launch of the march kernels from the newest committed ncu capture (profiles/rNN_traffic.json,
+    written by tests/tools/ncu_traffic.py from an `ncu --set full` report of this same command)."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_traffic.json")))
+    if not files:
+        return {}, None
+    try:
+        return json.load(open(files[-1])), os.path.relpath(files[-1], ROOT)
+    except Exception:
+        return {}, None
 
 
 def main():
@@ -173,7 +227,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--skip-extras", action="store_true", help="skip the C2 image / reference-CUDA side measurements")
+    ap.add_argument("--skip-extras", action="store_true", help="skip the side measurements (C2 / C4 / C5, reference CUDA)")
+    ap.add_argument("--skip-c5", action="store_true", help="skip the depth-10 / 64-channel scene of the extras (8.4 GB)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else max(args.warmup, 1)
     if args.impl == "reference":
@@ -187,44 +242,80 @@ def main():
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    C.load_library()
+    lib = C.load_library()
 
-    tr, f, o, d = scene_numpy(1 + rank)
-    Q, D, M = Q_PER_GPU, D_FEAT, tr["M"]
+    tr, f, o, d = scene_numpy()
+    D, M = D_FEAT, tr["M"]
+    lo, hi = svd.shard_range(Q_GLOBAL, rank, world)          # this rank's contiguous slice of the global batch
+    Q = hi - lo
     tree = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=D, map_location=dev)
     feats = torch.from_numpy(f).to(dev)
-    o_t, d_t = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
-    g_t = torch.randn(Q, D, device=dev, generator=torch.Generator(device=dev).manual_seed(5 + rank))
+    o_t, d_t = torch.from_numpy(o[lo:hi]).to(dev), torch.from_numpy(d[lo:hi]).to(dev)
+    g_all = torch.randn(Q_GLOBAL, D, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    g_t = g_all[lo:hi].contiguous()                          # the same global grad_out on every rank, sliced
     renderer = sv.VolumeRenderer(tree)
     opt = renderer._get_options()
     ts = tree._spec(feats)
-    rs = sv.renderer._rays_spec_from_rays(sv.Rays(o_t, d_t, d_t))
     accel = tree.accel(feats)
-
+    xchg = svd.LeafGradExchange(M, D, dev)                   # symmetric-memory gradient table + exchange kernel
+    bopt = opt._c(sigma_thresh=0.0, stop_thresh=-1.0)
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
-    def step(rec=None):
-        e = [ev() for _ in range(4)] if rec is not None else None
-        if e: e[0].record()
+    def refresh_tables():
         # features change every training step: the per-row activation pass and the refresh of the accelerator's
         # hit marks (both derived from the features) are part of the step
         ts._act = C.Activated(feats)
         if accel is not None:
             accel._marks_key = None
             accel.mark_hits(feats)
+
+    def fwd_bwd(o_s, d_s, g_s, grad, e=None):
+        rs = sv.renderer._rays_spec_from_rays(sv.Rays(o_s, d_s, d_s))
         out = C.volume_render(ts, rs, opt)
-        if e: e[1].record()
-        grad = torch.zeros_like(feats)
         if e: e[2].record()
-        C._check(C.load_library().svoxb_render_rays_bwd(
-            C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), C._ptr(d_t), Q,
-            C.ctypes.byref(opt._c(sigma_thresh=0.0, stop_thresh=-1.0)),
-            C._ptr(g_t), C._ptr(out), C._ptr(grad), C._stream()))
+        grad.zero_()
+        C._check(lib.svoxb_render_rays_bwd_cost(C.ctypes.byref(ts._c()), C._ptr(o_s), C._ptr(d_s), C._ptr(d_s), o_s.shape[0],
+                                                C.ctypes.byref(bopt), C._ptr(g_s), C._ptr(out), C._ptr(grad),
+                                                C._ptr(rs._cost), C._stream()))   # rs._cost: short batches, else None
+        return out
+
+    def step(rec=None):
+        e = [ev() for _ in range(5)] if rec is not None else None
+        if e: e[0].record()
+        refresh_tables()
+        if e: e[1].record()
+        out = fwd_bwd(o_t, d_t, g_t, xchg.table, e)
         if e: e[3].record()
-        svd.all_reduce_leaf_grads(grad)
+        xchg.all_reduce_()
+        if e: e[4].record()
         if rec is not None:
             rec.append(e)
-        return out, grad
+        return out
+
+    # ---- N > 1: the sharded + exchanged gradient equals the single-GPU gradient ---------------------------------------
+    dist_parity = None
+    if world > 1:
+        n = PARITY_SAMPLE
+        plo, phi = svd.shard_range(n, rank, world)
+        o_p, d_p = torch.from_numpy(o[:n]).to(dev), torch.from_numpy(d[:n]).to(dev)
+        g_p = g_all[:n].contiguous()
+        refresh_tables()
+        fwd_bwd(o_p[plo:phi].contiguous(), d_p[plo:phi].contiguous(), g_p[plo:phi].contiguous(), xchg.table)
+        xchg.all_reduce_()
+        rel = torch.zeros(1, device=dev, dtype=torch.float64)
+        if rank == 0:
+            alone = torch.empty_like(feats)
+            fwd_bwd(o_p, d_p, g_p, alone)
+            rel[0] = (xchg.table.double() - alone.double()).norm() / alone.double().norm()
+            del alone
+        torch.distributed.broadcast(rel, 0)
+        dist_parity = float(rel.item())
+        assert xchg.status() == 0, "exchange kernel: a flag barrier timed out"
+        if not dist_parity < 1e-5:
+            log(f"FAIL: sharded gradient differs from the single-GPU gradient: rel L2 {dist_parity:.3e}")
+            sys.exit(3)
+        del o_p, d_p, g_p
+    del g_all
 
     for _ in range(args.warmup):
         step()
@@ -247,23 +338,24 @@ def main():
     launches = C.launch_count() - launches0
     total_ms = svd.max_over_ranks(e0.elapsed_time(e1), dev)
     ms_per_step = total_ms / args.steps
-    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in rec]))       # includes the activation pass
-    bwd_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in rec]))
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    value = world * Q / (ms_per_step * 1e-3) / 1e6
+    stage = lambda i, j: float(np.mean([e[i].elapsed_time(e[j]) for e in rec]))
+    tables_ms, fwd_ms, bwd_ms, xchg_ms = stage(0, 1), stage(1, 2), stage(2, 3), stage(3, 4)
+    value = Q_GLOBAL / (ms_per_step * 1e-3) / 1e6
 
     # ---- end to end through the public API: pinned host rays + targets in, loss out, every step ----------------------
     # Data-loader style pipeline: two device buffer sets; while step k renders out of one, a copy stream uploads the
     # inputs of step k+1 into the other. Every step's host->device copy and loss read-back happen inside the timed
     # region (K uploads + K renders + K read-backs for K steps; the first upload is exposed, the rest overlap).
-    # Per-step host inputs: ray origins + directions (what VolumeRenderer.forward takes) and the supervision a
-    # training step consumes -- an RGB target and an opacity target per ray, as in image-supervised training, where
-    # the 31 rendered feature channels pass through a fixed decoder (mean of three channel groups) before the loss.
-    h_o, h_d = torch.from_numpy(o).pin_memory(), torch.from_numpy(d).pin_memory()
+    # Per-step host inputs of a rank: its slice of the ray origins + directions (what VolumeRenderer.forward takes) and
+    # of the supervision a training step consumes -- an RGB target and an opacity target per ray, as in image-supervised
+    # training, where the 31 rendered feature channels pass through a fixed decoder (mean of three channel groups)
+    # before the loss. The gradient lands in the exchange's symmetric table and is summed over the GPUs inside backward().
+    h_o, h_d = torch.from_numpy(o[lo:hi].copy()).pin_memory(), torch.from_numpy(d[lo:hi].copy()).pin_memory()
     gen = torch.Generator().manual_seed(7 + rank)
     h_rgb = torch.rand(Q, 3, generator=gen).pin_memory()
     h_alpha = torch.rand(Q, generator=gen).pin_memory()
     fparam = feats.clone().requires_grad_(True)
+    renderer.leaf_grad_exchange = xchg
     bufs = [(torch.empty(Q, 3, device=dev), torch.empty(Q, 3, device=dev), torch.empty(Q, 3, device=dev),
              torch.empty(Q, device=dev)) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
@@ -297,9 +389,9 @@ def main():
                 fparam.add_(0.0)                       # stands in for the optimiser update: features change every step
             out = renderer(fparam, sv.Rays(bo, bd, bd))
             dec = out @ w_dec                          # [Q, 4]: decoded RGB + opacity
-            loss = 0.5 * ((dec[:, :3] - brgb) ** 2).mean() + 0.5 * ((dec[:, 3] - ba) ** 2).mean()
-            loss.backward()
-            svd.all_reduce_leaf_grads(fparam.grad)
+            # this rank's share of the global mean-squared error (sum over its rays / global ray count)
+            loss = (0.5 / (3 * Q_GLOBAL)) * ((dec[:, :3] - brgb) ** 2).sum() + (0.5 / Q_GLOBAL) * ((dec[:, 3] - ba) ** 2).sum()
+            loss.backward()                            # leaf gradients summed over the GPUs inside (leaf_grad_exchange)
             free_ev[k & 1] = torch.cuda.Event(); free_ev[k & 1].record(main_stream)
             losses.append(float(loss.item()))          # device -> host read of the step's result
             ready = nxt
@@ -307,79 +399,136 @@ def main():
 
     e2e_run(3)
     svd.barrier(); torch.cuda.synchronize()
+    t_wall2 = time.time()
     e0, e1 = ev(), ev()
     e0.record()
     e2e_run(args.steps)
     e1.record()
     torch.cuda.synchronize(); svd.barrier()
+    t_wall3 = time.time()
     e2e_ms = svd.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
-    e2e = {"value": world * Q / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(h_o.numel() + h_d.numel() + h_rgb.numel() + h_alpha.numel()) * 4,
-           "d2h_bytes_per_step": 4,
-           "api": "VolumeRenderer.forward + autograd backward; loss = MSE(decoded RGB, rgb target) + MSE(opacity, alpha "
-                  "target), RGB / opacity = a fixed linear decoder (out @ W[32,4]: means of three groups of the rendered feature channels, opacity passed through). Every step uploads its ray "
-                  "origins, directions, RGB and opacity targets from pinned host memory and reads the loss back; the "
-                  "upload of step k+1 overlaps the render of step k (double buffering)"}
+    clocks = sampler.stop([(t_wall0, t_wall1), (t_wall2, t_wall3)]) if sampler else None
+    grad_aliases = bool(fparam.grad is not None and fparam.grad.data_ptr() == xchg.table.data_ptr())
+    h2d_rank = int(h_o.numel() + h_d.numel() + h_rgb.numel() + h_alpha.numel()) * 4
+    e2e = {"value": Q_GLOBAL / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(svd.sum_over_ranks(h2d_rank, dev)), "d2h_bytes_per_step": 4 * world,
+           "grad_is_exchange_table": grad_aliases,
+           "api": "VolumeRenderer.forward + autograd backward (leaf gradients summed over the GPUs inside backward()); "
+                  "loss = this rank's share of MSE(decoded RGB, rgb target) + MSE(opacity, alpha target), RGB / opacity = a "
+                  "fixed linear decoder (out @ W[32,4]). Every step every rank uploads its slice of the ray origins, "
+                  "directions, RGB and opacity targets from pinned host memory and reads its loss back; the upload of "
+                  "step k+1 overlaps the render of step k (double buffering). Bytes are summed over the ranks"}
+    renderer.leaf_grad_exchange = None
 
+    # ---- N > 1: round 1's weak-scaling workload (2^20 rays PER GPU), a short run for continuity ------------------------
+    weak = None
+    if world > 1 and not args.skip_extras:
+        del bufs, fparam
+        o_w, d_w = synth.synth_rays(Q_GLOBAL, seed=1 + rank)
+        o_w, d_w = torch.from_numpy(o_w).to(dev), torch.from_numpy(d_w).to(dev)
+        g_w = torch.randn(Q_GLOBAL, D, device=dev, generator=torch.Generator(device=dev).manual_seed(50 + rank))
+
+        def weak_step():
+            refresh_tables()
+            fwd_bwd(o_w, d_w, g_w, xchg.table)
+            xchg.all_reduce_()
+        for _ in range(3):
+            weak_step()
+        svd.barrier(); torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(5):
+            weak_step()
+        e1.record()
+        torch.cuda.synchronize(); svd.barrier()
+        wms = svd.max_over_ranks(e0.elapsed_time(e1), dev) / 5
+        weak = {"scaling": "weak", "rays_per_gpu": Q_GLOBAL, "global_rays": world * Q_GLOBAL, "ms_per_step": wms,
+                "value": world * Q_GLOBAL / (wms * 1e-3) / 1e6, "unit": "Mrays/s", "steps": 5}
+        del o_w, d_w, g_w
+    status = xchg.status()
+    xchg_desc = xchg.describe()
     if world > 1:
         import torch.distributed as tdist
         svd.barrier()
         tdist.destroy_process_group()
     if rank != 0:
         return
+    assert status == 0, "exchange kernel: a flag barrier timed out"
     # ---- CPU baseline + counters (rank 0, bounded sample) ---------------------------------------------------------------
-    cores = host_threads()
     from oracle import oracle as orc
+    cores = host_threads(orc)
     T = orc.Tree(tr["child"], tr["data"])
     n = CPU_SAMPLE
     g_np = np.random.default_rng(5).standard_normal((n, D)).astype(np.float32)
     cpu_s, cnt = cpu_port_step(T, f, o[:n], d[:n], g_np, orc)
     cpu_baseline = {"value": n / cpu_s / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                     "sample": f"first {n} of the 2^20 rays, fwd+bwd once, C oracle with OpenMP over rays ({cpu_s:.2f} s)"}
-    scale = Q / cnt["Q"]
-    cnt_full = {k: (v * scale if k != "Q" else Q) for k, v in cnt.items()}
-    b_fwd, b_bwd = algorithmic_bytes(cnt_full, D, M)
+    scale = Q / cnt["Q"]                               # one launch on this rank marches its Q-ray slice
+    cnt_rank = {k: (v * scale if k != "Q" else Q) for k, v in cnt.items()}
+    b_fwd, b_bwd = algorithmic_bytes(cnt_rank, D, M)
+    stages = accel.describe()["stages"] if accel is not None else 1
+    bd_fwd, bd_bwd = design_bytes(cnt_rank, D, M, stages)
     peak, peak_src = measured_peaks()
-    traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp))
-    roof = lambda b, ms, key: {"bound": "hbm", "achieved": b / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                               "frac": b / (ms * 1e-3) / 1e9 / peak, "traffic": traffic.get(key),
-                               "kernel": key, "ms_per_launch": ms, "algorithmic_bytes_per_launch": b,
-                               "peak_source": peak_src}
+    traffic, traffic_src = latest_traffic()
+    if world > 1:
+        traffic = {}                                   # the capture is of the N = 1 launch (2^20 rays)
+
+    def roof(b, ms, kernel, tkey=None):
+        return {"bound": "hbm", "achieved": b / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": b / (ms * 1e-3) / 1e9 / peak, "traffic": traffic.get(tkey) if tkey else None,
+                "traffic_source": traffic_src if tkey and traffic.get(tkey) else None,
+                "kernel": kernel, "ms_per_launch": ms, "algorithmic_bytes_per_launch": b, "rays_per_launch": Q,
+                "peak_source": peak_src}
+
     out = {
-        "metric": "Mrays/s fwd+bwd feature render", "value": value, "unit": "Mrays/s", "n_gpus": world,
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_gpu": Q, "global_rays": world * Q, "D": D, "leaf_rows": M,
-                   "nodes": tr["n_nodes"], "options": "step_size=1e-3, background=1, sigma_thresh=stop_thresh=0",
-                   "parallelism": f"ray-sharded x{world}, tree+features replicated, NCCL all-reduce of grad[M,D]",
-                   "l2": "inputs larger than L2: features 243 MB + grad 243 MB + out 134 MB + rays 25 MB vs 126 MB",
-                   "accelerator": accel.describe() if accel is not None else None},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": bench_config(world, tr),
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": roof(b_bwd, bwd_ms, "march_bwd_kernel"),
-        "roofline_fwd": roof(b_fwd, fwd_ms, "march_fwd_kernel"),
+        "roofline": roof(b_bwd, bwd_ms, "svoxb::march_bwd_quad_kernel (+ the zero-fill of grad[M,D], inside the timed window)",
+                         "march_bwd_quad_kernel"),
+        "roofline_fwd": roof(b_fwd, fwd_ms, "svoxb::march_fwd_quad_kernel", "march_fwd_quad_kernel"),
+        "roofline_design": {"bwd": roof(bd_bwd, bwd_ms, "svoxb::march_bwd_quad_kernel"),
+                            "fwd": roof(bd_fwd, fwd_ms, "svoxb::march_fwd_quad_kernel"),
+                            "note": "same times, bytes of this design: <= 1 brick word per sample and stage instead of "
+                                    "the reference's per-level child lookups + data-slot read; hit rows only (sigma "
+                                    "arrives with the row; rows with sigma <= 0 are never fetched)"},
         "roofline_step": {"achieved": (b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": (b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9 / peak,
-                          "bytes_per_ray": (b_fwd + b_bwd) / Q},
+                          "bytes_per_ray": (b_fwd + b_bwd) / Q,
+                          "note": "rank 0's march bytes over the whole step time (tables + exchange included)"},
+        "stage_ms": {"activation_and_marks": tables_ms, "fwd": fwd_ms, "zero_fill_and_bwd": bwd_ms, "exchange": xchg_ms,
+                     "note": "rank 0, CUDA events on the launch stream, mean over the timed steps; the exchange includes "
+                             "the wait for the slowest rank's backward"},
         "kernel_ms": {"fwd": fwd_ms, "bwd": bwd_ms},
-        "fwd_only": {"value": world * Q / (fwd_ms * 1e-3) / 1e6, "unit": "Mrays/s",
-                     "note": "forward feature render alone (BASELINE metric (i)), incl. the per-step activation + marking passes"},
+        "exchange": xchg_desc,
+        "design": {"accelerator": accel.describe() if accel is not None else None},
+        "fwd_only": {"value": Q_GLOBAL / ((tables_ms + fwd_ms) * 1e-3) / 1e6, "unit": "Mrays/s",
+                     "note": "forward feature render alone (BASELINE metric (i)), incl. the per-step activation + marking "
+                             "passes; rank 0's times, no exchange in the forward"},
         "counters_per_ray": {k: cnt[k] / cnt["Q"] for k in ("S", "LV", "V", "H")},
         "cpu_baseline": cpu_baseline,
     }
+    if dist_parity is not None:
+        out["dist_parity_rel_l2"] = dist_parity
+        out["dist_parity"] = {"rays": PARITY_SAMPLE, "tolerance": 1e-5,
+                              "what": "grad[M,D] of the sample rendered in N slices + exchanged vs rendered by rank 0 alone"}
+    if weak is not None:
+        out.setdefault("extras", {})["weak_scaling"] = weak
     if not args.skip_extras and world == 1:
-        out["extras"] = extras(sv, C, synth, tree, feats, renderer, opt, ts, rs, o_t, d_t, g_t, dev, peak)
+        out["extras"] = extras(args, sv, C, synth, orc, tree, feats, renderer, opt, ts, o_t, d_t, g_t, dev, peak, f, tr, T)
     emit(out)
 
 
-def extras(sv, C, synth, tree, feats, renderer, opt, ts, rs, o_t, d_t, g_t, dev, peak):
-    """Side measurements (N = 1): config C2 image render, and the reference's own CUDA kernels on the same inputs."""
+def extras(args, sv, C, synth, orc, tree, feats, renderer, opt, ts, o_t, d_t, g_t, dev, peak, f_np, tr, T):
+    """Side measurements (N = 1): the other BASELINE configs with their own rooflines, and the reference's own CUDA
+    kernels on the same inputs (timed AND compared)."""
     import torch
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    rs = sv.renderer._rays_spec_from_rays(sv.Rays(o_t, d_t, d_t))
 
     def best(fn, warm=2, it=5):
         for _ in range(warm):
@@ -391,11 +540,33 @@ def extras(sv, C, synth, tree, feats, renderer, opt, ts, rs, o_t, d_t, g_t, dev,
             ts_.append(a.elapsed_time(b))
         return float(np.median(ts_))
 
+    def image_roofline(T_, f_, c2w, W, H, fx, D, M, stages, ms, every=8):
+        """Roofline of an image render from the oracle's counters on a pixel subsample (every `every`-th row/column)."""
+        oo, dd = orc.camera_rays(c2w, fx, fx, W, H)
+        sel = (np.arange(0, H, every)[:, None] * W + np.arange(0, W, every)[None, :]).reshape(-1)
+        _, _, cnt = orc.render_rays(T_, f_, oo[sel], dd[sel], want_counters=True)
+        k = W * H / cnt["Q"]
+        full = {key: (v * k if key != "Q" else W * H) for key, v in cnt.items()}
+        b, _ = algorithmic_bytes(full, D, M, explicit_rays=False, depth=True)
+        bdz, _ = design_bytes(full, D, M, stages, explicit_rays=False, depth=True)
+        return {"bound": "hbm", "achieved": b / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": b / (ms * 1e-3) / 1e9 / peak, "frac_design_bytes": bdz / (ms * 1e-3) / 1e9 / peak,
+                "algorithmic_bytes_per_launch": b, "ms_per_launch": ms,
+                "counters_per_ray": {key: cnt[key] / cnt["Q"] for key in ("S", "LV", "V", "H")},
+                "sample": f"oracle counters on every {every}th pixel row/column ({cnt['Q']} rays), scaled to {W}x{H}"}
+
     ex = {}
-    cam = torch.from_numpy(synth.synth_cameras(1)[0]).to(dev)
-    cs = sv.renderer._make_camera_spec(cam, 800, 800, 1111.111, 1111.111)
-    ms = best(lambda: C.volume_render_image_with_depth(ts, cs, opt))
-    ex["c2_image_800x800_fwd_with_depth"] = {"ms": ms, "Mrays/s": 0.64 / (ms * 1e-3)}
+    stages = ts._accel.describe()["stages"] if ts._accel is not None else 1
+    M, D = feats.shape
+    cams = synth.synth_cameras(1)
+    cam = torch.from_numpy(cams[0]).to(dev)
+    try:   # config C2: 800x800 render_persp forward with feature + opacity + depth outputs
+        cs = sv.renderer._make_camera_spec(cam, 800, 800, 1111.111, 1111.111)
+        ms = best(lambda: C.volume_render_image_with_depth(ts, cs, opt))
+        ex["c2_image_800x800_fwd_with_depth"] = {"ms": ms, "Mrays/s": 0.64 / (ms * 1e-3),
+                                                 "roofline": image_roofline(T, f_np, cams[0], 800, 800, 1111.111, D, M, stages, ms)}
+    except Exception as e:
+        ex["c2_image_800x800_fwd_with_depth"] = {"unavailable": str(e)[:200]}
     try:   # secondary forward-only series of SURVEY 8d: fast=True thresholds (sigma_thresh = stop_thresh = 1e-2)
         fast = renderer._get_options(True)
         ms = best(lambda: C.volume_render(ts, rs, fast))
@@ -403,9 +574,32 @@ def extras(sv, C, synth, tree, feats, renderer, opt, ts, rs, o_t, d_t, g_t, dev,
                                         "sigma_thresh": fast.sigma_thresh, "stop_thresh": fast.stop_thresh}
     except Exception as e:
         ex["c3_fwd_fast_thresholds"] = {"unavailable": str(e)[:200]}
+    try:   # the reference's own CUDA kernels (oracle/_ref, unmodified svox_t csrc for sm_100a) on the SAME full-size inputs
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import refdrv
+        if refdrv.available():
+            m = refdrv.module()
+            rts = refdrv.tree_spec(feats, tree.child, tree.data, tree.parent_depth, tree.offset, tree.invradius, tree.filled)
+            rrs, ro = refdrv.rays_spec(o_t, d_t), refdrv.options()
+            f_ms = best(lambda: m.volume_render(rts, rrs, ro), 1, 3)
+            b_ms = best(lambda: m.volume_render_backward(rts, rrs, ro, g_t), 1, 3)
+            ref_out = m.volume_render(rts, rrs, ro)
+            ref_grad = m.volume_render_backward(rts, rrs, ro, g_t)
+            mine_out = C.volume_render(ts, rs, opt)
+            mine_grad = C.volume_render_backward(ts, rs, opt, g_t, saved_out=mine_out)
+            err = (mine_out - ref_out).abs()
+            ex["reference_cuda_same_inputs"] = {
+                "fwd_ms": f_ms, "bwd_ms": b_ms, "Mrays/s_fwd_bwd": o_t.shape[0] / ((f_ms + b_ms) * 1e-3) / 1e6,
+                "parity": {"fwd_max_abs_err": float(err.max()),
+                           "fwd_frac_outside_1e-4+1e-3rel": float((err > 1e-4 + 1e-3 * ref_out.abs()).float().mean()),
+                           "grad_rel_l2": float((mine_grad - ref_grad).norm() / ref_grad.norm())},
+                "note": "unmodified svox_t csrc compiled for sm_100a (oracle/_ref); parity = this library against it on "
+                        "the full 2^20-ray batch"}
+            del ref_out, ref_grad, mine_out, mine_grad, err
+    except Exception as e:  # the checker is optional here
+        ex["reference_cuda_same_inputs"] = {"unavailable": str(e)[:200]}
     try:   # motion-feature render on the same tree and rays: J = 24 joints, F = 32, B = 4
         rng = np.random.default_rng(0)
-        M = feats.shape[0]
         jf = torch.randn(24, 32, device=dev, requires_grad=True)
         sw = torch.from_numpy(rng.dirichlet(np.ones(4), M).astype(np.float32)).to(dev)
         ji = torch.from_numpy(rng.integers(0, 24, (M, 4)).astype(np.int32)).to(dev)
@@ -421,39 +615,116 @@ def extras(sv, C, synth, tree, feats, renderer, opt, ts, rs, o_t, d_t, g_t, dev,
     except Exception as e:
         ex["motion_feature_render_J24_F32_B4"] = {"unavailable": str(e)[:200]}
     try:   # config C4: animated frame = LBS warp of 2^20 points + p2v splat (256^3) + octree rebuild to depth 8 + accelerator
-        P = 1 << 20   #            + 1920x1080 render with opacity and depth; per-frame latency, CUDA events around the frame
+        P = 1 << 20   #            + 1920x1080 render with opacity and depth; per-stage and per-frame latency
         vox = synth._occupied_keys(8, "ball")
         pts = synth.voxel_centers(vox[np.random.default_rng(2).permutation(len(vox))[:P]], 8)
         Tm, w4, j4 = synth.synth_skeleton(P)
         p_t, Tm_t, w_t, j_t = (torch.from_numpy(a).to(dev) for a in (pts, Tm, w4, j4))
-        f4 = torch.from_numpy(synth.synth_features(P, 32)).to(dev)
+        f4_np = synth.synth_features(P, 32)
+        f4 = torch.from_numpy(f4_np).to(dev)
         corner, size = torch.zeros(3, device=dev), torch.ones(3, device=dev)
         tree4 = sv.N3Tree(N=2, data_dim=32, map_location=dev)
         r4 = sv.VolumeRenderer(tree4)
+        names = ["warp_vertices", "p2v", "rebuild", "accelerator", "render_1080p"]
 
-        def frame():
+        def frame(rec=None):
+            e = [ev() for _ in range(6)]
+            e[0].record()
             warped, _ = sv.warp_vertices(Tm_t, p_t, w_t, j_t)
+            e[1].record()
             sv.voxelize(warped, f4, corner, size, 256, 1.5 / 256, 2.0 / 256)
+            e[2].record()
             tree4.build_from_points(warped, 8)
+            e[3].record()
+            tree4.accel(f4)
+            e[4].record()
             r4.render_persp_with_depth(f4, cam, width=1920, height=1080, fx=1500.0)
-        ex["c4_animated_frame_1080p"] = {"ms_per_frame": best(frame, 2, 5), "points": P, "nodes": int(tree4.filled)}
+            e[5].record()
+            if rec is not None:
+                torch.cuda.synchronize()
+                rec.append([e[i].elapsed_time(e[i + 1]) for i in range(5)] + [e[0].elapsed_time(e[5])])
+            return warped
+        for _ in range(3):
+            frame()
+        rec4 = []
+        for _ in range(7):
+            warped = frame(rec4)
+        med = np.median(np.array(rec4), axis=0)
+        c4 = {"ms_per_frame": float(med[5]), "stage_ms": {n_: float(med[i]) for i, n_ in enumerate(names)},
+              "points": P, "nodes": int(tree4.filled)}
+        T4 = orc.Tree(tree4.child.cpu().numpy(), tree4.data.cpu().numpy())
+        st4 = tree4.accel(f4).describe()["stages"]
+        c4["render_roofline"] = image_roofline(T4, f4_np, cams[0], 1920, 1080, 1500.0, 32, P, st4, float(med[4]), every=12)
+        ex["c4_animated_frame_1080p"] = c4
+        del p_t, w_t, j_t, f4, tree4, r4, warped
     except Exception as e:
         ex["c4_animated_frame_1080p"] = {"unavailable": str(e)[:200]}
-    try:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import refdrv
-        if refdrv.available():
-            m = refdrv.module()
-            rts = refdrv.tree_spec(feats, tree.child, tree.data, tree.parent_depth, tree.offset, tree.invradius, tree.filled)
-            rrs, ro = refdrv.rays_spec(o_t, d_t), refdrv.options()
-            f_ms = best(lambda: m.volume_render(rts, rrs, ro), 1, 3)
-            b_ms = best(lambda: m.volume_render_backward(rts, rrs, ro, g_t), 1, 3)
-            ex["reference_cuda_same_inputs"] = {"fwd_ms": f_ms, "bwd_ms": b_ms,
-                                                "Mrays/s_fwd_bwd": Q_PER_GPU / ((f_ms + b_ms) * 1e-3) / 1e6,
-                                                "note": "unmodified svox_t csrc compiled for sm_100a (oracle/_ref)"}
-    except Exception as e:  # the checker is optional here
-        ex["reference_cuda_same_inputs"] = {"unavailable": str(e)[:200]}
+    if not args.skip_c5:
+        try:
+            ex["c5_depth10_shell_D64"] = extras_c5(sv, C, synth, orc, dev, peak, best, image_roofline)
+        except Exception as e:
+            ex["c5_depth10_shell_D64"] = {"unavailable": str(e)[:300]}
     return ex
+
+
+def extras_c5(sv, C, synth, orc, dev, peak, best, image_roofline):
+    """Config C5's scene on one GPU: depth-10 shell octree (~32.9 M leaf rows x 64 channels = 8.4 GB of features, M*D > 2^31),
+    one 1920x1080 view with depth and a 2^20 random-ray fwd+bwd step, each with its roofline (oracle counters on samples)."""
+    import torch
+    L, D = 10, 64
+    t0 = time.time()
+    tr = synth.synth_tree(L, "shell")
+    M = tr["M"]
+    g = torch.Generator(device=dev).manual_seed(0)
+    feats = torch.randn(M, D, device=dev, generator=g)
+    feats[:, -1] = torch.rand(M, device=dev, generator=g) * 10 - 2
+    tree = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=D, map_location=dev)
+    r = sv.VolumeRenderer(tree)
+    opt = r._get_options()
+    ts = r._render_spec(feats, 1 << 21)                # activated table + hit marks, as VolumeRenderer attaches them
+    stages = ts._accel.describe()["stages"]
+    res = {"leaf_rows": int(M), "nodes": int(tr["n_nodes"]), "feature_bytes": int(M) * D * 4,
+           "accelerator": ts._accel.describe(), "host_scene_build_s": round(time.time() - t0, 1)}
+    T = orc.Tree(tr["child"], tr["data"])
+    f_np = feats.cpu().numpy()
+    cams = synth.synth_cameras(1)
+    cam = torch.from_numpy(cams[0]).to(dev)
+    cs = sv.renderer._make_camera_spec(cam, 1920, 1080, 1500.0, 1500.0)
+    ms = best(lambda: C.volume_render_image_with_depth(ts, cs, opt), 1, 3)
+    res["view_1080p_fwd_with_depth"] = {"ms": ms, "Mpixel/s": 2.0736 / (ms * 1e-3),
+                                        "roofline": image_roofline(T, f_np, cams[0], 1920, 1080, 1500.0, D, M, stages, ms, every=12)}
+    Q = 1 << 20
+    o, d = synth.synth_rays(Q)
+    o_t, d_t = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
+    rs = sv.renderer._rays_spec_from_rays(sv.Rays(o_t, d_t, d_t))
+    gout = torch.randn(Q, D, device=dev)
+    out = C.volume_render(ts, rs, opt)
+    f_ms = best(lambda: C.volume_render(ts, rs, opt), 1, 3)
+    grad = torch.zeros_like(feats)
+    lib, bopt = C.load_library(), opt._c(sigma_thresh=0.0, stop_thresh=-1.0)
+
+    def bwd():      # the march alone: the 8.4 GB zero-fill is a separate, trivially bandwidth-bound pass
+        C._check(lib.svoxb_render_rays_bwd(C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), C._ptr(d_t), Q,
+                                           C.ctypes.byref(bopt), C._ptr(gout), C._ptr(out), C._ptr(grad), C._stream()))
+    b_ms = best(bwd, 1, 3)
+    z_ms = best(lambda: grad.zero_(), 1, 3)
+    sel = np.arange(0, Q, Q // 4096)[:4096]
+    ref_o, _, cnt = orc.render_rays(T, f_np, o[sel], d[sel], want_counters=True)
+    err = np.abs(out.cpu().numpy()[sel] - ref_o)
+    k = Q / cnt["Q"]
+    full = {key: (v * k if key != "Q" else Q) for key, v in cnt.items()}
+    b_f, b_b = algorithmic_bytes(full, D, M, zero_fill=False)
+    d_f, d_b = design_bytes(full, D, M, stages, zero_fill=False)
+    rf = lambda b, t: {"bound": "hbm", "achieved": b / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                       "frac": b / (t * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": b, "ms_per_launch": t}
+    res["random_rays_2^20"] = {
+        "fwd_ms": f_ms, "bwd_ms": b_ms, "grad_zero_fill_ms": z_ms, "Mrays/s_fwd_bwd": Q / ((f_ms + b_ms) * 1e-3) / 1e6,
+        "roofline_fwd": rf(b_f, f_ms), "roofline_bwd": rf(b_b, b_ms), "roofline_fwd_bwd": rf(b_f + b_b, f_ms + b_ms),
+        "roofline_design_fwd_bwd": rf(d_f + d_b, f_ms + b_ms),
+        "counters_per_ray": {key: cnt[key] / cnt["Q"] for key in ("S", "LV", "V", "H")},
+        "oracle_sample": {"rays": int(cnt["Q"]), "fwd_max_abs_err": float(err.max()),
+                          "frac_outside_1e-4+1e-3rel": float((err > 1e-4 + 1e-3 * np.abs(ref_o)).mean())}}
+    return res
 
 
 if __name__ == "__main__":

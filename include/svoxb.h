@@ -204,6 +204,19 @@ SVOXB_API int svoxb_render_rays_bwd(const svoxb_tree* tree, const float* origins
                           int64_t Q, const svoxb_render_options* opt, const float* grad_out, const float* saved_out,
                           float* grad_features, void* stream);
 
+/* The same two calls for a forward/backward PAIR over one ray batch, sharing a scheduling hint (no reference
+ * counterpart). Short batches -- up to svoxb_ray_order_max_rays() rays, about three per resident lane -- are marched
+ * longest ray first (svoxb_order.cu): the forward orders by an estimate and writes ray_cost[Q] (int32: the march
+ * iterations of each ray where the kernel can count them, else the estimate); the backward orders by that array. Longer
+ * batches neither write nor read ray_cost. Results are those of the plain calls (only the lane a ray runs on changes). */
+SVOXB_API int64_t svoxb_ray_order_max_rays(void);
+SVOXB_API int svoxb_render_rays_fwd_cost(const svoxb_tree* tree, const float* origins, const float* dirs, const float* vdirs,
+                               int64_t Q, const svoxb_render_options* opt, float* out, float* depth, int32_t* ray_cost,
+                               void* stream);
+SVOXB_API int svoxb_render_rays_bwd_cost(const svoxb_tree* tree, const float* origins, const float* dirs, const float* vdirs,
+                               int64_t Q, const svoxb_render_options* opt, const float* grad_out, const float* saved_out,
+                               float* grad_features, const int32_t* ray_cost, void* stream);
+
 /* volume_render_image / _backward (rt_kernel.cu:1152-1166, 1193-1238, 1381-1452): pinhole camera rays generated
  * in-kernel; out[H, W, D], depth[H, W] (nullable). */
 SVOXB_API int svoxb_render_image_fwd(const svoxb_tree* tree, const svoxb_camera* cam, const svoxb_render_options* opt,

@@ -59,6 +59,11 @@ def lib():
     return _lib
 
 
+def set_threads(n):
+    """Use ``n`` OpenMP threads in the oracle's loops (returns the count in effect); see orc_set_threads."""
+    return int(lib().orc_set_threads(ctypes.c_int(int(n))))
+
+
 def _sfx(dtype):
     dtype = np.dtype(dtype)
     if dtype == np.float32:

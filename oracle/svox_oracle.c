@@ -68,3 +68,13 @@ int64_t orc_leafset(const int64_t* node_ids, int64_t Q, int N, int64_t* leaf_nod
 }
 
 int orc_abi_version(void) { return 1; }
+
+/* Thread count of the OpenMP loops over rays / points. Launchers such as torchrun export OMP_NUM_THREADS=1, which the
+ * runtime reads once at load time; bench.py's CPU legs set the count explicitly through this call instead. Returns
+ * the count now in effect. */
+#ifdef _OPENMP
+#include <omp.h>
+int orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
+#else
+int orc_set_threads(int n) { (void)n; return 1; }
+#endif

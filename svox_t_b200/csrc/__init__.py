@@ -86,6 +86,9 @@ SYMBOLS = {
     "svoxb_render_rays_fwd": (ctypes.c_int, [_PT, _VP, _VP, _VP, _I64, _PO, _VP, _VP, _VP]),
     "svoxb_out_data_dim": (ctypes.c_int, [_I32, _I32, _I32]),
     "svoxb_render_rays_bwd": (ctypes.c_int, [_PT, _VP, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _VP]),
+    "svoxb_ray_order_max_rays": (_I64, []),
+    "svoxb_render_rays_fwd_cost": (ctypes.c_int, [_PT, _VP, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _VP]),
+    "svoxb_render_rays_bwd_cost": (ctypes.c_int, [_PT, _VP, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _VP, _VP]),
     "svoxb_render_image_fwd": (ctypes.c_int, [_PT, _PC, _PO, _VP, _VP, _VP]),
     "svoxb_render_image_bwd": (ctypes.c_int, [_PT, _PC, _PO, _VP, _VP, _VP, _VP]),
     "svoxb_render_depth": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP]),
@@ -191,6 +194,8 @@ class RaysSpec:
         self.origins = None
         self.dirs = None
         self.vdirs = None
+        self._cost = None           # svox_t_b200 extension: per-ray march cost written by the forward (short batches), the
+                                    # backward's scheduling hint (svoxb_render_rays_fwd_cost / _bwd_cost)
 
     def check(self):
         for n in ("origins", "dirs", "vdirs"):
@@ -212,6 +217,8 @@ class TreeSpec:
         self.joint_index = None
         self.transformation_matrices = None
         self.n_internal = 0
+        self._grad_exchange = None  # svox_t_b200 extension: dist.LeafGradExchange -- the backward reduces into its symmetric
+                                    # table and sums it over the GPUs (None = a fresh zeros_like(features), as the reference)
         self._accel = None          # svox_t_b200 extension: Accel handle cached by N3Tree (None = reference walk)
         self._act = None            # svox_t_b200 extension: Activated table for `features` (None = sigmoid in-kernel)
 
@@ -454,6 +461,16 @@ def _accumulate_weights(tree, ct, rays, cam_c, opt):
                                         ctypes.byref(opt._c()), _ptr(wa), _stream()))
 
 
+_ORDER_MAX = None
+
+
+def _order_max_rays():
+    global _ORDER_MAX
+    if _ORDER_MAX is None:
+        _ORDER_MAX = int(load_library().svoxb_ray_order_max_rays())
+    return _ORDER_MAX
+
+
 def _render_fwd(tree, rays, opt, want_depth):
     lib = load_library()
     rays.check()
@@ -470,8 +487,11 @@ def _render_fwd(tree, rays, opt, want_depth):
             want_depth = False
         fused = torch.empty((Q, 1), dtype=torch.float32, device=dev) if want_depth else None
         depth = fused if want_depth else depth
-        _check(lib.svoxb_render_rays_fwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), _ptr(rays.vdirs), Q,
-                                         ctypes.byref(opt._c()), _ptr(out), _ptr(fused), _stream()))
+        rays._cost = None
+        if ct.accel and 2048 <= Q <= _order_max_rays():     # short batch: the forward leaves the backward its ray costs
+            rays._cost = torch.empty((Q,), dtype=torch.int32, device=dev)
+        _check(lib.svoxb_render_rays_fwd_cost(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), _ptr(rays.vdirs), Q,
+                                              ctypes.byref(opt._c()), _ptr(out), _ptr(fused), _ptr(rays._cost), _stream()))
         _accumulate_weights(tree, ct, rays, None, opt)
     return out, depth
 
@@ -517,9 +537,18 @@ def volume_render_backward(tree, rays, opt, grad_output, saved_out=None):
 
     with torch.cuda.device(dev):
         so = _saved_out_for_backward(tree, opt, saved_out, again, grad_output.shape)
-        grad = torch.zeros_like(tree.features)
-        _check(lib.svoxb_render_rays_bwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), _ptr(rays.vdirs), Q,
-                                         ctypes.byref(bopt), _ptr(grad_output), _ptr(so), _ptr(grad), _stream()))
+        xchg = getattr(tree, "_grad_exchange", None)
+        # multi-GPU: reduce into the exchange's symmetric table and sum it over the ranks right here (dist.LeafGradExchange)
+        grad = xchg.zeroed_table() if xchg is not None else torch.zeros_like(tree.features)
+        cost = getattr(rays, "_cost", None)
+        if cost is not None and (cost.shape[0] != Q or cost.device != dev):
+            cost = None
+        _check(lib.svoxb_render_rays_bwd_cost(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), _ptr(rays.vdirs), Q,
+                                              ctypes.byref(bopt), _ptr(grad_output), _ptr(so), _ptr(grad), _ptr(cost),
+                                              _stream()))
+        if xchg is not None:
+            xchg.all_reduce_()
+            grad = grad.view(grad.shape)        # a fresh tensor object over the table: autograd adopts it without a copy
     return grad
 
 

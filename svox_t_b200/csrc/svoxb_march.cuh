@@ -32,6 +32,7 @@ struct RaySource {
     float ndc_focal;
     int chunk;                     // explicit rays: rays fetched from the queue per atomic (0 = RAY_CHUNK)
     const int* order;              // explicit rays, optional: queue position -> ray index (svoxb_order.cu: longest first)
+    int* steps_out;                // explicit rays, optional [Q]: march iterations of each ray, written by the forward
 };
 
 struct ViewDir {
@@ -322,8 +323,9 @@ static int persistent_grid(Kern kern, size_t smem, int64_t queue_len, int& grid,
 bool quad_supported(const TreeArgs& tr);
 // svoxb_order.cu: longest-first order of a short explicit ray batch (stream-ordered scratch, released by the caller)
 bool want_ray_order(const TreeArgs& tr, int64_t Q);
-int build_ray_order(const TreeArgs& tr, const float* origins, const float* dirs, int64_t Q, float step, int** order,
-                    cudaStream_t st);
+int64_t ray_order_max_rays();
+int build_ray_order(const TreeArgs& tr, const float* origins, const float* dirs, int64_t Q, float step, int* cost,
+                    bool cost_is_input, int** order, cudaStream_t st);
 int launch_fwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, float* out,
                     float* depth, cudaStream_t st);
 int launch_bwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, const float* grad_out,

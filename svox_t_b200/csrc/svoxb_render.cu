@@ -474,9 +474,9 @@ static int dispatch_bwd(const TreeArgs& tr, const RaySource& src, const MarchOpt
 
 using namespace svoxb;
 
-extern "C" int svoxb_render_rays_fwd(const svoxb_tree* tree, const float* origins, const float* dirs,
-                                     const float* vdirs, int64_t Q, const svoxb_render_options* opt, float* out,
-                                     float* depth, void* stream) {
+static int render_rays_fwd_impl(const svoxb_tree* tree, const float* origins, const float* dirs,
+                                const float* vdirs, int64_t Q, const svoxb_render_options* opt, float* out,
+                                float* depth, int32_t* ray_cost, void* stream) {
     TreeArgs tr; MarchOpts m; RaySource src;
     int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = check_opts(opt, m); if (rc) return rc;
@@ -490,7 +490,11 @@ extern "C" int svoxb_render_rays_fwd(const svoxb_tree* tree, const float* origin
     // short batches: hand the rays out longest first (svoxb_order.cu)
     cudaStream_t st = (cudaStream_t)stream;
     int* order = nullptr;
-    if (want_ray_order(tr, Q)) { rc = build_ray_order(tr, origins, dirs, Q, m.step, &order, st); if (rc) return rc; }
+    if (want_ray_order(tr, Q)) {
+        // the estimate lands in the caller's ray_cost (if any); the RGBA march then overwrites it with the exact counts
+        rc = build_ray_order(tr, origins, dirs, Q, m.step, ray_cost, false, &order, st); if (rc) return rc;
+        src.steps_out = ray_cost;
+    }
     src.order = order;
     if (opt->format != SVOXB_FORMAT_RGBA) rc = fmt_render_fwd(tree, tr, src, m, opt, false, out, st);
     else rc = dispatch_fwd<false>(tr, src, m, out, depth, st);
@@ -498,9 +502,24 @@ extern "C" int svoxb_render_rays_fwd(const svoxb_tree* tree, const float* origin
     return rc;
 }
 
-extern "C" int svoxb_render_rays_bwd(const svoxb_tree* tree, const float* origins, const float* dirs,
-                                     const float* vdirs, int64_t Q, const svoxb_render_options* opt,
-                                     const float* grad_out, const float* saved_out, float* grad_features, void* stream) {
+extern "C" int svoxb_render_rays_fwd(const svoxb_tree* tree, const float* origins, const float* dirs,
+                                     const float* vdirs, int64_t Q, const svoxb_render_options* opt, float* out,
+                                     float* depth, void* stream) {
+    return render_rays_fwd_impl(tree, origins, dirs, vdirs, Q, opt, out, depth, nullptr, stream);
+}
+
+extern "C" int svoxb_render_rays_fwd_cost(const svoxb_tree* tree, const float* origins, const float* dirs,
+                                          const float* vdirs, int64_t Q, const svoxb_render_options* opt, float* out,
+                                          float* depth, int32_t* ray_cost, void* stream) {
+    return render_rays_fwd_impl(tree, origins, dirs, vdirs, Q, opt, out, depth, ray_cost, stream);
+}
+
+extern "C" int64_t svoxb_ray_order_max_rays(void) { return ray_order_max_rays(); }
+
+static int render_rays_bwd_impl(const svoxb_tree* tree, const float* origins, const float* dirs,
+                                const float* vdirs, int64_t Q, const svoxb_render_options* opt,
+                                const float* grad_out, const float* saved_out, float* grad_features,
+                                const int32_t* ray_cost, void* stream) {
     TreeArgs tr; MarchOpts m; RaySource src;
     int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = check_opts(opt, m); if (rc) return rc;
@@ -512,12 +531,28 @@ extern "C" int svoxb_render_rays_bwd(const svoxb_tree* tree, const float* origin
     }
     cudaStream_t st = (cudaStream_t)stream;
     int* order = nullptr;
-    if (want_ray_order(tr, Q)) { rc = build_ray_order(tr, origins, dirs, Q, m.step, &order, st); if (rc) return rc; }
+    if (want_ray_order(tr, Q)) {
+        rc = build_ray_order(tr, origins, dirs, Q, m.step, const_cast<int32_t*>(ray_cost), ray_cost != nullptr, &order, st);
+        if (rc) return rc;
+    }
     src.order = order;
     if (opt->format != SVOXB_FORMAT_RGBA) rc = fmt_render_bwd(tree, tr, src, m, opt, false, grad_out, saved_out, grad_features, st);
     else rc = dispatch_bwd<false>(tr, src, m, grad_out, saved_out, grad_features, st);
     if (order) cudaFreeAsync(order, st);
     return rc;
+}
+
+extern "C" int svoxb_render_rays_bwd(const svoxb_tree* tree, const float* origins, const float* dirs,
+                                     const float* vdirs, int64_t Q, const svoxb_render_options* opt,
+                                     const float* grad_out, const float* saved_out, float* grad_features, void* stream) {
+    return render_rays_bwd_impl(tree, origins, dirs, vdirs, Q, opt, grad_out, saved_out, grad_features, nullptr, stream);
+}
+
+extern "C" int svoxb_render_rays_bwd_cost(const svoxb_tree* tree, const float* origins, const float* dirs,
+                                          const float* vdirs, int64_t Q, const svoxb_render_options* opt,
+                                          const float* grad_out, const float* saved_out, float* grad_features,
+                                          const int32_t* ray_cost, void* stream) {
+    return render_rays_bwd_impl(tree, origins, dirs, vdirs, Q, opt, grad_out, saved_out, grad_features, ray_cost, stream);
 }
 
 extern "C" int svoxb_render_image_fwd(const svoxb_tree* tree, const svoxb_camera* cam,

@@ -185,8 +185,11 @@ __device__ __forceinline__ RowBlk<V4> load_row_block(const char* p, uint64_t pol
 // multiple of 4 floats: 16-byte aligned rows, D = 33 is served like D = 32), sigma comes from the compact sigma[M]
 // array next to it (one 4-byte gather per candidate, L2-resident), and the output rows / gradient rows of the
 // caller's unaligned [M, D] layout are written channel by channel.
-template <int LPR, int V4, bool ACCEL, bool IMAGE, bool DEPTH, bool AL>
-__global__ void __launch_bounds__(((DEPTH || !AL) ? Quad<LPR, V4>::THREADS : Quad<LPR, V4>::FWD_THREADS), 1)   // 80 registers
+// COUNT: also write the number of march iterations of every ray (RaySource::steps_out) -- the exact per-ray cost the
+// backward over the same batch is ordered by (svoxb_order.cu). One more live register per lane: its own instantiation
+// with the 80-register budget, used for short batches only (where the order matters and the 28th warp does not).
+template <int LPR, int V4, bool ACCEL, bool IMAGE, bool DEPTH, bool AL, bool COUNT = false>
+__global__ void __launch_bounds__(((DEPTH || !AL || COUNT) ? Quad<LPR, V4>::THREADS : Quad<LPR, V4>::FWD_THREADS), 1)   // 80 registers
 march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
                       unsigned long long* counter) {
     using G = Quad<LPR, V4>;
@@ -220,6 +223,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     Ray ray;
     float T = 1.0f, p_dt = 0.0f, p_t = 0.0f;
     int row = 0, p_idx = -1;
+    [[maybe_unused]] int steps = 0;
     bool active = false, got_depth = false, trav_done = true;
     Queue qu{0, 0, false};
     unsigned need = FULL;
@@ -229,6 +233,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             const unsigned got = refill<IMAGE>(src, off, scl, counter, qu, need, lane, ray, row);
             if ((got >> lane) & 1u) {
                 active = true; trav_done = false; T = 1.0f; got_depth = false;
+                if constexpr (COUNT) steps = 0;
                 if (DEPTH) depth[row] = 0.0f;           // overwritten at the first hit, if any
             }
             need = 0;
@@ -311,6 +316,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                 if (DEPTH) n_t = ray.t;
                 probe_end<ACCEL>(tr, pb, ray, opt.step, n_idx, n_dt);
                 ray.t += n_dt;
+                if constexpr (COUNT) ++steps;
                 if (!(ray.t < ray.tmax)) trav_done = true;
             }
         }
@@ -358,6 +364,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             }
             if (fin != 0) {
                 if constexpr (!AL) __stcs(out + (int64_t)row * D + (D - 1), 1.0f - T);   // opacity, by the owner lane
+                if constexpr (COUNT) src.steps_out[row] = steps;                         // the backward's scheduling hint
                 active = false;
             }
             need = fm;
@@ -618,11 +625,17 @@ static int launch_fwd_q(const TreeArgs& tr, const RaySource& src_in, const March
     using G = Quad<LPR, V4>;
     RaySource src = src_in;
     src.chunk = chunk_for(src, IMAGE);
-    const int threads = threads_for((depth || !AL) ? G::THREADS : G::FWD_THREADS, src.total, src.chunk);
+    bool count = false;
+    if constexpr (ACCEL && !IMAGE && AL) count = src.steps_out != nullptr && !depth;
+    const int threads = threads_for((depth || !AL || count) ? G::THREADS : G::FWD_THREADS, src.total, src.chunk);
     const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * (threads / 32) * 32 * LPR * V4;
     void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
     if (depth) kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, true, AL>;
     else kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, false, AL>;
+    if constexpr (ACCEL && !IMAGE && AL) {
+        if (count) kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, false, AL, true>;
+    }
+    if (!count) src.steps_out = nullptr;
     int grid = 0;
     int rc = persistent_grid(kern, smem, src.total, grid, threads, carveout_kb(smem), src.chunk);
     if (rc) return rc;

@@ -50,34 +50,38 @@ int sm_count() {
 // A ring of 64-bit work counters per (device, stream); each launch gets the next slot of ITS stream's ring, zeroed in
 // that stream's order. A slot is reused after N_COUNTERS later launches on the same stream, which stream order places
 // after the kernel that owned it; launches on other streams never touch it (a ring shared by all streams would let 256
-// short launches on stream B reset the queue of a long persistent march on stream A).
+// short launches on stream B reset the queue of a long persistent march on stream A). All rings of a device come from
+// one allocation made at the first launch (no cudaMalloc later: launches inside a stream capture stay legal); streams
+// beyond N_RINGS share rings by hash.
 static constexpr int N_COUNTERS = 256;
-struct CounterRing {
-    int dev;
-    cudaStream_t stream;
-    unsigned long long* base;
-    unsigned next;
+static constexpr int N_RINGS = 32;
+struct DeviceRings {
+    unsigned long long* base = nullptr;
+    cudaStream_t owner[N_RINGS] = {};
+    bool used[N_RINGS] = {};
+    unsigned next[N_RINGS] = {};
 };
-static std::vector<CounterRing> g_rings;
+static DeviceRings g_rings[64];
 static std::mutex g_counter_mu;
 
 unsigned long long* work_counter(cudaStream_t stream) {
     int dev = 0;
     if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return nullptr;
+    if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return nullptr; }
     unsigned long long* c = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_counter_mu);
-        CounterRing* ring = nullptr;
-        for (auto& r : g_rings)
-            if (r.dev == dev && r.stream == stream) { ring = &r; break; }
-        if (!ring) {
-            unsigned long long* p = nullptr;
-            if (check_cuda(cudaMalloc(&p, sizeof(unsigned long long) * N_COUNTERS), "cudaMalloc(work counters)"))
-                return nullptr;
-            g_rings.push_back(CounterRing{dev, stream, p, 0u});
-            ring = &g_rings.back();
-        }
-        c = ring->base + (ring->next++ % N_COUNTERS);
+        DeviceRings& d = g_rings[dev];
+        if (!d.base &&
+            check_cuda(cudaMalloc(&d.base, sizeof(unsigned long long) * N_COUNTERS * N_RINGS), "cudaMalloc(work counters)"))
+            return nullptr;
+        int ring = -1;
+        for (int i = 0; i < N_RINGS && ring < 0; ++i)
+            if (d.used[i] && d.owner[i] == stream) ring = i;
+        for (int i = 0; i < N_RINGS && ring < 0; ++i)
+            if (!d.used[i]) { d.used[i] = true; d.owner[i] = stream; ring = i; }
+        if (ring < 0) ring = (int)(((uintptr_t)stream >> 4) % N_RINGS);
+        c = d.base + (size_t)ring * N_COUNTERS + (d.next[ring]++ % N_COUNTERS);
     }
     if (check_cuda(cudaMemsetAsync(c, 0, sizeof(unsigned long long), stream), "cudaMemsetAsync(work counter)"))
         return nullptr;

@@ -169,6 +169,14 @@ def max_over_ranks(value_ms, device):
     return float(t.item())
 
 
+def sum_over_ranks(value, device):
+    """Sum of a per-rank scalar over all ranks."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
 def render_step_sharded(renderer, features, rays, loss_fn, rank, world):
     """One ray-sharded training step: this rank renders its slice, back-propagates, and the leaf gradients are
     summed over ranks. ``loss_fn(out, lo, hi)`` must return this shard's contribution to the global loss.

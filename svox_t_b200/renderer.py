@@ -139,12 +139,16 @@ class VolumeRenderer(nn.Module):
         if self.max_comp < 0:
             self.max_comp += self.data_format.basis_dim
         self.tree._weight_accum = None
+        # multi-GPU training (svox_t_b200 extension): set to a dist.LeafGradExchange and backward() leaves the leaf
+        # gradients of forward() summed over the GPUs, in the exchange's table (valid until the next backward)
+        self.leaf_grad_exchange = None
 
     def _render_spec(self, features, n_rays, **kw):
         """TreeSpec for a march over ``n_rays`` rays. When the batch is large enough for every leaf row to be visited
         many times, attach the pre-activated table (sigmoid once per row instead of once per visit); small batches
         keep the in-kernel sigmoid, for which one pass over the whole table would cost more than it saves."""
         ts = self.tree._spec(features, **kw)
+        ts._grad_exchange = getattr(self, "leaf_grad_exchange", None)
         M, D = features.shape
         if n_rays * 32 >= M and features.is_cuda:
             if self.data_format.format == DataFormat.RGBA and 2 <= D <= 128:

@@ -30,8 +30,8 @@ base = None
 for Q in (1 << 20, 1 << 19, 1 << 18, 1 << 17, 1 << 16):
     o_t, d_t, g_t = O[:Q].contiguous(), Dr[:Q].contiguous(), G[:Q].contiguous()
     rs = sv.renderer._rays_spec_from_rays(sv.Rays(o_t, d_t, d_t))
-    rows = []
-    for it in range(10):
+    rows, evs = [], []
+    for it in range(12):                 # queued back to back: the host runs ahead, the windows hold GPU time only
         e = [ev() for _ in range(6)]
         e[0].record()
         ts._act = C.Activated(feats)
@@ -43,13 +43,14 @@ for Q in (1 << 20, 1 << 19, 1 << 18, 1 << 17, 1 << 16):
         e[3].record()
         grad.zero_()
         e[4].record()
-        C._check(lib.svoxb_render_rays_bwd(C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), C._ptr(d_t), Q,
-                                           C.ctypes.byref(opt._c(sigma_thresh=0.0, stop_thresh=-1.0)),
-                                           C._ptr(g_t), C._ptr(out), C._ptr(grad), C._stream()))
+        C._check(lib.svoxb_render_rays_bwd_cost(C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), C._ptr(d_t), Q,
+                                                C.ctypes.byref(opt._c(sigma_thresh=0.0, stop_thresh=-1.0)),
+                                                C._ptr(g_t), C._ptr(out), C._ptr(grad), C._ptr(rs._cost), C._stream()))
         e[5].record()
-        torch.cuda.synchronize()
-        if it >= 3:
-            rows.append([e[i].elapsed_time(e[i + 1]) for i in range(5)] + [e[0].elapsed_time(e[5])])
+        evs.append(e)
+    torch.cuda.synchronize()
+    for e in evs[4:]:
+        rows.append([e[i].elapsed_time(e[i + 1]) for i in range(5)] + [e[0].elapsed_time(e[5])])
     m = np.median(np.array(rows), axis=0)
     rate = Q / (m[5] * 1e-3) / 1e6
     if base is None:
