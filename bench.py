@@ -12,8 +12,8 @@ and the step ends with the sum of the leaf-gradient tables over the GPUs -- STRO
 `value` at N GPUs against `value` at 1 GPU is the speed-up of that one step. (The weak-scaling number of round 1,
 2^20 rays PER GPU, is kept under `extras.weak_scaling`.)
 
-A step on every rank: per-row activation pass + hit marks (the features change every training step) -> forward march
--> zero-fill of the gradient table -> backward march -> exchange (svox_t_b200.dist.LeafGradExchange: one hand-written
+A step on every rank: ONE table pass (activated table + hit marks + zero-fill of the gradient table; the features change
+every training step) -> forward march -> backward march -> exchange (svox_t_b200.dist.LeafGradExchange: one hand-written
 kernel over symmetric memory, NVSwitch multicast reduction; NCCL all-reduce only as the fallback).
 
 One JSON line on stdout (rank 0). `value` = whole-job Mrays/s with inputs resident in HBM; `e2e` = the same step
@@ -262,18 +262,16 @@ def main():
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def refresh_tables():
-        # features change every training step: the per-row activation pass and the refresh of the accelerator's
-        # hit marks (both derived from the features) are part of the step
-        ts._act = C.Activated(feats)
-        if accel is not None:
-            accel._marks_key = None
-            accel.mark_hits(feats)
+        # features change every training step: ONE pass over the rows (svoxb_prepare_step) rebuilds the activated table,
+        # refreshes the accelerator's hit marks and zero-fills the gradient table this step's backward reduces into
+        ts._act = C.Activated(feats, accel=accel, zero_table=xchg.table)
 
-    def fwd_bwd(o_s, d_s, g_s, grad, e=None):
+    def fwd_bwd(o_s, d_s, g_s, grad, e=None, zero=False):
         rs = sv.renderer._rays_spec_from_rays(sv.Rays(o_s, d_s, d_s))
         out = C.volume_render(ts, rs, opt)
         if e: e[2].record()
-        grad.zero_()
+        if zero:
+            grad.zero_()
         C._check(lib.svoxb_render_rays_bwd_cost(C.ctypes.byref(ts._c()), C._ptr(o_s), C._ptr(d_s), C._ptr(d_s), o_s.shape[0],
                                                 C.ctypes.byref(bopt), C._ptr(g_s), C._ptr(out), C._ptr(grad),
                                                 C._ptr(rs._cost), C._stream()))   # rs._cost: short batches, else None
@@ -286,7 +284,7 @@ def main():
         if e: e[1].record()
         out = fwd_bwd(o_t, d_t, g_t, xchg.table, e)
         if e: e[3].record()
-        xchg.all_reduce_()
+        xchg.all_reduce_(features=feats)
         if e: e[4].record()
         if rec is not None:
             rec.append(e)
@@ -301,11 +299,11 @@ def main():
         g_p = g_all[:n].contiguous()
         refresh_tables()
         fwd_bwd(o_p[plo:phi].contiguous(), d_p[plo:phi].contiguous(), g_p[plo:phi].contiguous(), xchg.table)
-        xchg.all_reduce_()
+        xchg.all_reduce_(features=feats)
         rel = torch.zeros(1, device=dev, dtype=torch.float64)
         if rank == 0:
             alone = torch.empty_like(feats)
-            fwd_bwd(o_p, d_p, g_p, alone)
+            fwd_bwd(o_p, d_p, g_p, alone, zero=True)
             rel[0] = (xchg.table.double() - alone.double()).norm() / alone.double().norm()
             del alone
         torch.distributed.broadcast(rel, 0)
@@ -341,6 +339,12 @@ def main():
     stage = lambda i, j: float(np.mean([e[i].elapsed_time(e[j]) for e in rec]))
     tables_ms, fwd_ms, bwd_ms, xchg_ms = stage(0, 1), stage(1, 2), stage(2, 3), stage(3, 4)
     value = Q_GLOBAL / (ms_per_step * 1e-3) / 1e6
+    stage_ranks = None
+    if world > 1:       # every rank's stage times (the exchange's first barrier waits for the slowest backward)
+        mine = torch.tensor([tables_ms, fwd_ms, bwd_ms, xchg_ms], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        torch.distributed.all_gather(allr, mine)
+        stage_ranks = [[round(float(v), 4) for v in t] for t in allr]
 
     # ---- end to end through the public API: pinned host rays + targets in, loss out, every step ----------------------
     # Data-loader style pipeline: two device buffer sets; while step k renders out of one, a copy stream uploads the
@@ -377,7 +381,13 @@ def main():
             e = torch.cuda.Event(); e.record(copy_stream)
         return e
 
+    h_loss = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+
     def e2e_run(n_steps):
+        # the loss of step k is copied to pinned host memory in stream order and READ by the host after step k+1 has been
+        # queued (a training loop logs its loss one step late rather than draining the GPU every step); every step's loss
+        # is read inside the timed region, the last one after the loop
         losses = []
         ready = upload(0)
         for k in range(n_steps):
@@ -393,8 +403,14 @@ def main():
             loss = (0.5 / (3 * Q_GLOBAL)) * ((dec[:, :3] - brgb) ** 2).sum() + (0.5 / Q_GLOBAL) * ((dec[:, 3] - ba) ** 2).sum()
             loss.backward()                            # leaf gradients summed over the GPUs inside (leaf_grad_exchange)
             free_ev[k & 1] = torch.cuda.Event(); free_ev[k & 1].record(main_stream)
-            losses.append(float(loss.item()))          # device -> host read of the step's result
+            h_loss[k & 1:(k & 1) + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # device -> host, this step's result
+            loss_ev[k & 1].record(main_stream)
+            if k > 0:
+                loss_ev[(k - 1) & 1].synchronize()
+                losses.append(float(h_loss[(k - 1) & 1]))
             ready = nxt
+        loss_ev[(n_steps - 1) & 1].synchronize()
+        losses.append(float(h_loss[(n_steps - 1) & 1]))
         return losses
 
     e2e_run(3)
@@ -402,7 +418,7 @@ def main():
     t_wall2 = time.time()
     e0, e1 = ev(), ev()
     e0.record()
-    e2e_run(args.steps)
+    e2e_losses = e2e_run(args.steps)
     e1.record()
     torch.cuda.synchronize(); svd.barrier()
     t_wall3 = time.time()
@@ -412,12 +428,14 @@ def main():
     h2d_rank = int(h_o.numel() + h_d.numel() + h_rgb.numel() + h_alpha.numel()) * 4
     e2e = {"value": Q_GLOBAL / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(svd.sum_over_ranks(h2d_rank, dev)), "d2h_bytes_per_step": 4 * world,
-           "grad_is_exchange_table": grad_aliases,
+           "grad_is_exchange_table": grad_aliases, "losses_read": len(e2e_losses),
+           "loss_first_last": [e2e_losses[0], e2e_losses[-1]],
            "api": "VolumeRenderer.forward + autograd backward (leaf gradients summed over the GPUs inside backward()); "
                   "loss = this rank's share of MSE(decoded RGB, rgb target) + MSE(opacity, alpha target), RGB / opacity = a "
                   "fixed linear decoder (out @ W[32,4]). Every step every rank uploads its slice of the ray origins, "
-                  "directions, RGB and opacity targets from pinned host memory and reads its loss back; the upload of "
-                  "step k+1 overlaps the render of step k (double buffering). Bytes are summed over the ranks"}
+                  "directions, RGB and opacity targets from pinned host memory and reads its loss back (the upload of "
+                  "step k+1 overlaps the render of step k -- double buffering; the loss of step k is copied to pinned memory "
+                  "in stream order and read by the host once step k+1 is queued). Bytes are summed over the ranks"}
     renderer.leaf_grad_exchange = None
 
     # ---- N > 1: round 1's weak-scaling workload (2^20 rays PER GPU), a short run for continuity ------------------------
@@ -431,7 +449,7 @@ def main():
         def weak_step():
             refresh_tables()
             fwd_bwd(o_w, d_w, g_w, xchg.table)
-            xchg.all_reduce_()
+            xchg.all_reduce_(features=feats)
         for _ in range(3):
             weak_step()
         svd.barrier(); torch.cuda.synchronize()
@@ -465,9 +483,11 @@ def main():
                     "sample": f"first {n} of the 2^20 rays, fwd+bwd once, C oracle with OpenMP over rays ({cpu_s:.2f} s)"}
     scale = Q / cnt["Q"]                               # one launch on this rank marches its Q-ray slice
     cnt_rank = {k: (v * scale if k != "Q" else Q) for k, v in cnt.items()}
-    b_fwd, b_bwd = algorithmic_bytes(cnt_rank, D, M)
+    # the zero-fill of grad[M, D] happens in the table pass (stage "tables"), not in the window that times the backward
+    b_fwd, b_bwd = algorithmic_bytes(cnt_rank, D, M, zero_fill=False)
+    b_tables = 4 * M * D * 3 + 4 * M                   # features read, activated table + zeroed gradient table written
     stages = accel.describe()["stages"] if accel is not None else 1
-    bd_fwd, bd_bwd = design_bytes(cnt_rank, D, M, stages)
+    bd_fwd, bd_bwd = design_bytes(cnt_rank, D, M, stages, zero_fill=False)
     peak, peak_src = measured_peaks()
     traffic, traffic_src = latest_traffic()
     if world > 1:
@@ -488,19 +508,19 @@ def main():
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": roof(b_bwd, bwd_ms, "svoxb::march_bwd_quad_kernel (+ the zero-fill of grad[M,D], inside the timed window)",
-                         "march_bwd_quad_kernel"),
+        "roofline": roof(b_bwd, bwd_ms, "svoxb::march_bwd_quad_kernel", "march_bwd_quad_kernel"),
         "roofline_fwd": roof(b_fwd, fwd_ms, "svoxb::march_fwd_quad_kernel", "march_fwd_quad_kernel"),
         "roofline_design": {"bwd": roof(bd_bwd, bwd_ms, "svoxb::march_bwd_quad_kernel"),
                             "fwd": roof(bd_fwd, fwd_ms, "svoxb::march_fwd_quad_kernel"),
                             "note": "same times, bytes of this design: <= 1 brick word per sample and stage instead of "
                                     "the reference's per-level child lookups + data-slot read; hit rows only (sigma "
                                     "arrives with the row; rows with sigma <= 0 are never fetched)"},
-        "roofline_step": {"achieved": (b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                          "frac": (b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9 / peak,
+        "roofline_tables": roof(b_tables, tables_ms, "svoxb::prepare4_kernel (activation + hit marks + grad zero-fill)"),
+        "roofline_step": {"achieved": (b_fwd + b_bwd + b_tables) / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": (b_fwd + b_bwd + b_tables) / (ms_per_step * 1e-3) / 1e9 / peak,
                           "bytes_per_ray": (b_fwd + b_bwd) / Q,
-                          "note": "rank 0's march bytes over the whole step time (tables + exchange included)"},
-        "stage_ms": {"activation_and_marks": tables_ms, "fwd": fwd_ms, "zero_fill_and_bwd": bwd_ms, "exchange": xchg_ms,
+                          "note": "rank 0's march + table-pass bytes over the whole step time (exchange included)"},
+        "stage_ms": {"tables": tables_ms, "fwd": fwd_ms, "bwd": bwd_ms, "exchange": xchg_ms,
                      "note": "rank 0, CUDA events on the launch stream, mean over the timed steps; the exchange includes "
                              "the wait for the slowest rank's backward"},
         "kernel_ms": {"fwd": fwd_ms, "bwd": bwd_ms},
@@ -512,6 +532,8 @@ def main():
         "counters_per_ray": {k: cnt[k] / cnt["Q"] for k in ("S", "LV", "V", "H")},
         "cpu_baseline": cpu_baseline,
     }
+    if stage_ranks is not None:
+        out["stage_ms_ranks"] = {"columns": ["tables", "fwd", "bwd", "exchange"], "rows": stage_ranks}
     if dist_parity is not None:
         out["dist_parity_rel_l2"] = dist_parity
         out["dist_parity"] = {"rays": PARITY_SAMPLE, "tolerance": 1e-5,

@@ -74,6 +74,7 @@ SYMBOLS = {
                                             ctypes.POINTER(_I64)]),
     "svoxb_accel_mark_hits": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP]),
     "svoxb_activate_features": (ctypes.c_int, [_VP, _I64, _I32, _VP, _I32, _VP, _VP]),
+    "svoxb_prepare_step": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP, _I32, _VP, _VP, _VP]),
     "svoxb_query": (ctypes.c_int, [_PT, _VP, _I64, _VP, _VP, _VP, _VP, _VP]),
     "svoxb_leafset_scratch_bytes": (ctypes.c_size_t, [_I64]),
     "svoxb_leafset_scan": (ctypes.c_int, [_VP, _I64, _VP, _VP, _VP]),
@@ -87,6 +88,7 @@ SYMBOLS = {
     "svoxb_out_data_dim": (ctypes.c_int, [_I32, _I32, _I32]),
     "svoxb_render_rays_bwd": (ctypes.c_int, [_PT, _VP, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _VP]),
     "svoxb_ray_order_max_rays": (_I64, []),
+    "svoxb_ray_order_min_rays": (_I64, []),
     "svoxb_render_rays_fwd_cost": (ctypes.c_int, [_PT, _VP, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _VP]),
     "svoxb_render_rays_bwd_cost": (ctypes.c_int, [_PT, _VP, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _VP, _VP]),
     "svoxb_render_image_fwd": (ctypes.c_int, [_PT, _PC, _PO, _VP, _VP, _VP]),
@@ -105,6 +107,7 @@ SYMBOLS = {
     "svoxb_p2v": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP, _VP, _I32, _F, _F, _VP, _VP]),
     "svoxb_exchange_max_blocks": (ctypes.c_int, []),
     "svoxb_exchange_sum": (ctypes.c_int, [ctypes.POINTER(_CPeerGroup), _I64, _VP]),
+    "svoxb_exchange_sum_rows": (ctypes.c_int, [ctypes.POINTER(_CPeerGroup), _I64, _I32, _VP, _VP]),
     "svoxb_build_work_bytes": (ctypes.c_size_t, [_I64, _I32]),
     "svoxb_build_octree_count": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP, _VP, ctypes.POINTER(_I64), _VP]),
     "svoxb_build_octree_emit": (ctypes.c_int, [_I64, _I32, _VP, _I64, _VP, _VP, _VP, _VP]),
@@ -126,7 +129,7 @@ def load_library():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.svoxb_abi_version() != 8:
+        if lib.svoxb_abi_version() != 9:
             raise ImportError("svox_t_b200: libsvoxb.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib
@@ -378,15 +381,22 @@ class Accel:
 
 
 class Activated:
-    """features with the sigmoid applied once per row to the payload channels (svoxb_activate_features). Valid for
+    """features with the sigmoid applied once per row to the payload channels (svoxb_prepare_step). Valid for
     exactly one (storage object, version, layout) of ``features`` (_TensorIdentity); the renderer rebuilds it whenever
-    features change or another tensor is passed -- also one that reuses the address of a freed one."""
+    features change or another tensor is passed -- also one that reuses the address of a freed one.
 
-    def __init__(self, features):
+    The same pass over the rows can do the other per-step table work: ``accel`` -- refresh that accelerator's hit marks
+    for these features; ``zero_table`` -- zero-fill the [M, D] gradient table the step's backward will reduce into."""
+
+    def __init__(self, features, accel=None, zero_table=None):
         lib = load_library()
         _check_input(features, "features", torch.float32)
         self._key = _TensorIdentity(features)
         M, D = features.shape
+        if zero_table is not None:
+            _check_input(zero_table, "zero_table", torch.float32)
+            if tuple(zero_table.shape) != (M, D):
+                raise RuntimeError("zero_table must have the shape of features")
         with torch.cuda.device(features.device):
             if D % 4 == 0:
                 self.table, self.sigma = torch.empty_like(features), None
@@ -395,8 +405,10 @@ class Activated:
                 stride = (D - 1 + 3) // 4 * 4
                 self.table = torch.empty((M, stride), dtype=torch.float32, device=features.device)
                 self.sigma = torch.empty((M,), dtype=torch.float32, device=features.device)
-            _check(lib.svoxb_activate_features(_ptr(features), M, D, _ptr(self.table), stride, _ptr(self.sigma),
-                                               _stream()))
+            _check(lib.svoxb_prepare_step(accel.handle if accel is not None else None, _ptr(features), M, D,
+                                          _ptr(self.table), stride, _ptr(self.sigma), _ptr(zero_table), _stream()))
+        if accel is not None:
+            accel._marks_key = _TensorIdentity(features)
 
     def matches(self, features):
         return self._key.matches(features)
@@ -461,14 +473,16 @@ def _accumulate_weights(tree, ct, rays, cam_c, opt):
                                         ctypes.byref(opt._c()), _ptr(wa), _stream()))
 
 
-_ORDER_MAX = None
+_ORDER_RANGE = None
 
 
-def _order_max_rays():
-    global _ORDER_MAX
-    if _ORDER_MAX is None:
-        _ORDER_MAX = int(load_library().svoxb_ray_order_max_rays())
-    return _ORDER_MAX
+def _order_range():
+    """Batch sizes for which the forward leaves the backward its per-ray march costs (svoxb_order.cu)."""
+    global _ORDER_RANGE
+    if _ORDER_RANGE is None:
+        lib = load_library()
+        _ORDER_RANGE = (int(lib.svoxb_ray_order_min_rays()), int(lib.svoxb_ray_order_max_rays()))
+    return _ORDER_RANGE
 
 
 def _render_fwd(tree, rays, opt, want_depth):
@@ -488,7 +502,8 @@ def _render_fwd(tree, rays, opt, want_depth):
         fused = torch.empty((Q, 1), dtype=torch.float32, device=dev) if want_depth else None
         depth = fused if want_depth else depth
         rays._cost = None
-        if ct.accel and 2048 <= Q <= _order_max_rays():     # short batch: the forward leaves the backward its ray costs
+        lo, hi = _order_range()
+        if ct.accel and lo <= Q <= hi:                      # short batch: the forward leaves the backward its ray costs
             rays._cost = torch.empty((Q,), dtype=torch.int32, device=dev)
         _check(lib.svoxb_render_rays_fwd_cost(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), _ptr(rays.vdirs), Q,
                                               ctypes.byref(opt._c()), _ptr(out), _ptr(fused), _ptr(rays._cost), _stream()))
@@ -539,7 +554,7 @@ def volume_render_backward(tree, rays, opt, grad_output, saved_out=None):
         so = _saved_out_for_backward(tree, opt, saved_out, again, grad_output.shape)
         xchg = getattr(tree, "_grad_exchange", None)
         # multi-GPU: reduce into the exchange's symmetric table and sum it over the ranks right here (dist.LeafGradExchange)
-        grad = xchg.zeroed_table() if xchg is not None else torch.zeros_like(tree.features)
+        grad = xchg.table_for_backward(tree.features) if xchg is not None else torch.zeros_like(tree.features)
         cost = getattr(rays, "_cost", None)
         if cost is not None and (cost.shape[0] != Q or cost.device != dev):
             cost = None
@@ -547,7 +562,7 @@ def volume_render_backward(tree, rays, opt, grad_output, saved_out=None):
                                               ctypes.byref(bopt), _ptr(grad_output), _ptr(so), _ptr(grad), _ptr(cost),
                                               _stream()))
         if xchg is not None:
-            xchg.all_reduce_()
+            xchg.all_reduce_(features=tree.features)     # rows with sigma <= 0 hold zeros on every rank: skipped
             grad = grad.view(grad.shape)        # a fresh tensor object over the table: autograd adopts it without a copy
     return grad
 

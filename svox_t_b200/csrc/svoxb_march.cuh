@@ -321,11 +321,12 @@ static int persistent_grid(Kern kern, size_t smem, int64_t queue_len, int& grid,
 
 // Quad-lane kernels (svoxb_render_q.cu): D % 4 == 0 (4 <= D <= 128), or any D <= 128 with the padded activated table.
 bool quad_supported(const TreeArgs& tr);
-// svoxb_order.cu: longest-first order of a short explicit ray batch (stream-ordered scratch, released by the caller)
+// svoxb_order.cu: longest-first order of a short explicit ray batch for the backward, from the forward's exact per-ray
+// iteration counts (stream-ordered scratch, released by the caller)
 bool want_ray_order(const TreeArgs& tr, int64_t Q);
 int64_t ray_order_max_rays();
-int build_ray_order(const TreeArgs& tr, const float* origins, const float* dirs, int64_t Q, float step, int* cost,
-                    bool cost_is_input, int** order, cudaStream_t st);
+int64_t ray_order_min_rays();
+int build_ray_order(const int* cost, int64_t Q, int** order, cudaStream_t st);
 int launch_fwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, float* out,
                     float* depth, cudaStream_t st);
 int launch_bwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, const float* grad_out,

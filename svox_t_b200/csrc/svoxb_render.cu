@@ -21,6 +21,7 @@
 //     (9 shuffles per 8 hits) and the row gradient leaves as one coalesced red.global.add per hit;
 //   * N == 2 trees are walked through the packed grid+brick accelerator (top grid staged in shared memory),
 //     any other N through the reference tensors.
+#include <stdlib.h>
 #include "svoxb_march.cuh"
 
 namespace svoxb {
@@ -487,18 +488,16 @@ static int render_rays_fwd_impl(const svoxb_tree* tree, const float* origins, co
         SVOXB_REQUIRE(vdirs != nullptr, "view-dependent formats need vdirs");
         SVOXB_REQUIRE(depth == nullptr, "fused depth is only available for the RGBA format; call svoxb_render_depth");
     }
-    // short batches: hand the rays out longest first (svoxb_order.cu)
+    // short batches: the march also writes every ray's iteration count, which the backward over the same batch is
+    // ordered by (svoxb_order.cu); the forward itself runs in the caller's order
     cudaStream_t st = (cudaStream_t)stream;
-    int* order = nullptr;
-    if (want_ray_order(tr, Q)) {
-        // the estimate lands in the caller's ray_cost (if any); the RGBA march then overwrites it with the exact counts
-        rc = build_ray_order(tr, origins, dirs, Q, m.step, ray_cost, false, &order, st); if (rc) return rc;
+    if (ray_cost != nullptr && want_ray_order(tr, Q)) {
+        // ray_cost[0] = -1 until a kernel that counts overwrites it: the backward then keeps the caller's order
+        SVOXB_CUDA(cudaMemsetAsync(ray_cost, 0xff, sizeof(int32_t), st));
         src.steps_out = ray_cost;
     }
-    src.order = order;
     if (opt->format != SVOXB_FORMAT_RGBA) rc = fmt_render_fwd(tree, tr, src, m, opt, false, out, st);
     else rc = dispatch_fwd<false>(tr, src, m, out, depth, st);
-    if (order) cudaFreeAsync(order, st);
     return rc;
 }
 
@@ -515,6 +514,7 @@ extern "C" int svoxb_render_rays_fwd_cost(const svoxb_tree* tree, const float* o
 }
 
 extern "C" int64_t svoxb_ray_order_max_rays(void) { return ray_order_max_rays(); }
+extern "C" int64_t svoxb_ray_order_min_rays(void) { return ray_order_min_rays(); }
 
 static int render_rays_bwd_impl(const svoxb_tree* tree, const float* origins, const float* dirs,
                                 const float* vdirs, int64_t Q, const svoxb_render_options* opt,
@@ -531,8 +531,8 @@ static int render_rays_bwd_impl(const svoxb_tree* tree, const float* origins, co
     }
     cudaStream_t st = (cudaStream_t)stream;
     int* order = nullptr;
-    if (want_ray_order(tr, Q)) {
-        rc = build_ray_order(tr, origins, dirs, Q, m.step, const_cast<int32_t*>(ray_cost), ray_cost != nullptr, &order, st);
+    if (ray_cost != nullptr && want_ray_order(tr, Q)) {
+        rc = build_ray_order(ray_cost, Q, &order, st);
         if (rc) return rc;
     }
     src.order = order;

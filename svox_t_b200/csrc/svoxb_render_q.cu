@@ -597,7 +597,8 @@ static int carveout_kb(size_t smem) {
 }
 
 // Short queues: spread the warps over the SMs (smaller CTAs) instead of filling a few SMs with 24 warps each.
-static int threads_for(int max_threads, int64_t queue_len, int chunk) {
+static int threads_for(int max_threads, int64_t queue_len, int chunk, const char* cap_env = nullptr) {
+    if (cap_env && getenv(cap_env)) max_threads = min(max_threads, max(64, atoi(getenv(cap_env)) / 32 * 32));   // dev knob
     const int64_t warps_needed = (queue_len + chunk - 1) / chunk;
     const int64_t per_sm = (warps_needed + sm_count() - 1) / sm_count();
     return (int)max((int64_t)64, min((int64_t)max_threads, per_sm * 32));
@@ -627,7 +628,7 @@ static int launch_fwd_q(const TreeArgs& tr, const RaySource& src_in, const March
     src.chunk = chunk_for(src, IMAGE);
     bool count = false;
     if constexpr (ACCEL && !IMAGE && AL) count = src.steps_out != nullptr && !depth;
-    const int threads = threads_for((depth || !AL || count) ? G::THREADS : G::FWD_THREADS, src.total, src.chunk);
+    const int threads = threads_for((depth || !AL || count) ? G::THREADS : G::FWD_THREADS, src.total, src.chunk, "SVOXB_FWD_THREADS_CAP");
     const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * (threads / 32) * 32 * LPR * V4;
     void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
     if (depth) kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, true, AL>;
@@ -667,7 +668,7 @@ static int launch_bwd_q(const TreeArgs& tr, const RaySource& src_in, const March
     using G = Quad<LPR, V4>;
     RaySource src = src_in;
     src.chunk = chunk_for(src, IMAGE);
-    const int threads = threads_for(G::THREADS, src.total, src.chunk);
+    const int threads = threads_for(G::THREADS, src.total, src.chunk, "SVOXB_BWD_THREADS_CAP");
     const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * (threads / 32) * 32 * G::DP;
     auto kern = march_bwd_quad_kernel<LPR, V4, ACCEL, IMAGE, AL>;
     int grid = 0;

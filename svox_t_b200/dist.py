@@ -110,34 +110,89 @@ class LeafGradExchange:
             torch.cuda.synchronize(self.device)
         dist.barrier(self.group)                                     # every rank's flags are zero before the first use
         mc = int(getattr(hdl, "multicast_ptr", 0) or 0)                # 0: the fabric offers no multicast mapping
-        if self.backend == "p2p":
-            mc = 0
-        elif self.backend == "nvls" and not mc:
+        if self.backend == "nvls" and not mc:
             raise RuntimeError("SVOXB_EXCHANGE=nvls but the symmetric allocation has no multicast mapping")
-        self.backend = "nvls" if mc else "p2p"
         self._buf, self._hdl = buf, hdl
         self._ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
-        self._pg = self._C._CPeerGroup(
-            rank=self.rank, world=self.world, buffers=ctypes.cast(self._ptrs, ctypes.POINTER(ctypes.c_void_p)),
-            multicast=ctypes.c_void_p(mc), table_offset=0, flags_offset=self.n_floats * 4,
-            status_offset=self.n_floats * 4 + self.FLAG_BYTES - 4, blocks=self.blocks, epoch=1)
+        self._epoch = 1
+
+        def group_for(multicast):
+            return self._C._CPeerGroup(
+                rank=self.rank, world=self.world, buffers=ctypes.cast(self._ptrs, ctypes.POINTER(ctypes.c_void_p)),
+                multicast=ctypes.c_void_p(multicast), table_offset=0, flags_offset=self.n_floats * 4,
+                status_offset=self.n_floats * 4 + self.FLAG_BYTES - 4, blocks=self.blocks, epoch=1)
+        forms = {"p2p": group_for(0)}
+        if mc:
+            forms["nvls"] = group_for(mc)
+        if self.backend in forms:
+            self._pg = forms[self.backend]
+        else:
+            # auto: both forms move the same bytes through different hardware (in-switch reduction + multicast against
+            # plain peer loads / stores); which one wins depends on the number of GPUs -- time them on this table
+            self.tuning = {}
+            for name, pg in forms.items():
+                self._pg = pg
+                for _ in range(2):
+                    self._launch(None)
+                torch.cuda.synchronize(self.device)
+                dist.barrier(self.group)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(4):
+                    self._launch(None)
+                e1.record()
+                torch.cuda.synchronize(self.device)
+                t = torch.tensor([e0.elapsed_time(e1) / 4], dtype=torch.float64, device=self.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)      # every rank sees the same numbers
+                self.tuning[name] = float(t.item())
+            self.backend = min(self.tuning, key=self.tuning.get)
+            self._pg = forms[self.backend]
+            buf[:self.n_floats].zero_()
+            torch.cuda.synchronize(self.device)
+            dist.barrier(self.group)
+
+    def _launch(self, features):
+        lib = self._C.load_library()
+        self._pg.epoch = self._epoch
+        with torch.cuda.device(self.device):
+            if features is not None:
+                self._C._check(lib.svoxb_exchange_sum_rows(ctypes.byref(self._pg), self.M, self.D,
+                                                           self._C._ptr(features), self._C._stream()))
+            else:
+                self._C._check(lib.svoxb_exchange_sum(ctypes.byref(self._pg), self.n_floats, self._C._stream()))
+        self._epoch = (self._epoch + 2) & 0xFFFFFFFF
 
     def zeroed_table(self):
         """The [M, D] table, zero-filled in stream order (the reference's zeros_like(features), rt_kernel.cu:1415)."""
+        self._zeroed_for = None
         self.table.zero_()
         return self.table
 
-    def all_reduce_(self):
-        """Sum the table over the ranks, in place, in stream order on the current stream. Collective."""
+    def note_zeroed(self, features):
+        """The table has just been zero-filled (in stream order) by the per-step table pass of the forward over
+        ``features`` (csrc.Activated): the next backward for exactly these features reduces into it as it is."""
+        self._zeroed_for = self._C._TensorIdentity(features)
+
+    def table_for_backward(self, features):
+        """The zero-filled table a backward reduces into: as left by the forward's table pass when that pass zeroed it
+        for these features and nothing has used it since, else zero-filled now. One backward per zero-fill."""
+        key, self._zeroed_for = getattr(self, "_zeroed_for", None), None
+        if key is not None and key.matches(features):
+            return self.table
+        return self.zeroed_table()
+
+    def all_reduce_(self, features=None):
+        """Sum the table over the ranks, in place, in stream order on the current stream. Collective.
+        ``features``: the table holds the gradient a backward produced for these (replicated) features -- rows with
+        sigma <= 0 got no gradient on any rank and are left out of the exchange (svoxb_exchange_sum_rows)."""
         if self.world == 1:
             return self.table
         if self._hdl is None:
             dist.all_reduce(self.table, op=dist.ReduceOp.SUM, group=self.group)
             return self.table
-        with torch.cuda.device(self.device):
-            self._C._check(self._C.load_library().svoxb_exchange_sum(ctypes.byref(self._pg), self.n_floats,
-                                                                     self._C._stream()))
-        self._pg.epoch = (self._pg.epoch + 2) & 0xFFFFFFFF
+        rows = (features is not None and tuple(features.shape) == (self.M, self.D) and features.is_contiguous()
+                and features.dtype == torch.float32 and features.device == self.table.device)
+        self._launch(features if rows else None)
         return self.table
 
     def status(self):
@@ -151,6 +206,8 @@ class LeafGradExchange:
         d = {"backend": self.backend, "world": self.world, "bytes": self.n_floats * 4}
         if self._hdl is not None:
             d["blocks"] = self.blocks
+            if getattr(self, "tuning", None):
+                d["tuning_ms"] = {k: round(v, 4) for k, v in self.tuning.items()}
         if hasattr(self, "_why_nccl"):
             d["fallback_reason"] = self._why_nccl[:200]
         return d

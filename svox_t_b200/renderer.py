@@ -152,8 +152,11 @@ class VolumeRenderer(nn.Module):
         M, D = features.shape
         if n_rays * 32 >= M and features.is_cuda:
             if self.data_format.format == DataFormat.RGBA and 2 <= D <= 128:
-                ts._act = self.tree.activated(features.detach())
-            if ts._accel is not None:       # every format keeps sigma in the last channel: dead rows are never fetched
+                # one pass over the rows: activated table + hit marks (+ zero-fill of the exchange's gradient table when
+                # this forward will be back-propagated)
+                xchg = ts._grad_exchange if (features.requires_grad and torch.is_grad_enabled()) else None
+                ts._act = self.tree.activated(features.detach(), accel=ts._accel, grad_exchange=xchg)
+            elif ts._accel is not None:     # every format keeps sigma in the last channel: dead rows are never fetched
                 ts._accel.mark_hits(features.detach())
         return ts
 

@@ -322,12 +322,19 @@ class N3Tree(nn.Module):
             self._accel_cache = acc
         return acc
 
-    def activated(self, features):
-        """Table of ``features`` with the sigmoid applied once per row (cached until ``features`` changes)."""
+    def activated(self, features, accel=None, grad_exchange=None):
+        """Table of ``features`` with the sigmoid applied once per row (cached until ``features`` changes). The pass that
+        builds it also refreshes ``accel``'s hit marks and zero-fills ``grad_exchange``'s gradient table for the
+        backward of the step that starts with these features (csrc.Activated)."""
         act = getattr(self, "_act_cache", None)
         if act is None or not act.matches(features):
-            act = _C.Activated(features)
+            zero = grad_exchange.table if grad_exchange is not None else None
+            act = _C.Activated(features, accel=accel, zero_table=zero)
+            if grad_exchange is not None:
+                grad_exchange.note_zeroed(features)
             self._act_cache = act
+        elif accel is not None:
+            accel.mark_hits(features)
         return act
 
     def _spec(self, features, joint_features=None, skinning_weights=None, joint_index=None,

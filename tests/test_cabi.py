@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), f"{name} declared in include/svoxb.h but not exported by libsvoxb.so"
     assert sorted(C.SYMBOLS) == declared_symbols(), "python prototypes out of sync with include/svoxb.h"
-    assert lib.svoxb_abi_version() == 8
+    assert lib.svoxb_abi_version() == 9
 
 
 def test_struct_layouts_match_header():

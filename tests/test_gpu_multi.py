@@ -45,11 +45,22 @@ def _worker(rank, world, port, q):
     frame_ok = bool(torch.equal(frame, r.render_persp(feats.detach(), cam, width=90, height=61, fx=100.0)))
     imgs, (lo, hi) = svd.render_views_sharded(r, feats.detach(), [cam] * 3, 32, 24, 40.0, rank=rank, world=world)
     assert len(imgs) == hi - lo and frame_ok
+    # the same step with the hand-written exchange (symmetric memory; NVLS multicast or peer-to-peer): the backward
+    # reduces into the exchange's table, the sum over the GPUs happens inside backward()
+    xchg = svd.LeafGradExchange(tr["M"], D, dev)
+    r.leaf_grad_exchange = xchg
+    f2 = feats.detach().clone().requires_grad_(True)
+    lo, hi = svd.shard_range(Q, rank, world)
+    (r(f2, svd.shard_rays(rays, rank, world)) * g_t[lo:hi]).sum().backward()
+    torch.cuda.synchronize()
+    assert xchg.status() == 0
+    r.leaf_grad_exchange = None
     if rank == 0:
         full = feats.detach().clone().requires_grad_(True)
         (r(full, rays) * g_t).sum().backward()
         rel = float((grad - full.grad).norm() / full.grad.norm())
-        q.put(rel)
+        rel2 = float((f2.grad - full.grad).norm() / full.grad.norm())
+        q.put((rel, rel2, xchg.describe()["backend"]))
     svd.barrier()
     dist.destroy_process_group()
 
@@ -62,8 +73,9 @@ def test_two_gpu_sharded_gradients_match_single_gpu():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    rel = q.get(timeout=300)
+    rel, rel2, backend = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     assert rel < 1e-5, rel
+    assert rel2 < 1e-5, (rel2, backend)

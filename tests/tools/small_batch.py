@@ -25,7 +25,7 @@ lib = C.load_library()
 ev = lambda: torch.cuda.Event(enable_timing=True)
 grad = torch.zeros_like(feats)
 print(f"C3 tree L={L} D={D} M={tr['M']}; per-stage ms (median of 7)")
-print("    rays  act   marks  fwd    zero   bwd    total   Mrays/s   vs 2^20 per-ray rate")
+print("    rays  tables  -    fwd    -      bwd    total   Mrays/s   vs 2^20 per-ray rate")
 base = None
 for Q in (1 << 20, 1 << 19, 1 << 18, 1 << 17, 1 << 16):
     o_t, d_t, g_t = O[:Q].contiguous(), Dr[:Q].contiguous(), G[:Q].contiguous()
@@ -34,14 +34,11 @@ for Q in (1 << 20, 1 << 19, 1 << 18, 1 << 17, 1 << 16):
     for it in range(12):                 # queued back to back: the host runs ahead, the windows hold GPU time only
         e = [ev() for _ in range(6)]
         e[0].record()
-        ts._act = C.Activated(feats)
+        ts._act = C.Activated(feats, accel=accel, zero_table=grad)      # one pass: activation + hit marks + grad zero-fill
         e[1].record()
-        accel._marks_key = None
-        accel.mark_hits(feats)
         e[2].record()
         out = C.volume_render(ts, rs, opt)
         e[3].record()
-        grad.zero_()
         e[4].record()
         C._check(lib.svoxb_render_rays_bwd_cost(C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), C._ptr(d_t), Q,
                                                 C.ctypes.byref(opt._c(sigma_thresh=0.0, stop_thresh=-1.0)),
@@ -56,4 +53,16 @@ for Q in (1 << 20, 1 << 19, 1 << 18, 1 << 17, 1 << 16):
     if base is None:
         base = (m[2] + m[4]) / Q
     eff = base * Q / (m[2] + m[4])
-    print(f"{Q:8d}  {m[0]:.3f} {m[1]:.3f}  {m[2]:.3f}  {m[3]:.3f}  {m[4]:.3f}  {m[5]:.3f}   {rate:7.1f}   march {eff:.2f}")
+    extra = ""
+    if rs._cost is not None:            # forward again, ordered by the EXACT counts the first forward left: the bound of the estimate
+        os.environ["SVOXB_FWD_COST_INPUT"] = "1"
+        tt = []
+        for it in range(8):
+            a, b = ev(), ev()
+            a.record()
+            C._check(lib.svoxb_render_rays_fwd_cost(C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), C._ptr(d_t), Q,
+                                                    C.ctypes.byref(opt._c()), C._ptr(out), None, C._ptr(rs._cost), C._stream()))
+            b.record(); torch.cuda.synchronize(); tt.append(a.elapsed_time(b))
+        del os.environ["SVOXB_FWD_COST_INPUT"]
+        extra = f"   fwd ordered by exact counts {np.median(tt[2:]):.3f}"
+    print(f"{Q:8d}  {m[0]:.3f} {m[1]:.3f}  {m[2]:.3f}  {m[3]:.3f}  {m[4]:.3f}  {m[5]:.3f}   {rate:7.1f}   march {eff:.2f}{extra}")
