@@ -260,7 +260,26 @@ __device__ __forceinline__ void probe_begin(const TreeArgs& tr, const uint32_t* 
     }
 }
 
+// Trees deeper than two stages (depth > 8): consume the stage-1 word and ISSUE the stage-2 lookup. Stage 1 is small
+// (L2-resident); stage 2 of a depth-10 scene is hundreds of MB, its lookup goes to DRAM -- called between the row
+// requests and the compositing, that latency hides behind the compositing instead of being waited for in probe_end
+// (C5, 2^20 random rays: forward 5.6 -> see profiles/NOTES_r02.md). A no-op (no wait on the stage-1 word) for <= 2 stages.
 template <bool ACCEL>
+__device__ __forceinline__ void probe_mid(const TreeArgs& tr, Probe& pb) {
+    if (ACCEL) {
+        const AccelView& a = tr.acc;
+        if (a.n_stages > 2 && (pb.cell & ACC_PTR)) {
+            const float s = __int_as_float((127 + a.lmax) << 23);
+            const int Ix = (int)(pb.px * s), Iy = (int)(pb.py * s), Iz = (int)(pb.pz * s);
+            const int b = a.bits[2], sh = a.shift[2], m = (1 << b) - 1;
+            const uint32_t lin = (((((Ix >> sh) & m) << b) | ((Iy >> sh) & m)) << b) | ((Iz >> sh) & m);
+            pb.cell = __ldg(a.cells[2] + (((size_t)(pb.cell & 0x7fffffffu)) << (3 * b)) + lin);
+        }
+    }
+}
+
+// FIRST: the first stage probe_end may still have to resolve (2; 3 when the caller ran probe_mid).
+template <bool ACCEL, int FIRST = 2>
 __device__ __forceinline__ void probe_end(const TreeArgs& tr, const Probe& pb, const Ray& r, float step,
                                           int& idx, float& delta_t) {
     float rx, ry, rz, smin, smax;
@@ -271,7 +290,7 @@ __device__ __forceinline__ void probe_end(const TreeArgs& tr, const Probe& pb, c
             const float s = __int_as_float((127 + a.lmax) << 23);
             const int Ix = (int)(pb.px * s), Iy = (int)(pb.py * s), Iz = (int)(pb.pz * s);
 #pragma unroll
-            for (int st = 2; st < MAX_STAGES; ++st) {
+            for (int st = FIRST; st < MAX_STAGES; ++st) {
                 if (cell & ACC_PTR) {
                     const int b = a.bits[st], sh = a.shift[st], m = (1 << b) - 1;
                     const uint32_t lin = (((((Ix >> sh) & m) << b) | ((Iy >> sh) & m)) << b) | ((Iz >> sh) & m);

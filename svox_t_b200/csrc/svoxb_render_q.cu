@@ -189,7 +189,7 @@ __device__ __forceinline__ RowBlk<V4> load_row_block(const char* p, uint64_t pol
 // backward over the same batch is ordered by (svoxb_order.cu). One more live register per lane: its own instantiation
 // with the 80-register budget, used for short batches only (where the order matters and the 28th warp does not).
 template <int LPR, int V4, bool ACCEL, bool IMAGE, bool DEPTH, bool AL, bool COUNT = false>
-__global__ void __launch_bounds__(((DEPTH || !AL || COUNT) ? Quad<LPR, V4>::THREADS : Quad<LPR, V4>::FWD_THREADS), 1)   // 80 registers
+__global__ void __launch_bounds__(((DEPTH || !AL) ? Quad<LPR, V4>::THREADS : Quad<LPR, V4>::FWD_THREADS), 1)
 march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
                       unsigned long long* counter) {
     using G = Quad<LPR, V4>;
@@ -200,7 +200,8 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31;
     // this warp's 32 x DP partial outputs: accs[(j * V4 + h) * 32] = float4 h of this lane's block of ray RPI*j + q
-    float4* accs = reinterpret_cast<float4*>(smem_u32 + top_words) + (size_t)(threadIdx.x >> 5) * 32 * LPR * V4 + lane;
+    float4* accs = reinterpret_cast<float4*>(smem_u32 + top_words + (COUNT ? blockDim.x : 0)) +
+                   (size_t)(threadIdx.x >> 5) * 32 * LPR * V4 + lane;
     static_assert(AL || V4 == 1, "padded rows use 128-bit blocks");
     const int q = lane / LPR, c = lane % LPR;
     const int D = tr.D, DV = AL ? D / VEC : (D - 1 + VEC - 1) / VEC;
@@ -223,7 +224,11 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     Ray ray;
     float T = 1.0f, p_dt = 0.0f, p_t = 0.0f;
     int row = 0, p_idx = -1;
-    [[maybe_unused]] int steps = 0;
+    // COUNT: a ray's cost = loop iterations between its refill and its end. The loop counter is warp-uniform (a uniform
+    // register), the iteration a lane's ray started at waits in shared memory (one int per thread between the top grid
+    // and the accumulators): no 73rd vector register, no per-iteration work
+#define SVOXB_STEPS_S (reinterpret_cast<int*>(smem_u32 + top_words)[threadIdx.x])
+    [[maybe_unused]] int iter = 0;
     bool active = false, got_depth = false, trav_done = true;
     Queue qu{0, 0, false};
     unsigned need = FULL;
@@ -233,12 +238,13 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             const unsigned got = refill<IMAGE>(src, off, scl, counter, qu, need, lane, ray, row);
             if ((got >> lane) & 1u) {
                 active = true; trav_done = false; T = 1.0f; got_depth = false;
-                if constexpr (COUNT) steps = 0;
+                if constexpr (COUNT) SVOXB_STEPS_S = iter;
                 if (DEPTH) depth[row] = 0.0f;           // overwritten at the first hit, if any
             }
             need = 0;
         }
         if (__ballot_sync(FULL, active) == 0u) break;
+        if constexpr (COUNT) ++iter;
 
         // ---- S0: request the rows of batch 0 of the pending candidates. First thing in the iteration (a load left
         // in flight across the loop back-edge is waited for at the loop header); unconditional on purpose (a guarded
@@ -259,6 +265,8 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             if (!(ray.t < ray.tmax)) { trav_done = true; trav = false; }
             else probe_begin<ACCEL>(tr, top, ray, pb);
         }
+
+        if (trav) probe_mid<ACCEL>(tr, pb);
 
         const unsigned pm = __ballot_sync(FULL, p_idx >= 0);
         bool stopped = false;
@@ -314,9 +322,8 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             // ---- S3 (once, after the first batch) ------------------------------------------------------------------
             if (b == 0 && trav) {
                 if (DEPTH) n_t = ray.t;
-                probe_end<ACCEL>(tr, pb, ray, opt.step, n_idx, n_dt);
+                probe_end<ACCEL, 3>(tr, pb, ray, opt.step, n_idx, n_dt);
                 ray.t += n_dt;
-                if constexpr (COUNT) ++steps;
                 if (!(ray.t < ray.tmax)) trav_done = true;
             }
         }
@@ -364,7 +371,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             }
             if (fin != 0) {
                 if constexpr (!AL) __stcs(out + (int64_t)row * D + (D - 1), 1.0f - T);   // opacity, by the owner lane
-                if constexpr (COUNT) src.steps_out[row] = steps;                         // the backward's scheduling hint
+                if constexpr (COUNT) src.steps_out[row] = iter - SVOXB_STEPS_S;                         // the backward's scheduling hint
                 active = false;
             }
             need = fm;
@@ -473,6 +480,8 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
             else probe_begin<ACCEL>(tr, top, ray, pb);
         }
 
+        if (trav) probe_mid<ACCEL>(tr, pb);
+
         const unsigned pm = __ballot_sync(FULL, p_idx >= 0);
         int n_idx = -1;
         float n_dt = 0.0f;
@@ -563,7 +572,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
             }
             // ---- S3 (once, after the first batch) ------------------------------------------------------------------
             if (b == 0 && trav) {
-                probe_end<ACCEL>(tr, pb, ray, opt.step, n_idx, n_dt);
+                probe_end<ACCEL, 3>(tr, pb, ray, opt.step, n_idx, n_dt);
                 ray.t += n_dt;
                 if (!(ray.t < ray.tmax)) trav_done = true;
             }
@@ -628,8 +637,9 @@ static int launch_fwd_q(const TreeArgs& tr, const RaySource& src_in, const March
     src.chunk = chunk_for(src, IMAGE);
     bool count = false;
     if constexpr (ACCEL && !IMAGE && AL) count = src.steps_out != nullptr && !depth;
-    const int threads = threads_for((depth || !AL || count) ? G::THREADS : G::FWD_THREADS, src.total, src.chunk, "SVOXB_FWD_THREADS_CAP");
-    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * (threads / 32) * 32 * LPR * V4;
+    const int threads = threads_for((depth || !AL) ? G::THREADS : G::FWD_THREADS, src.total, src.chunk, "SVOXB_FWD_THREADS_CAP");
+    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * (threads / 32) * 32 * LPR * V4 +
+                        (count ? sizeof(int) * threads : 0);
     void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
     if (depth) kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, true, AL>;
     else kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, false, AL>;

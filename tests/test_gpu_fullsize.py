@@ -7,8 +7,10 @@
   C4  the animated frame: LBS warp -> Gaussian splat -> octree rebuild to depth 8 from 2^20 warped points -> render,
       against the same pipeline driven through the REFERENCE's kernels (warp_vertices, p2v, query_vertical + the
       refine step of svox.py:488-560 + construct_tree) -- tree isomorphism, then render parity;
-  C5  depth-10 shell, 64 channels (M*D > 2^31 elements -- the regime the reference's 32-bit accessors cannot address,
-      include/data_spec_packed.cuh:60): 4096 random rays fwd + bwd and a band of a 1920x1080 view against the CPU oracle.
+  C5  depth-10 shell, 64 channels (32.9 M rows, 8.4 GB: byte offsets beyond 2^32, element offsets at the edge of the
+      reference's 32-bit accessors, include/data_spec_packed.cuh:60): 4096 random rays fwd + bwd and a band of a
+      1920x1080 view against the CPU oracle; and the same tree with 68 channels (M*D > 2^31 ELEMENTS, which those
+      accessors cannot address at all): a ray sample fwd + bwd and the far end of the table against the oracle.
 
 Tolerances: integers bit-exact; fwd |a-ref| <= 1e-4 + 1e-3|ref| on >= 99.9 % of entries and mean abs
 err <= 1e-5; depth <= 1e-5 on >= 99.9 % of rays; gradients relative L2 <= 1e-4 and per-row max rel err <= 1e-3 on
@@ -174,7 +176,7 @@ def test_c5_shaped_scene_against_oracle(dev):
     L, D = 10, 64
     tr = synth.synth_tree(L, "shell")
     M = int(tr["M"])
-    assert M * D > 2 ** 31                                        # beyond the reference's 32-bit accessors
+    assert M * D * 4 > 2 ** 32 and M * D > 2 ** 30                # byte offsets beyond 32 bits
     g = torch.Generator(device=dev).manual_seed(0)
     feats = torch.randn(M, D, device=dev, generator=g)
     feats[:, -1] = torch.rand(M, device=dev, generator=g) * 10 - 2
@@ -201,13 +203,24 @@ def test_c5_shaped_scene_against_oracle(dev):
         assert rel_l2_t(grad, ref_grad) <= 1e-4
         ok, touched = rows_within(grad, ref_grad)
         assert touched > 100_000 and ok >= 0.999
-        assert bool(grad[-1].abs().sum() >= 0) and grad.shape == (M, D)     # the last row (element index > 2^31) is addressable
+        assert grad.shape == (M, D)
         del grad, out, depth
     del ref_grad
+    # M*D = 2.107e9 still fits the reference's 32-bit accessors (< 2^31): its own kernels run this scene too
+    if os.path.exists(refdrv.REF_SO):
+        m = refdrv.module()
+        rts = refdrv.tree_spec(feats, tree.child, tree.data, tree.parent_depth, tree.offset, tree.invradius, tree.filled)
+        rrs, ro = refdrv.rays_spec(o_t, d_t), refdrv.options()
+        spec = r._render_spec(feats, 1 << 21)
+        out = C.volume_render(spec, rs, opt)
+        assert float((out - m.volume_render(rts, rrs, ro)).abs().max()) <= 1e-5
+        grad = C.volume_render_backward(spec, rs, opt, cu(g_np, dev), saved_out=out)
+        assert rel_l2_t(grad, m.volume_render_backward(rts, rrs, ro, cu(g_np, dev))) <= 1e-5
+        del grad, out, rts
     # rows at the far end of the table are really reached (element offsets beyond 2^31)
     pts = cu(synth.voxel_centers(synth._occupied_keys(L, "shell")[-4096:], L), dev)
     v, nid, did = tree(feats, pts, want_node_ids=True, want_data_ids=True)
-    assert int(did.max()) * D > 2 ** 31 and torch.equal(v, feats[did])
+    assert int(did.max()) * D * 4 > 2 ** 32 and torch.equal(v, feats[did])
     # (b) a band of a 1920x1080 view (rows 536..551, through the middle of the object) with depth
     cam_np = synth.synth_cameras(1)[0]
     cs = sv.renderer._make_camera_spec(cu(cam_np, dev), 1920, 1080, 1500.0, 1500.0)
@@ -220,3 +233,35 @@ def test_c5_shaped_scene_against_oracle(dev):
     assert frac_within_t(img.reshape(-1, D), cu(ref_img, dev)) >= 0.999
     assert float(((dep.reshape(-1) - cu(ref_dep, dev)).abs() <= 1e-5).float().mean()) >= 0.999
     assert float((img[..., -1] > 0).float().mean()) > 0.2
+
+
+def test_table_beyond_2_31_elements_against_oracle(dev):
+    """M*D > 2^31 float elements (depth-10 shell x 68 channels, 8.95 GB): every index computation must be 64-bit."""
+    L, D = 10, 68
+    tr = synth.synth_tree(L, "shell")
+    M = int(tr["M"])
+    assert M * D > 2 ** 31
+    g = torch.Generator(device=dev).manual_seed(1)
+    feats = torch.randn(M, D, device=dev, generator=g)
+    feats[:, -1] = torch.rand(M, device=dev, generator=g) * 10 - 2
+    tree = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=D, map_location=dev)
+    r = sv.VolumeRenderer(tree)
+    opt = r._get_options()
+    T = orc.Tree(tr["child"], tr["data"])
+    f_np = feats.cpu().numpy()
+    Q = 2048
+    o, d = synth.synth_rays(Q, seed=4)
+    g_np = np.random.default_rng(6).standard_normal((Q, D)).astype(np.float32)
+    ref_out = cu(orc.render_rays(T, f_np, o, d)[0], dev)
+    ref_grad = cu(orc.render_rays_backward(T, f_np, o, d, g_np), dev)
+    rs = sv.renderer._rays_spec_from_rays(sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev)))
+    spec = r._render_spec(feats, 1 << 21)                          # activated table + hit marks (one table pass)
+    out = C.volume_render(spec, rs, opt)
+    assert frac_within_t(out, ref_out) >= 0.999 and float((out - ref_out).abs().mean()) <= 1e-5
+    grad = C.volume_render_backward(spec, rs, opt, cu(g_np, dev), saved_out=out)
+    assert rel_l2_t(grad, ref_grad) <= 1e-4
+    hi = ref_grad[M - (M // 16):]                                  # rows whose element offsets exceed 2^31
+    assert int((hi.abs().amax(dim=1) > 0).sum()) > 1000 and rel_l2_t(grad[M - (M // 16):], hi) <= 1e-4
+    pts = cu(synth.voxel_centers(synth._occupied_keys(L, "shell")[-4096:], L), dev)
+    v, nid, did = tree(feats, pts, want_node_ids=True, want_data_ids=True)
+    assert int(did.max()) * D > 2 ** 31 and torch.equal(v, feats[did])
