@@ -117,6 +117,11 @@ SVOXB_API int svoxb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * in stream order on that same stream, after the work this library launched with the accelerator on other streams
  * (the four most recent distinct streams are remembered and waited for with an event each). */
 SVOXB_API int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* stream, svoxb_accel** out);
+/* With max_depth > 0 and depth <= 8 (two stages) NOTHING synchronises: the second stage is allocated for the most bricks
+ * the top grid can point to, brick counts and flags stay on the device (svoxb_accel_describe fetches them), and
+ * svoxb_accel_rebuild refills such an accelerator for another child/data of the same max_depth on the same stream
+ * without any allocation (SVOXB_EUNSUPPORTED if it cannot: create a new one) -- the per-frame rebuild path. */
+SVOXB_API int svoxb_accel_rebuild(svoxb_accel* accel, const svoxb_tree* tree, int max_depth, void* stream);
 SVOXB_API void svoxb_accel_destroy(svoxb_accel* accel);
 SVOXB_API int64_t svoxb_accel_bytes(const svoxb_accel* accel);
 SVOXB_API int svoxb_accel_describe(const svoxb_accel* accel, int* n_stages, int* bits /*[4]*/, int64_t* bricks /*[4]*/);
@@ -329,6 +334,20 @@ SVOXB_API int svoxb_build_octree_count(const float* pts, int64_t P, int32_t L, c
                              void* work, int64_t* n_nodes_host, void* stream);
 SVOXB_API int svoxb_build_octree_emit(int64_t P, int32_t L, const void* work, int64_t n_nodes,
                             int32_t* child, int32_t* data, int32_t* parent_depth, void* stream);
+
+/* The same build without a sort and without any host read-back, for depths L <= svoxb_build_dense_max_depth() (10):
+ * occupancy bitmaps + a pyramid of rank directories (svoxb_build_dense.cu; every kernel hand-written, no library
+ * primitives). The caller sizes child / data / parent_depth for a node CAPACITY `cap_nodes`; rows beyond the nodes
+ * actually needed are initialised as unreachable empty nodes. status_dev (device, optional) receives
+ * [0] = nodes needed, [1] = 1 if that exceeds cap_nodes (the tree is then truncated: do not use it). Same tensors as
+ * svoxb_build_octree_count/_emit, bit for bit, when the capacity suffices. `work`: 256-byte aligned device memory of
+ * svoxb_build_dense_work_bytes(L) bytes. Nothing synchronises: a whole frame (warp -> splat -> rebuild ->
+ * accelerator -> render) can be queued, or captured in a CUDA graph, in one go. */
+SVOXB_API int32_t svoxb_build_dense_max_depth(void);
+SVOXB_API size_t svoxb_build_dense_work_bytes(int32_t L);
+SVOXB_API int svoxb_build_dense(const float* pts, int64_t P, int32_t L, const float* offset, const float* scaling,
+                      void* work, int64_t cap_nodes, int32_t* child, int32_t* data, int32_t* parent_depth,
+                      int64_t* status_dev, void* stream);
 
 /* ---- multi-GPU exchange (no reference counterpart: the reference is single-GPU) --------------- */
 /* The path's one exchange step: the leaf-gradient table grad[M, D] -- the reference's

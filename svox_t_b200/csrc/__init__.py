@@ -68,6 +68,7 @@ SYMBOLS = {
     "svoxb_launch_count": (_I64, []),
     "svoxb_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3),
     "svoxb_accel_create": (ctypes.c_int, [_PT, ctypes.c_int, _VP, ctypes.POINTER(_VP)]),
+    "svoxb_accel_rebuild": (ctypes.c_int, [_VP, _PT, ctypes.c_int, _VP]),
     "svoxb_accel_destroy": (None, [_VP]),
     "svoxb_accel_bytes": (_I64, [_VP]),
     "svoxb_accel_describe": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
@@ -111,6 +112,9 @@ SYMBOLS = {
     "svoxb_build_work_bytes": (ctypes.c_size_t, [_I64, _I32]),
     "svoxb_build_octree_count": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP, _VP, ctypes.POINTER(_I64), _VP]),
     "svoxb_build_octree_emit": (ctypes.c_int, [_I64, _I32, _VP, _I64, _VP, _VP, _VP, _VP]),
+    "svoxb_build_dense_max_depth": (_I32, []),
+    "svoxb_build_dense_work_bytes": (ctypes.c_size_t, [_I32]),
+    "svoxb_build_dense": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _VP]),
 }
 
 _lib = None
@@ -344,6 +348,20 @@ class Accel:
         k = self._key
         return bool(self.handle) and k[0].matches(ts.child) and k[1].matches(ts.data) and \
             k[2:] == (int(ts.features.shape[0]), int(ts.n_internal))
+
+    def rebuild(self, tree_spec, max_depth):
+        """Refill this accelerator for another child/data of the same depth, in place (svoxb_accel_rebuild: no
+        allocation, no host synchronisation -- the per-frame path). False if it has to be created anew."""
+        if not self.handle:
+            return False
+        tree_spec._accel = None
+        with torch.cuda.device(tree_spec.child.device):
+            rc = self._lib.svoxb_accel_rebuild(self.handle, ctypes.byref(tree_spec._c()), int(max_depth), _stream())
+        if rc != 0:
+            return False
+        self._key = self._make_key(tree_spec)
+        self._marks_key = None
+        return True
 
     def mark_hits(self, features):
         """Refresh the per-leaf "sigma <= 0" marks for this exact (storage, version) of ``features``; the march then
@@ -787,30 +805,67 @@ def p2v(points, point_features, volume_corner, volume_size, n_voxels, kernel_rad
     return vox
 
 
-def build_octree(points, depth, offset, scaling):
+_BUILD_WORK = {}
+
+
+def build_octree(points, depth, offset, scaling, capacity=None, sort_based=False):
     """One-shot octree of finest level ``depth`` whose leaves at that level are the cells occupied by ``points``
     (svox_t_b200 extension; replaces depth-1 rounds of tree[pts].refine() + construct_tree, svox.py:488-560).
-    Returns (child[n,2,2,2], data[n,2,2,2,1], parent_depth[n,2]) int32, reference format; data = point index."""
+    Returns (child[n,2,2,2], data[n,2,2,2,1], parent_depth[n,2], status) int32, reference format; data = point index.
+
+    ``capacity=None``: tensors of exactly the nodes needed (one host read-back of the node count), status None.
+    ``capacity=n``: tensors of n nodes, NO host synchronisation; ``status`` is a device int64[2] = (nodes needed,
+    overflow flag) to be read whenever convenient -- the per-frame path. Depths beyond the bitmap build's limit (10),
+    or ``sort_based=True``, take the sort-based build (svoxb_build.cu)."""
     lib = load_library()
     _check_input(points, "points", torch.float32)
     _check_input(offset, "offset", torch.float32)
     _check_input(scaling, "scaling", torch.float32)
-    P, dev = points.shape[0], points.device
+    P, dev, depth = points.shape[0], points.device, int(depth)
     with torch.cuda.device(dev):
-        nbytes = lib.svoxb_build_work_bytes(P, int(depth))
-        if nbytes == 0:
-            raise RuntimeError("svox_t_b200.csrc.build_octree: depth/point count out of range")
-        work = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-        n = ctypes.c_int64(0)
-        _check(lib.svoxb_build_octree_count(_ptr(points), P, int(depth), _ptr(offset), _ptr(scaling), _ptr(work),
-                                            ctypes.byref(n), _stream()))
-        n = int(n.value)
-        child = torch.empty((n, 2, 2, 2), dtype=torch.int32, device=dev)
-        data = torch.empty((n, 2, 2, 2, 1), dtype=torch.int32, device=dev)
-        parent_depth = torch.empty((n, 2), dtype=torch.int32, device=dev)
-        _check(lib.svoxb_build_octree_emit(P, int(depth), _ptr(work), n, _ptr(child), _ptr(data), _ptr(parent_depth),
-                                           _stream()))
-    return child, data, parent_depth
+        if sort_based or depth > lib.svoxb_build_dense_max_depth():
+            if capacity is not None:
+                raise RuntimeError("the sort-based build returns exactly-sized tensors (capacity must be None)")
+            nbytes = lib.svoxb_build_work_bytes(P, depth)
+            if nbytes == 0:
+                raise RuntimeError("svox_t_b200.csrc.build_octree: depth/point count out of range")
+            work = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            n = ctypes.c_int64(0)
+            _check(lib.svoxb_build_octree_count(_ptr(points), P, depth, _ptr(offset), _ptr(scaling), _ptr(work),
+                                                ctypes.byref(n), _stream()))
+            n = int(n.value)
+            child = torch.empty((n, 2, 2, 2), dtype=torch.int32, device=dev)
+            data = torch.empty((n, 2, 2, 2, 1), dtype=torch.int32, device=dev)
+            parent_depth = torch.empty((n, 2), dtype=torch.int32, device=dev)
+            _check(lib.svoxb_build_octree_emit(P, depth, _ptr(work), n, _ptr(child), _ptr(data), _ptr(parent_depth),
+                                               _stream()))
+            return child, data, parent_depth, None
+        key = (dev, depth)
+        work = _BUILD_WORK.get(key)             # the bitmaps: reused from frame to frame (stream-ordered use)
+        if work is None:
+            work = _BUILD_WORK[key] = torch.empty((lib.svoxb_build_dense_work_bytes(depth),), dtype=torch.uint8, device=dev)
+        status = torch.zeros((2,), dtype=torch.int64, device=dev)
+
+        def run(cap):
+            child = torch.empty((cap, 2, 2, 2), dtype=torch.int32, device=dev)
+            data = torch.empty((cap, 2, 2, 2, 1), dtype=torch.int32, device=dev)
+            parent_depth = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+            _check(lib.svoxb_build_dense(_ptr(points), P, depth, _ptr(offset), _ptr(scaling), _ptr(work), cap, _ptr(child),
+                                         _ptr(data), _ptr(parent_depth), _ptr(status), _stream()))
+            return child, data, parent_depth
+        if capacity is not None:
+            return (*run(int(capacity)), status)
+        # exact size: a first pass with an upper bound ((depth-1) internal nodes per point + the root, and no more than
+        # a full tree), one read-back, then trim (views of the same storage)
+        bound = min(1 + P * max(depth - 1, 0), sum(8 ** l for l in range(depth)))
+        child, data, parent_depth = run(max(1, min(bound, 1 << 22)))
+        need, over = (int(v) for v in status.tolist())
+        if over:
+            child, data, parent_depth = run(need)
+        child, data, parent_depth = child[:need], data[:need], parent_depth[:need]
+        if child.untyped_storage().nbytes() > 2 * child.numel() * 4:      # do not pin the upper-bound allocation
+            child, data, parent_depth = child.clone(), data.clone(), parent_depth.clone()
+        return child, data, parent_depth, None
 
 
 def _unsupported(name, why):

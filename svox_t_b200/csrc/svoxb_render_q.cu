@@ -200,8 +200,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31;
     // this warp's 32 x DP partial outputs: accs[(j * V4 + h) * 32] = float4 h of this lane's block of ray RPI*j + q
-    float4* accs = reinterpret_cast<float4*>(smem_u32 + top_words + (COUNT ? blockDim.x : 0)) +
-                   (size_t)(threadIdx.x >> 5) * 32 * LPR * V4 + lane;
+    float4* accs = reinterpret_cast<float4*>(smem_u32 + top_words) + (size_t)(threadIdx.x >> 5) * 32 * LPR * V4 + lane;
     static_assert(AL || V4 == 1, "padded rows use 128-bit blocks");
     const int q = lane / LPR, c = lane % LPR;
     const int D = tr.D, DV = AL ? D / VEC : (D - 1 + VEC - 1) / VEC;
@@ -224,11 +223,10 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     Ray ray;
     float T = 1.0f, p_dt = 0.0f, p_t = 0.0f;
     int row = 0, p_idx = -1;
-    // COUNT: a ray's cost = loop iterations between its refill and its end. The loop counter is warp-uniform (a uniform
-    // register), the iteration a lane's ray started at waits in shared memory (one int per thread between the top grid
-    // and the accumulators): no 73rd vector register, no per-iteration work
-#define SVOXB_STEPS_S (reinterpret_cast<int*>(smem_u32 + top_words)[threadIdx.x])
-    [[maybe_unused]] int iter = 0;
+    // COUNT: the iteration counter takes the register of `row`, which waits in shared memory (one word per thread behind
+    // the accumulators) between the refill and the end of its ray -- the kernel keeps its 72 registers and 28 warps
+    [[maybe_unused]] int steps = 0;
+#define SVOXB_ROW_S (reinterpret_cast<int*>(smem_u32 + top_words + blockDim.x * (LPR * V4 * 4))[threadIdx.x])
     bool active = false, got_depth = false, trav_done = true;
     Queue qu{0, 0, false};
     unsigned need = FULL;
@@ -238,13 +236,12 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             const unsigned got = refill<IMAGE>(src, off, scl, counter, qu, need, lane, ray, row);
             if ((got >> lane) & 1u) {
                 active = true; trav_done = false; T = 1.0f; got_depth = false;
-                if constexpr (COUNT) SVOXB_STEPS_S = iter;
+                if constexpr (COUNT) { steps = 0; SVOXB_ROW_S = row; }
                 if (DEPTH) depth[row] = 0.0f;           // overwritten at the first hit, if any
             }
             need = 0;
         }
         if (__ballot_sync(FULL, active) == 0u) break;
-        if constexpr (COUNT) ++iter;
 
         // ---- S0: request the rows of batch 0 of the pending candidates. First thing in the iteration (a load left
         // in flight across the loop back-edge is waited for at the loop header); unconditional on purpose (a guarded
@@ -324,6 +321,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                 if (DEPTH) n_t = ray.t;
                 probe_end<ACCEL, 3>(tr, pb, ray, opt.step, n_idx, n_dt);
                 ray.t += n_dt;
+                if constexpr (COUNT) ++steps;
                 if (!(ray.t < ray.tmax)) trav_done = true;
             }
         }
@@ -333,6 +331,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
 
         const unsigned fm = __ballot_sync(FULL, fin != 0);
         if (fm) {
+            if constexpr (COUNT) row = SVOXB_ROW_S;
 #pragma unroll
             for (int j = 0; j < LPR; ++j) {
                 const unsigned gm = (fm >> ((RPI * j) & 31)) & low_mask<RPI>();
@@ -371,7 +370,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             }
             if (fin != 0) {
                 if constexpr (!AL) __stcs(out + (int64_t)row * D + (D - 1), 1.0f - T);   // opacity, by the owner lane
-                if constexpr (COUNT) src.steps_out[row] = iter - SVOXB_STEPS_S;                         // the backward's scheduling hint
+                if constexpr (COUNT) src.steps_out[row] = steps;                         // the backward's scheduling hint
                 active = false;
             }
             need = fm;

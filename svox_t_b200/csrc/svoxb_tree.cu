@@ -12,6 +12,7 @@
 #include <atomic>
 #include <mutex>
 #include <vector>
+#include <stdlib.h>
 #include "svoxb_common.cuh"
 
 namespace svoxb {
@@ -106,6 +107,11 @@ struct svoxb_accel {
                             // that a pass over the ROWS can refresh the hit marks (svoxb_prepare_step); 0xFFFFFFFF = none
     int rows_shared;        // a row is held by several leaf cells (children of a refined leaf inherit its row,
                             // svox.py:539-540) or a stage has >= 2^30 cells: the inverse map is not usable
+    int* d_flags;           // device scalars of the build: [1] overflow, [2 + s] bricks of stage s + 1, [6] rows shared
+    int lazy;               // built without read-backs: brick counts / flags are only known on the device (d_flags)
+    int inplace;            // built by the no-read-back path: svoxb_accel_rebuild can refill it without any allocation
+    int32_t* roots;         // no-read-back path: brick roots of stage 1 (kept for the next rebuild)
+    int64_t roots_cap, row_cap;
     cudaStream_t used[4];   // streams other than `stream` that kernels reading the cells were launched on (the most
     int n_used;             // recent four): svoxb_accel_destroy orders the release after their work
 };
@@ -198,8 +204,10 @@ __global__ void accel_stage_kernel(const int32_t* __restrict__ child, const int3
                                    const int32_t* __restrict__ roots, int64_t n_bricks, int bits, int base_depth,
                                    uint32_t* __restrict__ cells, int32_t* __restrict__ next_roots,
                                    int* __restrict__ next_count, int is_last, int* __restrict__ overflow,
-                                   uint32_t* __restrict__ row_cell, uint32_t stage_tag, int* __restrict__ rows_shared) {
+                                   uint32_t* __restrict__ row_cell, uint32_t stage_tag, int* __restrict__ rows_shared,
+                                   const int* __restrict__ n_bricks_dev) {
     const int64_t per = 1ll << (3 * bits);
+    if (n_bricks_dev) n_bricks = min(n_bricks, (int64_t)*n_bricks_dev);     // built without a read-back: the count is here
     const int64_t total = n_bricks * per;
     for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
          gid += (int64_t)gridDim.x * blockDim.x) {
@@ -242,7 +250,10 @@ __global__ void accel_stage_kernel(const int32_t* __restrict__ child, const int3
 // Hit marks: one thread per cell; leaf cells that hold a row get ACC_MISS iff !(sigma > 0) -- the negation of the
 // hit predicate of the march (rt_kernel.cu:279 with the default threshold, :382/:456 always), NaN included.
 __global__ void __launch_bounds__(256)
-accel_mark_kernel(uint32_t* __restrict__ cells, int64_t n, const float* __restrict__ features, int D) {
+accel_mark_kernel(uint32_t* __restrict__ cells, int64_t n, const float* __restrict__ features, int D,
+                  const int* __restrict__ n_bricks_dev, int64_t per_brick, const int* __restrict__ only_if) {
+    if (only_if && !*only_if) return;
+    if (n_bricks_dev) n = min(n, (int64_t)*n_bricks_dev * per_brick);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t cell = cells[i];
         if (cell & ACC_PTR) continue;
@@ -301,7 +312,8 @@ struct CellPtrs {
 // 0.144 -> 0.165 ms at C3.)
 __global__ void __launch_bounds__(256)
 prepare4_kernel(const float4* __restrict__ f, int64_t n4, int D4, float4* __restrict__ act, float4* __restrict__ zero,
-                const uint32_t* __restrict__ row_cell, CellPtrs cells) {
+                const uint32_t* __restrict__ row_cell, CellPtrs cells, const int* __restrict__ rows_shared_dev) {
+    if (rows_shared_dev && *rows_shared_dev) row_cell = nullptr;      // the pass over the cells marks instead
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool is_sigma = (int)(tid % D4) == D4 - 1;
@@ -544,19 +556,94 @@ extern "C" void svoxb_accel_destroy(svoxb_accel* a) {
     for (int s = 0; s < MAX_STAGES; ++s)
         if (a->cells[s]) cudaFreeAsync(a->cells[s], a->stream);
     if (a->row_cell) cudaFreeAsync(a->row_cell, a->stream);
+    if (a->d_flags) cudaFreeAsync(a->d_flags, a->stream);
+    if (a->roots) cudaFreeAsync(a->roots, a->stream);
     delete a;
 }
 
 extern "C" int64_t svoxb_accel_bytes(const svoxb_accel* a) { return a ? a->bytes : 0; }
 
-extern "C" int svoxb_accel_describe(const svoxb_accel* a, int* n_stages, int* bits, int64_t* bricks) {
-    SVOXB_REQUIRE(a != nullptr, "accel is NULL");
+// Built without read-backs: fetch the brick counts and flags now (synchronises the creation stream).
+static int accel_resolve(svoxb_accel* a) {
+    if (!a->lazy) return 0;
+    int h[8];
+    SVOXB_CUDA(cudaMemcpyAsync(h, a->d_flags, sizeof(h), cudaMemcpyDeviceToHost, a->stream));
+    SVOXB_CUDA(cudaStreamSynchronize(a->stream));
+    a->lazy = 0;
+    for (int s = 1; s < a->view.n_stages; ++s) a->n_bricks[s] = min(a->n_bricks[s], (int64_t)h[2 + s - 1]);
+    if (h[6]) a->rows_shared = 1;
+    SVOXB_REQUIRE(!h[1], "tree is deeper than max_depth=%d", a->view.lmax);
+    return 0;
+}
+
+extern "C" int svoxb_accel_describe(const svoxb_accel* a_in, int* n_stages, int* bits, int64_t* bricks) {
+    SVOXB_REQUIRE(a_in != nullptr, "accel is NULL");
+    svoxb_accel* a = const_cast<svoxb_accel*>(a_in);
+    if (int rc = accel_resolve(a)) return rc;
     if (n_stages) *n_stages = a->view.n_stages;
     for (int s = 0; s < MAX_STAGES; ++s) {
         if (bits) bits[s] = s < a->view.n_stages ? a->view.bits[s] : 0;
         if (bricks) bricks[s] = s < a->view.n_stages ? a->n_bricks[s] : 0;
     }
     return 0;
+}
+
+// (Re)fill an accelerator of at most two stages without any read-back: stage 1 is sized for the most bricks the top
+// grid can point to, its kernel takes the actual count from device memory, and the flags (overflow, shared rows) stay
+// on the device (svoxb_accel_describe fetches them on demand). Buffers already present and large enough are reused.
+static int accel_fill_nosync(svoxb_accel* a, const svoxb_tree* tree, cudaStream_t st) {
+    AccelView& v = a->view;
+    int rc;
+    a->M = tree->M; a->child = tree->child; a->data = tree->data;
+    a->lazy = 1; a->rows_shared = 0; a->marks_features = nullptr;
+    SVOXB_CUDA(cudaMemsetAsync(a->d_flags, 0, sizeof(int) * 8, st));
+    if (tree->M > a->row_cap) {
+        if (a->row_cell) { cudaFreeAsync(a->row_cell, st); a->bytes -= (int64_t)sizeof(uint32_t) * a->row_cap; a->row_cell = nullptr; }
+        if ((rc = pool_alloc((void**)&a->row_cell, sizeof(uint32_t) * (size_t)tree->M, st))) return rc;
+        a->row_cap = tree->M;
+        a->bytes += (int64_t)sizeof(uint32_t) * tree->M;
+    }
+    if (tree->M > 0) SVOXB_CUDA(cudaMemsetAsync(a->row_cell, 0xff, sizeof(uint32_t) * (size_t)tree->M, st));
+    if (v.n_stages > 1 && tree->n_internal > a->roots_cap) {
+        if (a->roots) cudaFreeAsync(a->roots, st);
+        a->roots = nullptr;
+        if ((rc = pool_alloc((void**)&a->roots, sizeof(int32_t) * (size_t)tree->n_internal, st))) return rc;
+        a->roots_cap = tree->n_internal;
+    }
+    int64_t bound = 1;
+    int base = 0;
+    for (int s = 0; s < v.n_stages; ++s) {
+        const int64_t words = bound << (3 * v.bits[s]);
+        if (!a->cells[s] || a->n_bricks[s] < bound) {
+            if (a->cells[s]) { cudaFreeAsync(a->cells[s], st); a->bytes -= (int64_t)sizeof(uint32_t) * (a->n_bricks[s] << (3 * v.bits[s])); }
+            a->cells[s] = nullptr;
+            if ((rc = pool_alloc((void**)&a->cells[s], sizeof(uint32_t) * (size_t)words, st))) return rc;
+            a->bytes += (int64_t)sizeof(uint32_t) * words;
+        }
+        a->n_bricks[s] = bound;
+        v.cells[s] = a->cells[s];
+        const int is_last = (s == v.n_stages - 1);
+        const int grid = (int)min((words + 255) / 256, (int64_t)sm_count() * 16);
+        accel_stage_kernel<<<grid, 256, 0, st>>>(tree->child, tree->data, tree->M, s == 0 ? nullptr : a->roots, bound, v.bits[s],
+                                                 base, a->cells[s], is_last ? nullptr : a->roots, a->d_flags + 2 + s, is_last,
+                                                 a->d_flags + 1, tree->M > 0 ? a->row_cell : nullptr, (uint32_t)s << 30,
+                                                 a->d_flags + 6, s == 0 ? nullptr : a->d_flags + 2 + s - 1);
+        count_launch();
+        if ((rc = check_cuda(cudaGetLastError(), "accel_stage_kernel launch"))) return rc;
+        bound = min((int64_t)1 << (3 * v.bits[s]), tree->n_internal);      // pointers a grid of 8^bits cells can hold
+        base += v.bits[s];
+    }
+    return 0;
+}
+
+extern "C" int svoxb_accel_rebuild(svoxb_accel* a, const svoxb_tree* tree, int max_depth, void* stream) {
+    SVOXB_REQUIRE(a != nullptr && tree != nullptr && tree->child && tree->data, "NULL argument");
+    if (!a->inplace || tree->N != 2 || max_depth != a->view.lmax || tree->M >= (int64_t)ACC_EMPTY ||
+        (cudaStream_t)stream != a->stream) {
+        set_error("this accelerator cannot be refilled in place for this tree (create a new one)");
+        return SVOXB_EUNSUPPORTED;
+    }
+    return accel_fill_nosync(a, tree, (cudaStream_t)stream);
 }
 
 extern "C" int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* stream, svoxb_accel** out) {
@@ -609,6 +696,16 @@ extern "C" int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* s
     int resolved = 0;
     for (int s = 0; s < v.n_stages; ++s) { resolved += v.bits[s]; v.shift[s] = lmax - resolved; }
 
+    // Known depth and at most two stages (depth <= 8): NO read-back (accel_fill_nosync). A per-frame rebuild then never
+    // synchronises, and svoxb_accel_rebuild refills the same allocations frame after frame.
+    if (max_depth > 0 && v.n_stages <= 2 && !getenv("SVOXB_ACCEL_SYNC")) {
+        a->d_flags = d_scalars;
+        a->inplace = 1;
+        rc = accel_fill_nosync(a, tree, st);
+        if (rc) { svoxb_accel_destroy(a); return rc; }
+        *out = a;
+        return 0;
+    }
     int32_t* roots[2] = {nullptr, nullptr};
     auto fail = [&](int code) {
         if (roots[0]) cudaFreeAsync(roots[0], st);
@@ -642,7 +739,7 @@ extern "C" int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* s
                                                      n_bricks, v.bits[s], base_depth, a->cells[s],
                                                      is_last ? nullptr : roots[s & 1], d_scalars + 2 + s, is_last,
                                                      d_scalars + 1, words < (1ll << 30) ? a->row_cell : nullptr,
-                                                     (uint32_t)s << 30, d_scalars + 6);
+                                                     (uint32_t)s << 30, d_scalars + 6, nullptr);
             count_launch();
             if ((rc = check_cuda(cudaGetLastError(), "accel_stage_kernel launch"))) return fail(rc);
         }
@@ -665,21 +762,29 @@ extern "C" int svoxb_accel_create(const svoxb_tree* tree, int max_depth, void* s
     return 0;
 }
 
-extern "C" int svoxb_accel_mark_hits(svoxb_accel* a, const float* features, int64_t M, int32_t D, void* stream) {
-    SVOXB_REQUIRE(a != nullptr, "accel is NULL");
-    SVOXB_REQUIRE(M == a->M, "accelerator was built for M=%lld, got M=%lld", (long long)a->M, (long long)M);
-    SVOXB_REQUIRE(D >= 2 && (features != nullptr || M == 0), "bad feature table");
-    cudaStream_t st = (cudaStream_t)stream;
+// The pass over the cells. `only_if_shared` (accelerators built without read-backs): the kernels run only if the
+// device-side flag says a row is held by several cells -- otherwise the table pass has marked through the inverse map.
+static int mark_cells(svoxb_accel* a, const float* features, int64_t M, int32_t D, bool only_if_shared, cudaStream_t st) {
     for (int s = 0; s < a->view.n_stages && M > 0; ++s) {
-        const int64_t words = a->n_bricks[s] << (3 * a->view.bits[s]);
+        const int64_t per = (int64_t)1 << (3 * a->view.bits[s]);
+        const int64_t words = a->n_bricks[s] * per;
         if (words <= 0) continue;
         const int grid = (int)min((words + 255) / 256, (int64_t)sm_count() * 16);
-        accel_mark_kernel<<<grid, 256, 0, st>>>(a->cells[s], words, features, D);
+        accel_mark_kernel<<<grid, 256, 0, st>>>(a->cells[s], words, features, D,
+                                                (a->lazy && s > 0) ? a->d_flags + 2 + s - 1 : nullptr, per,
+                                                only_if_shared ? a->d_flags + 6 : nullptr);
         count_launch();
         SVOXB_CUDA(cudaGetLastError());
     }
     a->marks_features = features; a->marks_D = D;
     return 0;
+}
+
+extern "C" int svoxb_accel_mark_hits(svoxb_accel* a, const float* features, int64_t M, int32_t D, void* stream) {
+    SVOXB_REQUIRE(a != nullptr, "accel is NULL");
+    SVOXB_REQUIRE(M == a->M, "accelerator was built for M=%lld, got M=%lld", (long long)a->M, (long long)M);
+    SVOXB_REQUIRE(D >= 2 && (features != nullptr || M == 0), "bad feature table");
+    return mark_cells(a, features, M, D, false, (cudaStream_t)stream);
 }
 
 extern "C" int svoxb_activate_features(const float* features, int64_t M, int32_t D, float* out, int32_t out_stride,
@@ -724,7 +829,7 @@ extern "C" int svoxb_prepare_step(svoxb_accel* a, const float* features, int64_t
         if (rc == 0 && zero_table) rc = check_cuda(cudaMemsetAsync(zero_table, 0, sizeof(float) * (size_t)M * D, st), "memset");
         return rc;
     }
-    const bool marks_here = a != nullptr && a->row_cell != nullptr && !a->rows_shared;
+    const bool marks_here = a != nullptr && a->row_cell != nullptr && !a->rows_shared;      // (lazy: decided on the device)
     CellPtrs cp;
     for (int s = 0; s < MAX_STAGES; ++s) cp.c[s] = a ? a->cells[s] : nullptr;
     const int64_t n4 = M * D / 4;
@@ -732,13 +837,14 @@ extern "C" int svoxb_prepare_step(svoxb_accel* a, const float* features, int64_t
     grid = (grid + D / 4 - 1) / (D / 4) * (D / 4);          // grid stride = a whole number of rows (see the kernel)
     prepare4_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(features), n4, D / 4,
                                           reinterpret_cast<float4*>(act), reinterpret_cast<float4*>(zero_table),
-                                          marks_here ? a->row_cell : nullptr, cp);
+                                          marks_here ? a->row_cell : nullptr, cp, (marks_here && a->lazy) ? a->d_flags + 6 : nullptr);
     count_launch();
     int rc = check_cuda(cudaGetLastError(), "prepare4_kernel launch");
     if (rc) return rc;
     if (a) {
-        if (marks_here) { a->marks_features = features; a->marks_D = D; }
-        else rc = svoxb_accel_mark_hits(a, features, M, D, stream);
+        if (!marks_here) rc = svoxb_accel_mark_hits(a, features, M, D, stream);
+        else if (a->lazy) rc = mark_cells(a, features, M, D, true, st);        // no-ops unless rows turn out to be shared
+        else { a->marks_features = features; a->marks_D = D; }
     }
     return rc;
 }

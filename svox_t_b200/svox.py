@@ -126,22 +126,54 @@ class N3Tree(nn.Module):
         tree._invalidate()
         return tree
 
-    def build_from_points(self, points, depth):
+    def build_from_points(self, points, depth, capacity=None):
         """Rebuild the whole tree in one shot: finest level ``depth``, one depth-``depth`` leaf per occupied cell,
         leaf row = index of the (last) point inside it. Equivalent to (depth-1) x ``tree[points].refine()`` followed by
-        ``construct_tree(points)`` (the per-frame rebuild of svox.py:160-161,488-560), isomorphic result."""
+        ``construct_tree(points)`` (the per-frame rebuild of svox.py:160-161,488-560), isomorphic result.
+
+        ``capacity`` (nodes): build into tensors of that many nodes WITHOUT any host synchronisation -- the per-frame
+        path. ``tree.filled`` then stays unknown until first asked for (one read-back, raising if the capacity was too
+        small); the march, the accelerator and the point query only need the tensors."""
         assert self.N == 2, "the one-shot builder is octree-only"
         if self._lock_tree_structure:
             raise RuntimeError("Tree locked")
         if depth - 1 > self.depth_limit:
             raise RuntimeError("depth exceeds depth_limit")
-        child, data, parent_depth = _C.build_octree(points, depth, self.offset, self.invradius)
+        child, data, parent_depth, status = _C.build_octree(points, depth, self.offset, self.invradius, capacity=capacity)
         self.child, self.data, self.parent_depth = child, data, parent_depth
-        self.filled = int(child.shape[0])
-        self._n_internal.fill_(self.filled)
+        if status is None:
+            self.filled = int(child.shape[0])
+            self._n_internal.fill_(self.filled)
+        else:
+            self._filled_pending = status            # resolved by the `filled` property on first use
+            self._n_internal.copy_(status[0].clamp(max=child.shape[0]))
         self._invalidate()
         self._known_depth = int(depth)     # spares the accelerator build its max-depth reduction + read-back
         return self
+
+    @property
+    def filled(self):
+        """Number of nodes in use. After a capacity-bounded rebuild the count lives on the device until asked for."""
+        st = self.__dict__.get("_filled_pending")
+        if st is not None:
+            need, over = (int(v) for v in st.tolist())
+            self.__dict__["_filled_pending"] = None
+            if over:
+                raise RuntimeError(f"build_from_points: capacity {self.child.shape[0]} is too small, {need} nodes needed")
+            self.__dict__["_filled"] = need
+        return self.__dict__.get("_filled", 0)
+
+    @filled.setter
+    def filled(self, v):
+        self.__dict__["_filled_pending"] = None
+        self.__dict__["_filled"] = int(v)
+
+    def _filled_bound(self):
+        """Nodes in use, or -- while the exact count is still on the device -- the capacity (an upper bound: rows beyond
+        the nodes in use are initialised, unreachable empty nodes)."""
+        if self.__dict__.get("_filled_pending") is not None:
+            return int(self.child.shape[0])
+        return self.filled
 
     def construct_tree(self, indices):
         """data[leaf(p_i)] = i: point i becomes the feature row of its leaf (svox.py:160-161)."""
@@ -303,7 +335,8 @@ class N3Tree(nn.Module):
         self._known_depth = 0
         self._ver += 1
         self._last_all_leaves = None
-        self._accel_cache = None
+        # a stale accelerator is kept as a shell: the per-frame rebuild refills its allocations in place
+        self._accel_stale, self._accel_cache = getattr(self, "_accel_cache", None) or getattr(self, "_accel_stale", None), None
 
     # ---- the bridge to the kernels ---------------------------------------------------------------------------
     def accel(self, features=None, max_depth=0):
@@ -314,8 +347,14 @@ class N3Tree(nn.Module):
         spec = self._spec(feats, _with_accel=False)
         acc = self._accel_cache
         if acc is None or not acc.matches(spec):
+            depth = max_depth or getattr(self, "_known_depth", 0)
+            stale, self._accel_stale = getattr(self, "_accel_stale", None), None
+            if stale is not None and depth and stale.rebuild(spec, depth):      # same allocations, no host sync
+                self._accel_cache = stale
+                return stale
+            del stale
             try:
-                acc = _C.Accel(spec, max_depth=max_depth or getattr(self, "_known_depth", 0))
+                acc = _C.Accel(spec, max_depth=depth)
             except RuntimeError as e:      # e.g. more rows than the packed index field can hold
                 warn(f"svox_t_b200: accelerator not built ({e}); walking the reference tensors instead")
                 acc = None
@@ -354,7 +393,7 @@ class N3Tree(nn.Module):
             if getattr(self, "_unit_xform", None) is None or self._unit_xform[0].device != dev:
                 self._unit_xform = (torch.zeros(3, device=dev), torch.ones(3, device=dev))
             ts.offset, ts.scaling = self._unit_xform
-        ts.n_internal = self.filled
+        ts.n_internal = self._filled_bound()
         ts._weight_accum = self._weight_accum
         ts.joint_features, ts.skinning_weights, ts.joint_index = joint_features, skinning_weights, joint_index
         ts.transformation_matrices = transformation_matrices

@@ -29,6 +29,8 @@ def frame(rebuild="oneshot"):
     ev[2].record()
     if rebuild == "oneshot":
         tree.build_from_points(warped, L)
+    elif rebuild == "oneshot_nosync":
+        tree.build_from_points(warped, L, capacity=CAP)
     else:
         t2 = sv.N3Tree(N=2, data_dim=D, init_reserve=300000, map_location=dev)
         for _ in range(L - 1):
@@ -47,7 +49,9 @@ def frame(rebuild="oneshot"):
     t["total"] = ev[0].elapsed_time(ev[5])
     return t, img, depth, grid
 
-for mode in ("oneshot", "refine_loop"):
+tree.build_from_points(sv.warp_vertices(Tm_t, p, w_t, ji_t)[0], L)
+CAP = int(tree.filled * 1.25)
+for mode in ("oneshot_nosync", "oneshot", "refine_loop"):
     for _ in range(3):
         t, img, depth, grid = frame(mode)
     ts = [frame(mode)[0] for _ in range(5)]

@@ -54,15 +54,4 @@ for Q in (1 << 20, 1 << 19, 1 << 18, 1 << 17, 1 << 16):
         base = (m[2] + m[4]) / Q
     eff = base * Q / (m[2] + m[4])
     extra = ""
-    if rs._cost is not None:            # forward again, ordered by the EXACT counts the first forward left: the bound of the estimate
-        os.environ["SVOXB_FWD_COST_INPUT"] = "1"
-        tt = []
-        for it in range(8):
-            a, b = ev(), ev()
-            a.record()
-            C._check(lib.svoxb_render_rays_fwd_cost(C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), C._ptr(d_t), Q,
-                                                    C.ctypes.byref(opt._c()), C._ptr(out), None, C._ptr(rs._cost), C._stream()))
-            b.record(); torch.cuda.synchronize(); tt.append(a.elapsed_time(b))
-        del os.environ["SVOXB_FWD_COST_INPUT"]
-        extra = f"   fwd ordered by exact counts {np.median(tt[2:]):.3f}"
     print(f"{Q:8d}  {m[0]:.3f} {m[1]:.3f}  {m[2]:.3f}  {m[3]:.3f}  {m[4]:.3f}  {m[5]:.3f}   {rate:7.1f}   march {eff:.2f}{extra}")
