@@ -515,7 +515,8 @@ def main():
                             "note": "same times, bytes of this design: <= 1 brick word per sample and stage instead of "
                                     "the reference's per-level child lookups + data-slot read; hit rows only (sigma "
                                     "arrives with the row; rows with sigma <= 0 are never fetched)"},
-        "roofline_tables": roof(b_tables, tables_ms, "svoxb::prepare4_kernel (activation + hit marks + grad zero-fill)"),
+        "roofline_tables": roof(b_tables, tables_ms, "svoxb::prepare4_kernel (activation + hit marks + grad zero-fill)",
+                                "prepare4_kernel"),
         "roofline_step": {"achieved": (b_fwd + b_bwd + b_tables) / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": (b_fwd + b_bwd + b_tables) / (ms_per_step * 1e-3) / 1e9 / peak,
                           "bytes_per_ray": (b_fwd + b_bwd) / Q,

@@ -2,16 +2,20 @@
 //
 // Same semantics as the scalar-lane kernels in svoxb_render.cu (reference: rt_kernel.cu:221-328 forward,
 // 330-496 backward, 781-834 depth); what changes is how a warp touches the feature table:
-//   * a feature row is covered by LPR lanes holding V4 float4 each (V4 = 2 when D % 8 == 0: Blackwell's 256-bit
-//     LDG, LPR = pow2ceil(D/8); else V4 = 1, LPR = pow2ceil(D/4)), so ONE load instruction fetches RPI = 32/LPR
-//     whole rows (8 rows = 1 KB at D = 32) and V4 red.global.add.v4.f32 per lane scatter RPI gradient rows;
+//   * a feature row is covered by LPR = pow2ceil(D/4) lanes holding one float4 each, so ONE load instruction fetches
+//     RPI = 32/LPR whole rows (4 rows = 512 B at D = 32) and one red.global.add.v4.f32 per lane scatters RPI gradient
+//     rows (256-bit row blocks, V4 = 2, exist behind SVOXB_WIDE_ROWS: fewer instructions but measured slower);
 //   * the lanes' traversal never reads the feature table: every leaf that holds a row becomes a candidate, the rows
 //     of the candidates are requested as a batch and each owner lane picks its sample's sigma out of the loaded row
-//     with one shuffle (the reference's separate 4-byte sigma gather and second dependent round trip are gone);
+//     with one shuffle (the reference's separate 4-byte sigma gather and second dependent round trip are gone); rows the
+//     accelerator's hit marks flag as sigma <= 0 never become candidates;
 //   * software pipelining: the brick lookup of sample i+1 is issued before, and consumed after, the compositing of
-//     sample i, whose rows were requested one step earlier -- both latencies hide behind arithmetic;
+//     sample i, whose rows were requested one step earlier -- both latencies hide behind arithmetic; for widths that
+//     take several batches per iteration (D > 32) the rows of batch b+1 are requested as soon as batch b has left the
+//     registers, ahead of the wait for the brick word;
 //   * the 32 x D partial outputs of a warp's rays (forward) / the staged grad_out rows (backward) live in shared
-//     memory, which keeps the kernels at 80 registers (3 CTAs per SM at D <= 32);
+//     memory: ONE CTA per SM, 28 warps at 72 registers (forward, D <= 32) or 24 warps at 80 (backward, depth
+//     variants); the shared-memory carve-out is set to what the CTA needs so that the rest of the 228 KB stays L1;
 //   * the per-hit channel dot product of the backward is reduced with a transposing butterfly over the LPR lanes
 //     of a row (LPR-1 shuffles for LPR hits instead of log2(LPR) per hit).
 // Lane layout: lane = q * LPR + c; q = which of the RPI rows of a load, c = channel block (channels VEC*c ..
@@ -176,8 +180,9 @@ __device__ __forceinline__ RowBlk<V4> load_row_block(const char* p, uint64_t pol
 //   S0   request the rows of batch 0 of the pending candidates (found in the PREVIOUS iteration)
 //   S1   probe_begin : next sample position, top-grid lookup in shared memory, brick lookup ISSUED
 //   S2.0 composite batch 0 (its rows have been in flight since S0)
-//   S3   probe_end   : brick word consumed -> new candidates, t advanced
-//   S2.b request rows of batch b, composite it            (b = 1 .. NBATCH-1; latency hides behind S3 / S2.b-1)
+//   S2.0'request the rows of batch 1 (the registers of batch 0 are free)
+//   S3   probe_end   : brick word consumed -> new candidates, t advanced   (the rows of batch 1 are in flight)
+//   S2.b composite batch b, request the rows of batch b+1  (b = 1 .. NBATCH-1)
 //   S4   flush finished rays, refill; the rows of batch 0 of the new candidates are requested first thing in the
 //        next iteration (S0), ahead of S1
 // AL (aligned): D % VEC == 0, rows are read in the caller's [M, D] layout (raw or activated). !AL: any other D -- the
@@ -271,14 +276,6 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
         float n_dt = 0.0f, n_t = 0.0f;
 #pragma unroll
         for (int b = 0; b < NBATCH; ++b) {
-            if (b > 0) {        // rows of batch b of the pending candidates (batch 0 was requested last iteration)
-#pragma unroll
-                for (int jj = 0; jj < NB; ++jj) {
-                    const int idx = max(__shfl_sync(FULL, p_idx, RPI * (b * NB + jj) + q), 0);
-                    SVOXB_DBG((int64_t)idx < max(tr.M, (int64_t)1));
-                    x[jj] = load_row_block<V4, false>(fbase + (size_t)(unsigned)idx * row_bytes, 0);
-                }
-            }
             // ---- S2.b: composite ---------------------------------------------------------------------------------
             const unsigned bm = NBATCH == 1 ? pm : (pm >> ((RPB * b) & 31)) & low_mask<RPB>();
             if (bm) {
@@ -314,6 +311,16 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                             accs[(j * V4 + h) * 32] = a;
                         }
                     }
+                }
+            }
+            // rows of batch b+1 of the pending candidates: requested as soon as batch b has left the registers, so that
+            // they are in flight while S3 waits for its brick word (batch 0 was requested at the top of the iteration)
+            if (b + 1 < NBATCH) {
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) {
+                    const int idx = max(__shfl_sync(FULL, p_idx, RPI * ((b + 1) * NB + jj) + q), 0);
+                    SVOXB_DBG((int64_t)idx < max(tr.M, (int64_t)1));
+                    x[jj] = load_row_block<V4, false>(fbase + (size_t)(unsigned)idx * row_bytes, 0);
                 }
             }
             // ---- S3 (once, after the first batch) ------------------------------------------------------------------
@@ -486,14 +493,6 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
         float n_dt = 0.0f;
 #pragma unroll
         for (int b = 0; b < NBATCH; ++b) {
-            if (b > 0) {
-#pragma unroll
-                for (int jj = 0; jj < NB; ++jj) {
-                    const int idx = max(__shfl_sync(FULL, p_idx, RPI * (b * NB + jj) + q), 0);
-                    SVOXB_DBG((int64_t)idx < max(tr.M, (int64_t)1));
-                    x[jj] = load_row_block<V4, SVOXB_BWD_HINTS != 0>(fbase + (size_t)(unsigned)idx * row_bytes, pol_first);
-                }
-            }
             // ---- S2.b: gradient of batch b of the pending candidates ------------------------------------------------
             const unsigned bm = NBATCH == 1 ? pm : (pm >> ((RPB * b) & 31)) & low_mask<RPB>();
             if (bm) {
@@ -567,6 +566,14 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                             }
                         }
                     }
+                }
+            }
+            if (b + 1 < NBATCH) {     // rows of batch b+1: in flight while S3 waits for its brick word (see the forward)
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) {
+                    const int idx = max(__shfl_sync(FULL, p_idx, RPI * ((b + 1) * NB + jj) + q), 0);
+                    SVOXB_DBG((int64_t)idx < max(tr.M, (int64_t)1));
+                    x[jj] = load_row_block<V4, SVOXB_BWD_HINTS != 0>(fbase + (size_t)(unsigned)idx * row_bytes, pol_first);
                 }
             }
             // ---- S3 (once, after the first batch) ------------------------------------------------------------------
