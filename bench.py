@@ -12,8 +12,8 @@ and the step ends with the sum of the leaf-gradient tables over the GPUs -- STRO
 `value` at N GPUs against `value` at 1 GPU is the speed-up of that one step. (The weak-scaling number of round 1,
 2^20 rays PER GPU, is kept under `extras.weak_scaling`.)
 
-A step on every rank: ONE table pass (activated table + hit marks + zero-fill of the gradient table; the features change
-every training step) -> forward march -> backward march -> exchange (svox_t_b200.dist.LeafGradExchange: one hand-written
+A step on every rank: ONE table pass (activated table + hit marks; the features change every training step) -> forward
+march (the zero-fill of the gradient table runs beside it on a second stream) -> backward march -> exchange (svox_t_b200.dist.LeafGradExchange: one hand-written
 kernel over symmetric memory, NVSwitch multicast reduction; NCCL all-reduce only as the fallback).
 
 One JSON line on stdout (rank 0). `value` = whole-job Mrays/s with inputs resident in HBM; `e2e` = the same step
@@ -262,9 +262,11 @@ def main():
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def refresh_tables():
-        # features change every training step: ONE pass over the rows (svoxb_prepare_step) rebuilds the activated table,
-        # refreshes the accelerator's hit marks and zero-fills the gradient table this step's backward reduces into
-        ts._act = C.Activated(feats, accel=accel, zero_table=xchg.table)
+        # features change every training step: ONE pass over the rows (svoxb_prepare_step) rebuilds the activated table and
+        # refreshes the accelerator's hit marks; the gradient table this step's backward reduces into is zero-filled
+        # on a side stream meanwhile
+        ts._act = C.Activated(feats, accel=accel)
+        xchg.zero_async()                              # side stream: overlaps the forward, the backward waits for it
 
     def fwd_bwd(o_s, d_s, g_s, grad, e=None, zero=False):
         rs = sv.renderer._rays_spec_from_rays(sv.Rays(o_s, d_s, d_s))
@@ -272,6 +274,8 @@ def main():
         if e: e[2].record()
         if zero:
             grad.zero_()
+        else:
+            xchg.wait_zero()
         C._check(lib.svoxb_render_rays_bwd_cost(C.ctypes.byref(ts._c()), C._ptr(o_s), C._ptr(d_s), C._ptr(d_s), o_s.shape[0],
                                                 C.ctypes.byref(bopt), C._ptr(g_s), C._ptr(out), C._ptr(grad),
                                                 C._ptr(rs._cost), C._stream()))   # rs._cost: short batches, else None
@@ -356,12 +360,10 @@ def main():
     # before the loss. The gradient lands in the exchange's symmetric table and is summed over the GPUs inside backward().
     h_o, h_d = torch.from_numpy(o[lo:hi].copy()).pin_memory(), torch.from_numpy(d[lo:hi].copy()).pin_memory()
     gen = torch.Generator().manual_seed(7 + rank)
-    h_rgb = torch.rand(Q, 3, generator=gen).pin_memory()
-    h_alpha = torch.rand(Q, generator=gen).pin_memory()
+    h_tgt = torch.rand(Q, 4, generator=gen).pin_memory()          # per ray: RGB target (3) + opacity target (1)
     fparam = feats.clone().requires_grad_(True)
     renderer.leaf_grad_exchange = xchg
-    bufs = [(torch.empty(Q, 3, device=dev), torch.empty(Q, 3, device=dev), torch.empty(Q, 3, device=dev),
-             torch.empty(Q, device=dev)) for _ in range(2)]
+    bufs = [(torch.empty(Q, 3, device=dev), torch.empty(Q, 3, device=dev), torch.empty(Q, 4, device=dev)) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
     free_ev = [None, None]
@@ -370,14 +372,16 @@ def main():
     for c in range(3):                                 # column 3 passes the opacity through
         w_dec[c * G3:(c + 1) * G3, c] = 1.0 / G3
     w_dec[D - 1, 3] = 1.0
+    # this rank's share of the global mean-squared error: 0.5 * mean over rays and RGB + 0.5 * mean over rays of opacity
+    w_col = torch.tensor([0.5 / (3 * Q_GLOBAL)] * 3 + [0.5 / Q_GLOBAL], device=dev)
 
     def upload(k):
-        bo, bd, brgb, ba = bufs[k & 1]
+        bo, bd, btgt = bufs[k & 1]
         with torch.cuda.stream(copy_stream):
             if free_ev[k & 1] is not None:
                 copy_stream.wait_event(free_ev[k & 1])          # the step that last used this buffer set is done
             bo.copy_(h_o, non_blocking=True); bd.copy_(h_d, non_blocking=True)
-            brgb.copy_(h_rgb, non_blocking=True); ba.copy_(h_alpha, non_blocking=True)
+            btgt.copy_(h_tgt, non_blocking=True)
             e = torch.cuda.Event(); e.record(copy_stream)
         return e
 
@@ -393,14 +397,13 @@ def main():
         for k in range(n_steps):
             nxt = upload(k + 1) if k + 1 < n_steps else None
             main_stream.wait_event(ready)
-            bo, bd, brgb, ba = bufs[k & 1]
+            bo, bd, btgt = bufs[k & 1]
             fparam.grad = None
             with torch.no_grad():
                 fparam.add_(0.0)                       # stands in for the optimiser update: features change every step
             out = renderer(fparam, sv.Rays(bo, bd, bd))
-            dec = out @ w_dec                          # [Q, 4]: decoded RGB + opacity
-            # this rank's share of the global mean-squared error (sum over its rays / global ray count)
-            loss = (0.5 / (3 * Q_GLOBAL)) * ((dec[:, :3] - brgb) ** 2).sum() + (0.5 / Q_GLOBAL) * ((dec[:, 3] - ba) ** 2).sum()
+            diff = out @ w_dec - btgt                  # [Q, 4]: decoded RGB + opacity against their targets
+            loss = (diff * diff * w_col).sum()
             loss.backward()                            # leaf gradients summed over the GPUs inside (leaf_grad_exchange)
             free_ev[k & 1] = torch.cuda.Event(); free_ev[k & 1].record(main_stream)
             h_loss[k & 1:(k & 1) + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # device -> host, this step's result
@@ -425,7 +428,7 @@ def main():
     e2e_ms = svd.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
     clocks = sampler.stop([(t_wall0, t_wall1), (t_wall2, t_wall3)]) if sampler else None
     grad_aliases = bool(fparam.grad is not None and fparam.grad.data_ptr() == xchg.table.data_ptr())
-    h2d_rank = int(h_o.numel() + h_d.numel() + h_rgb.numel() + h_alpha.numel()) * 4
+    h2d_rank = int(h_o.numel() + h_d.numel() + h_tgt.numel()) * 4
     e2e = {"value": Q_GLOBAL / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(svd.sum_over_ranks(h2d_rank, dev)), "d2h_bytes_per_step": 4 * world,
            "grad_is_exchange_table": grad_aliases, "losses_read": len(e2e_losses),
@@ -483,9 +486,9 @@ def main():
                     "sample": f"first {n} of the 2^20 rays, fwd+bwd once, C oracle with OpenMP over rays ({cpu_s:.2f} s)"}
     scale = Q / cnt["Q"]                               # one launch on this rank marches its Q-ray slice
     cnt_rank = {k: (v * scale if k != "Q" else Q) for k, v in cnt.items()}
-    # the zero-fill of grad[M, D] happens in the table pass (stage "tables"), not in the window that times the backward
+    # the zero-fill of grad[M, D] runs on a side stream beside the forward, not in the window that times the backward
     b_fwd, b_bwd = algorithmic_bytes(cnt_rank, D, M, zero_fill=False)
-    b_tables = 4 * M * D * 3 + 4 * M                   # features read, activated table + zeroed gradient table written
+    b_tables = 4 * M * D * 2 + 4 * M                   # features read, activated table written (+ the row -> cell map)
     stages = accel.describe()["stages"] if accel is not None else 1
     bd_fwd, bd_bwd = design_bytes(cnt_rank, D, M, stages, zero_fill=False)
     peak, peak_src = measured_peaks()
@@ -515,12 +518,12 @@ def main():
                             "note": "same times, bytes of this design: <= 1 brick word per sample and stage instead of "
                                     "the reference's per-level child lookups + data-slot read; hit rows only (sigma "
                                     "arrives with the row; rows with sigma <= 0 are never fetched)"},
-        "roofline_tables": roof(b_tables, tables_ms, "svoxb::prepare4_kernel (activation + hit marks + grad zero-fill)",
+        "roofline_tables": roof(b_tables, tables_ms, "svoxb::prepare4_kernel (activation + hit marks)",
                                 "prepare4_kernel"),
-        "roofline_step": {"achieved": (b_fwd + b_bwd + b_tables) / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                          "frac": (b_fwd + b_bwd + b_tables) / (ms_per_step * 1e-3) / 1e9 / peak,
+        "roofline_step": {"achieved": (b_fwd + b_bwd + b_tables + 4 * M * D) / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": (b_fwd + b_bwd + b_tables + 4 * M * D) / (ms_per_step * 1e-3) / 1e9 / peak,
                           "bytes_per_ray": (b_fwd + b_bwd) / Q,
-                          "note": "rank 0's march + table-pass bytes over the whole step time (exchange included)"},
+                          "note": "rank 0's march + table-pass + zero-fill bytes over the whole step time (exchange included)"},
         "stage_ms": {"tables": tables_ms, "fwd": fwd_ms, "bwd": bwd_ms, "exchange": xchg_ms,
                      "note": "rank 0, CUDA events on the launch stream, mean over the timed steps; the exchange includes "
                              "the wait for the slowest rank's backward"},

@@ -521,7 +521,7 @@ def _render_fwd(tree, rays, opt, want_depth):
         depth = fused if want_depth else depth
         rays._cost = None
         lo, hi = _order_range()
-        if ct.accel and lo <= Q <= hi:                      # short batch: the forward leaves the backward its ray costs
+        if ct.accel and lo <= Q <= hi:                      # short batch: the forward leaves the backward its completion list
             rays._cost = torch.empty((Q,), dtype=torch.int32, device=dev)
         _check(lib.svoxb_render_rays_fwd_cost(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), _ptr(rays.vdirs), Q,
                                               ctypes.byref(opt._c()), _ptr(out), _ptr(fused), _ptr(rays._cost), _stream()))

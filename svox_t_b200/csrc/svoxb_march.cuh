@@ -32,7 +32,9 @@ struct RaySource {
     float ndc_focal;
     int chunk;                     // explicit rays: rays fetched from the queue per atomic (0 = RAY_CHUNK)
     const int* order;              // explicit rays, optional: queue position -> ray index (svoxb_order.cu: longest first)
-    int* steps_out;                // explicit rays, optional [Q]: march iterations of each ray, written by the forward
+    int order_rev;                 // read `order` back to front (the forward's completion list: shortest rays first)
+    int* done_list;                // explicit rays, optional [Q]: the forward appends every ray's index when it ends
+    unsigned long long* done_count;    // ... at the position this counter hands out
 };
 
 struct ViewDir {
@@ -145,7 +147,7 @@ __device__ __forceinline__ unsigned refill(const RaySource& src, const float* of
                 }
             } else {
                 valid = true;
-                const int id = src.order ? __ldg(src.order + pos) : pos;
+                const int id = src.order ? __ldg(src.order + (src.order_rev ? (int)src.total - 1 - pos : pos)) : pos;
                 const float* o = src.origins + (int64_t)id * 3;
                 const float* d = src.dirs + (int64_t)id * 3;
                 ox = __ldg(o); oy = __ldg(o + 1); oz = __ldg(o + 2);
@@ -262,8 +264,9 @@ __device__ __forceinline__ void probe_begin(const TreeArgs& tr, const uint32_t* 
 
 // Trees deeper than two stages (depth > 8): consume the stage-1 word and ISSUE the stage-2 lookup. Stage 1 is small
 // (L2-resident); stage 2 of a depth-10 scene is hundreds of MB, its lookup goes to DRAM -- called between the row
-// requests and the compositing, that latency hides behind the compositing instead of being waited for in probe_end
-// (C5, 2^20 random rays: forward 5.6 -> see profiles/NOTES_r02.md). A no-op (no wait on the stage-1 word) for <= 2 stages.
+// requests and the compositing, so that it is in flight during the compositing instead of being waited for in
+// probe_end (measured on the C5 scene: no change, 5.60 vs 5.57 ms -- the lookup is not the exposed latency there; kept
+// because it costs nothing). A no-op (no wait on the stage-1 word) for <= 2 stages.
 template <bool ACCEL>
 __device__ __forceinline__ void probe_mid(const TreeArgs& tr, Probe& pb) {
     if (ACCEL) {
@@ -283,12 +286,13 @@ template <bool ACCEL, int FIRST = 2>
 __device__ __forceinline__ void probe_end(const TreeArgs& tr, const Probe& pb, const Ray& r, float step,
                                           int& idx, float& delta_t) {
     float rx, ry, rz, smin, smax;
+    const float px = pb.px, py = pb.py, pz = pb.pz;
     if (ACCEL) {
         const AccelView& a = tr.acc;
         uint32_t cell = pb.cell;
         if (cell & ACC_PTR) {                                   // trees deeper than two stages (depth > 8)
             const float s = __int_as_float((127 + a.lmax) << 23);
-            const int Ix = (int)(pb.px * s), Iy = (int)(pb.py * s), Iz = (int)(pb.pz * s);
+            const int Ix = (int)(px * s), Iy = (int)(py * s), Iz = (int)(pz * s);
 #pragma unroll
             for (int st = FIRST; st < MAX_STAGES; ++st) {
                 if (cell & ACC_PTR) {
@@ -304,13 +308,13 @@ __device__ __forceinline__ void probe_end(const TreeArgs& tr, const Probe& pb, c
         // rows marked "sigma <= 0" are not candidates: no row fetch, exactly what the hit predicate would decide
         idx = (ci == ACC_EMPTY || (cell & tr.acc_miss_mask)) ? -1 : (int)ci;
         const float sc = __int_as_float((127 + d) << 23);
-        const float qx = pb.px * sc, qy = pb.py * sc, qz = pb.pz * sc;
+        const float qx = px * sc, qy = py * sc, qz = pz * sc;
         rx = qx - floorf(qx); ry = qy - floorf(qy); rz = qz - floorf(qz);
         dda_unit(rx, ry, rz, r.ix, r.iy, r.iz, smin, smax);
         delta_t = (smax - smin) * __int_as_float((127 - d) << 23) + step;
     } else {
         float cube;
-        const int64_t slot = descend_ref(tr.child, tr.N, pb.px, pb.py, pb.pz, rx, ry, rz, cube);
+        const int64_t slot = descend_ref(tr.child, tr.N, px, py, pz, rx, ry, rz, cube);
         const int di = __ldg(tr.data + slot);
         idx = ((int64_t)di >= tr.M || di < 0) ? -1 : di;
         dda_unit(rx, ry, rz, r.ix, r.iy, r.iz, smin, smax);
@@ -340,12 +344,12 @@ static int persistent_grid(Kern kern, size_t smem, int64_t queue_len, int& grid,
 
 // Quad-lane kernels (svoxb_render_q.cu): D % 4 == 0 (4 <= D <= 128), or any D <= 128 with the padded activated table.
 bool quad_supported(const TreeArgs& tr);
-// svoxb_order.cu: longest-first order of a short explicit ray batch for the backward, from the forward's exact per-ray
-// iteration counts (stream-ordered scratch, released by the caller)
+// svoxb_order.cu: longest-first order of a short explicit ray batch for the backward = the forward's completion list
+// read back to front
 bool want_ray_order(const TreeArgs& tr, int64_t Q);
 int64_t ray_order_max_rays();
 int64_t ray_order_min_rays();
-int build_ray_order(const int* cost, int64_t Q, int** order, cudaStream_t st);
+int fill_reverse_identity(int* list, int64_t Q, cudaStream_t st);
 int launch_fwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, float* out,
                     float* depth, cudaStream_t st);
 int launch_bwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, const float* grad_out,

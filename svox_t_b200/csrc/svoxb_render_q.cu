@@ -190,9 +190,21 @@ __device__ __forceinline__ RowBlk<V4> load_row_block(const char* p, uint64_t pol
 // multiple of 4 floats: 16-byte aligned rows, D = 33 is served like D = 32), sigma comes from the compact sigma[M]
 // array next to it (one 4-byte gather per candidate, L2-resident), and the output rows / gradient rows of the
 // caller's unaligned [M, D] layout are written channel by channel.
-// COUNT: also write the number of march iterations of every ray (RaySource::steps_out) -- the exact per-ray cost the
-// backward over the same batch is ordered by (svoxb_order.cu). One more live register per lane: its own instantiation
+// COUNT: also append every ray's index to a list when it ends (RaySource::done_list). With about one ray per lane all
+// rays start together, so the list is sorted by march length; the backward over the same batch reads it back to front --
+// longest ray first (svoxb_order.cu). Nothing is carried through the loop: 72 registers, 28 warps, like the plain kernel. One more live register per lane: its own instantiation
 // with the 80-register budget, used for short batches only (where the order matters and the 28th warp does not).
+// A real call on purpose: inlined, these few instructions perturb the register allocation of the whole 72-register loop
+// into spilling (16-24 bytes, reloaded every iteration); as a call the live registers are saved around this cold site only.
+__device__ __noinline__ void append_done(int* __restrict__ list, unsigned long long* __restrict__ count, unsigned fm,
+                                         bool mine, int row) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(fm));
+    base = __shfl_sync(FULL, base, 0);
+    if (mine) list[base + __popc(fm & ((1u << lane) - 1u))] = row;
+}
+
 template <int LPR, int V4, bool ACCEL, bool IMAGE, bool DEPTH, bool AL, bool COUNT = false>
 __global__ void __launch_bounds__(((DEPTH || !AL) ? Quad<LPR, V4>::THREADS : Quad<LPR, V4>::FWD_THREADS), 1)
 march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ out, float* __restrict__ depth,
@@ -228,10 +240,6 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     Ray ray;
     float T = 1.0f, p_dt = 0.0f, p_t = 0.0f;
     int row = 0, p_idx = -1;
-    // COUNT: the iteration counter takes the register of `row`, which waits in shared memory (one word per thread behind
-    // the accumulators) between the refill and the end of its ray -- the kernel keeps its 72 registers and 28 warps
-    [[maybe_unused]] int steps = 0;
-#define SVOXB_ROW_S (reinterpret_cast<int*>(smem_u32 + top_words + blockDim.x * (LPR * V4 * 4))[threadIdx.x])
     bool active = false, got_depth = false, trav_done = true;
     Queue qu{0, 0, false};
     unsigned need = FULL;
@@ -241,7 +249,6 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             const unsigned got = refill<IMAGE>(src, off, scl, counter, qu, need, lane, ray, row);
             if ((got >> lane) & 1u) {
                 active = true; trav_done = false; T = 1.0f; got_depth = false;
-                if constexpr (COUNT) { steps = 0; SVOXB_ROW_S = row; }
                 if (DEPTH) depth[row] = 0.0f;           // overwritten at the first hit, if any
             }
             need = 0;
@@ -328,7 +335,6 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                 if (DEPTH) n_t = ray.t;
                 probe_end<ACCEL, 3>(tr, pb, ray, opt.step, n_idx, n_dt);
                 ray.t += n_dt;
-                if constexpr (COUNT) ++steps;
                 if (!(ray.t < ray.tmax)) trav_done = true;
             }
         }
@@ -338,7 +344,6 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
 
         const unsigned fm = __ballot_sync(FULL, fin != 0);
         if (fm) {
-            if constexpr (COUNT) row = SVOXB_ROW_S;
 #pragma unroll
             for (int j = 0; j < LPR; ++j) {
                 const unsigned gm = (fm >> ((RPI * j) & 31)) & low_mask<RPI>();
@@ -375,9 +380,10 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                     }
                 }
             }
+            // completion list: the rays that end now take the next popc(fm) positions
+            if constexpr (COUNT) append_done(src.done_list, src.done_count, fm, fin != 0, row);
             if (fin != 0) {
                 if constexpr (!AL) __stcs(out + (int64_t)row * D + (D - 1), 1.0f - T);   // opacity, by the owner lane
-                if constexpr (COUNT) src.steps_out[row] = steps;                         // the backward's scheduling hint
                 active = false;
             }
             need = fm;
@@ -642,17 +648,21 @@ static int launch_fwd_q(const TreeArgs& tr, const RaySource& src_in, const March
     RaySource src = src_in;
     src.chunk = chunk_for(src, IMAGE);
     bool count = false;
-    if constexpr (ACCEL && !IMAGE && AL) count = src.steps_out != nullptr && !depth;
+    if constexpr (ACCEL && !IMAGE && AL) count = src.done_list != nullptr && !depth;
     const int threads = threads_for((depth || !AL) ? G::THREADS : G::FWD_THREADS, src.total, src.chunk, "SVOXB_FWD_THREADS_CAP");
-    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * (threads / 32) * 32 * LPR * V4 +
-                        (count ? sizeof(int) * threads : 0);
+    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * (threads / 32) * 32 * LPR * V4;
     void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
     if (depth) kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, true, AL>;
     else kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, false, AL>;
     if constexpr (ACCEL && !IMAGE && AL) {
         if (count) kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, false, AL, true>;
     }
-    if (!count) src.steps_out = nullptr;
+    if (count) {
+        src.done_count = work_counter(st);
+        if (!src.done_count) return SVOXB_ECUDA;
+    } else {
+        src.done_list = nullptr;
+    }
     int grid = 0;
     int rc = persistent_grid(kern, smem, src.total, grid, threads, carveout_kb(smem), src.chunk);
     if (rc) return rc;

@@ -170,18 +170,44 @@ class LeafGradExchange:
     def zeroed_table(self):
         """The [M, D] table, zero-filled in stream order (the reference's zeros_like(features), rt_kernel.cu:1415)."""
         self._zeroed_for = None
+        self.wait_zero()
         self.table.zero_()
         return self.table
+
+    def zero_async(self, features=None):
+        """Zero-fill the table on a side stream, ordered after everything the current stream has queued so far (the last
+        reader of the previous step's gradient) and overlapping whatever it queues next -- the forward march, which never
+        touches the table and leaves most of the DRAM bandwidth idle. ``table_for_backward`` makes the current stream
+        wait for the fill. ``features``: what the coming backward will be for (see ``table_for_backward``)."""
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._zero_done = torch.cuda.Event()
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self._side.wait_event(ready)
+        with torch.cuda.stream(self._side):
+            self.table.zero_()
+            self._zero_done.record(self._side)
+        self._zero_pending = True
+        self._zeroed_for = self._C._TensorIdentity(features) if features is not None else None
 
     def note_zeroed(self, features):
         """The table has just been zero-filled (in stream order) by the per-step table pass of the forward over
         ``features`` (csrc.Activated): the next backward for exactly these features reduces into it as it is."""
         self._zeroed_for = self._C._TensorIdentity(features)
 
+    def wait_zero(self):
+        """Make the current stream wait for a pending ``zero_async``."""
+        if getattr(self, "_zero_pending", False):
+            torch.cuda.current_stream(self.device).wait_event(self._zero_done)
+            self._zero_pending = False
+
     def table_for_backward(self, features):
-        """The zero-filled table a backward reduces into: as left by the forward's table pass when that pass zeroed it
-        for these features and nothing has used it since, else zero-filled now. One backward per zero-fill."""
+        """The zero-filled table a backward reduces into: as left by the forward's table pass / ``zero_async`` when that
+        zeroed it for these features and nothing has used it since, else zero-filled now. One backward per zero-fill."""
         key, self._zeroed_for = getattr(self, "_zeroed_for", None), None
+        self.wait_zero()
         if key is not None and key.matches(features):
             return self.table
         return self.zeroed_table()

@@ -363,14 +363,13 @@ class N3Tree(nn.Module):
 
     def activated(self, features, accel=None, grad_exchange=None):
         """Table of ``features`` with the sigmoid applied once per row (cached until ``features`` changes). The pass that
-        builds it also refreshes ``accel``'s hit marks and zero-fills ``grad_exchange``'s gradient table for the
-        backward of the step that starts with these features (csrc.Activated)."""
+        builds it also refreshes ``accel``'s hit marks (csrc.Activated); ``grad_exchange``'s gradient table is zero-filled
+        on a side stream for the backward of the step that starts with these features (it overlaps the forward)."""
         act = getattr(self, "_act_cache", None)
         if act is None or not act.matches(features):
-            zero = grad_exchange.table if grad_exchange is not None else None
-            act = _C.Activated(features, accel=accel, zero_table=zero)
-            if grad_exchange is not None:
-                grad_exchange.note_zeroed(features)
+            act = _C.Activated(features, accel=accel)
+            if grad_exchange is not None:          # the gradient table of this step's backward: zeroed beside the forward
+                grad_exchange.zero_async(features)
             self._act_cache = act
         elif accel is not None:
             accel.mark_hits(features)

@@ -1006,3 +1006,46 @@ def test_sg_asg_rgb_fast_path_vs_oracle(dev, fmt, B):
             assert np.abs(o_ref[:, :3]).max() > 0.05
             assert frac_within(out.detach().cpu().numpy(), o_ref) >= 0.999, (accel, with_tm)
             assert rel_l2(feats.grad.cpu().numpy(), g_ref) <= 1e-4, (accel, with_tm)
+
+
+def test_short_batch_completion_list_orders_the_backward(dev):
+    """One GPU's share of a batch split over 8 GPUs (131 072 rays): the forward keeps a completion list, the backward
+    marches it back to front. The list is a permutation; outputs and gradients equal the unordered calls."""
+    lib = C.load_library()
+    tr = synth.synth_tree(6, "ball")
+    D, Q = 32, 131072
+    assert lib.svoxb_ray_order_min_rays() <= Q <= lib.svoxb_ray_order_max_rays()
+    tree = make_tree(tr, D, dev)
+    feats = cu(synth.synth_features(tr["M"], D), dev)
+    o, d = synth.synth_rays(Q, seed=21)
+    o_t, d_t = cu(o, dev), cu(d, dev)
+    g = torch.randn(Q, D, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    r = sv.VolumeRenderer(tree)
+    ts = r._render_spec(feats, Q)
+    rs = sv.renderer._rays_spec_from_rays(sv.Rays(o_t, d_t, d_t))
+    opt = r._get_options()
+    out = C.volume_render(ts, rs, opt)                             # leaves rs._cost = the completion list
+    assert rs._cost is not None
+    assert torch.equal(torch.sort(rs._cost.long())[0], torch.arange(Q, device=dev))
+    grad = C.volume_render_backward(ts, rs, opt, g, saved_out=out)
+    # the plain C-ABI calls (no list)
+    out2 = torch.empty_like(out)
+    C._check(lib.svoxb_render_rays_fwd(C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), C._ptr(d_t), Q,
+                                       C.ctypes.byref(opt._c()), C._ptr(out2), None, C._stream()))
+    grad2 = torch.zeros_like(feats)
+    C._check(lib.svoxb_render_rays_bwd(C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), C._ptr(d_t), Q,
+                                       C.ctypes.byref(opt._c(sigma_thresh=0.0, stop_thresh=-1.0)), C._ptr(g), C._ptr(out2),
+                                       C._ptr(grad2), C._stream()))
+    assert torch.equal(out, out2)
+    assert float((grad - grad2).norm() / grad2.norm()) < 1e-6
+    # the list is (nearly) sorted by march length: its first tenth is much shorter than its last tenth
+    T = orc.Tree(tr["child"], tr["data"])
+    order = rs._cost.cpu().numpy()
+    first, last = order[: Q // 10][::64], order[-(Q // 10):][::64]
+    s_first = orc.render_rays(T, feats.cpu().numpy(), o[first], d[first], want_counters=True)[2]["S"] / len(first)
+    s_last = orc.render_rays(T, feats.cpu().numpy(), o[last], d[last], want_counters=True)[2]["S"] / len(last)
+    assert s_last > 1.5 * s_first
+    # a forward that keeps no list (fused depth) leaves the caller's order
+    rs2 = sv.renderer._rays_spec_from_rays(sv.Rays(o_t, d_t, d_t))
+    C.volume_render_with_depth(ts, rs2, opt)
+    assert torch.equal(rs2._cost.long(), torch.arange(Q - 1, -1, -1, device=dev))
