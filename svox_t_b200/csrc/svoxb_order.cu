@@ -16,6 +16,9 @@
 // extra kernel, and nothing carried through the forward's loop (an iteration counter per lane pushed its 72-register
 // instantiation into spilling: 0.45 -> 0.53 ms). The forward itself is never ordered: an exact order gains nothing
 // there (every ray has its own lane and the kernel ends with the longest ray either way).
+// Batches of more rays than the forward has lanes are marched in K launches of equal consecutive ranges (each keeps its
+// own list, every ray of a launch starts at once); the backward interleaves the K lists from their tails, which is
+// close to the globally sorted order (256 k rays, K = 2: backward 1.73 -> see profiles/NOTES_r02.md).
 // A forward that cannot keep the list (view-dependent formats, fused depth, odd widths) leaves the identity order.
 #include <stdlib.h>
 #include "svoxb_march.cuh"
@@ -33,15 +36,22 @@ bool want_ray_order(const TreeArgs& tr, int64_t Q) {
     return tr.use_accel && Q >= ray_order_min_rays() && Q <= ray_order_max_rays();
 }
 
-// list[i] = Q-1-i: read back to front this is the caller's own order -- what the backward sees when the forward that
-// ran could not keep a completion list (a counting forward overwrites every entry: each ray ends exactly once).
-__global__ void __launch_bounds__(256) reverse_identity_kernel(int* __restrict__ list, int Q) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Q; i += gridDim.x * blockDim.x) list[i] = Q - 1 - i;
+// Per range of the balanced K-way split: list[a + i] = len-1-i. Read back to front (and interleaved) this is close to
+// the caller's own order -- what the backward sees when the forward that ran could not keep completion lists (a
+// list-keeping forward overwrites every entry: each ray ends exactly once).
+__global__ void __launch_bounds__(256) reverse_identity_kernel(int* __restrict__ list, int Q, int K) {
+    const int base = Q / K, rem = Q % K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Q; i += gridDim.x * blockDim.x) {
+        int k = rem ? min(i / (base + 1), rem) : 0;                 // ranges 0 .. rem-1 hold base+1 entries
+        if (k == rem) k = rem + (i - rem * (base + 1)) / max(base, 1);
+        const int a = k * base + min(k, rem), len = base + (k < rem ? 1 : 0);
+        list[i] = len - 1 - (i - a);
+    }
 }
 
-int fill_reverse_identity(int* list, int64_t Q, cudaStream_t st) {
+int fill_reverse_identity(int* list, int64_t Q, int K, cudaStream_t st) {
     const int grid = (int)min((Q + 255) / 256, (int64_t)sm_count() * 8);
-    reverse_identity_kernel<<<grid, 256, 0, st>>>(list, (int)Q);
+    reverse_identity_kernel<<<grid, 256, 0, st>>>(list, (int)Q, K);
     count_launch();
     return check_cuda(cudaGetLastError(), "reverse_identity_kernel launch");
 }

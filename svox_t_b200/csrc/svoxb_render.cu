@@ -493,7 +493,7 @@ static int render_rays_fwd_impl(const svoxb_tree* tree, const float* origins, co
     cudaStream_t st = (cudaStream_t)stream;
     if (ray_cost != nullptr && want_ray_order(tr, Q)) {
         // identity order first; a forward kernel that keeps the completion list overwrites every entry
-        rc = fill_reverse_identity(ray_cost, Q, st); if (rc) return rc;
+        rc = fill_reverse_identity(ray_cost, Q, count_chunks(tr, Q, false), st); if (rc) return rc;
         src.done_list = ray_cost;
     }
     if (opt->format != SVOXB_FORMAT_RGBA) rc = fmt_render_fwd(tree, tr, src, m, opt, false, out, st);
@@ -533,6 +533,7 @@ static int render_rays_bwd_impl(const svoxb_tree* tree, const float* origins, co
     if (ray_cost != nullptr && want_ray_order(tr, Q)) {     // the forward's completion list, longest ray = last entry
         src.order = ray_cost;
         src.order_rev = 1;
+        src.order_k = count_chunks(tr, Q, false);
     }
     if (opt->format != SVOXB_FORMAT_RGBA) rc = fmt_render_bwd(tree, tr, src, m, opt, false, grad_out, saved_out, grad_features, st);
     else rc = dispatch_bwd<false>(tr, src, m, grad_out, saved_out, grad_features, st);

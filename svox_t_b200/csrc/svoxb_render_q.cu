@@ -635,16 +635,48 @@ static int chunk_for(const RaySource& src, bool image) {
     return (forced >= 1 && forced <= 64) ? forced : RAY_CHUNK;
 }
 
+
 static int pow2ceil(int n) {
     int l = 1;
     while (l < n) l <<= 1;
     return l;
 }
 
+// Lanes of the list-keeping forward (one CTA per SM): a launch of at most this many rays starts them all at once, so
+// its completion list is sorted by march length. Mirrors Quad<>::FWD_THREADS.
+static int64_t fwd_list_lanes(int D) {
+    const int dp = 4 * pow2ceil((D + 3) / 4);
+    const int threads = dp <= 32 ? SVOXB_FWD_THREADS32 : (dp <= 64 ? SVOXB_THREADS64 : SVOXB_THREADS128);
+    return (int64_t)sm_count() * threads;
+}
+
+int count_chunks(const TreeArgs& tr, int64_t Q, bool depth) {
+    if (!(tr.use_accel && tr.D % 4 == 0 && tr.D >= 4 && tr.D <= 128 && !depth)) return 1;    // no list is kept: one range
+    return (int)max((int64_t)1, (Q + fwd_list_lanes(tr.D) - 1) / fwd_list_lanes(tr.D));
+}
+
 template <int LPR, int V4, bool ACCEL, bool IMAGE, bool AL>
 static int launch_fwd_q(const TreeArgs& tr, const RaySource& src_in, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
     using G = Quad<LPR, V4>;
+    if constexpr (ACCEL && !IMAGE && AL) {
+        // list-keeping forward over more rays than lanes: K launches over balanced consecutive ranges (svoxb_order.cu)
+        const int K = (src_in.done_list != nullptr && !depth) ? count_chunks(tr, src_in.total, false) : 1;
+        if (K > 1) {
+            const int64_t base = src_in.total / K, rem = src_in.total % K;
+            for (int k = 0; k < K; ++k) {
+                const int64_t a = k * base + min((int64_t)k, rem), len = base + (k < rem ? 1 : 0);
+                RaySource sub = src_in;
+                sub.origins += 3 * a; sub.dirs += 3 * a;
+                if (sub.vdirs) sub.vdirs += 3 * a;
+                sub.done_list += a;
+                sub.total = len;
+                const int rc = launch_fwd_q<LPR, V4, ACCEL, IMAGE, AL>(tr, sub, m, out + a * tr.D, nullptr, st);
+                if (rc) return rc;
+            }
+            return 0;
+        }
+    }
     RaySource src = src_in;
     src.chunk = chunk_for(src, IMAGE);
     bool count = false;

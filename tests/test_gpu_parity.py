@@ -1049,3 +1049,24 @@ def test_short_batch_completion_list_orders_the_backward(dev):
     rs2 = sv.renderer._rays_spec_from_rays(sv.Rays(o_t, d_t, d_t))
     C.volume_render_with_depth(ts, rs2, opt)
     assert torch.equal(rs2._cost.long(), torch.arange(Q - 1, -1, -1, device=dev))
+    # more rays than the forward has lanes (a 4-GPU share, 262 144 rays): K = 2 launches, two lists, interleaved
+    Q2 = 262144
+    if Q2 <= lib.svoxb_ray_order_max_rays():
+        o2, d2 = synth.synth_rays(Q2, seed=22)
+        o2_t, d2_t = cu(o2, dev), cu(d2, dev)
+        g2 = torch.randn(Q2, D, device=dev, generator=torch.Generator(device=dev).manual_seed(6))
+        rs3 = sv.renderer._rays_spec_from_rays(sv.Rays(o2_t, d2_t, d2_t))
+        out3 = C.volume_render(ts, rs3, opt)
+        half = Q2 // 2
+        lists = rs3._cost.long()
+        assert torch.equal(torch.sort(lists[:half])[0], torch.arange(half, device=dev))
+        assert torch.equal(torch.sort(lists[half:])[0], torch.arange(half, device=dev))
+        grad3 = C.volume_render_backward(ts, rs3, opt, g2, saved_out=out3)
+        out4 = torch.empty_like(out3)
+        C._check(lib.svoxb_render_rays_fwd(C.ctypes.byref(ts._c()), C._ptr(o2_t), C._ptr(d2_t), C._ptr(d2_t), Q2,
+                                           C.ctypes.byref(opt._c()), C._ptr(out4), None, C._stream()))
+        grad4 = torch.zeros_like(feats)
+        C._check(lib.svoxb_render_rays_bwd(C.ctypes.byref(ts._c()), C._ptr(o2_t), C._ptr(d2_t), C._ptr(d2_t), Q2,
+                                           C.ctypes.byref(opt._c(sigma_thresh=0.0, stop_thresh=-1.0)), C._ptr(g2),
+                                           C._ptr(out4), C._ptr(grad4), C._stream()))
+        assert torch.equal(out3, out4) and float((grad3 - grad4).norm() / grad4.norm()) < 1e-6
