@@ -466,6 +466,15 @@ def main():
         weak = {"scaling": "weak", "rays_per_gpu": Q_GLOBAL, "global_rays": world * Q_GLOBAL, "ms_per_step": wms,
                 "value": world * Q_GLOBAL / (wms * 1e-3) / 1e6, "unit": "Mrays/s", "steps": 5}
         del o_w, d_w, g_w
+    # ---- N > 1: BASELINE config 5, the depth-10 / 64-channel scene replicated, a batch of 1080p views split over the GPUs
+    c5_views = None
+    if world > 1 and not args.skip_extras and not args.skip_c5:
+        del o_t, d_t, g_t, feats
+        xchg.table = None
+        try:
+            c5_views = c5_views_sharded(sv, svd, synth, dev, rank, world)
+        except Exception as e:      # every rank takes the same path: the scene is deterministic
+            c5_views = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
     status = xchg.status()
     xchg_desc = xchg.describe()
     if world > 1:
@@ -544,6 +553,8 @@ def main():
                               "what": "grad[M,D] of the sample rendered in N slices + exchanged vs rendered by rank 0 alone"}
     if weak is not None:
         out.setdefault("extras", {})["weak_scaling"] = weak
+    if c5_views is not None:
+        out.setdefault("extras", {})["c5_views_split_over_gpus"] = c5_views
     if not args.skip_extras and world == 1:
         out["extras"] = extras(args, sv, C, synth, orc, tree, feats, renderer, opt, ts, o_t, d_t, g_t, dev, peak, f, tr, T)
     emit(out)
@@ -698,6 +709,40 @@ def extras(args, sv, C, synth, orc, tree, feats, renderer, opt, ts, o_t, d_t, g_
         except Exception as e:
             ex["c5_depth10_shell_D64"] = {"unavailable": str(e)[:300]}
     return ex
+
+
+def c5_views_sharded(sv, svd, synth, dev, rank, world, n_views=16, W=1920, H=1080, fx=1500.0):
+    """Config C5 on N GPUs: depth-10 shell octree (32.9 M rows x 64 ch, 8.4 GB of features) replicated on every GPU, a batch
+    of `n_views` 1920x1080 views (Fibonacci-sphere cameras) split into whole views per GPU (dist.render_views_sharded), no
+    exchange. Whole-job Mpixel/s = all views / the slowest rank's device time; feature + opacity output per view."""
+    import torch
+    t0 = time.time()
+    tr = synth.synth_tree(10, "shell")
+    M, D = tr["M"], 64
+    g = torch.Generator(device=dev).manual_seed(0)
+    feats = torch.randn(M, D, device=dev, generator=g)
+    feats[:, -1] = torch.rand(M, device=dev, generator=g) * 10 - 2
+    tree = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=D, map_location=dev)
+    r = sv.VolumeRenderer(tree)
+    cams = [torch.from_numpy(c).to(dev) for c in synth.synth_cameras(n_views)]
+    build_s = time.time() - t0
+    imgs, (lo, hi) = svd.render_views_sharded(r, feats, cams, W, H, fx, rank=rank, world=world)      # warm-up (+ tables)
+    hit = float(torch.stack([(im[..., -1] > 0).float().mean() for im in imgs]).mean()) if imgs else 0.0
+    del imgs
+    svd.barrier(); torch.cuda.synchronize()
+    reps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        imgs, _ = svd.render_views_sharded(r, feats, cams, W, H, fx, rank=rank, world=world)
+        del imgs
+    e1.record()
+    torch.cuda.synchronize(); svd.barrier()
+    ms = svd.max_over_ranks(e0.elapsed_time(e1), dev) / reps
+    return {"views": n_views, "views_per_gpu": hi - lo, "width": W, "height": H, "leaf_rows": int(M), "D": D,
+            "ms_per_batch": ms, "Mpixel/s": n_views * W * H / (ms * 1e-3) / 1e6, "ms_per_view_per_gpu": ms / max(hi - lo, 1),
+            "hit_fraction_rank0": hit, "host_scene_build_s": round(build_s, 1),
+            "note": "tree + features replicated, whole views per GPU, no exchange; max over ranks of the device time"}
 
 
 def extras_c5(sv, C, synth, orc, dev, peak, best, image_roofline):

@@ -1070,3 +1070,34 @@ def test_short_batch_completion_list_orders_the_backward(dev):
                                            C.ctypes.byref(opt._c(sigma_thresh=0.0, stop_thresh=-1.0)), C._ptr(g2),
                                            C._ptr(out4), C._ptr(grad4), C._stream()))
         assert torch.equal(out3, out4) and float((grad3 - grad4).norm() / grad4.norm()) < 1e-6
+
+
+def test_fresh_feature_tensors_never_meet_a_stale_table(dev):
+    """Features are typically fresh network outputs every step: version 0, and the caching allocator hands the freed
+    block back at the same address. The activated table and the hit marks are keyed on the storage OBJECT, so the
+    second tensor must not be rendered (or back-propagated) with the first one's tables."""
+    tr = synth.synth_tree(5, "ball")
+    D, Q = 16, 20000
+    M = tr["M"]
+    tree = make_tree(tr, D, dev)
+    o, d = synth.synth_rays(Q, seed=4)
+    rays = sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev))
+    rs, r = sv.renderer._rays_spec_from_rays(rays), sv.VolumeRenderer(tree)
+    opt = r._get_options()
+    g = torch.randn(Q, D, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    ptrs = set()
+    for seed in range(5):
+        gen = torch.Generator(device=dev).manual_seed(100 + seed)
+        f = torch.randn(M, D, device=dev, generator=gen)
+        f[:, -1] = torch.rand(M, device=dev, generator=gen) * 10 - (2 + seed)      # another set of dead rows every time
+        ptrs.add(f.data_ptr())
+        f.requires_grad_(True)
+        out = r(f, rays)                                       # cached tables: activated + hit marks
+        (out * g).sum().backward()
+        plain = tree._spec(f.detach(), _with_accel=False)      # no accelerator, no activated table, no marks
+        ref_out = C.volume_render(plain, rs, opt)
+        ref_grad = C.volume_render_backward(plain, rs, opt, g, saved_out=ref_out)
+        assert float((out.detach() - ref_out).abs().max()) <= 2e-6
+        assert float((f.grad - ref_grad).norm() / ref_grad.norm()) <= 1e-5
+        del f, out, plain, ref_out, ref_grad
+    assert len(ptrs) < 5                                       # the allocator did hand an address back at least once
