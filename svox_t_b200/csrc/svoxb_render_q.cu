@@ -192,8 +192,7 @@ __device__ __forceinline__ RowBlk<V4> load_row_block(const char* p, uint64_t pol
 // caller's unaligned [M, D] layout are written channel by channel.
 // COUNT: also append every ray's index to a list when it ends (RaySource::done_list). With about one ray per lane all
 // rays start together, so the list is sorted by march length; the backward over the same batch reads it back to front --
-// longest ray first (svoxb_order.cu). Nothing is carried through the loop: 72 registers, 28 warps, like the plain kernel. One more live register per lane: its own instantiation
-// with the 80-register budget, used for short batches only (where the order matters and the 28th warp does not).
+// longest ray first (svoxb_order.cu). Nothing is carried through the loop: 72 registers, 28 warps, like the plain kernel.
 // A real call on purpose: inlined, these few instructions perturb the register allocation of the whole 72-register loop
 // into spilling (16-24 bytes, reloaded every iteration); as a call the live registers are saved around this cold site only.
 __device__ __noinline__ void append_done(int* __restrict__ list, unsigned long long* __restrict__ count, unsigned fm,
