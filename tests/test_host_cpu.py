@@ -220,3 +220,27 @@ def test_view_row_accessors_on_cpu_tensors():
         view.corners_local                       # calc_corners is a CUDA kernel: no CPU fallback
     with pytest.raises(RuntimeError):
         tree.set(torch.rand(4, 3), torch.rand(4, D))
+
+
+def test_leaf_grad_exchange_single_rank_bookkeeping():
+    """World of one (no process group): the exchange object is a plain table; the zero-fill bookkeeping hands the table
+    out as it is exactly once after a table pass for THESE features, and zero-fills it otherwise."""
+    import torch
+    from svox_t_b200 import dist as svd
+    x = svd.LeafGradExchange(6, 4, "cpu")
+    assert x.world == 1 and x.backend == "local" and x.table.shape == (6, 4) and x.status() == 0
+    f1, f2 = torch.randn(6, 4), torch.randn(6, 4)
+    x.table.fill_(3.0)
+    assert float(x.table_for_backward(f1).abs().sum()) == 0.0        # nothing was noted: zero-filled now
+    x.table.fill_(5.0)
+    x.note_zeroed(f1)                                                # "the table pass for f1 has just zeroed it"
+    assert float(x.table_for_backward(f1).sum()) == 5.0 * 24          # handed out untouched ...
+    assert float(x.table_for_backward(f1).abs().sum()) == 0.0        # ... once
+    x.table.fill_(7.0)
+    x.note_zeroed(f1)
+    assert float(x.table_for_backward(f2).abs().sum()) == 0.0        # other features: not trusted
+    x.table.fill_(1.0)
+    x.note_zeroed(f1)
+    f1.add_(1.0)                                                     # in-place update bumps the version: stale
+    assert float(x.table_for_backward(f1).abs().sum()) == 0.0
+    assert x.all_reduce_() is x.table and x.describe()["world"] == 1
