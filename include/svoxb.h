@@ -145,6 +145,12 @@ SVOXB_API int svoxb_accel_mark_hits(svoxb_accel* accel, const float* features, i
 SVOXB_API int svoxb_activate_features(const float* features, int64_t M, int32_t D, float* out, int32_t out_stride,
                             float* sigma_out, void* stream);
 
+/* sigma_out[i] = features[i, D-1]: the compact sigma array (svoxb_tree.features_sigma) on its own, for the marches that
+ * read nothing else of a row -- svoxb_render_depth, svoxb_opacity_render_fwd/_bwd, svoxb_motion_render: 4 M bytes that
+ * stay in L2 instead of one 32-byte sector of the [M, D] table per sample. Those entry points also honour the hit marks
+ * (svoxb_tree.accel_marks_current): rows with sigma <= 0 are not fetched at all. Both are pure accelerations. */
+SVOXB_API int svoxb_gather_sigma(const float* features, int64_t M, int32_t D, float* sigma_out, void* stream);
+
 /* ---- per-step table pass (no reference counterpart) --------------------------------------------------------------- */
 /* Everything a training step needs before its marches because `features` changed, in ONE streaming pass over the rows
  * (D % 4 == 0, 16-byte aligned tables; other shapes run the separate passes above, same results):
@@ -258,6 +264,12 @@ SVOXB_API int svoxb_opacity_render_fwd(const svoxb_tree* tree, const float* orig
  * (The reference's own entry point launches the wrong kernel, rt_kernel.cu:1607; this is the intended semantics.) */
 SVOXB_API int svoxb_opacity_render_bwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
                              const svoxb_render_options* opt, const float* grad_out, float* grad_features, void* stream);
+/* The same with the forward's own output: saved_out[Q] = svoxb_opacity_render_fwd's result for the SAME tree, rays and
+ * default thresholds (sigma_thresh = 0, stop_thresh <= 0) gives T_end = 1 - saved_out, so the backward marches once
+ * instead of twice. */
+SVOXB_API int svoxb_opacity_render_bwd_saved(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                                   const svoxb_render_options* opt, const float* grad_out, const float* saved_out,
+                                   float* grad_features, void* stream);
 
 /* motion_render (rt_kernel.cu:698-778, 1480-1504): at the first sample with sigma > sigma_thresh:
  * out[Q, J] = distance of the hit point to each row of extra_data[J, 3], depth[Q], hit_point[Q, 3], data_idx[Q]

@@ -76,6 +76,7 @@ SYMBOLS = {
     "svoxb_accel_mark_hits": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP]),
     "svoxb_activate_features": (ctypes.c_int, [_VP, _I64, _I32, _VP, _I32, _VP, _VP]),
     "svoxb_prepare_step": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP, _I32, _VP, _VP, _VP]),
+    "svoxb_gather_sigma": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP]),
     "svoxb_query": (ctypes.c_int, [_PT, _VP, _I64, _VP, _VP, _VP, _VP, _VP]),
     "svoxb_leafset_scratch_bytes": (ctypes.c_size_t, [_I64]),
     "svoxb_leafset_scan": (ctypes.c_int, [_VP, _I64, _VP, _VP, _VP]),
@@ -97,6 +98,7 @@ SYMBOLS = {
     "svoxb_render_depth": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP]),
     "svoxb_opacity_render_fwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP]),
     "svoxb_opacity_render_bwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP, _VP]),
+    "svoxb_opacity_render_bwd_saved": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _VP]),
     "svoxb_motion_render": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _I32, _VP, _VP, _VP, _VP, _VP]),
     "svoxb_accumulate_weights": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PC, _PO, _VP, _VP]),
     "svoxb_motion_feature_render_fwd": (ctypes.c_int, [_PT, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
@@ -228,6 +230,7 @@ class TreeSpec:
                                     # table and sums it over the GPUs (None = a fresh zeros_like(features), as the reference)
         self._accel = None          # svox_t_b200 extension: Accel handle cached by N3Tree (None = reference walk)
         self._act = None            # svox_t_b200 extension: Activated table for `features` (None = sigmoid in-kernel)
+        self._sigma = None          # svox_t_b200 extension: SigmaTable (compact sigma array) for the sigma-only marches
 
     def check(self):
         _check_input(self.features, "features", torch.float32)
@@ -273,7 +276,9 @@ class TreeSpec:
             extra_cols=self.extra_data.shape[1] if self.extra_data is not None and self.extra_data.numel() else 0,
             transformation_matrices=_ptr(self.transformation_matrices),
             features_act_stride=act.table.shape[1] if act is not None else 0,
-            features_sigma=_ptr(act.sigma) if act is not None else ctypes.c_void_p(0),
+            features_sigma=_ptr(act.sigma) if act is not None else (
+                _ptr(self._sigma.table) if self._sigma is not None and self._sigma.matches(self.features)
+                else ctypes.c_void_p(0)),
             accel_marks_current=1 if acc is not None and acc.marks_match(self.features) else 0)
         return c
 
@@ -427,6 +432,23 @@ class Activated:
                                           _ptr(self.table), stride, _ptr(self.sigma), _ptr(zero_table), _stream()))
         if accel is not None:
             accel._marks_key = _TensorIdentity(features)
+
+    def matches(self, features):
+        return self._key.matches(features)
+
+
+class SigmaTable:
+    """The sigma channel of ``features`` as a compact [M] array (svoxb_gather_sigma), for the marches that read nothing
+    else of a row (depth, opacity, motion). Valid for one (storage object, version, layout) of ``features``."""
+
+    def __init__(self, features):
+        lib = load_library()
+        _check_input(features, "features", torch.float32)
+        self._key = _TensorIdentity(features)
+        M, D = features.shape
+        with torch.cuda.device(features.device):
+            self.table = torch.empty((M,), dtype=torch.float32, device=features.device)
+            _check(lib.svoxb_gather_sigma(_ptr(features), M, D, _ptr(self.table), _stream()))
 
     def matches(self, features):
         return self._key.matches(features)
@@ -658,18 +680,27 @@ def opacity_render(tree, rays, opt):
     return out
 
 
-def opacity_render_backward(tree, rays, opt, grad_output):
+def opacity_render_backward(tree, rays, opt, grad_output, saved_out=None):
     """[M, D] gradient of opacity_render w.r.t. the sigma channel -- the semantics of the reference's
-    opacity_trace_ray_backward (rt_kernel.cu:562-651), which its own wrapper never launches (Appendix B2)."""
+    opacity_trace_ray_backward (rt_kernel.cu:562-651), which its own wrapper never launches (Appendix B2).
+    ``saved_out``: the UNMODIFIED output of opacity_render for the same tree, rays and default thresholds; the backward
+    then marches once (T_end = 1 - saved_out) instead of twice."""
     lib = load_library()
     rays.check()
     _check_input(grad_output, "grad_output", torch.float32)
     ct = tree._c()
     Q, dev = rays.origins.shape[0], rays.origins.device
+    use_saved = (saved_out is not None and tuple(saved_out.shape) == (Q, 1) and saved_out.dtype == torch.float32
+                 and saved_out.is_cuda and saved_out.is_contiguous() and opt.sigma_thresh == 0.0 and opt.stop_thresh <= 0.0)
     with torch.cuda.device(dev):
         grad = torch.zeros_like(tree.features)
-        _check(lib.svoxb_opacity_render_bwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q,
-                                            ctypes.byref(opt._c()), _ptr(grad_output), _ptr(grad), _stream()))
+        if use_saved:
+            _check(lib.svoxb_opacity_render_bwd_saved(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q,
+                                                      ctypes.byref(opt._c()), _ptr(grad_output), _ptr(saved_out), _ptr(grad),
+                                                      _stream()))
+        else:
+            _check(lib.svoxb_opacity_render_bwd(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q,
+                                                ctypes.byref(opt._c()), _ptr(grad_output), _ptr(grad), _stream()))
     return grad
 
 

@@ -135,6 +135,7 @@ struct Leaf {
     float rx, ry, rz; // position inside the leaf, [0,1)^3
     float inv_cube;   // 1 / cube_sz  (cube_sz = N^levels)
     float cube;       // cube_sz
+    bool miss;        // accelerator hit marks current and this row's sigma <= 0: the sample cannot be a hit (no fetch)
 };
 
 // Descent over the reference tensors, any N (include/common.cuh:62-100). p in [0,1]^3 (unclamped).
@@ -179,6 +180,7 @@ __device__ __forceinline__ Leaf locate(const TreeArgs& tr, const uint32_t* __res
         const int d = (int)(cell >> ACC_DEPTH_SHIFT) & 0xf;
         const uint32_t idx = cell & ACC_IDX_MASK;
         lf.idx = (idx == ACC_EMPTY) ? -1 : (int64_t)idx;
+        lf.miss = (cell & tr.acc_miss_mask) != 0;
         const float sc = __int_as_float((127 + d) << 23);           // cube_sz = 2^d
         lf.cube = sc;
         lf.inv_cube = __int_as_float((127 - d) << 23);
@@ -188,6 +190,7 @@ __device__ __forceinline__ Leaf locate(const TreeArgs& tr, const uint32_t* __res
         const int64_t slot = descend_ref(tr.child, tr.N, px, py, pz, lf.rx, lf.ry, lf.rz, lf.cube);
         const int idx = __ldg(tr.data + slot);
         lf.idx = ((int64_t)idx >= tr.M || idx < 0) ? -1 : (int64_t)idx;
+        lf.miss = false;
         lf.inv_cube = 1.0f / lf.cube;
     }
     return lf;

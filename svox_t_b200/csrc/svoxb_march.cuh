@@ -215,6 +215,14 @@ __device__ __forceinline__ void load_top(const TreeArgs& tr, uint32_t* top) {
                      : "=r"(done) : "r"(bar) : "memory");
 }
 
+// sigma of a located leaf for the kernels that need nothing else of the row (depth, opacity, motion): 0 for empty
+// leaves and for rows the hit marks flag as sigma <= 0 (no fetch); from the compact sigma array when the caller attached
+// one (svoxb_tree.features_sigma: 4 M bytes, L2-resident) instead of one 32-byte sector of the [M, D] table per sample.
+__device__ __forceinline__ float leaf_sigma(const TreeArgs& tr, const Leaf& lf) {
+    if (lf.idx < 0 || lf.miss) return 0.0f;
+    return tr.sigma_c ? __ldg(tr.sigma_c + lf.idx) : __ldg(tr.features + lf.idx * tr.D + (tr.D - 1));
+}
+
 // One march sample of the lane's ray (rt_kernel.cu:261-277): returns the leaf row (or -1), delta_t and sigma.
 template <bool ACCEL>
 __device__ __forceinline__ void sample(const TreeArgs& tr, const uint32_t* top, const Ray& r, float step,
@@ -226,8 +234,7 @@ __device__ __forceinline__ void sample(const TreeArgs& tr, const uint32_t* top, 
     const float tsub = ACCEL ? (smax - smin) * lf.inv_cube : (smax - smin) / lf.cube;
     delta_t = tsub + step;
     idx = lf.idx;
-    sigma = 0.0f;
-    if (idx >= 0) sigma = __ldg(tr.features + idx * tr.D + (tr.D - 1));
+    sigma = leaf_sigma(tr, lf);
 }
 
 

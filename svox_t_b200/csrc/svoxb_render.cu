@@ -585,6 +585,7 @@ extern "C" int svoxb_render_depth(const svoxb_tree* tree, const float* origins, 
     TreeArgs tr; MarchOpts m;
     int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = check_opts(opt, m); if (rc) return rc;
+    if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;
     SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (origins && dirs && depth)), "bad ray batch");
     if (Q == 0) return 0;
     const int grid = (int)min((Q + BLOCK - 1) / BLOCK, (int64_t)sm_count() * 8);

@@ -1,6 +1,7 @@
 // svoxb_render_x.cu -- march variants next to the feature render: opacity-only render with a
 // CORRECT backward, and the first-hit "motion" outputs. One thread per ray: these touch one float per sample
-// (sigma), so there is no row work to share across a warp.
+// (sigma), so there is no row work to share across a warp. sigma comes from the compact array when the caller attached
+// one (svoxb_gather_sigma), and rows the hit marks flag as dead are not fetched at all (leaf_sigma, svoxb_march.cuh).
 //
 // Replaces (reference paths relative to /root/reference/svox_t/csrc):
 //   opacity_trace_ray / opacity_render                 rt_kernel.cu:499-560, 1109-1126, 1574-1591
@@ -20,8 +21,7 @@ __device__ __forceinline__ void sample_sigma(const TreeArgs& tr, const uint32_t*
     dda_unit(lf.rx, lf.ry, lf.rz, r.ix, r.iy, r.iz, smin, smax);
     const float tsub = ACCEL ? (smax - smin) * lf.inv_cube : (smax - smin) / lf.cube;
     delta_t = tsub + step;
-    sigma = 0.0f;
-    if (lf.idx >= 0) sigma = __ldg(tr.features + lf.idx * tr.D + (tr.D - 1));
+    sigma = leaf_sigma(tr, lf);
 }
 
 __device__ __forceinline__ void load_ray(const TreeArgs& tr, const float* origins, const float* dirs, int64_t id, Ray& ray) {
@@ -57,7 +57,8 @@ opacity_fwd_kernel(TreeArgs tr, const float* __restrict__ origins, const float* 
 template <bool ACCEL>
 __global__ void __launch_bounds__(BLOCK)
 opacity_bwd_kernel(TreeArgs tr, const float* __restrict__ origins, const float* __restrict__ dirs, int64_t Q,
-                   MarchOpts opt, const float* __restrict__ grad_out, float* __restrict__ grad) {
+                   MarchOpts opt, const float* __restrict__ grad_out, const float* __restrict__ saved_out,
+                   float* __restrict__ grad) {
     extern __shared__ __align__(128) uint32_t smem_u32[];
     uint32_t* top = smem_u32;
     if (ACCEL) load_top(tr, top);
@@ -66,11 +67,15 @@ opacity_bwd_kernel(TreeArgs tr, const float* __restrict__ origins, const float* 
         load_ray(tr, origins, dirs, id, ray);
         const float t0 = ray.t;
         float T = 1.0f;
-        while (ray.t < ray.tmax) {                                           // pass 1: T_end
-            Leaf lf; float delta_t, sigma;
-            sample_sigma<ACCEL>(tr, top, ray, opt.step, lf, delta_t, sigma);
-            if (sigma > 0.0f) T *= expf(-delta_t * sigma * ray.ds);
-            ray.t += delta_t;
+        if (saved_out) {                                                     // T_end from the forward's own output
+            T = 1.0f - __ldg(saved_out + id);
+        } else {
+            while (ray.t < ray.tmax) {                                       // pass 1: T_end
+                Leaf lf; float delta_t, sigma;
+                sample_sigma<ACCEL>(tr, top, ray, opt.step, lf, delta_t, sigma);
+                if (sigma > 0.0f) T *= expf(-delta_t * sigma * ray.ds);
+                ray.t += delta_t;
+            }
         }
         const float gT = __ldg(grad_out + id) * T;
         ray.t = t0;
@@ -199,22 +204,37 @@ extern "C" int svoxb_opacity_render_fwd(const svoxb_tree* tree, const float* ori
     TreeArgs tr; MarchOpts m;
     int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = simple_opts(opt, m); if (rc) return rc;
+    if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;     // the marks encode sigma > 0: too strict for this predicate
     SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (origins && dirs && out)), "bad ray batch");
     if (Q == 0) return 0;
     return launch_simple(tr, Q, (cudaStream_t)stream, opacity_fwd_kernel<true>, opacity_fwd_kernel<false>, origins, dirs,
                          Q, m, out);
 }
 
-extern "C" int svoxb_opacity_render_bwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
-                                        const svoxb_render_options* opt, const float* grad_out, float* grad_features,
-                                        void* stream) {
+static int opacity_bwd_impl(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                            const svoxb_render_options* opt, const float* grad_out, const float* saved_out,
+                            float* grad_features, void* stream) {
     TreeArgs tr; MarchOpts m;
     int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = simple_opts(opt, m); if (rc) return rc;
+    if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;     // the marks encode sigma > 0: too strict for this predicate
     SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (origins && dirs && grad_out && grad_features)), "bad arguments");
     if (Q == 0) return 0;
     return launch_simple(tr, Q, (cudaStream_t)stream, opacity_bwd_kernel<true>, opacity_bwd_kernel<false>, origins, dirs,
-                         Q, m, grad_out, grad_features);
+                         Q, m, grad_out, saved_out, grad_features);
+}
+
+extern "C" int svoxb_opacity_render_bwd(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                                        const svoxb_render_options* opt, const float* grad_out, float* grad_features,
+                                        void* stream) {
+    return opacity_bwd_impl(tree, origins, dirs, Q, opt, grad_out, nullptr, grad_features, stream);
+}
+
+extern "C" int svoxb_opacity_render_bwd_saved(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
+                                              const svoxb_render_options* opt, const float* grad_out,
+                                              const float* saved_out, float* grad_features, void* stream) {
+    SVOXB_REQUIRE(Q == 0 || saved_out != nullptr, "saved_out is NULL");
+    return opacity_bwd_impl(tree, origins, dirs, Q, opt, grad_out, saved_out, grad_features, stream);
 }
 
 extern "C" int svoxb_motion_render(const svoxb_tree* tree, const float* origins, const float* dirs, int64_t Q,
@@ -223,6 +243,7 @@ extern "C" int svoxb_motion_render(const svoxb_tree* tree, const float* origins,
     TreeArgs tr; MarchOpts m;
     int rc = make_tree_args(tree, tr, stream); if (rc) return rc;
     rc = simple_opts(opt, m); if (rc) return rc;
+    if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;     // the marks encode sigma > 0: too strict for this predicate
     SVOXB_REQUIRE(J >= 0 && (J == 0 || extra_data), "extra_data is NULL");
     SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (origins && dirs && depth && hit_point && data_idx && (J == 0 || out))), "bad arguments");
     if (Q == 0) return 0;

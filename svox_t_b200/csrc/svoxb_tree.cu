@@ -813,6 +813,22 @@ extern "C" int svoxb_activate_features(const float* features, int64_t M, int32_t
     return check_cuda(cudaGetLastError(), "activate_kernel launch");
 }
 
+__global__ void __launch_bounds__(256)
+gather_sigma_kernel(const float* __restrict__ f, int64_t M, int D, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __ldg(f + i * D + (D - 1));
+}
+
+extern "C" int svoxb_gather_sigma(const float* features, int64_t M, int32_t D, float* sigma_out, void* stream) {
+    SVOXB_REQUIRE(M >= 0 && D >= 2, "bad sizes");
+    if (M == 0) return 0;
+    SVOXB_REQUIRE(features && sigma_out, "NULL tensor");
+    const int grid = (int)min((M + 255) / 256, (int64_t)sm_count() * 16);
+    gather_sigma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(features, M, D, sigma_out);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "gather_sigma_kernel launch");
+}
+
 extern "C" int svoxb_prepare_step(svoxb_accel* a, const float* features, int64_t M, int32_t D, float* act,
                                   int32_t act_stride, float* sigma_out, float* zero_table, void* stream) {
     SVOXB_REQUIRE(M >= 0 && D >= 2, "bad sizes");

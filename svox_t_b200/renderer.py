@@ -110,12 +110,15 @@ class _OpacityRenderFunction(autograd.Function):
     @staticmethod
     def forward(ctx, data, tree, rays, opt):
         ctx.tree, ctx.rays, ctx.opt = tree, rays, opt
-        return _C.opacity_render(tree, rays, opt)
+        out = _C.opacity_render(tree, rays, opt)
+        ctx.save_for_backward(out)          # T_end = 1 - out: the backward marches once instead of twice
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
         if ctx.needs_input_grad[0]:
-            return _C.opacity_render_backward(ctx.tree, ctx.rays, ctx.opt, grad_out.contiguous()), None, None, None
+            return (_C.opacity_render_backward(ctx.tree, ctx.rays, ctx.opt, grad_out.contiguous(),
+                                               saved_out=ctx.saved_tensors[0]), None, None, None)
         return None, None, None, None
 
 
@@ -157,6 +160,16 @@ class VolumeRenderer(nn.Module):
                 xchg = ts._grad_exchange if (features.requires_grad and torch.is_grad_enabled()) else None
                 ts._act = self.tree.activated(features.detach(), accel=ts._accel, grad_exchange=xchg)
             elif ts._accel is not None:     # every format keeps sigma in the last channel: dead rows are never fetched
+                ts._accel.mark_hits(features.detach())
+        return ts
+
+    def _sigma_spec(self, features, n_rays):
+        """TreeSpec for the marches that only read sigma (depth, opacity, motion): for batches large enough to pay for
+        two small passes, attach the compact sigma array and refresh the hit marks (dead rows are never fetched)."""
+        ts = self.tree._spec(features)
+        if n_rays * 32 >= features.shape[0] and features.is_cuda:
+            ts._sigma = self.tree.sigma_table(features.detach())
+            if ts._accel is not None:
                 ts._accel.mark_hits(features.detach())
         return ts
 
@@ -203,13 +216,15 @@ class VolumeRenderer(nn.Module):
     def render_depth(self, features, rays: Rays, cuda=True, fast=False):
         """First-hit depth (B, 1), not differentiable (renderer.py:377-382)."""
         self._require_cuda(cuda)
-        return _C.render_depth(self.tree._spec(features), _rays_spec_from_rays(rays), self._get_options(fast))
+        return _C.render_depth(self._sigma_spec(features, rays.origins.shape[0]), _rays_spec_from_rays(rays),
+                               self._get_options(fast))
 
     def motion_render(self, features, rays: Rays, cuda=True, fast=False):
         """First-hit joint distances, depth, hit point and data index (renderer.py:367-375)."""
         assert self.tree.extra_data is not None, "Need extra data to store skeleton postion."
         self._require_cuda(cuda)
-        return tuple(_C.motion_render(self.tree._spec(features), _rays_spec_from_rays(rays), self._get_options(fast)))
+        return tuple(_C.motion_render(self._sigma_spec(features, rays.origins.shape[0]), _rays_spec_from_rays(rays),
+                                      self._get_options(fast)))
 
     def motion_feature_render(self, features, joint_features, skinning_weights, joint_index, rays: Rays, cuda=True,
                               fast=False):
@@ -224,8 +239,8 @@ class VolumeRenderer(nn.Module):
     def opacity_render(self, features, rays: Rays, cuda=True, fast=False):
         """Opacity only (B, 1); differentiable w.r.t. the sigma channel of ``features`` (renderer.py:397-406)."""
         self._require_cuda(cuda)
-        return _OpacityRenderFunction.apply(features, self.tree._spec(features), _rays_spec_from_rays(rays),
-                                            self._get_options(fast))
+        return _OpacityRenderFunction.apply(features, self._sigma_spec(features, rays.origins.shape[0]),
+                                            _rays_spec_from_rays(rays), self._get_options(fast))
 
     def _get_options(self, fast=False):
         """RenderOptions for the kernels (renderer.py:408-439)."""

@@ -375,6 +375,13 @@ class N3Tree(nn.Module):
             accel.mark_hits(features)
         return act
 
+    def sigma_table(self, features):
+        """Compact sigma array of ``features`` (cached until ``features`` changes) for the sigma-only marches."""
+        st = getattr(self, "_sigma_cache", None)
+        if st is None or not st.matches(features):
+            st = self._sigma_cache = _C.SigmaTable(features)
+        return st
+
     def _spec(self, features, joint_features=None, skinning_weights=None, joint_index=None,
               transformation_matrices=None, world=True, _with_accel=True):
         """Pack the tree into a TreeSpec (svox.py:899-925). transformation_matrices / joint_* are carried for
