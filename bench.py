@@ -696,6 +696,21 @@ def extras(args, sv, C, synth, orc, tree, feats, renderer, opt, ts, o_t, d_t, g_
               "host_syncs_per_frame": 0,
               "note": "bitmap rebuild (no sort, no read-back) into tensors of node_capacity rows; accelerator built without "
                       "read-backs (depth known); stage times from CUDA events recorded in stream order"}
+        try:    # the same frame captured in ONE CUDA graph (nothing in it synchronises or allocates outside the graph pool)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    frame()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                frame()
+            c4["ms_per_frame_cuda_graph"] = best(graph.replay, 2, 7)
+            del graph
+        except Exception as e:
+            c4["ms_per_frame_cuda_graph"] = f"unavailable: {str(e)[:120]}"
         T4 = orc.Tree(tree4.child.cpu().numpy(), tree4.data.cpu().numpy())
         st4 = tree4.accel(f4).describe()["stages"]
         c4["render_roofline"] = image_roofline(T4, f4_np, cams[0], 1920, 1080, 1500.0, 32, P, st4, float(med[4]), every=12)

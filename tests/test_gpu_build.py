@@ -89,3 +89,51 @@ def test_accelerator_is_refilled_in_place_frame_after_frame(dev):
         assert torch.equal(out, out2) and torch.equal(depth, depth2)
         assert acc.describe()["bricks"][1] == fresh.accel(f).describe()["bricks"][1]
     assert len(handles) == 1                                   # one accelerator object, refilled
+
+
+def test_animated_frame_is_cuda_graph_capturable(dev):
+    """warp -> splat -> rebuild -> accelerator -> render issue no synchronisation and (after a warm-up frame) allocate
+    nothing outside torch's graph pool: the whole frame is captured once and replayed with new joint transforms."""
+    L, P, D = 6, 40000, 8
+    rng = np.random.default_rng(5)
+    pts = (0.5 + 0.25 * (rng.random((P, 3)) * 2 - 1)).astype(np.float32)
+    Tm, w, ji = synth.synth_skeleton(P)
+    p_t, w_t, j_t = (torch.from_numpy(a).to(dev) for a in (pts, w, ji))
+    Tm_t = torch.from_numpy(Tm).to(dev)
+    f = torch.from_numpy(synth.synth_features(P, D)).to(dev)
+    corner, size = torch.zeros(3, device=dev), torch.ones(3, device=dev)
+    cam = torch.from_numpy(synth.synth_cameras(1)[0]).to(dev)
+    tree = sv.N3Tree(N=2, data_dim=D, map_location=dev)
+    r = sv.VolumeRenderer(tree)
+
+    def frame():
+        warped, _ = sv.warp_vertices(Tm_t, p_t, w_t, j_t)
+        grid = sv.voxelize(warped, f, corner, size, 64, 1.5 / 64, 2.0 / 64)
+        tree.build_from_points(warped, L, capacity=80000)
+        img, depth = r.render_persp_with_depth(f, cam, width=160, height=120, fx=150.0)
+        return grid, img, depth
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                      # warm-up on the capture stream: bitmaps, accelerator, tables
+        for _ in range(2):
+            frame()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        grid_g, img_g, depth_g = frame()
+    # another pose: rotate every joint a little more, replay
+    Tm2 = Tm.copy()
+    Tm2[:, :3, 3] += 0.01
+    Tm_t.copy_(torch.from_numpy(Tm2).to(dev))
+    graph.replay()
+    torch.cuda.synchronize()
+    got = (grid_g.clone(), img_g.clone(), depth_g.clone())
+    ref_tree = sv.N3Tree(N=2, data_dim=D, map_location=dev)
+    warped, _ = sv.warp_vertices(Tm_t, p_t, w_t, j_t)
+    ref_tree.build_from_points(warped, L)
+    ref_img, ref_depth = sv.VolumeRenderer(ref_tree).render_persp_with_depth(f, cam, width=160, height=120, fx=150.0)
+    assert torch.equal(got[1], ref_img) and torch.equal(got[2], ref_depth)
+    assert float((got[0] - sv.voxelize(warped, f, corner, size, 64, 1.5 / 64, 2.0 / 64)).abs().max()) < 1e-4
+    assert float((img_g[..., -1] > 0).float().mean()) > 0.05
