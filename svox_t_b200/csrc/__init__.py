@@ -593,6 +593,13 @@ def volume_render_backward(tree, rays, opt, grad_output, saved_out=None):
     with torch.cuda.device(dev):
         so = _saved_out_for_backward(tree, opt, saved_out, again, grad_output.shape)
         xchg = getattr(tree, "_grad_exchange", None)
+        if xchg is not None:
+            # The gradient handed to autograd IS the exchange's table (no 243 MB copy). If features.grad still aliases it
+            # from an earlier backward (gradient accumulation over several backward calls), give that gradient a life
+            # of its own before the table is zeroed and reused -- autograd then adds the new sum to the copy.
+            fg = getattr(tree.features, "grad", None) if tree.features.is_leaf else None
+            if fg is not None and fg.data_ptr() == xchg.table.data_ptr():
+                tree.features.grad = fg.clone()
         # multi-GPU: reduce into the exchange's symmetric table and sum it over the ranks right here (dist.LeafGradExchange)
         grad = xchg.table_for_backward(tree.features) if xchg is not None else torch.zeros_like(tree.features)
         cost = getattr(rays, "_cost", None)

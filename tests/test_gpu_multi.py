@@ -54,13 +54,20 @@ def _worker(rank, world, port, q):
     (r(f2, svd.shard_rays(rays, rank, world)) * g_t[lo:hi]).sum().backward()
     torch.cuda.synchronize()
     assert xchg.status() == 0
+    # gradient accumulation over two backward calls: the first sum must survive the reuse of the exchange's table
+    f3 = feats.detach().clone().requires_grad_(True)
+    mine = svd.shard_rays(rays, rank, world)
+    (r(f3, mine) * g_t[lo:hi]).sum().backward()
+    (r(f3, mine) * g_t[lo:hi]).sum().backward()
+    torch.cuda.synchronize()
+    acc_rel = float((f3.grad - 2 * f2.grad).norm() / f2.grad.norm())
     r.leaf_grad_exchange = None
     if rank == 0:
         full = feats.detach().clone().requires_grad_(True)
         (r(full, rays) * g_t).sum().backward()
         rel = float((grad - full.grad).norm() / full.grad.norm())
         rel2 = float((f2.grad - full.grad).norm() / full.grad.norm())
-        q.put((rel, rel2, xchg.describe()["backend"]))
+        q.put((rel, rel2, xchg.describe()["backend"], acc_rel))
     svd.barrier()
     dist.destroy_process_group()
 
@@ -73,9 +80,10 @@ def test_two_gpu_sharded_gradients_match_single_gpu():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    rel, rel2, backend = q.get(timeout=300)
+    rel, rel2, backend, acc_rel = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     assert rel < 1e-5, rel
     assert rel2 < 1e-5, (rel2, backend)
+    assert acc_rel < 1e-5, acc_rel
