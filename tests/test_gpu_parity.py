@@ -1101,3 +1101,38 @@ def test_fresh_feature_tensors_never_meet_a_stale_table(dev):
         assert float((f.grad - ref_grad).norm() / ref_grad.norm()) <= 1e-5
         del f, out, plain, ref_out, ref_grad
     assert len(ptrs) < 5                                       # the allocator did hand an address back at least once
+
+
+@pytest.mark.parametrize("known_depth", [False, True], ids=["accel_sync", "accel_no_readback"])
+def test_rows_shared_by_several_leaves_keep_exact_hit_marks(dev, known_depth):
+    """After refine() the children of a split leaf inherit its row (svox.py:539-540): one row, eight leaf cells. The
+    table pass cannot mark through its row -> cell map then and must fall back to the pass over the cells -- decided on
+    the host when the accelerator was built with read-backs, on the device when it was built without."""
+    tr = synth.synth_tree(4, "ball")
+    D, Q = 16, 30000
+    tree = make_tree(tr, D, dev)
+    tree.refine()                                            # every leaf splits once; rows are now shared 8-fold
+    f = synth.synth_features(tr["M"], D)
+    f[:, -1] = np.random.default_rng(3).uniform(-4, 6, tr["M"]).astype(np.float32)     # ~40 % dead rows
+    feats = cu(f, dev)
+    o, d = synth.synth_rays(Q, seed=8)
+    rays = sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev))
+    rs = sv.renderer._rays_spec_from_rays(rays)
+    r = sv.VolumeRenderer(tree)
+    opt = r._get_options()
+    if known_depth:
+        acc = tree.accel(feats, max_depth=tree.max_depth + 1)
+        assert acc is not None
+    g = torch.randn(Q, D, device=dev, generator=torch.Generator(device=dev).manual_seed(2))
+    ts = r._render_spec(feats, Q)                            # activated table + hit marks
+    assert ts._accel is not None and ts._act is not None
+    out = C.volume_render(ts, rs, opt)
+    grad = C.volume_render_backward(ts, rs, opt, g, saved_out=out)
+    plain = tree._spec(feats, _with_accel=False)
+    out_ref = C.volume_render(plain, rs, opt)
+    grad_ref = C.volume_render_backward(plain, rs, opt, g, saved_out=out_ref)
+    assert float((out - out_ref).abs().max()) <= 2e-6
+    assert float((grad - grad_ref).norm() / grad_ref.norm()) <= 1e-5
+    T = orc.Tree(tree.child[:tree.filled].cpu().numpy(), tree.data[:tree.filled].cpu().numpy())
+    o_ref = orc.render_rays(T, f, o[:2000], d[:2000])[0]
+    assert frac_within(out.cpu().numpy()[:2000], o_ref) >= 0.999
