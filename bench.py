@@ -632,7 +632,25 @@ def extras(args, sv, C, synth, orc, tree, feats, renderer, opt, ts, o_t, d_t, g_
                            "grad_rel_l2": float((mine_grad - ref_grad).norm() / ref_grad.norm())},
                 "note": "unmodified svox_t csrc compiled for sm_100a (oracle/_ref); parity = this library against it on "
                         "the full 2^20-ray batch"}
-            del ref_out, ref_grad, mine_out, mine_grad, err
+            # the other two kernels SURVEY 8(d) names: first-hit depth and the batched point query (2^20 points), timed
+            # and compared (depth within 1e-5; leaf ids bit-exact)
+            ours_ts = renderer._sigma_spec(feats, o_t.shape[0])
+            d_ms = best(lambda: C.render_depth(ours_ts, rs, opt), 1, 5)
+            d_ref_ms = best(lambda: m.render_depth(rts, rrs, ro), 1, 3)
+            d_err = (C.render_depth(ours_ts, rs, opt) - m.render_depth(rts, rrs, ro)).abs()
+            pts = torch.rand(o_t.shape[0], 3, device=dev, generator=torch.Generator(device=dev).manual_seed(9)) * 0.7 + 0.15
+            q_ms = best(lambda: tree(feats, pts, want_node_ids=True, want_data_ids=True), 1, 5)
+            q_ref_ms = best(lambda: m.query_vertical(rts, pts), 1, 3)
+            _, nid, did = tree(feats, pts, want_node_ids=True, want_data_ids=True)
+            rv, rnid, rdid, _ = m.query_vertical(rts, pts)
+            has = did >= 0
+            ex["reference_cuda_same_inputs"].update({
+                "render_depth_ms": {"here": d_ms, "reference": d_ref_ms,
+                                    "frac_within_1e-5": float((d_err <= 1e-5).float().mean())},
+                "query_vertical_2^20_points_ms": {"here": q_ms, "reference": q_ref_ms,
+                                                  "node_ids_equal": bool(torch.equal(nid, rnid)),
+                                                  "data_ids_equal": bool(torch.equal(did[has], rdid[has]))}})
+            del ref_out, ref_grad, mine_out, mine_grad, err, d_err, pts, rv, rnid, rdid, nid, did
     except Exception as e:  # the checker is optional here
         ex["reference_cuda_same_inputs"] = {"unavailable": str(e)[:200]}
     try:   # motion-feature render on the same tree and rays: J = 24 joints, F = 32, B = 4
