@@ -248,6 +248,7 @@ dense_emit_kernel(DenseLevels lv, int64_t total_words, int64_t cap_nodes, int32_
             const uint32_t cell = (uint32_t)(w * 32 + b);
             const int64_t parent = l == 1 ? 0 : base_p + dense_rank(lv, l - 1, cell >> 3);
             const int slot = (int)(cell & 7u);
+            SVOXB_DBG(parent >= 0 && parent < node);
             if (node < cap_nodes) {
                 child[parent * 8 + slot] = (int32_t)(node - parent);
                 parent_depth[2 * node] = (int32_t)(parent * 8 + slot);
@@ -269,6 +270,7 @@ dense_leaf_kernel(DenseLevels lv, const float* __restrict__ pts, int64_t P, cons
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t k = point_key(pts, i, L, o0, o1, o2, s0, s1, s2, sc);
         const int64_t parent = L == 1 ? 0 : base_p + dense_rank(lv, L - 1, k >> 3);
+        SVOXB_DBG(parent >= 0 && parent < lv.meta[0]);
         if (parent < cap_nodes) atomicMax(data + parent * 8 + (k & 7u), (int32_t)i);     // the largest point index wins
     }
 }

@@ -160,6 +160,7 @@ __device__ __forceinline__ unsigned refill(const RaySource& src, const float* of
                         id = min(max(a + __ldg(src.order + a + len - 1 - j), 0), (int)src.total - 1);   // (a list of another batch stays in bounds)
                     }
                 }
+                SVOXB_DBG(id >= 0 && (int64_t)id < src.total);
                 const float* o = src.origins + (int64_t)id * 3;
                 const float* d = src.dirs + (int64_t)id * 3;
                 ox = __ldg(o); oy = __ldg(o + 1); oz = __ldg(o + 2);
