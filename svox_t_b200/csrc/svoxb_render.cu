@@ -78,7 +78,9 @@ march_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restrict__ 
             } else {
                 int64_t idx; float delta_t, sigma;
                 sample<ACCEL>(tr, top, ray, opt.step, idx, delta_t, sigma);
-                if (sigma > opt.sigma_thresh) {                                   // rt_kernel.cu:279-320
+                // idx >= 0: an EMPTY leaf counts as sigma = 0 in the reference, which then dereferences a null row when the
+                // threshold is negative (rt_kernel.cu:278-304); here it is simply not a hit
+                if (idx >= 0 && sigma > opt.sigma_thresh) {                                   // rt_kernel.cu:279-320
                     const float att = expf(-delta_t * ray.ds * sigma);
                     w = T * (1.0f - att);
                     hit = true; hidx = (int)idx;
@@ -436,9 +438,11 @@ static int launch_bwd(const TreeArgs& tr, const RaySource& src, const MarchOpts&
 }
 
 template <bool IMAGE>
-static int dispatch_fwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, float* out, float* depth,
+static int dispatch_fwd(const TreeArgs& tr_in, const RaySource& src, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
-    if (quad_supported(tr)) return launch_fwd_quad(tr, src, m, IMAGE, out, depth, st);
+    if (quad_supported(tr_in)) return launch_fwd_quad(tr_in, src, m, IMAGE, out, depth, st);
+    TreeArgs tr = tr_in;
+    if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;     // the marks encode sigma > 0: too strict for this predicate
     const int K = (tr.D + 31) / 32;
 #define SVOXB_FWD(KK)                                                                        \
     case KK:                                                                                 \

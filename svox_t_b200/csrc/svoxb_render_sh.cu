@@ -155,7 +155,9 @@ march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, floa
             } else {
                 int64_t idx; float delta_t, sigma;
                 sample<ACCEL>(tr, top, ray, opt.step, idx, delta_t, sigma);
-                if (sigma > opt.sigma_thresh) {
+                // idx >= 0: an EMPTY leaf counts as sigma = 0 in the reference, which then dereferences a null row when the
+                // threshold is negative (rt_kernel.cu:278-304); here it is simply not a hit
+                if (idx >= 0 && sigma > opt.sigma_thresh) {
                     const float att = expf(-delta_t * ray.ds * sigma);
                     w = T * (1.0f - att);
                     hit = true; hidx = (int)idx;
@@ -382,7 +384,9 @@ motion_feature_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, JointArgs j
             } else {
                 int64_t idx; float delta_t, sigma;
                 sample<ACCEL>(tr, top, ray, opt.step, idx, delta_t, sigma);
-                if (sigma > opt.sigma_thresh) {
+                // idx >= 0: an EMPTY leaf counts as sigma = 0 in the reference, which then dereferences a null row when the
+                // threshold is negative (rt_kernel.cu:278-304); here it is simply not a hit
+                if (idx >= 0 && sigma > opt.sigma_thresh) {
                     const float att = expf(-delta_t * ray.ds * sigma);
                     w = T * (1.0f - att);
                     hit = true; hidx = (int)idx;

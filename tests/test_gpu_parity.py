@@ -603,11 +603,13 @@ def test_accumulate_weights_context(dev):
     assert abs(once - float(img[..., -1].sum())) <= 1e-3 * once and abs(twice - 2 * once) <= 1e-3 * once
 
 
-def test_hit_marks_are_an_exact_acceleration(dev):
+@pytest.mark.parametrize("D", [16, 13], ids=["row_kernels", "scalar_lane_kernels"])
+def test_hit_marks_are_an_exact_acceleration(dev, D):
     """Rows marked sigma <= 0 are skipped without being fetched: outputs and gradients do not change, stale marks are
-    not trusted after an in-place update of the features, and a negative sigma_thresh ignores them."""
+    not trusted after an in-place update of the features, and a negative sigma_thresh ignores them. (D = 13 without an
+    activated table takes the scalar-lane kernels, whose samples honour the marks too.)"""
     tr = synth.synth_tree(6, "ball")
-    D, Q = 16, 4096
+    Q = 4096
     f = synth.synth_features(tr["M"], D)
     o, d = synth.synth_rays(Q)
     g = cu(np.random.default_rng(2).standard_normal((Q, D)).astype(np.float32), dev)
