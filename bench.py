@@ -814,9 +814,11 @@ def extras_c5(sv, C, synth, orc, dev, peak, best, image_roofline):
     grad = torch.zeros_like(feats)
     lib, bopt = C.load_library(), opt._c(sigma_thresh=0.0, stop_thresh=-1.0)
 
-    def bwd():      # the march alone: the 8.4 GB zero-fill is a separate, trivially bandwidth-bound pass
-        C._check(lib.svoxb_render_rays_bwd(C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), C._ptr(d_t), Q,
-                                           C.ctypes.byref(bopt), C._ptr(gout), C._ptr(out), C._ptr(grad), C._stream()))
+    def bwd():      # the march alone (ordered by the forward's step counts, as VolumeRenderer's backward runs it): the
+        #             8.4 GB zero-fill is a separate, trivially bandwidth-bound pass
+        C._check(lib.svoxb_render_rays_bwd_cost(C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), C._ptr(d_t), Q,
+                                                C.ctypes.byref(bopt), C._ptr(gout), C._ptr(out), C._ptr(grad),
+                                                C._ptr(rs._cost), C._stream()))
     b_ms = best(bwd, 1, 3)
     z_ms = best(lambda: grad.zero_(), 1, 3)
     sel = np.arange(0, Q, Q // 4096)[:4096]

@@ -228,12 +228,12 @@ SVOXB_API int svoxb_render_rays_bwd(const svoxb_tree* tree, const float* origins
                           float* grad_features, void* stream);
 
 /* The same two calls for a forward/backward PAIR over one ray batch, sharing a scheduling hint (no reference
- * counterpart). For short batches -- svoxb_ray_order_min_rays() <= Q <= svoxb_ray_order_max_rays(), about 0.75 to 3 rays
- * per resident lane, e.g. one GPU's share of a batch split over 8 GPUs -- the forward also writes ray_cost[Q] (int32):
- * the ray indices in the order in which their marches ended (shortest first; the caller's order reversed when the
- * kernel that ran keeps no such list), and the backward marches the rays in the reverse of that list -- longest first
- * (svoxb_order.cu; 128 k rays on the C3 tree: 1.10 -> 0.79 ms). Other batch sizes neither write nor read ray_cost.
- * Results are those of the plain calls (only the lane a ray runs on changes). */
+ * counterpart). For batches of at least svoxb_ray_order_min_rays() rays (about 0.75 per resident lane) the forward also
+ * writes ray_cost[Q] (int32: the march iterations of each ray; ray_cost[0] = -1 when the kernel that ran cannot count)
+ * and the backward marches the rays longest first by that array (svoxb_order.cu): the rays of a warp are then alike
+ * and busy at the same time -- 2^20 rays on the C3 tree 6.15 -> 4.94 ms, 128 k rays (one GPU's share of a batch split
+ * over 8 GPUs) 1.10 -> 0.79 ms. Smaller batches neither write nor read ray_cost. Results are those of the plain calls
+ * (only the lane a ray runs on, and with it the order of the floating-point reductions, changes). */
 SVOXB_API int64_t svoxb_ray_order_max_rays(void);
 SVOXB_API int64_t svoxb_ray_order_min_rays(void);
 SVOXB_API int svoxb_render_rays_fwd_cost(const svoxb_tree* tree, const float* origins, const float* dirs, const float* vdirs,

@@ -32,11 +32,7 @@ struct RaySource {
     float ndc_focal;
     int chunk;                     // explicit rays: rays fetched from the queue per atomic (0 = RAY_CHUNK)
     const int* order;              // explicit rays, optional: queue position -> ray index (svoxb_order.cu: longest first)
-    int order_rev;                 // read `order` back to front (the forward's completion list: shortest rays first)
-    int order_k;                   // `order` holds order_k completion lists of consecutive ray ranges (balanced split of
-                                   // `total`), entries relative to their range: interleave them from their tails
-    int* done_list;                // explicit rays, optional [Q]: the forward appends every ray's index when it ends
-    unsigned long long* done_count;    // ... at the position this counter hands out
+    int* steps_out;                // explicit rays, optional [Q]: march iterations of each ray, written by the forward
 };
 
 struct ViewDir {
@@ -149,17 +145,7 @@ __device__ __forceinline__ unsigned refill(const RaySource& src, const float* of
                 }
             } else {
                 valid = true;
-                int id = pos;
-                if (src.order) {
-                    if (!src.order_rev) {
-                        id = __ldg(src.order + pos);
-                    } else {        // K completion lists (shortest first) of balanced consecutive ranges, longest rays first
-                        const int K = src.order_k, base = (int)(src.total / K), rem = (int)(src.total % K);
-                        const int k = pos < K * base ? pos % K : pos - K * base, j = pos < K * base ? pos / K : base;
-                        const int a = k * base + min(k, rem), len = base + (k < rem ? 1 : 0);
-                        id = min(max(a + __ldg(src.order + a + len - 1 - j), 0), (int)src.total - 1);   // (a list of another batch stays in bounds)
-                    }
-                }
+                const int id = src.order ? __ldg(src.order + pos) : pos;
                 SVOXB_DBG(id >= 0 && (int64_t)id < src.total);
                 const float* o = src.origins + (int64_t)id * 3;
                 const float* d = src.dirs + (int64_t)id * 3;
@@ -364,14 +350,12 @@ static int persistent_grid(Kern kern, size_t smem, int64_t queue_len, int& grid,
 
 // Quad-lane kernels (svoxb_render_q.cu): D % 4 == 0 (4 <= D <= 128), or any D <= 128 with the padded activated table.
 bool quad_supported(const TreeArgs& tr);
-// svoxb_order.cu: longest-first order of a short explicit ray batch for the backward = the forward's completion list
-// read back to front
+// svoxb_order.cu: longest-first order of an explicit ray batch for the backward, from the forward's exact per-ray
+// iteration counts (stream-ordered scratch, released by the caller)
 bool want_ray_order(const TreeArgs& tr, int64_t Q);
 int64_t ray_order_max_rays();
 int64_t ray_order_min_rays();
-int fill_reverse_identity(int* list, int64_t Q, int K, cudaStream_t st);
-// svoxb_render_q.cu: number of launches (= completion lists) the list-keeping forward splits a batch of Q rays into
-int count_chunks(const TreeArgs& tr, int64_t Q, bool depth);
+int build_ray_order(const int* cost, int64_t Q, int** order, cudaStream_t st);
 int launch_fwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, float* out,
                     float* depth, cudaStream_t st);
 int launch_bwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, const float* grad_out,

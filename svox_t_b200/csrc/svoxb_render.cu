@@ -496,9 +496,9 @@ static int render_rays_fwd_impl(const svoxb_tree* tree, const float* origins, co
     // ordered by (svoxb_order.cu); the forward itself runs in the caller's order
     cudaStream_t st = (cudaStream_t)stream;
     if (ray_cost != nullptr && want_ray_order(tr, Q)) {
-        // identity order first; a forward kernel that keeps the completion list overwrites every entry
-        rc = fill_reverse_identity(ray_cost, Q, count_chunks(tr, Q, false), st); if (rc) return rc;
-        src.done_list = ray_cost;
+        // ray_cost[0] = -1 until a kernel that counts overwrites it: the backward then keeps the caller's order
+        SVOXB_CUDA(cudaMemsetAsync(ray_cost, 0xff, sizeof(int32_t), st));
+        src.steps_out = ray_cost;
     }
     if (opt->format != SVOXB_FORMAT_RGBA) rc = fmt_render_fwd(tree, tr, src, m, opt, false, out, st);
     else rc = dispatch_fwd<false>(tr, src, m, out, depth, st);
@@ -534,13 +534,15 @@ static int render_rays_bwd_impl(const svoxb_tree* tree, const float* origins, co
         SVOXB_REQUIRE(vdirs != nullptr, "view-dependent formats need vdirs");
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (ray_cost != nullptr && want_ray_order(tr, Q)) {     // the forward's completion list, longest ray = last entry
-        src.order = ray_cost;
-        src.order_rev = 1;
-        src.order_k = count_chunks(tr, Q, false);
+    int* order = nullptr;
+    if (ray_cost != nullptr && want_ray_order(tr, Q)) {
+        rc = build_ray_order(ray_cost, Q, &order, st);
+        if (rc) return rc;
     }
+    src.order = order;
     if (opt->format != SVOXB_FORMAT_RGBA) rc = fmt_render_bwd(tree, tr, src, m, opt, false, grad_out, saved_out, grad_features, st);
     else rc = dispatch_bwd<false>(tr, src, m, grad_out, saved_out, grad_features, st);
+    if (order) cudaFreeAsync(order, st);
     return rc;
 }
 

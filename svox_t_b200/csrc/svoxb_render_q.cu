@@ -190,18 +190,13 @@ __device__ __forceinline__ RowBlk<V4> load_row_block(const char* p, uint64_t pol
 // multiple of 4 floats: 16-byte aligned rows, D = 33 is served like D = 32), sigma comes from the compact sigma[M]
 // array next to it (one 4-byte gather per candidate, L2-resident), and the output rows / gradient rows of the
 // caller's unaligned [M, D] layout are written channel by channel.
-// COUNT: also append every ray's index to a list when it ends (RaySource::done_list). With about one ray per lane all
-// rays start together, so the list is sorted by march length; the backward over the same batch reads it back to front --
-// longest ray first (svoxb_order.cu). Nothing is carried through the loop: 72 registers, 28 warps, like the plain kernel.
-// A real call on purpose: inlined, these few instructions perturb the register allocation of the whole 72-register loop
-// into spilling (16-24 bytes, reloaded every iteration); as a call the live registers are saved around this cold site only.
-__device__ __noinline__ void append_done(int* __restrict__ list, unsigned long long* __restrict__ count, unsigned fm,
-                                         bool mine, int row) {
-    const int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(fm));
-    base = __shfl_sync(FULL, base, 0);
-    if (mine) list[base + __popc(fm & ((1u << lane) - 1u))] = row;
+// COUNT: also write the number of march iterations of every ray (RaySource::steps_out) -- the exact per-ray cost the
+// backward over the same batch is ordered by (svoxb_order.cu). One counter register per lane; the store is a real call
+// on purpose: inlined, those few instructions perturb the register allocation of the whole 72-register loop into
+// spilling (16-24 bytes, reloaded every iteration: 0.45 -> 0.53 ms at 131 072 rays); as a call the live registers are
+// saved around this cold site only and the kernel keeps 72 registers, no stack, 28 warps.
+__device__ __noinline__ void store_steps(int* __restrict__ steps_out, bool mine, int row, int steps) {
+    if (mine) steps_out[row] = steps;
 }
 
 template <int LPR, int V4, bool ACCEL, bool IMAGE, bool DEPTH, bool AL, bool COUNT = false>
@@ -240,6 +235,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     float T = 1.0f, p_dt = 0.0f, p_t = 0.0f;
     int row = 0, p_idx = -1;
     bool active = false, got_depth = false, trav_done = true;
+    [[maybe_unused]] int steps = 0;
     Queue qu{0, 0, false};
     unsigned need = FULL;
 
@@ -248,6 +244,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
             const unsigned got = refill<IMAGE>(src, off, scl, counter, qu, need, lane, ray, row);
             if ((got >> lane) & 1u) {
                 active = true; trav_done = false; T = 1.0f; got_depth = false;
+                if constexpr (COUNT) steps = 0;
                 if (DEPTH) depth[row] = 0.0f;           // overwritten at the first hit, if any
             }
             need = 0;
@@ -334,6 +331,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                 if (DEPTH) n_t = ray.t;
                 probe_end<ACCEL, 3>(tr, pb, ray, opt.step, n_idx, n_dt);
                 ray.t += n_dt;
+                if constexpr (COUNT) ++steps;
                 if (!(ray.t < ray.tmax)) trav_done = true;
             }
         }
@@ -379,8 +377,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                     }
                 }
             }
-            // completion list: the rays that end now take the next popc(fm) positions
-            if constexpr (COUNT) append_done(src.done_list, src.done_count, fm, fin != 0, row);
+            if constexpr (COUNT) store_steps(src.steps_out, fin != 0, row, steps);
             if (fin != 0) {
                 if constexpr (!AL) __stcs(out + (int64_t)row * D + (D - 1), 1.0f - T);   // opacity, by the owner lane
                 active = false;
@@ -641,45 +638,14 @@ static int pow2ceil(int n) {
     return l;
 }
 
-// Lanes of the list-keeping forward (one CTA per SM): a launch of at most this many rays starts them all at once, so
-// its completion list is sorted by march length. Mirrors Quad<>::FWD_THREADS.
-static int64_t fwd_list_lanes(int D) {
-    const int dp = 4 * pow2ceil((D + 3) / 4);
-    const int threads = dp <= 32 ? SVOXB_FWD_THREADS32 : (dp <= 64 ? SVOXB_THREADS64 : SVOXB_THREADS128);
-    return (int64_t)sm_count() * threads;
-}
-
-int count_chunks(const TreeArgs& tr, int64_t Q, bool depth) {
-    if (!(tr.use_accel && tr.D % 4 == 0 && tr.D >= 4 && tr.D <= 128 && !depth)) return 1;    // no list is kept: one range
-    return (int)max((int64_t)1, (Q + fwd_list_lanes(tr.D) - 1) / fwd_list_lanes(tr.D));
-}
-
 template <int LPR, int V4, bool ACCEL, bool IMAGE, bool AL>
 static int launch_fwd_q(const TreeArgs& tr, const RaySource& src_in, const MarchOpts& m, float* out, float* depth,
                         cudaStream_t st) {
     using G = Quad<LPR, V4>;
-    if constexpr (ACCEL && !IMAGE && AL) {
-        // list-keeping forward over more rays than lanes: K launches over balanced consecutive ranges (svoxb_order.cu)
-        const int K = (src_in.done_list != nullptr && !depth) ? count_chunks(tr, src_in.total, false) : 1;
-        if (K > 1) {
-            const int64_t base = src_in.total / K, rem = src_in.total % K;
-            for (int k = 0; k < K; ++k) {
-                const int64_t a = k * base + min((int64_t)k, rem), len = base + (k < rem ? 1 : 0);
-                RaySource sub = src_in;
-                sub.origins += 3 * a; sub.dirs += 3 * a;
-                if (sub.vdirs) sub.vdirs += 3 * a;
-                sub.done_list += a;
-                sub.total = len;
-                const int rc = launch_fwd_q<LPR, V4, ACCEL, IMAGE, AL>(tr, sub, m, out + a * tr.D, nullptr, st);
-                if (rc) return rc;
-            }
-            return 0;
-        }
-    }
     RaySource src = src_in;
     src.chunk = chunk_for(src, IMAGE);
     bool count = false;
-    if constexpr (ACCEL && !IMAGE && AL) count = src.done_list != nullptr && !depth;
+    if constexpr (ACCEL && !IMAGE && AL) count = src.steps_out != nullptr && !depth;
     const int threads = threads_for((depth || !AL) ? G::THREADS : G::FWD_THREADS, src.total, src.chunk, "SVOXB_FWD_THREADS_CAP");
     const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float4) * (threads / 32) * 32 * LPR * V4;
     void (*kern)(TreeArgs, RaySource, MarchOpts, float*, float*, unsigned long long*);
@@ -688,12 +654,7 @@ static int launch_fwd_q(const TreeArgs& tr, const RaySource& src_in, const March
     if constexpr (ACCEL && !IMAGE && AL) {
         if (count) kern = march_fwd_quad_kernel<LPR, V4, ACCEL, IMAGE, false, AL, true>;
     }
-    if (count) {
-        src.done_count = work_counter(st);
-        if (!src.done_count) return SVOXB_ECUDA;
-    } else {
-        src.done_list = nullptr;
-    }
+    if (!count) src.steps_out = nullptr;
     int grid = 0;
     int rc = persistent_grid(kern, smem, src.total, grid, threads, carveout_kb(smem), src.chunk);
     if (rc) return rc;

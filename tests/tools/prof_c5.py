@@ -37,8 +37,9 @@ def run(tag=""):
         e[0].record()
         out = C.volume_render(ts, rs, opt)
         e[1].record()
-        C._check(lib.svoxb_render_rays_bwd(C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), C._ptr(d_t), Q,
-                                           C.ctypes.byref(bopt), C._ptr(gout), C._ptr(out), C._ptr(grad), C._stream()))
+        C._check(lib.svoxb_render_rays_bwd_cost(C.ctypes.byref(ts._c()), C._ptr(o_t), C._ptr(d_t), C._ptr(d_t), Q,
+                                                C.ctypes.byref(bopt), C._ptr(gout), C._ptr(out), C._ptr(grad),
+                                                C._ptr(rs._cost), C._stream()))
         e[2].record()
         C.volume_render_image_with_depth(ts, cs, opt)
         e[3].record()
