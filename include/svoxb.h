@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SVOXB_ABI_VERSION 9
+#define SVOXB_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define SVOXB_API __attribute__((visibility("default")))
@@ -220,9 +220,11 @@ SVOXB_API int svoxb_render_rays_fwd(const svoxb_tree* tree, const float* origins
  * from it and cannot tell a stale or foreign buffer from the right one (the result would be plausible, wrong sigma
  * gradients). When in doubt, render again with those options and pass the fresh output. The caller zero-fills
  * grad_features (the reference allocates zeros_like(features), rt_kernel.cu:1415).
- * Limits of this build (stated once for every march entry point): float32 only -- the reference also instantiates
- * float64 (AT_DISPATCH_FLOATING_TYPES, rt_kernel.cu:1373); 2 <= D <= 128 -- the reference loops over any width
- * (rt_kernel.cu:302-306); wider tables fail with SVOXB_EINVAL ("feature width D=... is not supported"). */
+ * Widths and types (stated once for every march entry point): the RGBA format takes any D >= 2, like the reference's
+ * loop over out_data_dim (rt_kernel.cu:302-306) -- D <= 128 runs on the tuned register / shared-memory kernels, wider
+ * tables on the general kernels of svoxb_render_wide.cu (no accelerator, no NDC; same results, several times slower per
+ * byte). These entry points are float32; the reference's float64 instantiation (AT_DISPATCH_FLOATING_TYPES,
+ * rt_kernel.cu:1373) is the *_f64 family at the end of this header. */
 SVOXB_API int svoxb_render_rays_bwd(const svoxb_tree* tree, const float* origins, const float* dirs, const float* vdirs,
                           int64_t Q, const svoxb_render_options* opt, const float* grad_out, const float* saved_out,
                           float* grad_features, void* stream);
@@ -361,6 +363,49 @@ SVOXB_API size_t svoxb_build_dense_work_bytes(int32_t L);
 SVOXB_API int svoxb_build_dense(const float* pts, int64_t P, int32_t L, const float* offset, const float* scaling,
                       void* work, int64_t cap_nodes, int32_t* child, int32_t* data, int32_t* parent_depth,
                       int64_t* status_dev, void* stream);
+
+/* ---- float64 instantiation of the hot path ------------------------------------------------------------------- */
+/* The reference dispatches AT_DISPATCH_FLOATING_TYPES on every entry point (rt_kernel.cu:1373, 1413, 1517;
+ * svox_kernel.cu:290): features, offset, scaling, rays and outputs double, child / data int32, options unchanged
+ * (float fields, promoted). These are that instantiation for the RGBA format: point query, ray-batch and camera
+ * forward / backward, depth. Same argument meaning as the float32 calls above (saved_out = the forward output under the
+ * backward's predicate, caller-zeroed grad_features, band cameras); no accelerator, no NDC, any D >= 2, any N.
+ * Arithmetic is true fp64 throughout -- the reference's own double build calls expf() on doubles (rt_kernel.cu:280,
+ * 304), so it is float-accurate only; results agree with it to ~1e-6 and with an fp64 evaluation to ~1e-12. */
+typedef struct svoxb_tree_f64 {
+    const double* features;     /* [M, D] float64; last channel = sigma                              */
+    int64_t M;
+    int32_t D;
+    int32_t N;
+    const int32_t* child;       /* [n_nodes, N, N, N]                                                */
+    const int32_t* data;        /* [n_nodes, N, N, N, 1]                                             */
+    int64_t n_nodes;
+    int64_t n_internal;
+    const double* offset;       /* [3] device                                                        */
+    const double* scaling;      /* [3] device                                                        */
+} svoxb_tree_f64;
+
+typedef struct svoxb_camera_f64 {
+    const double* c2w;          /* device, row-major [3 or 4, 4]                                     */
+    double fx, fy;
+    int32_t width, height;
+    int32_t row_begin, row_end; /* as svoxb_camera                                                   */
+} svoxb_camera_f64;
+
+SVOXB_API int svoxb_query_f64(const svoxb_tree_f64* tree, const double* pts, int64_t Q, double* values,
+                    int64_t* node_ids, int64_t* data_ids, uint8_t* slot_mask, void* stream);
+SVOXB_API int svoxb_render_rays_fwd_f64(const svoxb_tree_f64* tree, const double* origins, const double* dirs, int64_t Q,
+                              const svoxb_render_options* opt, double* out, double* depth, void* stream);
+SVOXB_API int svoxb_render_rays_bwd_f64(const svoxb_tree_f64* tree, const double* origins, const double* dirs, int64_t Q,
+                              const svoxb_render_options* opt, const double* grad_out, const double* saved_out,
+                              double* grad_features, void* stream);
+SVOXB_API int svoxb_render_image_fwd_f64(const svoxb_tree_f64* tree, const svoxb_camera_f64* cam,
+                               const svoxb_render_options* opt, double* out, double* depth, void* stream);
+SVOXB_API int svoxb_render_image_bwd_f64(const svoxb_tree_f64* tree, const svoxb_camera_f64* cam,
+                               const svoxb_render_options* opt, const double* grad_out, const double* saved_out,
+                               double* grad_features, void* stream);
+SVOXB_API int svoxb_render_depth_f64(const svoxb_tree_f64* tree, const double* origins, const double* dirs, int64_t Q,
+                           const svoxb_render_options* opt, double* depth, void* stream);
 
 /* ---- multi-GPU exchange (no reference counterpart: the reference is single-GPU) --------------- */
 /* The path's one exchange step: the leaf-gradient table grad[M, D] -- the reference's

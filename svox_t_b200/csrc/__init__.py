@@ -7,7 +7,9 @@ torch tensors, allocates its outputs on the inputs' device (as the reference doe
 and raises ``RuntimeError`` on a failed check. Differences, all deliberate:
 
 * kernels launch on torch's *current* stream (the reference uses the legacy default stream);
-* only float32 is implemented (the reference also instantiates float64);
+* float64 (the reference dispatches AT_DISPATCH_FLOATING_TYPES) is implemented for the hot path proper -- point query,
+  ray-batch / camera render forward + backward, depth, RGBA format -- on the general kernels (``*_f64`` entry points); the
+  other operators are float32 only and say so;
 * there is NO CPU fallback: a missing ``libsvoxb.so`` or a non-CUDA tensor is an error, never a slow path.
 
 PyTorch is plumbing here (device memory, streams); all compute happens in hand-written sm_100a kernels.
@@ -37,6 +39,20 @@ class _CTree(ctypes.Structure):
     ]
 
 
+class _CTree64(ctypes.Structure):
+    _fields_ = [
+        ("features", ctypes.c_void_p), ("M", ctypes.c_int64), ("D", ctypes.c_int32), ("N", ctypes.c_int32),
+        ("child", ctypes.c_void_p), ("data", ctypes.c_void_p), ("n_nodes", ctypes.c_int64), ("n_internal", ctypes.c_int64),
+        ("offset", ctypes.c_void_p), ("scaling", ctypes.c_void_p),
+    ]
+
+
+class _CCamera64(ctypes.Structure):
+    _fields_ = [("c2w", ctypes.c_void_p), ("fx", ctypes.c_double), ("fy", ctypes.c_double),
+                ("width", ctypes.c_int32), ("height", ctypes.c_int32),
+                ("row_begin", ctypes.c_int32), ("row_end", ctypes.c_int32)]
+
+
 class _COptions(ctypes.Structure):
     _fields_ = [
         ("step_size", ctypes.c_float), ("background_brightness", ctypes.c_float),
@@ -62,6 +78,7 @@ class _CCamera(ctypes.Structure):
 # Every symbol include/svoxb.h declares: (restype, argtypes). tests/test_cabi.py checks the list against the header.
 _VP, _I64, _I32, _F = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float
 _PT, _PO, _PC = ctypes.POINTER(_CTree), ctypes.POINTER(_COptions), ctypes.POINTER(_CCamera)
+_PT64, _PC64 = ctypes.POINTER(_CTree64), ctypes.POINTER(_CCamera64)
 SYMBOLS = {
     "svoxb_abi_version": (ctypes.c_int, []),
     "svoxb_last_error": (ctypes.c_char_p, []),
@@ -111,6 +128,12 @@ SYMBOLS = {
     "svoxb_exchange_max_blocks": (ctypes.c_int, []),
     "svoxb_exchange_sum": (ctypes.c_int, [ctypes.POINTER(_CPeerGroup), _I64, _VP]),
     "svoxb_exchange_sum_rows": (ctypes.c_int, [ctypes.POINTER(_CPeerGroup), _I64, _I32, _VP, _VP]),
+    "svoxb_query_f64": (ctypes.c_int, [_PT64, _VP, _I64, _VP, _VP, _VP, _VP, _VP]),
+    "svoxb_render_rays_fwd_f64": (ctypes.c_int, [_PT64, _VP, _VP, _I64, _PO, _VP, _VP, _VP]),
+    "svoxb_render_rays_bwd_f64": (ctypes.c_int, [_PT64, _VP, _VP, _I64, _PO, _VP, _VP, _VP, _VP]),
+    "svoxb_render_image_fwd_f64": (ctypes.c_int, [_PT64, _PC64, _PO, _VP, _VP, _VP]),
+    "svoxb_render_image_bwd_f64": (ctypes.c_int, [_PT64, _PC64, _PO, _VP, _VP, _VP, _VP]),
+    "svoxb_render_depth_f64": (ctypes.c_int, [_PT64, _VP, _VP, _I64, _PO, _VP, _VP]),
     "svoxb_build_work_bytes": (ctypes.c_size_t, [_I64, _I32]),
     "svoxb_build_octree_count": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP, _VP, ctypes.POINTER(_I64), _VP]),
     "svoxb_build_octree_emit": (ctypes.c_int, [_I64, _I32, _VP, _I64, _VP, _VP, _VP, _VP]),
@@ -135,7 +158,7 @@ def load_library():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.svoxb_abi_version() != 9:
+        if lib.svoxb_abi_version() != 10:
             raise ImportError("svox_t_b200: libsvoxb.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib
@@ -173,7 +196,9 @@ def _check_input(t, name, dtype=None):
     if not t.is_contiguous():
         raise RuntimeError(f"{name} must be contiguous")
     if dtype is not None and t.dtype != dtype:
-        raise RuntimeError(f"{name} must be {dtype} (got {t.dtype}); only float32 features/rays are implemented")
+        raise RuntimeError(f"{name} must be {dtype} (got {t.dtype}): features, offset, scaling, rays / points and "
+                           "gradients must share one floating type (float32 everywhere; float64 for the point query, the "
+                           "RGBA render forward / backward and depth)")
 
 
 class _TensorIdentity:
@@ -206,9 +231,9 @@ class RaysSpec:
         self._cost = None           # svox_t_b200 extension: per-ray march cost written by the forward (short batches), the
                                     # backward's scheduling hint (svoxb_render_rays_fwd_cost / _bwd_cost)
 
-    def check(self):
+    def check(self, dtype=torch.float32):
         for n in ("origins", "dirs", "vdirs"):
-            _check_input(getattr(self, n), n, torch.float32)
+            _check_input(getattr(self, n), n, dtype)
 
 
 class TreeSpec:
@@ -231,6 +256,25 @@ class TreeSpec:
         self._accel = None          # svox_t_b200 extension: Accel handle cached by N3Tree (None = reference walk)
         self._act = None            # svox_t_b200 extension: Activated table for `features` (None = sigmoid in-kernel)
         self._sigma = None          # svox_t_b200 extension: SigmaTable (compact sigma array) for the sigma-only marches
+
+    @property
+    def is_f64(self):
+        """float64 instantiation (AT_DISPATCH_FLOATING_TYPES in the reference): decided by the feature table."""
+        return isinstance(self.features, torch.Tensor) and self.features.dtype == torch.float64
+
+    def _c64(self):
+        """svoxb_tree_f64: the double-precision view of the tree (general kernels: no accelerator, no derived tables)."""
+        _check_input(self.features, "features", torch.float64)
+        _check_input(self.data, "data", torch.int32)
+        _check_input(self.child, "child", torch.int32)
+        _check_input(self.offset, "offset", torch.float64)
+        _check_input(self.scaling, "scaling", torch.float64)
+        if self.features.dim() != 2 or self.child.dim() != 4:
+            raise RuntimeError("features must be [M, D] and child [n, N, N, N]")
+        return _CTree64(features=_ptr(self.features), M=self.features.shape[0], D=self.features.shape[1],
+                        N=self.child.shape[1], child=_ptr(self.child), data=_ptr(self.data),
+                        n_nodes=self.child.shape[0], n_internal=int(self.n_internal),
+                        offset=_ptr(self.offset), scaling=_ptr(self.scaling))
 
     def check(self):
         _check_input(self.features, "features", torch.float32)
@@ -297,6 +341,13 @@ class CameraSpec:
         _check_input(self.c2w, "c2w", torch.float32)
         if self.c2w.dim() != 2 or self.c2w.shape[1] != 4 or self.c2w.shape[0] < 3:
             raise RuntimeError("c2w must be [3 or 4, 4]")
+
+    def _c64(self):
+        _check_input(self.c2w, "c2w", torch.float64)
+        if self.c2w.dim() != 2 or self.c2w.shape[1] != 4 or self.c2w.shape[0] < 3:
+            raise RuntimeError("c2w must be [3 or 4, 4]")
+        return _CCamera64(c2w=_ptr(self.c2w), fx=float(self.fx), fy=float(self.fy), width=int(self.width),
+                          height=int(self.height), row_begin=int(self.row_begin), row_end=int(self.row_end))
 
     def _c(self):
         self.check()
@@ -459,21 +510,23 @@ def query_vertical(tree, indices):
     """(values[Q,D], node_ids[Q] i64, data_ids[Q] i64, leaf_node[n_hit,4] i64) -- svox_kernel.cu:274-324.
     Rows of ``values`` / ``data_ids`` whose leaf is empty are zero / -1 here (uninitialised in the reference)."""
     lib = load_library()
-    _check_input(indices, "indices", torch.float32)
+    f64 = tree.is_f64
+    real = torch.float64 if f64 else torch.float32
+    _check_input(indices, "indices", real)
     if indices.dim() != 2 or indices.shape[1] != 3:
         raise RuntimeError("indices must be [Q, 3]")
-    ct = tree._c()
+    ct = tree._c64() if f64 else tree._c()
     dev = indices.device
     Q, D = indices.shape[0], tree.features.shape[1]
     N = tree.child.shape[1]
     with torch.cuda.device(dev):
-        values = torch.zeros((Q, D), dtype=torch.float32, device=dev)
+        values = torch.zeros((Q, D), dtype=real, device=dev)
         node_ids = torch.empty((Q,), dtype=torch.int64, device=dev)
         data_ids = torch.full((Q,), -1, dtype=torch.int64, device=dev)
         n_slots = int(tree.n_internal) * N ** 3
         mask = torch.zeros((n_slots,), dtype=torch.uint8, device=dev)
-        _check(lib.svoxb_query(ctypes.byref(ct), _ptr(indices), Q, _ptr(values), _ptr(node_ids), _ptr(data_ids),
-                               _ptr(mask), _stream()))
+        _check((lib.svoxb_query_f64 if f64 else lib.svoxb_query)(
+            ctypes.byref(ct), _ptr(indices), Q, _ptr(values), _ptr(node_ids), _ptr(data_ids), _ptr(mask), _stream()))
         scratch = torch.empty((lib.svoxb_leafset_scratch_bytes(n_slots),), dtype=torch.uint8, device=dev)
         n_hit = torch.zeros((1,), dtype=torch.int64, device=dev)
         _check(lib.svoxb_leafset_scan(_ptr(mask), n_slots, _ptr(scratch), _ptr(n_hit), _stream()))
@@ -525,7 +578,31 @@ def _order_range():
     return _ORDER_RANGE
 
 
+def _require_rgba_f64(opt):
+    if int(opt.format) != FORMAT_RGBA:
+        raise RuntimeError("svox_t_b200.csrc: float64 is implemented for the RGBA format only (view-dependent formats "
+                           "are float32)")
+
+
+def _render_fwd_f64(tree, rays, opt, want_depth, c_opt=None):
+    lib = load_library()
+    _require_rgba_f64(opt)
+    rays.check(torch.float64)
+    ct = tree._c64()
+    Q, D = rays.origins.shape[0], tree.features.shape[1]
+    dev = rays.origins.device
+    with torch.cuda.device(dev):
+        out = torch.empty((Q, D), dtype=torch.float64, device=dev)
+        depth = torch.empty((Q, 1), dtype=torch.float64, device=dev) if want_depth else None
+        _check(lib.svoxb_render_rays_fwd_f64(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q,
+                                             ctypes.byref(c_opt if c_opt is not None else opt._c()), _ptr(out),
+                                             _ptr(depth), _stream()))
+    return out, depth
+
+
 def _render_fwd(tree, rays, opt, want_depth):
+    if tree.is_f64:
+        return _render_fwd_f64(tree, rays, opt, want_depth)
     lib = load_library()
     rays.check()
     ct = tree._c()
@@ -568,7 +645,7 @@ def _saved_out_for_backward(tree, opt, fwd_out, render_again, expect_shape=None)
     # backward reads T_end = 1 - out[:, D-1] and <grad_out, out> from it. Anything else (None, another shape, another
     # dtype / device) is not trusted and the state is re-rendered.
     if (fwd_out is not None and expect_shape is not None and tuple(fwd_out.shape) == tuple(expect_shape)
-            and fwd_out.dtype == torch.float32 and fwd_out.is_cuda and fwd_out.is_contiguous()
+            and fwd_out.dtype == tree.features.dtype and fwd_out.is_cuda and fwd_out.is_contiguous()
             and opt.sigma_thresh == 0.0 and opt.stop_thresh <= 0.0):
         return fwd_out
     return render_again()
@@ -577,6 +654,20 @@ def _saved_out_for_backward(tree, opt, fwd_out, render_again, expect_shape=None)
 def volume_render_backward(tree, rays, opt, grad_output, saved_out=None):
     """[M, D] dL/dfeatures (rt_kernel.cu:1402-1426). ``saved_out`` = the forward output, if the caller kept it."""
     lib = load_library()
+    if tree.is_f64:
+        _require_rgba_f64(opt)
+        rays.check(torch.float64)
+        _check_input(grad_output, "grad_output", torch.float64)
+        ct = tree._c64()
+        Q = rays.origins.shape[0]
+        bopt = opt._c(sigma_thresh=0.0, stop_thresh=-1.0)
+        with torch.cuda.device(rays.origins.device):
+            so = _saved_out_for_backward(tree, opt, saved_out, lambda: _render_fwd_f64(tree, rays, opt, False, bopt)[0],
+                                         grad_output.shape)
+            grad = torch.zeros_like(tree.features)
+            _check(lib.svoxb_render_rays_bwd_f64(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q,
+                                                 ctypes.byref(bopt), _ptr(grad_output), _ptr(so), _ptr(grad), _stream()))
+        return grad
     rays.check()
     _check_input(grad_output, "grad_output", torch.float32)
     ct = tree._c()
@@ -614,7 +705,24 @@ def volume_render_backward(tree, rays, opt, grad_output, saved_out=None):
     return grad
 
 
+def _render_image_fwd_f64(tree, cam, opt, want_depth, c_opt=None):
+    lib = load_library()
+    _require_rgba_f64(opt)
+    ct, cc = tree._c64(), cam._c64()
+    dev = tree.features.device
+    D = tree.features.shape[1]
+    with torch.cuda.device(dev):
+        out = torch.empty((cam.rows, cam.width, D), dtype=torch.float64, device=dev)
+        depth = torch.empty((cam.rows, cam.width, 1), dtype=torch.float64, device=dev) if want_depth else None
+        _check(lib.svoxb_render_image_fwd_f64(ctypes.byref(ct), ctypes.byref(cc),
+                                              ctypes.byref(c_opt if c_opt is not None else opt._c()), _ptr(out),
+                                              _ptr(depth), _stream()))
+    return out, depth
+
+
 def _render_image_fwd(tree, cam, opt, want_depth):
+    if tree.is_f64:
+        return _render_image_fwd_f64(tree, cam, opt, want_depth)
     lib = load_library()
     ct, cc = tree._c(), cam._c()
     dev = tree.features.device
@@ -641,6 +749,18 @@ def volume_render_image_with_depth(tree, cam, opt):
 
 def volume_render_image_backward(tree, cam, opt, grad_output, saved_out=None):
     lib = load_library()
+    if tree.is_f64:
+        _require_rgba_f64(opt)
+        _check_input(grad_output, "grad_output", torch.float64)
+        ct, cc = tree._c64(), cam._c64()
+        bopt = opt._c(sigma_thresh=0.0, stop_thresh=-1.0)
+        with torch.cuda.device(tree.features.device):
+            so = _saved_out_for_backward(tree, opt, saved_out,
+                                         lambda: _render_image_fwd_f64(tree, cam, opt, False, bopt)[0], grad_output.shape)
+            grad = torch.zeros_like(tree.features)
+            _check(lib.svoxb_render_image_bwd_f64(ctypes.byref(ct), ctypes.byref(cc), ctypes.byref(bopt),
+                                                  _ptr(grad_output), _ptr(so), _ptr(grad), _stream()))
+        return grad
     _check_input(grad_output, "grad_output", torch.float32)
     ct, cc = tree._c(), cam._c()
     dev = tree.features.device
@@ -663,6 +783,15 @@ def volume_render_image_backward(tree, cam, opt, grad_output, saved_out=None):
 def render_depth(tree, rays, opt):
     """[Q, 1] first-hit depth (rt_kernel.cu:1506-1523)."""
     lib = load_library()
+    if tree.is_f64:
+        rays.check(torch.float64)
+        ct = tree._c64()
+        Q = rays.origins.shape[0]
+        with torch.cuda.device(rays.origins.device):
+            depth = torch.empty((Q, 1), dtype=torch.float64, device=rays.origins.device)
+            _check(lib.svoxb_render_depth_f64(ctypes.byref(ct), _ptr(rays.origins), _ptr(rays.dirs), Q,
+                                              ctypes.byref(opt._c()), _ptr(depth), _stream()))
+        return depth
     rays.check()
     ct = tree._c()
     Q = rays.origins.shape[0]

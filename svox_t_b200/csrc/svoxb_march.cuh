@@ -360,5 +360,10 @@ int launch_fwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m
                     float* depth, cudaStream_t st);
 int launch_bwd_quad(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, const float* grad_out,
                     const float* saved_out, float* grad, cudaStream_t st);
+// General kernels (svoxb_render_wide.cu): any D, walk over child/data; the float32 route for D > 128.
+int launch_fwd_wide(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, float* out,
+                    float* depth, cudaStream_t st);
+int launch_bwd_wide(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, bool image, const float* grad_out,
+                    const float* saved_out, float* grad, cudaStream_t st);
 
 }  // namespace svoxb

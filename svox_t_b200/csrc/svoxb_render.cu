@@ -453,8 +453,7 @@ static int dispatch_fwd(const TreeArgs& tr_in, const RaySource& src, const March
         default: break;
     }
 #undef SVOXB_FWD
-    set_error("feature width D=%d not supported (max 128)", tr.D);
-    return SVOXB_EINVAL;
+    return launch_fwd_wide(tr, src, m, IMAGE, out, depth, st);      // D > 128: svoxb_render_wide.cu
 }
 
 template <bool IMAGE>
@@ -471,8 +470,7 @@ static int dispatch_bwd(const TreeArgs& tr, const RaySource& src, const MarchOpt
         default: break;
     }
 #undef SVOXB_BWD
-    set_error("feature width D=%d not supported (max 128)", tr.D);
-    return SVOXB_EINVAL;
+    return launch_bwd_wide(tr, src, m, IMAGE, go, so, grad, st);      // D > 128: svoxb_render_wide.cu
 }
 
 }  // namespace svoxb

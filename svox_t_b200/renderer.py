@@ -153,7 +153,7 @@ class VolumeRenderer(nn.Module):
         ts = self.tree._spec(features, **kw)
         ts._grad_exchange = getattr(self, "leaf_grad_exchange", None)
         M, D = features.shape
-        if n_rays * 32 >= M and features.is_cuda:
+        if n_rays * 32 >= M and features.is_cuda and features.dtype == torch.float32:
             if self.data_format.format == DataFormat.RGBA and 2 <= D <= 128:
                 # one pass over the rows: activated table + hit marks (+ zero-fill of the exchange's gradient table when
                 # this forward will be back-propagated)
@@ -167,7 +167,7 @@ class VolumeRenderer(nn.Module):
         """TreeSpec for the marches that only read sigma (depth, opacity, motion): for batches large enough to pay for
         two small passes, attach the compact sigma array and refresh the hit marks (dead rows are never fetched)."""
         ts = self.tree._spec(features)
-        if n_rays * 32 >= features.shape[0] and features.is_cuda:
+        if n_rays * 32 >= features.shape[0] and features.is_cuda and features.dtype == torch.float32:
             ts._sigma = self.tree.sigma_table(features.detach())
             if ts._accel is not None:
                 ts._accel.mark_hits(features.detach())

@@ -403,6 +403,11 @@ class N3Tree(nn.Module):
         ts._weight_accum = self._weight_accum
         ts.joint_features, ts.skinning_weights, ts.joint_index = joint_features, skinning_weights, joint_index
         ts.transformation_matrices = transformation_matrices
+        if features is not None and features.dtype == torch.float64:
+            # float64 instantiation (the reference's AT_DISPATCH_FLOATING_TYPES): the general kernels walk child / data
+            # in double; offset / scaling are promoted, no accelerator or derived table is attached
+            ts.offset, ts.scaling = ts.offset.double(), ts.scaling.double()
+            return ts
         if _with_accel:
             ts._accel = self.accel(features)
         return ts

@@ -17,7 +17,9 @@ def test_header_declares_the_documented_entry_points():
     syms = declared_symbols()
     for must in ("svoxb_query", "svoxb_render_rays_fwd", "svoxb_render_rays_bwd", "svoxb_render_image_fwd",
                  "svoxb_render_image_bwd", "svoxb_render_depth", "svoxb_construct_tree", "svoxb_warp_vertices",
-                 "svoxb_p2v", "svoxb_build_octree_count", "svoxb_build_octree_emit", "svoxb_accel_create"):
+                 "svoxb_p2v", "svoxb_build_octree_count", "svoxb_build_octree_emit", "svoxb_accel_create",
+                 "svoxb_query_f64", "svoxb_render_rays_fwd_f64", "svoxb_render_rays_bwd_f64",
+                 "svoxb_render_image_fwd_f64", "svoxb_render_image_bwd_f64", "svoxb_render_depth_f64"):
         assert must in syms
 
 
@@ -26,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), f"{name} declared in include/svoxb.h but not exported by libsvoxb.so"
     assert sorted(C.SYMBOLS) == declared_symbols(), "python prototypes out of sync with include/svoxb.h"
-    assert lib.svoxb_abi_version() == 9
+    assert lib.svoxb_abi_version() == 10
 
 
 def test_struct_layouts_match_header():
@@ -41,7 +43,8 @@ def test_struct_layouts_match_header():
 def test_ctypes_structs_match_the_header_as_gcc_lays_it_out(tmp_path):
     """Compile include/svoxb.h with gcc and compare sizeof / offsetof of every struct field with the ctypes mirrors."""
     import subprocess
-    structs = {"svoxb_tree": C._CTree, "svoxb_render_options": C._COptions, "svoxb_camera": C._CCamera}
+    structs = {"svoxb_tree": C._CTree, "svoxb_render_options": C._COptions, "svoxb_camera": C._CCamera,
+               "svoxb_tree_f64": C._CTree64, "svoxb_camera_f64": C._CCamera64}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.abspath(HEADER)}"', "int main(void) {"]
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
@@ -64,4 +67,6 @@ def test_bad_arguments_return_error_codes_not_crashes():
     rc = lib.svoxb_render_rays_fwd(None, None, None, None, 0, None, None, None, None)
     assert rc == -1 and b"NULL" in lib.svoxb_last_error()
     assert lib.svoxb_accel_describe(None, None, None, None) == -1
+    assert lib.svoxb_render_rays_fwd_f64(None, None, None, 0, None, None, None, None) == -1
+    assert b"NULL" in lib.svoxb_last_error()
     assert lib.svoxb_launch_count() == 0 or lib.svoxb_launch_count() > 0

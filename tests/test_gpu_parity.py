@@ -180,7 +180,7 @@ def test_edge_cases(dev):
     bad.data_format = sv.DataFormat("SH9")
     with pytest.raises(RuntimeError):
         bad(feats, sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev)))
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError):       # float64 features with float32 rays: mixed types are an error, not a cast
         r(feats.double(), sv.Rays(cu(o, dev), cu(d, dev), cu(d, dev)))
 
 
