@@ -30,6 +30,7 @@ constexpr int MAXC = 31;      // view-dependent output channels: C + 1 (opacity)
 
 struct FmtArgs {
     int format, B, C, min_comp, max_comp, extra_cols;
+    int S;                    // row stride of the per-warp row stage in floats: D rounded up to an odd number
     const float* extra;       // SG [B,>=4]: (lambda, mu) ; ASG [B,>=11]: (a, b, x, y, z)
     const float* tm;          // [M,4,4] per-row view rotation or nullptr
 };
@@ -110,6 +111,63 @@ struct FmtSmem {
     float acc[32][MAXC + 2];   // forward: partial outputs; backward: staged grad_out row (C+1 values); odd stride
 };
 
+// Row stage of the view-dependent kernels: 32 rows of S floats per warp, behind the FmtSmem array. The hits of a warp's
+// lanes are 32 different rows; read lane-privately, every one of the D-1 coefficient loads of an iteration touches 32
+// different sectors (D-1 instructions x 32 L1 wavefronts). Instead the WARP fetches each hit row with one coalesced
+// load per 32 channels (G rows in flight) and parks it in shared memory, row r for lane r; the lane-private dot products
+// then read shared memory, conflict-free because S is odd. The backward sends its gradient rows out the same way.
+template <int K>
+__device__ __forceinline__ void stage_hit_rows(const float* __restrict__ features, int D, int S, unsigned hm, int hidx,
+                                               int lane, float* rb) {
+    constexpr int G = K == 1 ? 16 : (K == 2 ? 8 : 4);
+#pragma unroll
+    for (int g0 = 0; g0 < 32; g0 += G) {
+        const unsigned gm = (hm >> g0) & ((G == 32) ? FULL : ((1u << G) - 1u));
+        if (gm == 0u) continue;
+        float x[G][K];
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const int idx_r = __shfl_sync(FULL, hidx, g0 + i);      // 0 for lanes without a hit: never dereferenced
+            const float* rowp = features + (size_t)(unsigned)idx_r * D + lane;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                x[i][k] = (((gm >> i) & 1u) && lane + 32 * k < D - 1) ? __ldg(rowp + 32 * k) : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            if ((gm >> i) & 1u) {
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (lane + 32 * k < D - 1) rb[(g0 + i) * S + lane + 32 * k] = x[i][k];
+            }
+        }
+    }
+}
+
+// The gradient rows the lanes left in the stage (row r = lane r's hit) go out as coalesced reductions, row by row.
+template <int K>
+__device__ __forceinline__ void reduce_hit_rows(float* __restrict__ grad, int D, int S, unsigned hm, int hidx, int lane,
+                                                const float* rb) {
+    while (hm) {
+        const int r = __ffs(hm) - 1;
+        hm &= hm - 1;
+        const int idx_r = __shfl_sync(FULL, hidx, r);
+        float* grow = grad + (size_t)(unsigned)idx_r * D + lane;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (lane + 32 * k < D) {
+                const float v = rb[r * S + lane + 32 * k];
+                if (v != 0.0f) atomicAdd(grow + 32 * k, v);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float* fmt_row_stage(uint32_t* smem_after_top, int S) {
+    FmtSmem* warps = reinterpret_cast<FmtSmem*>(smem_after_top);
+    return reinterpret_cast<float*>(warps + WARPS) + (size_t)(threadIdx.x >> 5) * 32 * S;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 template <int K, bool ACCEL, bool IMAGE>
 __global__ void __launch_bounds__(BLOCK)
@@ -121,7 +179,8 @@ march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, floa
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31;
     FmtSmem& sm = reinterpret_cast<FmtSmem*>(smem_u32 + top_words)[threadIdx.x >> 5];
-    const int D = tr.D, B = fa.B, C = fa.C, Co = C + 1;
+    float* rb = fmt_row_stage(smem_u32 + top_words, fa.S);
+    const int D = tr.D, B = fa.B, C = fa.C, Co = C + 1, S = fa.S;
     const float* off = tr.offset;
     const float* scl = tr.scaling;
     for (int r = 0; r < 32; ++r) sm.acc[r][lane] = 0.0f;
@@ -171,18 +230,23 @@ march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, floa
         }
         __syncwarp();
 
-        // ---- phase B (rt_kernel.cu:293-301): every lane evaluates its own hit -- C dot products of length <= B against
-        // its ray's basis (shared memory, lane-private slot) -- and adds to its ray's partial outputs. The B*C
-        // coefficients of a row are contiguous, so the lane's loads walk one or two 128-byte lines that stay in L1.
-        if (hit) {
-            const float* rowp = tr.features + (size_t)(unsigned)hidx * D;
-            for (int t = 0; t < C; ++t) {
-                float tmp = 0.0f;
-                for (int i = fa.min_comp; i <= fa.max_comp; ++i) tmp += sm.basis[lane][i] * __ldg(rowp + t * B + i);
-                sm.acc[lane][t] = fmaf(w, fast_sigmoid(tmp), sm.acc[lane][t]);
+        // ---- phase B (rt_kernel.cu:293-301): the warp stages the hit rows (coalesced), then every lane evaluates its
+        // own hit -- C dot products of length <= B against its ray's basis (shared memory, lane-private slot) -- and adds
+        // to its ray's partial outputs.
+        const unsigned hm = __ballot_sync(FULL, hit);
+        if (hm) {
+            stage_hit_rows<K>(tr.features, D, S, hm, hidx, lane, rb);
+            __syncwarp();
+            if (hit) {
+                const float* rowp = rb + lane * S;
+                for (int t = 0; t < C; ++t) {
+                    float tmp = 0.0f;
+                    for (int i = fa.min_comp; i <= fa.max_comp; ++i) tmp += sm.basis[lane][i] * rowp[t * B + i];
+                    sm.acc[lane][t] = fmaf(w, fast_sigmoid(tmp), sm.acc[lane][t]);
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
 
         // ---- finished rays (rt_kernel.cu:313-326) -----------------------------------------------------------------
         unsigned fm = __ballot_sync(FULL, fin != 0);
@@ -222,7 +286,8 @@ march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, cons
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31;
     FmtSmem& sm = reinterpret_cast<FmtSmem*>(smem_u32 + top_words)[threadIdx.x >> 5];
-    const int D = tr.D, B = fa.B, C = fa.C, Co = C + 1;
+    float* rb = fmt_row_stage(smem_u32 + top_words, fa.S);
+    const int D = tr.D, B = fa.B, C = fa.C, Co = C + 1, S = fa.S;
     const float* off = tr.offset;
     const float* scl = tr.scaling;
 
@@ -291,25 +356,34 @@ march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, cons
         const bool fin = active && trav_done && p_idx < 0;
         __syncwarp();
 
-        // Every lane serves its own hit (lane-private basis / staged grad_out slots in shared memory): C dot products,
-        // the coefficient gradients w g_t s_t(1-s_t) basis_i need no row data and leave as they are found
-        // (rt_kernel.cu:403-417), then the sigma gradient (rt_kernel.cu:479-490).
-        if (hit) {
-            const float* rowp = tr.features + (size_t)(unsigned)hidx * D;
-            float* grow = grad + (size_t)(unsigned)hidx * D;
-            float c = 0.0f;
-            for (int t = 0; t < C; ++t) {
-                float tmp = 0.0f;
-                for (int i = fa.min_comp; i <= fa.max_comp; ++i) tmp += sm.basis[lane][i] * __ldg(rowp + t * B + i);
-                const float s = fast_sigmoid(tmp), gv = sm.acc[lane][t];
-                c = fmaf(s, gv, c);
-                const float gs = w * s * (1.0f - s) * gv;
-                for (int i = fa.min_comp; i <= fa.max_comp; ++i) atomicAdd(grow + t * B + i, gs * sm.basis[lane][i]);
+        // The warp stages the hit rows; every lane then serves its own hit (lane-private basis / staged grad_out slots in
+        // shared memory): C dot products, the coefficient gradients w g_t s_t(1-s_t) basis_i (rt_kernel.cu:403-417)
+        // overwrite the row's coefficients in the stage, the sigma gradient (rt_kernel.cu:479-490) its last slot; the
+        // finished gradient rows leave as coalesced reductions.
+        const unsigned hm = __ballot_sync(FULL, hit);
+        if (hm) {
+            stage_hit_rows<K>(tr.features, D, S, hm, hidx, lane, rb);
+            __syncwarp();
+            if (hit) {
+                float* rowp = rb + lane * S;
+                float c = 0.0f;
+                for (int t = 0; t < C; ++t) {
+                    float tmp = 0.0f;
+                    for (int i = fa.min_comp; i <= fa.max_comp; ++i) tmp += sm.basis[lane][i] * rowp[t * B + i];
+                    const float s = fast_sigmoid(tmp), gv = sm.acc[lane][t];
+                    c = fmaf(s, gv, c);
+                    const float gs = w * s * (1.0f - s) * gv;
+                    for (int i = 0; i < B; ++i)
+                        rowp[t * B + i] = (i >= fa.min_comp && i <= fa.max_comp) ? gs * sm.basis[lane][i] : 0.0f;
+                }
+                for (int j = C * B; j < D - 1; ++j) rowp[j] = 0.0f;      // channels past the last whole basis block
+                accum -= w * c;
+                rowp[D - 1] = dd * (c * T - accum) + dd * gop * T_end;
             }
-            accum -= w * c;
-            atomicAdd(grow + (D - 1), dd * (c * T - accum) + dd * gop * T_end);
+            __syncwarp();
+            reduce_hit_rows<K>(grad, D, S, hm, hidx, lane, rb);
+            __syncwarp();
         }
-        __syncwarp();
 
         const unsigned fm = __ballot_sync(FULL, fin);
         if (fm) {
@@ -1163,7 +1237,12 @@ static int make_fmt(const svoxb_tree* tree, const svoxb_render_options* opt, Fmt
                       "SG/ASG formats need extra_data [>=%d, >=%d]", B, need);
     }
     f.tm = tree->transformation_matrices;
+    f.S = D | 1;
     return 0;
+}
+
+static size_t fmt_smem_bytes(const TreeArgs& tr, const FmtArgs& f, bool accel) {
+    return (accel ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + (sizeof(FmtSmem) + sizeof(float) * 32 * f.S) * WARPS;
 }
 
 template <int K, bool ACCEL, bool IMAGE>
@@ -1171,7 +1250,7 @@ static int launch_fmt_fwd(const TreeArgs& tr_in, const RaySource& src, const Mar
                           cudaStream_t st) {
     TreeArgs tr = tr_in;
     if (m.sigma_thresh < 0.0f) tr.acc_miss_mask = 0;     // the marks encode sigma > 0: too strict for this predicate
-    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(FmtSmem) * WARPS;
+    const size_t smem = fmt_smem_bytes(tr, f, ACCEL);
     auto kern = march_fmt_fwd_kernel<K, ACCEL, IMAGE>;
     int grid = 0;
     int rc = persistent_grid(kern, smem, src.total, grid);
@@ -1186,7 +1265,7 @@ static int launch_fmt_fwd(const TreeArgs& tr_in, const RaySource& src, const Mar
 template <int K, bool ACCEL, bool IMAGE>
 static int launch_fmt_bwd(const TreeArgs& tr, const RaySource& src, const MarchOpts& m, const FmtArgs& f,
                           const float* go, const float* so, float* grad, cudaStream_t st) {
-    const size_t smem = (ACCEL ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(FmtSmem) * WARPS;
+    const size_t smem = fmt_smem_bytes(tr, f, ACCEL);
     auto kern = march_fmt_bwd_kernel<K, ACCEL, IMAGE>;
     int grid = 0;
     int rc = persistent_grid(kern, smem, src.total, grid);
