@@ -30,7 +30,8 @@ constexpr int MAXC = 31;      // view-dependent output channels: C + 1 (opacity)
 
 struct FmtArgs {
     int format, B, C, min_comp, max_comp, extra_cols;
-    int S;                    // row stride of the per-warp row stage in floats: D rounded up to an odd number
+    int S, SB, SC;            // odd row strides (floats) of the per-warp shared-memory tables: row stage (>= D), basis
+                              // (>= B), partial outputs / staged grad_out (>= C + 1)
     const float* extra;       // SG [B,>=4]: (lambda, mu) ; ASG [B,>=11]: (a, b, x, y, z)
     const float* tm;          // [M,4,4] per-row view rotation or nullptr
 };
@@ -105,49 +106,56 @@ __device__ __forceinline__ void eval_basis_rotated(const FmtArgs& f, int idx, co
     eval_basis(f, x, y, z, out);
 }
 
-// Shared memory per warp of the view-dependent kernels.
-struct FmtSmem {
-    float basis[32][MAXB];     // basis of each lane's ray (odd stride: conflict-free lane-per-ray writes)
-    float acc[32][MAXC + 2];   // forward: partial outputs; backward: staged grad_out row (C+1 values); odd stride
+// Shared memory per warp of the view-dependent kernels, sized for the format at hand (FmtArgs::SB / SC / S are odd row
+// strides, so lane-per-row accesses are conflict-free):
+//   basis[32][SB]  basis of each lane's ray (B values);
+//   acc[32][SC]    forward: partial outputs of each lane's ray; backward: the ray's staged grad_out row (C + 1 values);
+//   rows[32][S]    row stage: row r = the feature row of lane r's pending candidate, D values.
+// Row stage. The candidates of a warp's lanes are 32 different rows; read lane-privately, each of the D-1 coefficient
+// loads of an iteration would touch 32 different sectors (D-1 instructions x 32 L1 wavefronts -- what bounded the first
+// version of these kernels). Instead every lane copies ITS channel (+32k) of every candidate row with cp.async: coalesced
+// global reads that land in shared memory without passing through registers, in flight while the lanes traverse to their
+// next sample. The lane-private dot products then read shared memory. The backward overwrites each staged row with its
+// gradient row and sends those out the same way, as coalesced reductions.
+struct FmtWarp {
+    float* basis;
+    float* acc;
+    float* rows;
 };
 
-// Row stage of the view-dependent kernels: 32 rows of S floats per warp, behind the FmtSmem array. The hits of a warp's
-// lanes are 32 different rows; read lane-privately, every one of the D-1 coefficient loads of an iteration touches 32
-// different sectors (D-1 instructions x 32 L1 wavefronts). Instead the WARP fetches each hit row with one coalesced
-// load per 32 channels (G rows in flight) and parks it in shared memory, row r for lane r; the lane-private dot products
-// then read shared memory, conflict-free because S is odd. The backward sends its gradient rows out the same way.
+__device__ __forceinline__ FmtWarp fmt_warp(uint32_t* smem_after_top, const FmtArgs& fa) {
+    const int per_warp = 32 * (fa.SB + fa.SC + fa.S);
+    float* base = reinterpret_cast<float*>(smem_after_top) + (size_t)(threadIdx.x >> 5) * per_warp;
+    return FmtWarp{base, base + 32 * fa.SB, base + 32 * (fa.SB + fa.SC)};
+}
+
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Request the feature rows (all D channels, sigma included) of the lanes' candidates: row of lane r -> rows[r * S ...].
 template <int K>
-__device__ __forceinline__ void stage_hit_rows(const float* __restrict__ features, int D, int S, unsigned hm, int hidx,
-                                               int lane, float* rb) {
-    constexpr int G = K == 1 ? 16 : (K == 2 ? 8 : 4);
+__device__ __forceinline__ void stage_rows_async(const float* __restrict__ features, int D, int S, unsigned cm, int idx,
+                                                 int lane, float* rows) {
+    while (cm) {
+        const int r = __ffs(cm) - 1;
+        cm &= cm - 1;
+        const int idx_r = __shfl_sync(FULL, idx, r);
+        const float* src = features + (size_t)(unsigned)idx_r * D + lane;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(rows + r * S + lane);
 #pragma unroll
-    for (int g0 = 0; g0 < 32; g0 += G) {
-        const unsigned gm = (hm >> g0) & ((G == 32) ? FULL : ((1u << G) - 1u));
-        if (gm == 0u) continue;
-        float x[G][K];
-#pragma unroll
-        for (int i = 0; i < G; ++i) {
-            const int idx_r = __shfl_sync(FULL, hidx, g0 + i);      // 0 for lanes without a hit: never dereferenced
-            const float* rowp = features + (size_t)(unsigned)idx_r * D + lane;
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                x[i][k] = (((gm >> i) & 1u) && lane + 32 * k < D - 1) ? __ldg(rowp + 32 * k) : 0.0f;
-        }
-#pragma unroll
-        for (int i = 0; i < G; ++i) {
-            if ((gm >> i) & 1u) {
-#pragma unroll
-                for (int k = 0; k < K; ++k)
-                    if (lane + 32 * k < D - 1) rb[(g0 + i) * S + lane + 32 * k] = x[i][k];
-            }
-        }
+        for (int k = 0; k < K; ++k)
+            if (lane + 32 * k < D) cp_async4(dst + 128u * k, src + 32 * k);
     }
+    cp_async_commit();
 }
 
 // The gradient rows the lanes left in the stage (row r = lane r's hit) go out as coalesced reductions, row by row.
 template <int K>
 __device__ __forceinline__ void reduce_hit_rows(float* __restrict__ grad, int D, int S, unsigned hm, int hidx, int lane,
-                                                const float* rb) {
+                                                const float* rows) {
     while (hm) {
         const int r = __ffs(hm) - 1;
         hm &= hm - 1;
@@ -156,19 +164,35 @@ __device__ __forceinline__ void reduce_hit_rows(float* __restrict__ grad, int D,
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             if (lane + 32 * k < D) {
-                const float v = rb[r * S + lane + 32 * k];
+                const float v = rows[r * S + lane + 32 * k];
                 if (v != 0.0f) atomicAdd(grow + 32 * k, v);
             }
         }
     }
 }
 
-__device__ __forceinline__ float* fmt_row_stage(uint32_t* smem_after_top, int S) {
-    FmtSmem* warps = reinterpret_cast<FmtSmem*>(smem_after_top);
-    return reinterpret_cast<float*>(warps + WARPS) + (size_t)(threadIdx.x >> 5) * 32 * S;
+// One traversal step of the software pipeline shared by both kernels: advances the lane's ray by one sample and returns
+// the leaf row of that sample (or -1: empty leaf, or a row the hit marks flag as sigma <= 0) with its delta_t.
+template <bool ACCEL>
+__device__ __forceinline__ void fmt_next_sample(const TreeArgs& tr, const uint32_t* top, float step, bool active, Ray& ray,
+                                                bool& trav_done, int& n_idx, float& n_dt) {
+    n_idx = -1; n_dt = 0.0f;
+    if (active && !trav_done) {
+        if (!(ray.t < ray.tmax)) trav_done = true;
+        else {
+            Probe pb;
+            probe_begin<ACCEL>(tr, top, ray, pb);
+            probe_end<ACCEL>(tr, pb, ray, step, n_idx, n_dt);
+            ray.t += n_dt;
+            if (!(ray.t < ray.tmax)) trav_done = true;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Forward (rt_kernel.cu:261-326), software-pipelined: the rows of the PENDING candidates are requested (cp.async into the
+// stage), the lanes traverse to their next sample while the rows are in flight, then every lane composites its pending
+// sample: sigma from the staged row, C dot products of length <= B against its ray's basis (lane-private slot).
 template <int K, bool ACCEL, bool IMAGE>
 __global__ void __launch_bounds__(BLOCK)
 march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, float* __restrict__ out,
@@ -178,18 +202,20 @@ march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, floa
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31;
-    FmtSmem& sm = reinterpret_cast<FmtSmem*>(smem_u32 + top_words)[threadIdx.x >> 5];
-    float* rb = fmt_row_stage(smem_u32 + top_words, fa.S);
-    const int D = tr.D, B = fa.B, C = fa.C, Co = C + 1, S = fa.S;
+    const FmtWarp sm = fmt_warp(smem_u32 + top_words, fa);
+    const int D = tr.D, B = fa.B, C = fa.C, Co = C + 1, S = fa.S, SB = fa.SB, SC = fa.SC;
     const float* off = tr.offset;
     const float* scl = tr.scaling;
-    for (int r = 0; r < 32; ++r) sm.acc[r][lane] = 0.0f;
+    float* my_basis = sm.basis + lane * SB;
+    float* my_acc = sm.acc + lane * SC;
+    const float* my_row = sm.rows + lane * S;
+    for (int t = 0; t < C; ++t) my_acc[t] = 0.0f;
 
     Ray ray;
     ViewDir vd{0.f, 0.f, 0.f};
-    float T = 1.0f;
-    int row = 0;
-    bool active = false;
+    float T = 1.0f, p_dt = 0.0f;
+    int row = 0, p_idx = -1;
+    bool active = false, trav_done = true;
     Queue q{0, 0, false};
     unsigned need = FULL;
 
@@ -197,62 +223,44 @@ march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, floa
         if (need) {
             const unsigned got = refill<IMAGE, true>(src, off, scl, counter, q, need, lane, ray, row, &vd);
             if ((got >> lane) & 1u) {
-                active = true; T = 1.0f;
-                eval_basis(fa, vd.x, vd.y, vd.z, sm.basis[lane]);
+                active = true; trav_done = false; T = 1.0f; p_idx = -1;
+                eval_basis(fa, vd.x, vd.y, vd.z, my_basis);
             }
             need = 0;
         }
         if (__ballot_sync(FULL, active) == 0u) break;
 
-        // ---- phase A: one sample per lane (rt_kernel.cu:261-292) ------------------------------------------------
-        bool hit = false;
-        float w = 0.0f;
-        int hidx = 0, fin = 0;
-        if (active) {
-            if (!(ray.t < ray.tmax)) {
-                fin = 1;
-            } else {
-                int64_t idx; float delta_t, sigma;
-                sample<ACCEL>(tr, top, ray, opt.step, idx, delta_t, sigma);
-                // idx >= 0: an EMPTY leaf counts as sigma = 0 in the reference, which then dereferences a null row when the
-                // threshold is negative (rt_kernel.cu:278-304); here it is simply not a hit
-                if (idx >= 0 && sigma > opt.sigma_thresh) {
-                    const float att = expf(-delta_t * ray.ds * sigma);
-                    w = T * (1.0f - att);
-                    hit = true; hidx = (int)idx;
-                    if (fa.tm) eval_basis_rotated(fa, hidx, vd, sm.basis[lane]);
-                    T *= att;
-                    if (T <= opt.stop_thresh) fin = 2;
-                }
-                ray.t += delta_t;
-                if (fin == 0 && !(ray.t < ray.tmax)) fin = 1;
-            }
-        }
+        stage_rows_async<K>(tr.features, D, S, __ballot_sync(FULL, p_idx >= 0), p_idx, lane, sm.rows);
+        int n_idx; float n_dt;
+        fmt_next_sample<ACCEL>(tr, top, opt.step, active, ray, trav_done, n_idx, n_dt);
+        cp_async_wait_all();
         __syncwarp();
 
-        // ---- phase B (rt_kernel.cu:293-301): the warp stages the hit rows (coalesced), then every lane evaluates its
-        // own hit -- C dot products of length <= B against its ray's basis (shared memory, lane-private slot) -- and adds
-        // to its ray's partial outputs.
-        const unsigned hm = __ballot_sync(FULL, hit);
-        if (hm) {
-            stage_hit_rows<K>(tr.features, D, S, hm, hidx, lane, rb);
-            __syncwarp();
-            if (hit) {
-                const float* rowp = rb + lane * S;
-                for (int t = 0; t < C; ++t) {
+        int fin = 0;                  // 1 = the ray left the volume, 2 = stopped early (T <= stop_thresh)
+        if (p_idx >= 0) {
+            const float sigma = my_row[D - 1];
+            if (sigma > opt.sigma_thresh) {                                      // rt_kernel.cu:279
+                const float att = expf(-p_dt * ray.ds * sigma);
+                const float w = T * (1.0f - att);
+                if (fa.tm) eval_basis_rotated(fa, p_idx, vd, my_basis);         // rt_kernel.cu:283-291
+                for (int t = 0; t < C; ++t) {                                    // rt_kernel.cu:293-301
                     float tmp = 0.0f;
-                    for (int i = fa.min_comp; i <= fa.max_comp; ++i) tmp += sm.basis[lane][i] * rowp[t * B + i];
-                    sm.acc[lane][t] = fmaf(w, fast_sigmoid(tmp), sm.acc[lane][t]);
+                    for (int i = fa.min_comp; i <= fa.max_comp; ++i) tmp += my_basis[i] * my_row[t * B + i];
+                    my_acc[t] = fmaf(w, fast_sigmoid(tmp), my_acc[t]);
                 }
+                T *= att;
+                if (T <= opt.stop_thresh) fin = 2;
             }
-            __syncwarp();
         }
+        p_idx = n_idx; p_dt = n_dt;
+        if (fin == 0 && active && trav_done && p_idx < 0) fin = 1;
+        __syncwarp();
 
         // ---- finished rays (rt_kernel.cu:313-326) -----------------------------------------------------------------
         unsigned fm = __ballot_sync(FULL, fin != 0);
         if (fm) {
             need = fm;
-            if (fin != 0) active = false;
+            if (fin != 0) { active = false; p_idx = -1; }
             while (fm) {
                 const int r = __ffs(fm) - 1;
                 fm &= fm - 1;
@@ -262,10 +270,10 @@ march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, floa
                 if (lane < Co) {
                     float v;
                     if (lane == C) v = 1.0f - T_r;
-                    else if (fin_r == 2) v = sm.acc[r][lane] * (float)(1.0 / (1.0 - (double)T_r));
-                    else v = sm.acc[r][lane] + T_r * opt.bg;
+                    else if (fin_r == 2) v = sm.acc[r * SC + lane] * (float)(1.0 / (1.0 - (double)T_r));
+                    else v = sm.acc[r * SC + lane] + T_r * opt.bg;
                     out[(int64_t)row_r * Co + lane] = v;
-                    sm.acc[r][lane] = 0.0f;
+                    if (lane < C) sm.acc[r * SC + lane] = 0.0f;
                 }
             }
             __syncwarp();
@@ -273,9 +281,9 @@ march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, floa
     }
 }
 
-// Backward of the above: ONE re-march with accum = <g, out> from the saved forward output (see svoxb_render.cu).
-// With per-row rotations the basis is re-evaluated at every hit -- the reference's second pass keeps the basis of
-// the last hit of its first pass (rt_kernel.cu:446-494 never call maybe_precalc_basis), which is not the gradient.
+// Backward of the above: ONE re-march with accum = <g, out> from the saved forward output (see svoxb_render.cu), the same
+// pipeline. With per-row rotations the basis is re-evaluated at every hit -- the reference's second pass keeps the basis
+// of the last hit of its first pass (rt_kernel.cu:446-494 never call maybe_precalc_basis), which is not the gradient.
 template <int K, bool ACCEL, bool IMAGE>
 __global__ void __launch_bounds__(BLOCK)
 march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, const float* __restrict__ grad_out,
@@ -285,11 +293,13 @@ march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, cons
     const int top_words = ACCEL ? (1 << (3 * tr.acc.bits[0])) : 0;
     if (ACCEL) load_top(tr, top);
     const int lane = threadIdx.x & 31;
-    FmtSmem& sm = reinterpret_cast<FmtSmem*>(smem_u32 + top_words)[threadIdx.x >> 5];
-    float* rb = fmt_row_stage(smem_u32 + top_words, fa.S);
-    const int D = tr.D, B = fa.B, C = fa.C, Co = C + 1, S = fa.S;
+    const FmtWarp sm = fmt_warp(smem_u32 + top_words, fa);
+    const int D = tr.D, B = fa.B, C = fa.C, Co = C + 1, S = fa.S, SB = fa.SB, SC = fa.SC;
     const float* off = tr.offset;
     const float* scl = tr.scaling;
+    float* my_basis = sm.basis + lane * SB;
+    const float* my_g = sm.acc + lane * SC;
+    float* my_row = sm.rows + lane * S;
 
     Ray ray;
     ViewDir vd{0.f, 0.f, 0.f};
@@ -303,8 +313,8 @@ march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, cons
         if (need) {
             unsigned got = refill<IMAGE, true>(src, off, scl, counter, q, need, lane, ray, row, &vd);
             if ((got >> lane) & 1u) {
-                active = true; trav_done = false; T = 1.0f;
-                eval_basis(fa, vd.x, vd.y, vd.z, sm.basis[lane]);
+                active = true; trav_done = false; T = 1.0f; p_idx = -1;
+                eval_basis(fa, vd.x, vd.y, vd.z, my_basis);
             }
             need = 0;
             while (got) {       // per new ray: stage grad_out, accum = sum_{t<C} g_t out_t, T_end, g_opacity
@@ -315,7 +325,7 @@ march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, cons
                 if (lane < Co) {
                     gv = __ldg(grad_out + (int64_t)row_r * Co + lane);
                     ov = __ldg(saved_out + (int64_t)row_r * Co + lane);
-                    sm.acc[r][lane] = gv;
+                    sm.acc[r * SC + lane] = gv;
                 }
                 float part = lane < C ? gv * ov : 0.0f;
 #pragma unroll
@@ -327,63 +337,48 @@ march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, cons
         }
         if (__ballot_sync(FULL, active) == 0u) break;
 
-        // software-pipelined like the forward kernel: pending candidate, sigma requested ahead of the traversal step
-        const float sig = __ldg(tr.features + (size_t)(unsigned)max(p_idx, 0) * D + (D - 1));
-        int n_idx = -1;
-        float n_dt = 0.0f;
-        if (active && !trav_done) {
-            if (!(ray.t < ray.tmax)) trav_done = true;
-            else {
-                Probe pb;
-                probe_begin<ACCEL>(tr, top, ray, pb);
-                probe_end<ACCEL>(tr, pb, ray, opt.step, n_idx, n_dt);
-                ray.t += n_dt;
-                if (!(ray.t < ray.tmax)) trav_done = true;
+        stage_rows_async<K>(tr.features, D, S, __ballot_sync(FULL, p_idx >= 0), p_idx, lane, sm.rows);
+        int n_idx; float n_dt;
+        fmt_next_sample<ACCEL>(tr, top, opt.step, active, ray, trav_done, n_idx, n_dt);
+        cp_async_wait_all();
+        __syncwarp();
+
+        // Every lane serves its own pending sample: C dot products, the coefficient gradients w g_t s_t(1-s_t) basis_i
+        // (rt_kernel.cu:403-417) overwrite the row's coefficients in the stage, the sigma gradient (rt_kernel.cu:479-490)
+        // its last slot; the finished gradient rows leave as coalesced reductions.
+        bool hit = false;
+        const int hidx = max(p_idx, 0);
+        if (p_idx >= 0) {
+            const float sig = my_row[D - 1];
+            if (sig > 0.0f) {                                                    // rt_kernel.cu:382,456
+                const float att = expf(-p_dt * sig * ray.ds);
+                const float w = T * (1.0f - att), dd = p_dt * ray.ds;
+                hit = true;
+                if (fa.tm) eval_basis_rotated(fa, p_idx, vd, my_basis);
+                T *= att;
+                float c = 0.0f;
+                for (int t = 0; t < C; ++t) {
+                    float tmp = 0.0f;
+                    for (int i = fa.min_comp; i <= fa.max_comp; ++i) tmp += my_basis[i] * my_row[t * B + i];
+                    const float s = fast_sigmoid(tmp), gv = my_g[t];
+                    c = fmaf(s, gv, c);
+                    const float gs = w * s * (1.0f - s) * gv;
+                    for (int i = 0; i < B; ++i)
+                        my_row[t * B + i] = (i >= fa.min_comp && i <= fa.max_comp) ? gs * my_basis[i] : 0.0f;
+                }
+                for (int j = C * B; j < D - 1; ++j) my_row[j] = 0.0f;     // channels past the last whole basis block
+                accum -= w * c;
+                my_row[D - 1] = dd * (c * T - accum) + dd * gop * T_end;
             }
         }
-        bool hit = false;
-        float w = 0.0f, dd = 0.0f;
-        int hidx = 0;
-        if (p_idx >= 0 && sig > 0.0f) {                                          // rt_kernel.cu:382,456
-            const float att = expf(-p_dt * sig * ray.ds);
-            w = T * (1.0f - att);
-            dd = p_dt * ray.ds;
-            hit = true; hidx = p_idx;
-            if (fa.tm) eval_basis_rotated(fa, hidx, vd, sm.basis[lane]);
-            T *= att;
+        const unsigned hm = __ballot_sync(FULL, hit);
+        if (hm) {
+            __syncwarp();
+            reduce_hit_rows<K>(grad, D, S, hm, hidx, lane, sm.rows);
         }
         p_idx = n_idx; p_dt = n_dt;
         const bool fin = active && trav_done && p_idx < 0;
         __syncwarp();
-
-        // The warp stages the hit rows; every lane then serves its own hit (lane-private basis / staged grad_out slots in
-        // shared memory): C dot products, the coefficient gradients w g_t s_t(1-s_t) basis_i (rt_kernel.cu:403-417)
-        // overwrite the row's coefficients in the stage, the sigma gradient (rt_kernel.cu:479-490) its last slot; the
-        // finished gradient rows leave as coalesced reductions.
-        const unsigned hm = __ballot_sync(FULL, hit);
-        if (hm) {
-            stage_hit_rows<K>(tr.features, D, S, hm, hidx, lane, rb);
-            __syncwarp();
-            if (hit) {
-                float* rowp = rb + lane * S;
-                float c = 0.0f;
-                for (int t = 0; t < C; ++t) {
-                    float tmp = 0.0f;
-                    for (int i = fa.min_comp; i <= fa.max_comp; ++i) tmp += sm.basis[lane][i] * rowp[t * B + i];
-                    const float s = fast_sigmoid(tmp), gv = sm.acc[lane][t];
-                    c = fmaf(s, gv, c);
-                    const float gs = w * s * (1.0f - s) * gv;
-                    for (int i = 0; i < B; ++i)
-                        rowp[t * B + i] = (i >= fa.min_comp && i <= fa.max_comp) ? gs * sm.basis[lane][i] : 0.0f;
-                }
-                for (int j = C * B; j < D - 1; ++j) rowp[j] = 0.0f;      // channels past the last whole basis block
-                accum -= w * c;
-                rowp[D - 1] = dd * (c * T - accum) + dd * gop * T_end;
-            }
-            __syncwarp();
-            reduce_hit_rows<K>(grad, D, S, hm, hidx, lane, rb);
-            __syncwarp();
-        }
 
         const unsigned fm = __ballot_sync(FULL, fin);
         if (fm) {
@@ -1237,12 +1232,12 @@ static int make_fmt(const svoxb_tree* tree, const svoxb_render_options* opt, Fmt
                       "SG/ASG formats need extra_data [>=%d, >=%d]", B, need);
     }
     f.tm = tree->transformation_matrices;
-    f.S = D | 1;
+    f.S = D | 1; f.SB = B | 1; f.SC = (f.C + 1) | 1;
     return 0;
 }
 
 static size_t fmt_smem_bytes(const TreeArgs& tr, const FmtArgs& f, bool accel) {
-    return (accel ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + (sizeof(FmtSmem) + sizeof(float) * 32 * f.S) * WARPS;
+    return (accel ? sizeof(uint32_t) << (3 * tr.acc.bits[0]) : 0) + sizeof(float) * 32 * (f.S + f.SB + f.SC) * WARPS;
 }
 
 template <int K, bool ACCEL, bool IMAGE>
