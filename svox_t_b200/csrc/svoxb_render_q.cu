@@ -57,6 +57,10 @@ __device__ __forceinline__ void red_add_v4_hint(float* p, float a, float b, floa
     asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(a), "f"(b), "f"(c),
                  "f"(d), "l"(pol) : "memory");
 }
+// Empty-space step of the forward (see the kernel): 0 disables it.
+#ifndef SVOXB_EMPTY_STEP
+#define SVOXB_EMPTY_STEP 1
+#endif
 #ifndef SVOXB_ROWS_NO_L1
 #define SVOXB_ROWS_NO_L1 0
 #endif
@@ -251,6 +255,28 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
         }
         if (__ballot_sync(FULL, active) == 0u) break;
 
+        const unsigned pm = __ballot_sync(FULL, p_idx >= 0);
+        bool stopped = false;
+        int n_idx = -1;
+        float n_dt = 0.0f, n_t = 0.0f;
+        if (SVOXB_EMPTY_STEP && IMAGE && pm == 0u) {
+            // ---- empty space: no lane of the warp holds a pending candidate (the coherent rays of a pixel tile in front
+            // of / behind the object, sparse scenes): nothing to fetch and nothing to composite, the lanes only traverse.
+            // Camera rays only -- measured on B200: C5 1080p view 3.96 -> 3.82 ms, C4 1080p render 1.88 -> 1.85 ms; random
+            // ray batches never have 32 idle lanes at once and only pay for the test (C3 forward 2.87 -> 2.93 ms).
+            if (active && !trav_done) {
+                if (!(ray.t < ray.tmax)) trav_done = true;
+                else {
+                    Probe pb;
+                    probe_begin<ACCEL>(tr, top, ray, pb);
+                    if (DEPTH) n_t = ray.t;
+                    probe_end<ACCEL>(tr, pb, ray, opt.step, n_idx, n_dt);
+                    ray.t += n_dt;
+                    if constexpr (COUNT) ++steps;
+                    if (!(ray.t < ray.tmax)) trav_done = true;
+                }
+            }
+        } else {
         // ---- S0: request the rows of batch 0 of the pending candidates. First thing in the iteration (a load left
         // in flight across the loop back-edge is waited for at the loop header); unconditional on purpose (a guarded
         // load turns x into a phi whose register copies stall on the data); row 0 stands in for "no candidate".
@@ -273,10 +299,6 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
 
         if (trav) probe_mid<ACCEL>(tr, pb);
 
-        const unsigned pm = __ballot_sync(FULL, p_idx >= 0);
-        bool stopped = false;
-        int n_idx = -1;
-        float n_dt = 0.0f, n_t = 0.0f;
 #pragma unroll
         for (int b = 0; b < NBATCH; ++b) {
             // ---- S2.b: composite ---------------------------------------------------------------------------------
@@ -335,6 +357,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                 if (!(ray.t < ray.tmax)) trav_done = true;
             }
         }
+        }   // pm != 0
         if (stopped) { n_idx = -1; trav_done = true; }
         p_idx = n_idx; p_dt = n_dt; p_t = n_t;
         const int fin = (active && trav_done && p_idx < 0) ? (stopped ? 2 : 1) : 0;
