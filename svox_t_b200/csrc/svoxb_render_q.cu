@@ -57,6 +57,11 @@ __device__ __forceinline__ void red_add_v4_hint(float* p, float a, float b, floa
     asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(a), "f"(b), "f"(c),
                  "f"(d), "l"(pol) : "memory");
 }
+// Camera rays, forward: a warp takes 32 new pixels only when ALL its lanes have finished (the rays of a pixel tile stay in
+// step, so the empty-space step below is taken by whole warps); 0 = refill lane by lane like the explicit ray batches.
+#ifndef SVOXB_TILE_SYNC
+#define SVOXB_TILE_SYNC 1
+#endif
 // Empty-space step of the forward (see the kernel): 0 disables it.
 #ifndef SVOXB_EMPTY_STEP
 #define SVOXB_EMPTY_STEP 1
@@ -244,7 +249,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
     unsigned need = FULL;
 
     while (true) {
-        if (need) {
+        if (SVOXB_TILE_SYNC && IMAGE ? need == FULL : need != 0u) {
             const unsigned got = refill<IMAGE>(src, off, scl, counter, qu, need, lane, ray, row);
             if ((got >> lane) & 1u) {
                 active = true; trav_done = false; T = 1.0f; got_depth = false;
@@ -405,7 +410,7 @@ march_fwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, float* __restri
                 if constexpr (!AL) __stcs(out + (int64_t)row * D + (D - 1), 1.0f - T);   // opacity, by the owner lane
                 active = false;
             }
-            need = fm;
+            need |= fm;
         }
     }
 }
