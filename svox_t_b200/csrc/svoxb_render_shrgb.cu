@@ -15,6 +15,10 @@
 
 namespace svoxb {
 
+#ifndef SVOXB_TILE_SYNC
+#define SVOXB_TILE_SYNC 1
+#endif
+
 // L2 eviction priority of the gradient table (read-modify-written: a miss costs a DRAM read and a write-back), as in the
 // quad backward (svoxb_render_q.cu).
 __device__ __forceinline__ uint64_t sh_policy_evict_last() {
@@ -156,7 +160,9 @@ sh_rgb_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, float* _
     unsigned need = FULL;
 
     while (true) {
-        if (need) {
+        // Camera rays: a warp takes 32 new pixels only when ALL its lanes have finished -- the rays of a pixel tile then
+        // stay in step and whole warps skip the row stage while they cross empty space (as in svoxb_render_q.cu).
+        if (SVOXB_TILE_SYNC && IMAGE ? need == FULL : need != 0u) {
             const unsigned got = refill<IMAGE, true>(src, off, scl, counter, q, need, lane, ray, row, &vd);
             if ((got >> lane) & 1u) {
                 active = true; trav_done = false; T = 1.0f; a0 = a1 = a2 = 0.0f;
@@ -166,10 +172,12 @@ sh_rgb_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, float* _
         }
         if (__ballot_sync(FULL, active) == 0u) break;
 
-        // S0: row of the pending candidate (row 0 stands in for "none": unconditional loads)
+        // S0: row of the pending candidate (row 0 stands in for "none": unconditional loads, except that a camera-ray warp
+        // without any pending candidate -- empty space -- skips the stage)
         float v[D];
         SVOXB_DBG((int64_t)max(p_idx, 0) < max(tr.M, (int64_t)1));
-        load_row<B, VEC>(tr.features + (size_t)(unsigned)max(p_idx, 0) * D, v);
+        const bool rows_wanted = !(SVOXB_TILE_SYNC && IMAGE) || __ballot_sync(FULL, p_idx >= 0) != 0u;
+        if (rows_wanted) load_row<B, VEC>(tr.features + (size_t)(unsigned)max(p_idx, 0) * D, v);
         // S1: next sample, brick lookup issued
         bool trav = active && !trav_done;
         Probe pb;
@@ -179,7 +187,7 @@ sh_rgb_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, float* _
         }
         // S2: composite the pending candidate
         bool stopped = false;
-        if (p_idx >= 0 && v[D - 1] > opt.sigma_thresh) {                              // rt_kernel.cu:279-320
+        if (rows_wanted && p_idx >= 0 && v[D - 1] > opt.sigma_thresh) {                // rt_kernel.cu:279-320
             float tmp[3];
             const float att = expf(-p_dt * ray.ds * v[D - 1]);
             const float w = T * (1.0f - att);
@@ -214,7 +222,7 @@ sh_rgb_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, ShArgs sa, float* _
             __stcs(reinterpret_cast<float4*>(out) + row, o);
             active = false;
         }
-        need = __ballot_sync(FULL, fin != 0);
+        need |= __ballot_sync(FULL, fin != 0);
     }
 }
 
