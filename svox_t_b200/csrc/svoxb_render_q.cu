@@ -62,6 +62,9 @@ __device__ __forceinline__ void red_add_v4_hint(float* p, float a, float b, floa
 #ifndef SVOXB_TILE_SYNC
 #define SVOXB_TILE_SYNC 1
 #endif
+#ifndef SVOXB_TILE_SYNC_BWD
+#define SVOXB_TILE_SYNC_BWD 1
+#endif
 // Empty-space step of the forward (see the kernel): 0 disables it.
 #ifndef SVOXB_EMPTY_STEP
 #define SVOXB_EMPTY_STEP 1
@@ -462,7 +465,7 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
     unsigned need = FULL;
 
     while (true) {
-        if (need) {
+        if (SVOXB_TILE_SYNC_BWD && IMAGE ? need == FULL : need != 0u) {      // camera rays: whole tiles, as in the forward
             unsigned got = refill<IMAGE>(src, off, scl, counter, qu, need, lane, ray, row);
             if ((got >> lane) & 1u) { active = true; trav_done = false; T = 1.0f; }
             need = 0;
@@ -498,6 +501,22 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
         }
         if (__ballot_sync(FULL, active) == 0u) break;
 
+        const unsigned pm = __ballot_sync(FULL, p_idx >= 0);
+        int n_idx = -1;
+        float n_dt = 0.0f;
+        if (SVOXB_TILE_SYNC_BWD && IMAGE && pm == 0u) {
+            // ---- empty space (camera rays; see the forward): the lanes only traverse
+            if (active && !trav_done) {
+                if (!(ray.t < ray.tmax)) trav_done = true;
+                else {
+                    Probe pb;
+                    probe_begin<ACCEL>(tr, top, ray, pb);
+                    probe_end<ACCEL>(tr, pb, ray, opt.step, n_idx, n_dt);
+                    ray.t += n_dt;
+                    if (!(ray.t < ray.tmax)) trav_done = true;
+                }
+            }
+        } else {
         // ---- S0: rows of batch 0 of the pending candidates (see the forward kernel) ---------------------------------
 #pragma unroll
         for (int jj = 0; jj < NB; ++jj) {
@@ -518,9 +537,6 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
 
         if (trav) probe_mid<ACCEL>(tr, pb);
 
-        const unsigned pm = __ballot_sync(FULL, p_idx >= 0);
-        int n_idx = -1;
-        float n_dt = 0.0f;
 #pragma unroll
         for (int b = 0; b < NBATCH; ++b) {
             // ---- S2.b: gradient of batch b of the pending candidates ------------------------------------------------
@@ -613,13 +629,14 @@ march_bwd_quad_kernel(TreeArgs tr, RaySource src, MarchOpts opt, const float* __
                 if (!(ray.t < ray.tmax)) trav_done = true;
             }
         }
+        }   // pm != 0
         p_idx = n_idx; p_dt = n_dt;
         const bool fin = active && trav_done && p_idx < 0;
 
         const unsigned fm = __ballot_sync(FULL, fin);
         if (fm) {
             if (fin) active = false;
-            need = fm;
+            need |= fm;
         }
     }
 }
