@@ -143,6 +143,7 @@ __device__ __forceinline__ void stage_rows_async(const float* __restrict__ featu
         const int r = __ffs(cm) - 1;
         cm &= cm - 1;
         const int idx_r = __shfl_sync(FULL, idx, r);
+        SVOXB_DBG(idx_r >= 0 && S >= D);
         const float* src = features + (size_t)(unsigned)idx_r * D + lane;
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(rows + r * S + lane);
 #pragma unroll
@@ -237,6 +238,7 @@ march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, floa
         __syncwarp();
 
         int fin = 0;                  // 1 = the ray left the volume, 2 = stopped early (T <= stop_thresh)
+        SVOXB_DBG(p_idx < 0 || (int64_t)p_idx < tr.M);
         if (p_idx >= 0) {
             const float sigma = my_row[D - 1];
             if (sigma > opt.sigma_thresh) {                                      // rt_kernel.cu:279
@@ -348,6 +350,7 @@ march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, cons
         // its last slot; the finished gradient rows leave as coalesced reductions.
         bool hit = false;
         const int hidx = max(p_idx, 0);
+        SVOXB_DBG(p_idx < 0 || (int64_t)p_idx < tr.M);
         if (p_idx >= 0) {
             const float sig = my_row[D - 1];
             if (sig > 0.0f) {                                                    // rt_kernel.cu:382,456

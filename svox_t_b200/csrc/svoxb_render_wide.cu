@@ -162,6 +162,7 @@ __device__ __forceinline__ void g_sample(const GTree<R>& tr, const GRay<R>& r, R
     const R px = g_fma(r.t, r.dx, r.ox), py = g_fma(r.t, r.dy, r.oy), pz = g_fma(r.t, r.dz, r.oz);
     R rx, ry, rz, cube, smin, smax;
     const int64_t slot = g_descend(tr.child, tr.N, px, py, pz, rx, ry, rz, cube);
+    SVOXB_DBG(slot >= 0);
     const int di = __ldg(tr.data + slot);
     idx = ((int64_t)di >= tr.M || di < 0) ? -1 : di;
     g_dda(rx, ry, rz, r.ix, r.iy, r.iz, smin, smax);
@@ -225,6 +226,7 @@ wide_fwd_kernel(GTree<R> tr, GSource<R> src, GOpts<R> opt, R* out, R* depth) {
                 hm &= hm - 1;
                 const int idx_r = __shfl_sync(FULL, hidx, r);
                 const R w_r = __shfl_sync(FULL, w, r);
+                SVOXB_DBG(idx_r >= 0 && (int64_t)idx_r < tr.M && base + r < src.total);
                 const R* f = tr.features + (int64_t)idx_r * D;
                 R* o = out + (base + r) * D;
                 for (int c = lane; c < D - 1; c += 32) o[c] = g_fma(w_r, g_sigmoid(__ldg(f + c)), o[c]);
@@ -303,6 +305,7 @@ wide_bwd_kernel(GTree<R> tr, GSource<R> src, GOpts<R> opt, const R* __restrict__
                 const int idx_r = __shfl_sync(FULL, hidx, r);
                 const R w_r = __shfl_sync(FULL, w, r);
                 const R* f = tr.features + (int64_t)idx_r * D;
+                SVOXB_DBG(idx_r >= 0 && (int64_t)idx_r < tr.M && base + r < src.total);
                 const R* g = grad_out + (base + r) * D;
                 R* grow = grad + (int64_t)idx_r * D;
                 R cp = (R)0;

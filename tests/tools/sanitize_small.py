@@ -72,5 +72,17 @@ cam = C.CameraSpec(); cam.c2w = torch.from_numpy(synth.synth_cameras(1)[0]).to(d
 C.grid_weight_render(torch.rand(17, 17, 17, device=dev) * 9 - 3, cam, r._get_options(), torch.zeros(3, device=dev), torch.ones(3, device=dev))
 with tree.accumulate_weights() as acc:
     r(feats, rays); r.render_persp(feats, torch.from_numpy(synth.synth_cameras(1)[0]).to(dev), width=29, height=19, fx=25.0)
+# general kernels: feature rows wider than 128 channels (float32) and the float64 instantiation
+for D, dt in ((150, torch.float32), (9, torch.float64), (131, torch.float64)):
+    tw = sv.N3Tree.from_tensors(tr["child"], tr["data"], tr["parent_depth"], data_dim=D, map_location=dev)
+    fw = torch.randn(M, D, device=dev, dtype=dt, requires_grad=True)
+    rw = sv.Rays(*(t.to(dt) for t in rays))
+    rr = sv.VolumeRenderer(tw)
+    ow, dw = rr.forward_with_depth(fw, rw)
+    ow.sum().backward()
+    rr.render_depth(fw.detach(), rw)
+    camw = torch.from_numpy(synth.synth_cameras(1)[0]).to(dev).to(dt)
+    rr.render_persp(fw, camw, width=29, height=19, fx=25.0, rows=(8, 19)).sum().backward()
+    tw(fw.detach(), torch.rand(500, 3, device=dev, dtype=dt) * 1.2 - 0.1, want_node_ids=True, want_leaf_node=True)
 torch.cuda.synchronize()
 print("sanitize_small done, launches", C.launch_count())
