@@ -223,8 +223,9 @@ SVOXB_API int svoxb_render_rays_fwd(const svoxb_tree* tree, const float* origins
  * Widths and types (stated once for every march entry point): the RGBA format takes any D >= 2, like the reference's
  * loop over out_data_dim (rt_kernel.cu:302-306) -- D <= 128 runs on the tuned register / shared-memory kernels, wider
  * tables on the general kernels of svoxb_render_wide.cu (no accelerator, no NDC; same results, several times slower per
- * byte). These entry points are float32; the reference's float64 instantiation (AT_DISPATCH_FLOATING_TYPES,
- * rt_kernel.cu:1373) is the *_f64 family at the end of this header. */
+ * byte). The view-dependent formats (SH / SG / ASG) take D <= 128 with at most 31 output channels and basis_dim <= 25
+ * (SVOXB_EINVAL beyond). These entry points are float32; the reference's float64 instantiation
+ * (AT_DISPATCH_FLOATING_TYPES, rt_kernel.cu:1373) is the *_f64 family at the end of this header. */
 SVOXB_API int svoxb_render_rays_bwd(const svoxb_tree* tree, const float* origins, const float* dirs, const float* vdirs,
                           int64_t Q, const svoxb_render_options* opt, const float* grad_out, const float* saved_out,
                           float* grad_features, void* stream);
