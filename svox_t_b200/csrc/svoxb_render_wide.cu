@@ -20,8 +20,6 @@
 
 namespace svoxb {
 
-int make_tree_args(const svoxb_tree* t, TreeArgs& a, void* use_stream);   // svoxb_tree.cu
-
 template <typename R>
 struct GTree {
     const R* features;
@@ -389,16 +387,16 @@ static GOpts<R> g_opts(const svoxb_render_options* o) {
     return GOpts<R>{(R)o->step_size, (R)o->background_brightness, (R)o->sigma_thresh, (R)o->stop_thresh};
 }
 
-static int g_grid(int64_t total, bool warp_per_32) {
-    const int64_t per_block = warp_per_32 ? WIDE_BLOCK : WIDE_BLOCK;
-    const int64_t want = (total + per_block - 1) / per_block;
+// One ray (point) per thread and round; grid-stride beyond 16 CTAs per SM.
+static int g_grid(int64_t total) {
+    const int64_t want = (total + WIDE_BLOCK - 1) / WIDE_BLOCK;
     return (int)max((int64_t)1, min(want, (int64_t)sm_count() * 16));
 }
 
 template <typename R>
 static int g_launch_fwd(const GTree<R>& tr, const GSource<R>& src, const GOpts<R>& m, bool image, R* out, R* depth,
                         cudaStream_t st) {
-    const int grid = g_grid(src.total, true);
+    const int grid = g_grid(src.total);
     if (image) wide_fwd_kernel<R, true><<<grid, WIDE_BLOCK, 0, st>>>(tr, src, m, out, depth);
     else wide_fwd_kernel<R, false><<<grid, WIDE_BLOCK, 0, st>>>(tr, src, m, out, depth);
     count_launch();
@@ -408,7 +406,7 @@ static int g_launch_fwd(const GTree<R>& tr, const GSource<R>& src, const GOpts<R
 template <typename R>
 static int g_launch_bwd(const GTree<R>& tr, const GSource<R>& src, const GOpts<R>& m, bool image, const R* go,
                         const R* so, R* grad, cudaStream_t st) {
-    const int grid = g_grid(src.total, true);
+    const int grid = g_grid(src.total);
     if (image) wide_bwd_kernel<R, true><<<grid, WIDE_BLOCK, 0, st>>>(tr, src, m, go, so, grad);
     else wide_bwd_kernel<R, false><<<grid, WIDE_BLOCK, 0, st>>>(tr, src, m, go, so, grad);
     count_launch();
@@ -490,7 +488,7 @@ extern "C" int svoxb_query_f64(const svoxb_tree_f64* tree, const double* pts, in
     int rc = g_tree_f64(tree, tr); if (rc) return rc;
     SVOXB_REQUIRE(Q >= 0 && (Q == 0 || (pts && node_ids)), "pts/node_ids NULL");
     if (Q == 0) return 0;
-    wide_query_kernel<double><<<g_grid(Q, true), WIDE_BLOCK, 0, (cudaStream_t)stream>>>(tr, pts, Q, values, node_ids,
+    wide_query_kernel<double><<<g_grid(Q), WIDE_BLOCK, 0, (cudaStream_t)stream>>>(tr, pts, Q, values, node_ids,
                                                                                         data_ids, slot_mask);
     count_launch();
     return check_cuda(cudaGetLastError(), "wide_query_kernel launch");
@@ -551,7 +549,7 @@ extern "C" int svoxb_render_depth_f64(const svoxb_tree_f64* tree, const double* 
     rc = g_rays_f64(origins, dirs, Q, src); if (rc) return rc;
     SVOXB_REQUIRE(Q == 0 || depth != nullptr, "depth is NULL");
     if (Q == 0) return 0;
-    wide_depth_kernel<double><<<g_grid(Q, false), WIDE_BLOCK, 0, (cudaStream_t)stream>>>(tr, src, g_opts<double>(opt), depth);
+    wide_depth_kernel<double><<<g_grid(Q), WIDE_BLOCK, 0, (cudaStream_t)stream>>>(tr, src, g_opts<double>(opt), depth);
     count_launch();
     return check_cuda(cudaGetLastError(), "wide_depth_kernel launch");
 }
