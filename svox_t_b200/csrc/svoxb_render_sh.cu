@@ -25,6 +25,9 @@
 
 namespace svoxb {
 
+#ifndef SVOXB_TILE_SYNC
+#define SVOXB_TILE_SYNC 1
+#endif
 constexpr int MAXB = 25;      // basis functions per channel (SH degree 4)
 constexpr int MAXC = 31;      // view-dependent output channels: C + 1 (opacity) values per ray are served by one warp
 
@@ -221,7 +224,7 @@ march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, floa
     unsigned need = FULL;
 
     while (true) {
-        if (need) {
+        if (SVOXB_TILE_SYNC && IMAGE ? need == FULL : need != 0u) {   // camera rays: whole tiles (svoxb_render_q.cu)
             const unsigned got = refill<IMAGE, true>(src, off, scl, counter, q, need, lane, ray, row, &vd);
             if ((got >> lane) & 1u) {
                 active = true; trav_done = false; T = 1.0f; p_idx = -1;
@@ -261,7 +264,7 @@ march_fmt_fwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, floa
         // ---- finished rays (rt_kernel.cu:313-326) -----------------------------------------------------------------
         unsigned fm = __ballot_sync(FULL, fin != 0);
         if (fm) {
-            need = fm;
+            need |= fm;
             if (fin != 0) { active = false; p_idx = -1; }
             while (fm) {
                 const int r = __ffs(fm) - 1;
@@ -312,7 +315,7 @@ march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, cons
     unsigned need = FULL;
 
     while (true) {
-        if (need) {
+        if (SVOXB_TILE_SYNC && IMAGE ? need == FULL : need != 0u) {   // camera rays: whole tiles (svoxb_render_q.cu)
             unsigned got = refill<IMAGE, true>(src, off, scl, counter, q, need, lane, ray, row, &vd);
             if ((got >> lane) & 1u) {
                 active = true; trav_done = false; T = 1.0f; p_idx = -1;
@@ -386,7 +389,7 @@ march_fmt_bwd_kernel(TreeArgs tr, RaySource src, MarchOpts opt, FmtArgs fa, cons
         const unsigned fm = __ballot_sync(FULL, fin);
         if (fm) {
             if (fin) active = false;
-            need = fm;
+            need |= fm;
         }
     }
 }
