@@ -578,15 +578,18 @@ def _order_range():
     return _ORDER_RANGE
 
 
-def _require_rgba_f64(opt):
+def _require_rgba_f64(opt, tree=None):
     if int(opt.format) != FORMAT_RGBA:
         raise RuntimeError("svox_t_b200.csrc: float64 is implemented for the RGBA format only (view-dependent formats "
                            "are float32)")
+    wa = getattr(tree, "_weight_accum", None)
+    if wa is not None and wa.numel():
+        raise RuntimeError("svox_t_b200.csrc: accumulate_weights is float32 only")
 
 
 def _render_fwd_f64(tree, rays, opt, want_depth, c_opt=None):
     lib = load_library()
-    _require_rgba_f64(opt)
+    _require_rgba_f64(opt, tree)
     rays.check(torch.float64)
     ct = tree._c64()
     Q, D = rays.origins.shape[0], tree.features.shape[1]
@@ -707,7 +710,7 @@ def volume_render_backward(tree, rays, opt, grad_output, saved_out=None):
 
 def _render_image_fwd_f64(tree, cam, opt, want_depth, c_opt=None):
     lib = load_library()
-    _require_rgba_f64(opt)
+    _require_rgba_f64(opt, tree)
     ct, cc = tree._c64(), cam._c64()
     dev = tree.features.device
     D = tree.features.shape[1]
