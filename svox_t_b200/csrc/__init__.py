@@ -659,6 +659,8 @@ def volume_render_backward(tree, rays, opt, grad_output, saved_out=None):
     lib = load_library()
     if tree.is_f64:
         _require_rgba_f64(opt)
+        if getattr(tree, "_grad_exchange", None) is not None:
+            raise RuntimeError("svox_t_b200.csrc: the multi-GPU leaf-gradient exchange is float32 only")
         rays.check(torch.float64)
         _check_input(grad_output, "grad_output", torch.float64)
         ct = tree._c64()
