@@ -4,6 +4,8 @@ import os
 import re
 
 import numpy as np
+import ctypes
+
 import pytest
 import torch
 
@@ -105,6 +107,30 @@ def test_no_cpu_fallback_anywhere():
         t(t.features, torch.rand(3, 3))
     with pytest.raises(RuntimeError):
         sv.csrc.volume_render(t._spec(t.features), sv.renderer._rays_spec_from_rays(rays), r._get_options())
+
+
+def test_float64_specs_dispatch_and_refuse_cpu_tensors():
+    """A double feature table selects the float64 instantiation (promoted offset / scaling, no accelerator or derived
+    tables); like every other path it refuses CPU tensors instead of falling back."""
+    t = sv.N3Tree(data_dim=8, init_refine=1)
+    f64 = t.features.detach().double()
+    ts = t._spec(f64)
+    assert ts.is_f64 and ts.offset.dtype == torch.float64 and ts.scaling.dtype == torch.float64 and ts._accel is None
+    assert not t._spec(t.features, _with_accel=False).is_f64
+    assert torch.equal(ts.offset, t.offset.double())
+    rays = sv.renderer._rays_spec_from_rays(sv.Rays(torch.zeros(4, 3).double(), torch.ones(4, 3).double(),
+                                                    torch.ones(4, 3).double()))
+    opt = sv.VolumeRenderer(t)._get_options()
+    for call in (lambda: sv.csrc.volume_render(ts, rays, opt),
+                 lambda: sv.csrc.render_depth(ts, rays, opt),
+                 lambda: sv.csrc.volume_render_backward(ts, rays, opt, torch.zeros(4, 8).double()),
+                 lambda: sv.csrc.query_vertical(ts, torch.rand(3, 3).double())):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            call()
+    opt.format = sv.csrc.FORMAT_SH                               # view-dependent formats are float32 only
+    with pytest.raises(RuntimeError, match="RGBA"):
+        sv.csrc.volume_render(ts, rays, opt)
+    assert ctypes.sizeof(sv.csrc._CTree64) == 72 and ctypes.sizeof(sv.csrc._CCamera64) == 40
 
 
 def test_drop_in_alias_package():
