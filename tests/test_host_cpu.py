@@ -1,11 +1,10 @@
 """CPU tests of the host logic: N3Tree structure ops, spec packing, options, persistence, and that the product
 path FAILS LOUDLY (no CPU fallback, no oracle behind the API) when there is no CUDA device."""
+import ctypes
 import os
 import re
 
 import numpy as np
-import ctypes
-
 import pytest
 import torch
 
