@@ -26,6 +26,7 @@ namespace svoxb {
 
 constexpr int ORD_BINS = 1024;
 constexpr int ORD_THREADS = 256;
+constexpr int ORD_ITEMS = 4;          // rays per thread and tile of the scatter
 
 // Histogram of the per-ray costs (the forward's exact iteration counts).
 __global__ void __launch_bounds__(ORD_THREADS)
@@ -70,9 +71,35 @@ ray_order_scatter_kernel(const int* __restrict__ cost, int Q, const unsigned* __
         for (int r = blockIdx.x * ORD_THREADS + threadIdx.x; r < Q; r += gridDim.x * ORD_THREADS) order[r] = r;
         return;
     }
-    for (int r = blockIdx.x * ORD_THREADS + threadIdx.x; r < Q; r += gridDim.x * ORD_THREADS) {
-        const int key = max(0, min(ORD_BINS - 1, __ldg(cost + r)));
-        order[base[key] + atomicAdd(cursor + key, 1u)] = r;
+    // Tiles of ORD_THREADS * ORD_ITEMS rays: ranks inside the tile from shared-memory counters, then ONE global
+    // reservation per occupied bin of the tile. (A global atomic per ray lands on the ~200 distinct step counts of a
+    // batch: 0.21 ms for 2^20 rays, as much as the table pass of the whole step.)
+    __shared__ unsigned lcount[ORD_BINS];
+    constexpr int TILE = ORD_THREADS * ORD_ITEMS;
+    for (int t0 = blockIdx.x * TILE; t0 < Q; t0 += gridDim.x * TILE) {
+        for (int b = threadIdx.x; b < ORD_BINS; b += ORD_THREADS) lcount[b] = 0;
+        __syncthreads();
+        int key[ORD_ITEMS];
+        unsigned rank[ORD_ITEMS];
+#pragma unroll
+        for (int j = 0; j < ORD_ITEMS; ++j) {
+            const int r = t0 + j * ORD_THREADS + threadIdx.x;
+            key[j] = -1;
+            if (r < Q) {
+                key[j] = max(0, min(ORD_BINS - 1, __ldg(cost + r)));
+                rank[j] = atomicAdd(&lcount[key[j]], 1u);
+            }
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < ORD_BINS; b += ORD_THREADS) {
+            const unsigned n = lcount[b];
+            if (n) lcount[b] = base[b] + atomicAdd(cursor + b, n);      // first position of the tile's rays of bin b
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ORD_ITEMS; ++j)
+            if (key[j] >= 0) order[lcount[key[j]] + rank[j]] = t0 + j * ORD_THREADS + threadIdx.x;
+        __syncthreads();
     }
 }
 
@@ -103,7 +130,8 @@ int build_ray_order(const int* cost, int64_t Q, int** order, cudaStream_t st) {
     if (e == cudaSuccess) {
         const int grid = (int)min((Q + ORD_THREADS - 1) / ORD_THREADS, (int64_t)sm_count() * 8);
         ray_hist_kernel<<<grid, ORD_THREADS, 0, st>>>(cost, (int)Q, hist);
-        ray_order_scatter_kernel<<<grid, ORD_THREADS, 0, st>>>(cost, (int)Q, hist, hist + ORD_BINS, ord);
+        const int sgrid = (int)min((Q + ORD_THREADS * ORD_ITEMS - 1) / (ORD_THREADS * ORD_ITEMS), (int64_t)sm_count() * 8);
+        ray_order_scatter_kernel<<<sgrid, ORD_THREADS, 0, st>>>(cost, (int)Q, hist, hist + ORD_BINS, ord);
         count_launch(2);
         e = cudaGetLastError();
     }
