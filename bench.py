@@ -520,7 +520,11 @@ def main():
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": roof(b_bwd, bwd_ms, "svoxb::march_bwd_quad_kernel", "march_bwd_quad_kernel"),
+        "roofline": dict(roof(b_bwd, bwd_ms, "svoxb::march_bwd_quad_kernel", "march_bwd_quad_kernel"),
+                         note="SURVEY 8(d) bytes: they charge the reference's per-level child lookups (4 LV) and the rows of "
+                              "dead leaves, neither of which this design loads, and the L2 serves about half of the row "
+                              "traffic (see `traffic`: measured DRAM bytes per launch) -- so `frac` can exceed 1; "
+                              "`roofline_design` has the bytes this design moves"),
         "roofline_fwd": roof(b_fwd, fwd_ms, "svoxb::march_fwd_quad_kernel", "march_fwd_quad_kernel"),
         "roofline_design": {"bwd": roof(bd_bwd, bwd_ms, "svoxb::march_bwd_quad_kernel"),
                             "fwd": roof(bd_fwd, fwd_ms, "svoxb::march_fwd_quad_kernel"),
