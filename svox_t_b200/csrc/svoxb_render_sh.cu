@@ -11,11 +11,15 @@
 //
 // Same skeleton as the scalar-lane RGBA kernels (svoxb_render.cu): persistent warps, lane = ray for the traversal,
 // finished lanes refilled from the global queue. What differs is the per-hit arithmetic:
-//   view-dependent : LANE-private -- the owner lane evaluates its hit against its ray's basis (a 25-float slot in shared
-//                    memory, re-evaluated per hit when per-row rotations are given): C dot products of length <= B over
-//                    the row's contiguous coefficients, in the reference's order; the coefficient gradients
-//                    w g_t s_t(1-s_t) basis_i need no row data. (A first, warp-cooperative version that served the
-//                    32 hits of an iteration one after another was slower than the reference's thread-per-ray code.)
+//   view-dependent : LANE-private arithmetic over a warp-cooperative ROW STAGE -- the rows of the lanes' pending candidates
+//                    are copied into shared memory with cp.async (coalesced; in flight during the traversal of the next
+//                    sample), then the owner lane evaluates its hit against its ray's basis (a lane-private slot in
+//                    shared memory, re-evaluated per hit when per-row rotations are given): C dot products of length
+//                    <= B over the row's coefficients, in the reference's order; the backward writes its gradient row
+//                    (w g_t s_t(1-s_t) basis_i, sigma gradient last) over the staged row and the warp reduces the rows
+//                    out coalesced. (Lane-private global reads of the rows cost D-1 load instructions x 32 L1 wavefronts
+//                    per iteration: 2.6x slower. A first, fully warp-cooperative version that served the 32 hits of an
+//                    iteration one after another was slower than the reference's thread-per-ray code.)
 //                    SH rows with three output channels take the register-only kernels of svoxb_render_shrgb.cu.
 //   motion feature : lane k < F accumulates sum_j w_j * JF[joint_j][k] (the joint table is a few KB, L1-resident);
 //                    the backward reduces dL/dJF in a per-CTA shared-memory table (J x F addresses receive every
